@@ -1,0 +1,185 @@
+/* marian_b200.h — C ABI of the B200-native hot path of Marian (v1.2.1 fork
+ * tneck/marian-nmt-distributed).
+ *
+ * The reference has no plugin/FFI boundary: its drop-in boundary is the set of
+ * C++ free functions on marian::Tensor declared in
+ *   /root/reference/src/kernels/tensor_operators.h:19-397  (+ kernels/dropout.h:10-12)
+ * which the graph nodes (src/graph/node_operators_*.h), optimizers
+ * (src/optimizers/*.cu) and graph groups (src/training/graph_group_*.cu) call.
+ * The C++ side of that boundary is kept source-compatible in
+ *   marian-nmt-distributed_b200/csrc/kernels/tensor_operators.h
+ * This header is the flat C view of the SAME kernels plus the training-step
+ * driver, for callers that cannot link C++ (ctypes, cgo, JNI ...).  Every entry
+ * cites the reference interface it stands for.
+ *
+ * Conventions
+ *  - every function returns 0 on success, non-zero on failure;
+ *    mrn_last_error() returns the message of the calling thread's last failure.
+ *    (The reference aborts the process: src/common/logging.h:43-65.)
+ *  - tensors are described by mrn_tensor: a raw float pointer in DEVICE memory
+ *    plus a Marian shape (rank <= 4, row-major, last dimension contiguous),
+ *    exactly what marian::TensorBase carries (src/tensors/tensor.h:15-65).
+ *    Shapes are right-aligned to 4-D inside the kernels like
+ *    gpu::ConstantShape (src/gpu/shape.h:40-51).
+ *  - all device work is asynchronous on one stream (mrn_set_stream); only the
+ *    functions documented as blocking synchronise.
+ *  - forward operators overwrite `out`; backward operators accumulate (+=)
+ *    EXCEPT transpose_nd, shift, highway_backward, deconcatenate (they assign),
+ *    as in the reference.
+ */
+#ifndef MARIAN_B200_H
+#define MARIAN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct mrn_tensor {
+  float* data; /* device pointer */
+  int rank;    /* 1..4 */
+  int shape[4];
+} mrn_tensor;
+
+/* ---- library / device ------------------------------------------------- */
+const char* mrn_last_error(void);
+const char* mrn_backend_name(void); /* "cuda" (product) or "cpu-oracle" (test oracle build) */
+int mrn_set_device(int device);
+int mrn_set_stream(void* cuda_stream); /* NULL = engine-owned stream */
+int mrn_synchronize(void);             /* blocking */
+
+/* device memory helpers (cudaMalloc / cudaMemcpyAsync on the engine stream) */
+int mrn_malloc(void** ptr, size_t bytes);
+int mrn_free(void* ptr);
+int mrn_memcpy_h2d(void* dst, const void* src, size_t bytes); /* blocking */
+int mrn_memcpy_d2h(void* dst, const void* src, size_t bytes); /* blocking */
+int mrn_memset_zero(void* dst, size_t bytes);
+
+/* ---- GEMM context: replaces cublasHandle_t of Prod/ProdBatched --------- */
+/* mode: 0 = fp32 SIMT (exact), 1 = bf16 tcgen05, 2 = bf16x3 split tcgen05 */
+int mrn_gemm_create(void** handle, int device);
+int mrn_gemm_destroy(void* handle);
+int mrn_gemm_set_mode(void* handle, int mode);
+
+/* Prod / ProdBatched: tensor_operators.h:295-311, .cu:543-654 */
+int mrn_prod(void* gemm, mrn_tensor C, mrn_tensor A, mrn_tensor B, int transA, int transB, float beta, float scalar);
+int mrn_prod_batched(void* gemm, mrn_tensor C, mrn_tensor A, mrn_tensor B, int transA, int transB, float beta, float scalar);
+/* AffineNodeOp forward (Prod + Add(_1, val, bias)): node_operators_binary.h:172-186 */
+int mrn_prod_affine(void* gemm, mrn_tensor C, mrn_tensor A, mrn_tensor B, mrn_tensor bias);
+
+/* ---- element-wise family: Element / Add / Reduce templates ------------- */
+/* tensor_operators.h:26-274.  The functor is selected by name from the set the
+ * graph nodes use (node_operators_unary.h / _binary.h), e.g. "plus" (_1 = _2 + _3),
+ * "mult", "minus", "div", "swish", "tanh3", "logit", "relu", "scale" (_1 = c * _2),
+ * "shift" (_1 = _2 + c), "neg", "exp", "log", "sqrt", "square".
+ * n_in inputs (<= 3), `c` is the captured scalar where the functor has one. */
+int mrn_element(const char* functor, mrn_tensor out, const mrn_tensor* ins, int n_in, float c);
+/* out += scale * reduce_or_broadcast(f(ins...)); functors: "id" (_1), "mult" (_1*_2),
+ * "neg", "tanh_grad" (_1*(1-_2*_2)), "swish_grad", "div_grad_b", "scale" (c*_1) ... */
+int mrn_add(const char* functor, float scale, mrn_tensor out, const mrn_tensor* ins, int n_in, float c);
+
+/* ---- row operators ------------------------------------------------------ */
+/* Softmax / LogSoftmax (+Grad): tensor_operators.h:278-282, .cu:202-519. mask may be NULL */
+int mrn_softmax(mrn_tensor out, mrn_tensor in, const mrn_tensor* mask);
+int mrn_logsoftmax(mrn_tensor out, mrn_tensor in);
+int mrn_softmax_grad(mrn_tensor grad, mrn_tensor adj, mrn_tensor val);
+int mrn_logsoftmax_grad(mrn_tensor grad, mrn_tensor adj, mrn_tensor val);
+/* CrossEntropyPick(+Backward): tensor_operators.h:290-291, .cu:1115-1283; pick holds labels as floats */
+int mrn_cross_entropy_pick(mrn_tensor out, mrn_tensor in, mrn_tensor pick);
+int mrn_cross_entropy_pick_backward(mrn_tensor out, mrn_tensor adj, mrn_tensor in, mrn_tensor pick);
+/* LayerNormalization(+Grad): tensor_operators.h:351-364, .cu:1447-1674; beta / grad_beta may be NULL */
+int mrn_layer_norm(mrn_tensor out, mrn_tensor in, mrn_tensor gamma, const mrn_tensor* beta, float eps);
+int mrn_layer_norm_grad(mrn_tensor grad_x, mrn_tensor grad_gamma, const mrn_tensor* grad_beta, mrn_tensor adj, mrn_tensor y, mrn_tensor x, mrn_tensor gamma, const mrn_tensor* beta, float eps);
+/* Att / AttBack: tensor_operators.h:342-349, .cu:1307-1445 */
+int mrn_att(mrn_tensor out, mrn_tensor va, mrn_tensor context, mrn_tensor state);
+int mrn_att_back(mrn_tensor g_va, mrn_tensor g_context, mrn_tensor g_state, mrn_tensor va, mrn_tensor context, mrn_tensor state, mrn_tensor adj);
+
+/* ---- recurrent cells ---------------------------------------------------- */
+/* GRUFastForward/Backward: tensor_operators.h:335-340, .cu:934-1113.
+ * inputs = {state, xW, sU, b[, mask]} ; outputs (grads) may have data == NULL */
+int mrn_gru_fast_forward(mrn_tensor out, const mrn_tensor* inputs, int n_inputs, int final);
+int mrn_gru_fast_backward(const mrn_tensor* outputs, const mrn_tensor* inputs, int n_inputs, mrn_tensor adj, int final);
+/* LSTMCell/Output Forward/Backward: tensor_operators.h:326-333, .cu:1749-2031 */
+int mrn_lstm_cell_forward(mrn_tensor out, const mrn_tensor* inputs, int n_inputs);
+int mrn_lstm_output_forward(mrn_tensor out, const mrn_tensor* inputs, int n_inputs);
+int mrn_lstm_cell_backward(const mrn_tensor* outputs, const mrn_tensor* inputs, int n_inputs, mrn_tensor adj);
+int mrn_lstm_output_backward(const mrn_tensor* outputs, const mrn_tensor* inputs, int n_inputs, mrn_tensor adj);
+/* HighwayForward/Backward: tensor_operators.h:372-383, .cu:2033-2104 */
+int mrn_highway_forward(mrn_tensor out, mrn_tensor in1, mrn_tensor in2, mrn_tensor t);
+int mrn_highway_backward(mrn_tensor out1, mrn_tensor out2, mrn_tensor outt, mrn_tensor in1, mrn_tensor in2, mrn_tensor t, mrn_tensor adj);
+
+/* ---- data movement ------------------------------------------------------ */
+/* TransposeND: tensor_operators.h:72, .cu:164-200; axes has in.rank entries */
+int mrn_transpose_nd(mrn_tensor out, mrn_tensor in, const int* axes);
+/* Concatenate / Deconcatenate: tensor_operators.h:86-88, .cu:35-162 */
+int mrn_concatenate(mrn_tensor out, const mrn_tensor* ins, int n, int axis);
+int mrn_deconcatenate(const mrn_tensor* outs, int n, mrn_tensor in, int axis);
+/* CopyRows / PasteRows: tensor_operators.h:318-320, .cu:656-746; indices: int32 in DEVICE memory */
+int mrn_copy_rows(mrn_tensor out, mrn_tensor in, const int* device_indices, size_t n);
+int mrn_paste_rows(mrn_tensor out, mrn_tensor in, const int* device_indices, size_t n);
+/* Shift: tensor_operators.h:366, .cu:1676-1707; shift has in.rank entries */
+int mrn_shift(mrn_tensor out, mrn_tensor in, const int* shift, int invert);
+
+/* ---- norms and optimizer ------------------------------------------------ */
+/* L2Norm: tensor_operators.h:276, .cu:1286-1305 (blocking: returns the value) */
+int mrn_l2norm(mrn_tensor in, float* result);
+/* Norm::clip + Adam::updateImpl fused: optimizers/clippers.cu:12-17, optimizers.cu:43-73.
+ * t = 1-based step; grad_scale multiplies every gradient (1/N of a summed shard);
+ * clip_norm <= 0 disables clipping. */
+int mrn_adam_step(mrn_tensor params, mrn_tensor grads, mrn_tensor mt, mrn_tensor vt, float eta, float beta1, float beta2, float eps, int t, float grad_scale, float clip_norm);
+
+/* ======================================================================== */
+/* Training-step driver: ExpressionGraph + model + GraphGroup behind a handle
+ * (reference: Train<GraphGroup>::run's hot loop, src/training/training.h:51-57;
+ * SingletonGraph::execute graph_group_singleton.cu:21-66; SyncGraphGroup::execute
+ * graph_group_sync.cu:42-188).
+ * options: "key=value;key=value" over the reference's defaults
+ * (src/common/config_parser.cpp:214-467), e.g.
+ *   "type=transformer;dim-vocabs=32000,32000;enc-depth=6;dec-depth=6;gemm-mode=1"
+ * rank/nranks > 1 selects the sharded SyncGraphGroup of this rank. */
+int mrn_trainer_create(void** trainer, const char* options, int device, int rank, int nranks);
+int mrn_trainer_destroy(void* trainer);
+
+/* Batch in the reference's CorpusBatch layout (src/data/corpus.h:49-205):
+ * per side time-major indices[t*B+b] (int64) and mask[t*B+b] in {0,1}; HOST memory. */
+int mrn_trainer_set_batch(void* trainer, int batch_size, int src_len, const int64_t* src_idx, const float* src_mask, int trg_len, const int64_t* trg_idx, const float* trg_mask);
+/* Synthetic bitext of SURVEY.md 8d generated inside the library (same RNG stream on
+ * both builds): padded = 0 dense / 1 padded+sorted.  Advances the corpus. */
+int mrn_trainer_next_synthetic_batch(void* trainer, int batch_size, int max_len_src, int max_len_trg, int padded, int split_rank, int split_n);
+
+/* forward + backward of the current batch (CUDA-graph replay after the first
+ * occurrences of a shape).  Asynchronous. keep_logits != 0 keeps the logits node. */
+int mrn_trainer_compute_gradients(void* trainer, int keep_logits);
+/* single-process update: clip + optimizer over the whole arena. Asynchronous. */
+int mrn_trainer_update(void* trainer);
+/* sharded update of this rank's shard from the summed gradient shard
+ * (mrn_trainer_shard_grads_ptr), then invalidates packed weights. Asynchronous. */
+int mrn_trainer_update_shard(void* trainer);
+/* blocking: waits for the stream, returns the cost of the last batch */
+int mrn_trainer_cost(void* trainer, float* cost);
+
+/* flat arenas (src/graph/parameters.h:58-80): device pointers + element counts */
+int mrn_trainer_params(void* trainer, float** ptr, size_t* elements);
+int mrn_trainer_grads(void* trainer, float** ptr, size_t* elements);
+int mrn_trainer_shard_grads(void* trainer, float** ptr, size_t* elements);
+/* copies of named tensors to HOST memory (blocking); name = parameter name,
+ * or "logits" / "cost"; returns the element count in *elements (buffer may be NULL to query) */
+int mrn_trainer_get_tensor(void* trainer, const char* name, int want_grad, float* host_buffer, size_t capacity, size_t* elements);
+/* newline separated "name rank d0 d1 .." list of parameters in arena order */
+int mrn_trainer_param_names(void* trainer, char* buffer, size_t capacity, size_t* needed);
+/* words in the current batch: source-side (reference's log line) and source+target */
+int mrn_trainer_batch_words(void* trainer, size_t* src_words, size_t* total_words);
+/* statistics: number of tape nodes of the last eager build, captured plans, replays */
+int mrn_trainer_stats(void* trainer, size_t* tape_nodes, size_t* plans, size_t* replays, size_t* workspace_bytes);
+
+/* Runs one of the reference's unit-test graphs (src/tests/*.cpp) through the
+ * graph API and returns the values the reference test asserts on.  Used by the
+ * golden-vector tests; see tests/cpp/graph_golden.cpp for the case names. */
+int mrn_test_golden(const char* test_case, float* out, size_t capacity, size_t* count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MARIAN_B200_H */

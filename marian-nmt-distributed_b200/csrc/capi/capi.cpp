@@ -1,0 +1,482 @@
+// extern "C" boundary (include/marian_b200.h) over the tensor operators and the
+// training-step driver.  Compiled into the product library (CUDA kernels) and,
+// unchanged, into the test oracle (CPU restatement); which one answers is
+// reported by mrn_backend_name().
+#include "marian_b200.h"
+
+#include <cstring>
+#include <map>
+#include <string>
+
+#include "data/batch.h"
+#include "kernels/tensor_operators.h"
+#include "training/graph_group.h"
+
+using namespace marian;
+
+namespace {
+
+thread_local std::string g_lastError;
+
+template <class F>
+int guarded(F f) {
+  try {
+    f();
+    return 0;
+  } catch(const std::exception& e) {
+    g_lastError = e.what();
+    return 1;
+  } catch(...) {
+    g_lastError = "unknown error";
+    return 2;
+  }
+}
+
+Tensor wrap(const mrn_tensor& t) {
+  if(!t.data)
+    return nullptr;
+  ABORT_IF(t.rank < 1 || t.rank > 4, "mrn_tensor rank must be 1..4");
+  std::vector<int> dims(t.shape, t.shape + t.rank);
+  Shape shape(dims);
+  auto mem = New<MemoryPiece>((uint8_t*)t.data, (size_t)shape.elements() * sizeof(float));
+  return Tensor(new TensorBase(mem, shape, device::getDevice()));
+}
+Tensor wrapOpt(const mrn_tensor* t) {
+  return t ? wrap(*t) : nullptr;
+}
+std::vector<Tensor> wrapAll(const mrn_tensor* ts, int n) {
+  std::vector<Tensor> v;
+  for(int i = 0; i < n; ++i)
+    v.push_back(wrap(ts[i]));
+  return v;
+}
+
+struct Trainer {
+  Ptr<Options> options;
+  int device{0}, rank{0}, nranks{1};
+  Ptr<SingletonGraph> single;
+  Ptr<SyncGraphGroup> sync;
+  Ptr<data::CorpusBatch> batch;
+  Ptr<data::SyntheticCorpus> corpus;
+  size_t replays{0};
+
+  GradientWorker& worker() { return single ? single->worker() : sync->worker(); }
+};
+
+}  // namespace
+
+extern "C" {
+
+const char* mrn_last_error(void) {
+  return g_lastError.c_str();
+}
+const char* mrn_backend_name(void) {
+  return device::backendName();
+}
+int mrn_set_device(int d) {
+  return guarded([&] { device::setDevice(d); });
+}
+int mrn_set_stream(void* s) {
+  return guarded([&] { device::setStream(s); });
+}
+int mrn_synchronize(void) {
+  return guarded([&] { device::synchronize(); });
+}
+
+int mrn_malloc(void** ptr, size_t bytes) {
+  return guarded([&] { *ptr = device::mallocDevice(bytes); });
+}
+int mrn_free(void* ptr) {
+  return guarded([&] { device::freeDevice(ptr); });
+}
+int mrn_memcpy_h2d(void* dst, const void* src, size_t bytes) {
+  return guarded([&] { device::copyH2DBlocking(dst, src, bytes); });
+}
+int mrn_memcpy_d2h(void* dst, const void* src, size_t bytes) {
+  return guarded([&] {
+    void* p = device::mallocPinned(bytes);
+    device::copyD2H(p, src, bytes);
+    device::synchronize();
+    std::memcpy(dst, p, bytes);
+    device::freePinned(p);
+  });
+}
+int mrn_memset_zero(void* dst, size_t bytes) {
+  return guarded([&] { device::zero(dst, bytes); });
+}
+
+int mrn_gemm_create(void** handle, int dev) {
+  return guarded([&] { *handle = createGemmContext(dev); });
+}
+int mrn_gemm_destroy(void* handle) {
+  return guarded([&] { destroyGemmContext((GemmHandle)handle); });
+}
+int mrn_gemm_set_mode(void* handle, int mode) {
+  return guarded([&] { setGemmMode((GemmHandle)handle, (GemmMode)mode); });
+}
+
+int mrn_prod(void* g, mrn_tensor C, mrn_tensor A, mrn_tensor B, int tA, int tB, float beta, float scalar) {
+  return guarded([&] {
+    gemmInvalidateCache((GemmHandle)g);
+    Prod((GemmHandle)g, wrap(C), wrap(A), wrap(B), tA, tB, beta, scalar);
+  });
+}
+int mrn_prod_batched(void* g, mrn_tensor C, mrn_tensor A, mrn_tensor B, int tA, int tB, float beta, float scalar) {
+  return guarded([&] {
+    gemmInvalidateCache((GemmHandle)g);
+    ProdBatched((GemmHandle)g, wrap(C), wrap(A), wrap(B), tA, tB, beta, scalar);
+  });
+}
+int mrn_prod_affine(void* g, mrn_tensor C, mrn_tensor A, mrn_tensor B, mrn_tensor bias) {
+  return guarded([&] {
+    gemmInvalidateCache((GemmHandle)g);
+    ProdAffine((GemmHandle)g, wrap(C), wrap(A), wrap(B), wrap(bias));
+  });
+}
+
+int mrn_element(const char* functor, mrn_tensor out, const mrn_tensor* ins, int n_in, float c) {
+  return guarded([&] {
+    using namespace functional;
+    std::string f = functor;
+    Tensor o = wrap(out);
+    auto in = wrapAll(ins, n_in);
+    auto need = [&](int n) { ABORT_IF(n_in != n, "mrn_element: wrong number of inputs for functor", f); };
+    if(f == "plus") { need(2); Element(_1 = _2 + _3, o, in[0], in[1]); }
+    else if(f == "minus") { need(2); Element(_1 = _2 - _3, o, in[0], in[1]); }
+    else if(f == "mult") { need(2); Element(_1 = _2 * _3, o, in[0], in[1]); }
+    else if(f == "div") { need(2); Element(_1 = _2 / _3, o, in[0], in[1]); }
+    else if(f == "tanh3") { need(3); Element(_1 = tanh(_2 + _3 + _4), o, in[0], in[1], in[2]); }
+    else if(f == "tanh2") { need(2); Element(_1 = tanh(_2 + _3), o, in[0], in[1]); }
+    else if(f == "tanh") { need(1); Element(_1 = tanh(_2), o, in[0]); }
+    else if(f == "swish") { need(1); Element(_1 = _2 * logit(_2), o, in[0]); }
+    else if(f == "logit") { need(1); Element(_1 = logit(_2), o, in[0]); }
+    else if(f == "relu") { need(1); Element(_1 = ReLU(_2), o, in[0]); }
+    else if(f == "scale") { need(1); Element(_1 = c * _2, o, in[0]); }
+    else if(f == "shift") { need(1); Element(_1 = _2 + c, o, in[0]); }
+    else if(f == "neg") { need(1); Element(_1 = -_2, o, in[0]); }
+    else if(f == "exp") { need(1); Element(_1 = exp(_2), o, in[0]); }
+    else if(f == "log") { need(1); Element(_1 = log(_2), o, in[0]); }
+    else if(f == "sqrt") { need(1); Element(_1 = sqrt(_2 + c), o, in[0]); }
+    else if(f == "square") { need(1); Element(_1 = _2 * _2, o, in[0]); }
+    else if(f == "axpy_self") { need(1); Element(_1 = _1 + c * _2, o, in[0]); }
+    else ABORT("mrn_element: unknown functor", f);
+  });
+}
+
+int mrn_add(const char* functor, float scale, mrn_tensor out, const mrn_tensor* ins, int n_in, float c) {
+  return guarded([&] {
+    using namespace functional;
+    std::string f = functor;
+    Tensor o = wrap(out);
+    auto in = wrapAll(ins, n_in);
+    auto need = [&](int n) { ABORT_IF(n_in != n, "mrn_add: wrong number of inputs for functor", f); };
+    if(f == "id") { need(1); Add(_1, scale, o, in[0]); }
+    else if(f == "neg") { need(1); Add(-_1, scale, o, in[0]); }
+    else if(f == "scale") { need(1); Add(c * _1, scale, o, in[0]); }
+    else if(f == "mult") { need(2); Add(_1 * _2, scale, o, in[0], in[1]); }
+    else if(f == "tanh_grad") { need(2); Add(_1 * (1.0f - (_2 * _2)), scale, o, in[0], in[1]); }
+    else if(f == "logit_grad") { need(2); Add(_1 * _2 * (1.0f - _2), scale, o, in[0], in[1]); }
+    else if(f == "swish_grad") { need(3); Add(_1 * (_3 + logit(_2) * (1.f - _3)), scale, o, in[0], in[1], in[2]); }
+    else if(f == "relu_grad") { need(2); Add(_1 * ReLUback(_2), scale, o, in[0], in[1]); }
+    else if(f == "div_grad_a") { need(2); Add(_1 * 1.0f / _2, scale, o, in[0], in[1]); }
+    else if(f == "div_grad_b") { need(3); Add(-_1 * _2 / (_3 * _3), scale, o, in[0], in[1], in[2]); }
+    else ABORT("mrn_add: unknown functor", f);
+  });
+}
+
+int mrn_softmax(mrn_tensor out, mrn_tensor in, const mrn_tensor* mask) {
+  return guarded([&] { Softmax(wrap(out), wrap(in), wrapOpt(mask)); });
+}
+int mrn_logsoftmax(mrn_tensor out, mrn_tensor in) {
+  return guarded([&] { LogSoftmax(wrap(out), wrap(in)); });
+}
+int mrn_softmax_grad(mrn_tensor grad, mrn_tensor adj, mrn_tensor val) {
+  return guarded([&] { SoftmaxGrad(wrap(grad), wrap(adj), wrap(val)); });
+}
+int mrn_logsoftmax_grad(mrn_tensor grad, mrn_tensor adj, mrn_tensor val) {
+  return guarded([&] { LogSoftmaxGrad(wrap(grad), wrap(adj), wrap(val)); });
+}
+int mrn_cross_entropy_pick(mrn_tensor out, mrn_tensor in, mrn_tensor pick) {
+  return guarded([&] { CrossEntropyPick(wrap(out), wrap(in), wrap(pick)); });
+}
+int mrn_cross_entropy_pick_backward(mrn_tensor out, mrn_tensor adj, mrn_tensor in, mrn_tensor pick) {
+  return guarded([&] { CrossEntropyPickBackward(wrap(out), wrap(adj), wrap(in), wrap(pick)); });
+}
+int mrn_layer_norm(mrn_tensor out, mrn_tensor in, mrn_tensor gamma, const mrn_tensor* beta, float eps) {
+  return guarded([&] { LayerNormalization(wrap(out), wrap(in), wrap(gamma), wrapOpt(beta), eps); });
+}
+int mrn_layer_norm_grad(mrn_tensor gx, mrn_tensor gg, const mrn_tensor* gb, mrn_tensor adj, mrn_tensor y, mrn_tensor x, mrn_tensor gamma, const mrn_tensor* beta, float eps) {
+  return guarded([&] {
+    LayerNormalizationGrad(wrap(gx), wrap(gg), wrapOpt(gb), wrap(adj), wrap(y), wrap(x), wrap(gamma), wrapOpt(beta), eps);
+  });
+}
+int mrn_att(mrn_tensor out, mrn_tensor va, mrn_tensor context, mrn_tensor state) {
+  return guarded([&] { Att(wrap(out), wrap(va), wrap(context), wrap(state)); });
+}
+int mrn_att_back(mrn_tensor gva, mrn_tensor gc, mrn_tensor gs, mrn_tensor va, mrn_tensor context, mrn_tensor state, mrn_tensor adj) {
+  return guarded([&] { AttBack(wrap(gva), wrap(gc), wrap(gs), wrap(va), wrap(context), wrap(state), wrap(adj)); });
+}
+
+int mrn_gru_fast_forward(mrn_tensor out, const mrn_tensor* inputs, int n, int final) {
+  return guarded([&] { GRUFastForward(wrap(out), wrapAll(inputs, n), final != 0); });
+}
+int mrn_gru_fast_backward(const mrn_tensor* outputs, const mrn_tensor* inputs, int n, mrn_tensor adj, int final) {
+  return guarded([&] { GRUFastBackward(wrapAll(outputs, 4), wrapAll(inputs, n), wrap(adj), final != 0); });
+}
+int mrn_lstm_cell_forward(mrn_tensor out, const mrn_tensor* inputs, int n) {
+  return guarded([&] { LSTMCellForward(wrap(out), wrapAll(inputs, n)); });
+}
+int mrn_lstm_output_forward(mrn_tensor out, const mrn_tensor* inputs, int n) {
+  return guarded([&] { LSTMOutputForward(wrap(out), wrapAll(inputs, n)); });
+}
+int mrn_lstm_cell_backward(const mrn_tensor* outputs, const mrn_tensor* inputs, int n, mrn_tensor adj) {
+  return guarded([&] { LSTMCellBackward(wrapAll(outputs, 4), wrapAll(inputs, n), wrap(adj)); });
+}
+int mrn_lstm_output_backward(const mrn_tensor* outputs, const mrn_tensor* inputs, int n, mrn_tensor adj) {
+  return guarded([&] { LSTMOutputBackward(wrapAll(outputs, 4), wrapAll(inputs, n), wrap(adj)); });
+}
+int mrn_highway_forward(mrn_tensor out, mrn_tensor in1, mrn_tensor in2, mrn_tensor t) {
+  return guarded([&] { HighwayForward(wrap(out), wrap(in1), wrap(in2), wrap(t)); });
+}
+int mrn_highway_backward(mrn_tensor o1, mrn_tensor o2, mrn_tensor ot, mrn_tensor in1, mrn_tensor in2, mrn_tensor t, mrn_tensor adj) {
+  return guarded([&] { HighwayBackward(wrap(o1), wrap(o2), wrap(ot), wrap(in1), wrap(in2), wrap(t), wrap(adj)); });
+}
+
+int mrn_transpose_nd(mrn_tensor out, mrn_tensor in, const int* axes) {
+  return guarded([&] { TransposeND(wrap(out), wrap(in), std::vector<int>(axes, axes + in.rank)); });
+}
+int mrn_concatenate(mrn_tensor out, const mrn_tensor* ins, int n, int axis) {
+  return guarded([&] {
+    int ax = axis < 0 ? out.rank + axis : axis;
+    Concatenate(wrap(out), wrapAll(ins, n), ax);
+  });
+}
+int mrn_deconcatenate(const mrn_tensor* outs, int n, mrn_tensor in, int axis) {
+  return guarded([&] {
+    int ax = axis < 0 ? in.rank + axis : axis;
+    auto o = wrapAll(outs, n);
+    Deconcatenate(o, wrap(in), ax);
+  });
+}
+int mrn_copy_rows(mrn_tensor out, mrn_tensor in, const int* idx, size_t n) {
+  return guarded([&] { CopyRows(wrap(out), wrap(in), idx, n); });
+}
+int mrn_paste_rows(mrn_tensor out, mrn_tensor in, const int* idx, size_t n) {
+  return guarded([&] { PasteRows(wrap(out), wrap(in), idx, n); });
+}
+int mrn_shift(mrn_tensor out, mrn_tensor in, const int* shift, int invert) {
+  return guarded([&] { Shift(wrap(out), wrap(in), Shape(std::vector<int>(shift, shift + in.rank)), invert != 0); });
+}
+
+int mrn_l2norm(mrn_tensor in, float* result) {
+  return guarded([&] { *result = L2Norm(wrap(in)); });
+}
+
+int mrn_adam_step(mrn_tensor params, mrn_tensor grads, mrn_tensor mt, mrn_tensor vt, float eta, float beta1, float beta2, float eps, int t, float grad_scale, float clip_norm) {
+  return guarded([&] {
+    AdamArgs a;
+    a.eta = eta;
+    a.beta1 = beta1;
+    a.beta2 = beta2;
+    a.eps = eps;
+    a.denom1 = (float)(1 - std::pow((double)beta1, (double)t));
+    a.denom2 = (float)(1 - std::pow((double)beta2, (double)t));
+    a.gradScale = grad_scale;
+    a.clipNorm = clip_norm;
+    Tensor normSq = nullptr;
+    Ptr<TensorAllocator> scratch;
+    if(clip_norm > 0) {
+      scratch = New<TensorAllocator>(device::getDevice());
+      scratch->reserveExact(256);
+      scratch->allocate(normSq, Shape{1, 1});
+      SumSquares(normSq, wrap(grads));
+    }
+    AdamUpdate(wrap(params), wrap(grads), wrap(mt), wrap(vt), a, normSq);
+    if(scratch)
+      device::synchronize();  // scratch is released on return
+  });
+}
+
+// ---------------------------------------------------------------------------
+// training-step driver
+// ---------------------------------------------------------------------------
+int mrn_trainer_create(void** trainer, const char* options, int dev, int rank, int nranks) {
+  return guarded([&] {
+    auto t = new Trainer();
+    t->options = defaultOptions();
+    Options user(options ? options : "");
+    t->options->overwrite(user);
+    t->device = dev;
+    t->rank = rank;
+    t->nranks = nranks;
+    Config::seed = t->options->get<size_t>("seed");
+    device::setDevice(dev);
+    if(nranks > 1)
+      t->sync = New<SyncGraphGroup>(t->options, dev, rank, nranks);
+    else
+      t->single = New<SingletonGraph>(t->options, dev);
+    auto gemm = t->worker().graph()->getBackend()->getGemmHandle();
+    setGemmMode(gemm, (GemmMode)t->options->get<int>("gemm-mode", 0));
+    auto voc = t->options->get<std::vector<int>>("dim-vocabs");
+    t->corpus = New<data::SyntheticCorpus>(voc[0], voc[1], (uint32_t)t->options->get<int>("data-seed", 1111));
+    *trainer = t;
+  });
+}
+int mrn_trainer_destroy(void* trainer) {
+  return guarded([&] {
+    auto t = (Trainer*)trainer;
+    device::setDevice(t->device);
+    device::synchronize();
+    delete t;
+  });
+}
+
+int mrn_trainer_set_batch(void* trainer, int B, int Ts, const int64_t* srcIdx, const float* srcMask, int Tt, const int64_t* trgIdx, const float* trgMask) {
+  return guarded([&] {
+    auto t = (Trainer*)trainer;
+    auto mk = [&](int T, const int64_t* idx, const float* mask) {
+      auto sb = New<data::SubBatch>(B, T);
+      size_t words = 0;
+      for(size_t i = 0; i < (size_t)B * T; ++i) {
+        sb->indices()[i] = (Word)idx[i];
+        sb->mask()[i] = mask[i];
+        if(mask[i] != 0)
+          words++;
+      }
+      sb->setWords(words);
+      return sb;
+    };
+    t->batch = New<data::CorpusBatch>(std::vector<Ptr<data::SubBatch>>{mk(Ts, srcIdx, srcMask), mk(Tt, trgIdx, trgMask)});
+  });
+}
+
+int mrn_trainer_next_synthetic_batch(void* trainer, int B, int Ls, int Lt, int padded, int splitRank, int splitN) {
+  return guarded([&] {
+    auto t = (Trainer*)trainer;
+    auto full = t->corpus->next(B, Ls, Lt, padded != 0);
+    if(splitN > 1)
+      t->batch = full->split(splitN)[splitRank];
+    else
+      t->batch = full;
+  });
+}
+
+int mrn_trainer_compute_gradients(void* trainer, int keepLogits) {
+  return guarded([&] {
+    auto t = (Trainer*)trainer;
+    ABORT_IF(!t->batch, "no batch set");
+    if(t->sync) {
+      ABORT_IF(keepLogits, "keep_logits is only supported on the single-process trainer");
+      t->sync->computeGradients(t->batch);
+    } else {
+      t->worker().computeGradients(t->batch, keepLogits != 0);
+    }
+    if(t->worker().lastStepReplayed())
+      t->replays++;
+  });
+}
+int mrn_trainer_update(void* trainer) {
+  return guarded([&] {
+    auto t = (Trainer*)trainer;
+    ABORT_IF(!t->single, "mrn_trainer_update: sharded trainers use mrn_trainer_update_shard");
+    t->single->optimizer()->update(t->worker().graph());
+  });
+}
+int mrn_trainer_update_shard(void* trainer) {
+  return guarded([&] {
+    auto t = (Trainer*)trainer;
+    ABORT_IF(!t->sync, "mrn_trainer_update_shard needs nranks > 1");
+    t->sync->updateShard();
+  });
+}
+int mrn_trainer_cost(void* trainer, float* cost) {
+  return guarded([&] { *cost = ((Trainer*)trainer)->worker().cost(); });
+}
+
+int mrn_trainer_params(void* trainer, float** ptr, size_t* elements) {
+  return guarded([&] {
+    auto p = ((Trainer*)trainer)->worker().graph()->params()->vals();
+    *ptr = p->data();
+    *elements = p->size();
+  });
+}
+int mrn_trainer_grads(void* trainer, float** ptr, size_t* elements) {
+  return guarded([&] {
+    auto g = ((Trainer*)trainer)->worker().graph()->params();
+    g->allocateBackward();
+    auto p = g->grads();
+    *ptr = p->data();
+    *elements = p->size();
+  });
+}
+int mrn_trainer_shard_grads(void* trainer, float** ptr, size_t* elements) {
+  return guarded([&] {
+    auto t = (Trainer*)trainer;
+    ABORT_IF(!t->sync, "mrn_trainer_shard_grads needs nranks > 1");
+    auto p = t->sync->shardGrads();
+    *ptr = p->data();
+    *elements = p->size();
+  });
+}
+
+int mrn_trainer_get_tensor(void* trainer, const char* name, int wantGrad, float* host, size_t capacity, size_t* elements) {
+  return guarded([&] {
+    auto t = (Trainer*)trainer;
+    std::string n = name;
+    Tensor src;
+    if(n == "logits") {
+      auto l = t->worker().logits();
+      ABORT_IF(!l, "no logits kept: call mrn_trainer_compute_gradients(keep_logits=1)");
+      src = wantGrad ? l->grad() : l->val();
+    } else {
+      auto p = t->worker().graph()->params()->get(n);
+      ABORT_IF(!p, "unknown parameter", n);
+      src = wantGrad ? p->grad() : p->val();
+    }
+    ABORT_IF(!src, "tensor not allocated", n);
+    *elements = src->size();
+    if(host) {
+      ABORT_IF(capacity < src->size(), "buffer too small for", n);
+      std::vector<float> v;
+      src->get(v);
+      std::memcpy(host, v.data(), v.size() * sizeof(float));
+    }
+  });
+}
+
+int mrn_trainer_param_names(void* trainer, char* buffer, size_t capacity, size_t* needed) {
+  return guarded([&] {
+    auto t = (Trainer*)trainer;
+    std::string s;
+    for(auto p : *t->worker().graph()->params()) {
+      s += p->name() + " " + std::to_string(p->shape().size());
+      for(auto d : p->shape())
+        s += " " + std::to_string(d);
+      s += "\n";
+    }
+    *needed = s.size() + 1;
+    if(buffer && capacity >= s.size() + 1)
+      std::memcpy(buffer, s.c_str(), s.size() + 1);
+  });
+}
+
+int mrn_trainer_batch_words(void* trainer, size_t* srcWords, size_t* totalWords) {
+  return guarded([&] {
+    auto t = (Trainer*)trainer;
+    ABORT_IF(!t->batch, "no batch set");
+    *srcWords = t->batch->words();
+    *totalWords = t->batch->wordsTotal();
+  });
+}
+
+int mrn_trainer_stats(void* trainer, size_t* tapeNodes, size_t* plans, size_t* replays, size_t* workspaceBytes) {
+  return guarded([&] {
+    auto t = (Trainer*)trainer;
+    *tapeNodes = t->worker().graph()->numNodes();
+    *plans = t->worker().replay().size();
+    *replays = t->replays;
+    *workspaceBytes = t->worker().graph()->allocator()->peak();
+  });
+}
+
+}  // extern "C"

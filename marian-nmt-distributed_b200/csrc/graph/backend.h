@@ -1,0 +1,40 @@
+// Per-graph device backend.
+//
+// Role of the reference's Backend/BackendGPU (src/graph/backend.h:5-8,
+// src/graph/backend_gpu.h:20-55: cuBLAS handle + cuRAND generator per graph).
+// Here it owns the GEMM context (tcgen05 kernels + packed-operand scratch, see
+// kernels/tensor_operators.h) and the counter that seeds dropout masks.
+#pragma once
+
+#include "common/definitions.h"
+#include "kernels/tensor_operators.h"
+
+namespace marian {
+
+class Backend {
+public:
+  Backend(int deviceId, size_t seed) : device_(deviceId), seed_(seed) {
+    device::setDevice(deviceId);
+    gemm_ = createGemmContext(deviceId);
+  }
+  ~Backend() { destroyGemmContext(gemm_); }
+
+  void setDevice(size_t) { device::setDevice(device_); }
+  int getDevice() const { return device_; }
+
+  GemmHandle getGemmHandle() { return gemm_; }
+  // source-compatible spelling used by node operators ported from Marian
+  GemmHandle getCublasHandle() { return gemm_; }
+
+  uint64_t nextDropoutSeed() { return (uint64_t)seed_ * 0x9E3779B97F4A7C15ULL + (++dropCounter_); }
+
+private:
+  int device_;
+  size_t seed_;
+  uint64_t dropCounter_{0};
+  GemmHandle gemm_{nullptr};
+};
+
+typedef Backend BackendGPU;
+
+}  // namespace marian

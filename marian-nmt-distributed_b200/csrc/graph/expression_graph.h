@@ -1,0 +1,405 @@
+// ExpressionGraph: the define-by-run tape + parameter store of one device.
+//
+// API and execution order follow the reference (src/graph/expression_graph.h:28-512,
+// src/graph/parameters.h:10-89, src/graph/node_operators.h:8-80):
+//   add()      CSE by hash, tape push, top-node bookkeeping          (:385-409)
+//   forward()  params arena, then allocate/init/forward per node      (:134-162)
+//   backward() zero param grads, seed top node with 1, reverse sweep,
+//              zero child adjoints lazily, drop children as we go     (:180-215)
+// Parameters live in two exact-size arenas (values / gradients) that expose the
+// whole model as ONE flat tensor - the layout the optimizer and the multi-GPU
+// shard exchange rely on.
+//
+// B200-first differences: nothing here synchronises the stream; constants and
+// index vectors are uploaded through pinned staging owned by the graph; batch
+// dependent uploads are recorded (batchUploads()) so a captured CUDA graph of
+// the whole step can be replayed on the next batch of the same shape
+// (training/graph_replay.h).
+#pragma once
+
+#include <list>
+#include <map>
+#include <unordered_map>
+#include <unordered_set>
+
+#include "common/definitions.h"
+#include "common/keywords.h"
+#include "graph/backend.h"
+#include "graph/node.h"
+#include "layers/param_initializers.h"
+#include "tensors/allocator.h"
+#include "tensors/staging.h"
+
+namespace marian {
+
+namespace data {
+class CorpusBatch;
+}
+
+struct ConstantNode : public Node {
+  ConstantNode(Ptr<ExpressionGraph> graph, const Shape& shape, std::function<void(Tensor)> init)
+      : Node(graph, shape), init_(init) {
+    setTrainable(false);
+  }
+  virtual void init() {
+    if(!initialized_) {
+      init_(val_);
+      initialized_ = true;
+    }
+  }
+  const std::string type() { return "const"; }
+  virtual size_t hash() {
+    size_t seed = std::hash<std::string>()(name());
+    hash_combine(seed, type());
+    hash_combine(seed, (size_t)this);
+    return seed;
+  }
+  virtual bool equal(Expr node) { return this == node.get(); }
+
+protected:
+  std::function<void(Tensor)> init_;
+  bool initialized_{false};
+};
+
+struct ParamNode : public Node {
+  ParamNode(Ptr<ExpressionGraph> graph, const Shape& shape, std::function<void(Tensor)> init, bool fixed)
+      : Node(graph, shape), init_(init) {
+    setTrainable(!fixed);
+  }
+  virtual void init() {
+    if(!initialized_) {
+      init_(val_);
+      initialized_ = true;
+    }
+  }
+  const std::string type() { return "param"; }
+  virtual size_t hash() {
+    size_t seed = std::hash<std::string>()(name());
+    hash_combine(seed, type());
+    hash_combine(seed, (size_t)this);
+    return seed;
+  }
+  virtual bool equal(Expr node) { return name() == node->name(); }
+
+private:
+  std::function<void(Tensor)> init_;
+  bool initialized_{false};
+};
+
+class Parameters {
+public:
+  void init(int device) {
+    vals_ = New<TensorAllocator>(device);
+    grads_ = New<TensorAllocator>(device);
+  }
+
+  std::vector<Expr>::iterator begin() { return params_.begin(); }
+  std::vector<Expr>::iterator end() { return params_.end(); }
+  std::map<std::string, Expr>& getMap() { return named_; }
+
+  Expr get(const std::string& name) {
+    auto it = named_.find(name);
+    return it != named_.end() ? it->second : Expr();
+  }
+  size_t size() { return params_.size(); }
+
+  // Bytes of one flat arena.  With setShardCount(N) the arena is padded so it
+  // splits into N equal, 256-byte aligned shards (what reduce-scatter /
+  // all-gather need); the padding holds zeros and never receives gradients.
+  size_t totalCapacity(Ptr<TensorAllocator> alloc) {
+    size_t sum = 0;
+    for(auto p : params_)
+      sum += alloc->capacity(p->shape());
+    size_t quantum = 256 * (size_t)shards_;
+    return (sum + quantum - 1) / quantum * quantum;
+  }
+  void setShardCount(int n) { shards_ = n > 0 ? n : 1; }
+  int shardCount() const { return shards_; }
+
+  void add(Expr p, const std::string& name) {
+    ABORT_IF(named_.count(name), "Parameter already exists:", name);
+    params_.push_back(p);
+    named_[name] = p;
+  }
+
+  void allocateForward() {
+    if(vals_->size() == 0 && !params_.empty()) {
+      vals_->reserveExact(totalCapacity(vals_));
+      vals_->asTensor()->set(0);  // padding must be defined (flat tensor is exchanged as a whole)
+      for(auto p : params_)
+        if(!p->val())
+          vals_->allocate(p->val(), p->shape());
+    }
+  }
+  void allocateBackward() {
+    if(grads_->size() == 0 && !params_.empty()) {
+      grads_->reserveExact(totalCapacity(grads_));
+      for(auto p : params_)
+        if(!p->grad())
+          grads_->allocate(p->grad(), p->shape());
+    }
+  }
+  void set_zero_adjoint() { grads()->set(0); }
+
+  Tensor vals() { return vals_->asTensor(); }
+  Tensor grads() { return grads_->asTensor(); }
+
+  void clear() {
+    params_.clear();
+    named_.clear();
+    vals_->clear();
+    grads_->clear();
+  }
+
+private:
+  std::vector<Expr> params_;
+  std::map<std::string, Expr> named_;
+  Ptr<TensorAllocator> vals_;
+  Ptr<TensorAllocator> grads_;
+  int shards_{1};
+};
+
+template <class T, typename... Args>
+Expr Expression(Args&&... args);
+
+class ExpressionGraph : public std::enable_shared_from_this<ExpressionGraph> {
+public:
+  explicit ExpressionGraph(bool inference = false) : inferenceOnly_(inference) {}
+  ExpressionGraph(const ExpressionGraph&) = delete;
+
+  ~ExpressionGraph() {
+    clear();
+    if(params_)
+      params_->clear();
+  }
+
+  void setInference(bool inference) { inferenceOnly_ = inference; }
+
+  void setDevice(size_t device = 0) {
+    device_ = (int)device;
+    device::setDevice(device_);
+    params_ = New<Parameters>();
+    params_->init(device_);
+    tensors_ = New<TensorAllocator>(device_);
+    backend_ = New<Backend>(device_, Config::seed);
+  }
+  size_t getDevice() { return device_; }
+  Ptr<Backend> getBackend() { return backend_; }
+
+  void switchParams(const std::string& newNamespace) { namespace_ = newNamespace; }
+
+  void reserveWorkspaceMB(size_t num) { tensors_->reserve(num * 1024 * 1024 - 1); }
+
+  void copyParams(Ptr<ExpressionGraph> graph) {
+    for(auto p : *graph->params())
+      param(p->name(), p->shape());
+    params()->allocateForward();
+    params()->vals()->copyFrom(graph->params()->vals());
+  }
+
+  void backprop() {
+    forward();
+    backward();
+  }
+
+  bool fits() {
+    try {
+      tensors_->throwAtReallocation(true);
+      backprop();
+      tensors_->throwAtReallocation(false);
+    } catch(AllocationException&) {
+      tensors_->throwAtReallocation(false);
+      return false;
+    }
+    return true;
+  }
+
+  void forward() {
+    device::setDevice(device_);
+    params_->allocateForward();
+    gemmInvalidateCache(backend_->getGemmHandle());
+    forwardNext();
+  }
+
+  void forwardNext() {
+    StagingScope scope(staging_.get());
+    hashMap_.clear();
+    while(!nodesForward_.empty()) {
+      auto v = nodesForward_.front();
+      v->allocate();
+      v->init();
+      v->forward();
+      if(inferenceOnly_)
+        v->children().clear();
+      nodesForward_.pop_front();
+    }
+  }
+
+  void backward() {
+    ABORT_IF(topNodes_.size() > 1, "There are more than one top most node for backward step");
+    device::setDevice(device_);
+    StagingScope scope(staging_.get());
+
+    params_->allocateBackward();
+    params_->set_zero_adjoint();
+
+    for(auto&& v : topNodes_)
+      v->init_dependent();
+
+    topNodes_.clear();
+    hashMap_.clear();
+
+    while(!nodesBackward_.empty()) {
+      auto v = nodesBackward_.back();
+      nodesBackward_.pop_back();
+
+      for(auto&& child : v->children())
+        if(child->trainable())
+          child->set_zero_adjoint();
+
+      if(v->trainable())
+        v->backward();
+
+      v->children().clear();
+    }
+  }
+
+  template <typename... Args>
+  Expr param(std::string name, Shape shape, Args... args) {
+    if(!namespace_.empty())
+      name = namespace_ + "::" + name;
+
+    bool fixed = keywords::Get(keywords::fixed, false, args...);
+    auto p = params_->get(name);
+    if(p) {
+      ABORT_IF(shape != p->shape(), "Requested shape for existing parameter does not match original shape:", name);
+      p->setTrainable(!fixed);
+      add(p);
+      return p;
+    }
+    ABORT_IF(reloaded_, "Graph was reloaded and parameter is newly created:", name);
+
+    std::function<void(Tensor)> init = keywords::Get(keywords::init, std::function<void(Tensor)>([](Tensor) {}), args...);
+    p = Expression<ParamNode>(shared_from_this(), shape, init, fixed);
+    p->set_name(name);
+    params_->add(p, name);
+    return p;
+  }
+
+  template <typename... Args>
+  Expr constant(Shape shape, Args... args) {
+    std::function<void(Tensor)> init = keywords::Get(keywords::init, std::function<void(Tensor)>([](Tensor) {}), args...);
+    return Expression<ConstantNode>(shared_from_this(), shape, init);
+  }
+  Expr ones(Shape shape) { return constant(shape, keywords::init = inits::ones); }
+  Expr zeros(Shape shape) { return constant(shape, keywords::init = inits::zeros); }
+
+  // Constant whose content is a function of the current batch (indices, masks).
+  // `fill` writes shape.elements() floats into pinned staging; it is called now
+  // and again on every replay of a captured step with the next batch.
+  typedef std::function<void(const data::CorpusBatch&, float*)> BatchFillF;
+  typedef std::function<void(const data::CorpusBatch&, int*)> BatchFillI;
+  Expr batchConstant(Shape shape, BatchFillF fill, Ptr<data::CorpusBatch> batch);
+
+  // Device int32 index vector (embedding rows) uploaded through staging.  The
+  // returned piece is workspace memory; the caller frees it via allocator().
+  Ptr<MemoryPiece> uploadIndices(const std::vector<size_t>& indices);
+  Ptr<MemoryPiece> uploadIndices(size_t n, BatchFillI fill, Ptr<data::CorpusBatch> batch);
+
+  Expr dropout(float prob, Shape shape);
+
+  Expr get(std::string name) {
+    if(!namespace_.empty())
+      name = namespace_ + "::" + name;
+    return params_->get(name);
+  }
+
+  Ptr<Parameters>& params() { return params_; }
+
+  Expr add(Expr node) {
+    size_t hash = node->hash();
+    auto it = hashMap_.find(hash);
+    if(it != hashMap_.end()) {
+      for(auto foundWeak : it->second) {
+        auto found = foundWeak.lock();
+        if(found && node->equal(found))
+          return found;
+      }
+    }
+    hashMap_[hash].push_back(node);
+    node->setId(count_++);
+
+    nodesForward_.push_back(node);
+    if(!inferenceOnly_ && node->trainable()) {
+      nodesBackward_.push_back(node);
+      topNodes_.insert(node);
+    }
+    return node;
+  }
+
+  void remove_top_node(Expr node) { topNodes_.erase(node); }
+
+  void tensor(Tensor& t, const Shape& shape) { tensors_->allocate(t, shape); }
+  void free(Tensor& t) {
+    if(tensors_)
+      tensors_->free(t);
+  }
+  Ptr<Allocator> allocator() { return tensors_->allocator(); }
+
+  void clear() {
+    count_ = 0;
+    nodesForward_.clear();
+    nodesBackward_.clear();
+    topNodes_.clear();
+    hashMap_.clear();
+    if(tensors_)
+      tensors_->clear();
+    batchUploads_.clear();
+    staging_->reset();
+  }
+
+  void clearParameters() { params_->clear(); }
+  void setReloaded(bool reloaded) { reloaded_ = reloaded; }
+
+  // --- replay support --------------------------------------------------
+  std::vector<BatchUpload>& batchUploads() { return batchUploads_; }
+  Staging& staging() { return *staging_; }
+  // Hands the pinned staging (and the recorded uploads) of the current tape to
+  // a captured step; the graph continues with a fresh staging.
+  Ptr<Staging> detachStaging() {
+    auto s = staging_;
+    staging_ = New<Staging>();
+    return s;
+  }
+  size_t numNodes() const { return count_; }
+
+  struct StagingScope {
+    Staging* prev;
+    explicit StagingScope(Staging* s) : prev(currentStagingSlot()) { currentStagingSlot() = s; }
+    ~StagingScope() { currentStagingSlot() = prev; }
+  };
+
+private:
+  size_t count_{0};
+  std::list<Expr> nodesForward_;
+  std::list<Expr> nodesBackward_;
+  std::unordered_set<Expr> topNodes_;
+  Ptr<Parameters> params_;
+  Ptr<TensorAllocator> tensors_;
+  int device_{0};
+  Ptr<Backend> backend_;
+  std::unordered_map<size_t, std::vector<WExpr>> hashMap_;
+  bool inferenceOnly_{false};
+  bool reloaded_{false};
+  std::string namespace_;
+  Ptr<Staging> staging_{New<Staging>()};
+  std::vector<BatchUpload> batchUploads_;
+};
+
+template <class T, typename... Args>
+Expr Expression(Args&&... args) {
+  auto e = Expr(new T(std::forward<Args>(args)...));
+  return e->graph()->add(e);
+}
+
+}  // namespace marian

@@ -1,0 +1,193 @@
+// Chainable / Node / NaryNodeOp: one element of the define-by-run tape.
+//
+// API-compatible with the reference (src/graph/chainable.h:59-99,
+// src/graph/node.h:14-190): forwardOps()/backwardOps() return closures calling
+// the tensor operators; runBackward() skips non-trainable children; nodes are
+// hashed for common-subexpression elimination by (name, type, children ids
+// [+ op attributes]).  The boost::hash machinery is replaced by a local
+// hash_combine; graphviz/debug plumbing is reduced to what tests use.
+#pragma once
+
+#include <algorithm>
+#include <functional>
+#include <string>
+#include <vector>
+
+#include "common/definitions.h"
+#include "common/keywords.h"
+#include "common/shape.h"
+#include "tensors/tensor.h"
+
+namespace marian {
+
+#define NodeOp(op) [=]() { op; }
+typedef std::vector<std::function<void()>> NodeOps;
+
+class ExpressionGraph;
+class Backend;
+
+template <class T>
+inline void hash_combine(size_t& seed, const T& v) {
+  seed ^= std::hash<T>()(v) + 0x9e3779b97f4a7c15ULL + (seed << 6) + (seed >> 2);
+}
+
+template <class DataType>
+struct Chainable {
+  Chainable() {}
+  virtual ~Chainable() {}
+
+  virtual void forward() = 0;
+  virtual void backward() = 0;
+  virtual NodeOps forwardOps() = 0;
+  virtual NodeOps backwardOps() = 0;
+
+  virtual size_t allocate() = 0;
+  virtual void free() = 0;
+  virtual void init() = 0;
+  virtual void init_dependent() {}
+  virtual void set_zero_adjoint() {}
+  virtual bool trainable() = 0;
+  virtual void setTrainable(bool) = 0;
+
+  virtual void setId(size_t) = 0;
+  virtual size_t getId() = 0;
+
+  virtual Ptr<ExpressionGraph> graph() = 0;
+  virtual const Shape& shape() = 0;
+  virtual std::vector<Expr>& children() = 0;
+  virtual Expr child(size_t) = 0;
+  virtual DataType& val() = 0;
+  virtual DataType& grad() = 0;
+  virtual float scalar() = 0;
+
+  virtual const std::string type() = 0;
+  virtual void set_name(const std::string&) = 0;
+  virtual const std::string& name() const = 0;
+
+  virtual void debug(const std::string& message) = 0;
+  virtual bool marked_for_debug() = 0;
+  virtual const std::string& debug_message() = 0;
+
+  virtual size_t hash() = 0;
+  virtual bool equal(Expr) = 0;
+};
+
+class Node : public Chainable<Tensor>, public std::enable_shared_from_this<Node> {
+protected:
+  size_t id_{0};
+  bool trainable_{true};
+  bool destroy_{true};
+  std::vector<Expr> children_;
+  Weak<ExpressionGraph> graph_;
+  Shape shape_{1, 1, 1, 1};
+  std::string name_{"none"};
+  Tensor val_{nullptr};
+  Tensor adj_{nullptr};
+  bool markedForDebug_{false};
+  std::string debugMessage_;
+
+public:
+  Node(Ptr<ExpressionGraph> graph, const Shape& shape) : graph_(graph), shape_(shape) {}
+
+  virtual ~Node() {
+    if(destroy_)
+      free();
+  }
+
+  virtual float scalar();
+
+  virtual NodeOps forwardOps() { return {}; }
+  virtual NodeOps backwardOps() { return {}; }
+
+  virtual void runForward(const NodeOps& ops) {
+    for(auto&& op : ops)
+      op();
+  }
+  // Backward closure i belongs to child i and only runs if that child needs a
+  // gradient (reference: node.h:57-62).
+  virtual void runBackward(const NodeOps& ops) {
+    size_t i = 0;
+    for(auto&& op : ops)
+      if(child(i++)->trainable())
+        op();
+  }
+
+  virtual void forward() { runForward(forwardOps()); }
+  virtual void backward() { runBackward(backwardOps()); }
+
+  virtual bool trainable() { return trainable_; }
+  virtual void setTrainable(bool trainable) { trainable_ = trainable; }
+
+  virtual void setId(size_t id) { id_ = id; }
+  virtual size_t getId() { return id_; }
+
+  virtual Ptr<ExpressionGraph> graph() { return graph_.lock(); }
+
+  virtual void debug(const std::string& message) {
+    debugMessage_ = message;
+    markedForDebug_ = true;
+  }
+  virtual bool marked_for_debug() { return markedForDebug_; }
+  virtual const std::string& debug_message() { return debugMessage_; }
+
+  virtual size_t allocate();
+  virtual void free();
+  virtual void init() {}
+  virtual void init_dependent();
+  virtual void set_zero_adjoint();
+
+  virtual Tensor& val() { return val_; }
+  virtual Tensor& grad() { return adj_; }
+  virtual const Shape& shape() { return shape_; }
+
+  void set_name(const std::string& name) { name_ = name; }
+  const std::string& name() const { return name_; }
+
+  virtual std::vector<Expr>& children() { return children_; }
+  virtual Expr child(size_t i) { return children_[i]; }
+
+  Ptr<Backend> getBackend();
+};
+
+struct NaryNodeOp : public Node {
+  size_t hash_{0};
+
+  NaryNodeOp(const std::vector<Expr>& nodes, const Shape& shape) : Node(nodes.front()->graph(), shape) {
+    setup(nodes);
+  }
+  // default shape: the first child's
+  explicit NaryNodeOp(const std::vector<Expr>& nodes) : Node(nodes.front()->graph(), nodes.front()->shape()) {
+    setup(nodes);
+  }
+
+  virtual ~NaryNodeOp() {}
+
+  virtual size_t hash() {
+    if(!hash_) {
+      size_t seed = std::hash<std::string>()(name());
+      hash_combine(seed, type());
+      for(size_t i = 0; i < children_.size(); ++i)
+        hash_combine(seed, child(i)->hash());
+      hash_ = seed;
+    }
+    return hash_;
+  }
+
+  virtual bool equal(Expr node) {
+    if(type() != node->type())
+      return false;
+    if(name() != node->name())
+      return false;
+    if(children().size() != node->children().size())
+      return false;
+    for(size_t i = 0; i < children().size(); ++i)
+      if(children()[i]->getId() != node->children()[i]->getId())
+        return false;
+    return true;
+  }
+
+private:
+  void setup(const std::vector<Expr>& nodes);
+};
+
+}  // namespace marian

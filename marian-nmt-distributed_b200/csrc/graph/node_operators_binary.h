@@ -1,0 +1,315 @@
+// Multi-input graph nodes.  Forward/backward formulas follow the reference's
+// src/graph/node_operators_binary.h (cited per class).
+#pragma once
+
+#include "graph/backend.h"
+#include "graph/expression_graph.h"
+#include "graph/node.h"
+#include "kernels/tensor_operators.h"
+
+namespace marian {
+
+namespace detail {
+inline Shape dotShape(Expr a, Expr b, bool transA, bool transB) {
+  auto shapeA = a->shape();
+  if(transA) {
+    shapeA.set(-2, a->shape()[-1]);
+    shapeA.set(-1, a->shape()[-2]);
+  }
+  auto shapeB = b->shape();
+  if(transB) {
+    shapeB.set(-2, b->shape()[-1]);
+    shapeB.set(-1, b->shape()[-2]);
+  }
+  Shape outShape = shapeA;
+  outShape.set(-1, shapeB[-1]);
+  ABORT_IF(shapeA[-1] != shapeB[-2], "matrix product requires dimensions to match", shapeA.toString(), shapeB.toString());
+  return outShape;
+}
+}  // namespace detail
+
+// C = scalar * op(A) op(B); all leading dims of A flattened into rows.
+// reference: node_operators_binary.h:13-157.  The four backward transpose cases
+// are generated from one table instead of four copies.
+class DotNodeOp : public NaryNodeOp {
+protected:
+  bool transA_;
+  bool transB_;
+  float scalar_;
+
+  virtual void prod(Tensor C, Tensor A, Tensor B, bool tA, bool tB, float beta) {
+    Prod(getBackend()->getGemmHandle(), C, A, B, tA, tB, beta, scalar_);
+  }
+
+public:
+  DotNodeOp(Expr a, Expr b, bool transA, bool transB, float scalar)
+      : NaryNodeOp({a, b}, detail::dotShape(a, b, transA, transB)), transA_(transA), transB_(transB), scalar_(scalar) {}
+
+  NodeOps forwardOps() { return {NodeOp(prod(val_, child(0)->val(), child(1)->val(), transA_, transB_, 0.f))}; }
+
+  NodeOps backwardOps() {
+    // D = adj, A = child0, B = child1
+    if(!transA_ && transB_)   // C = A B^T : dA += D B ; dB += D^T A
+      return {NodeOp(prod(child(0)->grad(), adj_, child(1)->val(), false, false, 1.f)),
+              NodeOp(prod(child(1)->grad(), adj_, child(0)->val(), true, false, 1.f))};
+    if(transA_ && !transB_)   // C = A^T B : dA += B D^T ; dB += A D
+      return {NodeOp(prod(child(0)->grad(), child(1)->val(), adj_, false, true, 1.f)),
+              NodeOp(prod(child(1)->grad(), child(0)->val(), adj_, false, false, 1.f))};
+    if(transA_ && transB_)    // C = A^T B^T : dA += B^T D^T ; dB += D^T A^T
+      return {NodeOp(prod(child(0)->grad(), child(1)->val(), adj_, true, true, 1.f)),
+              NodeOp(prod(child(1)->grad(), adj_, child(0)->val(), true, true, 1.f))};
+    // C = A B : dA += D B^T ; dB += A^T D
+    return {NodeOp(prod(child(0)->grad(), adj_, child(1)->val(), false, true, 1.f)),
+            NodeOp(prod(child(1)->grad(), child(0)->val(), adj_, true, false, 1.f))};
+  }
+
+  virtual size_t hash() {
+    if(!hash_) {
+      hash_ = NaryNodeOp::hash();
+      hash_combine(hash_, transA_);
+      hash_combine(hash_, transB_);
+      hash_combine(hash_, scalar_);
+    }
+    return hash_;
+  }
+  virtual bool equal(Expr node) {
+    if(!NaryNodeOp::equal(node))
+      return false;
+    auto cnode = std::dynamic_pointer_cast<DotNodeOp>(node);
+    return cnode && transA_ == cnode->transA_ && transB_ == cnode->transB_ && scalar_ == cnode->scalar_;
+  }
+  const std::string type() { return "dot"; }
+};
+
+// Batched over the leading dims (attention scores / contexts).
+// reference: node_operators_binary.h:221-369
+class DotBatchedNodeOp : public DotNodeOp {
+protected:
+  virtual void prod(Tensor C, Tensor A, Tensor B, bool tA, bool tB, float beta) {
+    ProdBatched(getBackend()->getGemmHandle(), C, A, B, tA, tB, beta, scalar_);
+  }
+
+public:
+  DotBatchedNodeOp(Expr a, Expr b, bool transA, bool transB, float scalar) : DotNodeOp(a, b, transA, transB, scalar) {}
+  const std::string type() { return "bdot"; }
+};
+
+// x W + b.  reference: :159-218 (Prod, then Add(_1, val, bias) as a 2nd kernel;
+// here the bias is applied in the GEMM epilogue).  Backward: dx += D W^T,
+// dW += x^T D, db += column sums of D.
+struct AffineNodeOp : public NaryNodeOp {
+  AffineNodeOp(const std::vector<Expr>& nodes) : NaryNodeOp(nodes, newShape(nodes)) {}
+
+  static Shape newShape(const std::vector<Expr>& nodes) {
+    Shape shape1 = nodes[0]->shape();
+    Shape shape2 = nodes[1]->shape();
+    ABORT_IF(shape1[-1] != shape2[-2], "matrix product requires dimensions to match");
+    shape1.set(-1, shape2[-1]);
+    return shape1;
+  }
+
+  NodeOps forwardOps() {
+    return {NodeOp(ProdAffine(getBackend()->getGemmHandle(), val_, child(0)->val(), child(1)->val(), child(2)->val()))};
+  }
+  NodeOps backwardOps() {
+    using namespace functional;
+    return {NodeOp(Prod(getBackend()->getGemmHandle(), child(0)->grad(), adj_, child(1)->val(), false, true, 1.0)),
+            NodeOp(Prod(getBackend()->getGemmHandle(), child(1)->grad(), child(0)->val(), adj_, true, false, 1.0)),
+            NodeOp(Add(_1, child(2)->grad(), adj_))};
+  }
+  const std::string type() { return "affine"; }
+};
+
+// sum_axis(a * b).  reference: :371-404
+struct ScalarProductNodeOp : public NaryNodeOp {
+  ScalarProductNodeOp(Expr a, Expr b, keywords::axis_k ax) : NaryNodeOp({a, b}, newShape(a, b, ax.value)) {}
+  static Shape newShape(Expr a, Expr b, int ax) {
+    Shape full = Shape::broadcast({a, b});
+    full.set(full.axis(ax), 1);
+    return full;
+  }
+  NodeOps forwardOps() {
+    using namespace functional;
+    return {NodeOp(Reduce(_1 * _2, val_, child(0)->val(), child(1)->val()))};
+  }
+  NodeOps backwardOps() {
+    using namespace functional;
+    return {NodeOp(Add(_1 * _2, child(0)->grad(), child(1)->val(), adj_)),
+            NodeOp(Add(_1 * _2, child(1)->grad(), child(0)->val(), adj_))};
+  }
+  const std::string type() { return "scalar-product"; }
+};
+
+struct ElementBinaryNodeOp : public NaryNodeOp {
+  ElementBinaryNodeOp(Expr a, Expr b) : NaryNodeOp({a, b}, Shape::broadcast({a, b})) {}
+};
+
+// reference: :418-436
+struct PlusNodeOp : public ElementBinaryNodeOp {
+  PlusNodeOp(Expr a, Expr b) : ElementBinaryNodeOp(a, b) {}
+  NodeOps forwardOps() {
+    using namespace functional;
+    return {NodeOp(Element(_1 = _2 + _3, val_, child(0)->val(), child(1)->val()))};
+  }
+  NodeOps backwardOps() {
+    using namespace functional;
+    return {NodeOp(Add(_1, child(0)->grad(), adj_)), NodeOp(Add(_1, child(1)->grad(), adj_))};
+  }
+  const std::string type() { return "+"; }
+};
+
+// reference: :438-456
+struct MinusNodeOp : public ElementBinaryNodeOp {
+  MinusNodeOp(Expr a, Expr b) : ElementBinaryNodeOp(a, b) {}
+  NodeOps forwardOps() {
+    using namespace functional;
+    return {NodeOp(Element(_1 = _2 - _3, val_, child(0)->val(), child(1)->val()))};
+  }
+  NodeOps backwardOps() {
+    using namespace functional;
+    return {NodeOp(Add(_1, child(0)->grad(), adj_)), NodeOp(Add(-_1, child(1)->grad(), adj_))};
+  }
+  const std::string type() { return "-"; }
+};
+
+// reference: :458-476
+struct MultNodeOp : public ElementBinaryNodeOp {
+  MultNodeOp(Expr a, Expr b) : ElementBinaryNodeOp(a, b) {}
+  NodeOps forwardOps() {
+    using namespace functional;
+    return {NodeOp(Element(_1 = _2 * _3, val_, child(0)->val(), child(1)->val()))};
+  }
+  NodeOps backwardOps() {
+    using namespace functional;
+    return {NodeOp(Add(_1 * _2, child(0)->grad(), adj_, child(1)->val())),
+            NodeOp(Add(_1 * _2, child(1)->grad(), adj_, child(0)->val()))};
+  }
+  const std::string type() { return "x"; }
+};
+
+// reference: :478-505
+struct DivNodeOp : public ElementBinaryNodeOp {
+  DivNodeOp(Expr a, Expr b) : ElementBinaryNodeOp(a, b) {}
+  NodeOps forwardOps() {
+    using namespace functional;
+    return {NodeOp(Element(_1 = _2 / _3, val_, child(0)->val(), child(1)->val()))};
+  }
+  NodeOps backwardOps() {
+    using namespace functional;
+    return {NodeOp(Add(_1 * 1.0f / _2, child(0)->grad(), adj_, child(1)->val())),
+            NodeOp(Add(-_1 * _2 / (_3 * _3), child(1)->grad(), adj_, child(0)->val(), child(1)->val()))};
+  }
+  const std::string type() { return "/"; }
+};
+
+// -log softmax(a)[b] per row; labels are a float tensor.  reference: :531-553
+struct CrossEntropyNodeOp : public NaryNodeOp {
+  CrossEntropyNodeOp(Expr a, Expr b) : NaryNodeOp({a, b}, newShape(a)) {}
+  static Shape newShape(Expr a) {
+    Shape shape1 = a->shape();
+    shape1.set(-1, 1);
+    return shape1;
+  }
+  NodeOps forwardOps() { return {NodeOp(CrossEntropyPick(val_, child(0)->val(), child(1)->val()))}; }
+  NodeOps backwardOps() {
+    return {NodeOp(CrossEntropyPickBackward(child(0)->grad(), adj_, child(0)->val(), child(1)->val()))};
+  }
+  const std::string type() { return "x-ent"; }
+};
+
+// reference: :555-613.  backward() zeroes the child adjoints itself and
+// Deconcatenate ASSIGNS (kept as is).
+struct ConcatenateNodeOp : public NaryNodeOp {
+  ConcatenateNodeOp(const std::vector<Expr>& nodes, keywords::axis_k ax)
+      : NaryNodeOp(nodes, newShape(nodes, ax.value)), ax_(nodes.back()->shape().axis(ax.value)) {}
+
+  static Shape newShape(const std::vector<Expr>& nodes, int ax) {
+    Shape shape = nodes.back()->shape();
+    int a = shape.axis(ax);
+    int sum = 0;
+    for(auto child : nodes)
+      sum += child->shape()[a];
+    shape.set(a, sum);
+    return shape;
+  }
+
+  void forward() {
+    std::vector<Tensor> concatenees;
+    for(size_t i = 0; i < children_.size(); ++i)
+      concatenees.push_back(child(i)->val());
+    Concatenate(val_, concatenees, ax_);
+  }
+  void backward() {
+    std::vector<Tensor> deconcatenees;
+    for(size_t i = 0; i < children_.size(); ++i) {
+      auto childPtr = child(i);
+      childPtr->set_zero_adjoint();
+      deconcatenees.push_back(childPtr->grad());
+    }
+    Deconcatenate(deconcatenees, adj_, ax_);
+  }
+
+  virtual size_t hash() {
+    if(!hash_) {
+      hash_ = NaryNodeOp::hash();
+      hash_combine(hash_, ax_);
+    }
+    return hash_;
+  }
+  virtual bool equal(Expr node) {
+    if(!NaryNodeOp::equal(node))
+      return false;
+    auto cnode = std::dynamic_pointer_cast<ConcatenateNodeOp>(node);
+    return cnode && ax_ == cnode->ax_;
+  }
+  const std::string type() { return "concat"; }
+  int ax_;
+};
+
+// reference: :657-688.  ONE backward closure guarded by child(0) (the input);
+// gamma/beta gradients are produced by the same kernel.
+struct LayerNormalizationOp : public NaryNodeOp {
+  LayerNormalizationOp(const std::vector<Expr>& nodes, float eps = 1e-9) : NaryNodeOp(nodes), eps_(eps) {}
+
+  NodeOps forwardOps() {
+    return {NodeOp(LayerNormalization(
+        val_, child(0)->val(), child(1)->val(), (children_.size() == 3) ? child(2)->val() : nullptr, eps_))};
+  }
+  NodeOps backwardOps() {
+    return {NodeOp(LayerNormalizationGrad(child(0)->grad(),
+                                          child(1)->grad(),
+                                          (children_.size() == 3) ? child(2)->grad() : nullptr,
+                                          adj_,
+                                          val_,
+                                          child(0)->val(),
+                                          child(1)->val(),
+                                          (children_.size() == 3) ? child(2)->val() : nullptr,
+                                          eps_))};
+  }
+  virtual size_t hash() {
+    if(!hash_) {
+      hash_ = NaryNodeOp::hash();
+      hash_combine(hash_, eps_);
+    }
+    return hash_;
+  }
+  const std::string type() { return "layer_normalization"; }
+
+private:
+  float eps_;
+};
+
+// sigma(t)*y + (1-sigma(t))*x.  reference: :690-709 (backward assigns)
+struct HighwayNodeOp : public NaryNodeOp {
+  HighwayNodeOp(const std::vector<Expr>& nodes) : NaryNodeOp(nodes) {}
+  NodeOps forwardOps() {
+    return {NodeOp(HighwayForward(val_, child(0)->val(), child(1)->val(), child(2)->val()))};
+  }
+  NodeOps backwardOps() {
+    return {NodeOp(HighwayBackward(
+        child(0)->grad(), child(1)->grad(), child(2)->grad(), child(0)->val(), child(1)->val(), child(2)->val(), adj_))};
+  }
+  const std::string type() { return "highway"; }
+};
+
+}  // namespace marian

@@ -1,0 +1,127 @@
+// THE DROP-IN BOUNDARY of the hot path: the tensor operators every graph node,
+// optimizer and graph group is written against.
+//
+// Names, argument order and semantics follow the reference's
+// src/kernels/tensor_operators.h:19-397 (+ src/kernels/dropout.h:10-12):
+// forward operators overwrite `out`, backward operators accumulate (+=) into
+// their gradient outputs EXCEPT TransposeND, Shift, HighwayBackward and
+// Deconcatenate, which assign.  Implementations:
+//   * product build: hand-written sm_100a CUDA in csrc/kernels/*.cu, all
+//     asynchronous on device::currentStream();
+//   * test oracle:   oracle/cpu/tensor_operators_cpu.cpp (CPU restatement).
+// The element-wise templates Element/Add/Reduce live in kernels/element.h
+// (the oracle shadows that header with host loops).
+//
+// The flat C ABI over the same kernels is include/marian_b200.h.
+#pragma once
+
+#include <vector>
+
+#include "common/definitions.h"
+#include "common/shape.h"
+#include "functional/functional.h"
+#include "tensors/allocator.h"
+#include "tensors/tensor.h"
+
+namespace marian {
+
+// GEMM context: replaces the cublasHandle_t argument of the reference's
+// Prod/ProdBatched (tensor_operators.h:295-311).  Owns the arithmetic mode and
+// the scratch for bf16-packed operands.
+enum class GemmMode : int {
+  FP32 = 0,    // fp32 SIMT contraction (exact-mode, used for 1e-4 parity runs)
+  BF16 = 1,    // tcgen05 bf16 operands, fp32 accumulate in TMEM (throughput mode)
+  BF16X3 = 2,  // tcgen05 with hi/lo bf16 split operands (3 products), ~fp32 accuracy
+};
+struct GemmContext;
+typedef GemmContext* GemmHandle;
+GemmHandle createGemmContext(int deviceId);
+void destroyGemmContext(GemmHandle);
+void setGemmMode(GemmHandle, GemmMode);
+GemmMode getGemmMode(GemmHandle);
+// Packed-operand cache: bf16 copies of GEMM operands are keyed by (pointer,
+// layout) and reused until invalidated; the graph invalidates at the start of
+// forward and after the optimizer step.
+void gemmInvalidateCache(GemmHandle);
+
+bool IsNan(Tensor in);
+
+void TransposeND(Tensor out, Tensor in, const std::vector<int>& vAxis);
+
+void Select(Ptr<Allocator> allocator, Tensor out, Tensor in, int axis, const std::vector<size_t>&);
+void Insert(Ptr<Allocator> allocator, Tensor out, Tensor in, int axis, const std::vector<size_t>&);
+
+void Concatenate(Tensor out, const std::vector<Tensor>& inputs, int ax);
+void Deconcatenate(std::vector<Tensor>& outputs, const Tensor in, int ax);
+
+float L2Norm(Tensor in);
+// Asynchronous variant: writes sum(x^2) (NOT the root) to a device scalar.
+void SumSquares(Tensor outScalar, Tensor in);
+
+void Softmax(Tensor out, Tensor in, Tensor mask = nullptr);
+void LogSoftmax(Tensor out, Tensor in);
+void SoftmaxGrad(Tensor grad, Tensor adj, Tensor val);
+void LogSoftmaxGrad(Tensor grad, Tensor adj, Tensor val);
+
+void CrossEntropyPick(Tensor out, Tensor in, Tensor pick);
+void CrossEntropyPickBackward(Tensor out, Tensor adj, Tensor a, Tensor pick);
+
+void Prod(GemmHandle handle, Tensor C, const Tensor A, const Tensor B, bool transA, bool transB, float beta = 0, float scalar = 1);
+void ProdBatched(GemmHandle handle, Tensor C, const Tensor A, const Tensor B, bool transA, bool transB, float beta = 0, float scalar = 1);
+// Affine = Prod + bias row broadcast in the GEMM epilogue (the reference's
+// AffineNodeOp issues Prod then Add(_1, val, bias): node_operators_binary.h:172-186).
+void ProdAffine(GemmHandle handle, Tensor C, const Tensor A, const Tensor B, const Tensor bias);
+
+// The reference takes std::vector<size_t> and cudaMallocs a device copy per
+// call (tensor_operators.cu:679-746).  Here indices are int32 in device memory
+// (uploaded once per graph through pinned staging); the vector overloads
+// upload and forward.
+void CopyRows(Tensor out, const Tensor in, const int* deviceIndices, size_t n);
+void PasteRows(Tensor out, const Tensor in, const int* deviceIndices, size_t n);
+void CopyRows(Tensor out, const Tensor in, const std::vector<size_t>& indices);
+void PasteRows(Tensor out, const Tensor in, const std::vector<size_t>& indices);
+void CopyCols(Tensor out, const Tensor in, const std::vector<size_t>& indices);
+void PasteCols(Tensor out, const Tensor in, const std::vector<size_t>& indices);
+
+void LSTMCellForward(Tensor out, std::vector<Tensor> inputs);
+void LSTMOutputForward(Tensor out, std::vector<Tensor> inputs);
+void LSTMCellBackward(std::vector<Tensor> outputs, std::vector<Tensor> inputs, Tensor adj);
+void LSTMOutputBackward(std::vector<Tensor> outputs, std::vector<Tensor> inputs, Tensor adj);
+
+void GRUFastForward(Tensor out, std::vector<Tensor> inputs, bool final = false);
+void GRUFastBackward(std::vector<Tensor> outputs, std::vector<Tensor> inputs, Tensor adj, bool final = false);
+
+void Att(Tensor out, Tensor va, Tensor context, Tensor state);
+void AttBack(Tensor gva, Tensor gContext, Tensor gState, Tensor va, Tensor context, Tensor state, Tensor adj);
+
+void LayerNormalization(Tensor out, Tensor in, Tensor gamma, Tensor beta, float eps = 1e-9);
+void LayerNormalizationGrad(Tensor gradX, Tensor gradGamma, Tensor gradBeta, Tensor adj, Tensor y, Tensor x, Tensor gamma, Tensor beta, float eps = 1e-9);
+
+void Shift(Tensor out, Tensor in, Shape shift, bool invert = false);
+
+void HighwayForward(Tensor out, const Tensor in1, const Tensor in2, const Tensor t);
+void HighwayBackward(Tensor out1, Tensor out2, Tensor outt, const Tensor in1, const Tensor in2, const Tensor t, const Tensor adj);
+
+// Inverted-dropout mask: Bernoulli(1-p)/(1-p) (reference: kernels/dropout.cu:34-42,
+// cuRAND XORWOW there; here a counter-based Philox-style hash keyed by `seed`).
+void Dropout(Tensor mask, float dropProb, uint64_t seed);
+
+// Fused optimizer kernels over flat parameter tensors (reference:
+// src/optimizers/optimizers.cu:7-73 issues 1-3 Element passes per update and
+// clippers.cu:12-17 a separate norm + scale pass).
+// gradScale is applied to every gradient element as it is read (clipping and/or
+// 1/N averaging); when `normSq` is given the clip factor is computed ON DEVICE
+// from *normSq: scale = gradScale * min(1, clipNorm / sqrt(*normSq * gradScale^2)).
+struct AdamArgs {
+  float eta, beta1, beta2, eps;
+  float denom1, denom2;  // 1 - beta1^t, 1 - beta2^t
+  float gradScale;       // multiplies every gradient before use
+  float clipNorm;        // <= 0: no clipping
+};
+void AdamUpdate(Tensor params, Tensor grads, Tensor mt, Tensor vt, const AdamArgs& args, Tensor normSq = nullptr);
+void SgdUpdate(Tensor params, Tensor grads, float eta, float gradScale, float clipNorm, Tensor normSq = nullptr);
+void AdagradUpdate(Tensor params, Tensor grads, Tensor gt, float eta, float eps, float gradScale, float clipNorm, Tensor normSq = nullptr);
+
+}  // namespace marian
+
+#include "kernels/element.h"

@@ -1,0 +1,68 @@
+// Device memory + stream services used by the host engine.
+//
+// The reference hard-wires cudaMalloc/cudaMemcpy + cudaStreamSynchronize(0)
+// into TensorBase and DeviceGPU (src/tensors/tensor.cu:21-74,
+// src/tensors/device_gpu.cu:17-36).  Here every device interaction of the
+// host engine goes through this small interface so that
+//   * the product build (device_gpu.cu) issues everything asynchronously on
+//     ONE explicit stream, which makes a whole training step capturable into
+//     a CUDA graph, and
+//   * the test oracle (oracle/cpu/device_cpu.cpp) can link the same host
+//     graph code against plain host memory.
+#pragma once
+
+#include <cstddef>
+#include <cstdint>
+
+namespace marian {
+namespace device {
+
+// Selects the CUDA device for the calling thread (no-op on the CPU oracle).
+void setDevice(int deviceId);
+int getDevice();
+
+// The stream all engine work of the calling thread is issued on.  The product
+// build returns a cudaStream_t (as void*).  setStream(nullptr) restores the
+// engine-owned stream.
+void* currentStream();
+void setStream(void* stream);
+
+void* mallocDevice(size_t bytes);
+void freeDevice(void* p);
+void* mallocPinned(size_t bytes);
+void freePinned(void* p);
+
+// All asynchronous on currentStream().  `src` of copyH2D must be pinned memory
+// that stays valid until the copy ran (see tensors/staging.h).
+void copyH2D(void* dst, const void* pinnedSrc, size_t bytes);
+void copyD2H(void* pinnedDst, const void* src, size_t bytes);
+void copyD2D(void* dst, const void* src, size_t bytes);
+void zero(void* dst, size_t bytes);
+void fill(float* dst, float value, size_t n);
+
+// Blocks the host until currentStream() is drained.
+void synchronize();
+
+// True while currentStream() is being captured into a CUDA graph; host code
+// uses it to refuse operations that need a host round-trip.
+bool capturing();
+
+// Blocking upload from pageable host memory (large one-off initialisations).
+void copyH2DBlocking(void* dst, const void* src, size_t bytes);
+
+// ---- whole-step capture (CUDA graphs) -----------------------------------
+// captureSupported() is false on the CPU oracle.  beginCapture() starts
+// recording everything issued on currentStream(); endCapture() returns an
+// executable graph handle (nullptr if recording failed, the work was then NOT
+// executed and the caller must run it eagerly).
+bool captureSupported();
+void beginCapture();
+void* endCapture();
+void launchGraph(void* exec);
+void destroyGraph(void* exec);
+
+// "cuda" for the product, "cpu-oracle" for the test oracle.
+const char* backendName();
+
+}  // namespace device
+}  // namespace marian

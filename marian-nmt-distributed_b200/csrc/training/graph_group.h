@@ -1,0 +1,224 @@
+// Graph groups: one training update = forward, backward, gradient exchange,
+// optimizer step.
+//
+// SingletonGraph follows the reference's src/training/graph_group_singleton.cu:21-66.
+// SyncGraphGroup is the data-parallel group of src/training/graph_group_sync.cu:42-188
+// re-cut for ONE PROCESS PER GPU: each rank owns one ExpressionGraph and the
+// parameter shard `rank` (shardSize = total/N on the padded arena) with its own
+// optimizer state.  An update is
+//     computeGradients(batch_rank)             forward+backward (CUDA-graph replay)
+//     reduce-scatter(sum) of the flat gradient arena      [exchange, see below]
+//     updateShard()      fused {x 1/N, shard-norm clip, Adam} on the owned shard
+//     all-gather of the flat parameter arena              [exchange]
+// which is the reference's gather/add/update/scatter loop (:125-151) expressed
+// as collectives.  The exchange itself is injected (ShardExchange): the product
+// harness drives NCCL through torch.distributed on the engine stream, tests
+// drive gloo over the CPU oracle - the group logic is the same code.
+// Kept reference semantics: gradients are divided by N regardless of per-rank
+// sentence counts; clipping uses the SHARD's norm; cost is the mean over ranks.
+#pragma once
+
+#include "data/batch.h"
+#include "graph/expression_graph.h"
+#include "models/model_factory.h"
+#include "optimizers/optimizers.h"
+#include "training/graph_replay.h"
+
+namespace marian {
+
+class GraphGroup {
+protected:
+  Ptr<Options> options_;
+  Ptr<OptimizerBase> opt_;
+
+public:
+  GraphGroup(Ptr<Options> options) : options_(options), opt_(Optimizer(options)) {}
+  virtual ~GraphGroup() {}
+  virtual void update(Ptr<data::CorpusBatch>) = 0;
+  virtual float cost() = 0;
+};
+
+// forward + backward of one batch on one graph, eagerly or by graph replay
+class GradientWorker {
+public:
+  GradientWorker(Ptr<Options> options, int device) {
+    graph_ = New<ExpressionGraph>();
+    graph_->setDevice(device);
+    graph_->reserveWorkspaceMB(options->get<size_t>("workspace"));
+    builder_ = models::from_options(options);
+    pinnedCost_ = (float*)device::mallocPinned(sizeof(float));
+    *pinnedCost_ = 0.f;
+    replay_.setEnabled(options->get<bool>("graph-replay", true));
+  }
+  ~GradientWorker() {
+    replay_.clear();
+    device::freePinned(pinnedCost_);
+  }
+
+  Ptr<ExpressionGraph> graph() { return graph_; }
+  Ptr<EncoderDecoder> builder() { return builder_; }
+  StepReplay& replay() { return replay_; }
+
+  // Enqueues forward+backward on the engine stream; cost lands in pinned memory.
+  void computeGradients(Ptr<data::CorpusBatch> batch, bool keepLogits = false) {
+    device::setDevice((int)graph_->getDevice());
+    auto key = batch->shapeKey();
+    if(!keepLogits) {
+      if(auto plan = replay_.find(key)) {
+        replay_.replay(*plan, *batch);
+        lastReplayed_ = true;
+        return;
+      }
+    }
+    lastReplayed_ = false;
+    bool capture = !keepLogits && replay_.shouldCapture(key);
+    auto costNode = builder_->build(graph_, batch);
+    if(capture)
+      device::beginCapture();
+    graph_->forward();
+    device::copyD2H(pinnedCost_, costNode->val()->data(), sizeof(float));
+    if(keepLogits)
+      logits_ = builder_->lastLogits();
+    graph_->backward();
+    if(capture) {
+      void* exec = device::endCapture();
+      ABORT_IF(!exec, "CUDA graph capture of the training step failed");
+      auto& plan = replay_.store(key, exec, graph_);
+      device::launchGraph(plan.exec);
+      plan.launches++;
+    }
+  }
+
+  // Blocks until the enqueued work is done and returns the batch cost.
+  float cost() {
+    device::setDevice((int)graph_->getDevice());
+    device::synchronize();
+    return *pinnedCost_;
+  }
+
+  Expr logits() { return logits_; }
+  bool lastStepReplayed() const { return lastReplayed_; }
+
+private:
+  Ptr<ExpressionGraph> graph_;
+  Ptr<EncoderDecoder> builder_;
+  StepReplay replay_;
+  float* pinnedCost_;
+  Expr logits_;
+  bool lastReplayed_{false};
+};
+
+class SingletonGraph : public GraphGroup {
+public:
+  SingletonGraph(Ptr<Options> options, int device = 0) : GraphGroup(options), worker_(options, device) {}
+
+  void update(Ptr<data::CorpusBatch> batch) {
+    worker_.computeGradients(batch);
+    opt_->update(worker_.graph());
+  }
+  float cost() { return worker_.cost(); }
+
+  GradientWorker& worker() { return worker_; }
+  Ptr<OptimizerBase> optimizer() { return opt_; }
+
+private:
+  GradientWorker worker_;
+};
+
+// Injected collective step of SyncGraphGroup (NCCL in the product harness, gloo
+// in CPU tests, or in-process loops for single-process multi-rank simulation).
+struct ShardExchange {
+  virtual ~ShardExchange() {}
+  // sum over ranks of flatGrads[rank*shard .. +shard) into shardOut on each rank
+  virtual void reduceScatter(float* flatGrads, float* shardOut, size_t shardElements) = 0;
+  // every rank's flatParams[rank*shard .. +shard) to all ranks, in place
+  virtual void allGather(float* flatParams, size_t shardElements) = 0;
+  // rank 0's buffer to all ranks
+  virtual void broadcast(float* flat, size_t elements) = 0;
+  virtual float meanCost(float localCost) = 0;
+};
+
+class SyncGraphGroup : public GraphGroup {
+public:
+  SyncGraphGroup(Ptr<Options> options, int device, int rank, int nranks, Ptr<ShardExchange> exchange = nullptr)
+      : GraphGroup(options), worker_(options, device), rank_(rank), nranks_(nranks), exchange_(exchange) {
+    worker_.graph()->params()->setShardCount(nranks);
+  }
+
+  void setExchange(Ptr<ShardExchange> e) { exchange_ = e; }
+
+  // `batch` is this rank's part: batch->split(N)[rank] of the global batch
+  // (reference :43), or a full per-rank batch for weak scaling.
+  void update(Ptr<data::CorpusBatch> batch) {
+    ABORT_IF(!exchange_, "SyncGraphGroup::update needs a ShardExchange");
+    computeGradients(batch);
+    if(first_) {
+      // reference :46-53: all replicas start from graph 0's parameters
+      exchange_->broadcast(flatParams()->data(), flatParams()->size());
+      first_ = false;
+    }
+    exchange_->reduceScatter(flatGrads()->data(), shardGrads()->data(), shardSize());
+    updateShard();
+    exchange_->allGather(flatParams()->data(), shardSize());
+  }
+
+  // --- the phases, individually callable so a host harness can interleave its
+  //     own collectives (bench.py / tests drive torch.distributed here) -------
+  void computeGradients(Ptr<data::CorpusBatch> batch) {
+    worker_.computeGradients(batch);
+    ensureShard();
+  }
+
+  // fused {x 1/N, clip by shard norm, optimizer} on params[rank*shard ..) using
+  // the summed gradient shard in shardGrads()
+  void updateShard() {
+    ensureShard();
+    auto p = flatParams()->subtensor((int)(rank_ * shardSize_), (int)shardSize_);
+    opt_->update(p, shardGrads_, 1.f, 1.f / (float)nranks_);
+    gemmInvalidateCache(worker_.graph()->getBackend()->getGemmHandle());
+  }
+
+  float cost() {
+    float c = worker_.cost();
+    return exchange_ ? exchange_->meanCost(c) : c;
+  }
+  float localCost() { return worker_.cost(); }
+
+  Tensor flatParams() { return worker_.graph()->params()->vals(); }
+  Tensor flatGrads() { return worker_.graph()->params()->grads(); }
+  Tensor shardGrads() {
+    ensureShard();
+    return shardGrads_;
+  }
+  size_t shardSize() {
+    ensureShard();
+    return shardSize_;
+  }
+  int rank() const { return rank_; }
+  int nranks() const { return nranks_; }
+  GradientWorker& worker() { return worker_; }
+  Ptr<OptimizerBase> optimizer() { return opt_; }
+
+private:
+  void ensureShard() {
+    if(shardGrads_)
+      return;
+    size_t total = flatParams()->size();
+    ABORT_IF(total % nranks_ != 0, "parameter arena is not divisible into shards");
+    shardSize_ = total / nranks_;
+    shardAlloc_ = New<TensorAllocator>((int)worker_.graph()->getDevice());
+    shardAlloc_->reserveExact(shardSize_ * sizeof(float));
+    shardAlloc_->allocate(shardGrads_, Shape{1, (int)shardSize_});
+    shardGrads_->set(0);
+  }
+
+  GradientWorker worker_;
+  int rank_, nranks_;
+  Ptr<ShardExchange> exchange_;
+  bool first_{true};
+  size_t shardSize_{0};
+  Ptr<TensorAllocator> shardAlloc_;
+  Tensor shardGrads_;
+};
+
+}  // namespace marian

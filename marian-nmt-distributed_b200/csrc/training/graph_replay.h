@@ -1,0 +1,87 @@
+// Whole-step CUDA-graph capture and replay.
+//
+// The reference rebuilds the tape and launches ~1.5k kernels (plus hundreds of
+// stream syncs) for every batch (SURVEY.md section 7 "hard parts").  The tape
+// topology and every buffer address only depend on the batch SHAPE: the model
+// code is deterministic, the workspace arena never moves and is reset before
+// each build.  So the first time a shape is seen after parameters exist, the
+// forward+backward sweep is recorded into a CUDA graph; afterwards a step is
+//   refill pinned staging with the new batch  ->  one cudaGraphLaunch.
+// The define-by-run API is untouched: a new shape simply builds a new tape.
+//
+// What is recorded: constant/index uploads (as memcpy nodes reading the
+// plan-owned pinned staging), all kernels of forward() and backward(), and the
+// D2H copy of the cost scalar.  The optimizer step stays outside (its bias
+// correction terms change every step).
+#pragma once
+
+#include <map>
+#include <vector>
+
+#include "data/batch.h"
+#include "graph/expression_graph.h"
+#include "tensors/device.h"
+
+namespace marian {
+
+class StepReplay {
+public:
+  struct Plan {
+    void* exec{nullptr};
+    Ptr<Staging> staging;
+    std::vector<BatchUpload> uploads;
+    size_t launches{0};
+  };
+
+  ~StepReplay() { clear(); }
+
+  void clear() {
+    for(auto& it : plans_)
+      if(it.second.exec)
+        device::destroyGraph(it.second.exec);
+    plans_.clear();
+    seen_.clear();
+  }
+
+  bool enabled() const { return enabled_ && device::captureSupported(); }
+  void setEnabled(bool e) { enabled_ = e; }
+
+  Plan* find(const std::vector<int>& key) {
+    auto it = plans_.find(key);
+    return it == plans_.end() ? nullptr : &it->second;
+  }
+
+  // A shape is captured the SECOND time it shows up: the first pass runs
+  // eagerly so that parameter initialisation, arena growth and packed-weight
+  // scratch growth all happen outside a recording.
+  bool shouldCapture(const std::vector<int>& key) {
+    if(!enabled())
+      return false;
+    return seen_[key]++ >= 1;
+  }
+
+  void replay(Plan& plan, const data::CorpusBatch& batch) {
+    for(auto& u : plan.uploads)
+      u.refill(u.pinned, batch);
+    device::launchGraph(plan.exec);
+    plan.launches++;
+  }
+
+  // Takes ownership of the recorded graph and of the tape's staging/uploads.
+  Plan& store(const std::vector<int>& key, void* exec, Ptr<ExpressionGraph> graph) {
+    Plan& p = plans_[key];
+    p.exec = exec;
+    p.uploads = graph->batchUploads();
+    p.staging = graph->detachStaging();
+    return p;
+  }
+
+  size_t size() const { return plans_.size(); }
+
+private:
+  bool enabled_{true};
+  std::map<std::vector<int>, Plan> plans_;
+  std::map<std::vector<int>, int> seen_;
+};
+
+}  // namespace marian

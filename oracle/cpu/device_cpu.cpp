@@ -1,0 +1,49 @@
+// TEST ORACLE — not part of the product.  Host-memory implementation of the
+// engine's device services (csrc/tensors/device.h) so that the host graph code
+// can be linked against the CPU restatement of the tensor operators.
+#include <cstdlib>
+#include <cstring>
+
+#include "common/definitions.h"
+#include "tensors/device.h"
+
+namespace marian {
+namespace device {
+
+void setDevice(int) {}
+int getDevice() { return 0; }
+void* currentStream() { return nullptr; }
+void setStream(void*) {}
+
+void* mallocDevice(size_t bytes) {
+  void* p = nullptr;
+  if(posix_memalign(&p, 256, bytes ? bytes : 256) != 0)
+    ABORT("oracle: out of host memory", bytes);
+  return p;
+}
+void freeDevice(void* p) { std::free(p); }
+void* mallocPinned(size_t bytes) { return mallocDevice(bytes); }
+void freePinned(void* p) { std::free(p); }
+
+void copyH2D(void* dst, const void* src, size_t bytes) { std::memcpy(dst, src, bytes); }
+void copyH2DBlocking(void* dst, const void* src, size_t bytes) { std::memcpy(dst, src, bytes); }
+void copyD2H(void* dst, const void* src, size_t bytes) { std::memcpy(dst, src, bytes); }
+void copyD2D(void* dst, const void* src, size_t bytes) { std::memmove(dst, src, bytes); }
+void zero(void* dst, size_t bytes) { std::memset(dst, 0, bytes); }
+void fill(float* dst, float value, size_t n) {
+  for(size_t i = 0; i < n; ++i)
+    dst[i] = value;
+}
+void synchronize() {}
+bool capturing() { return false; }
+
+bool captureSupported() { return false; }
+void beginCapture() { ABORT("oracle: capture not supported"); }
+void* endCapture() { return nullptr; }
+void launchGraph(void*) {}
+void destroyGraph(void*) {}
+
+const char* backendName() { return "cpu-oracle"; }
+
+}  // namespace device
+}  // namespace marian

@@ -1,0 +1,938 @@
+// TEST ORACLE — not part of the product.  Only tests/, __graft_entry__.smoke()
+// and bench.py's cpu_baseline / --impl reference legs may link or call this.
+//
+// CPU restatement (fp32, host threads) of every tensor operator on the hot
+// path of the reference, following its CUDA kernels in
+//   /root/reference/src/kernels/tensor_operators.cu  (cited per function)
+// The reference has NO CPU backend, so this file is the
+// parity oracle for the sm_100a kernels and the timed "CPU baseline".
+//
+// Pinning: reproduces the golden vectors of the reference's own unit tests
+// (src/tests/operator_tests.cpp, rnn_tests.cpp, attention_tests.cpp) - see
+// tests/test_oracle_golden.py.  What those tests do not cover (backward
+// passes, cross-entropy, Adam) is pinned by fp64 PyTorch autograd checks in
+// tests/test_oracle_gradients.py.
+//
+// Conventions: reductions accumulate in double and round once (the
+// reference's shared-memory tree order is not reproducible off-GPU; double
+// makes the oracle the more accurate side).  Element-wise math uses the same
+// libm calls as the reference's device code (expf/tanhf/logf/sqrtf); the
+// reference is compiled with --use_fast_math, i.e. its __expf/__logf differ
+// from these by ~1e-6 relative - inside every tolerance used.
+#include <cmath>
+#include <cstring>
+#include <random>
+
+#include "kernels/tensor_operators.h"
+
+namespace marian {
+
+struct GemmContext {
+  GemmMode mode{GemmMode::FP32};
+};
+GemmHandle createGemmContext(int) { return new GemmContext(); }
+void destroyGemmContext(GemmHandle h) { delete h; }
+void setGemmMode(GemmHandle h, GemmMode m) { h->mode = m; }
+GemmMode getGemmMode(GemmHandle h) { return h->mode; }
+void gemmInvalidateCache(GemmHandle) {}
+
+static inline float stableLogit(float x) {
+  // reference: tensor_operators.cu:15-23
+  if(x >= 0) {
+    float z = expf(-x);
+    return 1.0f / (1.0f + z);
+  } else {
+    float z = expf(x);
+    return z / (1.0f + z);
+  }
+}
+
+bool IsNan(Tensor) { return false; }  // reference: stubbed to false (:25-33)
+
+// ---------------------------------------------------------------------------
+// Concatenate / Deconcatenate      reference: :35-162
+// ---------------------------------------------------------------------------
+void Concatenate(Tensor out, const std::vector<Tensor>& inputs, int ax) {
+  // rows = product of dims before ax; every input contributes a contiguous
+  // block of (its elements / rows) per row.  Covers both ConcatCont and
+  // Concatenate1 of the reference.
+  size_t step = 1;
+  for(int i = 0; i < ax; ++i)
+    step *= out->shape()[i];
+  size_t offset1 = 0;
+  for(size_t i = 0; i < step; ++i)
+    for(auto in : inputs) {
+      size_t size = in->shape().elements() / step;
+      std::memcpy(out->data() + offset1, in->data() + i * size, size * sizeof(float));
+      offset1 += size;
+    }
+}
+
+void Deconcatenate(std::vector<Tensor>& outputs, const Tensor in, int ax) {
+  size_t step = 1;
+  for(int i = 0; i < ax; ++i)
+    step *= in->shape()[i];
+  size_t offset1 = 0;
+  for(size_t i = 0; i < step; ++i)
+    for(auto out : outputs) {
+      size_t size = out->shape().elements() / step;
+      std::memcpy(out->data() + i * size, in->data() + offset1, size * sizeof(float));  // ASSIGNS
+      offset1 += size;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// TransposeND       reference: :164-200
+// ---------------------------------------------------------------------------
+void TransposeND(Tensor out, Tensor in, const std::vector<int>& vAxis) {
+  Shape4 os(out->shape()), is(in->shape());
+  int permute[4];
+  int diff = 4 - (int)vAxis.size();
+  for(int i = 0; i < 4; ++i)
+    permute[i] = i < diff ? i : vAxis[i - diff] + diff;
+  int length = os.elements();
+  float* o = out->data();
+  const float* p = in->data();
+#pragma omp parallel for if(length > 16384)
+  for(int index = 0; index < length; ++index) {
+    int oDims[4], pDims[4];
+    os.dims(index, oDims);
+    for(int i = 0; i < 4; ++i)
+      pDims[permute[i]] = oDims[i];
+    o[index] = p[is.index(pDims)];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Softmax family     reference: :202-519
+// ---------------------------------------------------------------------------
+void Softmax(Tensor out, Tensor in, Tensor mask) {
+  Shape4 os(out->shape());
+  Shape4 ms = mask ? Shape4(mask->shape()) : os;
+  int rows = os.elements() / os.back();
+  int cols = os.back();
+  bool broadcast = os != ms;
+  const float* m = mask ? mask->data() : nullptr;
+#pragma omp parallel for if((long)rows * cols > 16384)
+  for(int j = 0; j < rows; ++j) {
+    float* so = out->data() + (size_t)j * cols;
+    const float* sp = in->data() + (size_t)j * cols;
+    auto maskVal = [&](int id) -> float {
+      if(!m)
+        return 1.f;
+      int mIndex = id + j * cols;
+      if(broadcast) {
+        int dims[4];
+        os.dims(mIndex, dims);
+        mIndex = ms.bindex(dims);
+      }
+      return m[mIndex];
+    };
+    float max = -1.70141e+38f;  // CUDA_FLT_MAX of the reference
+    for(int id = 0; id < cols; ++id)
+      if(maskVal(id) && sp[id] > max)
+        max = sp[id];
+    double sum = 0;
+    for(int id = 0; id < cols; ++id) {
+      float ex = 0;
+      if(maskVal(id))
+        ex = expf(sp[id] - max);
+      so[id] = ex;
+      sum += ex;
+    }
+    float fsum = (float)sum;
+    for(int id = 0; id < cols; ++id)
+      so[id] = so[id] / fsum;
+  }
+}
+
+void LogSoftmax(Tensor out, Tensor in) {
+  // reference: gLogSoftmax :318-386: out = (x - max) - log(sum exp(x - max))
+  int cols = out->shape().back();
+  int rows = out->shape().elements() / cols;
+#pragma omp parallel for if((long)rows * cols > 16384)
+  for(int j = 0; j < rows; ++j) {
+    float* so = out->data() + (size_t)j * cols;
+    const float* sp = in->data() + (size_t)j * cols;
+    float max = sp[0];
+    for(int id = 1; id < cols; ++id)
+      if(sp[id] > max)
+        max = sp[id];
+    double sum = 0;
+    for(int id = 0; id < cols; ++id) {
+      float sm = sp[id] - max;
+      so[id] = sm;
+      sum += expf(sm);
+    }
+    float lsum = logf((float)sum);
+    for(int id = 0; id < cols; ++id)
+      so[id] -= lsum;
+  }
+}
+
+void SoftmaxGrad(Tensor grad, Tensor adj, Tensor val) {
+  // reference: gSoftmaxGrad :404-445: g += p * (adj - sum(p*adj))
+  int cols = grad->shape().back();
+  int rows = grad->shape().elements() / cols;
+#pragma omp parallel for if((long)rows * cols > 16384)
+  for(int j = 0; j < rows; ++j) {
+    float* g = grad->data() + (size_t)j * cols;
+    const float* a = adj->data() + (size_t)j * cols;
+    const float* v = val->data() + (size_t)j * cols;
+    double sum = 0;
+    for(int id = 0; id < cols; ++id)
+      sum += v[id] * a[id];
+    float fsum = (float)sum;
+    for(int id = 0; id < cols; ++id) {
+      float x = v[id] * (a[id] - fsum);
+      if(x)
+        g[id] += x;
+    }
+  }
+}
+
+void LogSoftmaxGrad(Tensor grad, Tensor adj, Tensor val) {
+  // reference: gLogSoftmaxGrad :464-502: g += adj - exp(val) * sum(adj)
+  int cols = grad->shape().back();
+  int rows = grad->shape().elements() / cols;
+#pragma omp parallel for if((long)rows * cols > 16384)
+  for(int j = 0; j < rows; ++j) {
+    float* g = grad->data() + (size_t)j * cols;
+    const float* a = adj->data() + (size_t)j * cols;
+    const float* v = val->data() + (size_t)j * cols;
+    double sum = 0;
+    for(int id = 0; id < cols; ++id)
+      sum += a[id];
+    float fsum = (float)sum;
+    for(int id = 0; id < cols; ++id)
+      g[id] += a[id] - (expf(v[id]) * fsum);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Cross entropy      reference: :1115-1283
+// ---------------------------------------------------------------------------
+void CrossEntropyPick(Tensor out, Tensor in, Tensor pick) {
+  int cols = in->shape().back();
+  int rows = in->shape().elements() / cols;
+#pragma omp parallel for if((long)rows * cols > 16384)
+  for(int j = 0; j < rows; ++j) {
+    const float* sp = in->data() + (size_t)j * cols;
+    float max = sp[0];
+    for(int id = 1; id < cols; ++id)
+      if(sp[id] > max)
+        max = sp[id];
+    double sum = 0;
+    for(int id = 0; id < cols; ++id)
+      sum += expf(sp[id] - max);
+    int id = (int)pick->data()[j];
+    out->data()[j] = logf((float)sum) - sp[id] + max;
+  }
+}
+
+void CrossEntropyPickBackward(Tensor out, Tensor adj, Tensor a, Tensor pick) {
+  int cols = out->shape().back();
+  int rows = out->shape().elements() / cols;
+#pragma omp parallel for if((long)rows * cols > 16384)
+  for(int j = 0; j < rows; ++j) {
+    const float* sp = a->data() + (size_t)j * cols;
+    float* so = out->data() + (size_t)j * cols;
+    float max = sp[0];
+    for(int id = 1; id < cols; ++id)
+      if(sp[id] > max)
+        max = sp[id];
+    double sum = 0;
+    for(int id = 0; id < cols; ++id)
+      sum += expf(sp[id] - max);
+    float fsum = (float)sum;
+    int p = (int)pick->data()[j];
+    float adjj = adj->data()[j];
+    for(int id = 0; id < cols; ++id) {
+      float sub = (float)(id == p);
+      so[id] += adjj * (expf(sp[id] - max) / fsum - sub);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// GEMM: C = alpha * op(A) op(B) + beta * C       reference: Prod :543-594,
+// ProdBatched :596-654 (cublasSgemm / cublasSgemmStridedBatched, fp32)
+// ---------------------------------------------------------------------------
+namespace {
+
+// C[M,N] (ldc) (+)= alpha * A[M,K] (lda) * B[K,N] (ldb), all row-major.
+void sgemm_nn(int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb, float beta, float* C, int ldc, bool parallel) {
+  constexpr int BM = 8, BN = 64;
+  int mBlocks = (M + BM - 1) / BM, nBlocks = (N + BN - 1) / BN;
+#pragma omp parallel for collapse(2) schedule(static) if(parallel)
+  for(int mb = 0; mb < mBlocks; ++mb)
+    for(int nb = 0; nb < nBlocks; ++nb) {
+      int i0 = mb * BM, j0 = nb * BN;
+      int im = std::min(BM, M - i0), jn = std::min(BN, N - j0);
+      float acc[BM][BN];
+      for(int i = 0; i < BM; ++i)
+        for(int j = 0; j < BN; ++j)
+          acc[i][j] = 0.f;
+      if(im == BM && jn == BN) {
+        for(int k = 0; k < K; ++k) {
+          const float* b = B + (size_t)k * ldb + j0;
+          for(int i = 0; i < BM; ++i) {
+            float a = A[(size_t)(i0 + i) * lda + k];
+#pragma omp simd
+            for(int j = 0; j < BN; ++j)
+              acc[i][j] += a * b[j];
+          }
+        }
+      } else {
+        for(int k = 0; k < K; ++k) {
+          const float* b = B + (size_t)k * ldb + j0;
+          for(int i = 0; i < im; ++i) {
+            float a = A[(size_t)(i0 + i) * lda + k];
+            for(int j = 0; j < jn; ++j)
+              acc[i][j] += a * b[j];
+          }
+        }
+      }
+      for(int i = 0; i < im; ++i) {
+        float* c = C + (size_t)(i0 + i) * ldc + j0;
+        if(beta == 0.f)
+          for(int j = 0; j < jn; ++j)
+            c[j] = alpha * acc[i][j];
+        else
+          for(int j = 0; j < jn; ++j)
+            c[j] = alpha * acc[i][j] + beta * c[j];
+      }
+    }
+}
+
+void transposeInto(std::vector<float>& dst, const float* src, int rows, int cols) {
+  dst.resize((size_t)rows * cols);
+#pragma omp parallel for if((long)rows * cols > 65536)
+  for(int r = 0; r < rows; ++r)
+    for(int c = 0; c < cols; ++c)
+      dst[(size_t)c * rows + r] = src[(size_t)r * cols + c];
+}
+
+// one (possibly transposed) product on raw row-major storage
+void gemmRaw(float* C, const float* A, const float* B, int rowsA, int colsA, int rowsB, int colsB, bool transA, bool transB, float beta, float alpha, bool parallel) {
+  int m = transA ? colsA : rowsA;
+  int k = transA ? rowsA : colsA;
+  int n = transB ? rowsB : colsB;
+  std::vector<float> At, Bt;
+  const float* a = A;
+  const float* b = B;
+  int lda = colsA, ldb = colsB;
+  if(transA) {
+    transposeInto(At, A, rowsA, colsA);
+    a = At.data();
+    lda = rowsA;
+  }
+  if(transB) {
+    transposeInto(Bt, B, rowsB, colsB);
+    b = Bt.data();
+    ldb = rowsB;
+  }
+  sgemm_nn(m, n, k, alpha, a, lda, b, ldb, beta, C, n, parallel);
+}
+}  // namespace
+
+void Prod(GemmHandle, Tensor C, const Tensor A, const Tensor B, bool transA, bool transB, float beta, float scalar) {
+  int colsA = A->shape().back(), rowsA = A->shape().elements() / colsA;
+  int colsB = B->shape().back(), rowsB = B->shape().elements() / colsB;
+  gemmRaw(C->data(), A->data(), B->data(), rowsA, colsA, rowsB, colsB, transA, transB, beta, scalar, true);
+}
+
+void ProdAffine(GemmHandle h, Tensor C, const Tensor A, const Tensor B, const Tensor bias) {
+  // reference AffineNodeOp::forwardOps (node_operators_binary.h:172-186): Prod, then Add(_1, val, bias)
+  using namespace functional;
+  Prod(h, C, A, B, false, false, 0.f, 1.f);
+  Add(_1, C, bias);
+}
+
+void ProdBatched(GemmHandle, Tensor C, const Tensor A, const Tensor B, bool transA, bool transB, float beta, float scalar) {
+  int rowsA = A->shape()[-2], colsA = A->shape()[-1];
+  int rowsB = B->shape()[-2], colsB = B->shape()[-1];
+  size_t batchA = A->shape().elements() / (rowsA * colsA);
+  size_t batchB = B->shape().elements() / (rowsB * colsB);
+  int m = transA ? colsA : rowsA;
+  int n = transB ? rowsB : colsB;
+  size_t batches = std::max(batchA, batchB);
+  size_t strideA = batchA == 1 ? 0 : (size_t)rowsA * colsA;
+  size_t strideB = batchB == 1 ? 0 : (size_t)rowsB * colsB;
+#pragma omp parallel for
+  for(size_t b = 0; b < batches; ++b)
+    gemmRaw(C->data() + b * (size_t)m * n, A->data() + b * strideA, B->data() + b * strideB, rowsA, colsA, rowsB, colsB, transA, transB, beta, scalar, false);
+}
+
+// ---------------------------------------------------------------------------
+// Row gather / scatter     reference: :656-746
+// ---------------------------------------------------------------------------
+void CopyRows(Tensor out, const Tensor in, const int* idx, size_t n) {
+  size_t cols = in->shape().back();
+#pragma omp parallel for if(n * cols > 16384)
+  for(size_t j = 0; j < n; ++j)
+    std::memcpy(out->data() + j * cols, in->data() + (size_t)idx[j] * cols, cols * sizeof(float));
+}
+void PasteRows(Tensor out, const Tensor in, const int* idx, size_t n) {
+  size_t cols = in->shape().back();
+  for(size_t j = 0; j < n; ++j) {  // serial: rows may repeat (atomicAdd in the reference)
+    float* o = out->data() + (size_t)idx[j] * cols;
+    const float* i = in->data() + j * cols;
+    for(size_t c = 0; c < cols; ++c)
+      o[c] += i[c];
+  }
+}
+static std::vector<int> toInt(const std::vector<size_t>& v) {
+  return std::vector<int>(v.begin(), v.end());
+}
+void CopyRows(Tensor out, const Tensor in, const std::vector<size_t>& indices) {
+  auto i = toInt(indices);
+  CopyRows(out, in, i.data(), i.size());
+}
+void PasteRows(Tensor out, const Tensor in, const std::vector<size_t>& indices) {
+  auto i = toInt(indices);
+  PasteRows(out, in, i.data(), i.size());
+}
+void CopyCols(Tensor out, const Tensor in, const std::vector<size_t>& indices) {
+  // reference: gCopyCols :750-774
+  size_t colsIn = in->shape().back(), colsOut = indices.size();
+  size_t rows = in->shape().elements() / colsIn;
+  for(size_t j = 0; j < rows; ++j)
+    for(size_t i = 0; i < colsOut; ++i)
+      out->data()[j * colsOut + i] = in->data()[j * colsIn + indices[i]];
+}
+void PasteCols(Tensor out, const Tensor in, const std::vector<size_t>& indices) {
+  // reference: gPasteCols :797-821 (assigns; last writer wins)
+  size_t colsOut = out->shape().back(), colsIn = indices.size();
+  size_t rows = out->shape().elements() / colsOut;
+  for(size_t j = 0; j < rows; ++j)
+    for(size_t i = 0; i < colsIn; ++i)
+      out->data()[j * colsOut + indices[i]] = in->data()[j * colsIn + i];
+}
+
+void Select(Ptr<Allocator>, Tensor out, Tensor in, int axis, const std::vector<size_t>& indices) {
+  // reference: gSelect :842-860
+  Shape4 os(out->shape()), is(in->shape());
+  int ax = axis + 4 - (int)out->shape().size();
+  int length = os.elements();
+  for(int index = 0; index < length; ++index) {
+    int dims[4];
+    os.dims(index, dims);
+    dims[ax] = (int)indices[dims[ax]];
+    out->data()[index] = in->data()[is.index(dims)];
+  }
+}
+void Insert(Ptr<Allocator>, Tensor out, Tensor in, int axis, const std::vector<size_t>& indices) {
+  // reference: gInsert :862-880 (its index lookup is buggy, `d_indices[dims[index]]`;
+  // the intended scatter-add is implemented here; not reached by any config)
+  Shape4 os(out->shape()), is(in->shape());
+  int ax = axis + 4 - (int)out->shape().size();
+  int length = is.elements();
+  for(int index = 0; index < length; ++index) {
+    int dims[4];
+    is.dims(index, dims);
+    dims[ax] = (int)indices[dims[ax]];
+    out->data()[os.index(dims)] += in->data()[index];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// GRU / LSTM fused cells     reference: :934-1113, :1749-2031
+// ---------------------------------------------------------------------------
+void GRUFastForward(Tensor out, std::vector<Tensor> inputs, bool final) {
+  int cols = out->shape().back();
+  int rows = out->shape().elements() / cols;
+  const float* state = inputs[0]->data();
+  const float* xW = inputs[1]->data();
+  const float* sU = inputs[2]->data();
+  const float* b = inputs[3]->data();
+  const float* mask = inputs.size() > 4 ? inputs[4]->data() : nullptr;
+#pragma omp parallel for if((long)rows * cols > 8192)
+  for(int j = 0; j < rows; ++j) {
+    float m = !mask || mask[j];
+    float* rowOut = out->data() + (size_t)j * cols;
+    const float* rowState = state + (size_t)j * cols;
+    const float* xWrow = xW + (size_t)j * cols * 3;
+    const float* sUrow = sU + (size_t)j * cols * 3;
+    for(int i = 0; i < cols; ++i) {
+      float r = stableLogit(xWrow[i] + sUrow[i] + b[i]);
+      int k = i + cols;
+      float z = stableLogit(xWrow[k] + sUrow[k] + b[k]);
+      int l = i + 2 * cols;
+      float h;
+      if(final)
+        h = tanhf(xWrow[l] + (sUrow[l] + b[l]) * r);
+      else
+        h = tanhf(xWrow[l] + sUrow[l] * r + b[l]);
+      float o = (1.0f - z) * h + z * rowState[i];
+      rowOut[i] = m * o + (1 - m) * rowState[i];
+    }
+  }
+}
+
+void GRUFastBackward(std::vector<Tensor> outputs, std::vector<Tensor> inputs, Tensor adj, bool final) {
+  int cols = adj->shape().back();
+  int rows = adj->shape().elements() / cols;
+  float* outState = outputs[0] ? outputs[0]->data() : nullptr;
+  float* outXW = outputs[1] ? outputs[1]->data() : nullptr;
+  float* outSU = outputs[2] ? outputs[2]->data() : nullptr;
+  float* outB = outputs[3] ? outputs[3]->data() : nullptr;
+  const float* state = inputs[0]->data();
+  const float* xW = inputs[1]->data();
+  const float* sU = inputs[2]->data();
+  const float* b = inputs[3]->data();
+  const float* mask = inputs.size() > 4 ? inputs[4]->data() : nullptr;
+  std::vector<double> biasAcc(outB ? (size_t)cols * 3 : 0, 0.0);
+  for(int j = 0; j < rows; ++j) {  // serial over rows: bias gradient is a column sum
+    float m = !mask || mask[j];
+    float* rowOutState = outState ? outState + (size_t)j * cols : nullptr;
+    float* rowOutXW = outXW ? outXW + (size_t)j * cols * 3 : nullptr;
+    float* rowOutSU = outSU ? outSU + (size_t)j * cols * 3 : nullptr;
+    const float* rowState = state + (size_t)j * cols;
+    const float* rowXW = xW + (size_t)j * cols * 3;
+    const float* rowSU = sU + (size_t)j * cols * 3;
+    const float* rowAdj = adj->data() + (size_t)j * cols;
+    for(int i = 0; i < cols; ++i) {
+      int k = i + cols;
+      int l = i + 2 * cols;
+      float r = stableLogit(rowXW[i] + rowSU[i] + b[i]);
+      float z = stableLogit(rowXW[k] + rowSU[k] + b[k]);
+      float h;
+      if(final)
+        h = tanhf(rowXW[l] + (rowSU[l] + b[l]) * r);
+      else
+        h = tanhf(rowXW[l] + rowSU[l] * r + b[l]);
+      float a = rowAdj[i];
+      float t = (1 - z) * (1 - h * h);
+
+      if(rowOutState)
+        rowOutState[i] += (m * z - m + 1) * a;
+
+      float dfdxW_r = m * r * (1 - r) * t * a;
+      if(final)
+        dfdxW_r *= rowSU[l] + b[l];
+      else
+        dfdxW_r *= rowSU[l];
+      if(rowOutXW)
+        rowOutXW[i] += dfdxW_r;
+      if(rowOutSU)
+        rowOutSU[i] += dfdxW_r;
+      if(outB)
+        biasAcc[i] += dfdxW_r;
+
+      float dfdxW_z = m * (1 - z) * z * (rowState[i] - h) * a;
+      if(rowOutXW)
+        rowOutXW[k] += dfdxW_z;
+      if(rowOutSU)
+        rowOutSU[k] += dfdxW_z;
+      if(outB)
+        biasAcc[k] += dfdxW_z;
+
+      float dfdxW_x = m * t * a;
+      if(rowOutXW)
+        rowOutXW[l] += dfdxW_x;
+      if(rowOutSU)
+        rowOutSU[l] += dfdxW_x * r;
+      if(outB)
+        biasAcc[l] += final ? dfdxW_x * r : dfdxW_x;
+    }
+  }
+  if(outB)
+    for(int i = 0; i < cols * 3; ++i)
+      outB[i] += (float)biasAcc[i];
+}
+
+void LSTMCellForward(Tensor out, std::vector<Tensor> inputs) {
+  int cols = out->shape().back();
+  int rows = out->shape().elements() / cols;
+  const float* cell = inputs[0]->data();
+  const float* xW = inputs[1]->data();
+  const float* sU = inputs[2]->data();
+  const float* b = inputs[3]->data();
+  const float* mask = inputs.size() > 4 ? inputs[4]->data() : nullptr;
+#pragma omp parallel for if((long)rows * cols > 8192)
+  for(int j = 0; j < rows; ++j) {
+    float m = !mask || mask[j];
+    float* rowOut = out->data() + (size_t)j * cols;
+    const float* rowCell = cell + (size_t)j * cols;
+    const float* xWrow = xW + (size_t)j * cols * 4;
+    const float* sUrow = sU + (size_t)j * cols * 4;
+    for(int i = 0; i < cols; ++i) {
+      float gf = stableLogit(xWrow[i] + sUrow[i] + b[i]);
+      int k = i + cols;
+      float gi = stableLogit(xWrow[k] + sUrow[k] + b[k]);
+      int l = i + 2 * cols;
+      float gc = tanhf(xWrow[l] + sUrow[l] + b[l]);
+      float cout = gf * rowCell[i] + gi * gc;
+      rowOut[i] = m * cout + (1 - m) * rowCell[i];
+    }
+  }
+}
+
+void LSTMOutputForward(Tensor out, std::vector<Tensor> inputs) {
+  int cols = out->shape().back();
+  int rows = out->shape().elements() / cols;
+  const float* cell = inputs[0]->data();
+  const float* xW = inputs[1]->data();
+  const float* sU = inputs[2]->data();
+  const float* b = inputs[3]->data();
+#pragma omp parallel for if((long)rows * cols > 8192)
+  for(int j = 0; j < rows; ++j) {
+    float* rowOut = out->data() + (size_t)j * cols;
+    const float* rowCell = cell + (size_t)j * cols;
+    const float* xWrow = xW + (size_t)j * cols * 4;
+    const float* sUrow = sU + (size_t)j * cols * 4;
+    for(int i = 0; i < cols; ++i) {
+      int k = i + 3 * cols;
+      float go = stableLogit(xWrow[k] + sUrow[k] + b[k]);
+      rowOut[i] = go * tanhf(rowCell[i]);
+    }
+  }
+}
+
+void LSTMCellBackward(std::vector<Tensor> outputs, std::vector<Tensor> inputs, Tensor adj) {
+  int cols = adj->shape().back();
+  int rows = adj->shape().elements() / cols;
+  float* outCell = outputs[0] ? outputs[0]->data() : nullptr;
+  float* outXW = outputs[1] ? outputs[1]->data() : nullptr;
+  float* outSU = outputs[2] ? outputs[2]->data() : nullptr;
+  float* outB = outputs[3] ? outputs[3]->data() : nullptr;
+  const float* cell = inputs[0]->data();
+  const float* xW = inputs[1]->data();
+  const float* sU = inputs[2]->data();
+  const float* b = inputs[3]->data();
+  const float* mask = inputs.size() > 4 ? inputs[4]->data() : nullptr;
+  std::vector<double> biasAcc(outB ? (size_t)cols * 4 : 0, 0.0);
+  for(int j = 0; j < rows; ++j) {
+    float m = !mask || mask[j];
+    float* rowOutCell = outCell ? outCell + (size_t)j * cols : nullptr;
+    float* rowOutXW = outXW ? outXW + (size_t)j * cols * 4 : nullptr;
+    float* rowOutSU = outSU ? outSU + (size_t)j * cols * 4 : nullptr;
+    const float* rowCell = cell + (size_t)j * cols;
+    const float* xWrow = xW + (size_t)j * cols * 4;
+    const float* sUrow = sU + (size_t)j * cols * 4;
+    const float* rowAdj = adj->data() + (size_t)j * cols;
+    for(int i = 0; i < cols; ++i) {
+      float gf = stableLogit(xWrow[i] + sUrow[i] + b[i]);
+      int k = i + cols;
+      float gi = stableLogit(xWrow[k] + sUrow[k] + b[k]);
+      int l = i + 2 * cols;
+      float gc = tanhf(xWrow[l] + sUrow[l] + b[l]);
+      float a = rowAdj[i];
+
+      if(rowOutCell)
+        rowOutCell[i] += (m * gf - m + 1) * a;
+
+      float dcdxf = m * rowCell[i] * gf * (1 - gf) * a;
+      if(rowOutXW)
+        rowOutXW[i] += dcdxf;
+      if(rowOutSU)
+        rowOutSU[i] += dcdxf;
+      if(outB)
+        biasAcc[i] += dcdxf;
+
+      float dcdb_i = m * gc * gi * (1 - gi) * a;
+      if(rowOutXW)
+        rowOutXW[k] += dcdb_i;
+      if(rowOutSU)
+        rowOutSU[k] += dcdb_i;
+      if(outB)
+        biasAcc[k] += dcdb_i;
+
+      float dcdxc = m * gi * (1 - gc * gc) * a;
+      if(rowOutXW)
+        rowOutXW[l] += dcdxc;
+      if(rowOutSU)
+        rowOutSU[l] += dcdxc;
+      if(outB)
+        biasAcc[l] += dcdxc;
+    }
+  }
+  if(outB)
+    for(int i = 0; i < cols * 4; ++i)
+      outB[i] += (float)biasAcc[i];
+}
+
+void LSTMOutputBackward(std::vector<Tensor> outputs, std::vector<Tensor> inputs, Tensor adj) {
+  int cols = adj->shape().back();
+  int rows = adj->shape().elements() / cols;
+  float* outCell = outputs[0] ? outputs[0]->data() : nullptr;
+  float* outXW = outputs[1] ? outputs[1]->data() : nullptr;
+  float* outSU = outputs[2] ? outputs[2]->data() : nullptr;
+  float* outB = outputs[3] ? outputs[3]->data() : nullptr;
+  const float* cell = inputs[0]->data();
+  const float* xW = inputs[1]->data();
+  const float* sU = inputs[2]->data();
+  const float* b = inputs[3]->data();
+  std::vector<double> biasAcc(outB ? (size_t)cols * 4 : 0, 0.0);
+  for(int j = 0; j < rows; ++j) {
+    float* rowOutCell = outCell ? outCell + (size_t)j * cols : nullptr;
+    float* rowOutXW = outXW ? outXW + (size_t)j * cols * 4 : nullptr;
+    float* rowOutSU = outSU ? outSU + (size_t)j * cols * 4 : nullptr;
+    const float* rowCell = cell + (size_t)j * cols;
+    const float* xWrow = xW + (size_t)j * cols * 4;
+    const float* sUrow = sU + (size_t)j * cols * 4;
+    const float* rowAdj = adj->data() + (size_t)j * cols;
+    for(int i = 0; i < cols; ++i) {
+      int k = i + 3 * cols;
+      float go = stableLogit(xWrow[k] + sUrow[k] + b[k]);
+      float t = tanhf(rowCell[i]);
+      float a = rowAdj[i];
+      if(rowOutCell)
+        rowOutCell[i] += go * (1 - t * t) * a;
+      float dcdxo = t * go * (1 - go) * a;
+      if(rowOutXW)
+        rowOutXW[k] += dcdxo;
+      if(rowOutSU)
+        rowOutSU[k] += dcdxo;
+      if(outB)
+        biasAcc[k] += dcdxo;
+    }
+  }
+  if(outB)
+    for(int i = 0; i < cols * 4; ++i)
+      outB[i] += (float)biasAcc[i];
+}
+
+// ---------------------------------------------------------------------------
+// Bahdanau attention score      reference: :1307-1445
+// ---------------------------------------------------------------------------
+void Att(Tensor out, Tensor va, Tensor context, Tensor state) {
+  int m = out->shape().elements() / out->shape().back();
+  int k = context->shape()[-1];
+  int b = context->shape()[-2];
+  int t = context->shape()[-3];
+  const float* vaRow = va->data();
+#pragma omp parallel for if((long)m * k > 8192)
+  for(int j = 0; j < m; ++j) {
+    const float* ctxRow = context->data() + (size_t)(j % (b * t)) * k;
+    const float* stateRow = state->data() + (size_t)((j / (b * t)) * b + j % b) * k;
+    double sum = 0;
+    for(int id = 0; id < k; ++id) {
+      float z = ctxRow[id] + stateRow[id];
+      sum += tanhf(z) * vaRow[id];
+    }
+    out->data()[j] = (float)sum;
+  }
+}
+
+void AttBack(Tensor gVa, Tensor gContext, Tensor gState, Tensor va, Tensor context, Tensor state, Tensor adj) {
+  int m = adj->shape().elements() / adj->shape().back();
+  int k = context->shape()[-1];
+  int n = context->shape()[-2];
+  std::vector<double> gvaAcc(k, 0.0);
+  for(int j = 0; j < m; ++j) {
+    float* gcRow = gContext->data() + (size_t)j * k;
+    float* gsRow = gState->data() + (size_t)(j % n) * k;
+    const float* cRow = context->data() + (size_t)j * k;
+    const float* sRow = state->data() + (size_t)(j % n) * k;
+    float a = adj->data()[j];
+    for(int id = 0; id < k; ++id) {
+      float z = cRow[id] + sRow[id];
+      float t = tanhf(z);
+      float r = va->data()[id] * (1.f - t * t);
+      gcRow[id] += r * a;
+      gsRow[id] += r * a;
+      gvaAcc[id] += t * a;
+    }
+  }
+  for(int id = 0; id < k; ++id)
+    gVa->data()[id] += (float)gvaAcc[id];
+}
+
+// ---------------------------------------------------------------------------
+// Layer normalisation       reference: :1447-1674
+// ---------------------------------------------------------------------------
+void LayerNormalization(Tensor out, Tensor in, Tensor gamma, Tensor beta, float eps) {
+  int cols = in->shape().back();
+  int rows = in->shape().elements() / cols;
+  const float* alpha = gamma->data();
+  const float* bet = beta ? beta->data() : nullptr;
+#pragma omp parallel for if((long)rows * cols > 16384)
+  for(int j = 0; j < rows; ++j) {
+    float* so = out->data() + (size_t)j * cols;
+    const float* sp = in->data() + (size_t)j * cols;
+    double sum = 0;
+    for(int id = 0; id < cols; ++id)
+      sum += sp[id];
+    float mean = (float)sum / cols;
+    double sq = 0;
+    for(int id = 0; id < cols; ++id) {
+      float ex = sp[id] - mean;
+      sq += ex * ex;
+    }
+    float sigma = sqrtf(eps + ((float)sq / cols));  // eps INSIDE the root, biased variance
+    for(int id = 0; id < cols; ++id) {
+      float t = alpha[id] * ((sp[id] - mean) / sigma);
+      if(bet)
+        t += bet[id];
+      so[id] = t;
+    }
+  }
+}
+
+void LayerNormalizationGrad(Tensor gradX, Tensor gradGamma, Tensor gradBeta, Tensor adj, Tensor y, Tensor x, Tensor gamma, Tensor beta, float eps) {
+  int cols = y->shape().back();
+  int rows = y->shape().elements() / cols;
+  const float* g = gamma->data();
+  const float* bet = beta ? beta->data() : nullptr;
+  std::vector<double> gGamma(cols, 0.0), gBeta(cols, 0.0);
+  for(int j = 0; j < rows; ++j) {
+    const float* xRow = x->data() + (size_t)j * cols;
+    const float* yRow = y->data() + (size_t)j * cols;
+    const float* adjRow = adj->data() + (size_t)j * cols;
+    float* gradXRow = gradX->data() + (size_t)j * cols;
+    double sum_x = 0, sum_adj = 0, sum_adj_x = 0;
+    for(int id = 0; id < cols; ++id) {
+      sum_x += xRow[id];
+      // x_hat is recovered from y: (y - beta) / gamma   (reference :1574-1576)
+      sum_adj_x += adjRow[id] * (yRow[id] - (bet ? bet[id] : 0)) / g[id];
+      sum_adj += adjRow[id];
+    }
+    float mean = (float)sum_x / cols;
+    double sq = 0;
+    for(int id = 0; id < cols; ++id) {
+      float ex = xRow[id] - mean;
+      sq += ex * ex;
+    }
+    float sigma = sqrtf(eps + ((float)sq / cols));
+    float fsum_adj = (float)sum_adj, fsum_adj_x = (float)sum_adj_x;
+    for(int id = 0; id < cols; ++id) {
+      float grad_x = 0.0f;
+      float x_hat = (yRow[id] - (bet ? bet[id] : 0)) / g[id];
+      grad_x += cols * adjRow[id];
+      grad_x -= fsum_adj;
+      grad_x -= fsum_adj_x * x_hat;
+      grad_x /= (cols * sigma);
+      float valX = g[id] * grad_x;
+      float sign = (0.f < valX) - (valX < 0.f);
+      valX = fabsf(valX) > 1000 ? sign * 1000 : valX;  // clip kept from the reference (:1631-1632)
+      gradXRow[id] += valX;
+      gGamma[id] += adjRow[id] * x_hat;
+      gBeta[id] += adjRow[id];
+    }
+  }
+  for(int id = 0; id < cols; ++id) {
+    gradGamma->data()[id] += (float)gGamma[id];
+    if(bet)
+      gradBeta->data()[id] += (float)gBeta[id];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Shift / Highway      reference: :1676-1707, :2033-2104
+// ---------------------------------------------------------------------------
+void Shift(Tensor out, Tensor in, Shape shift, bool invert) {
+  ABORT_IF(in->shape().size() != shift.size(), "bad dimensions");
+  int offset = 0;
+  for(int i = 0; i < (int)shift.size(); ++i)
+    offset += in->shape().stride(i) * shift[i];
+  if(invert)
+    offset = -offset;
+  int length = out->shape().elements();
+  for(int index = 0; index < length; ++index) {
+    if(index - offset < 0 || index - offset >= length)
+      out->data()[index] = 0;
+    else
+      out->data()[index] = in->data()[index - offset];
+  }
+}
+
+void HighwayForward(Tensor out, const Tensor in1, const Tensor in2, const Tensor t) {
+  int length = out->shape().elements();
+  for(int i = 0; i < length; ++i) {
+    float sigma = stableLogit(t->data()[i]);
+    out->data()[i] = in1->data()[i] * sigma + in2->data()[i] * (1.f - sigma);
+  }
+}
+
+void HighwayBackward(Tensor out1, Tensor out2, Tensor outt, const Tensor in1, const Tensor in2, const Tensor t, const Tensor adj) {
+  int length = out1->shape().elements();
+  for(int i = 0; i < length; ++i) {  // ASSIGNS, as the reference (:2074-2077)
+    float sigma = stableLogit(t->data()[i]);
+    out1->data()[i] = sigma * adj->data()[i];
+    out2->data()[i] = (1.f - sigma) * adj->data()[i];
+    outt->data()[i] = sigma * (1.f - sigma) * (in1->data()[i] - in2->data()[i]) * adj->data()[i];
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Norms, dropout, optimizers
+// ---------------------------------------------------------------------------
+void SumSquares(Tensor outScalar, Tensor in) {
+  double s = 0;
+  size_t n = in->size();
+  const float* p = in->data();
+#pragma omp parallel for reduction(+ : s) if(n > 65536)
+  for(size_t i = 0; i < n; ++i)
+    s += (double)p[i] * p[i];
+  outScalar->data()[0] = (float)s;
+}
+
+float L2Norm(Tensor in) {
+  // reference: :1286-1305 (ReduceAll(_1 * _1) then sqrtf on the host)
+  double s = 0;
+  size_t n = in->size();
+  const float* p = in->data();
+#pragma omp parallel for reduction(+ : s) if(n > 65536)
+  for(size_t i = 0; i < n; ++i)
+    s += (double)p[i] * p[i];
+  return sqrtf((float)s);
+}
+
+void Dropout(Tensor mask, float dropProb, uint64_t seed) {
+  // reference: kernels/dropout.cu:25-42 - uniform(0,1] from cuRAND, then
+  // mask = (u >= p) / (1 - p).  The random stream itself is unpinned.
+  std::mt19937_64 rng(seed);
+  std::uniform_real_distribution<float> u(0.f, 1.f);
+  float scale = 1.f / (1.f - dropProb);
+  for(size_t i = 0; i < mask->size(); ++i)
+    mask->data()[i] = (u(rng) >= dropProb) ? scale : 0.f;
+}
+
+static float clipFactor(float gradScale, float clipNorm, Tensor normSq) {
+  // reference: Norm::clip (optimizers/clippers.cu:12-17): if(|g| >= c) g *= c/|g|
+  float scale = gradScale;
+  if(clipNorm > 0 && normSq) {
+    float norm = sqrtf(normSq->data()[0]) * gradScale;
+    if(norm >= clipNorm)
+      scale *= clipNorm / norm;
+  }
+  return scale;
+}
+
+void AdamUpdate(Tensor params, Tensor grads, Tensor mt, Tensor vt, const AdamArgs& a, Tensor normSq) {
+  // reference: Adam::updateImpl (optimizers/optimizers.cu:43-73)
+  float scale = clipFactor(a.gradScale, a.clipNorm, normSq);
+  size_t n = params->size();
+  float* p = params->data();
+  const float* g = grads->data();
+  float* m = mt->data();
+  float* v = vt->data();
+#pragma omp parallel for if(n > 65536)
+  for(size_t i = 0; i < n; ++i) {
+    float gi = g[i] * scale;
+    m[i] = (a.beta1 * m[i]) + ((1 - a.beta1) * gi);
+    v[i] = (a.beta2 * v[i]) + ((1 - a.beta2) * (gi * gi));
+    p[i] = p[i] - a.eta * (m[i] / a.denom1) / (sqrtf(v[i] / a.denom2) + a.eps);
+  }
+}
+
+void SgdUpdate(Tensor params, Tensor grads, float eta, float gradScale, float clipNorm, Tensor normSq) {
+  float scale = clipFactor(gradScale, clipNorm, normSq);
+  size_t n = params->size();
+  for(size_t i = 0; i < n; ++i)
+    params->data()[i] -= eta * (grads->data()[i] * scale);
+}
+
+void AdagradUpdate(Tensor params, Tensor grads, Tensor gt, float eta, float eps, float gradScale, float clipNorm, Tensor normSq) {
+  float scale = clipFactor(gradScale, clipNorm, normSq);
+  size_t n = params->size();
+  for(size_t i = 0; i < n; ++i) {
+    float gi = grads->data()[i] * scale;
+    gt->data()[i] += gi * gi;
+    params->data()[i] -= (eta / (sqrtf(gt->data()[i]) + eps)) * gi;
+  }
+}
+
+}  // namespace marian
