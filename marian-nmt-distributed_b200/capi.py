@@ -1,0 +1,344 @@
+"""ctypes binding of the C ABI declared in include/marian_b200.h.
+
+`Library(path)` wraps ONE shared object exporting the mrn_* symbols.  The
+product library is loaded by `marian_nmt_distributed_b200.load()`; tests load
+the CPU oracle (oracle/_build/libmarian_oracle.so) through the same class, which
+is what lets a parity test run the identical call sequence on both.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+c_float_p = ctypes.POINTER(ctypes.c_float)
+
+
+class MrnTensor(ctypes.Structure):
+    _fields_ = [("data", ctypes.c_void_p), ("rank", ctypes.c_int), ("shape", ctypes.c_int * 4)]
+
+
+class MarianError(RuntimeError):
+    pass
+
+
+# name -> (argtypes); every function returns int status unless listed in _SPECIAL
+_T, _TP, _I, _F, _V, _SZ = MrnTensor, ctypes.POINTER(MrnTensor), ctypes.c_int, ctypes.c_float, ctypes.c_void_p, ctypes.c_size_t
+_SIGNATURES = {
+    "mrn_set_device": [_I],
+    "mrn_set_stream": [_V],
+    "mrn_synchronize": [],
+    "mrn_malloc": [ctypes.POINTER(_V), _SZ],
+    "mrn_free": [_V],
+    "mrn_memcpy_h2d": [_V, _V, _SZ],
+    "mrn_memcpy_d2h": [_V, _V, _SZ],
+    "mrn_memset_zero": [_V, _SZ],
+    "mrn_gemm_create": [ctypes.POINTER(_V), _I],
+    "mrn_gemm_destroy": [_V],
+    "mrn_gemm_set_mode": [_V, _I],
+    "mrn_prod": [_V, _T, _T, _T, _I, _I, _F, _F],
+    "mrn_prod_batched": [_V, _T, _T, _T, _I, _I, _F, _F],
+    "mrn_prod_affine": [_V, _T, _T, _T, _T],
+    "mrn_element": [ctypes.c_char_p, _T, _TP, _I, _F],
+    "mrn_add": [ctypes.c_char_p, _F, _T, _TP, _I, _F],
+    "mrn_softmax": [_T, _T, _TP],
+    "mrn_logsoftmax": [_T, _T],
+    "mrn_softmax_grad": [_T, _T, _T],
+    "mrn_logsoftmax_grad": [_T, _T, _T],
+    "mrn_cross_entropy_pick": [_T, _T, _T],
+    "mrn_cross_entropy_pick_backward": [_T, _T, _T, _T],
+    "mrn_layer_norm": [_T, _T, _T, _TP, _F],
+    "mrn_layer_norm_grad": [_T, _T, _TP, _T, _T, _T, _T, _TP, _F],
+    "mrn_att": [_T, _T, _T, _T],
+    "mrn_att_back": [_T, _T, _T, _T, _T, _T, _T],
+    "mrn_gru_fast_forward": [_T, _TP, _I, _I],
+    "mrn_gru_fast_backward": [_TP, _TP, _I, _T, _I],
+    "mrn_lstm_cell_forward": [_T, _TP, _I],
+    "mrn_lstm_output_forward": [_T, _TP, _I],
+    "mrn_lstm_cell_backward": [_TP, _TP, _I, _T],
+    "mrn_lstm_output_backward": [_TP, _TP, _I, _T],
+    "mrn_highway_forward": [_T, _T, _T, _T],
+    "mrn_highway_backward": [_T, _T, _T, _T, _T, _T, _T],
+    "mrn_transpose_nd": [_T, _T, ctypes.POINTER(_I)],
+    "mrn_concatenate": [_T, _TP, _I, _I],
+    "mrn_deconcatenate": [_TP, _I, _T, _I],
+    "mrn_copy_rows": [_T, _T, _V, _SZ],
+    "mrn_paste_rows": [_T, _T, _V, _SZ],
+    "mrn_shift": [_T, _T, ctypes.POINTER(_I), _I],
+    "mrn_l2norm": [_T, c_float_p],
+    "mrn_adam_step": [_T, _T, _T, _T, _F, _F, _F, _F, _I, _F, _F],
+    "mrn_trainer_create": [ctypes.POINTER(_V), ctypes.c_char_p, _I, _I, _I],
+    "mrn_trainer_destroy": [_V],
+    "mrn_trainer_set_batch": [_V, _I, _I, _V, _V, _I, _V, _V],
+    "mrn_trainer_next_synthetic_batch": [_V, _I, _I, _I, _I, _I, _I],
+    "mrn_trainer_compute_gradients": [_V, _I],
+    "mrn_trainer_update": [_V],
+    "mrn_trainer_update_shard": [_V],
+    "mrn_trainer_cost": [_V, c_float_p],
+    "mrn_trainer_params": [_V, ctypes.POINTER(_V), ctypes.POINTER(_SZ)],
+    "mrn_trainer_grads": [_V, ctypes.POINTER(_V), ctypes.POINTER(_SZ)],
+    "mrn_trainer_shard_grads": [_V, ctypes.POINTER(_V), ctypes.POINTER(_SZ)],
+    "mrn_trainer_get_tensor": [_V, ctypes.c_char_p, _I, _V, _SZ, ctypes.POINTER(_SZ)],
+    "mrn_trainer_param_names": [_V, ctypes.c_char_p, _SZ, ctypes.POINTER(_SZ)],
+    "mrn_trainer_batch_words": [_V, ctypes.POINTER(_SZ), ctypes.POINTER(_SZ)],
+    "mrn_trainer_stats": [_V, ctypes.POINTER(_SZ), ctypes.POINTER(_SZ), ctypes.POINTER(_SZ), ctypes.POINTER(_SZ)],
+}
+# exported by the golden-vector driver (tests/cpp/graph_golden.cpp)
+_TEST_SIGNATURES = {"mrn_test_golden": [ctypes.c_char_p, _V, _SZ, ctypes.POINTER(_SZ)]}
+
+DECLARED_SYMBOLS = sorted(list(_SIGNATURES) + ["mrn_last_error", "mrn_backend_name"])
+
+
+class DeviceArray:
+    """A float32 (or int32) array in the library's device memory."""
+
+    def __init__(self, lib, shape, dtype=np.float32):
+        self.lib = lib
+        self.shape = tuple(int(s) for s in shape)
+        self.dtype = np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        ptr = ctypes.c_void_p()
+        lib._ck(lib.c.mrn_malloc(ctypes.byref(ptr), max(self.nbytes, 256)))
+        self.ptr = ptr.value
+
+    def upload(self, a):
+        a = np.ascontiguousarray(a, dtype=self.dtype)
+        assert a.nbytes == self.nbytes, (a.shape, self.shape)
+        self.lib._ck(self.lib.c.mrn_memcpy_h2d(self.ptr, a.ctypes.data, self.nbytes))
+        return self
+
+    def numpy(self):
+        out = np.empty(self.shape, dtype=self.dtype)
+        self.lib._ck(self.lib.c.mrn_memcpy_d2h(out.ctypes.data, self.ptr, self.nbytes))
+        return out
+
+    def zero(self):
+        self.lib._ck(self.lib.c.mrn_memset_zero(self.ptr, self.nbytes))
+        self.lib.synchronize()
+        return self
+
+    def t(self, shape=None):
+        """mrn_tensor view (optionally with another Marian shape of the same size)."""
+        shape = self.shape if shape is None else tuple(shape)
+        assert int(np.prod(shape)) * self.dtype.itemsize == self.nbytes
+        assert 1 <= len(shape) <= 4
+        m = MrnTensor()
+        m.data = self.ptr
+        m.rank = len(shape)
+        for i, s in enumerate(shape):
+            m.shape[i] = int(s)
+        return m
+
+    def free(self):
+        if self.ptr:
+            self.lib.c.mrn_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def null_tensor():
+    m = MrnTensor()
+    m.data = None
+    m.rank = 1
+    m.shape[0] = 1
+    return m
+
+
+class Library:
+    def __init__(self, path, tests_path=None):
+        if not os.path.exists(path):
+            raise MarianError("shared library not found: %s (run __graft_entry__.build())" % path)
+        self.path = path
+        self.c = ctypes.CDLL(path)
+        self.c.mrn_last_error.restype = ctypes.c_char_p
+        self.c.mrn_backend_name.restype = ctypes.c_char_p
+        for name, args in _SIGNATURES.items():
+            fn = getattr(self.c, name)
+            fn.argtypes = args
+            fn.restype = ctypes.c_int
+        self.tests = None
+        tpath = tests_path
+        if tpath is None and hasattr(self.c, "mrn_test_golden"):
+            self.tests = self.c
+        elif tpath and os.path.exists(tpath):
+            self.tests = ctypes.CDLL(tpath)
+        if self.tests is not None:
+            for name, args in _TEST_SIGNATURES.items():
+                fn = getattr(self.tests, name)
+                fn.argtypes = args
+                fn.restype = ctypes.c_int
+
+    # -- helpers -----------------------------------------------------------
+    def _ck(self, rc):
+        if rc != 0:
+            raise MarianError(self.c.mrn_last_error().decode(errors="replace"))
+
+    @property
+    def backend(self):
+        return self.c.mrn_backend_name().decode()
+
+    def synchronize(self):
+        self._ck(self.c.mrn_synchronize())
+
+    def set_stream(self, stream_ptr):
+        self._ck(self.c.mrn_set_stream(stream_ptr))
+
+    def array(self, a, dtype=np.float32):
+        a = np.asarray(a, dtype=dtype)
+        return DeviceArray(self, a.shape, dtype).upload(a)
+
+    def zeros(self, shape, dtype=np.float32):
+        return DeviceArray(self, shape, dtype).zero()
+
+    def call(self, name, *args):
+        self._ck(getattr(self.c, name)(*args))
+
+    @staticmethod
+    def tensor_list(ts):
+        arr = (MrnTensor * len(ts))()
+        for i, t in enumerate(ts):
+            arr[i] = t
+        return arr
+
+    def golden(self, case):
+        assert self.tests is not None, "golden-vector driver not linked into this library"
+        n = ctypes.c_size_t(0)
+        rc = self.tests.mrn_test_golden(case.encode(), None, 0, ctypes.byref(n))
+        if rc != 0:
+            raise MarianError("mrn_test_golden(%s) failed with %d: %s" % (case, rc, self.c.mrn_last_error().decode()))
+        out = np.zeros(n.value, dtype=np.float32)
+        rc = self.tests.mrn_test_golden(case.encode(), out.ctypes.data, n.value, ctypes.byref(n))
+        if rc != 0:
+            raise MarianError("mrn_test_golden(%s) failed with %d" % (case, rc))
+        return out
+
+    def gemm(self, mode=0, device=0):
+        return Gemm(self, mode, device)
+
+    def trainer(self, options, device=0, rank=0, nranks=1):
+        return Trainer(self, options, device, rank, nranks)
+
+
+class Gemm:
+    def __init__(self, lib, mode, device):
+        self.lib = lib
+        h = ctypes.c_void_p()
+        lib._ck(lib.c.mrn_gemm_create(ctypes.byref(h), device))
+        self.h = h
+        lib._ck(lib.c.mrn_gemm_set_mode(h, mode))
+
+    def set_mode(self, mode):
+        self.lib._ck(self.lib.c.mrn_gemm_set_mode(self.h, mode))
+
+    def __del__(self):
+        try:
+            if self.h:
+                self.lib.c.mrn_gemm_destroy(self.h)
+                self.h = None
+        except Exception:
+            pass
+
+
+class Trainer:
+    """Training-step driver (reference: SingletonGraph / SyncGraphGroup)."""
+
+    def __init__(self, lib, options, device=0, rank=0, nranks=1):
+        self.lib = lib
+        if isinstance(options, dict):
+            options = ";".join("%s=%s" % (k, ",".join(map(str, v)) if isinstance(v, (list, tuple)) else v) for k, v in options.items())
+        self.options = options
+        self.rank, self.nranks = rank, nranks
+        h = ctypes.c_void_p()
+        lib._ck(lib.c.mrn_trainer_create(ctypes.byref(h), options.encode(), device, rank, nranks))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.lib._ck(self.lib.c.mrn_trainer_destroy(self.h))
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_batch(self, src_idx, src_mask, trg_idx, trg_mask):
+        """Arrays are time-major [T, B] as in the reference's SubBatch."""
+        src_idx = np.ascontiguousarray(src_idx, dtype=np.int64)
+        trg_idx = np.ascontiguousarray(trg_idx, dtype=np.int64)
+        src_mask = np.ascontiguousarray(src_mask, dtype=np.float32)
+        trg_mask = np.ascontiguousarray(trg_mask, dtype=np.float32)
+        Ts, B = src_idx.shape
+        Tt, B2 = trg_idx.shape
+        assert B == B2
+        self.lib._ck(self.lib.c.mrn_trainer_set_batch(self.h, B, Ts, src_idx.ctypes.data, src_mask.ctypes.data, Tt, trg_idx.ctypes.data, trg_mask.ctypes.data))
+
+    def next_synthetic_batch(self, batch_size, len_src, len_trg, padded=False, split_rank=0, split_n=1):
+        self.lib._ck(self.lib.c.mrn_trainer_next_synthetic_batch(self.h, batch_size, len_src, len_trg, int(padded), split_rank, split_n))
+
+    def compute_gradients(self, keep_logits=False):
+        self.lib._ck(self.lib.c.mrn_trainer_compute_gradients(self.h, int(keep_logits)))
+
+    def update(self):
+        self.lib._ck(self.lib.c.mrn_trainer_update(self.h))
+
+    def update_shard(self):
+        self.lib._ck(self.lib.c.mrn_trainer_update_shard(self.h))
+
+    def cost(self):
+        c = ctypes.c_float()
+        self.lib._ck(self.lib.c.mrn_trainer_cost(self.h, ctypes.byref(c)))
+        return c.value
+
+    def _arena(self, fn):
+        p, n = ctypes.c_void_p(), ctypes.c_size_t()
+        self.lib._ck(fn(self.h, ctypes.byref(p), ctypes.byref(n)))
+        return p.value, n.value
+
+    def params_arena(self):
+        return self._arena(self.lib.c.mrn_trainer_params)
+
+    def grads_arena(self):
+        return self._arena(self.lib.c.mrn_trainer_grads)
+
+    def shard_grads_arena(self):
+        return self._arena(self.lib.c.mrn_trainer_shard_grads)
+
+    def arena_numpy(self, which="params"):
+        ptr, n = {"params": self.params_arena, "grads": self.grads_arena, "shard_grads": self.shard_grads_arena}[which]()
+        out = np.empty(n, dtype=np.float32)
+        self.lib._ck(self.lib.c.mrn_memcpy_d2h(out.ctypes.data, ptr, n * 4))
+        return out
+
+    def get_tensor(self, name, grad=False):
+        n = ctypes.c_size_t()
+        self.lib._ck(self.lib.c.mrn_trainer_get_tensor(self.h, name.encode(), int(grad), None, 0, ctypes.byref(n)))
+        out = np.empty(n.value, dtype=np.float32)
+        self.lib._ck(self.lib.c.mrn_trainer_get_tensor(self.h, name.encode(), int(grad), out.ctypes.data, n.value, ctypes.byref(n)))
+        return out
+
+    def param_names(self):
+        need = ctypes.c_size_t()
+        self.lib._ck(self.lib.c.mrn_trainer_param_names(self.h, None, 0, ctypes.byref(need)))
+        buf = ctypes.create_string_buffer(need.value)
+        self.lib._ck(self.lib.c.mrn_trainer_param_names(self.h, buf, need.value, ctypes.byref(need)))
+        out = []
+        for line in buf.value.decode().strip().split("\n"):
+            parts = line.split()
+            out.append((parts[0], tuple(int(x) for x in parts[2:])))
+        return out
+
+    def batch_words(self):
+        s, t = ctypes.c_size_t(), ctypes.c_size_t()
+        self.lib._ck(self.lib.c.mrn_trainer_batch_words(self.h, ctypes.byref(s), ctypes.byref(t)))
+        return s.value, t.value
+
+    def stats(self):
+        a, b, c, d = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()
+        self.lib._ck(self.lib.c.mrn_trainer_stats(self.h, ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.byref(d)))
+        return {"tape_nodes": a.value, "plans": b.value, "replays": c.value, "workspace_peak_bytes": d.value}

@@ -218,6 +218,10 @@ public:
     device::setDevice(device_);
     params_->allocateForward();
     gemmInvalidateCache(backend_->getGemmHandle());
+    if(params_->size() > 0) {
+      auto vals = params_->vals();
+      gemmSetStableRange(backend_->getGemmHandle(), vals->data(), vals->size() * sizeof(float));
+    }
     forwardNext();
   }
 

@@ -1,0 +1,387 @@
+// Element / Add / Reduce: the fused element-wise kernel family (CUDA, sm_100a).
+//
+// Call syntax and dispatch rules of the reference's templates
+// (src/kernels/tensor_operators.h:26-274):
+//   Element(f, out, ins...)          out[i] = f(out[i], ins[bcast(i)]...)
+//   Add(f, [scale,] out, ins...)     out += scale * reduce_or_broadcast(f(ins...))
+//      (1) full.back()!=1 && out.back()==1 : last-axis reduction   (gAddReduce there)
+//      (2) out.shape()==full               : element-wise accumulate (gAddEqual)
+//      (3) otherwise                       : generic reduction       (gAddGeneric)
+//   Reduce = out->set(0); Add(...)
+//
+// Kernel design (all HBM-bound):
+//  * one kernel template for Element and Add-case-(2): each thread owns FOUR
+//    consecutive elements of a row; the broadcast row base of every operand is
+//    resolved once per thread (the reference does a 4-D div/mod per element per
+//    operand), contiguous operands are read with 128-bit loads, operands whose
+//    last dim is 1 with one scalar load.  Operands the functor never reads
+//    (`_1 = _2 + _3` does not read out) are not loaded (functional::Reads).
+//  * case (1): one warp per row, lanes stride the row, shuffle reduction
+//    (the reference: 512-thread blocks with a shared-memory tree per row).
+//  * case (3): one thread per OUTPUT element so that consecutive threads read
+//    consecutive addresses of every operand, the reduced sub-space is split over
+//    gridDim.y slices that combine with atomicAdd (the reference runs the whole
+//    reduction serially in one thread per output: the bias gradient of a
+//    [3200,512] adjoint ran on 512 threads).
+// Grids are sized in multiples of the 148 SMs.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include "common/shape.h"
+#include "functional/functional.h"
+#include "kernels/cuda_helpers.h"
+#include "tensors/tensor.h"
+
+namespace marian {
+namespace ew {
+
+template <int K>
+struct Operands {
+  const float* p[K];
+  int rb[K][3];  // broadcast strides of dims 0..2 (row base)
+  int cs[K];     // stride of the last dim: 1, or 0 when broadcast along it
+};
+
+struct RowGeom {
+  int rows, cols;  // rows = product of dims 0..2 of the iteration shape
+  int d1, d2;      // extents of dims 1 and 2 (row decode)
+};
+
+template <int K, bool ACC, bool VEC, class Functor>
+__global__ void __launch_bounds__(256) gElementwise(Functor f, float* __restrict__ out, Operands<K> ops, RowGeom g, float scale) {
+  const int cpr = (g.cols + 3) >> 2;  // 4-element chunks per row
+  const long long items = (long long)g.rows * cpr;
+  for(long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < items; w += (long long)gridDim.x * blockDim.x) {
+    int row = (int)(w / cpr);
+    int c = (int)(w - (long long)row * cpr) << 2;
+    int o2 = row % g.d2;
+    int t = row / g.d2;
+    int o1 = t % g.d1;
+    int o0 = t / g.d1;
+
+    float v[K][4];
+#pragma unroll
+    for(int k = 0; k < K; ++k) {
+      // Element mode: operand 0 is `out`; skip the load if the functor ignores it
+      if(!ACC && k == 0 && !functional::Reads<Functor, 1>::value) {
+        v[k][0] = v[k][1] = v[k][2] = v[k][3] = 0.f;
+        continue;
+      }
+      const float* base = ops.p[k] + (size_t)o0 * ops.rb[k][0] + (size_t)o1 * ops.rb[k][1] + (size_t)o2 * ops.rb[k][2];
+      if(ops.cs[k] == 0) {
+        float s = __ldg(base);
+        v[k][0] = v[k][1] = v[k][2] = v[k][3] = s;
+      } else if(VEC) {
+        float4 q = *reinterpret_cast<const float4*>(base + c);
+        v[k][0] = q.x;
+        v[k][1] = q.y;
+        v[k][2] = q.z;
+        v[k][3] = q.w;
+      } else {
+#pragma unroll
+        for(int e = 0; e < 4; ++e)
+          v[k][e] = (c + e < g.cols) ? base[c + e] : 0.f;
+      }
+    }
+
+    float r[4];
+#pragma unroll
+    for(int e = 0; e < 4; ++e) {
+      float a[K];
+#pragma unroll
+      for(int k = 0; k < K; ++k)
+        a[k] = v[k][e];
+      r[e] = f(a);
+    }
+
+    float* o = out + (size_t)row * g.cols + c;
+    if(VEC) {
+      float4 q;
+      if(ACC) {
+        q = *reinterpret_cast<float4*>(o);
+        q.x += r[0] * scale;
+        q.y += r[1] * scale;
+        q.z += r[2] * scale;
+        q.w += r[3] * scale;
+      } else {
+        q = make_float4(r[0], r[1], r[2], r[3]);
+      }
+      *reinterpret_cast<float4*>(o) = q;
+    } else {
+#pragma unroll
+      for(int e = 0; e < 4; ++e)
+        if(c + e < g.cols) {
+          if(ACC)
+            o[e] += r[e] * scale;
+          else
+            o[e] = r[e];
+        }
+    }
+  }
+}
+
+// case (1): out[row] += scale * sum_c f(ins[row, c]); one warp per row
+template <int K, class Functor>
+__global__ void __launch_bounds__(256) gAddReduceRows(Functor f, float* __restrict__ out, Operands<K> ops, RowGeom g, float scale) {
+  int warpsPerBlock = blockDim.x >> 5;
+  int lane = threadIdx.x & 31;
+  for(int row = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); row < g.rows; row += gridDim.x * warpsPerBlock) {
+    int o2 = row % g.d2;
+    int t = row / g.d2;
+    int o1 = t % g.d1;
+    int o0 = t / g.d1;
+    const float* base[K];
+#pragma unroll
+    for(int k = 0; k < K; ++k)
+      base[k] = ops.p[k] + (size_t)o0 * ops.rb[k][0] + (size_t)o1 * ops.rb[k][1] + (size_t)o2 * ops.rb[k][2];
+    float acc = 0.f;
+    for(int c = lane; c < g.cols; c += 32) {
+      float a[K];
+#pragma unroll
+      for(int k = 0; k < K; ++k)
+        a[k] = base[k][(size_t)c * ops.cs[k]];
+      acc += f(a);
+    }
+    acc = warpSum(acc);
+    if(lane == 0)
+      out[row] += acc * scale;
+  }
+}
+
+struct GenericGeom {
+  Shape4 out;     // output shape (4-D)
+  int len[4];     // reduced extent per dim (full[i] / out[i])
+  int total;      // product of len
+  int chunk;      // reduced elements per slice
+  int outLength;
+  int atomic;     // slices > 1
+};
+
+template <int K>
+struct FullOperands {
+  const float* p[K];
+  int bst[K][4];
+};
+
+// case (3): thread per output element, reduced sub-space split over blockIdx.y
+template <int K, class Functor>
+__global__ void __launch_bounds__(128) gAddGeneric(Functor f, float* __restrict__ out, FullOperands<K> ops, GenericGeom g, float scale) {
+  int o = blockIdx.x * blockDim.x + threadIdx.x;
+  if(o >= g.outLength)
+    return;
+  int od[4];
+  g.out.dims(o, od);
+  int begin = blockIdx.y * g.chunk;
+  int end = min(g.total, begin + g.chunk);
+  if(begin >= end)
+    return;
+
+  // decode `begin` into a 4-D counter over len[], then advance with carries
+  int i[4];
+  {
+    int r = begin;
+    i[3] = r % g.len[3];
+    r /= g.len[3];
+    i[2] = r % g.len[2];
+    r /= g.len[2];
+    i[1] = r % g.len[1];
+    i[0] = r / g.len[1];
+  }
+  size_t idx[K];
+#pragma unroll
+  for(int k = 0; k < K; ++k) {
+    idx[k] = 0;
+#pragma unroll
+    for(int j = 0; j < 4; ++j)
+      idx[k] += (size_t)(od[j] + i[j]) * ops.bst[k][j];
+  }
+
+  float acc = 0.f;
+  for(int r = begin; r < end; ++r) {
+    float a[K];
+#pragma unroll
+    for(int k = 0; k < K; ++k)
+      a[k] = ops.p[k][idx[k]];
+    acc += f(a);
+    // increment the counter (dim 3 fastest) and the operand offsets
+    int j = 3;
+#pragma unroll
+    for(int step = 0; step < 4; ++step) {
+      if(j < 0)
+        break;
+      i[j]++;
+#pragma unroll
+      for(int k = 0; k < K; ++k)
+        idx[k] += ops.bst[k][j];
+      if(i[j] < g.len[j])
+        break;
+#pragma unroll
+      for(int k = 0; k < K; ++k)
+        idx[k] -= (size_t)g.len[j] * ops.bst[k][j];
+      i[j] = 0;
+      --j;
+    }
+  }
+  if(g.atomic)
+    atomicAdd(out + o, acc * scale);
+  else
+    out[o] += acc * scale;
+}
+
+inline bool aligned16(const void* p) {
+  return ((uintptr_t)p & 15) == 0;
+}
+
+// Fills row-geometry + operand strides for iterating `iter` (the shape being
+// walked) with operands of (possibly broadcast) shapes.
+template <int K>
+inline void setupOperands(const Shape4& iter, const Tensor* ts, Operands<K>& ops, RowGeom& g, bool& vec, bool collapse) {
+  if(collapse) {
+    // every operand has exactly the iteration shape: walk it as one long row
+    g.rows = 1;
+    g.cols = iter.elements();
+    g.d1 = g.d2 = 1;
+    for(int k = 0; k < K; ++k) {
+      ops.p[k] = ts[k]->data();
+      ops.rb[k][0] = ops.rb[k][1] = ops.rb[k][2] = 0;
+      ops.cs[k] = 1;
+    }
+  } else {
+    g.cols = iter.d[3];
+    g.rows = iter.d[0] * iter.d[1] * iter.d[2];
+    g.d1 = iter.d[1];
+    g.d2 = iter.d[2];
+    for(int k = 0; k < K; ++k) {
+      Shape4 s(ts[k]->shape());
+      ops.p[k] = ts[k]->data();
+      ops.rb[k][0] = s.bst[0];
+      ops.rb[k][1] = s.bst[1];
+      ops.rb[k][2] = s.bst[2];
+      ops.cs[k] = s.bst[3];
+    }
+  }
+  vec = (g.cols % 4 == 0);
+  for(int k = 0; k < K; ++k)
+    if(ops.cs[k] == 1 && !aligned16(ops.p[k]))
+      vec = false;
+}
+
+}  // namespace ew
+
+template <class Functor, class... Tensors>
+void Element(Functor functor, Tensor out, Tensors... tensors) {
+  device::setDevice(out->getDevice());
+  constexpr int K = sizeof...(tensors) + 1;
+  Tensor ts[K] = {out, tensors...};
+
+  Shape4 iter(out->shape());
+  bool broadcast = false;
+  for(int i = 1; i < K; ++i)
+    broadcast = broadcast || iter != Shape4(ts[i]->shape());
+
+  ew::Operands<K> ops;
+  ew::RowGeom g;
+  bool vec;
+  ew::setupOperands<K>(iter, ts, ops, g, vec, !broadcast);
+  if(g.rows == 0 || g.cols == 0)
+    return;
+
+  long long items = (long long)g.rows * ((g.cols + 3) / 4);
+  int grid = gridFor((size_t)items, 256);
+  auto stream = cudaStreamOfEngine();
+  if(vec)
+    ew::gElementwise<K, false, true><<<grid, 256, 0, stream>>>(functor, out->data(), ops, g, 1.f);
+  else
+    ew::gElementwise<K, false, false><<<grid, 256, 0, stream>>>(functor, out->data(), ops, g, 1.f);
+  CUDA_LAUNCH_CHECK();
+}
+
+template <class Functor, class... Tensors>
+void Add(Functor functor, float scale, Tensor out, Tensors... tensors) {
+  device::setDevice(out->getDevice());
+  constexpr int K = sizeof...(Tensors);
+  Tensor ts[K] = {tensors...};
+
+  std::vector<Shape> shapes = {out->shape(), tensors->shape()...};
+  Shape4 full(Shape::broadcast(shapes));
+  Shape4 outS(out->shape());
+  auto stream = cudaStreamOfEngine();
+  if(full.elements() == 0)
+    return;
+
+  if(full.back() != 1 && outS.back() == 1) {
+    // (1) reduce the last axis
+    ew::Operands<K> ops;
+    ew::RowGeom g;
+    bool vec;
+    ew::setupOperands<K>(full, ts, ops, g, vec, false);
+    int warpsPerBlock = 8;
+    int grid = gridFor((size_t)g.rows * 32, 256);
+    (void)warpsPerBlock;
+    ew::gAddReduceRows<K><<<grid, 256, 0, stream>>>(functor, out->data(), ops, g, scale);
+  } else if(outS == full) {
+    // (2) element-wise accumulate
+    bool broadcast = false;
+    for(int i = 0; i < K; ++i)
+      broadcast = broadcast || full != Shape4(ts[i]->shape());
+    ew::Operands<K> ops;
+    ew::RowGeom g;
+    bool vec;
+    ew::setupOperands<K>(full, ts, ops, g, vec, !broadcast);
+    if(!ew::aligned16(out->data()))
+      vec = false;
+    long long items = (long long)g.rows * ((g.cols + 3) / 4);
+    int grid = gridFor((size_t)items, 256);
+    if(vec)
+      ew::gElementwise<K, true, true><<<grid, 256, 0, stream>>>(functor, out->data(), ops, g, scale);
+    else
+      ew::gElementwise<K, true, false><<<grid, 256, 0, stream>>>(functor, out->data(), ops, g, scale);
+  } else {
+    // (3) generic reduction over the dims where out has extent 1
+    ew::FullOperands<K> ops;
+    for(int k = 0; k < K; ++k) {
+      Shape4 s(ts[k]->shape());
+      ops.p[k] = ts[k]->data();
+      for(int j = 0; j < 4; ++j)
+        ops.bst[k][j] = s.bst[j];
+    }
+    ew::GenericGeom g;
+    g.out = outS;
+    g.total = 1;
+    for(int j = 0; j < 4; ++j) {
+      g.len[j] = full.d[j] / outS.d[j];
+      g.total *= g.len[j];
+    }
+    g.outLength = outS.elements();
+    int blocksX = (g.outLength + 127) / 128;
+    // enough slices to fill the machine (148 SMs x 8 blocks), at least 8 reduced elements per slice
+    int slices = std::max(1, std::min((kNumSMs * 8 + blocksX - 1) / blocksX, (g.total + 7) / 8));
+    slices = std::min(slices, 65535);
+    g.chunk = (g.total + slices - 1) / slices;
+    slices = (g.total + g.chunk - 1) / g.chunk;
+    g.atomic = slices > 1;
+    dim3 grid(blocksX, slices);
+    ew::gAddGeneric<K><<<grid, 128, 0, stream>>>(functor, out->data(), ops, g, scale);
+  }
+  CUDA_LAUNCH_CHECK();
+}
+
+template <class Functor, class... Tensors>
+void Add(Functor functor, Tensor out, Tensors... tensors) {
+  Add(functor, 1.f, out, tensors...);
+}
+
+template <class Functor, class... Tensors>
+void Reduce(Functor functor, float scale, Tensor out, Tensors... tensors) {
+  out->set(0);
+  Add(functor, scale, out, tensors...);
+}
+
+template <class Functor, class... Tensors>
+void Reduce(Functor functor, Tensor out, Tensors... tensors) {
+  out->set(0);
+  Add(functor, 1.f, out, tensors...);
+}
+
+}  // namespace marian

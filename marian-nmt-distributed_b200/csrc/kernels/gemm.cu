@@ -1,0 +1,840 @@
+// Prod / ProdBatched / ProdAffine: the one dense contraction of the hot path.
+//
+// Reference: src/kernels/tensor_operators.cu:543-654 (cublasSgemm /
+// cublasSgemmStridedBatched in fp32, tensor-op math disabled) driven by
+// DotNodeOp / AffineNodeOp / DotBatchedNodeOp (src/graph/node_operators_binary.h:13-369).
+//
+// Three arithmetic modes (GemmMode, kernels/tensor_operators.h):
+//   BF16    tcgen05.mma kind::f16 (bf16 x bf16 -> fp32 in TMEM), operands
+//           staged by TMA into 128B-swizzled shared memory          [throughput]
+//   BF16X3  same kernel on hi/lo-split operands laid out along K:
+//             A' = [A_hi | A_lo | A_hi],  B' = [B_hi | B_hi | B_lo]
+//           so one pass over K' = 3K accumulates hi*hi + lo*hi + hi*lo in fp32
+//           (~2^-16 relative operand error; used for the 1e-4 parity runs)
+//   FP32    tiled SIMT fp32 kernel (exact-mode fallback and debugging aid)
+//
+// The tensor-core kernel computes  C[M,N] (+)= alpha * A[M,K] B[N,K]^T (+ bias)
+// with BOTH operands K-major.  The four transpose cases of the reference API,
+// the fp32 -> bf16 conversion and the hi/lo split are all handled by ONE
+// packing pass per operand (read fp32 once, write bf16 once; weights are
+// packed once per step and cached, see gemmSetStableRange).
+//
+// Kernel anatomy (one 128 x BN output tile per CTA, 192 threads):
+//   warp 0      TMA producer: cp.async.bulk.tensor.2d -> smem ring (STAGES deep),
+//               mbarrier expect_tx / complete_tx
+//   warp 1      TMEM allocator + single-thread tcgen05.mma issuer; tcgen05.commit
+//               releases smem stages and finally signals the epilogue
+//   warps 2-5   epilogue: tcgen05.ld 32 lanes x 32 columns -> registers ->
+//               alpha/beta/bias -> global (128-bit stores; red.add for split-K)
+// 2 CTAs are resident per SM (<= 96 KB smem, 128 TMEM columns each) so one
+// tile's epilogue overlaps the other's main loop.  Small-M / large-K products
+// (weight gradients: K = 3200 rows of the batch) are split along K across
+// gridDim.z and combined with atomic adds.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <unordered_map>
+
+#include "kernels/cuda_helpers.h"
+#include "kernels/tensor_operators.h"
+
+namespace marian {
+
+// =============================================================================
+// context: mode, scratch arena for packed operands, packed-weight cache
+// =============================================================================
+struct GemmContext {
+  int device{0};
+  GemmMode mode{GemmMode::FP32};
+
+  struct Chunk {
+    uint8_t* base;
+    size_t size;
+  };
+  std::vector<Chunk> chunks;
+  size_t cur{0}, off{0};
+
+  // sources inside [stableLo, stableHi) (the parameter arena) keep their packed
+  // copies until the next gemmInvalidateCache()
+  const uint8_t* stableLo{nullptr};
+  const uint8_t* stableHi{nullptr};
+  struct Key {
+    const void* p;
+    int rows, cols, flags;
+    bool operator==(const Key& o) const { return p == o.p && rows == o.rows && cols == o.cols && flags == o.flags; }
+  };
+  struct KeyHash {
+    size_t operator()(const Key& k) const {
+      return std::hash<const void*>()(k.p) ^ ((size_t)k.rows * 1000003u) ^ ((size_t)k.cols * 7919u) ^ ((size_t)k.flags << 20);
+    }
+  };
+  std::unordered_map<Key, void*, KeyHash> cache;
+
+  typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  EncodeTiledFn encodeTiled{nullptr};
+
+  void* take(size_t bytes) {
+    bytes = (bytes + 1023) & ~size_t(1023);
+    while(true) {
+      if(cur < chunks.size() && off + bytes <= chunks[cur].size) {
+        void* p = chunks[cur].base + off;
+        off += bytes;
+        return p;
+      }
+      if(cur + 1 < chunks.size()) {
+        ++cur;
+        off = 0;
+        continue;
+      }
+      size_t sz = std::max(bytes, (size_t)256 << 20);
+      Chunk c;
+      c.base = (uint8_t*)device::mallocDevice(sz);
+      c.size = sz;
+      chunks.push_back(c);
+      cur = chunks.size() - 1;
+      off = 0;
+    }
+  }
+};
+
+GemmHandle createGemmContext(int deviceId) {
+  auto c = new GemmContext();
+  c->device = deviceId;
+  return c;
+}
+void destroyGemmContext(GemmHandle h) {
+  if(!h)
+    return;
+  for(auto& c : h->chunks)
+    device::freeDevice(c.base);
+  delete h;
+}
+void setGemmMode(GemmHandle h, GemmMode m) {
+  h->mode = m;
+}
+GemmMode getGemmMode(GemmHandle h) {
+  return h->mode;
+}
+void gemmInvalidateCache(GemmHandle h) {
+  h->cache.clear();
+  h->cur = 0;
+  h->off = 0;
+}
+void gemmSetStableRange(GemmHandle h, const void* lo, size_t bytes) {
+  h->stableLo = (const uint8_t*)lo;
+  h->stableHi = h->stableLo + bytes;
+}
+
+namespace {
+
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 16;
+
+// =============================================================================
+// operand packing: fp32 [rows, cols] (row-major) -> bf16 K-major [outRows, Kp]
+// =============================================================================
+enum PackFlags { PACK_TRANSPOSE = 1, PACK_X3 = 2, PACK_ROLE_B = 4 };
+
+struct PackGeom {
+  int srcRows, srcCols;  // per batch
+  int outRows;           // valid output rows per batch (= srcRows, or srcCols when transposed)
+  int outRowsPad;        // rows per batch in the packed buffer (zero padded)
+  int K, Kp;             // reduction length and its 64-padded size
+  int segs;              // 1, or 3 for the hi/lo split
+  int roleB;
+  size_t srcBatchStride;
+};
+
+__device__ __forceinline__ void splitBf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+// segment s of the split layout holds hi or lo depending on the operand role:
+//   A: [hi, lo, hi]   B: [hi, hi, lo]
+__device__ __forceinline__ bool segmentIsLo(int s, int roleB) {
+  return roleB ? (s == 2) : (s == 1);
+}
+
+// no transpose: out[r][k] = src[r][k]; one thread per (row, pair of k)
+__global__ void __launch_bounds__(256) gPackRows(__nv_bfloat16* __restrict__ dst, const float* __restrict__ src, PackGeom g, int batches) {
+  int kPairs = g.Kp >> 1;
+  long long perBatch = (long long)g.outRowsPad * kPairs;
+  long long items = perBatch * batches;
+  size_t dstRowElems = (size_t)g.Kp * g.segs;
+  for(long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < items; w += (long long)gridDim.x * blockDim.x) {
+    int b = (int)(w / perBatch);
+    long long rem = w - (long long)b * perBatch;
+    int r = (int)(rem / kPairs);
+    int k = (int)(rem - (long long)r * kPairs) << 1;
+    float x0 = 0.f, x1 = 0.f;
+    if(r < g.outRows) {
+      const float* s = src + (size_t)b * g.srcBatchStride + (size_t)r * g.srcCols;
+      if(k < g.K)
+        x0 = s[k];
+      if(k + 1 < g.K)
+        x1 = s[k + 1];
+    }
+    __nv_bfloat16 h0, l0, h1, l1;
+    splitBf16(x0, h0, l0);
+    splitBf16(x1, h1, l1);
+    __nv_bfloat16* d = dst + ((size_t)b * g.outRowsPad + r) * dstRowElems + k;
+    for(int s = 0; s < g.segs; ++s) {
+      bool lo = g.segs == 3 && segmentIsLo(s, g.roleB);
+      __nv_bfloat162 v;
+      v.x = lo ? l0 : h0;
+      v.y = lo ? l1 : h1;
+      *reinterpret_cast<__nv_bfloat162*>(d + (size_t)s * g.Kp) = v;
+    }
+  }
+}
+
+// transpose: out[r][k] = src[k][r]; 32x32 tiles through shared memory
+__global__ void __launch_bounds__(256) gPackTranspose(__nv_bfloat16* __restrict__ dst, const float* __restrict__ src, PackGeom g) {
+  __shared__ float tile[32][33];
+  int b = blockIdx.z;
+  const float* s = src + (size_t)b * g.srcBatchStride;
+  int r0 = blockIdx.y * 32;  // output rows  = source columns
+  int k0 = blockIdx.x * 32;  // output K     = source rows
+  for(int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int sr = k0 + i, sc = r0 + threadIdx.x;
+    tile[i][threadIdx.x] = (sr < g.srcRows && sc < g.srcCols) ? s[(size_t)sr * g.srcCols + sc] : 0.f;
+  }
+  __syncthreads();
+  size_t dstRowElems = (size_t)g.Kp * g.segs;
+  for(int i = threadIdx.y; i < 32; i += blockDim.y) {
+    int r = r0 + i, k = k0 + threadIdx.x;
+    if(r < g.outRowsPad && k < g.Kp) {
+      float x = tile[threadIdx.x][i];  // zero outside the source by construction
+      __nv_bfloat16 hi, lo;
+      splitBf16(x, hi, lo);
+      __nv_bfloat16* d = dst + ((size_t)b * g.outRowsPad + r) * dstRowElems + k;
+      for(int sgm = 0; sgm < g.segs; ++sgm)
+        d[(size_t)sgm * g.Kp] = (g.segs == 3 && segmentIsLo(sgm, g.roleB)) ? lo : hi;
+    }
+  }
+}
+
+inline int roundUp(int x, int m) {
+  return (x + m - 1) / m * m;
+}
+
+struct Packed {
+  __nv_bfloat16* data;
+  int rowsPad;  // rows per batch
+  int Ktotal;   // Kp * segs
+};
+
+// Packs `batches` matrices [srcRows, srcCols] into K-major bf16.
+Packed packOperand(GemmHandle h, const float* src, int srcRows, int srcCols, int batches, size_t srcBatchStride, bool transpose, bool roleB, bool x3, int padRowsTo) {
+  PackGeom g;
+  g.srcRows = srcRows;
+  g.srcCols = srcCols;
+  g.outRows = transpose ? srcCols : srcRows;
+  g.K = transpose ? srcRows : srcCols;
+  g.Kp = roundUp(g.K, BLOCK_K);
+  g.segs = x3 ? 3 : 1;
+  g.roleB = roleB;
+  g.outRowsPad = padRowsTo > 0 ? roundUp(g.outRows, padRowsTo) : g.outRows;
+  g.srcBatchStride = srcBatchStride;
+
+  int flags = (transpose ? PACK_TRANSPOSE : 0) | (x3 ? PACK_X3 : 0) | (roleB ? PACK_ROLE_B : 0) | (padRowsTo << 4) | (batches << 12);
+  GemmContext::Key key{src, srcRows, srcCols, flags};
+  bool stable = h->stableLo && (const uint8_t*)src >= h->stableLo && (const uint8_t*)src < h->stableHi;
+  if(stable) {
+    auto it = h->cache.find(key);
+    if(it != h->cache.end())
+      return Packed{(__nv_bfloat16*)it->second, g.outRowsPad, g.Kp * g.segs};
+  }
+
+  size_t elems = (size_t)batches * g.outRowsPad * g.Kp * g.segs;
+  auto dst = (__nv_bfloat16*)h->take(elems * sizeof(__nv_bfloat16));
+  auto st = cudaStreamOfEngine();
+  if(!transpose) {
+    long long items = (long long)batches * g.outRowsPad * (g.Kp / 2);
+    gPackRows<<<gridFor((size_t)items, 256), 256, 0, st>>>(dst, src, g, batches);
+  } else {
+    dim3 grid((g.Kp + 31) / 32, (g.outRowsPad + 31) / 32, batches);
+    gPackTranspose<<<grid, dim3(32, 8), 0, st>>>(dst, src, g);
+  }
+  CUDA_LAUNCH_CHECK();
+  if(stable)
+    h->cache[key] = dst;
+  return Packed{dst, g.outRowsPad, g.Kp * g.segs};
+}
+
+// =============================================================================
+// fp32 SIMT GEMM (exact mode)
+// =============================================================================
+struct SimtArgs {
+  const float* A;
+  const float* B;
+  float* C;
+  const float* bias;
+  int M, N, K;
+  int lda, ldb, ldc;
+  int transA, transB;
+  float alpha, beta;
+  size_t strideA, strideB, strideC;
+};
+
+__global__ void __launch_bounds__(256) gGemmSimt(SimtArgs a) {
+  constexpr int TM = 64, TN = 64, TK = 16;
+  __shared__ float As[TK][TM + 1];
+  __shared__ float Bs[TK][TN + 1];
+  int b = blockIdx.z;
+  const float* A = a.A + (size_t)b * a.strideA;
+  const float* B = a.B + (size_t)b * a.strideB;
+  float* C = a.C + (size_t)b * a.strideC;
+  int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;  // 16 x 16 threads, 4 x 4 outputs each
+  float acc[4][4];
+#pragma unroll
+  for(int i = 0; i < 4; ++i)
+#pragma unroll
+    for(int j = 0; j < 4; ++j)
+      acc[i][j] = 0.f;
+
+  for(int k0 = 0; k0 < a.K; k0 += TK) {
+    for(int e = threadIdx.x; e < TM * TK; e += 256) {
+      // consecutive threads walk the contiguous source dimension
+      int mm, kk;
+      if(a.transA) {
+        mm = e % TM;
+        kk = e / TM;
+      } else {
+        kk = e % TK;
+        mm = e / TK;
+      }
+      int m = m0 + mm, k = k0 + kk;
+      float v = 0.f;
+      if(m < a.M && k < a.K)
+        v = a.transA ? A[(size_t)k * a.lda + m] : A[(size_t)m * a.lda + k];
+      As[kk][mm] = v;
+    }
+    for(int e = threadIdx.x; e < TN * TK; e += 256) {
+      int nn, kk;
+      if(a.transB) {
+        kk = e % TK;
+        nn = e / TK;
+      } else {
+        nn = e % TN;
+        kk = e / TN;
+      }
+      int n = n0 + nn, k = k0 + kk;
+      float v = 0.f;
+      if(n < a.N && k < a.K)
+        v = a.transB ? B[(size_t)n * a.ldb + k] : B[(size_t)k * a.ldb + n];
+      Bs[kk][nn] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for(int kk = 0; kk < TK; ++kk) {
+      float av[4], bv[4];
+#pragma unroll
+      for(int i = 0; i < 4; ++i)
+        av[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for(int j = 0; j < 4; ++j)
+        bv[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for(int i = 0; i < 4; ++i)
+#pragma unroll
+        for(int j = 0; j < 4; ++j)
+          acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for(int i = 0; i < 4; ++i) {
+    int m = m0 + ty * 4 + i;
+    if(m >= a.M)
+      continue;
+#pragma unroll
+    for(int j = 0; j < 4; ++j) {
+      int n = n0 + tx * 4 + j;
+      if(n >= a.N)
+        continue;
+      float v = a.alpha * acc[i][j];
+      if(a.bias)
+        v += a.bias[n];
+      size_t idx = (size_t)m * a.ldc + n;
+      if(a.beta != 0.f)
+        v += a.beta * C[idx];
+      C[idx] = v;
+    }
+  }
+}
+
+// =============================================================================
+// tcgen05 / TMA / TMEM kernel
+// =============================================================================
+__device__ __forceinline__ uint32_t smemAddr(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbarInit(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smemAddr(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbarExpectTx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P1;\n\t"
+      "LAB_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n\t"
+      "@P1 bra DONE;\n\t"
+      "bra LAB_WAIT;\n\t"
+      "DONE:\n\t"
+      "}" ::"r"(smemAddr(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tmaLoad2D(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smemAddr(dst)),
+      "l"((uint64_t)map),
+      "r"(smemAddr(bar)),
+      "r"(c0),
+      "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma(uint32_t tmemD, uint64_t descA, uint64_t descB, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmemD),
+      "l"(descA),
+      "l"(descB),
+      "r"(idesc),
+      "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void ummaCommit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smemAddr(bar)) : "memory");
+}
+__device__ __forceinline__ void tcgenFenceBefore() {
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tcgenFenceAfter() {
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+
+// K-major, 128-byte swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor):
+//   bits [0,14)  start address >> 4          bits [16,30) leading byte offset >> 4 (= 1, unused for SW128 K-major)
+//   bits [32,46) stride byte offset >> 4 (8 rows x 128 B = 1024 -> 64)
+//   bits [46,48) version = 1 (Blackwell)     bits [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t makeSmemDesc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)64 << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor) for bf16 x bf16 -> fp32, both K-major
+__host__ __device__ constexpr uint32_t makeInstrDesc(int M, int N) {
+  return (1u << 4)     // c_format  = F32
+         | (1u << 7)   // a_format  = BF16
+         | (1u << 10)  // b_format  = BF16
+         | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+struct TcArgs {
+  float* C;
+  const float* bias;
+  int M, N;
+  int ldc;
+  int kBlocks;          // total 64-wide K blocks
+  int kBlocksPerSplit;  // blocks handled by one z-slice
+  int splits;
+  int rowsPerBatchA, rowsPerBatchB;  // row pitch between batches in the packed operands (0 = shared)
+  size_t strideC;
+  float alpha, beta;
+  int atomicOut;  // combine with red.add (split-K)
+};
+
+template <int BN, int STAGES>
+struct TcSmem {
+  static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
+  static constexpr int B_BYTES = BN * BLOCK_K * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;  // + alignment slack
+};
+
+template <int BN, int STAGES>
+__global__ void __launch_bounds__(192) gGemmTcgen05(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcArgs a) {
+  typedef TcSmem<BN, STAGES> L;
+  extern __shared__ uint8_t smemRaw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smemRaw + 1023) & ~(uintptr_t)1023);
+  uint64_t* fullBar = (uint64_t*)(smem + L::BAR_OFFSET);
+  uint64_t* emptyBar = fullBar + STAGES;
+  uint64_t* tmemFullBar = emptyBar + STAGES;
+  uint32_t* tmemHolder = (uint32_t*)(tmemFullBar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m0 = blockIdx.x * BLOCK_M;
+  const int n0 = blockIdx.y * BN;
+  const int batch = blockIdx.z / a.splits;
+  const int split = blockIdx.z - batch * a.splits;
+  const int kb0 = split * a.kBlocksPerSplit;
+  const int nkb = min(a.kBlocksPerSplit, a.kBlocks - kb0);
+
+  if(warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
+    for(int s = 0; s < STAGES; ++s) {
+      mbarInit(fullBar + s, 1);
+      mbarInit(emptyBar + s, 1);
+    }
+    mbarInit(tmemFullBar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if(warp == 1) {
+    // 128 lanes x BN fp32 columns of tensor memory for the accumulator
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smemAddr(tmemHolder)), "r"((uint32_t)(BN < 32 ? 32 : BN)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgenFenceBefore();
+  __syncthreads();
+  tcgenFenceAfter();
+  const uint32_t tmemBase = *tmemHolder;
+
+  if(warp == 0) {
+    if(lane == 0) {
+      // ---------------- TMA producer ----------------
+      const int rowA = batch * a.rowsPerBatchA + m0;
+      const int rowB = batch * a.rowsPerBatchB + n0;
+      for(int i = 0; i < nkb; ++i) {
+        int s = i % STAGES;
+        uint32_t phase = (uint32_t)(i / STAGES) & 1u;
+        mbarWait(emptyBar + s, phase ^ 1u);
+        mbarExpectTx(fullBar + s, (uint32_t)L::STAGE_BYTES);
+        uint8_t* sa = smem + s * L::STAGE_BYTES;
+        uint8_t* sb = sa + L::A_BYTES;
+        int kc = (kb0 + i) * BLOCK_K;
+        tmaLoad2D(&tmA, fullBar + s, sa, kc, rowA);
+        tmaLoad2D(&tmB, fullBar + s, sb, kc, rowB);
+      }
+    }
+  } else if(warp == 1) {
+    if(lane == 0) {
+      // ---------------- MMA issuer (single thread) ----------------
+      constexpr uint32_t idesc = makeInstrDesc(BLOCK_M, BN);
+      for(int i = 0; i < nkb; ++i) {
+        int s = i % STAGES;
+        uint32_t phase = (uint32_t)(i / STAGES) & 1u;
+        mbarWait(fullBar + s, phase);
+        tcgenFenceAfter();
+        uint32_t sa = smemAddr(smem + s * L::STAGE_BYTES);
+        uint32_t sb = sa + L::A_BYTES;
+        uint64_t descA = makeSmemDesc(sa);
+        uint64_t descB = makeSmemDesc(sb);
+#pragma unroll
+        for(int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+          // advance 16 bf16 = 32 bytes inside the 128-byte swizzle row: +2 in the (>>4) address field
+          umma(tmemBase, descA + (uint64_t)(k * 2), descB + (uint64_t)(k * 2), idesc, (uint32_t)((i | k) != 0));
+        }
+        ummaCommit(emptyBar + s);  // frees the smem stage once these MMAs retire
+      }
+      ummaCommit(tmemFullBar);  // accumulator complete
+    }
+  } else {
+    // ---------------- epilogue: TMEM -> registers -> global ----------------
+    mbarWait(tmemFullBar, 0);
+    tcgenFenceAfter();
+    const int q = warp & 3;  // TMEM lane quarter this warp may access
+    const int row = m0 + q * 32 + lane;
+    float* Cb = a.C + (size_t)batch * a.strideC;
+    const bool addBias = a.bias != nullptr && split == 0;
+#pragma unroll 1
+    for(int c0 = 0; c0 < BN; c0 += 32) {
+      uint32_t r[32];
+      uint32_t taddr = tmemBase + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+            "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+            "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+            "=r"(r[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      int col0 = n0 + c0;
+      if(row < a.M && col0 < a.N) {
+        float* crow = Cb + (size_t)row * a.ldc + col0;
+        int ncols = min(32, a.N - col0);
+        bool vec = ncols == 32 && ((((uintptr_t)crow) & 15) == 0);
+        if(a.atomicOut) {
+          for(int j = 0; j < ncols; ++j) {
+            float v = a.alpha * __uint_as_float(r[j]);
+            if(addBias)
+              v += a.bias[col0 + j];
+            atomicAdd(crow + j, v);
+          }
+        } else if(vec) {
+#pragma unroll
+          for(int j = 0; j < 32; j += 4) {
+            float4 v;
+            v.x = a.alpha * __uint_as_float(r[j]);
+            v.y = a.alpha * __uint_as_float(r[j + 1]);
+            v.z = a.alpha * __uint_as_float(r[j + 2]);
+            v.w = a.alpha * __uint_as_float(r[j + 3]);
+            if(addBias) {
+              float4 bq = *reinterpret_cast<const float4*>(a.bias + col0 + j);
+              v.x += bq.x;
+              v.y += bq.y;
+              v.z += bq.z;
+              v.w += bq.w;
+            }
+            if(a.beta != 0.f) {
+              float4 cq = *reinterpret_cast<const float4*>(crow + j);
+              v.x += a.beta * cq.x;
+              v.y += a.beta * cq.y;
+              v.z += a.beta * cq.z;
+              v.w += a.beta * cq.w;
+            }
+            *reinterpret_cast<float4*>(crow + j) = v;
+          }
+        } else {
+          for(int j = 0; j < ncols; ++j) {
+            float v = a.alpha * __uint_as_float(r[j]);
+            if(addBias)
+              v += a.bias[col0 + j];
+            if(a.beta != 0.f)
+              v += a.beta * crow[j];
+            crow[j] = v;
+          }
+        }
+      }
+    }
+  }
+
+  tcgenFenceBefore();
+  __syncthreads();
+  if(warp == 1) {
+    __syncwarp();
+    tcgenFenceAfter();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "r"((uint32_t)(BN < 32 ? 32 : BN)));
+  }
+}
+
+CUtensorMap makeTensorMap(GemmHandle h, const __nv_bfloat16* base, uint64_t rows, uint64_t K, uint32_t boxRows) {
+  if(!h->encodeTiled) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    ABORT_IF(!fn || qres != cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available from the driver");
+    h->encodeTiled = (GemmContext::EncodeTiledFn)fn;
+  }
+  CUtensorMap map;
+  cuuint64_t gdim[2] = {K, rows};
+  cuuint64_t gstride[1] = {K * sizeof(__nv_bfloat16)};
+  cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, boxRows};
+  cuuint32_t estride[2] = {1, 1};
+  CUresult rc = h->encodeTiled(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ABORT_IF(rc != CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with code", (int)rc);
+  return map;
+}
+
+template <int BN, int STAGES>
+void launchTc(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, int batches) {
+  typedef TcSmem<BN, STAGES> L;
+  static bool configured = false;
+  if(!configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(gGemmTcgen05<BN, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  dim3 grid((a.M + BLOCK_M - 1) / BLOCK_M, (a.N + BN - 1) / BN, batches * a.splits);
+  gGemmTcgen05<BN, STAGES><<<grid, 192, L::TOTAL, cudaStreamOfEngine()>>>(tmA, tmB, a);
+  CUDA_LAUNCH_CHECK();
+}
+
+struct GemmProblem {
+  Tensor C, A, B, bias;
+  int rowsA, colsA, rowsB, colsB;  // per batch, as stored
+  int batches;
+  size_t strideA, strideB;  // 0 when the operand is shared by all batches
+  bool transA, transB;
+  float beta, alpha;
+};
+
+void runSimt(const GemmProblem& p) {
+  SimtArgs a;
+  a.A = p.A->data();
+  a.B = p.B->data();
+  a.C = p.C->data();
+  a.bias = p.bias ? p.bias->data() : nullptr;
+  a.M = p.transA ? p.colsA : p.rowsA;
+  a.K = p.transA ? p.rowsA : p.colsA;
+  a.N = p.transB ? p.rowsB : p.colsB;
+  a.lda = p.colsA;
+  a.ldb = p.colsB;
+  a.ldc = a.N;
+  a.transA = p.transA;
+  a.transB = p.transB;
+  a.alpha = p.alpha;
+  a.beta = p.beta;
+  a.strideA = p.strideA;
+  a.strideB = p.strideB;
+  a.strideC = (size_t)a.M * a.N;
+  dim3 grid((a.N + 63) / 64, (a.M + 63) / 64, p.batches);
+  gGemmSimt<<<grid, 256, 0, cudaStreamOfEngine()>>>(a);
+  CUDA_LAUNCH_CHECK();
+}
+
+void runTensorCore(GemmHandle h, const GemmProblem& p) {
+  const bool x3 = h->mode == GemmMode::BF16X3;
+  int M = p.transA ? p.colsA : p.rowsA;
+  int K = p.transA ? p.rowsA : p.colsA;
+  int N = p.transB ? p.rowsB : p.colsB;
+  bool batched = p.batches > 1;
+
+  // tile shape: fill the machine if 128-wide tiles cannot
+  long tiles128 = (long)((M + BLOCK_M - 1) / BLOCK_M) * ((N + 127) / 128) * p.batches;
+  int BN = (tiles128 >= kNumSMs && N > 64) ? 128 : 64;
+
+  // A operand (rows = M): K-major means "not transposed" for A, transposed source when transA
+  int batchesA = p.strideA ? p.batches : 1;
+  int batchesB = p.strideB ? p.batches : 1;
+  Packed pa = packOperand(h, p.A->data(), p.rowsA, p.colsA, batchesA, p.strideA, p.transA, false, x3, batched ? BLOCK_M : 0);
+  // B operand (rows = N): stored [K, N] when !transB -> needs the transposing pack
+  Packed pb = packOperand(h, p.B->data(), p.rowsB, p.colsB, batchesB, p.strideB, !p.transB, true, x3, batched ? BN : 0);
+  ABORT_IF(pa.Ktotal != pb.Ktotal, "packed operands disagree on K");
+
+  CUtensorMap tmA = makeTensorMap(h, pa.data, (uint64_t)pa.rowsPad * batchesA, (uint64_t)pa.Ktotal, BLOCK_M);
+  CUtensorMap tmB = makeTensorMap(h, pb.data, (uint64_t)pb.rowsPad * batchesB, (uint64_t)pb.Ktotal, (uint32_t)BN);
+
+  TcArgs a;
+  a.C = p.C->data();
+  a.bias = p.bias ? p.bias->data() : nullptr;
+  a.M = M;
+  a.N = N;
+  a.ldc = N;
+  a.kBlocks = pa.Ktotal / BLOCK_K;
+  a.rowsPerBatchA = (batched && p.strideA) ? pa.rowsPad : 0;
+  a.rowsPerBatchB = (batched && p.strideB) ? pb.rowsPad : 0;
+  a.strideC = (size_t)M * N;
+  a.alpha = p.alpha;
+  a.beta = p.beta;
+
+  // split-K when the tile grid cannot fill the SMs but K is long (weight gradients)
+  long tiles = (long)((M + BLOCK_M - 1) / BLOCK_M) * ((N + BN - 1) / BN) * p.batches;
+  int splits = 1;
+  if(!batched && tiles * 2 <= kNumSMs && a.kBlocks >= 8) {
+    splits = (int)std::min<long>((kNumSMs * 2 + tiles - 1) / tiles, a.kBlocks / 4);
+    splits = std::max(1, std::min(splits, 32));
+  }
+  a.kBlocksPerSplit = (a.kBlocks + splits - 1) / splits;
+  splits = (a.kBlocks + a.kBlocksPerSplit - 1) / a.kBlocksPerSplit;
+  a.splits = splits;
+  a.atomicOut = splits > 1;
+  if(a.atomicOut && p.beta != 1.f) {
+    // atomics accumulate onto C: bring C to beta * C first
+    using namespace functional;
+    if(p.beta == 0.f)
+      p.C->set(0);
+    else
+      Element(_1 = p.beta * _1, p.C);
+  }
+
+  if(BN == 128)
+    launchTc<128, 3>(tmA, tmB, a, p.batches);
+  else
+    launchTc<64, 4>(tmA, tmB, a, p.batches);
+}
+
+void runGemm(GemmHandle h, const GemmProblem& p) {
+  device::setDevice(p.C->getDevice());
+  int M = p.transA ? p.colsA : p.rowsA;
+  int K = p.transA ? p.rowsA : p.colsA;
+  int Kb = p.transB ? p.colsB : p.rowsB;
+  int N = p.transB ? p.rowsB : p.colsB;
+  ABORT_IF(K != Kb, "matrix product requires dimensions to match", K, Kb);
+  ABORT_IF((long)p.C->size() != (long)M * N * p.batches, "Prod: output tensor has the wrong size");
+  if(M == 0 || N == 0)
+    return;
+  if(h->mode == GemmMode::FP32)
+    runSimt(p);
+  else
+    runTensorCore(h, p);
+}
+
+}  // namespace
+
+void Prod(GemmHandle h, Tensor C, const Tensor A, const Tensor B, bool transA, bool transB, float beta, float scalar) {
+  GemmProblem p;
+  p.C = C;
+  p.A = A;
+  p.B = B;
+  p.bias = nullptr;
+  p.colsA = A->shape().back();
+  p.rowsA = A->shape().elements() / p.colsA;
+  p.colsB = B->shape().back();
+  p.rowsB = B->shape().elements() / p.colsB;
+  p.batches = 1;
+  p.strideA = p.strideB = 0;
+  p.transA = transA;
+  p.transB = transB;
+  p.beta = beta;
+  p.alpha = scalar;
+  runGemm(h, p);
+}
+
+void ProdAffine(GemmHandle h, Tensor C, const Tensor A, const Tensor B, const Tensor bias) {
+  GemmProblem p;
+  p.C = C;
+  p.A = A;
+  p.B = B;
+  p.bias = bias;
+  p.colsA = A->shape().back();
+  p.rowsA = A->shape().elements() / p.colsA;
+  p.colsB = B->shape().back();
+  p.rowsB = B->shape().elements() / p.colsB;
+  ABORT_IF((int)bias->size() != p.colsB, "ProdAffine: bias must be a row vector of the output width");
+  p.batches = 1;
+  p.strideA = p.strideB = 0;
+  p.transA = p.transB = false;
+  p.beta = 0.f;
+  p.alpha = 1.f;
+  runGemm(h, p);
+}
+
+void ProdBatched(GemmHandle h, Tensor C, const Tensor A, const Tensor B, bool transA, bool transB, float beta, float scalar) {
+  GemmProblem p;
+  p.C = C;
+  p.A = A;
+  p.B = B;
+  p.bias = nullptr;
+  p.rowsA = A->shape()[-2];
+  p.colsA = A->shape()[-1];
+  p.rowsB = B->shape()[-2];
+  p.colsB = B->shape()[-1];
+  size_t batchA = A->shape().elements() / ((size_t)p.rowsA * p.colsA);
+  size_t batchB = B->shape().elements() / ((size_t)p.rowsB * p.colsB);
+  p.batches = (int)std::max(batchA, batchB);
+  p.strideA = batchA == 1 ? 0 : (size_t)p.rowsA * p.colsA;
+  p.strideB = batchB == 1 ? 0 : (size_t)p.rowsB * p.colsB;
+  if(p.batches == 1)
+    p.strideA = p.strideB = 0;
+  p.transA = transA;
+  p.transB = transB;
+  p.beta = beta;
+  p.alpha = scalar;
+  runGemm(h, p);
+}
+
+}  // namespace marian

@@ -43,6 +43,9 @@ GemmMode getGemmMode(GemmHandle);
 // layout) and reused until invalidated; the graph invalidates at the start of
 // forward and after the optimizer step.
 void gemmInvalidateCache(GemmHandle);
+// Sources inside [ptr, ptr+bytes) (the parameter arena) are packed once per
+// step: their bf16 copies survive until the next gemmInvalidateCache().
+void gemmSetStableRange(GemmHandle, const void* ptr, size_t bytes);
 
 bool IsNan(Tensor in);
 

@@ -1,0 +1,161 @@
+// CUDA implementation of the engine's device services (tensors/device.h).
+//
+// One explicit stream per host thread carries ALL engine work: kernels, the
+// pinned-staging uploads, cost read-back.  Nothing in here synchronises except
+// synchronize() / copyH2DBlocking().  (The reference uses the legacy/per-thread
+// default stream and cudaStreamSynchronize(0) after most tensor methods:
+// src/tensors/tensor.cu:21-74.)
+#include <cuda_runtime.h>
+
+#include <cstdio>
+
+#include "common/definitions.h"
+#include "kernels/cuda_helpers.h"
+#include "tensors/device.h"
+
+namespace marian {
+namespace device {
+
+namespace {
+struct ThreadCtx {
+  int device{-1};
+  cudaStream_t own{nullptr};   // engine-owned stream of the current device
+  cudaStream_t user{nullptr};  // stream injected by the host harness
+  bool hasUser{false};
+  bool capturing{false};
+};
+thread_local ThreadCtx tctx;
+
+cudaStream_t stream() {
+  if(tctx.hasUser)
+    return tctx.user;
+  if(!tctx.own) {
+    if(tctx.device < 0)
+      setDevice(0);
+    CUDA_CHECK(cudaStreamCreateWithFlags(&tctx.own, cudaStreamNonBlocking));
+  }
+  return tctx.own;
+}
+
+__global__ void gFill(float* d, float v, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  size_t stride = (size_t)gridDim.x * blockDim.x;
+  for(; i < n; i += stride)
+    d[i] = v;
+}
+}  // namespace
+
+void setDevice(int deviceId) {
+  if(tctx.device == deviceId)
+    return;
+  CUDA_CHECK(cudaSetDevice(deviceId));
+  tctx.device = deviceId;
+  tctx.own = nullptr;  // stream is (re)created lazily for the new device
+}
+int getDevice() {
+  return tctx.device < 0 ? 0 : tctx.device;
+}
+
+void* currentStream() {
+  return (void*)stream();
+}
+void setStream(void* s) {
+  tctx.user = (cudaStream_t)s;
+  tctx.hasUser = (s != nullptr);
+}
+
+void* mallocDevice(size_t bytes) {
+  void* p = nullptr;
+  CUDA_CHECK(cudaMalloc(&p, bytes ? bytes : 256));
+  return p;
+}
+void freeDevice(void* p) {
+  if(p)
+    CUDA_CHECK(cudaFree(p));
+}
+void* mallocPinned(size_t bytes) {
+  void* p = nullptr;
+  CUDA_CHECK(cudaHostAlloc(&p, bytes ? bytes : 256, cudaHostAllocDefault));
+  return p;
+}
+void freePinned(void* p) {
+  if(p)
+    CUDA_CHECK(cudaFreeHost(p));
+}
+
+void copyH2D(void* dst, const void* src, size_t bytes) {
+  CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream()));
+}
+void copyH2DBlocking(void* dst, const void* src, size_t bytes) {
+  ABORT_IF(tctx.capturing, "blocking upload during CUDA graph capture");
+  CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream()));
+  CUDA_CHECK(cudaStreamSynchronize(stream()));
+}
+void copyD2H(void* dst, const void* src, size_t bytes) {
+  CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, stream()));
+}
+void copyD2D(void* dst, const void* src, size_t bytes) {
+  CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToDevice, stream()));
+}
+void zero(void* dst, size_t bytes) {
+  CUDA_CHECK(cudaMemsetAsync(dst, 0, bytes, stream()));
+}
+void fill(float* dst, float value, size_t n) {
+  if(!n)
+    return;
+  int threads = 256;
+  int blocks = (int)std::min<size_t>((n + threads - 1) / threads, 148 * 8);
+  gFill<<<blocks, threads, 0, stream()>>>(dst, value, n);
+  CUDA_CHECK(cudaGetLastError());
+}
+
+void synchronize() {
+  ABORT_IF(tctx.capturing, "stream synchronisation during CUDA graph capture");
+  CUDA_CHECK(cudaStreamSynchronize(stream()));
+}
+
+bool capturing() {
+  return tctx.capturing;
+}
+bool captureSupported() {
+  return true;
+}
+void beginCapture() {
+  ABORT_IF(tctx.capturing, "nested capture");
+  CUDA_CHECK(cudaStreamBeginCapture(stream(), cudaStreamCaptureModeRelaxed));
+  tctx.capturing = true;
+}
+void* endCapture() {
+  ABORT_IF(!tctx.capturing, "endCapture without beginCapture");
+  tctx.capturing = false;
+  cudaGraph_t graph = nullptr;
+  cudaError_t rc = cudaStreamEndCapture(stream(), &graph);
+  if(rc != cudaSuccess || !graph) {
+    fprintf(stderr, "[marian_b200] graph capture failed: %s\n", cudaGetErrorString(rc));
+    cudaGetLastError();
+    return nullptr;
+  }
+  cudaGraphExec_t exec = nullptr;
+  rc = cudaGraphInstantiate(&exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if(rc != cudaSuccess) {
+    fprintf(stderr, "[marian_b200] graph instantiate failed: %s\n", cudaGetErrorString(rc));
+    cudaGetLastError();
+    return nullptr;
+  }
+  return (void*)exec;
+}
+void launchGraph(void* exec) {
+  CUDA_CHECK(cudaGraphLaunch((cudaGraphExec_t)exec, stream()));
+}
+void destroyGraph(void* exec) {
+  if(exec)
+    cudaGraphExecDestroy((cudaGraphExec_t)exec);
+}
+
+const char* backendName() {
+  return "cuda";
+}
+
+}  // namespace device
+}  // namespace marian

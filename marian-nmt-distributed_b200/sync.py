@@ -1,0 +1,113 @@
+"""Host-side mirror of SyncGraphGroup for ONE PROCESS PER GPU.
+
+Reference: src/training/graph_group_sync.cu:42-188.  Each rank owns a Trainer
+(ExpressionGraph + model + shard optimizer, all native) and this class drives
+one update:
+
+    compute_gradients()                      native forward+backward (graph replay)
+    reduce_scatter(sum) flat gradient arena  torch.distributed (NCCL over NVLink / gloo in CPU tests)
+    update_shard()                           native fused {x 1/N, shard-norm clip, Adam}
+    all_gather flat parameter arena          torch.distributed
+
+torch is used only as plumbing: the arenas are exposed zero-copy as torch
+tensors (CUDA array interface / numpy) and the engine runs on torch's current
+CUDA stream so that collectives and kernels are ordered without host syncs.
+"""
+import ctypes
+
+import numpy as np
+
+
+class _CudaView:
+    """Zero-copy __cuda_array_interface__ view of engine device memory."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (ptr, False), "version": 2}
+
+
+class TorchExchange:
+    """reduce-scatter / all-gather / broadcast over a torch.distributed process group."""
+
+    def __init__(self, group=None):
+        import torch.distributed as dist
+
+        self.dist = dist
+        self.group = group
+        self.world = dist.get_world_size(group)
+        self.rank = dist.get_rank(group)
+
+    def reduce_scatter(self, shard_out, flat):
+        if self.dist.get_backend(self.group) == "gloo":
+            # gloo has no reduce_scatter: all-reduce the arena, keep the owned shard
+            self.dist.all_reduce(flat, group=self.group)
+            n = shard_out.numel()
+            shard_out.copy_(flat[self.rank * n:(self.rank + 1) * n])
+        else:
+            self.dist.reduce_scatter_tensor(shard_out, flat, group=self.group)
+
+    def all_gather(self, flat, shard_elems):
+        mine = flat[self.rank * shard_elems:(self.rank + 1) * shard_elems]
+        if self.dist.get_backend(self.group) == "gloo":
+            parts = [flat[r * shard_elems:(r + 1) * shard_elems] for r in range(self.world)]
+            self.dist.all_gather(parts, mine.clone(), group=self.group)
+        else:
+            self.dist.all_gather_into_tensor(flat, mine, group=self.group)
+
+    def broadcast(self, flat):
+        self.dist.broadcast(flat, src=0, group=self.group)
+
+    def mean_cost(self, c, device):
+        import torch
+
+        t = torch.tensor([c], dtype=torch.float64, device=device)
+        self.dist.all_reduce(t, group=self.group)
+        return float(t.item()) / self.world
+
+
+class SyncTrainer:
+    def __init__(self, lib, options, device, rank, nranks, exchange):
+        import torch
+
+        self.torch = torch
+        self.lib = lib
+        self.rank, self.nranks = rank, nranks
+        self.exchange = exchange
+        self.cuda = lib.backend == "cuda"
+        self.device = torch.device("cuda", device) if self.cuda else torch.device("cpu")
+        if self.cuda:
+            torch.cuda.set_device(device)
+            # engine work is issued on torch's current stream: collectives and
+            # kernels are then ordered by the stream, no host synchronisation
+            lib.set_stream(torch.cuda.current_stream().cuda_stream)
+        self.trainer = lib.trainer(options, device=device, rank=rank, nranks=nranks)
+        self.first = True
+        self._views = None
+
+    def _tensor(self, ptr, n):
+        if self.cuda:
+            return self.torch.as_tensor(_CudaView(ptr, n), device=self.device)
+        buf = (ctypes.c_float * n).from_address(ptr)
+        return self.torch.from_numpy(np.frombuffer(buf, dtype=np.float32))
+
+    def _arenas(self):
+        if self._views is None:
+            p, n = self.trainer.params_arena()
+            g, ng = self.trainer.grads_arena()
+            s, ns = self.trainer.shard_grads_arena()
+            assert n == ng == ns * self.nranks, (n, ng, ns)
+            self._views = (self._tensor(p, n), self._tensor(g, ng), self._tensor(s, ns), ns)
+        return self._views
+
+    def step(self):
+        """One update on the trainer's current batch (set via self.trainer.*batch*)."""
+        self.trainer.compute_gradients()
+        params, grads, shard, ns = self._arenas()
+        if self.first:
+            self.exchange.broadcast(params)  # reference :46-53: replicas start from graph 0
+            self.first = False
+        self.exchange.reduce_scatter(shard, grads)
+        self.trainer.update_shard()
+        self.exchange.all_gather(params, ns)
+
+    def cost(self):
+        return self.exchange.mean_cost(self.trainer.cost(), self.device)

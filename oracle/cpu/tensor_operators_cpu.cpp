@@ -35,6 +35,7 @@ void destroyGemmContext(GemmHandle h) { delete h; }
 void setGemmMode(GemmHandle h, GemmMode m) { h->mode = m; }
 GemmMode getGemmMode(GemmHandle h) { return h->mode; }
 void gemmInvalidateCache(GemmHandle) {}
+void gemmSetStableRange(GemmHandle, const void*, size_t) {}
 
 static inline float stableLogit(float x) {
   // reference: tensor_operators.cu:15-23

