@@ -63,6 +63,11 @@ int mrn_gemm_create(void** handle, int device);
 int mrn_gemm_destroy(void* handle);
 int mrn_gemm_set_mode(void* handle, int mode);
 
+/* measurement hook: enable != 0 resets and starts timing every tensor-core GEMM launch with
+ * CUDA events on the engine stream; enable == 0 stops and returns total ms, algorithmic
+ * flops (2MNK) and launch count.  Eager steps only (not inside a replayed graph). */
+int mrn_gemm_profile(int enable, double* ms, double* flops, size_t* launches);
+
 /* Prod / ProdBatched: tensor_operators.h:295-311, .cu:543-654 */
 int mrn_prod(void* gemm, mrn_tensor C, mrn_tensor A, mrn_tensor B, int transA, int transB, float beta, float scalar);
 int mrn_prod_batched(void* gemm, mrn_tensor C, mrn_tensor A, mrn_tensor B, int transA, int transB, float beta, float scalar);
@@ -173,6 +178,9 @@ int mrn_trainer_param_names(void* trainer, char* buffer, size_t capacity, size_t
 int mrn_trainer_batch_words(void* trainer, size_t* src_words, size_t* total_words);
 /* statistics: number of tape nodes of the last eager build, captured plans, replays */
 int mrn_trainer_stats(void* trainer, size_t* tape_nodes, size_t* plans, size_t* replays, size_t* workspace_bytes);
+
+/* kernel nodes in the most recently captured step graph (0 before any capture) */
+int mrn_trainer_graph_kernels(void* trainer, size_t* kernels);
 
 /* Runs one of the reference's unit-test graphs (src/tests/*.cpp) through the
  * graph API and returns the values the reference test asserts on.  Used by the

@@ -35,6 +35,7 @@ _SIGNATURES = {
     "mrn_gemm_create": [ctypes.POINTER(_V), _I],
     "mrn_gemm_destroy": [_V],
     "mrn_gemm_set_mode": [_V, _I],
+    "mrn_gemm_profile": [_I, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_SZ)],
     "mrn_prod": [_V, _T, _T, _T, _I, _I, _F, _F],
     "mrn_prod_batched": [_V, _T, _T, _T, _I, _I, _F, _F],
     "mrn_prod_affine": [_V, _T, _T, _T, _T],
@@ -80,6 +81,7 @@ _SIGNATURES = {
     "mrn_trainer_get_tensor": [_V, ctypes.c_char_p, _I, _V, _SZ, ctypes.POINTER(_SZ)],
     "mrn_trainer_param_names": [_V, ctypes.c_char_p, _SZ, ctypes.POINTER(_SZ)],
     "mrn_trainer_batch_words": [_V, ctypes.POINTER(_SZ), ctypes.POINTER(_SZ)],
+    "mrn_trainer_graph_kernels": [_V, ctypes.POINTER(_SZ)],
     "mrn_trainer_stats": [_V, ctypes.POINTER(_SZ), ctypes.POINTER(_SZ), ctypes.POINTER(_SZ), ctypes.POINTER(_SZ)],
 }
 # exported by the golden-vector driver (tests/cpp/graph_golden.cpp)
@@ -126,6 +128,7 @@ class DeviceArray:
         m.rank = len(shape)
         for i, s in enumerate(shape):
             m.shape[i] = int(s)
+        m._owner = self  # keeps the device buffer alive as long as the view exists
         return m
 
     def free(self):
@@ -202,6 +205,7 @@ class Library:
         arr = (MrnTensor * len(ts))()
         for i, t in enumerate(ts):
             arr[i] = t
+        arr._owners = list(ts)  # element assignment copies the struct, not the python-side owner
         return arr
 
     def golden(self, case):
@@ -337,6 +341,11 @@ class Trainer:
         s, t = ctypes.c_size_t(), ctypes.c_size_t()
         self.lib._ck(self.lib.c.mrn_trainer_batch_words(self.h, ctypes.byref(s), ctypes.byref(t)))
         return s.value, t.value
+
+    def graph_kernels(self):
+        k = ctypes.c_size_t()
+        self.lib._ck(self.lib.c.mrn_trainer_graph_kernels(self.h, ctypes.byref(k)))
+        return k.value
 
     def stats(self):
         a, b, c, d = ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t(), ctypes.c_size_t()

@@ -94,11 +94,10 @@ int mrn_memcpy_h2d(void* dst, const void* src, size_t bytes) {
 }
 int mrn_memcpy_d2h(void* dst, const void* src, size_t bytes) {
   return guarded([&] {
-    void* p = device::mallocPinned(bytes);
+    void* p = device::pinnedScratch(bytes);
     device::copyD2H(p, src, bytes);
     device::synchronize();
     std::memcpy(dst, p, bytes);
-    device::freePinned(p);
   });
 }
 int mrn_memset_zero(void* dst, size_t bytes) {
@@ -113,6 +112,10 @@ int mrn_gemm_destroy(void* handle) {
 }
 int mrn_gemm_set_mode(void* handle, int mode) {
   return guarded([&] { setGemmMode((GemmHandle)handle, (GemmMode)mode); });
+}
+
+int mrn_gemm_profile(int enable, double* ms, double* flops, size_t* launches) {
+  return guarded([&] { gemmProfile(enable, ms, flops, launches); });
 }
 
 int mrn_prod(void* g, mrn_tensor C, mrn_tensor A, mrn_tensor B, int tA, int tB, float beta, float scalar) {
@@ -477,6 +480,10 @@ int mrn_trainer_stats(void* trainer, size_t* tapeNodes, size_t* plans, size_t* r
     *replays = t->replays;
     *workspaceBytes = t->worker().graph()->allocator()->peak();
   });
+}
+
+int mrn_trainer_graph_kernels(void* trainer, size_t* kernels) {
+  return guarded([&] { *kernels = ((Trainer*)trainer)->worker().replay().lastPlanKernels(); });
 }
 
 }  // extern "C"

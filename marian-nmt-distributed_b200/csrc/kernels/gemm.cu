@@ -127,6 +127,44 @@ void gemmSetStableRange(GemmHandle h, const void* lo, size_t bytes) {
   h->stableHi = h->stableLo + bytes;
 }
 
+// ---- optional per-launch timing of the tensor-core kernel (bench.py roofline) ----
+namespace {
+struct GemmProfile {
+  bool enabled{false};
+  double flops{0};
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
+};
+GemmProfile g_profile;
+}  // namespace
+
+// enable != 0: reset and start recording; enable == 0: stop, synchronise and report
+void gemmProfile(int enable, double* ms, double* flops, size_t* launches) {
+  if(enable) {
+    for(auto& e : g_profile.events) {
+      cudaEventDestroy(e.first);
+      cudaEventDestroy(e.second);
+    }
+    g_profile.events.clear();
+    g_profile.flops = 0;
+    g_profile.enabled = true;
+    *ms = 0;
+    *flops = 0;
+    *launches = 0;
+    return;
+  }
+  g_profile.enabled = false;
+  device::synchronize();
+  double total = 0;
+  for(auto& e : g_profile.events) {
+    float t = 0;
+    if(cudaEventElapsedTime(&t, e.first, e.second) == cudaSuccess)
+      total += t;
+  }
+  *ms = total;
+  *flops = g_profile.flops;
+  *launches = g_profile.events.size();
+}
+
 namespace {
 
 constexpr int BLOCK_M = 128;
@@ -751,10 +789,22 @@ void runTensorCore(GemmHandle h, const GemmProblem& p) {
       Element(_1 = p.beta * _1, p.C);
   }
 
+  bool profile = g_profile.enabled && !device::capturing();
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if(profile) {
+    CUDA_CHECK(cudaEventCreate(&e0));
+    CUDA_CHECK(cudaEventCreate(&e1));
+    CUDA_CHECK(cudaEventRecord(e0, cudaStreamOfEngine()));
+  }
   if(BN == 128)
     launchTc<128, 3>(tmA, tmB, a, p.batches);
   else
     launchTc<64, 4>(tmA, tmB, a, p.batches);
+  if(profile) {
+    CUDA_CHECK(cudaEventRecord(e1, cudaStreamOfEngine()));
+    g_profile.events.push_back({e0, e1});
+    g_profile.flops += 2.0 * M * N * K * p.batches;  // algorithmic flops (not the 3x of the split mode)
+  }
 }
 
 void runGemm(GemmHandle h, const GemmProblem& p) {

@@ -47,6 +47,9 @@ void gemmInvalidateCache(GemmHandle);
 // step: their bf16 copies survive until the next gemmInvalidateCache().
 void gemmSetStableRange(GemmHandle, const void* ptr, size_t bytes);
 
+// Per-launch CUDA-event timing of the tensor-core GEMM (eager steps only).
+void gemmProfile(int enable, double* ms, double* flops, size_t* launches);
+
 bool IsNan(Tensor in);
 
 void TransposeND(Tensor out, Tensor in, const std::vector<int>& vAxis);

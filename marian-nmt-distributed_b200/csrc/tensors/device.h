@@ -31,6 +31,10 @@ void* mallocDevice(size_t bytes);
 void freeDevice(void* p);
 void* mallocPinned(size_t bytes);
 void freePinned(void* p);
+// Thread-local pinned bounce buffer of at least `bytes` (grows, never shrinks):
+// cudaHostAlloc/cudaFreeHost cost ~0.1-100 ms per call depending on the host, so
+// blocking read-backs must not allocate.  Valid until the next call on this thread.
+void* pinnedScratch(size_t bytes);
 
 // All asynchronous on currentStream().  `src` of copyH2D must be pinned memory
 // that stays valid until the copy ran (see tensors/staging.h).
@@ -58,6 +62,8 @@ void copyH2DBlocking(void* dst, const void* src, size_t bytes);
 bool captureSupported();
 void beginCapture();
 void* endCapture();
+// kernel nodes in the graph returned by the last endCapture() of this thread
+size_t lastCaptureKernelCount();
 void launchGraph(void* exec);
 void destroyGraph(void* exec);
 

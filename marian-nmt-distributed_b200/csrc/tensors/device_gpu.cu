@@ -7,7 +7,9 @@
 // src/tensors/tensor.cu:21-74.)
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstdio>
+#include <vector>
 
 #include "common/definitions.h"
 #include "kernels/cuda_helpers.h"
@@ -23,6 +25,7 @@ struct ThreadCtx {
   cudaStream_t user{nullptr};  // stream injected by the host harness
   bool hasUser{false};
   bool capturing{false};
+  size_t lastKernelCount{0};
 };
 thread_local ThreadCtx tctx;
 
@@ -83,6 +86,18 @@ void freePinned(void* p) {
     CUDA_CHECK(cudaFreeHost(p));
 }
 
+void* pinnedScratch(size_t bytes) {
+  static thread_local void* buf = nullptr;
+  static thread_local size_t cap = 0;
+  if(bytes > cap) {
+    if(buf)
+      CUDA_CHECK(cudaFreeHost(buf));
+    cap = std::max(bytes, (size_t)1 << 20);
+    CUDA_CHECK(cudaHostAlloc(&buf, cap, cudaHostAllocDefault));
+  }
+  return buf;
+}
+
 void copyH2D(void* dst, const void* src, size_t bytes) {
   CUDA_CHECK(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyHostToDevice, stream()));
 }
@@ -135,6 +150,19 @@ void* endCapture() {
     cudaGetLastError();
     return nullptr;
   }
+  {
+    size_t n = 0;
+    tctx.lastKernelCount = 0;
+    if(cudaGraphGetNodes(graph, nullptr, &n) == cudaSuccess && n > 0) {
+      std::vector<cudaGraphNode_t> nodes(n);
+      cudaGraphGetNodes(graph, nodes.data(), &n);
+      for(auto node : nodes) {
+        cudaGraphNodeType type;
+        if(cudaGraphNodeGetType(node, &type) == cudaSuccess && type == cudaGraphNodeTypeKernel)
+          tctx.lastKernelCount++;
+      }
+    }
+  }
   cudaGraphExec_t exec = nullptr;
   rc = cudaGraphInstantiate(&exec, graph, 0);
   cudaGraphDestroy(graph);
@@ -144,6 +172,9 @@ void* endCapture() {
     return nullptr;
   }
   return (void*)exec;
+}
+size_t lastCaptureKernelCount() {
+  return tctx.lastKernelCount;
 }
 void launchGraph(void* exec) {
   CUDA_CHECK(cudaGraphLaunch((cudaGraphExec_t)exec, stream()));

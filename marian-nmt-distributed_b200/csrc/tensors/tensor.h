@@ -119,11 +119,7 @@ public:
       return p;
     }
     // no graph scope (tests, one-off initialisation): blocking upload
-    void* p = device::mallocPinned(bytes);
-    std::memcpy(p, src, bytes);
-    device::copyH2D(data(), p, bytes);
-    device::synchronize();
-    device::freePinned(p);
+    device::copyH2DBlocking(data(), src, bytes);
     return nullptr;
   }
 
@@ -133,11 +129,10 @@ private:
   void fetch(const float* src, float* dst, size_t n) {
     ABORT_IF(device::capturing(), "Host read-back of a tensor during CUDA graph capture");
     device::setDevice(device_);
-    void* p = device::mallocPinned(n * sizeof(float));
+    void* p = device::pinnedScratch(n * sizeof(float));
     device::copyD2H(p, src, n * sizeof(float));
     device::synchronize();
     std::memcpy(dst, p, n * sizeof(float));
-    device::freePinned(p);
   }
 
   Ptr<MemoryPiece> memory_;

@@ -31,6 +31,7 @@ public:
     Ptr<Staging> staging;
     std::vector<BatchUpload> uploads;
     size_t launches{0};
+    size_t kernels{0};  // kernel nodes recorded in the graph
   };
 
   ~StepReplay() { clear(); }
@@ -71,15 +72,19 @@ public:
   Plan& store(const std::vector<int>& key, void* exec, Ptr<ExpressionGraph> graph) {
     Plan& p = plans_[key];
     p.exec = exec;
+    p.kernels = device::lastCaptureKernelCount();
+    lastKernels_ = p.kernels;
     p.uploads = graph->batchUploads();
     p.staging = graph->detachStaging();
     return p;
   }
 
   size_t size() const { return plans_.size(); }
+  size_t lastPlanKernels() const { return lastKernels_; }
 
 private:
   bool enabled_{true};
+  size_t lastKernels_{0};
   std::map<std::vector<int>, Plan> plans_;
   std::map<std::vector<int>, int> seen_;
 };

@@ -25,6 +25,16 @@ void freeDevice(void* p) { std::free(p); }
 void* mallocPinned(size_t bytes) { return mallocDevice(bytes); }
 void freePinned(void* p) { std::free(p); }
 
+void* pinnedScratch(size_t bytes) {
+  static thread_local void* buf = nullptr;
+  static thread_local size_t cap = 0;
+  if(bytes > cap) {
+    std::free(buf);
+    cap = bytes < 4096 ? 4096 : bytes;
+    buf = mallocDevice(cap);
+  }
+  return buf;
+}
 void copyH2D(void* dst, const void* src, size_t bytes) { std::memcpy(dst, src, bytes); }
 void copyH2DBlocking(void* dst, const void* src, size_t bytes) { std::memcpy(dst, src, bytes); }
 void copyD2H(void* dst, const void* src, size_t bytes) { std::memcpy(dst, src, bytes); }
@@ -40,6 +50,7 @@ bool capturing() { return false; }
 bool captureSupported() { return false; }
 void beginCapture() { ABORT("oracle: capture not supported"); }
 void* endCapture() { return nullptr; }
+size_t lastCaptureKernelCount() { return 0; }
 void launchGraph(void*) {}
 void destroyGraph(void*) {}
 

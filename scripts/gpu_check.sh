@@ -12,9 +12,8 @@ run() { # name timeout cmd...
   echo "rc=$rc $(tail -n 1 gpurun_out/$name.log)" | tee -a gpurun_out/summary.txt
 }
 : > gpurun_out/summary.txt
-run golden 300 python -m pytest tests/test_gpu_golden.py -q -x -m gpu
-run ops 600 python -m pytest tests/test_gpu_ops.py -q -m gpu
-run gemm_fp32 600 python -m pytest tests/test_gpu_gemm.py -q -m gpu -k "0-"
-run gemm_tc 600 python -m pytest tests/test_gpu_gemm.py -q -m gpu -k "not 0-"
-run model 900 python -m pytest tests/test_gpu_model.py -q -m gpu
-for f in golden ops gemm_fp32 gemm_tc model; do echo "--- $f"; grep -E "^(FAILED|ERROR)|passed|failed" gpurun_out/$f.log | head -40; done
+run golden 300 python -m pytest tests/test_gpu_golden.py -q -x -m gpu --durations=8
+run ops 600 python -m pytest tests/test_gpu_ops.py -q -m gpu --durations=8
+run gemm 900 python -m pytest tests/test_gpu_gemm.py -q -m gpu --durations=8
+run model 900 python -m pytest tests/test_gpu_model.py -q -m gpu --durations=8
+for f in golden ops gemm model; do echo "--- $f"; grep -E "^(FAILED|ERROR)|passed|failed" gpurun_out/$f.log | head -40; done

@@ -65,7 +65,7 @@ def test_prod(cuda, oracle, mode, sa, sb, tA, tB, beta, alpha):
     ((64, 8, 50, 64), (64, 8, 50, 64), False, True),    # Q K^T  (config B)
     ((64, 8, 50, 50), (64, 8, 50, 64), False, False),   # P V
     ((64, 8, 50, 50), (64, 8, 50, 64), True, False),    # backward forms
-    ((64, 8, 50, 64), (64, 8, 50, 50), False, True),
+    ((64, 8, 50, 64), (64, 8, 50, 64), True, False),    # A^T B  [64,64]
     ((3, 2, 7, 5), (3, 2, 5, 9), False, False),
     ((1, 1, 130, 70), (4, 2, 70, 33), False, False),    # A shared by all batches (stride 0)
     ((4, 2, 33, 70), (1, 1, 70, 130), False, False),    # B shared
