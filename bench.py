@@ -200,7 +200,11 @@ def main():
     pkg = graft.load_package()
     lib = pkg.load()
     lib.call("mrn_set_device", local_rank)
-    lib.set_stream(torch.cuda.current_stream().cuda_stream)  # engine work on torch's stream: events + NCCL ordering
+    # engine work, NCCL collectives and the timing events all live on ONE side stream
+    # (the legacy default stream cannot be graph-captured)
+    side = torch.cuda.Stream()
+    torch.cuda.set_stream(side)
+    lib.set_stream(side.cuda_stream)
 
     W = max(3, args.warmup)
     K = args.steps

@@ -169,6 +169,7 @@ namespace {
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle row
+constexpr int kStagePitch = 36;  // floats per staged epilogue row: 144 B keeps float4 alignment, conflict-free
 constexpr int UMMA_K = 16;
 
 // =============================================================================
@@ -594,7 +595,6 @@ __global__ void __launch_bounds__(192) gGemmTcgen05(const __grid_constant__ CUte
     mbarWait(tmemFullBar, 0);
     tcgenFenceAfter();
     const int q = warp & 3;  // TMEM lane quarter this warp may access
-    const int row = m0 + q * 32 + lane;
     float* Cb = a.C + (size_t)batch * a.strideC;
     const bool addBias = a.bias != nullptr && split == 0;
 #pragma unroll 1
@@ -611,53 +611,68 @@ __global__ void __launch_bounds__(192) gGemmTcgen05(const __grid_constant__ CUte
             "=r"(r[31])
           : "r"(taddr));
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      int col0 = n0 + c0;
-      if(row < a.M && col0 < a.N) {
-        float* crow = Cb + (size_t)row * a.ldc + col0;
-        int ncols = min(32, a.N - col0);
-        bool vec = ncols == 32 && ((((uintptr_t)crow) & 15) == 0);
-        if(a.atomicOut) {
-          for(int j = 0; j < ncols; ++j) {
-            float v = a.alpha * __uint_as_float(r[j]);
-            if(addBias)
-              v += a.bias[col0 + j];
-            atomicAdd(crow + j, v);
-          }
-        } else if(vec) {
+      // Stage the 32 x 32 block through shared memory (the smem ring is idle once the
+      // accumulator is complete) so that global accesses are row-contiguous: a thread owns
+      // a ROW of the TMEM tile, but 8 lanes x float4 must cover 128 contiguous bytes of C.
+      float* stage = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * kStagePitch);
+      {
+        float4* srow = reinterpret_cast<float4*>(stage + lane * kStagePitch);
 #pragma unroll
-          for(int j = 0; j < 32; j += 4) {
-            float4 v;
-            v.x = a.alpha * __uint_as_float(r[j]);
-            v.y = a.alpha * __uint_as_float(r[j + 1]);
-            v.z = a.alpha * __uint_as_float(r[j + 2]);
-            v.w = a.alpha * __uint_as_float(r[j + 3]);
-            if(addBias) {
-              float4 bq = *reinterpret_cast<const float4*>(a.bias + col0 + j);
-              v.x += bq.x;
-              v.y += bq.y;
-              v.z += bq.z;
-              v.w += bq.w;
+        for(int j = 0; j < 8; ++j)
+          srow[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+      }
+      __syncwarp();
+      const int col0 = n0 + c0;
+      const int rowBase = m0 + q * 32;
+      if(col0 < a.N && rowBase < a.M) {
+        const int ncols = min(32, a.N - col0);
+        const bool vec = ncols == 32 && ((a.ldc & 3) == 0) && ((((uintptr_t)(Cb + col0)) & 15) == 0) && !a.atomicOut;
+        if(vec) {
+          const int sub = lane >> 3;         // row within a group of 4
+          const int cq = (lane & 7) * 4;     // first of this lane's 4 columns
+          float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+          if(addBias)
+            bq = *reinterpret_cast<const float4*>(a.bias + col0 + cq);
+#pragma unroll
+          for(int rr = 0; rr < 32; rr += 4) {
+            int rloc = rr + sub;
+            int grow = rowBase + rloc;
+            if(grow < a.M) {
+              float4 acc = *reinterpret_cast<const float4*>(stage + rloc * kStagePitch + cq);
+              float* cp = Cb + (size_t)grow * a.ldc + col0 + cq;
+              float4 v;
+              v.x = a.alpha * acc.x + bq.x;
+              v.y = a.alpha * acc.y + bq.y;
+              v.z = a.alpha * acc.z + bq.z;
+              v.w = a.alpha * acc.w + bq.w;
+              if(a.beta != 0.f) {
+                float4 old = *reinterpret_cast<const float4*>(cp);
+                v.x += a.beta * old.x;
+                v.y += a.beta * old.y;
+                v.z += a.beta * old.z;
+                v.w += a.beta * old.w;
+              }
+              *reinterpret_cast<float4*>(cp) = v;
             }
-            if(a.beta != 0.f) {
-              float4 cq = *reinterpret_cast<const float4*>(crow + j);
-              v.x += a.beta * cq.x;
-              v.y += a.beta * cq.y;
-              v.z += a.beta * cq.z;
-              v.w += a.beta * cq.w;
-            }
-            *reinterpret_cast<float4*>(crow + j) = v;
           }
-        } else {
-          for(int j = 0; j < ncols; ++j) {
-            float v = a.alpha * __uint_as_float(r[j]);
-            if(addBias)
-              v += a.bias[col0 + j];
-            if(a.beta != 0.f)
-              v += a.beta * crow[j];
-            crow[j] = v;
+        } else if(lane < ncols) {
+          // general path: lane = column, rows walked one by one (still 128-byte contiguous per row)
+          float bv = addBias ? a.bias[col0 + lane] : 0.f;
+          int rmax = min(32, a.M - rowBase);
+          for(int rloc = 0; rloc < rmax; ++rloc) {
+            float v = a.alpha * stage[rloc * kStagePitch + lane] + bv;
+            float* cp = Cb + (size_t)(rowBase + rloc) * a.ldc + col0 + lane;
+            if(a.atomicOut) {
+              atomicAdd(cp, v);
+            } else {
+              if(a.beta != 0.f)
+                v += a.beta * *cp;
+              *cp = v;
+            }
           }
         }
       }
+      __syncwarp();  // staging buffer is reused by the next 32-column block
     }
   }
 

@@ -76,8 +76,12 @@ class SyncTrainer:
         self.device = torch.device("cuda", device) if self.cuda else torch.device("cpu")
         if self.cuda:
             torch.cuda.set_device(device)
-            # engine work is issued on torch's current stream: collectives and
-            # kernels are then ordered by the stream, no host synchronisation
+            # Engine work and torch's collectives share ONE non-default stream: kernels,
+            # NCCL and CUDA-event timing are then ordered by the stream with no host
+            # synchronisation.  (The legacy default stream cannot be graph-captured.)
+            if torch.cuda.current_stream().cuda_stream == 0:
+                self.stream = torch.cuda.Stream(device)
+                torch.cuda.set_stream(self.stream)
             lib.set_stream(torch.cuda.current_stream().cuda_stream)
         self.trainer = lib.trainer(options, device=device, rank=rank, nranks=nranks)
         self.first = True

@@ -270,7 +270,7 @@ namespace {
 void sgemm_nn(int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb, float beta, float* C, int ldc, bool parallel) {
   constexpr int BM = 8, BN = 64;
   int mBlocks = (M + BM - 1) / BM, nBlocks = (N + BN - 1) / BN;
-#pragma omp parallel for collapse(2) schedule(static) if(parallel)
+#pragma omp parallel for collapse(2) schedule(static) if(parallel && (long)M * N * K > (1L << 20))
   for(int mb = 0; mb < mBlocks; ++mb)
     for(int nb = 0; nb < nBlocks; ++nb) {
       int i0 = mb * BM, j0 = nb * BN;
@@ -365,7 +365,7 @@ void ProdBatched(GemmHandle, Tensor C, const Tensor A, const Tensor B, bool tran
   size_t batches = std::max(batchA, batchB);
   size_t strideA = batchA == 1 ? 0 : (size_t)rowsA * colsA;
   size_t strideB = batchB == 1 ? 0 : (size_t)rowsB * colsB;
-#pragma omp parallel for
+#pragma omp parallel for if(batches * (size_t)m * n > 4096)
   for(size_t b = 0; b < batches; ++b)
     gemmRaw(C->data() + b * (size_t)m * n, A->data() + b * strideA, B->data() + b * strideB, rowsA, colsA, rowsB, colsB, transA, transB, beta, scalar, false);
 }

@@ -5,6 +5,10 @@ import sys
 import numpy as np
 import pytest
 
+# The oracle parallelises with OpenMP; on a 128-core GPU host the fork/join cost of tiny
+# loops dominates the small-model parity tests, so the test suite caps the team size.
+os.environ.setdefault("OMP_NUM_THREADS", "16")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
