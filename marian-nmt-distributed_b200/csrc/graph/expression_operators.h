@@ -78,6 +78,8 @@ Expr shift(Expr a, Shape shift);
 
 Expr layer_norm(Expr x, Expr gamma, Expr beta = nullptr, float eps = 1e-9);
 Expr highway(Expr y, Expr x, Expr t);
+// fused multi-head attention core on [beam, B, T, d] projections; mask additive (may be null)
+Expr multi_head_attention(Expr q, Expr k, Expr v, Expr mask, int heads, float scale);
 
 // inverted dropout with an explicit mask node (reference: expression_operators.h:122-133)
 template <typename... Args>

@@ -43,7 +43,7 @@ void Node::init_dependent() {
 void Node::set_zero_adjoint() {
   if(!adj_) {
     graph()->tensor(adj_, shape_);
-    adj_->set(0);
+    adj_->setLazyZero();  // zeroed on first touch, or assigned by the first accumulating writer
   }
 }
 

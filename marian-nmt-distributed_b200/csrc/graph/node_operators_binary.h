@@ -299,6 +299,58 @@ private:
   float eps_;
 };
 
+// Fused multi-head attention core: children {q, k, v[, additive mask]} in [beam, B, T, d]
+// layout.  Replaces the node sequence SplitHeads x3 / bdot / + / softmax / bdot / JoinHeads of
+// the reference's Transformer::MultiHead (src/models/transformer.h:153-261) by one forward and
+// one backward kernel; the softmax output is kept in a workspace tensor for the backward pass.
+struct MultiHeadAttentionNodeOp : public NaryNodeOp {
+  MultiHeadAttentionNodeOp(const std::vector<Expr>& nodes, int heads, float scale)
+      : NaryNodeOp(nodes, nodes[0]->shape()), heads_(heads), scale_(scale) {
+    if(nodes.size() > 3)
+      ABORT_IF(nodes[3]->trainable(), "attention mask must not require a gradient");
+  }
+  ~MultiHeadAttentionNodeOp() {
+    auto g = graph();
+    if(probs_ && g)
+      g->free(probs_);
+  }
+
+  void forward() {
+    int Tq = child(0)->shape()[-2], Tk = child(1)->shape()[-2];
+    int batch = child(0)->shape().elements() / (Tq * child(0)->shape()[-1]);
+    if(!probs_)
+      graph()->tensor(probs_, Shape{batch, heads_, Tq, Tk});
+    MultiHeadAttention(val_, probs_, child(0)->val(), child(1)->val(), child(2)->val(), children_.size() > 3 ? child(3)->val() : nullptr, heads_, scale_);
+  }
+  void backward() {
+    // q, k, v come out of trainable projections in every model; a frozen input would still
+    // get a (discarded) adjoint from set_zero_adjoint only if trainable, so require it
+    ABORT_IF(!child(0)->trainable() || !child(1)->trainable() || !child(2)->trainable(), "fused attention expects trainable q, k, v");
+    MultiHeadAttentionGrad(child(0)->grad(), child(1)->grad(), child(2)->grad(), adj_, val_, probs_, child(0)->val(), child(1)->val(), child(2)->val(), heads_, scale_);
+  }
+
+  virtual size_t hash() {
+    if(!hash_) {
+      hash_ = NaryNodeOp::hash();
+      hash_combine(hash_, heads_);
+      hash_combine(hash_, scale_);
+    }
+    return hash_;
+  }
+  virtual bool equal(Expr node) {
+    if(!NaryNodeOp::equal(node))
+      return false;
+    auto cnode = std::dynamic_pointer_cast<MultiHeadAttentionNodeOp>(node);
+    return cnode && heads_ == cnode->heads_ && scale_ == cnode->scale_;
+  }
+  const std::string type() { return "multi-head-attention"; }
+
+private:
+  int heads_;
+  float scale_;
+  Tensor probs_;
+};
+
 // sigma(t)*y + (1-sigma(t))*x.  reference: :690-709 (backward assigns)
 struct HighwayNodeOp : public NaryNodeOp {
   HighwayNodeOp(const std::vector<Expr>& nodes) : NaryNodeOp(nodes) {}

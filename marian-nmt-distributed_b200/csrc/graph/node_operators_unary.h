@@ -553,7 +553,8 @@ public:
   Tensor& grad() {
     auto childGrad = stepNode_->grad();
     size_t offset = (size_t)step_ * shape().elements() * sizeof(float);
-    auto mem = New<MemoryPiece>(childGrad->memory()->data() + offset, childGrad->memory()->size());
+    // data(): a partial view cannot carry the lazy-zero state of the whole adjoint
+    auto mem = New<MemoryPiece>((uint8_t*)childGrad->data() + offset, childGrad->memory()->size());
     adj_.reset(new TensorBase(mem, shape(), childGrad->getDevice()));
     return adj_;
   }

@@ -1,0 +1,368 @@
+// Fused multi-head scaled-dot-product attention (forward and backward).
+//
+// The reference's Transformer::MultiHead / Attention (src/models/transformer.h:153-261) issues,
+// per attention block, SplitHeads x3 (reshape + TransposeND), bdot(q, k^T) (cublasSgemmStridedBatched),
+// an Element add of the -99999999 mask, Softmax, bdot(weights, v), JoinHeads (TransposeND) - nine
+// kernels forward and about twenty backward, with the [B,H,Tq,Tk] scores and their gradient
+// round-tripping through HBM several times.  Here one CTA owns one (sentence, head) pair:
+//
+//   forward : Q,K,V head slices are read straight out of the [B,T,H*dk] projections (the head
+//             split is an address computation), S = scale QK^T + mask, row softmax and PV all
+//             happen in shared memory; the context is written back in [B,Tq,H*dk] layout (the
+//             head join) and the probabilities P are saved for the backward pass.
+//   backward: dV = P^T dO, dP = dO V^T, dS = P o (dP - rowsum(dO o O)), dQ = scale dS K,
+//             dK = scale dS^T Q - all five products on shared-memory tiles of one head.
+//
+// At the config-B shape (B=64, H=8, T=50, dk=64) a head is 3 x 12.8 KB of operands and
+// 2 x 160 KFMA per product: far below one tensor-core tile, so the products run as
+// register-tiled fp32 FMAs (4x4 micro-tiles, 128-bit shared-memory loads).  That also makes
+// the block exact fp32 in every GEMM mode.  Algorithmic HBM bytes: forward reads Q,K,V
+// (3 B T d 4) and writes O and P; backward reads Q,K,V,O,dO,P and updates dQ,dK,dV.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+
+#include "kernels/cuda_helpers.h"
+#include "kernels/tensor_operators.h"
+
+namespace marian {
+
+namespace {
+
+struct AttnGeom {
+  int B, H, Tq, Tk, dk;  // model width d = H * dk
+  int maskRows;          // 1 (key mask, broadcast over queries) or Tq (e.g. causal)
+  float scale;
+};
+
+constexpr int kAttnThreads = 256;
+
+__host__ __device__ inline int pad4(int x) {
+  return (x + 3) & ~3;
+}
+
+// Copies the [T, dk] head slice of a [B, T, H*dk] tensor into shared memory with row pitch ld.
+__device__ __forceinline__ void loadHead(float* dst, int ld, const float* src, int T, int dk, int d) {
+  int v4 = dk >> 2;
+  for(int e = threadIdx.x; e < T * v4; e += blockDim.x) {
+    int r = e / v4, c = (e - r * v4) << 2;
+    *reinterpret_cast<float4*>(dst + r * ld + c) = *reinterpret_cast<const float4*>(src + (size_t)r * d + c);
+  }
+}
+
+// out(i, j) = sum_c A[i*lda + c] * Bm[j*ldb + c]   (i < M, j < N, c < L, L % 4 == 0).
+// 4 x 4 outputs per thread; a thread's rows/columns are INTERLEAVED (i = ty + RG q) so that
+// neighbouring threads read neighbouring shared-memory rows: with a pitch of 4 (mod 32) words
+// the 128-bit loads of a quarter warp fall on distinct banks.
+template <class Store>
+__device__ __forceinline__ void tileMulNT(const float* A, int lda, int M, const float* Bm, int ldb, int N, int L, Store store) {
+  const int RG = (M + 3) >> 2, CG = (N + 3) >> 2;
+  for(int tile = threadIdx.x; tile < RG * CG; tile += blockDim.x) {
+    const int ty = tile / CG, tx = tile - ty * CG;
+    const float* ap[4];
+    const float* bp[4];
+#pragma unroll
+    for(int q = 0; q < 4; ++q) {
+      ap[q] = A + min(ty + RG * q, M - 1) * lda;
+      bp[q] = Bm + min(tx + CG * q, N - 1) * ldb;
+    }
+    float acc[4][4];
+#pragma unroll
+    for(int q = 0; q < 4; ++q)
+#pragma unroll
+      for(int s = 0; s < 4; ++s)
+        acc[q][s] = 0.f;
+    for(int c = 0; c < L; c += 4) {
+      float4 a[4], b[4];
+#pragma unroll
+      for(int q = 0; q < 4; ++q) {
+        a[q] = *reinterpret_cast<const float4*>(ap[q] + c);
+        b[q] = *reinterpret_cast<const float4*>(bp[q] + c);
+      }
+#pragma unroll
+      for(int q = 0; q < 4; ++q)
+#pragma unroll
+        for(int s = 0; s < 4; ++s) {
+          acc[q][s] = fmaf(a[q].x, b[s].x, acc[q][s]);
+          acc[q][s] = fmaf(a[q].y, b[s].y, acc[q][s]);
+          acc[q][s] = fmaf(a[q].z, b[s].z, acc[q][s]);
+          acc[q][s] = fmaf(a[q].w, b[s].w, acc[q][s]);
+        }
+    }
+#pragma unroll
+    for(int q = 0; q < 4; ++q) {
+      int i = ty + RG * q;
+      if(i < M) {
+#pragma unroll
+        for(int s = 0; s < 4; ++s) {
+          int j = tx + CG * s;
+          if(j < N)
+            store(i, j, acc[q][s]);
+        }
+      }
+    }
+  }
+}
+
+// out(r, 4t .. 4t+3) = sum_j Pm[r*sr + j*sj] * Vm[j*ldv + 4t ..]   (r < R, t < C/4, j < J).
+// sr = ld, sj = 1 multiplies by Pm; sr = 1, sj = ld multiplies by Pm^T.
+template <class Store>
+__device__ __forceinline__ void tileMulVec(const float* Pm, int sr, int sj, int R, const float* Vm, int ldv, int J, int C, Store store) {
+  const int RG = (R + 3) >> 2, C4 = C >> 2;
+  for(int tile = threadIdx.x; tile < RG * C4; tile += blockDim.x) {
+    const int ty = tile / C4, tx = tile - ty * C4;
+    const float* pp[4];
+#pragma unroll
+    for(int q = 0; q < 4; ++q)
+      pp[q] = Pm + min(ty + RG * q, R - 1) * sr;
+    float4 acc[4];
+#pragma unroll
+    for(int q = 0; q < 4; ++q)
+      acc[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float* vp = Vm + 4 * tx;
+#pragma unroll 2
+    for(int j = 0; j < J; ++j) {
+      float4 v = *reinterpret_cast<const float4*>(vp + j * ldv);
+#pragma unroll
+      for(int q = 0; q < 4; ++q) {
+        float p = pp[q][j * sj];
+        acc[q].x = fmaf(p, v.x, acc[q].x);
+        acc[q].y = fmaf(p, v.y, acc[q].y);
+        acc[q].z = fmaf(p, v.z, acc[q].z);
+        acc[q].w = fmaf(p, v.w, acc[q].w);
+      }
+    }
+#pragma unroll
+    for(int q = 0; q < 4; ++q) {
+      int r = ty + RG * q;
+      if(r < R)
+        store(r, 4 * tx, acc[q]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// forward
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(kAttnThreads) gAttentionForward(float* __restrict__ out,
+                                                                  float* __restrict__ probs,
+                                                                  const float* __restrict__ q,
+                                                                  const float* __restrict__ k,
+                                                                  const float* __restrict__ v,
+                                                                  const float* __restrict__ mask,
+                                                                  AttnGeom g) {
+  extern __shared__ __align__(16) float smemF[];
+  const int ld = g.dk + 4;        // operand row pitch: 4 (mod 32) words for dk = 64
+  const int ldS = pad4(g.Tk) + 1;  // odd pitch: the column walk of P^T products stays conflict free
+  float* sQ = smemF;
+  float* sK = sQ + g.Tq * ld;
+  float* sV = sK + g.Tk * ld;
+  float* sS = sV + g.Tk * ld;
+
+  const int b = blockIdx.x / g.H, h = blockIdx.x - b * g.H;
+  const int d = g.H * g.dk;
+  loadHead(sQ, ld, q + ((size_t)b * g.Tq) * d + h * g.dk, g.Tq, g.dk, d);
+  loadHead(sK, ld, k + ((size_t)b * g.Tk) * d + h * g.dk, g.Tk, g.dk, d);
+  loadHead(sV, ld, v + ((size_t)b * g.Tk) * d + h * g.dk, g.Tk, g.dk, d);
+  __syncthreads();
+
+  // S = scale Q K^T + mask
+  const float* mrow = mask ? mask + (size_t)b * g.maskRows * g.Tk : nullptr;
+  const int maskPitch = g.maskRows > 1 ? g.Tk : 0;
+  tileMulNT(sQ, ld, g.Tq, sK, ld, g.Tk, g.dk, [&](int i, int j, float acc) {
+    float s = acc * g.scale;
+    if(mrow)
+      s += mrow[i * maskPitch + j];
+    sS[i * ldS + j] = s;
+  });
+  __syncthreads();
+
+  // row softmax (one warp per row), P saved for the backward pass
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for(int i = warp; i < g.Tq; i += nwarps) {
+    float* row = sS + i * ldS;
+    float m = -3.0e38f;
+    for(int j = lane; j < g.Tk; j += 32)
+      m = fmaxf(m, row[j]);
+    m = warpMax(m);
+    float sum = 0.f;
+    for(int j = lane; j < g.Tk; j += 32) {
+      float e = __expf(row[j] - m);
+      row[j] = e;
+      sum += e;
+    }
+    sum = warpSum(sum);
+    float inv = 1.f / sum;
+    float* prow = probs ? probs + (((size_t)b * g.H + h) * g.Tq + i) * g.Tk : nullptr;
+    for(int j = lane; j < g.Tk; j += 32) {
+      float p = row[j] * inv;
+      row[j] = p;
+      if(prow)
+        prow[j] = p;
+    }
+  }
+  __syncthreads();
+
+  // O = P V, written in [B, Tq, H*dk] layout (head join)
+  float* ob = out + ((size_t)b * g.Tq) * d + h * g.dk;
+  tileMulVec(sS, ldS, 1, g.Tq, sV, ld, g.Tk, g.dk, [&](int i, int c, float4 acc) { *reinterpret_cast<float4*>(ob + (size_t)i * d + c) = acc; });
+}
+
+// ------------------------------------------------------------------------------------------
+// backward
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ void emit(float* p, float4 v, bool accumulate) {
+  if(accumulate) {
+    float4 o = *reinterpret_cast<const float4*>(p);
+    v.x += o.x;
+    v.y += o.y;
+    v.z += o.z;
+    v.w += o.w;
+  }
+  *reinterpret_cast<float4*>(p) = v;
+}
+
+__global__ void __launch_bounds__(kAttnThreads) gAttentionBackward(float* __restrict__ dq,
+                                                                   float* __restrict__ dk_,
+                                                                   float* __restrict__ dv,
+                                                                   const float* __restrict__ dout,
+                                                                   const float* __restrict__ out,
+                                                                   const float* __restrict__ probs,
+                                                                   const float* __restrict__ q,
+                                                                   const float* __restrict__ k,
+                                                                   const float* __restrict__ v,
+                                                                   AttnGeom g,
+                                                                   int accQ,
+                                                                   int accK,
+                                                                   int accV) {
+  extern __shared__ __align__(16) float smemF[];
+  const int ld = g.dk + 4;
+  const int ldS = pad4(g.Tk) + 1;
+  float* sQ = smemF;
+  float* sK = sQ + g.Tq * ld;
+  float* sV = sK + g.Tk * ld;
+  float* sdO = sV + g.Tk * ld;
+  float* sP = sdO + g.Tq * ld;  // P, later overwritten by dS
+  float* sD = sP + g.Tq * ldS;  // D_i = sum_c dO_ic O_ic = sum_j dP_ij P_ij
+
+  const int b = blockIdx.x / g.H, h = blockIdx.x - b * g.H;
+  const int d = g.H * g.dk;
+  const size_t offQ = ((size_t)b * g.Tq) * d + h * g.dk;
+  const size_t offK = ((size_t)b * g.Tk) * d + h * g.dk;
+  loadHead(sQ, ld, q + offQ, g.Tq, g.dk, d);
+  loadHead(sK, ld, k + offK, g.Tk, g.dk, d);
+  loadHead(sV, ld, v + offK, g.Tk, g.dk, d);
+  loadHead(sdO, ld, dout + offQ, g.Tq, g.dk, d);
+  const float* pb = probs + (((size_t)b * g.H + h) * g.Tq) * g.Tk;
+  for(int e = threadIdx.x; e < g.Tq * g.Tk; e += blockDim.x) {
+    int i = e / g.Tk, j = e - i * g.Tk;
+    sP[i * ldS + j] = pb[e];
+  }
+  __syncthreads();
+
+  // D_i (one warp per row; O read from global memory, dO from shared memory)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for(int i = warp; i < g.Tq; i += nwarps) {
+    const float* orow = out + offQ + (size_t)i * d;
+    float s = 0.f;
+    for(int c = lane; c < g.dk; c += 32)
+      s = fmaf(sdO[i * ld + c], orow[c], s);
+    s = warpSum(s);
+    if(lane == 0)
+      sD[i] = s;
+  }
+
+  // dV = P^T dO
+  tileMulVec(sP, 1, ldS, g.Tk, sdO, ld, g.Tq, g.dk, [&](int j, int c, float4 acc) { emit(dv + offK + (size_t)j * d + c, acc, accV != 0); });
+  __syncthreads();
+
+  // dS = P o (dO V^T - D), in place over P (each element is read and rewritten by its owner)
+  tileMulNT(sdO, ld, g.Tq, sV, ld, g.Tk, g.dk, [&](int i, int j, float acc) {
+    float p = sP[i * ldS + j];
+    sP[i * ldS + j] = p * (acc - sD[i]) * g.scale;
+  });
+  __syncthreads();
+
+  // dQ = dS K,  dK = dS^T Q   (scale already folded into dS)
+  tileMulVec(sP, ldS, 1, g.Tq, sK, ld, g.Tk, g.dk, [&](int i, int c, float4 acc) { emit(dq + offQ + (size_t)i * d + c, acc, accQ != 0); });
+  tileMulVec(sP, 1, ldS, g.Tk, sQ, ld, g.Tq, g.dk, [&](int j, int c, float4 acc) { emit(dk_ + offK + (size_t)j * d + c, acc, accK != 0); });
+}
+
+size_t forwardSmem(const AttnGeom& g) {
+  return ((size_t)(g.Tq + 2 * g.Tk) * (g.dk + 4) + (size_t)g.Tq * (pad4(g.Tk) + 1)) * sizeof(float);
+}
+size_t backwardSmem(const AttnGeom& g) {
+  return ((size_t)(2 * g.Tq + 2 * g.Tk) * (g.dk + 4) + (size_t)g.Tq * (pad4(g.Tk) + 1) + g.Tq) * sizeof(float);
+}
+constexpr size_t kSmemLimit = 227 * 1024;
+
+AttnGeom geometry(Tensor q, Tensor k, Tensor mask, int heads, float scale) {
+  AttnGeom g;
+  int d = q->shape()[-1];
+  ABORT_IF(d % heads != 0, "attention: model width must be divisible by the number of heads");
+  g.H = heads;
+  g.dk = d / heads;
+  g.Tq = q->shape()[-2];
+  g.Tk = k->shape()[-2];
+  g.B = (int)(q->shape().elements() / ((size_t)g.Tq * d));
+  ABORT_IF((size_t)g.B * g.Tk * d != (size_t)k->shape().elements(), "attention: queries and keys disagree on the batch size");
+  g.maskRows = 1;
+  if(mask) {
+    size_t me = mask->shape().elements();
+    if(me == (size_t)g.B * g.Tk)
+      g.maskRows = 1;
+    else if(me == (size_t)g.B * g.Tq * g.Tk)
+      g.maskRows = g.Tq;
+    else
+      ABORT("attention: mask must hold B*Tk or B*Tq*Tk elements, got", mask->shape().toString());
+  }
+  g.scale = scale;
+  return g;
+}
+
+}  // namespace
+
+bool AttentionFusable(int Tq, int Tk, int dimModel, int heads) {
+  if(heads <= 0 || dimModel % heads != 0)
+    return false;
+  AttnGeom g{1, heads, Tq, Tk, dimModel / heads, 1, 1.f};
+  return (g.dk % 4 == 0) && backwardSmem(g) <= kSmemLimit;
+}
+
+void MultiHeadAttention(Tensor out, Tensor probs, const Tensor q, const Tensor k, const Tensor v, const Tensor mask, int heads, float scale) {
+  device::setDevice(out->getDevice());
+  out->takeLazyZero();
+  AttnGeom g = geometry(q, k, mask, heads, scale);
+  size_t smem = forwardSmem(g);
+  ABORT_IF(g.dk % 4 != 0 || smem > kSmemLimit, "attention: shape not supported by the fused kernel", g.Tq, g.Tk, g.dk);
+  static size_t configured = 0;
+  if(smem > configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(gAttentionForward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)48 * 1024)));
+    configured = smem;
+  }
+  gAttentionForward<<<g.B * g.H, kAttnThreads, smem, cudaStreamOfEngine()>>>(
+      out->data(), probs ? probs->data() : nullptr, q->data(), k->data(), v->data(), mask ? mask->data() : nullptr, g);
+  CUDA_LAUNCH_CHECK();
+}
+
+void MultiHeadAttentionGrad(Tensor dq, Tensor dk, Tensor dv, const Tensor adj, const Tensor out, const Tensor probs, const Tensor q, const Tensor k, const Tensor v, int heads, float scale) {
+  device::setDevice(adj->getDevice());
+  // first writer assigns; tensors that alias (k and v from the same node) are written in the
+  // order dV, dQ, dK inside the kernel, separated by block barriers, so the later one accumulates
+  bool accV = !dv->takeLazyZero();
+  bool accQ = !dq->takeLazyZero();
+  bool accK = !dk->takeLazyZero();
+  AttnGeom g = geometry(q, k, nullptr, heads, scale);
+  size_t smem = backwardSmem(g);
+  ABORT_IF(g.dk % 4 != 0 || smem > kSmemLimit, "attention backward: shape not supported by the fused kernel", g.Tq, g.Tk, g.dk);
+  static size_t configured = 0;
+  if(smem > configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(gAttentionBackward, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)48 * 1024)));
+    configured = smem;
+  }
+  gAttentionBackward<<<g.B * g.H, kAttnThreads, smem, cudaStreamOfEngine()>>>(
+      dq->data(), dk->data(), dv->data(), adj->data(), out->data(), probs->data(), q->data(), k->data(), v->data(), g, accQ, accK, accV);
+  CUDA_LAUNCH_CHECK();
+}
+
+}  // namespace marian

@@ -48,7 +48,9 @@ struct RowGeom {
   int d1, d2;      // extents of dims 1 and 2 (row decode)
 };
 
-template <int K, bool ACC, bool VEC, class Functor>
+// MODE 0: Element (operand 0 is `out`, out = f(...));  MODE 1: Add, out += scale f(ins);
+// MODE 2: Add into a lazily-zero output, out = scale f(ins) (first writer assigns)
+template <int K, int MODE, bool VEC, class Functor>
 __global__ void __launch_bounds__(256) gElementwise(Functor f, float* __restrict__ out, Operands<K> ops, RowGeom g, float scale) {
   const int cpr = (g.cols + 3) >> 2;  // 4-element chunks per row
   const long long items = (long long)g.rows * cpr;
@@ -64,7 +66,7 @@ __global__ void __launch_bounds__(256) gElementwise(Functor f, float* __restrict
 #pragma unroll
     for(int k = 0; k < K; ++k) {
       // Element mode: operand 0 is `out`; skip the load if the functor ignores it
-      if(!ACC && k == 0 && !functional::Reads<Functor, 1>::value) {
+      if(MODE == 0 && k == 0 && !functional::Reads<Functor, 1>::value) {
         v[k][0] = v[k][1] = v[k][2] = v[k][3] = 0.f;
         continue;
       }
@@ -98,12 +100,14 @@ __global__ void __launch_bounds__(256) gElementwise(Functor f, float* __restrict
     float* o = out + (size_t)row * g.cols + c;
     if(VEC) {
       float4 q;
-      if(ACC) {
+      if(MODE == 1) {
         q = *reinterpret_cast<float4*>(o);
         q.x += r[0] * scale;
         q.y += r[1] * scale;
         q.z += r[2] * scale;
         q.w += r[3] * scale;
+      } else if(MODE == 2) {
+        q = make_float4(r[0] * scale, r[1] * scale, r[2] * scale, r[3] * scale);
       } else {
         q = make_float4(r[0], r[1], r[2], r[3]);
       }
@@ -112,8 +116,10 @@ __global__ void __launch_bounds__(256) gElementwise(Functor f, float* __restrict
 #pragma unroll
       for(int e = 0; e < 4; ++e)
         if(c + e < g.cols) {
-          if(ACC)
+          if(MODE == 1)
             o[e] += r[e] * scale;
+          else if(MODE == 2)
+            o[e] = r[e] * scale;
           else
             o[e] = r[e];
         }
@@ -123,7 +129,7 @@ __global__ void __launch_bounds__(256) gElementwise(Functor f, float* __restrict
 
 // case (1): out[row] += scale * sum_c f(ins[row, c]); one warp per row
 template <int K, class Functor>
-__global__ void __launch_bounds__(256) gAddReduceRows(Functor f, float* __restrict__ out, Operands<K> ops, RowGeom g, float scale) {
+__global__ void __launch_bounds__(256) gAddReduceRows(Functor f, float* __restrict__ out, Operands<K> ops, RowGeom g, float scale, int assign) {
   int warpsPerBlock = blockDim.x >> 5;
   int lane = threadIdx.x & 31;
   for(int row = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); row < g.rows; row += gridDim.x * warpsPerBlock) {
@@ -145,7 +151,68 @@ __global__ void __launch_bounds__(256) gAddReduceRows(Functor f, float* __restri
     }
     acc = warpSum(acc);
     if(lane == 0)
-      out[row] += acc * scale;
+      out[row] = assign ? acc * scale : out[row] + acc * scale;
+  }
+}
+
+// case (3), column form: out[1,1,1,C] += scale * sum over all rows of f(ins[row, c]) - bias,
+// gamma and beta gradients.  blockDim = (32, 8): a warp covers 128 consecutive columns with
+// 128-bit loads, the 8 warps stride the rows of a slice, partial sums meet in shared memory
+// and leave through ONE atomicAdd per column and slice.
+template <int K, class Functor>
+__global__ void __launch_bounds__(256) gAddColumns(Functor f, float* __restrict__ out, Operands<K> ops, RowGeom g, float scale, int rowsPerSlice, int assign) {
+  __shared__ float red[8][32][5];
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
+  const int r0 = blockIdx.y * rowsPerSlice;
+  const int r1 = min(g.rows, r0 + rowsPerSlice);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if(c < g.cols) {
+    for(int row = r0 + threadIdx.y; row < r1; row += 8) {
+      int o2 = row % g.d2;
+      int t = row / g.d2;
+      int o1 = t % g.d1;
+      int o0 = t / g.d1;
+      float v[K][4];
+#pragma unroll
+      for(int k = 0; k < K; ++k) {
+        const float* base = ops.p[k] + (size_t)o0 * ops.rb[k][0] + (size_t)o1 * ops.rb[k][1] + (size_t)o2 * ops.rb[k][2];
+        if(ops.cs[k] == 0) {
+          float sv = __ldg(base);
+          v[k][0] = v[k][1] = v[k][2] = v[k][3] = sv;
+        } else {
+          float4 q = *reinterpret_cast<const float4*>(base + c);
+          v[k][0] = q.x;
+          v[k][1] = q.y;
+          v[k][2] = q.z;
+          v[k][3] = q.w;
+        }
+      }
+#pragma unroll
+      for(int e = 0; e < 4; ++e) {
+        float a[K];
+#pragma unroll
+        for(int k = 0; k < K; ++k)
+          a[k] = v[k][e];
+        acc[e] += f(a);
+      }
+    }
+  }
+#pragma unroll
+  for(int e = 0; e < 4; ++e)
+    red[threadIdx.y][threadIdx.x][e] = acc[e];
+  __syncthreads();
+  if(threadIdx.y == 0 && c < g.cols) {
+#pragma unroll
+    for(int e = 0; e < 4; ++e) {
+      float sum = 0.f;
+#pragma unroll
+      for(int y = 0; y < 8; ++y)
+        sum += red[y][threadIdx.x][e];
+      if(assign)
+        out[c + e] = sum * scale;
+      else
+        atomicAdd(out + c + e, sum * scale);
+    }
   }
 }
 
@@ -156,6 +223,7 @@ struct GenericGeom {
   int chunk;      // reduced elements per slice
   int outLength;
   int atomic;     // slices > 1
+  int assign;     // single slice into a lazily-zero output
 };
 
 template <int K>
@@ -225,6 +293,8 @@ __global__ void __launch_bounds__(128) gAddGeneric(Functor f, float* __restrict_
   }
   if(g.atomic)
     atomicAdd(out + o, acc * scale);
+  else if(g.assign)
+    out[o] = acc * scale;
   else
     out[o] += acc * scale;
 }
@@ -273,6 +343,8 @@ template <class Functor, class... Tensors>
 void Element(Functor functor, Tensor out, Tensors... tensors) {
   device::setDevice(out->getDevice());
   constexpr int K = sizeof...(tensors) + 1;
+  if(!functional::Reads<Functor, 1>::value)
+    out->takeLazyZero();  // every element is overwritten: a pending lazy zero is moot
   Tensor ts[K] = {out, tensors...};
 
   Shape4 iter(out->shape());
@@ -291,9 +363,9 @@ void Element(Functor functor, Tensor out, Tensors... tensors) {
   int grid = gridFor((size_t)items, 256);
   auto stream = cudaStreamOfEngine();
   if(vec)
-    ew::gElementwise<K, false, true><<<grid, 256, 0, stream>>>(functor, out->data(), ops, g, 1.f);
+    ew::gElementwise<K, 0, true><<<grid, 256, 0, stream>>>(functor, out->data(), ops, g, 1.f);
   else
-    ew::gElementwise<K, false, false><<<grid, 256, 0, stream>>>(functor, out->data(), ops, g, 1.f);
+    ew::gElementwise<K, 0, false><<<grid, 256, 0, stream>>>(functor, out->data(), ops, g, 1.f);
   CUDA_LAUNCH_CHECK();
 }
 
@@ -319,7 +391,8 @@ void Add(Functor functor, float scale, Tensor out, Tensors... tensors) {
     int warpsPerBlock = 8;
     int grid = gridFor((size_t)g.rows * 32, 256);
     (void)warpsPerBlock;
-    ew::gAddReduceRows<K><<<grid, 256, 0, stream>>>(functor, out->data(), ops, g, scale);
+    int assign = out->takeLazyZero() ? 1 : 0;
+    ew::gAddReduceRows<K><<<grid, 256, 0, stream>>>(functor, out->data(), ops, g, scale, assign);
   } else if(outS == full) {
     // (2) element-wise accumulate
     bool broadcast = false;
@@ -329,14 +402,40 @@ void Add(Functor functor, float scale, Tensor out, Tensors... tensors) {
     ew::RowGeom g;
     bool vec;
     ew::setupOperands<K>(full, ts, ops, g, vec, !broadcast);
+    bool assign = out->takeLazyZero();
     if(!ew::aligned16(out->data()))
       vec = false;
     long long items = (long long)g.rows * ((g.cols + 3) / 4);
     int grid = gridFor((size_t)items, 256);
-    if(vec)
-      ew::gElementwise<K, true, true><<<grid, 256, 0, stream>>>(functor, out->data(), ops, g, scale);
+    if(assign) {
+      if(vec)
+        ew::gElementwise<K, 2, true><<<grid, 256, 0, stream>>>(functor, out->data(), ops, g, scale);
+      else
+        ew::gElementwise<K, 2, false><<<grid, 256, 0, stream>>>(functor, out->data(), ops, g, scale);
+    } else if(vec)
+      ew::gElementwise<K, 1, true><<<grid, 256, 0, stream>>>(functor, out->data(), ops, g, scale);
     else
-      ew::gElementwise<K, true, false><<<grid, 256, 0, stream>>>(functor, out->data(), ops, g, scale);
+      ew::gElementwise<K, 1, false><<<grid, 256, 0, stream>>>(functor, out->data(), ops, g, scale);
+  } else if(outS.d[0] == 1 && outS.d[1] == 1 && outS.d[2] == 1 && outS.d[3] == full.d[3] && (full.d[3] & 3) == 0 && ew::aligned16(out->memory()->data())
+            && [&] {
+                 for(int k = 0; k < K; ++k) {
+                   Shape4 sk(ts[k]->shape());
+                   if(sk.bst[3] == 1 && (!ew::aligned16(ts[k]->data()) || (sk.d[3] & 3)))
+                     return false;
+                 }
+                 return true;
+               }()) {
+    // (3a) column sums over all leading dims (bias / gamma / beta gradients)
+    ew::Operands<K> ops;
+    ew::RowGeom g;
+    bool vec;
+    ew::setupOperands<K>(full, ts, ops, g, vec, false);
+    int strips = (g.cols / 4 + 31) / 32;
+    int slices = std::max(1, std::min((kNumSMs * 4 + strips - 1) / strips, (g.rows + 15) / 16));
+    int rowsPerSlice = (g.rows + slices - 1) / slices;
+    slices = (g.rows + rowsPerSlice - 1) / rowsPerSlice;
+    int assign = (slices == 1 && out->takeLazyZero()) ? 1 : 0;
+    ew::gAddColumns<K><<<dim3(strips, slices), dim3(32, 8), 0, stream>>>(functor, out->data(), ops, g, scale, rowsPerSlice, assign);
   } else {
     // (3) generic reduction over the dims where out has extent 1
     ew::FullOperands<K> ops;
@@ -361,6 +460,7 @@ void Add(Functor functor, float scale, Tensor out, Tensors... tensors) {
     g.chunk = (g.total + slices - 1) / slices;
     slices = (g.total + g.chunk - 1) / g.chunk;
     g.atomic = slices > 1;
+    g.assign = (!g.atomic && out->takeLazyZero()) ? 1 : 0;
     dim3 grid(blocksX, slices);
     ew::gAddGeneric<K><<<grid, 128, 0, stream>>>(functor, out->data(), ops, g, scale);
   }

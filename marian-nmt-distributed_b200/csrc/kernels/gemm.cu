@@ -4,7 +4,11 @@
 // cublasSgemmStridedBatched in fp32, tensor-op math disabled) driven by
 // DotNodeOp / AffineNodeOp / DotBatchedNodeOp (src/graph/node_operators_binary.h:13-369).
 //
-// Three arithmetic modes (GemmMode, kernels/tensor_operators.h):
+// Arithmetic modes (GemmMode, kernels/tensor_operators.h):
+//   TF32    tcgen05.mma kind::tf32 straight on the fp32 tensors: TMA loads the
+//           raw row-major operands (rounding fp32 -> tf32 in flight), K-major or
+//           MN-major shared-memory descriptors absorb all four transpose cases,
+//           so there is NO packing pass and no scratch traffic   [throughput]
 //   BF16    tcgen05.mma kind::f16 (bf16 x bf16 -> fp32 in TMEM), operands
 //           staged by TMA into 128B-swizzled shared memory          [throughput]
 //   BF16X3  same kernel on hi/lo-split operands laid out along K:
@@ -501,6 +505,9 @@ struct TcArgs {
   int atomicOut;  // combine with red.add (split-K)
 };
 
+template <int BN>
+__device__ __forceinline__ void epilogueTile(const TcArgs& a, uint32_t tmemBase, float* stage, int warp, int lane, int m0, int n0, int batch, int split);
+
 template <int BN, int STAGES>
 struct TcSmem {
   static constexpr int A_BYTES = BLOCK_M * BLOCK_K * 2;
@@ -591,89 +598,11 @@ __global__ void __launch_bounds__(192) gGemmTcgen05(const __grid_constant__ CUte
       ummaCommit(tmemFullBar);  // accumulator complete
     }
   } else {
-    // ---------------- epilogue: TMEM -> registers -> global ----------------
+    // ---------------- epilogue: TMEM -> registers -> smem staging -> global ----------------
     mbarWait(tmemFullBar, 0);
     tcgenFenceAfter();
-    const int q = warp & 3;  // TMEM lane quarter this warp may access
-    float* Cb = a.C + (size_t)batch * a.strideC;
-    const bool addBias = a.bias != nullptr && split == 0;
-#pragma unroll 1
-    for(int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[32];
-      uint32_t taddr = tmemBase + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
-      asm volatile(
-          "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-          "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-          "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-          : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
-            "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
-            "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
-            "=r"(r[31])
-          : "r"(taddr));
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-      // Stage the 32 x 32 block through shared memory (the smem ring is idle once the
-      // accumulator is complete) so that global accesses are row-contiguous: a thread owns
-      // a ROW of the TMEM tile, but 8 lanes x float4 must cover 128 contiguous bytes of C.
-      float* stage = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * kStagePitch);
-      {
-        float4* srow = reinterpret_cast<float4*>(stage + lane * kStagePitch);
-#pragma unroll
-        for(int j = 0; j < 8; ++j)
-          srow[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
-      }
-      __syncwarp();
-      const int col0 = n0 + c0;
-      const int rowBase = m0 + q * 32;
-      if(col0 < a.N && rowBase < a.M) {
-        const int ncols = min(32, a.N - col0);
-        const bool vec = ncols == 32 && ((a.ldc & 3) == 0) && ((((uintptr_t)(Cb + col0)) & 15) == 0) && !a.atomicOut;
-        if(vec) {
-          const int sub = lane >> 3;         // row within a group of 4
-          const int cq = (lane & 7) * 4;     // first of this lane's 4 columns
-          float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
-          if(addBias)
-            bq = *reinterpret_cast<const float4*>(a.bias + col0 + cq);
-#pragma unroll
-          for(int rr = 0; rr < 32; rr += 4) {
-            int rloc = rr + sub;
-            int grow = rowBase + rloc;
-            if(grow < a.M) {
-              float4 acc = *reinterpret_cast<const float4*>(stage + rloc * kStagePitch + cq);
-              float* cp = Cb + (size_t)grow * a.ldc + col0 + cq;
-              float4 v;
-              v.x = a.alpha * acc.x + bq.x;
-              v.y = a.alpha * acc.y + bq.y;
-              v.z = a.alpha * acc.z + bq.z;
-              v.w = a.alpha * acc.w + bq.w;
-              if(a.beta != 0.f) {
-                float4 old = *reinterpret_cast<const float4*>(cp);
-                v.x += a.beta * old.x;
-                v.y += a.beta * old.y;
-                v.z += a.beta * old.z;
-                v.w += a.beta * old.w;
-              }
-              *reinterpret_cast<float4*>(cp) = v;
-            }
-          }
-        } else if(lane < ncols) {
-          // general path: lane = column, rows walked one by one (still 128-byte contiguous per row)
-          float bv = addBias ? a.bias[col0 + lane] : 0.f;
-          int rmax = min(32, a.M - rowBase);
-          for(int rloc = 0; rloc < rmax; ++rloc) {
-            float v = a.alpha * stage[rloc * kStagePitch + lane] + bv;
-            float* cp = Cb + (size_t)(rowBase + rloc) * a.ldc + col0 + lane;
-            if(a.atomicOut) {
-              atomicAdd(cp, v);
-            } else {
-              if(a.beta != 0.f)
-                v += a.beta * *cp;
-              *cp = v;
-            }
-          }
-        }
-      }
-      __syncwarp();  // staging buffer is reused by the next 32-column block
-    }
+    float* stage = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * kStagePitch);
+    epilogueTile<BN>(a, tmemBase, stage, warp, lane, m0, n0, batch, split);
   }
 
   tcgenFenceBefore();
@@ -682,6 +611,270 @@ __global__ void __launch_bounds__(192) gGemmTcgen05(const __grid_constant__ CUte
     __syncwarp();
     tcgenFenceAfter();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "r"((uint32_t)(BN < 32 ? 32 : BN)));
+  }
+}
+
+
+// =============================================================================
+// tf32 kernel: operands are the fp32 tensors themselves
+// =============================================================================
+// Shared-memory tile of one operand per stage = 32 reduction elements x ROWS:
+//   K-major  (reduction dim contiguous in global memory): ONE TMA box {32 k, ROWS}; rows of
+//            128 bytes, SWIZZLE_128B; descriptor SBO = 1024 B (8 rows), k-step (8 tf32 = 32 B)
+//            advances the start address inside the swizzle row.
+//   MN-major (the M / N dim contiguous: transposed operands, i.e. weights in the forward
+//            product and both operands of dW = X^T dY): ROWS/32 TMA boxes {32 mn, 32 k}; each
+//            box is 32 k-rows of 128 bytes, swizzled in 32-byte atoms
+//            (CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B <-> UMMA SWIZZLE_128B_BASE32B, the only
+//            MN-major layout the tensor core accepts for 32-bit elements); descriptor
+//            LBO = 4096 B (next 32 mn), SBO = 512 B (next 4 k-rows), k-step (8 k-rows) = 1024 B.
+constexpr int TF_BLOCK_K = 32;
+
+__device__ __forceinline__ void tmaLoad3D(const CUtensorMap* map, uint64_t* bar, void* dst, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(smemAddr(dst)),
+      "l"((uint64_t)map),
+      "r"(smemAddr(bar)),
+      "r"(c0),
+      "r"(c1),
+      "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void ummaTf32(uint32_t tmemD, uint64_t descA, uint64_t descB, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+      "}" ::"r"(tmemD),
+      "l"(descA),
+      "l"(descB),
+      "r"(idesc),
+      "r"(accumulate)
+      : "memory");
+}
+template <bool MN>
+__device__ __forceinline__ uint64_t makeSmemDescTf32(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFF) >> 4);
+  if(MN) {
+    d |= (uint64_t)(4096 >> 4) << 16;  // LBO: next block of 32 mn
+    d |= (uint64_t)(512 >> 4) << 32;   // SBO: next 4 k-rows
+    d |= (uint64_t)1 << 46;            // descriptor version (Blackwell)
+    d |= (uint64_t)1 << 61;            // SWIZZLE_128B_BASE32B
+  } else {
+    d |= (uint64_t)1 << 16;
+    d |= (uint64_t)(1024 >> 4) << 32;  // SBO: next 8 rows
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)2 << 61;            // SWIZZLE_128B
+  }
+  return d;
+}
+__host__ __device__ constexpr uint32_t makeInstrDescTf32(int M, int N, bool aMN, bool bMN) {
+  return (1u << 4)     // c_format = F32
+         | (2u << 7)   // a_format = TF32
+         | (2u << 10)  // b_format = TF32
+         | ((aMN ? 1u : 0u) << 15) | ((bMN ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BN, int STAGES>
+struct TfSmem {
+  static constexpr int A_BYTES = BLOCK_M * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int BAR_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 1) * 8 + 16 + 1024;
+};
+
+// Shared epilogue of both tensor-core kernels: TMEM -> registers -> smem staging -> global
+// with alpha / beta / bias; `stage` is this warp's 32 x kStagePitch float scratch.
+template <int BN>
+__device__ __forceinline__ void epilogueTile(const TcArgs& a, uint32_t tmemBase, float* stage, int warp, int lane, int m0, int n0, int batch, int split) {
+  const int q = warp & 3;  // TMEM lane quarter this warp may access
+  float* Cb = a.C + (size_t)batch * a.strideC;
+  const bool addBias = a.bias != nullptr && split == 0;
+#pragma unroll 1
+  for(int c0 = 0; c0 < BN; c0 += 32) {
+    const int col0 = n0 + c0;
+    const int rowBase = m0 + q * 32;
+    if(col0 >= a.N || rowBase >= a.M)
+      break;
+    uint32_t r[32];
+    uint32_t taddr = tmemBase + ((uint32_t)(q * 32) << 16) + (uint32_t)c0;
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+          "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+          "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+          "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    {
+      float4* srow = reinterpret_cast<float4*>(stage + lane * kStagePitch);
+#pragma unroll
+      for(int j = 0; j < 8; ++j)
+        srow[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+    }
+    __syncwarp();
+    const int ncols = min(32, a.N - col0);
+    const bool vec = ncols == 32 && ((a.ldc & 3) == 0) && ((((uintptr_t)(Cb + col0)) & 15) == 0);
+    if(vec) {
+      const int sub = lane >> 3;      // row within a group of 4
+      const int cq = (lane & 7) * 4;  // first of this lane's 4 columns
+      float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+      if(addBias)
+        bq = *reinterpret_cast<const float4*>(a.bias + col0 + cq);
+#pragma unroll
+      for(int rr = 0; rr < 32; rr += 4) {
+        int rloc = rr + sub;
+        int grow = rowBase + rloc;
+        if(grow < a.M) {
+          float4 acc = *reinterpret_cast<const float4*>(stage + rloc * kStagePitch + cq);
+          float* cp = Cb + (size_t)grow * a.ldc + col0 + cq;
+          float4 v;
+          v.x = a.alpha * acc.x + bq.x;
+          v.y = a.alpha * acc.y + bq.y;
+          v.z = a.alpha * acc.z + bq.z;
+          v.w = a.alpha * acc.w + bq.w;
+          if(a.atomicOut) {
+            // split-K partial sums: vector reduction straight into L2 (sm_90+)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+          } else {
+            if(a.beta != 0.f) {
+              float4 old = *reinterpret_cast<const float4*>(cp);
+              v.x += a.beta * old.x;
+              v.y += a.beta * old.y;
+              v.z += a.beta * old.z;
+              v.w += a.beta * old.w;
+            }
+            *reinterpret_cast<float4*>(cp) = v;
+          }
+        }
+      }
+    } else if(lane < ncols) {
+      // general path: lane = column, rows walked one by one (still contiguous per row)
+      float bv = addBias ? a.bias[col0 + lane] : 0.f;
+      int rmax = min(32, a.M - rowBase);
+      for(int rloc = 0; rloc < rmax; ++rloc) {
+        float v = a.alpha * stage[rloc * kStagePitch + lane] + bv;
+        float* cp = Cb + (size_t)(rowBase + rloc) * a.ldc + col0 + lane;
+        if(a.atomicOut) {
+          atomicAdd(cp, v);
+        } else {
+          if(a.beta != 0.f)
+            v += a.beta * *cp;
+          *cp = v;
+        }
+      }
+    }
+    __syncwarp();  // staging buffer is reused by the next 32-column block
+  }
+}
+
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+__global__ void __launch_bounds__(192) gGemmTf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcArgs a) {
+  typedef TfSmem<BN, STAGES> L;
+  extern __shared__ uint8_t smemRaw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smemRaw + 1023) & ~(uintptr_t)1023);
+  uint64_t* fullBar = (uint64_t*)(smem + L::BAR_OFFSET);
+  uint64_t* emptyBar = fullBar + STAGES;
+  uint64_t* tmemFullBar = emptyBar + STAGES;
+  uint32_t* tmemHolder = (uint32_t*)(tmemFullBar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  const int m0 = blockIdx.x * BLOCK_M;
+  const int n0 = blockIdx.y * BN;
+  const int batch = blockIdx.z / a.splits;
+  const int split = blockIdx.z - batch * a.splits;
+  const int kb0 = split * a.kBlocksPerSplit;
+  const int nkb = min(a.kBlocksPerSplit, a.kBlocks - kb0);
+
+  if(warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
+    for(int s = 0; s < STAGES; ++s) {
+      mbarInit(fullBar + s, 1);
+      mbarInit(emptyBar + s, 1);
+    }
+    mbarInit(tmemFullBar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if(warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smemAddr(tmemHolder)), "r"((uint32_t)BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgenFenceBefore();
+  __syncthreads();
+  tcgenFenceAfter();
+  const uint32_t tmemBase = *tmemHolder;
+
+  if(warp == 0) {
+    if(lane == 0) {
+      // ---------------- TMA producer ----------------
+      const int batchA = a.rowsPerBatchA ? batch : 0;  // rowsPerBatch* != 0 marks a batched operand
+      const int batchB = a.rowsPerBatchB ? batch : 0;
+      for(int i = 0; i < nkb; ++i) {
+        int s = i % STAGES;
+        uint32_t phase = (uint32_t)(i / STAGES) & 1u;
+        mbarWait(emptyBar + s, phase ^ 1u);
+        mbarExpectTx(fullBar + s, (uint32_t)L::STAGE_BYTES);
+        uint8_t* sa = smem + s * L::STAGE_BYTES;
+        uint8_t* sb = sa + L::A_BYTES;
+        int kc = (kb0 + i) * TF_BLOCK_K;
+        if(A_MN) {
+#pragma unroll
+          for(int c = 0; c < BLOCK_M / 32; ++c)
+            tmaLoad3D(&tmA, fullBar + s, sa + c * 4096, m0 + 32 * c, kc, batchA);
+        } else {
+          tmaLoad3D(&tmA, fullBar + s, sa, kc, m0, batchA);
+        }
+        if(B_MN) {
+#pragma unroll
+          for(int c = 0; c < BN / 32; ++c)
+            tmaLoad3D(&tmB, fullBar + s, sb + c * 4096, n0 + 32 * c, kc, batchB);
+        } else {
+          tmaLoad3D(&tmB, fullBar + s, sb, kc, n0, batchB);
+        }
+      }
+    }
+  } else if(warp == 1) {
+    if(lane == 0) {
+      // ---------------- MMA issuer (single thread) ----------------
+      constexpr uint32_t idesc = makeInstrDescTf32(BLOCK_M, BN, A_MN, B_MN);
+      constexpr uint32_t stepA = A_MN ? (1024 >> 4) : (32 >> 4);
+      constexpr uint32_t stepB = B_MN ? (1024 >> 4) : (32 >> 4);
+      for(int i = 0; i < nkb; ++i) {
+        int s = i % STAGES;
+        uint32_t phase = (uint32_t)(i / STAGES) & 1u;
+        mbarWait(fullBar + s, phase);
+        tcgenFenceAfter();
+        uint32_t sa = smemAddr(smem + s * L::STAGE_BYTES);
+        uint32_t sb = sa + L::A_BYTES;
+        uint64_t descA = makeSmemDescTf32<A_MN>(sa);
+        uint64_t descB = makeSmemDescTf32<B_MN>(sb);
+#pragma unroll
+        for(int k = 0; k < TF_BLOCK_K / 8; ++k)
+          ummaTf32(tmemBase, descA + (uint64_t)(k * stepA), descB + (uint64_t)(k * stepB), idesc, (uint32_t)((i | k) != 0));
+        ummaCommit(emptyBar + s);
+      }
+      ummaCommit(tmemFullBar);
+    }
+  } else {
+    mbarWait(tmemFullBar, 0);
+    tcgenFenceAfter();
+    float* stage = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * kStagePitch);
+    epilogueTile<BN>(a, tmemBase, stage, warp, lane, m0, n0, batch, split);
+  }
+
+  tcgenFenceBefore();
+  __syncthreads();
+  if(warp == 1) {
+    __syncwarp();
+    tcgenFenceAfter();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "r"((uint32_t)BN));
   }
 }
 
@@ -750,7 +943,7 @@ void runSimt(const GemmProblem& p) {
 }
 
 void runTensorCore(GemmHandle h, const GemmProblem& p) {
-  const bool x3 = h->mode == GemmMode::BF16X3;
+  const bool x3 = h->mode == GemmMode::BF16X3 || h->mode == GemmMode::TF32;
   int M = p.transA ? p.colsA : p.rowsA;
   int K = p.transA ? p.rowsA : p.colsA;
   int N = p.transB ? p.rowsB : p.colsB;
@@ -822,8 +1015,136 @@ void runTensorCore(GemmHandle h, const GemmProblem& p) {
   }
 }
 
-void runGemm(GemmHandle h, const GemmProblem& p) {
+
+// ---- tf32 path: tensor maps over the fp32 tensors themselves ----
+// dims (innermost first): {inner, outer, batch}; box {32, boxOuter, 1}
+CUtensorMap makeTensorMapF32(GemmHandle h, const float* base, uint64_t inner, uint64_t outer, uint64_t batches, uint64_t pitchElems, uint64_t batchStrideElems, uint32_t boxOuter, bool mnMajor) {
+  if(!h->encodeTiled) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    ABORT_IF(!fn || qres != cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available from the driver");
+    h->encodeTiled = (GemmContext::EncodeTiledFn)fn;
+  }
+  CUtensorMap map;
+  cuuint64_t gdim[3] = {inner, outer, batches};
+  cuuint64_t gstride[2] = {pitchElems * sizeof(float), (batches > 1 ? batchStrideElems : pitchElems * outer) * sizeof(float)};
+  cuuint32_t box[3] = {(cuuint32_t)TF_BLOCK_K, boxOuter, 1};
+  cuuint32_t estride[3] = {1, 1, 1};
+  // TFLOAT32: the copy engine rounds fp32 -> tf32 (nearest) on the way into shared memory
+  CUresult rc = h->encodeTiled(&map, CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, 3, (void*)base, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               mnMajor ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ABORT_IF(rc != CUDA_SUCCESS, "cuTensorMapEncodeTiled (fp32) failed with code", (int)rc);
+  return map;
+}
+
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+void launchTf32(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, int batches) {
+  typedef TfSmem<BN, STAGES> L;
+  static bool configured = false;
+  if(!configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(gGemmTf32<BN, STAGES, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  dim3 grid((a.M + BLOCK_M - 1) / BLOCK_M, (a.N + BN - 1) / BN, batches * a.splits);
+  gGemmTf32<BN, STAGES, A_MN, B_MN><<<grid, 192, L::TOTAL, cudaStreamOfEngine()>>>(tmA, tmB, a);
+  CUDA_LAUNCH_CHECK();
+}
+
+template <bool A_MN, bool B_MN>
+void launchTf32Tile(int BN, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, int batches) {
+  if(BN == 128)
+    launchTf32<128, 3, A_MN, B_MN>(tmA, tmB, a, batches);
+  else
+    launchTf32<64, 4, A_MN, B_MN>(tmA, tmB, a, batches);
+}
+
+inline bool tmaUsable(const float* p, int cols, size_t batchStride) {
+  return (((uintptr_t)p) & 15) == 0 && (cols & 3) == 0 && (batchStride & 3) == 0;
+}
+
+// Returns false when an operand cannot be described by a tensor map (row pitch or
+// address not 16-byte aligned); the caller then takes the packed path.
+bool runTf32(GemmHandle h, const GemmProblem& p) {
+  if(!tmaUsable(p.A->data(), p.colsA, p.strideA) || !tmaUsable(p.B->data(), p.colsB, p.strideB))
+    return false;
+  int M = p.transA ? p.colsA : p.rowsA;
+  int K = p.transA ? p.rowsA : p.colsA;
+  int N = p.transB ? p.rowsB : p.colsB;
+  bool batched = p.batches > 1;
+  const bool aMN = p.transA;   // stored [K, M]: M contiguous
+  const bool bMN = !p.transB;  // stored [K, N]: N contiguous
+
+  long tiles128 = (long)((M + BLOCK_M - 1) / BLOCK_M) * ((N + 127) / 128) * p.batches;
+  int BN = (tiles128 >= kNumSMs && N > 64) ? 128 : 64;
+
+  uint64_t batchesA = p.strideA ? p.batches : 1, batchesB = p.strideB ? p.batches : 1;
+  // stored matrices are [rows, cols] row-major: inner = cols, outer = rows
+  CUtensorMap tmA = makeTensorMapF32(h, p.A->data(), (uint64_t)p.colsA, (uint64_t)p.rowsA, batchesA, (uint64_t)p.colsA, p.strideA, aMN ? TF_BLOCK_K : BLOCK_M, aMN);
+  CUtensorMap tmB = makeTensorMapF32(h, p.B->data(), (uint64_t)p.colsB, (uint64_t)p.rowsB, batchesB, (uint64_t)p.colsB, p.strideB, bMN ? TF_BLOCK_K : (uint32_t)BN, bMN);
+
+  TcArgs a;
+  a.C = p.C->data();
+  a.bias = p.bias ? p.bias->data() : nullptr;
+  a.M = M;
+  a.N = N;
+  a.ldc = N;
+  a.kBlocks = (K + TF_BLOCK_K - 1) / TF_BLOCK_K;
+  a.rowsPerBatchA = (batched && p.strideA) ? 1 : 0;  // batched-operand flags for the producer
+  a.rowsPerBatchB = (batched && p.strideB) ? 1 : 0;
+  a.strideC = (size_t)M * N;
+  a.alpha = p.alpha;
+  a.beta = p.beta;
+
+  long tiles = (long)((M + BLOCK_M - 1) / BLOCK_M) * ((N + BN - 1) / BN) * p.batches;
+  int splits = 1;
+  if(!batched && tiles * 2 <= kNumSMs && a.kBlocks >= 16) {
+    splits = (int)std::min<long>((kNumSMs * 2 + tiles - 1) / tiles, a.kBlocks / 8);
+    splits = std::max(1, std::min(splits, 32));
+  }
+  a.kBlocksPerSplit = (a.kBlocks + splits - 1) / splits;
+  splits = (a.kBlocks + a.kBlocksPerSplit - 1) / a.kBlocksPerSplit;
+  a.splits = splits;
+  a.atomicOut = splits > 1;
+  if(a.atomicOut && p.beta != 1.f) {
+    using namespace functional;
+    if(p.beta == 0.f)
+      p.C->set(0);
+    else
+      Element(_1 = p.beta * _1, p.C);
+  }
+
+  bool profile = g_profile.enabled && !device::capturing();
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if(profile) {
+    CUDA_CHECK(cudaEventCreate(&e0));
+    CUDA_CHECK(cudaEventCreate(&e1));
+    CUDA_CHECK(cudaEventRecord(e0, cudaStreamOfEngine()));
+  }
+  if(aMN && bMN)
+    launchTf32Tile<true, true>(BN, tmA, tmB, a, p.batches);
+  else if(aMN)
+    launchTf32Tile<true, false>(BN, tmA, tmB, a, p.batches);
+  else if(bMN)
+    launchTf32Tile<false, true>(BN, tmA, tmB, a, p.batches);
+  else
+    launchTf32Tile<false, false>(BN, tmA, tmB, a, p.batches);
+  if(profile) {
+    CUDA_CHECK(cudaEventRecord(e1, cudaStreamOfEngine()));
+    g_profile.events.push_back({e0, e1});
+    g_profile.flops += 2.0 * M * N * K * p.batches;
+  }
+  return true;
+}
+
+void runGemm(GemmHandle h, const GemmProblem& problem) {
+  GemmProblem p = problem;
   device::setDevice(p.C->getDevice());
+  // first writer assigns: an adjoint that is still "lazily zero" is overwritten (beta = 0)
+  // instead of being memset and then read back by the epilogue
+  if(p.C->takeLazyZero())
+    p.beta = 0.f;
   int M = p.transA ? p.colsA : p.rowsA;
   int K = p.transA ? p.rowsA : p.colsA;
   int Kb = p.transB ? p.colsB : p.rowsB;
@@ -834,7 +1155,10 @@ void runGemm(GemmHandle h, const GemmProblem& p) {
     return;
   if(h->mode == GemmMode::FP32)
     runSimt(p);
-  else
+  else if(h->mode == GemmMode::TF32) {
+    if(!runTf32(h, p))
+      runTensorCore(h, p);  // operand not TMA-addressable: packed hi/lo bf16 path (at least as precise)
+  } else
     runTensorCore(h, p);
 }
 

@@ -296,7 +296,7 @@ __global__ void gCrossEntropyPick(float* __restrict__ out, const float* __restri
 }
 
 template <bool WARP, bool VEC>
-__global__ void gCrossEntropyPickBackward(float* __restrict__ out, const float* __restrict__ adj, const float* __restrict__ in, const float* __restrict__ pick, int rows, int cols) {
+__global__ void gCrossEntropyPickBackward(float* __restrict__ out, const float* __restrict__ adj, const float* __restrict__ in, const float* __restrict__ pick, int rows, int cols, int assign) {
   __shared__ float smem[32];
   typedef RowCtx<WARP> R;
   for(int j = R::firstRow(); j < rows; j += R::rowStride()) {
@@ -314,7 +314,7 @@ __global__ void gCrossEntropyPickBackward(float* __restrict__ out, const float* 
       int n4 = cols >> 2;
       for(int i = R::firstCol(); i < n4; i += R::colStride()) {
         float4 x = p4[i];
-        float4 g = o4[i];
+        float4 g = assign ? make_float4(0.f, 0.f, 0.f, 0.f) : o4[i];
         int id = i << 2;
         g.x += a * (expf(x.x - M) / s - (float)(id == p));
         g.y += a * (expf(x.y - M) / s - (float)(id + 1 == p));
@@ -325,7 +325,8 @@ __global__ void gCrossEntropyPickBackward(float* __restrict__ out, const float* 
     } else {
       for(int id = R::firstCol(); id < cols; id += R::colStride()) {
         float sub = (float)(id == p);
-        so[id] += a * (expf(sp[id] - M) / s - sub);
+        float gval = a * (expf(sp[id] - M) / s - sub);
+        so[id] = assign ? gval : so[id] + gval;
       }
     }
   }
@@ -359,9 +360,10 @@ void CrossEntropyPickBackward(Tensor out, Tensor adj, Tensor a, Tensor pick) {
   int cols = out->shape().back();
   int rows = out->shape().elements() / cols;
   auto l = rowLaunch(rows, cols);
+  int assign = out->takeLazyZero() ? 1 : 0;  // first writer of the logits adjoint: no memset, no read-back
   bool vec = rowsVectorizable(a->data(), out->data(), cols);
   auto st = cudaStreamOfEngine();
-#define CE_BWD(W, V) gCrossEntropyPickBackward<W, V><<<l.grid, l.block, 0, st>>>(out->data(), adj->data(), a->data(), pick->data(), rows, cols)
+#define CE_BWD(W, V) gCrossEntropyPickBackward<W, V><<<l.grid, l.block, 0, st>>>(out->data(), adj->data(), a->data(), pick->data(), rows, cols, assign)
   if(l.warp) {
     if(vec) CE_BWD(true, true); else CE_BWD(true, false);
   } else {
@@ -476,22 +478,237 @@ __global__ void __launch_bounds__(128) gLayerNormalizationGrad(float* __restrict
   }
 }
 
+// ---- register-resident variants for rows of up to 128*VPL floats (16-byte aligned) --------
+// One warp per row; a lane keeps VPL float4 of the row in registers, so every input is read
+// from HBM exactly once and all row statistics are shuffle reductions (no __syncthreads).
+template <int VPL>
+__global__ void __launch_bounds__(256) gLNormalizationWarp(float* __restrict__ out, const float* __restrict__ in, const float* __restrict__ alpha, const float* __restrict__ beta, int rows, int cols, float eps) {
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  float4 g4[VPL], b4[VPL];
+#pragma unroll
+  for(int i = 0; i < VPL; ++i) {
+    int c = (i * 32 + lane) * 4;
+    g4[i] = c < cols ? *reinterpret_cast<const float4*>(alpha + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    b4[i] = (beta && c < cols) ? *reinterpret_cast<const float4*>(beta + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  for(int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
+    const float* sp = in + (size_t)row * cols;
+    float4 xv[VPL];
+    float s = 0.f;
+#pragma unroll
+    for(int i = 0; i < VPL; ++i) {
+      int c = (i * 32 + lane) * 4;
+      xv[i] = c < cols ? *reinterpret_cast<const float4*>(sp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      s += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
+    }
+    float mean = warpSum(s) / cols;
+    float sq = 0.f;
+#pragma unroll
+    for(int i = 0; i < VPL; ++i) {
+      int c = (i * 32 + lane) * 4;
+      if(c < cols) {
+        float e0 = xv[i].x - mean, e1 = xv[i].y - mean, e2 = xv[i].z - mean, e3 = xv[i].w - mean;
+        sq += (e0 * e0 + e1 * e1) + (e2 * e2 + e3 * e3);
+      }
+    }
+    float sigma = sqrtf(eps + (warpSum(sq) / cols));
+    float* so = out + (size_t)row * cols;
+#pragma unroll
+    for(int i = 0; i < VPL; ++i) {
+      int c = (i * 32 + lane) * 4;
+      if(c < cols) {
+        float4 t;
+        t.x = g4[i].x * ((xv[i].x - mean) / sigma) + b4[i].x;
+        t.y = g4[i].y * ((xv[i].y - mean) / sigma) + b4[i].y;
+        t.z = g4[i].z * ((xv[i].z - mean) / sigma) + b4[i].z;
+        t.w = g4[i].w * ((xv[i].w - mean) / sigma) + b4[i].w;
+        *reinterpret_cast<float4*>(so + c) = t;
+      }
+    }
+  }
+}
+
+__device__ __forceinline__ float lnGradElem(float a, float x_hat, float g, float sum_adj, float sum_adj_x, float cols, float sigma) {
+  float grad_x = cols * a;
+  grad_x -= sum_adj;
+  grad_x -= sum_adj_x * x_hat;
+  grad_x /= (cols * sigma);
+  float valX = g * grad_x;
+  float sign = (0.f < valX) - (valX < 0.f);
+  return fabsf(valX) > 1000.f ? sign * 1000.f : valX;  // clip kept from the reference
+}
+
+template <int VPL>
+__global__ void __launch_bounds__(256) gLayerNormalizationGradWarp(float* __restrict__ gradX,
+                                                                   float* __restrict__ gradGamma,
+                                                                   float* __restrict__ gradBeta,
+                                                                   const float* __restrict__ adj,
+                                                                   const float* __restrict__ y,
+                                                                   const float* __restrict__ x,
+                                                                   const float* __restrict__ gamma,
+                                                                   const float* __restrict__ beta,
+                                                                   int rows,
+                                                                   int cols,
+                                                                   float eps,
+                                                                   int assignX) {
+  __shared__ float4 red[8][32 * VPL];
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  float4 g4[VPL], b4[VPL], accG[VPL], accB[VPL];
+#pragma unroll
+  for(int i = 0; i < VPL; ++i) {
+    int c = (i * 32 + lane) * 4;
+    g4[i] = c < cols ? *reinterpret_cast<const float4*>(gamma + c) : make_float4(1.f, 1.f, 1.f, 1.f);
+    b4[i] = (beta && c < cols) ? *reinterpret_cast<const float4*>(beta + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    accG[i] = accB[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const float fcols = (float)cols;
+  for(int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
+    const size_t off = (size_t)row * cols;
+    float4 xh[VPL], av[VPL];
+    float sum_x = 0.f, sum_adj = 0.f, sum_adj_x = 0.f, sq = 0.f;
+    {
+      float4 xv[VPL];
+#pragma unroll
+      for(int i = 0; i < VPL; ++i) {
+        int c = (i * 32 + lane) * 4;
+        if(c < cols) {
+          xv[i] = *reinterpret_cast<const float4*>(x + off + c);
+          float4 yv = *reinterpret_cast<const float4*>(y + off + c);
+          av[i] = *reinterpret_cast<const float4*>(adj + off + c);
+          xh[i].x = (yv.x - b4[i].x) / g4[i].x;
+          xh[i].y = (yv.y - b4[i].y) / g4[i].y;
+          xh[i].z = (yv.z - b4[i].z) / g4[i].z;
+          xh[i].w = (yv.w - b4[i].w) / g4[i].w;
+        } else {
+          xv[i] = xh[i] = av[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        sum_x += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
+        sum_adj += (av[i].x + av[i].y) + (av[i].z + av[i].w);
+        sum_adj_x += (av[i].x * xh[i].x + av[i].y * xh[i].y) + (av[i].z * xh[i].z + av[i].w * xh[i].w);
+      }
+      sum_x = warpSum(sum_x);
+      sum_adj = warpSum(sum_adj);
+      sum_adj_x = warpSum(sum_adj_x);
+      float mean = sum_x / fcols;
+#pragma unroll
+      for(int i = 0; i < VPL; ++i) {
+        int c = (i * 32 + lane) * 4;
+        if(c < cols) {
+          float e0 = xv[i].x - mean, e1 = xv[i].y - mean, e2 = xv[i].z - mean, e3 = xv[i].w - mean;
+          sq += (e0 * e0 + e1 * e1) + (e2 * e2 + e3 * e3);
+        }
+      }
+    }
+    float sigma = sqrtf(eps + (warpSum(sq) / fcols));
+#pragma unroll
+    for(int i = 0; i < VPL; ++i) {
+      int c = (i * 32 + lane) * 4;
+      if(c < cols) {
+        float4 v;
+        v.x = lnGradElem(av[i].x, xh[i].x, g4[i].x, sum_adj, sum_adj_x, fcols, sigma);
+        v.y = lnGradElem(av[i].y, xh[i].y, g4[i].y, sum_adj, sum_adj_x, fcols, sigma);
+        v.z = lnGradElem(av[i].z, xh[i].z, g4[i].z, sum_adj, sum_adj_x, fcols, sigma);
+        v.w = lnGradElem(av[i].w, xh[i].w, g4[i].w, sum_adj, sum_adj_x, fcols, sigma);
+        float4* gx = reinterpret_cast<float4*>(gradX + off + c);
+        if(!assignX) {
+          float4 o = *gx;
+          v.x += o.x;
+          v.y += o.y;
+          v.z += o.z;
+          v.w += o.w;
+        }
+        *gx = v;
+        accG[i].x += av[i].x * xh[i].x;
+        accG[i].y += av[i].y * xh[i].y;
+        accG[i].z += av[i].z * xh[i].z;
+        accG[i].w += av[i].w * xh[i].w;
+        accB[i].x += av[i].x;
+        accB[i].y += av[i].y;
+        accB[i].z += av[i].z;
+        accB[i].w += av[i].w;
+      }
+    }
+  }
+  // column sums of the block: 8 warps meet in shared memory, ONE atomic per block and column
+#pragma unroll 1
+  for(int pass = 0; pass < 2; ++pass) {
+    float* dst = pass == 0 ? gradGamma : gradBeta;
+    if(!dst)
+      continue;
+    __syncthreads();
+#pragma unroll
+    for(int i = 0; i < VPL; ++i)
+      red[warp][i * 32 + lane] = pass == 0 ? accG[i] : accB[i];
+    __syncthreads();
+    for(int e = threadIdx.x; e < 32 * VPL; e += blockDim.x) {
+      int c = e * 4;
+      if(c < cols) {
+        float4 sum = red[0][e];
+#pragma unroll
+        for(int w = 1; w < 8; ++w) {
+          float4 t = red[w][e];
+          sum.x += t.x;
+          sum.y += t.y;
+          sum.z += t.z;
+          sum.w += t.w;
+        }
+        atomicAdd(dst + c, sum.x);
+        atomicAdd(dst + c + 1, sum.y);
+        atomicAdd(dst + c + 2, sum.z);
+        atomicAdd(dst + c + 3, sum.w);
+      }
+    }
+  }
+}
+
 }  // namespace
 
 void LayerNormalization(Tensor out, Tensor in, Tensor gamma, Tensor beta, float eps) {
   device::setDevice(out->getDevice());
   int cols = in->shape().back();
   int rows = in->shape().elements() / cols;
+  out->takeLazyZero();
+  const float* bp = beta ? beta->data() : nullptr;
+  bool aligned = (cols % 4 == 0) && (((uintptr_t)out->data() | (uintptr_t)in->data() | (uintptr_t)gamma->data() | (uintptr_t)bp) & 15) == 0;
+  if(aligned && cols <= 1024) {
+    int grid = std::max(1, std::min((rows + 7) / 8, kNumSMs * 4));
+    auto st = cudaStreamOfEngine();
+    if(cols <= 512)
+      gLNormalizationWarp<4><<<grid, 256, 0, st>>>(out->data(), in->data(), gamma->data(), bp, rows, cols, eps);
+    else
+      gLNormalizationWarp<8><<<grid, 256, 0, st>>>(out->data(), in->data(), gamma->data(), bp, rows, cols, eps);
+    CUDA_LAUNCH_CHECK();
+    return;
+  }
   auto l = rowLaunch(rows, cols);
-  ROW_DISPATCH(gLNormalization, l, out->data(), in->data(), gamma->data(), beta ? beta->data() : nullptr, rows, cols, eps);
+  ROW_DISPATCH(gLNormalization, l, out->data(), in->data(), gamma->data(), bp, rows, cols, eps);
 }
 
 void LayerNormalizationGrad(Tensor gradX, Tensor gradGamma, Tensor gradBeta, Tensor adj, Tensor y, Tensor x, Tensor gamma, Tensor beta, float eps) {
   device::setDevice(adj->getDevice());
   int cols = y->shape().back();
   int rows = y->shape().elements() / cols;
-  int grid = std::max(1, std::min(rows, kNumSMs * 4));
   auto st = cudaStreamOfEngine();
+  {
+    const float* bp = beta ? beta->data() : nullptr;
+    float* gbp = gradBeta ? gradBeta->data() : nullptr;
+    bool aligned = (cols % 4 == 0)
+                   && (((uintptr_t)gradX->memory()->data() | (uintptr_t)adj->data() | (uintptr_t)y->data() | (uintptr_t)x->data() | (uintptr_t)gamma->data() | (uintptr_t)bp) & 15) == 0;
+    if(aligned && cols <= 1024) {
+      int assignX = gradX->takeLazyZero() ? 1 : 0;
+      // few, fat blocks: every block ends with one atomic per column for gamma and beta
+      int grid = std::max(1, std::min((rows + 15) / 16, kNumSMs * 2));
+      if(cols <= 512)
+        gLayerNormalizationGradWarp<4><<<grid, 256, 0, st>>>(gradX->data(), gradGamma->data(), gbp, adj->data(), y->data(), x->data(), gamma->data(), bp, rows, cols, eps, assignX);
+      else
+        gLayerNormalizationGradWarp<8><<<grid, 256, 0, st>>>(gradX->data(), gradGamma->data(), gbp, adj->data(), y->data(), x->data(), gamma->data(), bp, rows, cols, eps, assignX);
+      CUDA_LAUNCH_CHECK();
+      return;
+    }
+  }
+  int grid = std::max(1, std::min(rows, kNumSMs * 4));
 #define LN_BWD(M)                                                                                                                  \
   gLayerNormalizationGrad<M><<<grid, 128, 0, st>>>(gradX->data(), gradGamma->data(), gradBeta ? gradBeta->data() : nullptr, adj->data(), \
                                                    y->data(), x->data(), gamma->data(), beta ? beta->data() : nullptr, rows, cols, eps)
@@ -1175,6 +1392,7 @@ struct TempIndices {
 
 void TransposeND(Tensor out, Tensor in, const std::vector<int>& vAxis) {
   device::setDevice(out->getDevice());
+  out->takeLazyZero();  // assigns every element
   Shape4 os(out->shape()), is(in->shape());
   Perm perm;
   int diff = 4 - (int)vAxis.size();
@@ -1225,6 +1443,7 @@ void Deconcatenate(std::vector<Tensor>& outputs, const Tensor in, int ax) {
   int offset = 0;
   for(auto out : outputs) {
     int width = out->shape().elements() / rows;
+    out->takeLazyZero();
     copyBlock<false>(in->data(), out->data(), rows, width, inWidth, offset);  // ASSIGNS
     offset += width;
   }
@@ -1295,6 +1514,7 @@ void Shift(Tensor out, Tensor in, Shape shift, bool invert) {
     offset += in->shape().stride(i) * shift[i];
   if(invert)
     offset = -offset;
+  out->takeLazyZero();  // assigns every element
   int length = out->shape().elements();
   gShift<<<gridFor(length, 256), 256, 0, cudaStreamOfEngine()>>>(out->data(), in->data(), length, offset);
   CUDA_LAUNCH_CHECK();

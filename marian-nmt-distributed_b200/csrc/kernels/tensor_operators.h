@@ -32,6 +32,7 @@ enum class GemmMode : int {
   FP32 = 0,    // fp32 SIMT contraction (exact-mode, used for 1e-4 parity runs)
   BF16 = 1,    // tcgen05 bf16 operands, fp32 accumulate in TMEM (throughput mode)
   BF16X3 = 2,  // tcgen05 with hi/lo bf16 split operands (3 products), ~fp32 accuracy
+  TF32 = 3,    // tcgen05 kind::tf32 directly on the fp32 tensors (no packing pass; throughput mode)
 };
 struct GemmContext;
 typedef GemmContext* GemmHandle;
@@ -99,6 +100,17 @@ void GRUFastBackward(std::vector<Tensor> outputs, std::vector<Tensor> inputs, Te
 
 void Att(Tensor out, Tensor va, Tensor context, Tensor state);
 void AttBack(Tensor gva, Tensor gContext, Tensor gState, Tensor va, Tensor context, Tensor state, Tensor adj);
+
+// Fused multi-head scaled-dot-product attention on [B, T, heads*dk] projections:
+//   out = JoinHeads(softmax(scale * SplitHeads(q) SplitHeads(k)^T + mask) SplitHeads(v))
+// i.e. the reference's Transformer::MultiHead core (src/models/transformer.h:153-192 with the
+// SplitHeads/JoinHeads of :58-77) as ONE operator.  `mask` is ADDITIVE (0 / -99999999) and holds
+// B*Tk (key mask) or B*Tq*Tk elements; `probs` [B, heads, Tq, Tk] receives the softmax output
+// for the backward pass (may be null in inference).  Grad ACCUMULATES into dq/dk/dv unless the
+// respective tensor is lazily zero (then it assigns).
+bool AttentionFusable(int Tq, int Tk, int dimModel, int heads);
+void MultiHeadAttention(Tensor out, Tensor probs, const Tensor q, const Tensor k, const Tensor v, const Tensor mask, int heads, float scale);
+void MultiHeadAttentionGrad(Tensor dq, Tensor dk, Tensor dv, const Tensor adj, const Tensor out, const Tensor probs, const Tensor q, const Tensor k, const Tensor v, int heads, float scale);
 
 void LayerNormalization(Tensor out, Tensor in, Tensor gamma, Tensor beta, float eps = 1e-9);
 void LayerNormalizationGrad(Tensor gradX, Tensor gradGamma, Tensor gradBeta, Tensor adj, Tensor y, Tensor x, Tensor gamma, Tensor beta, float eps = 1e-9);

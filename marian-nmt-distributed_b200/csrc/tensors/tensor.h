@@ -29,6 +29,8 @@ public:
     data_ = data;
     size_ = size;
   }
+  // see TensorBase::data(): shared by every tensor view over this piece (reshape nodes)
+  mutable bool lazyZero{false};
 
 private:
   uint8_t* data_;
@@ -45,16 +47,38 @@ public:
   TensorBase(Ptr<MemoryPiece> memory, Shape shape, int deviceId)
       : memory_(memory), shape_(shape), device_(deviceId) {}
 
-  float* data() const { return (float*)memory_->data(); }
+  // Lazy zero ("first writer assigns"): an adjoint starts as "logically all zeros, not yet
+  // written".  The reference memsets every adjoint and then accumulates into it
+  // (src/graph/node.cu:31-36 + a stream sync per set(0)); here an accumulating operator that
+  // finds the flag set ASSIGNS instead (takeLazyZero) - no memset, no read of the old value.
+  // Any other access through data() materialises the zeros first, so unaware code is safe.
+  float* data() const {
+    if(memory_->lazyZero) {
+      memory_->lazyZero = false;
+      device::setDevice(device_);
+      device::zero(memory_->data(), (size_t)shape_.elements() * sizeof(float));
+    }
+    return (float*)memory_->data();
+  }
+  void setLazyZero() { memory_->lazyZero = true; }
+  bool isLazyZero() const { return memory_->lazyZero; }
+  // true: the tensor holds no defined values and the caller promises to overwrite ALL of it
+  bool takeLazyZero() {
+    bool f = memory_->lazyZero;
+    memory_->lazyZero = false;
+    return f;
+  }
   const Shape& shape() const { return shape_; }
   size_t size() const { return (size_t)shape_.elements(); }
   Ptr<MemoryPiece> memory() const { return memory_; }
   int getDevice() const { return device_; }
 
-  void reset(Ptr<MemoryPiece> memory) { memory_ = memory; }
+  void reset(Ptr<MemoryPiece> memory) {
+    memory_ = memory;
+  }
 
   Tensor subtensor(int offset, int size) {
-    auto mem = New<MemoryPiece>(memory_->data() + sizeof(float) * (size_t)offset, sizeof(float) * (size_t)size);
+    auto mem = New<MemoryPiece>((uint8_t*)data() + sizeof(float) * (size_t)offset, sizeof(float) * (size_t)size);
     return Tensor(new TensorBase(mem, Shape{1, size}, device_));
   }
 
@@ -76,6 +100,7 @@ public:
   // --- asynchronous mutators ---
   void set(float value) {
     device::setDevice(device_);
+    memory_->lazyZero = false;
     if(value == 0.f)
       device::zero(data(), size() * sizeof(float));
     else
@@ -98,6 +123,7 @@ public:
   void copyFrom(Tensor in) {
     ABORT_IF(in->size() != size(), "copyFrom: size mismatch");
     device::setDevice(device_);
+    memory_->lazyZero = false;
     device::copyD2D(data(), in->data(), size() * sizeof(float));
   }
 
@@ -105,6 +131,8 @@ public:
   // caller can register a BatchUpload for it.
   void* upload(const void* src, size_t bytes) {
     device::setDevice(device_);
+    if(bytes >= size() * sizeof(float))
+      memory_->lazyZero = false;
     Staging* st = currentStaging();
     // large one-off uploads (parameter initialisation) do not go through the
     // graph's pinned staging: they would pin hundreds of MB for nothing

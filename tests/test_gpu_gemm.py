@@ -1,8 +1,9 @@
-"""Prod / ProdBatched / ProdAffine: the tcgen05 (bf16 and hi/lo-split bf16x3)
-and fp32 SIMT paths against the CPU oracle and against float64 numpy.
+"""Prod / ProdBatched / ProdAffine: the tcgen05 paths (tf32 on the raw fp32 tensors, packed
+bf16 and hi/lo-split bf16x3) and the fp32 SIMT path against the CPU oracle and float64 numpy.
 
 Tolerances (relative to the output magnitude):
   fp32 SIMT  1e-5      bf16x3  5e-5 (operands carry 16 mantissa bits)      bf16  1e-2
+  tf32  2e-3 (operands carry 11 mantissa bits)
 """
 import numpy as np
 import pytest
@@ -11,7 +12,7 @@ from test_gpu_ops import close, rnd
 
 pytestmark = pytest.mark.gpu
 
-TOL = {0: 1e-5, 2: 5e-5, 1: 1.5e-2}
+TOL = {0: 1e-5, 2: 5e-5, 1: 1.5e-2, 3: 2e-3}
 
 
 def ref_prod(A, B, tA, tB, beta, alpha, C0):
@@ -34,10 +35,17 @@ SHAPES = [  # (A shape, B shape, transA, transB)
     ((64, 1024), (1024, 3072), False, False),    # RNN step shape
     ((77, 40), (90, 77), True, True),
     ((1, 512), (512, 1000), False, False),
+    # 16-byte aligned ragged shapes: stay on the TMA-direct tf32 kernel in mode 3, all four layouts
+    ((300, 72), (72, 132), False, False),
+    ((132, 68), (36, 68), False, True),
+    ((68, 132), (68, 36), True, False),
+    ((76, 40), (92, 76), True, True),
+    ((3200, 512), (3200, 2048), True, False),    # FFN dW (split-K)
+    ((640, 4096), (4096, 512), False, False),    # long reduction
 ]
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 @pytest.mark.parametrize("sa,sb,tA,tB", SHAPES)
 @pytest.mark.parametrize("beta,alpha", [(0.0, 1.0), (1.0, 0.125)])
 def test_prod(cuda, oracle, mode, sa, sb, tA, tB, beta, alpha):
@@ -60,7 +68,7 @@ def test_prod(cuda, oracle, mode, sa, sb, tA, tB, beta, alpha):
         close(run(oracle, 0), exp, 1e-5, "oracle vs float64")
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 @pytest.mark.parametrize("sa,sb,tA,tB", [
     ((64, 8, 50, 64), (64, 8, 50, 64), False, True),    # Q K^T  (config B)
     ((64, 8, 50, 50), (64, 8, 50, 64), False, False),   # P V
@@ -69,6 +77,9 @@ def test_prod(cuda, oracle, mode, sa, sb, tA, tB, beta, alpha):
     ((3, 2, 7, 5), (3, 2, 5, 9), False, False),
     ((1, 1, 130, 70), (4, 2, 70, 33), False, False),    # A shared by all batches (stride 0)
     ((4, 2, 33, 70), (1, 1, 70, 130), False, False),    # B shared
+    ((5, 3, 52, 64), (5, 3, 64, 52), False, False),     # aligned: TMA-direct with batch coordinate
+    ((5, 3, 52, 64), (5, 3, 52, 40), True, False),
+    ((1, 1, 132, 72), (4, 2, 72, 36), False, False),
 ])
 def test_prod_batched(cuda, oracle, mode, sa, sb, tA, tB):
     A, B = rnd(1, *sa), rnd(2, *sb)
@@ -88,7 +99,7 @@ def test_prod_batched(cuda, oracle, mode, sa, sb, tA, tB):
     close(c.numpy(), exp, TOL[mode], "batched")
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 @pytest.mark.parametrize("M,K,N", [(3200, 512, 2048), (130, 70, 50), (320, 512, 32000)])
 def test_prod_affine(cuda, mode, M, K, N):
     A, B, bias = rnd(1, M, K), rnd(2, K, N), rnd(3, 1, N)
