@@ -20,6 +20,7 @@ CUDA_SOURCES = [
     "tensors/device_gpu.cu",
     "kernels/tensor_operators.cu",
     "kernels/gemm.cu",
+    "kernels/attention.cu",
 ]
 # host graph code: instantiates the Element/Add kernel templates, hence nvcc -x cu
 ENGINE_SOURCES = [

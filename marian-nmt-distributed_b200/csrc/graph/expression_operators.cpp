@@ -125,5 +125,11 @@ Expr highway(Expr y, Expr x, Expr t) {
   std::vector<Expr> nodes = {y, x, t};
   return Expression<HighwayNodeOp>(nodes);
 }
+Expr multi_head_attention(Expr q, Expr k, Expr v, Expr mask, int heads, float scale) {
+  std::vector<Expr> nodes = {q, k, v};
+  if(mask)
+    nodes.push_back(mask);
+  return Expression<MultiHeadAttentionNodeOp>(nodes, heads, scale);
+}
 
 }  // namespace marian

@@ -1,6 +1,8 @@
 // Node memory management + graph-side upload helpers.
 // Reference behaviour: src/graph/node.cu:7-51 (allocate / free / init_dependent
 // / set_zero_adjoint), src/graph/expression_graph.cu:24-35 (dropout mask node).
+#include <cstdlib>
+
 #include "graph/node.h"
 #include "graph/expression_graph.h"
 #include "data/batch.h"
@@ -43,7 +45,14 @@ void Node::init_dependent() {
 void Node::set_zero_adjoint() {
   if(!adj_) {
     graph()->tensor(adj_, shape_);
-    adj_->setLazyZero();  // zeroed on first touch, or assigned by the first accumulating writer
+    // zeroed on first touch, or assigned by the first accumulating writer
+    // (MRN_EAGER_ZERO=1 restores the reference's memset-then-accumulate for debugging)
+    static const bool eager = std::getenv("MRN_EAGER_ZERO") != nullptr;
+    static const char* eagerTypes = std::getenv("MRN_EAGER_TYPES");
+    if(eager || (eagerTypes && std::string(eagerTypes).find("," + type() + ",") != std::string::npos))
+      adj_->set(0);
+    else
+      adj_->setLazyZero();
   }
 }
 

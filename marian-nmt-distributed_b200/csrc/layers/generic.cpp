@@ -1,4 +1,7 @@
-// Training cost.  reference: src/layers/generic.cpp:5-42
+// Training cost on top of the logits.
+// Semantics of the reference's Cost() (src/layers/generic.cpp:5-42): per-token cross entropy,
+// optional label smoothing against the uniform distribution, masked, then reduced over time
+// (axis -3) and batch (axis -2) according to --cost-type.
 #include "layers/generic.h"
 
 namespace marian {
@@ -6,32 +9,30 @@ namespace marian {
 Expr Cost(Expr logits, Expr indices, Expr mask, std::string costType, float smoothing) {
   using namespace keywords;
 
-  auto ce = cross_entropy(logits, indices);
-
+  Expr tokenLoss = cross_entropy(logits, indices);
   if(smoothing > 0) {
-    // label smoothing: mix in the mean log-probability of the row
-    auto ceq = mean(logsoftmax(logits), axis = -1);
-    ce = (1 - smoothing) * ce - smoothing * ceq;
+    // smoothed target = (1 - s) * one-hot + s * uniform; the uniform part costs the mean log-prob
+    Expr uniformPart = mean(logsoftmax(logits), axis = -1);
+    tokenLoss = (1 - smoothing) * tokenLoss - smoothing * uniformPart;
   }
-
   if(mask)
-    ce = ce * mask;
+    tokenLoss = tokenLoss * mask;
 
-  Expr cost;
-  if(costType == "ce-mean" || costType == "cross-entropy") {
-    cost = mean(sum(ce, axis = -3), axis = -2);
-  } else if(costType == "ce-mean-words") {
-    cost = sum(sum(ce, axis = -3), axis = -2) / sum(sum(mask, axis = -3), axis = -2);
-  } else if(costType == "ce-sum") {
-    cost = sum(sum(ce, axis = -3), axis = -2);
-  } else if(costType == "perplexity") {
-    cost = exp(sum(sum(ce, axis = -3), axis = -2) / sum(sum(mask, axis = -3), axis = -2));
-  } else if(costType == "ce-rescore") {
-    cost = -sum(ce, axis = -3);
-  } else {
-    cost = mean(sum(ce, axis = -3), axis = -2);
-  }
-  return cost;
+  // [1, 1, B, 1] loss per sentence; the remaining reductions are over the batch axis
+  Expr perSentence = sum(tokenLoss, axis = -3);
+  auto overBatch = [](Expr x) { return sum(x, keywords::axis = -2); };
+  auto tokenCount = [&]() { return overBatch(sum(mask, axis = -3)); };
+
+  if(costType == "ce-sum")
+    return overBatch(perSentence);
+  if(costType == "ce-mean-words")
+    return overBatch(perSentence) / tokenCount();
+  if(costType == "perplexity")
+    return exp(overBatch(perSentence) / tokenCount());
+  if(costType == "ce-rescore")
+    return -perSentence;
+  // "ce-mean", "cross-entropy" and anything unknown: mean sentence loss
+  return mean(perSentence, axis = -2);
 }
 
 }  // namespace marian

@@ -1,11 +1,17 @@
-// Transformer encoder/decoder (Vaswani et al.) expressed in the operator API.
+// Transformer encoder / decoder (Vaswani et al. 2017) on the operator API.
 //
-// The node sequence - and therefore parameter creation order, which fixes the
-// random-initialisation stream - follows the reference's
-// src/models/transformer.h:7-662: embeddings * sqrt(d) + sinusoidal signal,
-// time<->batch transposes, additive -99999999 masks, per layer
-// {multi-head attention (4 affine + 2 bdot + softmax), add, layer-norm(1e-6),
-// FFN with swish, add, layer-norm}, output affine to the vocabulary.
+// Behavioural contract = the reference's src/models/transformer.h:7-662: same parameter names
+// and the same parameter CREATION ORDER (it fixes the random-initialisation stream, one seed
+// increment per tensor), embeddings * sqrt(d) + sinusoid table, batch-major layers, additive
+// -99999999 masks, sub-layer recipe strings ("dan": dropout, add residual, layer-norm(1e-6)),
+// swish feed-forward, vocabulary projection through mlp::dense.
+//
+// Organisation is this repo's own: a stateless TransformerSublayers toolbox parameterised by a
+// small Env (graph, options, inference flag), one routine for pre- and post-processing recipes,
+// and an attention core that is ONE fused operator (multi_head_attention, kernels/attention.cu)
+// whenever the shape allows it; the unfused node sequence of the reference (split heads, bdot,
+// mask add, softmax, bdot, join heads) stays available as "transformer-fused-attention=false"
+// and is what the CPU oracle builds.
 #pragma once
 
 #include <cmath>
@@ -14,315 +20,231 @@
 
 namespace marian {
 
-class Transformer {
-public:
-  Expr TransposeTimeBatch(Expr input) { return transpose(input, {0, 2, 1, 3}); }
+struct TransformerSublayers {
+  struct Env {
+    Ptr<ExpressionGraph> graph;
+    Ptr<Options> options;
+    bool inference;
 
-  // reference: transformer.h:11-35 (float arithmetic throughout)
-  Expr AddPositionalEmbeddings(Ptr<ExpressionGraph> graph, Expr input, int start = 0) {
-    using namespace keywords;
-    int dimEmb = input->shape()[-1];
-    int dimWords = input->shape()[-3];
+    float dropout(const char* key) const { return inference ? 0.f : options->get<float>(key); }
+    std::string recipe(const char* key) const { return options->get<std::string>(key); }
+    bool fuseAttention() const {
+      return options->get<bool>("transformer-fused-attention", std::string(device::backendName()) == "cuda");
+    }
+  };
 
-    float num_timescales = (float)(dimEmb / 2);
-    float log_timescale_increment = std::log(10000.f) / (num_timescales - 1.f);
+  // [.., T, B, d] <-> [.., B, T, d]
+  static Expr swapTimeBatch(Expr x) { return transpose(x, {0, 2, 1, 3}); }
 
-    std::vector<float> vPos((size_t)dimEmb * dimWords, 0);
-    for(int p = start; p < dimWords + start; ++p) {
-      for(int i = 0; i < num_timescales; ++i) {
-        float v = p * std::exp(i * -log_timescale_increment);
-        vPos[(p - start) * dimEmb + i] = std::sin(v);
-        vPos[(p - start) * dimEmb + (int)num_timescales + i] = std::cos(v);
+  // x + sinusoid(position): first half of the channels sin, second half cos, geometric
+  // wavelengths 1 .. 10000 (float arithmetic as in the reference, transformer.h:11-35)
+  static Expr addPositions(const Env& env, Expr x, int firstPosition = 0) {
+    const int channels = x->shape()[-1];
+    const int steps = x->shape()[-3];
+    const int half = channels / 2;
+    const float logStep = std::log(10000.f) / ((float)half - 1.f);
+
+    std::vector<float> table((size_t)steps * channels, 0.f);
+    for(int t = 0; t < steps; ++t) {
+      float* row = table.data() + (size_t)t * channels;
+      const int position = firstPosition + t;
+      for(int c = 0; c < half; ++c) {
+        float angle = position * std::exp(c * -logStep);
+        row[c] = std::sin(angle);
+        row[half + c] = std::cos(angle);
       }
     }
-    auto signal = graph->constant({dimWords, 1, dimEmb}, init = inits::from_vector(vPos));
-    return input + signal;
+    return x + env.graph->constant({steps, 1, channels}, keywords::init = inits::from_vector(table));
   }
 
-  Expr TriangleMask(Ptr<ExpressionGraph> graph, int length) {
+  // lower-triangular 0/1 matrix [1, n, n]: position i may look at j <= i
+  static Expr causalMask(const Env& env, int n) {
+    std::vector<float> tri((size_t)n * n, 0.f);
+    for(int i = 0; i < n; ++i)
+      std::fill(tri.begin() + (size_t)i * n, tri.begin() + (size_t)i * n + i + 1, 1.f);
+    return env.graph->constant({1, n, n}, keywords::init = inits::from_vector(tri));
+  }
+
+  // 0/1 mask [.., B, rows, T] -> additive {0, -99999999} mask [B, 1, rows, T] (broadcast over heads)
+  static Expr additiveMask(Expr keep) {
+    auto s = keep->shape();
+    return reshape((1 - keep) * -99999999.f, {s[-3], 1, s[-2], s[-1]});
+  }
+
+  // [1, B, T, 1] time-major padding mask -> [1, B, 1, T]
+  static Expr keyMask(Expr paddingMask, int batch, int steps) {
+    return reshape(swapTimeBatch(atleast_nd(paddingMask, 4)), {1, batch, 1, steps});
+  }
+
+  // One recipe interpreter for both ends of a sub-layer.  Letters: d dropout, a add the residual,
+  // h highway gate with the residual, n layer-norm.  `residual` == nullptr is the pre-processing
+  // flavour (no a/h; layer-norm parameters carry the "_pre" suffix).
+  static Expr runRecipe(const Env& env, const std::string& prefix, const std::string& recipe, Expr x, Expr residual, float dropProb) {
     using namespace keywords;
-    std::vector<float> vMask((size_t)length * length, 0);
-    for(int i = 0; i < length; ++i)
-      for(int j = 0; j <= i; ++j)
-        vMask[i * length + j] = 1.f;
-    return graph->constant({1, length, length}, init = inits::from_vector(vMask));
-  }
-
-  // 0/1 mask -> additive mask {0, -99999999}, shaped for broadcasting over heads
-  Expr InverseMask(Expr mask) {
-    auto ms = mask->shape();
-    mask = (1 - mask) * -99999999.f;
-    return reshape(mask, {ms[-3], 1, ms[-2], ms[-1]});
-  }
-
-  Expr SplitHeads(Expr input, int dimHeads) {
-    int dimModel = input->shape()[-1];
-    int dimSteps = input->shape()[-2];
-    int dimBatch = input->shape()[-3];
-    int dimBeam = input->shape()[-4];
-    int dimDepth = dimModel / dimHeads;
-    auto output = reshape(input, {dimBatch * dimBeam, dimSteps, dimHeads, dimDepth});
-    return transpose(output, {0, 2, 1, 3});
-  }
-
-  Expr JoinHeads(Expr input, int dimBeam = 1) {
-    int dimDepth = input->shape()[-1];
-    int dimSteps = input->shape()[-2];
-    int dimHeads = input->shape()[-3];
-    int dimBatchBeam = input->shape()[-4];
-    int dimModel = dimHeads * dimDepth;
-    int dimBatch = dimBatchBeam / dimBeam;
-    auto output = transpose(input, {0, 2, 1, 3});
-    return reshape(output, {dimBeam, dimBatch, dimSteps, dimModel});
-  }
-
-  Expr PreProcess(Ptr<ExpressionGraph> graph, std::string prefix, std::string ops, Expr input, float dropProb = 0.0f) {
-    using namespace keywords;
-    int dimModel = input->shape()[-1];
-    auto output = input;
-    for(auto op : ops) {
-      if(op == 'd' && dropProb > 0.0f) {
-        auto dropMask = graph->dropout(dropProb, output->shape());
-        output = dropout(output, mask = dropMask);
-      }
-      if(op == 'n') {
-        auto scale = graph->param(prefix + "_ln_scale_pre", {1, dimModel}, init = inits::ones);
-        auto bias = graph->param(prefix + "_ln_bias_pre", {1, dimModel}, init = inits::zeros);
-        output = layer_norm(output, scale, bias, 1e-6);
-      }
-    }
-    return output;
-  }
-
-  Expr PostProcess(Ptr<ExpressionGraph> graph,
-                   std::string prefix,
-                   std::string ops,
-                   Expr input,
-                   Expr prevInput,
-                   float dropProb = 0.0f) {
-    using namespace keywords;
-    int dimModel = input->shape()[-1];
-    auto output = input;
-    for(auto op : ops) {
-      if(op == 'd' && dropProb > 0.0f) {
-        auto dropMask = graph->dropout(dropProb, output->shape());
-        output = dropout(output, mask = dropMask);
-      }
-      if(op == 'a')
-        output = output + prevInput;
-      if(op == 'h') {
-        auto Wh = graph->param(prefix + "_Wh", {dimModel, dimModel}, init = inits::glorot_uniform);
-        auto bh = graph->param(prefix + "_bh", {1, dimModel}, init = inits::zeros);
-        auto t = affine(prevInput, Wh, bh);
-        output = highway(output, prevInput, t);
-      }
-      if(op == 'n') {
-        auto scale = graph->param(prefix + "_ln_scale", {1, dimModel}, init = inits::ones);
-        auto bias = graph->param(prefix + "_ln_bias", {1, dimModel}, init = inits::zeros);
-        output = layer_norm(output, scale, bias, 1e-6);
+    const int width = x->shape()[-1];
+    const std::string suffix = residual ? "" : "_pre";
+    for(char step : recipe) {
+      switch(step) {
+        case 'd':
+          if(dropProb > 0.f)
+            x = dropout(x, mask = env.graph->dropout(dropProb, x->shape()));
+          break;
+        case 'a':
+          if(residual)
+            x = x + residual;
+          break;
+        case 'h':
+          if(residual) {
+            auto Wh = env.graph->param(prefix + "_Wh", {width, width}, init = inits::glorot_uniform);
+            auto bh = env.graph->param(prefix + "_bh", {1, width}, init = inits::zeros);
+            x = highway(x, residual, affine(residual, Wh, bh));
+          }
+          break;
+        case 'n': {
+          auto gain = env.graph->param(prefix + "_ln_scale" + suffix, {1, width}, init = inits::ones);
+          auto shift = env.graph->param(prefix + "_ln_bias" + suffix, {1, width}, init = inits::zeros);
+          x = layer_norm(x, gain, shift, 1e-6);
+          break;
+        }
+        default: break;
       }
     }
-    return output;
+    return x;
   }
 
-  // softmax(q k^T / sqrt(dk) + mask) v     reference: :153-192
-  Expr Attention(Ptr<ExpressionGraph> graph,
-                 Ptr<Options> options,
-                 std::string prefix,
-                 Expr q,
-                 Expr k,
-                 Expr v,
-                 Expr mask = nullptr,
-                 bool inference = false) {
+  static Expr linear(const Env& env, const std::string& weight, const std::string& bias, Expr x, int in, int out) {
     using namespace keywords;
-    float dk = (float)k->shape()[-1];
-    float scale = 1.0f / std::sqrt(dk);
-
-    int dimBeamQ = q->shape()[-4];
-    int dimBeamK = k->shape()[-4];
-    int dimBeam = dimBeamQ / dimBeamK;
-    if(dimBeam > 1) {
-      k = repeat(k, dimBeam, axis = -4);
-      v = repeat(v, dimBeam, axis = -4);
-    }
-
-    auto weights = softmax(bdot(q, k, false, true, scale) + mask);
-
-    float dropProb = inference ? 0 : options->get<float>("transformer-dropout-attention");
-    if(dropProb) {
-      auto dropMask = graph->dropout(dropProb, weights->shape());
-      weights = dropout(weights, keywords::mask = dropMask);
-    }
-    return bdot(weights, v);
+    auto W = env.graph->param(weight, {in, out}, init = inits::glorot_uniform);
+    auto b = env.graph->param(bias, {1, out}, init = inits::zeros);
+    return affine(x, W, b);
   }
 
-  // reference: :194-261
-  Expr MultiHead(Ptr<ExpressionGraph> graph,
-                 Ptr<Options> options,
-                 std::string prefix,
-                 int dimOut,
-                 int dimHeads,
-                 Expr q,
-                 const std::vector<Expr>& keys,
-                 const std::vector<Expr>& values,
-                 const std::vector<Expr>& masks,
-                 bool inference = false) {
+  // ---- unfused attention core (the reference's node sequence, transformer.h:58-77,153-192) ----
+  static Expr splitHeads(Expr x, int heads) {
+    auto s = x->shape();
+    return transpose(reshape(x, {s[-3] * s[-4], s[-2], heads, s[-1] / heads}), {0, 2, 1, 3});
+  }
+  static Expr joinHeads(Expr x, int beam) {
+    auto s = x->shape();  // [B*beam, heads, T, dk]
+    return reshape(transpose(x, {0, 2, 1, 3}), {beam, s[-4] / beam, s[-2], s[-3] * s[-1]});
+  }
+  static Expr attendUnfused(const Env& env, Expr q, Expr k, Expr v, Expr mask, int heads, int beam) {
     using namespace keywords;
-    int dimModel = q->shape()[-1];
-
-    auto Wq = graph->param(prefix + "_Wq", {dimModel, dimModel}, init = inits::glorot_uniform);
-    auto bq = graph->param(prefix + "_bq", {1, dimModel}, init = inits::zeros);
-    auto qh = affine(q, Wq, bq);
-    qh = SplitHeads(qh, dimHeads);
-
-    std::vector<Expr> outputs;
-    for(size_t i = 0; i < keys.size(); ++i) {
-      std::string prefixProj = prefix;
-      if(i > 0)
-        prefixProj += "_enc" + std::to_string(i + 1);
-
-      auto Wk = graph->param(prefixProj + "_Wk", {dimModel, dimModel}, init = inits::glorot_uniform);
-      auto bk = graph->param(prefixProj + "_bk", {1, dimModel}, init = inits::zeros);
-      auto Wv = graph->param(prefixProj + "_Wv", {dimModel, dimModel}, init = inits::glorot_uniform);
-      auto bv = graph->param(prefixProj + "_bv", {1, dimModel}, init = inits::zeros);
-
-      auto kh = affine(keys[i], Wk, bk);
-      auto vh = affine(values[i], Wv, bv);
-      kh = SplitHeads(kh, dimHeads);
-      vh = SplitHeads(vh, dimHeads);
-
-      auto output = Attention(graph, options, prefix, qh, kh, vh, masks[i], inference);
-      output = JoinHeads(output, q->shape()[-4]);
-      outputs.push_back(output);
+    Expr qh = splitHeads(q, heads), kh = splitHeads(k, heads), vh = splitHeads(v, heads);
+    const float scale = 1.0f / std::sqrt((float)kh->shape()[-1]);
+    const int beamRatio = qh->shape()[-4] / kh->shape()[-4];
+    if(beamRatio > 1) {  // beam search: keys/values are shared by the hypotheses of a sentence
+      kh = repeat(kh, beamRatio, axis = -4);
+      vh = repeat(vh, beamRatio, axis = -4);
     }
-
-    Expr output = outputs.size() > 1 ? concatenate(outputs, axis = -1) : outputs.front();
-
-    int dimAtt = output->shape()[-1];
-    auto Wo = graph->param(prefix + "_Wo", {dimAtt, dimOut}, init = inits::glorot_uniform);
-    auto bo = graph->param(prefix + "_bo", {1, dimOut}, init = inits::zeros);
-    return affine(output, Wo, bo);
+    Expr weights = softmax(bdot(qh, kh, false, true, scale) + mask);
+    float dropProb = env.dropout("transformer-dropout-attention");
+    if(dropProb)
+      weights = dropout(weights, keywords::mask = env.graph->dropout(dropProb, weights->shape()));
+    return joinHeads(bdot(weights, vh), beam);
   }
 
-  Expr LayerAttention(Ptr<ExpressionGraph> graph,
-                      Ptr<Options> options,
-                      std::string prefix,
-                      Expr input,
-                      Expr keys,
-                      Expr values,
-                      Expr mask,
-                      bool inference = false) {
-    return LayerAttention(graph,
-                          options,
-                          prefix,
-                          input,
-                          std::vector<Expr>{keys},
-                          std::vector<Expr>{values},
-                          std::vector<Expr>{mask},
-                          inference);
+  // softmax(q k^T / sqrt(dk) + mask) v over `heads` heads; q, k, v are [beam, B, T, d] projections
+  static Expr attend(const Env& env, Expr q, Expr k, Expr v, Expr mask, int heads) {
+    const int beam = q->shape()[-4];
+    const int width = q->shape()[-1];
+    const bool fusable = env.fuseAttention() && beam == 1 && k->shape()[-4] == 1 && mask && env.dropout("transformer-dropout-attention") == 0.f
+                         && AttentionFusable(q->shape()[-2], k->shape()[-2], width, heads);
+    if(fusable)
+      return multi_head_attention(q, k, v, mask, heads, 1.0f / std::sqrt((float)(width / heads)));
+    return attendUnfused(env, q, k, v, mask, heads, beam);
   }
 
-  // reference: :281-316
-  Expr LayerAttention(Ptr<ExpressionGraph> graph,
-                      Ptr<Options> options,
-                      std::string prefix,
-                      Expr input,
-                      const std::vector<Expr>& keys,
-                      const std::vector<Expr>& values,
-                      const std::vector<Expr>& masks,
-                      bool inference = false) {
-    int dimModel = input->shape()[-1];
-    float dropProb = inference ? 0 : options->get<float>("transformer-dropout");
-    auto opsPre = options->get<std::string>("transformer-preprocess");
-    auto output = PreProcess(graph, prefix + "_Wo", opsPre, input, dropProb);
+  // projections + attention core + output projection.  Parameter order: Wq bq, then per memory
+  // Wk bk Wv bv, then Wo bo (reference :194-261).  Several memories (multi-source) are attended
+  // separately and concatenated before Wo.
+  static Expr multiHead(const Env& env, const std::string& prefix, int heads, Expr query, const std::vector<Expr>& memories, const std::vector<Expr>& masks) {
+    const int width = query->shape()[-1];
+    Expr q = linear(env, prefix + "_Wq", prefix + "_bq", query, width, width);
 
-    int heads = (int)options->get<float>("transformer-heads");
-    output = MultiHead(graph, options, prefix, dimModel, heads, output, keys, values, masks, inference);
-
-    auto opsPost = options->get<std::string>("transformer-postprocess");
-    return PostProcess(graph, prefix + "_Wo", opsPost, output, input, dropProb);
+    std::vector<Expr> contexts;
+    for(size_t m = 0; m < memories.size(); ++m) {
+      std::string p = m == 0 ? prefix : prefix + "_enc" + std::to_string(m + 1);
+      Expr k = linear(env, p + "_Wk", p + "_bk", memories[m], width, width);
+      Expr v = linear(env, p + "_Wv", p + "_bv", memories[m], width, width);
+      contexts.push_back(attend(env, q, k, v, masks[m], heads));
+    }
+    Expr joined = contexts.size() == 1 ? contexts.front() : concatenate(contexts, keywords::axis = -1);
+    return linear(env, prefix + "_Wo", prefix + "_bo", joined, joined->shape()[-1], width);
   }
 
-  // reference: :318-350
-  Expr LayerFFN(Ptr<ExpressionGraph> graph, Ptr<Options> options, std::string prefix, Expr input, bool inference = false) {
+  // pre-recipe -> multi-head attention over `memories` -> post-recipe with the residual
+  static Expr attentionSublayer(const Env& env, const std::string& prefix, Expr x, const std::vector<Expr>& memories, const std::vector<Expr>& masks) {
+    const float dropProb = env.dropout("transformer-dropout");
+    Expr h = runRecipe(env, prefix + "_Wo", env.recipe("transformer-preprocess"), x, nullptr, dropProb);
+    h = multiHead(env, prefix, (int)env.options->get<float>("transformer-heads"), h, memories, masks);
+    return runRecipe(env, prefix + "_Wo", env.recipe("transformer-postprocess"), h, x, dropProb);
+  }
+
+  // pre-recipe -> W2 swish(W1 x + b1) + b2 -> post-recipe with the residual (reference :318-350)
+  static Expr feedForwardSublayer(const Env& env, const std::string& prefix, Expr x) {
+    const int width = x->shape()[-1];
+    const int inner = env.options->get<int>("transformer-dim-ffn");
+    const float dropProb = env.dropout("transformer-dropout");
+    Expr h = runRecipe(env, prefix + "_ffn", env.recipe("transformer-preprocess"), x, nullptr, dropProb);
+    // all four parameters are created before the first product (initialisation stream order)
     using namespace keywords;
-    int dimModel = input->shape()[-1];
-    float dropProb = inference ? 0 : options->get<float>("transformer-dropout");
-    auto opsPre = options->get<std::string>("transformer-preprocess");
-    auto output = PreProcess(graph, prefix + "_ffn", opsPre, input, dropProb);
+    auto W1 = env.graph->param(prefix + "_W1", {width, inner}, init = inits::glorot_uniform);
+    auto b1 = env.graph->param(prefix + "_b1", {1, inner}, init = inits::zeros);
+    auto W2 = env.graph->param(prefix + "_W2", {inner, width}, init = inits::glorot_uniform);
+    auto b2 = env.graph->param(prefix + "_b2", {1, width}, init = inits::zeros);
+    h = affine(swish(affine(h, W1, b1)), W2, b2);
+    return runRecipe(env, prefix + "_ffn", env.recipe("transformer-postprocess"), h, x, dropProb);
+  }
 
-    int dimFfn = options->get<int>("transformer-dim-ffn");
-    auto W1 = graph->param(prefix + "_W1", {dimModel, dimFfn}, init = inits::glorot_uniform);
-    auto b1 = graph->param(prefix + "_b1", {1, dimFfn}, init = inits::zeros);
-    auto W2 = graph->param(prefix + "_W2", {dimFfn, dimModel}, init = inits::glorot_uniform);
-    auto b2 = graph->param(prefix + "_b2", {1, dimModel}, init = inits::zeros);
-
-    output = affine(output, W1, b1);
-    output = swish(output);
-    output = affine(output, W2, b2);
-
-    auto opsPost = options->get<std::string>("transformer-postprocess");
-    return PostProcess(graph, prefix + "_ffn", opsPost, output, input, dropProb);
+  // sqrt(d) * embeddings + positions, batch-major, embedding recipe applied
+  static Expr embedInput(const Env& env, const std::string& prefix, Expr embeddings, float wordDropout, int firstPosition) {
+    using namespace keywords;
+    if(wordDropout) {
+      int words = embeddings->shape()[-3];
+      embeddings = dropout(embeddings, mask = env.graph->dropout(wordDropout, {words, 1, 1}));
+    }
+    const int width = embeddings->shape()[-1];
+    Expr x = addPositions(env, std::sqrt((float)width) * embeddings, firstPosition);
+    x = swapTimeBatch(atleast_nd(x, 4));
+    return runRecipe(env, prefix + "_emb", env.recipe("transformer-postprocess-emb"), x, nullptr, env.dropout("transformer-dropout"));
   }
 };
 
-class EncoderTransformer : public EncoderBase, public Transformer {
+class EncoderTransformer : public EncoderBase {
 public:
   EncoderTransformer(Ptr<Options> options) : EncoderBase(options) {}
 
-  Expr WordEmbeddings(Ptr<ExpressionGraph> graph, Ptr<data::CorpusBatch> batch) {
-    int dimVoc = opt<std::vector<int>>("dim-vocabs")[batchIndex_];
-    int dimEmb = opt<int>("dim-emb");
-    auto embFactory = embedding(graph)("dimVocab", dimVoc)("dimEmb", dimEmb);
-    if(opt<bool>("tied-embeddings-src") || opt<bool>("tied-embeddings-all"))
-      embFactory("prefix", "Wemb");
-    else
-      embFactory("prefix", prefix_ + "_Wemb");
+  Expr sourceEmbeddings(Ptr<ExpressionGraph> graph) {
+    auto factory = embedding(graph)("dimVocab", opt<std::vector<int>>("dim-vocabs")[batchIndex_])("dimEmb", opt<int>("dim-emb"));
+    bool shared = opt<bool>("tied-embeddings-src") || opt<bool>("tied-embeddings-all");
+    factory("prefix", shared ? std::string("Wemb") : prefix_ + "_Wemb");
     if(options_->has("embedding-fix-src"))
-      embFactory("fixed", opt<bool>("embedding-fix-src"));
-    return embFactory.construct();
+      factory("fixed", opt<bool>("embedding-fix-src"));
+    return factory.construct();
   }
 
-  // reference: :384-449
+  // reference: transformer.h:384-449
   Ptr<EncoderState> build(Ptr<ExpressionGraph> graph, Ptr<data::CorpusBatch> batch) {
-    using namespace keywords;
-    int dimEmb = opt<int>("dim-emb");
-    int dimBatch = (int)batch->size();
-    int dimSrcWords = (int)(*batch)[batchIndex_]->batchWidth();
+    typedef TransformerSublayers T;
+    T::Env env{graph, options_, inference_};
+    const int sentences = (int)batch->size();
+    const int steps = (int)(*batch)[batchIndex_]->batchWidth();
 
-    auto embeddings = WordEmbeddings(graph, batch);
+    Expr tokens, padding;
+    std::tie(tokens, padding) = EncoderBase::lookup(sourceEmbeddings(graph), batch);
 
-    Expr batchEmbeddings, batchMask;
-    std::tie(batchEmbeddings, batchMask) = EncoderBase::lookup(embeddings, batch);
+    Expr x = T::embedInput(env, prefix_, tokens, env.dropout("dropout-src"), 0);
+    Expr padding4 = atleast_nd(padding, 4);
+    Expr mask = T::additiveMask(T::keyMask(padding4, sentences, steps));
 
-    float dropoutSrc = inference_ ? 0 : opt<float>("dropout-src");
-    if(dropoutSrc) {
-      int srcWords = batchEmbeddings->shape()[-3];
-      auto dropMask = graph->dropout(dropoutSrc, {srcWords, 1, 1});
-      batchEmbeddings = dropout(batchEmbeddings, mask = dropMask);
+    const int depth = opt<int>("enc-depth");
+    for(int l = 1; l <= depth; ++l) {
+      std::string layer = prefix_ + "_l" + std::to_string(l);
+      x = T::attentionSublayer(env, layer + "_self", x, {x}, {mask});
+      x = T::feedForwardSublayer(env, layer + "_ffn", x);
     }
-
-    auto scaledEmbeddings = std::sqrt((float)dimEmb) * batchEmbeddings;
-    scaledEmbeddings = AddPositionalEmbeddings(graph, scaledEmbeddings);
-    scaledEmbeddings = atleast_nd(scaledEmbeddings, 4);
-    batchMask = atleast_nd(batchMask, 4);
-    auto layer = TransposeTimeBatch(scaledEmbeddings);
-    auto layerMask = reshape(TransposeTimeBatch(batchMask), {1, dimBatch, 1, dimSrcWords});
-
-    auto opsEmb = opt<std::string>("transformer-postprocess-emb");
-    float dropProb = inference_ ? 0 : opt<float>("transformer-dropout");
-    layer = PreProcess(graph, prefix_ + "_emb", opsEmb, layer, dropProb);
-
-    layerMask = InverseMask(layerMask);
-
-    for(int i = 1; i <= opt<int>("enc-depth"); ++i) {
-      layer = LayerAttention(
-          graph, options_, prefix_ + "_l" + std::to_string(i) + "_self", layer, layer, layer, layerMask, inference_);
-      layer = LayerFFN(graph, options_, prefix_ + "_l" + std::to_string(i) + "_ffn", layer, inference_);
-    }
-
-    auto context = TransposeTimeBatch(layer);
-    return New<EncoderState>(context, batchMask, batch);
+    return New<EncoderState>(T::swapTimeBatch(x), padding4, batch);
   }
 
   void clear() {}
@@ -334,119 +256,67 @@ public:
       : DecoderState(states, probs, encStates) {}
 };
 
-class DecoderTransformer : public DecoderBase, public Transformer {
+class DecoderTransformer : public DecoderBase {
 public:
   DecoderTransformer(Ptr<Options> options) : DecoderBase(options) {}
 
-  virtual Ptr<DecoderState> startState(Ptr<ExpressionGraph> graph,
-                                       Ptr<data::CorpusBatch> batch,
-                                       std::vector<Ptr<EncoderState>>& encStates) {
-    rnn::States startStates;
-    return New<TransformerState>(startStates, nullptr, encStates);
+  virtual Ptr<DecoderState> startState(Ptr<ExpressionGraph>, Ptr<data::CorpusBatch>, std::vector<Ptr<EncoderState>>& encStates) {
+    return New<TransformerState>(rnn::States(), nullptr, encStates);
   }
 
-  // reference: :495-662
+  // reference: transformer.h:495-662.  During training the whole target is one "step".
   virtual Ptr<DecoderState> step(Ptr<ExpressionGraph> graph, Ptr<DecoderState> state) {
+    typedef TransformerSublayers T;
     using namespace keywords;
+    T::Env env{graph, options_, inference_};
 
-    auto embeddings = state->getTargetEmbeddings();
-    auto decoderMask = state->getTargetMask();
+    // layer inputs cached by previous decoding steps: new queries attend to old + new positions
+    auto history = state->getStates();
+    const int firstPosition = (history.size() == 0) ? 0 : history[0].output->shape()[-2];
 
-    float dropoutTrg = inference_ ? 0 : opt<float>("dropout-trg");
-    if(dropoutTrg) {
-      int trgWords = embeddings->shape()[-3];
-      auto trgWordDrop = graph->dropout(dropoutTrg, {trgWords, 1, 1});
-      embeddings = dropout(embeddings, mask = trgWordDrop);
+    Expr x = T::embedInput(env, prefix_, state->getTargetEmbeddings(), env.dropout("dropout-trg"), firstPosition);
+    const int beam = x->shape()[-4];
+    const int sentences = x->shape()[-3];
+    const int steps = x->shape()[-2];
+
+    Expr selfKeep = T::causalMask(env, steps);
+    if(Expr padding = state->getTargetMask())
+      selfKeep = selfKeep * T::keyMask(padding, sentences, steps);
+    Expr selfMask = T::additiveMask(selfKeep);
+
+    std::vector<Expr> memories, memoryMasks;
+    for(auto enc : state->getEncoderStates()) {
+      Expr memory = T::swapTimeBatch(enc->getContext());
+      Expr m = T::additiveMask(T::keyMask(enc->getMask(), sentences, memory->shape()[-2]));
+      if(beam > 1)
+        m = repeat(m, beam, axis = -4);
+      memories.push_back(memory);
+      memoryMasks.push_back(m);
     }
 
-    int dimEmb = embeddings->shape()[-1];
-    int dimBeam = 1;
-    if(embeddings->shape().size() > 3)
-      dimBeam = embeddings->shape()[-4];
+    rnn::States cache;
+    const int depth = opt<int>("dec-depth");
+    for(int l = 1; l <= depth; ++l) {
+      std::string layer = prefix_ + "_l" + std::to_string(l);
+      Expr selfMemory = (history.size() == 0) ? x : concatenate({history[l - 1].output, x}, axis = -2);
+      cache.push_back({selfMemory, nullptr});
 
-    auto scaledEmbeddings = std::sqrt((float)dimEmb) * embeddings;
-
-    int startPos = 0;
-    auto prevDecoderStates = state->getStates();
-    if(prevDecoderStates.size() > 0)
-      startPos = prevDecoderStates[0].output->shape()[-2];
-
-    scaledEmbeddings = AddPositionalEmbeddings(graph, scaledEmbeddings, startPos);
-    scaledEmbeddings = atleast_nd(scaledEmbeddings, 4);
-
-    auto query = TransposeTimeBatch(scaledEmbeddings);
-
-    auto opsEmb = opt<std::string>("transformer-postprocess-emb");
-    float dropProb = inference_ ? 0 : opt<float>("transformer-dropout");
-    query = PreProcess(graph, prefix_ + "_emb", opsEmb, query, dropProb);
-
-    rnn::States decoderStates;
-    int dimTrgWords = query->shape()[-2];
-    int dimBatch = query->shape()[-3];
-    auto selfMask = TriangleMask(graph, dimTrgWords);
-    if(decoderMask) {
-      decoderMask = atleast_nd(decoderMask, 4);
-      decoderMask = reshape(TransposeTimeBatch(decoderMask), {1, dimBatch, 1, dimTrgWords});
-      selfMask = selfMask * decoderMask;
-    }
-    selfMask = InverseMask(selfMask);
-
-    std::vector<Expr> encoderContexts;
-    std::vector<Expr> encoderMasks;
-    for(auto encoderState : state->getEncoderStates()) {
-      auto encoderContext = encoderState->getContext();
-      auto encoderMask = encoderState->getMask();
-
-      encoderContext = TransposeTimeBatch(encoderContext);
-      int dimSrcWords = encoderContext->shape()[-2];
-
-      encoderMask = atleast_nd(encoderMask, 4);
-      encoderMask = reshape(TransposeTimeBatch(encoderMask), {1, dimBatch, 1, dimSrcWords});
-      encoderMask = InverseMask(encoderMask);
-      if(dimBeam > 1)
-        encoderMask = repeat(encoderMask, dimBeam, axis = -4);
-
-      encoderContexts.push_back(encoderContext);
-      encoderMasks.push_back(encoderMask);
-    }
-
-    for(int i = 1; i <= opt<int>("dec-depth"); ++i) {
-      auto values = query;
-      if(prevDecoderStates.size() > 0)
-        values = concatenate({prevDecoderStates[i - 1].output, query}, axis = -2);
-      decoderStates.push_back({values, nullptr});
-
-      query = LayerAttention(
-          graph, options_, prefix_ + "_l" + std::to_string(i) + "_self", query, values, values, selfMask, inference_);
-
-      // one context-attention block per encoder, stacked (the reference's "stack" mode, :600-621)
-      for(size_t j = 0; j < encoderContexts.size(); ++j) {
-        std::string prefix = prefix_ + "_l" + std::to_string(i) + "_context";
-        if(j > 0)
-          prefix += "_enc" + std::to_string(j + 1);
-        query = LayerAttention(
-            graph, options_, prefix, query, encoderContexts[j], encoderContexts[j], encoderMasks[j], inference_);
+      x = T::attentionSublayer(env, layer + "_self", x, {selfMemory}, {selfMask});
+      // one cross-attention sub-layer per encoder, stacked
+      for(size_t e = 0; e < memories.size(); ++e) {
+        std::string name = layer + "_context" + (e == 0 ? std::string() : "_enc" + std::to_string(e + 1));
+        x = T::attentionSublayer(env, name, x, {memories[e]}, {memoryMasks[e]});
       }
-
-      query = LayerFFN(graph, options_, prefix_ + "_l" + std::to_string(i) + "_ffn", query, inference_);
+      x = T::feedForwardSublayer(env, layer + "_ffn", x);
     }
 
-    auto decoderContext = TransposeTimeBatch(query);
-
-    int dimTrgVoc = opt<std::vector<int>>("dim-vocabs").back();
-
-    auto layerOut = mlp::dense(graph)("prefix", prefix_ + "_ff_logit_out")("dim", dimTrgVoc);
+    auto projection = mlp::dense(graph)("prefix", prefix_ + "_ff_logit_out")("dim", opt<std::vector<int>>("dim-vocabs").back());
     if(opt<bool>("tied-embeddings") || opt<bool>("tied-embeddings-all")) {
-      std::string tiedPrefix = prefix_ + "_Wemb";
-      if(opt<bool>("tied-embeddings-all") || opt<bool>("tied-embeddings-src"))
-        tiedPrefix = "Wemb";
-      layerOut.tie_transposed("W", tiedPrefix);
+      bool shared = opt<bool>("tied-embeddings-all") || opt<bool>("tied-embeddings-src");
+      projection.tie_transposed("W", shared ? std::string("Wemb") : prefix_ + "_Wemb");
     }
-
-    auto output = mlp::mlp(graph).push_back(layerOut);
-    Expr logits = output->apply(decoderContext);
-
-    return New<TransformerState>(decoderStates, logits, state->getEncoderStates());
+    Expr logits = mlp::mlp(graph).push_back(projection)->apply(T::swapTimeBatch(x));
+    return New<TransformerState>(cache, logits, state->getEncoderStates());
   }
 
   void clear() {}

@@ -60,7 +60,15 @@ public:
     }
     return (float*)memory_->data();
   }
-  void setLazyZero() { memory_->lazyZero = true; }
+  void setLazyZero() {
+#ifdef MRN_ORACLE_CPU
+    // the CPU oracle keeps the reference's memset-then-accumulate (its operators also call
+    // data() from inside OpenMP regions, where a lazy memset would race)
+    set(0.f);
+#else
+    memory_->lazyZero = true;
+#endif
+  }
   bool isLazyZero() const { return memory_->lazyZero; }
   // true: the tensor holds no defined values and the caller promises to overwrite ALL of it
   bool takeLazyZero() {

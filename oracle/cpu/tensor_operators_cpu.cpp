@@ -747,6 +747,137 @@ void AttBack(Tensor gVa, Tensor gContext, Tensor gState, Tensor va, Tensor conte
 }
 
 // ---------------------------------------------------------------------------
+// Multi-head attention core: the reference has no such operator - it is the node
+// sequence of Transformer::MultiHead / Attention (src/models/transformer.h:58-77,153-192):
+//   SplitHeads (reshape [B,T,H,dk] + transpose {0,2,1,3}), bdot(q, k, false, true, scale),
+//   + additive mask, softmax over the keys, bdot(weights, v), JoinHeads.
+// Restated here as plain loops per (sentence, head) so the fused CUDA operator has a CPU
+// counterpart; the MODEL-level parity runs build the oracle graph from the unfused nodes.
+// Backward = the reference's backward of those nodes: bdot (node_operators_binary.h:221-369),
+// SoftmaxGrad (tensor_operators.cu:404-462: grad += val * (adj - sum(adj * val))).
+// ---------------------------------------------------------------------------
+namespace {
+struct AttnDims {
+  int B, H, Tq, Tk, dk, d, maskRows;
+};
+AttnDims attnDims(Tensor q, Tensor k, Tensor mask, int heads) {
+  AttnDims g;
+  g.d = q->shape()[-1];
+  g.H = heads;
+  g.dk = g.d / heads;
+  g.Tq = q->shape()[-2];
+  g.Tk = k->shape()[-2];
+  g.B = (int)(q->shape().elements() / ((size_t)g.Tq * g.d));
+  g.maskRows = 1;
+  if(mask && (size_t)mask->shape().elements() == (size_t)g.B * g.Tq * g.Tk)
+    g.maskRows = g.Tq;
+  return g;
+}
+}  // namespace
+
+bool AttentionFusable(int, int, int dimModel, int heads) {
+  return heads > 0 && dimModel % heads == 0;
+}
+
+void MultiHeadAttention(Tensor out, Tensor probs, const Tensor q, const Tensor k, const Tensor v, const Tensor mask, int heads, float scale) {
+  AttnDims g = attnDims(q, k, mask, heads);
+  const float* Q = q->data();
+  const float* K = k->data();
+  const float* V = v->data();
+  const float* M = mask ? mask->data() : nullptr;
+  float* O = out->data();
+  float* P = probs ? probs->data() : nullptr;
+#pragma omp parallel for collapse(2)
+  for(int b = 0; b < g.B; ++b)
+    for(int h = 0; h < g.H; ++h) {
+      std::vector<float> row(g.Tk);
+      for(int i = 0; i < g.Tq; ++i) {
+        const float* qi = Q + ((size_t)b * g.Tq + i) * g.d + h * g.dk;
+        float mx = -3.0e38f;
+        for(int j = 0; j < g.Tk; ++j) {
+          const float* kj = K + ((size_t)b * g.Tk + j) * g.d + h * g.dk;
+          double acc = 0;
+          for(int c = 0; c < g.dk; ++c)
+            acc += (double)qi[c] * kj[c];
+          float s = (float)acc * scale;
+          if(M)
+            s += M[((size_t)b * g.maskRows + (g.maskRows > 1 ? i : 0)) * g.Tk + j];
+          row[j] = s;
+          mx = std::max(mx, s);
+        }
+        double sum = 0;
+        for(int j = 0; j < g.Tk; ++j) {
+          row[j] = expf(row[j] - mx);
+          sum += row[j];
+        }
+        for(int j = 0; j < g.Tk; ++j) {
+          row[j] = (float)(row[j] / sum);
+          if(P)
+            P[(((size_t)b * g.H + h) * g.Tq + i) * g.Tk + j] = row[j];
+        }
+        float* oi = O + ((size_t)b * g.Tq + i) * g.d + h * g.dk;
+        for(int c = 0; c < g.dk; ++c) {
+          double acc = 0;
+          for(int j = 0; j < g.Tk; ++j)
+            acc += (double)row[j] * V[((size_t)b * g.Tk + j) * g.d + h * g.dk + c];
+          oi[c] = (float)acc;
+        }
+      }
+    }
+}
+
+void MultiHeadAttentionGrad(Tensor dq, Tensor dk, Tensor dv, const Tensor adj, const Tensor, const Tensor probs, const Tensor q, const Tensor k, const Tensor v, int heads, float scale) {
+  AttnDims g = attnDims(q, k, nullptr, heads);
+  const float* Q = q->data();
+  const float* K = k->data();
+  const float* V = v->data();
+  const float* P = probs->data();
+  const float* dO = adj->data();
+  float* dQ = dq->data();
+  float* dK = dk->data();
+  float* dV = dv->data();
+#pragma omp parallel for collapse(2)
+  for(int b = 0; b < g.B; ++b)
+    for(int h = 0; h < g.H; ++h) {
+      std::vector<double> dS((size_t)g.Tq * g.Tk);
+      for(int i = 0; i < g.Tq; ++i) {
+        const float* pi = P + (((size_t)b * g.H + h) * g.Tq + i) * g.Tk;
+        const float* doi = dO + ((size_t)b * g.Tq + i) * g.d + h * g.dk;
+        std::vector<double> dP(g.Tk);
+        double dot = 0;
+        for(int j = 0; j < g.Tk; ++j) {
+          const float* vj = V + ((size_t)b * g.Tk + j) * g.d + h * g.dk;
+          double acc = 0;
+          for(int c = 0; c < g.dk; ++c)
+            acc += (double)doi[c] * vj[c];
+          dP[j] = acc;            // d weights = dO V^T
+          dot += acc * pi[j];
+        }
+        for(int j = 0; j < g.Tk; ++j)
+          dS[(size_t)i * g.Tk + j] = pi[j] * (dP[j] - dot);   // softmax backward
+      }
+      for(int j = 0; j < g.Tk; ++j)
+        for(int c = 0; c < g.dk; ++c) {
+          double accV = 0, accK = 0;
+          for(int i = 0; i < g.Tq; ++i) {
+            accV += (double)P[(((size_t)b * g.H + h) * g.Tq + i) * g.Tk + j] * dO[((size_t)b * g.Tq + i) * g.d + h * g.dk + c];
+            accK += dS[(size_t)i * g.Tk + j] * Q[((size_t)b * g.Tq + i) * g.d + h * g.dk + c];
+          }
+          size_t o = ((size_t)b * g.Tk + j) * g.d + h * g.dk + c;
+          dV[o] += (float)accV;
+          dK[o] += (float)(accK * scale);
+        }
+      for(int i = 0; i < g.Tq; ++i)
+        for(int c = 0; c < g.dk; ++c) {
+          double acc = 0;
+          for(int j = 0; j < g.Tk; ++j)
+            acc += dS[(size_t)i * g.Tk + j] * K[((size_t)b * g.Tk + j) * g.d + h * g.dk + c];
+          dQ[((size_t)b * g.Tq + i) * g.d + h * g.dk + c] += (float)(acc * scale);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Layer normalisation       reference: :1447-1674
 // ---------------------------------------------------------------------------
 void LayerNormalization(Tensor out, Tensor in, Tensor gamma, Tensor beta, float eps) {

@@ -180,7 +180,8 @@ def test_cross_entropy(cuda, oracle, rows, cols):
 
 
 # ---------------------------------------------------------------- layer norm
-@pytest.mark.parametrize("rows,cols,eps,with_beta", [(64, 512, 1e-6, True), (33, 1024, 1e-9, True), (7, 3072, 1e-9, False), (5, 10, 1e-5, True)])
+@pytest.mark.parametrize("rows,cols,eps,with_beta", [(64, 512, 1e-6, True), (33, 1024, 1e-9, True), (7, 3072, 1e-9, False), (5, 10, 1e-5, True),
+                                                     (3200, 512, 1e-6, True), (130, 260, 1e-6, False), (50, 768, 1e-6, True)])
 def test_layer_norm(cuda, oracle, rows, cols, eps, with_beta):
     def fn(lib):
         x = lib.array(rnd(1, rows, cols))
@@ -200,6 +201,80 @@ def test_layer_norm(cuda, oracle, rows, cols, eps, with_beta):
         return r
 
     compare(cuda, oracle, fn, rtol=5e-5)
+
+
+# ---------------------------------------------------------------- fused multi-head attention
+def _attention_numpy(q, k, v, mask, heads, scale):
+    """float64 statement of Transformer::MultiHead's core (split heads, scaled scores + additive
+    mask, softmax over keys, weighted values, join heads) and its gradient via the closed form."""
+    B, Tq, d = q.shape
+    Tk = k.shape[1]
+    dk = d // heads
+    qh = q.reshape(B, Tq, heads, dk).transpose(0, 2, 1, 3).astype(np.float64)
+    kh = k.reshape(B, Tk, heads, dk).transpose(0, 2, 1, 3).astype(np.float64)
+    vh = v.reshape(B, Tk, heads, dk).transpose(0, 2, 1, 3).astype(np.float64)
+    s = scale * qh @ kh.transpose(0, 1, 3, 2)
+    if mask is not None:
+        s = s + mask.reshape(B, 1, -1, Tk)
+    s = s - s.max(-1, keepdims=True)
+    p = np.exp(s)
+    p /= p.sum(-1, keepdims=True)
+    o = (p @ vh).transpose(0, 2, 1, 3).reshape(B, Tq, d)
+    return o, p, (qh, kh, vh)
+
+
+@pytest.mark.parametrize("B,H,Tq,Tk,dk,mask_kind", [
+    (64, 8, 50, 50, 64, "key"),       # config B encoder self-attention
+    (64, 8, 50, 50, 64, "causal"),    # config B decoder self-attention
+    (5, 4, 13, 29, 16, "key"),        # cross attention, ragged
+    (3, 2, 33, 7, 32, "none"),
+    (2, 16, 80, 80, 64, "causal"),    # config E head shape
+    (2, 3, 128, 128, 64, "key"),      # largest supported sequence
+])
+def test_multi_head_attention(cuda, oracle, B, H, Tq, Tk, dk, mask_kind):
+    d = H * dk
+    q, k, v = rnd(1, B, Tq, d), rnd(2, B, Tk, d), rnd(3, B, Tk, d)
+    adj = rnd(4, B, Tq, d)
+    scale = 1.0 / np.sqrt(dk)
+    rs = np.random.RandomState(5)
+    if mask_kind == "key":
+        keep = (rs.rand(B, 1, 1, Tk) > 0.3).astype(np.float32)
+        keep[..., 0] = 1
+    elif mask_kind == "causal":
+        assert Tq == Tk
+        keep = np.tril(np.ones((Tq, Tk), dtype=np.float32))[None, None] * (rs.rand(B, 1, 1, Tk) > 0.2)
+        keep[..., 0] = 1
+        keep = np.ascontiguousarray(np.broadcast_to(keep, (B, 1, Tq, Tk))).astype(np.float32)
+    else:
+        keep = None
+    mask = None if keep is None else ((1 - keep) * -99999999.0).astype(np.float32)
+
+    def fn(lib):
+        out, probs = lib.zeros((B, Tq, d)), lib.zeros((B, H, Tq, Tk))
+        qa, ka, va = lib.array(q), lib.array(k), lib.array(v)
+        mt = lib.array(mask).t() if mask is not None else None
+        lib.call("mrn_multi_head_attention", out.t(), probs.t(), qa.t(), ka.t(), va.t(), mt, H, scale)
+        dq, dk_, dv = lib.array(rnd(6, B, Tq, d)), lib.array(rnd(7, B, Tk, d)), lib.array(rnd(8, B, Tk, d))
+        lib.call("mrn_multi_head_attention_grad", dq.t(), dk_.t(), dv.t(), lib.array(adj).t(), out.t(), probs.t(), qa.t(), ka.t(), va.t(), H, scale)
+        return {"out": out.numpy(), "probs": probs.numpy(), "dq": dq.numpy(), "dk": dk_.numpy(), "dv": dv.numpy()}
+
+    got, exp = both(cuda, oracle, fn)
+    for key in exp:
+        close(got[key], exp[key], 3e-5, key)
+    # independent float64 statement
+    o, p, (qh, kh, vh) = _attention_numpy(q, k, v, mask, H, scale)
+    close(got["out"], o, 3e-5, "out vs numpy")
+    close(got["probs"], p, 3e-5, "probs vs numpy")
+    do = adj.reshape(B, Tq, H, dk).transpose(0, 2, 1, 3).astype(np.float64)
+    dv = p.transpose(0, 1, 3, 2) @ do
+    dp = do @ vh.transpose(0, 1, 3, 2)
+    ds = p * (dp - (dp * p).sum(-1, keepdims=True))
+    dq = scale * ds @ kh
+    dk_ = scale * ds.transpose(0, 1, 3, 2) @ qh
+    join = lambda x, T: x.transpose(0, 2, 1, 3).reshape(B, T, d)  # noqa: E731
+    close(got["dq"], join(dq, Tq) + rnd(6, B, Tq, d), 3e-5, "dq vs numpy")
+    close(got["dk"], join(dk_, Tk) + rnd(7, B, Tk, d), 3e-5, "dk vs numpy")
+    close(got["dv"], join(dv, Tk) + rnd(8, B, Tk, d), 3e-5, "dv vs numpy")
 
 
 def test_layer_norm_reference_golden_input(cuda, oracle, goldens):
