@@ -317,34 +317,35 @@ def main():
 
 
 def gemm_profile(lib, pkg, gemm_mode, device):
-    """Times every tensor-core GEMM launch of eager steps with CUDA events recorded on the
-    engine stream around the launch (MRN_GEMM_PROFILE, see csrc/kernels/gemm.cu)."""
+    """In-graph duration of every tensor-core GEMM launch of ONE replayed step: CUDA events are
+    recorded on the engine stream around each launch while the step is captured (external
+    event-record nodes, csrc/kernels/gemm.cu ProfileScope) and re-stamped by every replay.  This
+    is a separate trainer: the event nodes perturb the step a little, so `value` is not taken here."""
     import ctypes
 
-    if not hasattr(lib.c, "mrn_gemm_profile"):
-        return None
     fn = lib.c.mrn_gemm_profile
     fn.argtypes = [ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_size_t)]
     fn.restype = ctypes.c_int
-    t = lib.trainer(dict(pkg.transformer_base_options(gemm_mode=gemm_mode), **{"graph-replay": "false"}), device=device)
-    for _ in range(2):
+    t = lib.trainer(pkg.transformer_base_options(gemm_mode=gemm_mode), device=device)
+
+    def step():
         t.next_synthetic_batch(BATCH, LEN, LEN)
         t.compute_gradients()
         t.update()
         t.cost()
+
+    step()  # eager: parameters, arenas
     ms, flops, n = ctypes.c_double(), ctypes.c_double(), ctypes.c_size_t()
     fn(1, ctypes.byref(ms), ctypes.byref(flops), ctypes.byref(n))  # enable + reset
-    steps = 3
-    for _ in range(steps):
-        t.next_synthetic_batch(BATCH, LEN, LEN)
-        t.compute_gradients()
-        t.update()
-        t.cost()
-    fn(0, ctypes.byref(ms), ctypes.byref(flops), ctypes.byref(n))  # disable + read
+    step()  # this shape's second appearance: captured with the event nodes, then launched
+    for _ in range(4):
+        step()  # replays re-stamp the events
+    stats = t.stats()
+    fn(0, ctypes.byref(ms), ctypes.byref(flops), ctypes.byref(n))  # disable + read the last replay
     t.close()
-    if n.value == 0 or ms.value <= 0:
+    if n.value == 0 or ms.value <= 0 or stats["plans"] < 1:
         return None
-    return {"tflops": flops.value / (ms.value / 1000.0) / 1e12, "ms": ms.value / steps, "gflop": flops.value / steps / 1e9, "launches": n.value // steps}
+    return {"tflops": flops.value / (ms.value / 1000.0) / 1e12, "ms": ms.value, "gflop": flops.value / 1e9, "launches": n.value}
 
 
 if __name__ == "__main__":

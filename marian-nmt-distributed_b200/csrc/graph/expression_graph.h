@@ -247,6 +247,10 @@ public:
     params_->allocateBackward();
     params_->set_zero_adjoint();
 
+    // Weight/bias gradients are issued on the side stream (Node::offCriticalPath) and may still
+    // be reading a node's adjoint after the node is gone: frees are parked until the join.
+    tensors_->allocator()->deferFrees(true);
+
     for(auto&& v : topNodes_)
       v->init_dependent();
 
@@ -266,6 +270,9 @@ public:
 
       v->children().clear();
     }
+    device::joinSide();
+    tensors_->allocator()->deferFrees(false);
+    tensors_->allocator()->flushDeferred();
   }
 
   template <typename... Args>

@@ -9,6 +9,7 @@
 #pragma once
 
 #include <algorithm>
+#include <cstdlib>
 #include <functional>
 #include <string>
 #include <vector>
@@ -147,6 +148,19 @@ public:
   virtual Expr child(size_t i) { return children_[i]; }
 
   Ptr<Backend> getBackend();
+
+  // Runs f on the side stream when it only produces the gradient of PARAMETER `target`:
+  // nothing downstream in the backward sweep reads it (device.h: forkSide/joinSide).
+  template <class F>
+  void offCriticalPath(Expr target, F f) {
+    static const bool enabled = std::getenv("MRN_NO_SIDE_STREAM") == nullptr;
+    bool side = enabled && target->type() == "param";
+    if(side)
+      device::forkSide();
+    f();
+    if(side)
+      device::returnFromSide();
+  }
 };
 
 struct NaryNodeOp : public Node {

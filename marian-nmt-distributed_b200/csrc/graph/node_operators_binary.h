@@ -40,6 +40,10 @@ protected:
   virtual void prod(Tensor C, Tensor A, Tensor B, bool tA, bool tB, float beta) {
     Prod(getBackend()->getGemmHandle(), C, A, B, tA, tB, beta, scalar_);
   }
+  // gradient of child i: weight gradients leave the critical path
+  void prodGrad(int i, Tensor A, Tensor B, bool tA, bool tB) {
+    offCriticalPath(child(i), [&] { prod(child(i)->grad(), A, B, tA, tB, 1.f); });
+  }
 
 public:
   DotNodeOp(Expr a, Expr b, bool transA, bool transB, float scalar)
@@ -49,18 +53,14 @@ public:
 
   NodeOps backwardOps() {
     // D = adj, A = child0, B = child1
-    if(!transA_ && transB_)   // C = A B^T : dA += D B ; dB += D^T A
-      return {NodeOp(prod(child(0)->grad(), adj_, child(1)->val(), false, false, 1.f)),
-              NodeOp(prod(child(1)->grad(), adj_, child(0)->val(), true, false, 1.f))};
-    if(transA_ && !transB_)   // C = A^T B : dA += B D^T ; dB += A D
-      return {NodeOp(prod(child(0)->grad(), child(1)->val(), adj_, false, true, 1.f)),
-              NodeOp(prod(child(1)->grad(), child(0)->val(), adj_, false, false, 1.f))};
-    if(transA_ && transB_)    // C = A^T B^T : dA += B^T D^T ; dB += D^T A^T
-      return {NodeOp(prod(child(0)->grad(), child(1)->val(), adj_, true, true, 1.f)),
-              NodeOp(prod(child(1)->grad(), adj_, child(0)->val(), true, true, 1.f))};
+    if(!transA_ && transB_)  // C = A B^T : dA += D B ; dB += D^T A
+      return {NodeOp(prodGrad(0, adj_, child(1)->val(), false, false)), NodeOp(prodGrad(1, adj_, child(0)->val(), true, false))};
+    if(transA_ && !transB_)  // C = A^T B : dA += B D^T ; dB += A D
+      return {NodeOp(prodGrad(0, child(1)->val(), adj_, false, true)), NodeOp(prodGrad(1, child(0)->val(), adj_, false, false))};
+    if(transA_ && transB_)  // C = A^T B^T : dA += B^T D^T ; dB += D^T A^T
+      return {NodeOp(prodGrad(0, child(1)->val(), adj_, true, true)), NodeOp(prodGrad(1, adj_, child(0)->val(), true, true))};
     // C = A B : dA += D B^T ; dB += A^T D
-    return {NodeOp(prod(child(0)->grad(), adj_, child(1)->val(), false, true, 1.f)),
-            NodeOp(prod(child(1)->grad(), child(0)->val(), adj_, true, false, 1.f))};
+    return {NodeOp(prodGrad(0, adj_, child(1)->val(), false, true)), NodeOp(prodGrad(1, child(0)->val(), adj_, true, false))};
   }
 
   virtual size_t hash() {
@@ -113,9 +113,10 @@ struct AffineNodeOp : public NaryNodeOp {
   }
   NodeOps backwardOps() {
     using namespace functional;
-    return {NodeOp(Prod(getBackend()->getGemmHandle(), child(0)->grad(), adj_, child(1)->val(), false, true, 1.0)),
-            NodeOp(Prod(getBackend()->getGemmHandle(), child(1)->grad(), child(0)->val(), adj_, true, false, 1.0)),
-            NodeOp(Add(_1, child(2)->grad(), adj_))};
+    // dW and db hang off the backward chain: side stream when W / b are parameters
+    return {NodeOp(offCriticalPath(child(0), [&] { Prod(getBackend()->getGemmHandle(), child(0)->grad(), adj_, child(1)->val(), false, true, 1.0); })),
+            NodeOp(offCriticalPath(child(1), [&] { Prod(getBackend()->getGemmHandle(), child(1)->grad(), child(0)->val(), adj_, true, false, 1.0); })),
+            NodeOp(offCriticalPath(child(2), [&] { Add(_1, child(2)->grad(), adj_); }))};
   }
   const std::string type() { return "affine"; }
 };

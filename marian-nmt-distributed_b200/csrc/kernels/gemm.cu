@@ -39,6 +39,9 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
 #include <unordered_map>
 
 #include "kernels/cuda_helpers.h"
@@ -137,11 +140,14 @@ struct GemmProfile {
   bool enabled{false};
   double flops{0};
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
+  std::vector<std::string> labels;  // one per event pair: "M,N,K,batches,layout,splits"
 };
 GemmProfile g_profile;
 }  // namespace
 
-// enable != 0: reset and start recording; enable == 0: stop, synchronise and report
+// enable != 0: reset and start recording; enable == 0: stop, synchronise and report.
+// Event pairs recorded while a step was being CAPTURED are re-stamped by every replay of that
+// graph: the report then covers the last replay (one step), measured inside the graph.
 void gemmProfile(int enable, double* ms, double* flops, size_t* launches) {
   if(enable) {
     for(auto& e : g_profile.events) {
@@ -149,6 +155,7 @@ void gemmProfile(int enable, double* ms, double* flops, size_t* launches) {
       cudaEventDestroy(e.second);
     }
     g_profile.events.clear();
+    g_profile.labels.clear();
     g_profile.flops = 0;
     g_profile.enabled = true;
     *ms = 0;
@@ -159,17 +166,56 @@ void gemmProfile(int enable, double* ms, double* flops, size_t* launches) {
   g_profile.enabled = false;
   device::synchronize();
   double total = 0;
-  for(auto& e : g_profile.events) {
+  // MRN_GEMM_PROFILE_DUMP=<file>: one CSV line per launch (shape, layout, in-graph microseconds)
+  FILE* dump = nullptr;
+  if(const char* path = std::getenv("MRN_GEMM_PROFILE_DUMP"))
+    dump = fopen(path, "w");
+  for(size_t i = 0; i < g_profile.events.size(); ++i) {
+    auto& e = g_profile.events[i];
     float t = 0;
     if(cudaEventElapsedTime(&t, e.first, e.second) == cudaSuccess)
       total += t;
+    if(dump)
+      fprintf(dump, "%s,%.2f\n", i < g_profile.labels.size() ? g_profile.labels[i].c_str() : "?", t * 1000.f);
   }
+  if(dump)
+    fclose(dump);
   *ms = total;
   *flops = g_profile.flops;
   *launches = g_profile.events.size();
 }
 
 namespace {
+
+// Event pair around one tensor-core launch.  Eagerly these are plain records; while the step is
+// being captured into a CUDA graph they become EXTERNAL event-record nodes, so every replay of
+// the graph re-stamps them and the host can read the in-graph duration of each launch.
+struct ProfileScope {
+  cudaEvent_t e0{nullptr}, e1{nullptr};
+  bool on{false};
+  explicit ProfileScope(double flops) {
+    on = g_profile.enabled;
+    if(!on)
+      return;
+    CUDA_CHECK(cudaEventCreate(&e0));
+    CUDA_CHECK(cudaEventCreate(&e1));
+    record(e0);
+    g_profile.flops += flops;
+  }
+  void finish(const std::string& label = std::string()) {
+    if(!on)
+      return;
+    record(e1);
+    g_profile.events.push_back({e0, e1});
+    g_profile.labels.push_back(label);
+  }
+  static void record(cudaEvent_t e) {
+    if(device::capturing())
+      CUDA_CHECK(cudaEventRecordWithFlags(e, cudaStreamOfEngine(), cudaEventRecordExternal));
+    else
+      CUDA_CHECK(cudaEventRecord(e, cudaStreamOfEngine()));
+  }
+};
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 64;  // 64 bf16 = 128 bytes = one swizzle row
@@ -506,7 +552,7 @@ struct TcArgs {
 };
 
 template <int BN>
-__device__ __forceinline__ void epilogueTile(const TcArgs& a, uint32_t tmemBase, float* stage, int warp, int lane, int m0, int n0, int batch, int split);
+__device__ __forceinline__ void epilogueTile(const TcArgs& a, uint32_t tmemBase, uint64_t* tmemFullBar, float* stage, int warp, int lane, int m0, int n0, int batch, int split);
 
 template <int BN, int STAGES>
 struct TcSmem {
@@ -599,10 +645,8 @@ __global__ void __launch_bounds__(192) gGemmTcgen05(const __grid_constant__ CUte
     }
   } else {
     // ---------------- epilogue: TMEM -> registers -> smem staging -> global ----------------
-    mbarWait(tmemFullBar, 0);
-    tcgenFenceAfter();
     float* stage = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * kStagePitch);
-    epilogueTile<BN>(a, tmemBase, stage, warp, lane, m0, n0, batch, split);
+    epilogueTile<BN>(a, tmemBase, tmemFullBar, stage, warp, lane, m0, n0, batch, split);
   }
 
   tcgenFenceBefore();
@@ -687,15 +731,37 @@ struct TfSmem {
 
 // Shared epilogue of both tensor-core kernels: TMEM -> registers -> smem staging -> global
 // with alpha / beta / bias; `stage` is this warp's 32 x kStagePitch float scratch.
+// beta != 0 (gradient accumulation): the old C values of a 32-column block are requested BEFORE
+// the accumulator is waited for / read back, so their latency hides behind the main loop's tail
+// and the TMEM read of the previous block.
 template <int BN>
-__device__ __forceinline__ void epilogueTile(const TcArgs& a, uint32_t tmemBase, float* stage, int warp, int lane, int m0, int n0, int batch, int split) {
+__device__ __forceinline__ void epilogueTile(const TcArgs& a, uint32_t tmemBase, uint64_t* tmemFullBar, float* stage, int warp, int lane, int m0, int n0, int batch, int split) {
   const int q = warp & 3;  // TMEM lane quarter this warp may access
   float* Cb = a.C + (size_t)batch * a.strideC;
   const bool addBias = a.bias != nullptr && split == 0;
+  const int rowBase = m0 + q * 32;
+  const int sub = lane >> 3;      // row within a group of 4
+  const int cq = (lane & 7) * 4;  // first of this lane's 4 columns
+  const bool readOld = a.beta != 0.f && !a.atomicOut;
+
+  auto isVec = [&](int col0) { return col0 + 32 <= a.N && ((a.ldc & 3) == 0) && ((((uintptr_t)(Cb + col0)) & 15) == 0); };
+  float4 oldv[8];
+  auto prefetchOld = [&](int col0) {
+    if(!readOld || col0 >= a.N || rowBase >= a.M || !isVec(col0))
+      return;
+#pragma unroll
+    for(int i = 0; i < 8; ++i) {
+      int grow = rowBase + i * 4 + sub;
+      oldv[i] = grow < a.M ? *reinterpret_cast<const float4*>(Cb + (size_t)grow * a.ldc + col0 + cq) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+
+  prefetchOld(n0);
+  mbarWait(tmemFullBar, 0);
+  tcgenFenceAfter();
 #pragma unroll 1
   for(int c0 = 0; c0 < BN; c0 += 32) {
     const int col0 = n0 + c0;
-    const int rowBase = m0 + q * 32;
     if(col0 >= a.N || rowBase >= a.M)
       break;
     uint32_t r[32];
@@ -718,55 +784,59 @@ __device__ __forceinline__ void epilogueTile(const TcArgs& a, uint32_t tmemBase,
     }
     __syncwarp();
     const int ncols = min(32, a.N - col0);
-    const bool vec = ncols == 32 && ((a.ldc & 3) == 0) && ((((uintptr_t)(Cb + col0)) & 15) == 0);
-    if(vec) {
-      const int sub = lane >> 3;      // row within a group of 4
-      const int cq = (lane & 7) * 4;  // first of this lane's 4 columns
+    if(isVec(col0)) {
       float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
       if(addBias)
         bq = *reinterpret_cast<const float4*>(a.bias + col0 + cq);
+      float4 outv[8];
 #pragma unroll
-      for(int rr = 0; rr < 32; rr += 4) {
-        int rloc = rr + sub;
-        int grow = rowBase + rloc;
+      for(int i = 0; i < 8; ++i) {
+        float4 acc = *reinterpret_cast<const float4*>(stage + (i * 4 + sub) * kStagePitch + cq);
+        float4 v;
+        v.x = a.alpha * acc.x + bq.x;
+        v.y = a.alpha * acc.y + bq.y;
+        v.z = a.alpha * acc.z + bq.z;
+        v.w = a.alpha * acc.w + bq.w;
+        if(readOld) {
+          v.x += a.beta * oldv[i].x;
+          v.y += a.beta * oldv[i].y;
+          v.z += a.beta * oldv[i].z;
+          v.w += a.beta * oldv[i].w;
+        }
+        outv[i] = v;
+      }
+      prefetchOld(col0 + 32);  // next block's old values travel while this one is stored
+#pragma unroll
+      for(int i = 0; i < 8; ++i) {
+        int grow = rowBase + i * 4 + sub;
         if(grow < a.M) {
-          float4 acc = *reinterpret_cast<const float4*>(stage + rloc * kStagePitch + cq);
           float* cp = Cb + (size_t)grow * a.ldc + col0 + cq;
-          float4 v;
-          v.x = a.alpha * acc.x + bq.x;
-          v.y = a.alpha * acc.y + bq.y;
-          v.z = a.alpha * acc.z + bq.z;
-          v.w = a.alpha * acc.w + bq.w;
           if(a.atomicOut) {
             // split-K partial sums: vector reduction straight into L2 (sm_90+)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp), "f"(outv[i].x), "f"(outv[i].y), "f"(outv[i].z), "f"(outv[i].w) : "memory");
           } else {
-            if(a.beta != 0.f) {
-              float4 old = *reinterpret_cast<const float4*>(cp);
-              v.x += a.beta * old.x;
-              v.y += a.beta * old.y;
-              v.z += a.beta * old.z;
-              v.w += a.beta * old.w;
-            }
-            *reinterpret_cast<float4*>(cp) = v;
+            *reinterpret_cast<float4*>(cp) = outv[i];
           }
         }
       }
-    } else if(lane < ncols) {
-      // general path: lane = column, rows walked one by one (still contiguous per row)
-      float bv = addBias ? a.bias[col0 + lane] : 0.f;
-      int rmax = min(32, a.M - rowBase);
-      for(int rloc = 0; rloc < rmax; ++rloc) {
-        float v = a.alpha * stage[rloc * kStagePitch + lane] + bv;
-        float* cp = Cb + (size_t)(rowBase + rloc) * a.ldc + col0 + lane;
-        if(a.atomicOut) {
-          atomicAdd(cp, v);
-        } else {
-          if(a.beta != 0.f)
-            v += a.beta * *cp;
-          *cp = v;
+    } else {
+      if(lane < ncols) {
+        // general path: lane = column, rows walked one by one (still contiguous per row)
+        float bv = addBias ? a.bias[col0 + lane] : 0.f;
+        int rmax = min(32, a.M - rowBase);
+        for(int rloc = 0; rloc < rmax; ++rloc) {
+          float v = a.alpha * stage[rloc * kStagePitch + lane] + bv;
+          float* cp = Cb + (size_t)(rowBase + rloc) * a.ldc + col0 + lane;
+          if(a.atomicOut) {
+            atomicAdd(cp, v);
+          } else {
+            if(a.beta != 0.f)
+              v += a.beta * *cp;
+            *cp = v;
+          }
         }
       }
+      prefetchOld(col0 + 32);
     }
     __syncwarp();  // staging buffer is reused by the next 32-column block
   }
@@ -863,10 +933,8 @@ __global__ void __launch_bounds__(192) gGemmTf32(const __grid_constant__ CUtenso
       ummaCommit(tmemFullBar);
     }
   } else {
-    mbarWait(tmemFullBar, 0);
-    tcgenFenceAfter();
     float* stage = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * kStagePitch);
-    epilogueTile<BN>(a, tmemBase, stage, warp, lane, m0, n0, batch, split);
+    epilogueTile<BN>(a, tmemBase, tmemFullBar, stage, warp, lane, m0, n0, batch, split);
   }
 
   tcgenFenceBefore();
@@ -950,6 +1018,10 @@ void runTensorCore(GemmHandle h, const GemmProblem& p) {
   bool batched = p.batches > 1;
 
   // tile shape: fill the machine if 128-wide tiles cannot
+  // The config-B products are LATENCY bound (one wave of CTAs, each a serial chain prologue ->
+  // first TMA round trip -> 16 k-blocks -> epilogue; measured in-graph: 128x128 tiles 19.8 us vs
+  // 128x64 tiles 16 us for 3200x512x512): prefer more, narrower CTAs until the wide tiles
+  // alone fill the machine.
   long tiles128 = (long)((M + BLOCK_M - 1) / BLOCK_M) * ((N + 127) / 128) * p.batches;
   int BN = (tiles128 >= kNumSMs && N > 64) ? 128 : 64;
 
@@ -997,22 +1069,12 @@ void runTensorCore(GemmHandle h, const GemmProblem& p) {
       Element(_1 = p.beta * _1, p.C);
   }
 
-  bool profile = g_profile.enabled && !device::capturing();
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if(profile) {
-    CUDA_CHECK(cudaEventCreate(&e0));
-    CUDA_CHECK(cudaEventCreate(&e1));
-    CUDA_CHECK(cudaEventRecord(e0, cudaStreamOfEngine()));
-  }
+  ProfileScope prof(2.0 * M * N * K * p.batches);  // algorithmic flops (not the 3x of the split mode)
   if(BN == 128)
     launchTc<128, 3>(tmA, tmB, a, p.batches);
   else
     launchTc<64, 4>(tmA, tmB, a, p.batches);
-  if(profile) {
-    CUDA_CHECK(cudaEventRecord(e1, cudaStreamOfEngine()));
-    g_profile.events.push_back({e0, e1});
-    g_profile.flops += 2.0 * M * N * K * p.batches;  // algorithmic flops (not the 3x of the split mode)
-  }
+  prof.finish();
 }
 
 
@@ -1076,6 +1138,10 @@ bool runTf32(GemmHandle h, const GemmProblem& p) {
   const bool aMN = p.transA;   // stored [K, M]: M contiguous
   const bool bMN = !p.transB;  // stored [K, N]: N contiguous
 
+  // The config-B products are LATENCY bound (one wave of CTAs, each a serial chain prologue ->
+  // first TMA round trip -> 16 k-blocks -> epilogue; measured in-graph: 128x128 tiles 19.8 us vs
+  // 128x64 tiles 16 us for 3200x512x512): prefer more, narrower CTAs until the wide tiles
+  // alone fill the machine.
   long tiles128 = (long)((M + BLOCK_M - 1) / BLOCK_M) * ((N + 127) / 128) * p.batches;
   int BN = (tiles128 >= kNumSMs && N > 64) ? 128 : 64;
 
@@ -1097,9 +1163,11 @@ bool runTf32(GemmHandle h, const GemmProblem& p) {
   a.alpha = p.alpha;
   a.beta = p.beta;
 
+  // split-K: fewer tiles than SMs and a long reduction -> slices of >= 8 k-blocks (256 elements)
+  // up to about two CTAs per SM; partial sums meet in L2 through red.add
   long tiles = (long)((M + BLOCK_M - 1) / BLOCK_M) * ((N + BN - 1) / BN) * p.batches;
   int splits = 1;
-  if(!batched && tiles * 2 <= kNumSMs && a.kBlocks >= 16) {
+  if(!batched && tiles <= kNumSMs && a.kBlocks >= 32) {
     splits = (int)std::min<long>((kNumSMs * 2 + tiles - 1) / tiles, a.kBlocks / 8);
     splits = std::max(1, std::min(splits, 32));
   }
@@ -1115,13 +1183,7 @@ bool runTf32(GemmHandle h, const GemmProblem& p) {
       Element(_1 = p.beta * _1, p.C);
   }
 
-  bool profile = g_profile.enabled && !device::capturing();
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if(profile) {
-    CUDA_CHECK(cudaEventCreate(&e0));
-    CUDA_CHECK(cudaEventCreate(&e1));
-    CUDA_CHECK(cudaEventRecord(e0, cudaStreamOfEngine()));
-  }
+  ProfileScope prof(2.0 * M * N * K * p.batches);
   if(aMN && bMN)
     launchTf32Tile<true, true>(BN, tmA, tmB, a, p.batches);
   else if(aMN)
@@ -1130,11 +1192,9 @@ bool runTf32(GemmHandle h, const GemmProblem& p) {
     launchTf32Tile<false, true>(BN, tmA, tmB, a, p.batches);
   else
     launchTf32Tile<false, false>(BN, tmA, tmB, a, p.batches);
-  if(profile) {
-    CUDA_CHECK(cudaEventRecord(e1, cudaStreamOfEngine()));
-    g_profile.events.push_back({e0, e1});
-    g_profile.flops += 2.0 * M * N * K * p.batches;
-  }
+  if(prof.on)
+    prof.finish(std::to_string(M) + "," + std::to_string(N) + "," + std::to_string(K) + "," + std::to_string(p.batches) + "," + (aMN ? "T" : "N") + (bMN ? "N" : "T") + ","
+                + std::to_string(BN) + "," + std::to_string(splits) + "," + std::to_string(p.beta));
   return true;
 }
 

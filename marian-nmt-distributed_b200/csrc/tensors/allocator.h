@@ -17,6 +17,7 @@
 #include <map>
 #include <set>
 #include <unordered_map>
+#include <vector>
 
 #include "common/definitions.h"
 #include "tensors/device.h"
@@ -90,9 +91,26 @@ public:
     return New<MemoryPiece>(gptr, bytes);
   }
 
+  // While side-stream work may still read freed tensors (see ExpressionGraph::backward) frees
+  // are parked; flushDeferred() performs them.
+  void deferFrees(bool on) { defer_ = on; }
+  void flushDeferred() {
+    std::vector<Ptr<MemoryPiece>> parked;
+    parked.swap(deferred_);
+    bool was = defer_;
+    defer_ = false;
+    for(auto& mp : parked)
+      free(mp);
+    defer_ = was;
+  }
+
   bool free(Ptr<MemoryPiece> mp) {
     if(!mp || !mp->data())
       return false;
+    if(defer_) {
+      deferred_.push_back(mp);
+      return true;
+    }
     auto it = allocated_.find(mp->data());
     if(it == allocated_.end())
       return false;
@@ -105,6 +123,7 @@ public:
   }
 
   void clear() {
+    deferred_.clear();
     bySize_.clear();
     byAddr_.clear();
     allocated_.clear();
@@ -201,6 +220,8 @@ private:
   size_t inUse_{0};
   size_t peak_{0};
   size_t generation_{0};
+  bool defer_{false};
+  std::vector<Ptr<MemoryPiece>> deferred_;
 };
 
 class TensorAllocator {

@@ -67,6 +67,17 @@ size_t lastCaptureKernelCount();
 void launchGraph(void* exec);
 void destroyGraph(void* exec);
 
+// ---- side stream: work off the critical path ---------------------------------
+// The backward sweep is a long dependency chain of small kernels; weight and bias gradients
+// hang off that chain (nothing reads them before the optimizer).  forkSide() routes the engine
+// work this thread issues next to a second stream, ordered after everything issued so far on
+// the main stream; returnFromSide() switches back (no ordering); joinSide() makes the main
+// stream wait for all side work.  Under capture the side stream joins the recording, so the
+// replayed graph has the same two branches.  No-ops on the CPU oracle.
+void forkSide();
+void returnFromSide();
+void joinSide();
+
 // "cuda" for the product, "cpu-oracle" for the test oracle.
 const char* backendName();
 

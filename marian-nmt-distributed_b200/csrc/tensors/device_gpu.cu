@@ -26,10 +26,33 @@ struct ThreadCtx {
   bool hasUser{false};
   bool capturing{false};
   size_t lastKernelCount{0};
+  // side stream (see device.h)
+  cudaStream_t side{nullptr};
+  bool onSide{false};
+  bool sideDirty{false};
+  std::vector<cudaEvent_t> events;  // fork/join markers, reused every step
+  size_t nextEvent{0};
 };
 thread_local ThreadCtx tctx;
 
+cudaStream_t mainStream();
+
 cudaStream_t stream() {
+  if(tctx.onSide)
+    return tctx.side;
+  return mainStream();
+}
+
+cudaEvent_t nextMarker() {
+  if(tctx.nextEvent == tctx.events.size()) {
+    cudaEvent_t e;
+    CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    tctx.events.push_back(e);
+  }
+  return tctx.events[tctx.nextEvent++];
+}
+
+cudaStream_t mainStream() {
   if(tctx.hasUser)
     return tctx.user;
   if(!tctx.own) {
@@ -53,7 +76,8 @@ void setDevice(int deviceId) {
     return;
   CUDA_CHECK(cudaSetDevice(deviceId));
   tctx.device = deviceId;
-  tctx.own = nullptr;  // stream is (re)created lazily for the new device
+  tctx.own = nullptr;  // streams are (re)created lazily for the new device
+  tctx.side = nullptr;
 }
 int getDevice() {
   return tctx.device < 0 ? 0 : tctx.device;
@@ -137,14 +161,14 @@ bool captureSupported() {
 }
 void beginCapture() {
   ABORT_IF(tctx.capturing, "nested capture");
-  CUDA_CHECK(cudaStreamBeginCapture(stream(), cudaStreamCaptureModeRelaxed));
+  CUDA_CHECK(cudaStreamBeginCapture(mainStream(), cudaStreamCaptureModeRelaxed));
   tctx.capturing = true;
 }
 void* endCapture() {
   ABORT_IF(!tctx.capturing, "endCapture without beginCapture");
   tctx.capturing = false;
   cudaGraph_t graph = nullptr;
-  cudaError_t rc = cudaStreamEndCapture(stream(), &graph);
+  cudaError_t rc = cudaStreamEndCapture(mainStream(), &graph);
   if(rc != cudaSuccess || !graph) {
     fprintf(stderr, "[marian_b200] graph capture failed: %s\n", cudaGetErrorString(rc));
     cudaGetLastError();
@@ -182,6 +206,32 @@ void launchGraph(void* exec) {
 void destroyGraph(void* exec) {
   if(exec)
     cudaGraphExecDestroy((cudaGraphExec_t)exec);
+}
+
+void forkSide() {
+  if(tctx.onSide)
+    return;
+  cudaStream_t main = mainStream();
+  if(!tctx.side)
+    CUDA_CHECK(cudaStreamCreateWithFlags(&tctx.side, cudaStreamNonBlocking));
+  cudaEvent_t e = nextMarker();
+  CUDA_CHECK(cudaEventRecord(e, main));
+  CUDA_CHECK(cudaStreamWaitEvent(tctx.side, e, 0));
+  tctx.onSide = true;
+  tctx.sideDirty = true;
+}
+void returnFromSide() {
+  tctx.onSide = false;
+}
+void joinSide() {
+  tctx.onSide = false;
+  if(tctx.sideDirty) {
+    cudaEvent_t e = nextMarker();
+    CUDA_CHECK(cudaEventRecord(e, tctx.side));
+    CUDA_CHECK(cudaStreamWaitEvent(mainStream(), e, 0));
+    tctx.sideDirty = false;
+  }
+  tctx.nextEvent = 0;
 }
 
 const char* backendName() {

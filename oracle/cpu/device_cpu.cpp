@@ -45,6 +45,9 @@ void fill(float* dst, float value, size_t n) {
     dst[i] = value;
 }
 void synchronize() {}
+void forkSide() {}
+void returnFromSide() {}
+void joinSide() {}
 bool capturing() { return false; }
 
 bool captureSupported() { return false; }
