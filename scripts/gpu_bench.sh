@@ -16,3 +16,7 @@ for k in $NCUFULL; do
   timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s ${NCUSKIP:-300} -c ${NCUCOUNT:-6} -o gpurun_out/prof_$k -f python scripts/profile_step.py 2 $MODE > gpurun_out/ncu_$k.log 2>&1; echo "ncu $k rc=$?"; tail -2 gpurun_out/ncu_$k.log
 done
 fi
+if [ -n "$NCUDRAM" ]; then
+# DRAM bytes + duration of every tensor-core GEMM launch of one eager step (roofline.traffic)
+timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:gGemm -c 2000 --csv --log-file gpurun_out/gemm_dram.csv python scripts/profile_step.py 2 $MODE > gpurun_out/ncu_dram.log 2>&1; echo "ncu dram rc=$?"
+fi

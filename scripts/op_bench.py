@@ -103,6 +103,21 @@ mine = timeit(lambda s: lib.call("mrn_softmax_grad", s[3].t(), s[2].t(), s[1].t(
 theirs = timeit(lambda s: ref.ref_softmax_grad(s[3].t(), s[2].t(), s[1].t()), pool, stream=LEGACY) if ref else None
 report("SoftmaxGrad 25600x50", 4 * n * 4, mine, theirs)
 
+# ---- fused multi-head attention (one encoder self-attention block of config B) ------
+Bq, Hh, Tt, dk = 64, 8, 50, 64
+def _attn_set():
+    return (lib.array(rnd(Bq, Tt, D)), lib.array(rnd(Bq, Tt, D)), lib.array(rnd(Bq, Tt, D)), lib.zeros((Bq, Tt, D)), lib.zeros((Bq, Hh, Tt, Tt)),
+            lib.array(rnd(Bq, Tt, D)), lib.zeros((Bq, Tt, D)), lib.zeros((Bq, Tt, D)), lib.zeros((Bq, Tt, D)))
+amask = lib.array(np.zeros((Bq, 1, 1, Tt), dtype=np.float32))
+pool = pool_of(_attn_set, 9 * R * D * 4)
+mine = timeit(lambda s: lib.call("mrn_multi_head_attention", s[3].t(), s[4].t(), s[0].t(), s[1].t(), s[2].t(), amask.t(), Hh, 0.125), pool)
+# algorithmic bytes: q, k, v in; out and probs out
+report("MultiHeadAttention fwd B64 H8 T50 dk64 (fused; reference = 9 kernels)", (4 * R * D + Bq * Hh * Tt * Tt) * 4, mine, None)
+mine = timeit(lambda s: lib.call("mrn_multi_head_attention_grad", s[6].t(), s[7].t(), s[8].t(), s[5].t(), s[3].t(), s[4].t(), s[0].t(), s[1].t(), s[2].t(), Hh, 0.125), pool)
+# q, k, v, out, dout, probs in; dq, dk, dv read + written
+report("MultiHeadAttentionGrad B64 H8 T50 dk64 (fused)", (11 * R * D + Bq * Hh * Tt * Tt) * 4, mine, None)
+del pool
+
 # ---- cross entropy fwd / bwd at the logits shape -------------------------------
 pick = lib.array(np.random.randint(0, V, size=(R, 1)).astype(np.float32))
 adj = lib.array(rnd(R, 1))
@@ -153,10 +168,10 @@ for (M, K, N, tA, tB, name) in ((R, D, D, 0, 0, "proj fwd"), (R, D, FF, 0, 0, "f
     A, B, C = lib.array(rnd(*a_shape)), lib.array(rnd(*b_shape)), lib.zeros((M, N))
     flops = 2.0 * M * N * K
     theirs = timeit(lambda s: ref.ref_prod(C.t(), A.t(), B.t(), tA, tB, F(0), F(1)), one, iters=5, warm=2, stream=LEGACY) if ref else None
-    for mode, mname in ((1, "bf16"), (2, "bf16x3")):
+    for mode, mname in ((3, "tf32 (no packing)"), (1, "bf16 (incl. operand packing)"), (2, "bf16x3 (incl. operand packing)")):
         gm = lib.gemm(mode)
         mine = timeit(lambda s: lib.call("mrn_prod", gm.h, C.t(), A.t(), B.t(), tA, tB, 0.0, 1.0), one, iters=10, warm=3)
-        report("Prod %s %dx%dx%d %s (incl. operand packing)" % (name, M, N, K, mname), 0, mine, theirs, flops=flops)
+        report("Prod %s %dx%dx%d %s" % (name, M, N, K, mname), 0, mine, theirs, flops=flops)
     del A, B, C
 
 print(json.dumps({"peaks": peaks, "rows": rows}))
