@@ -122,6 +122,8 @@ def run_reference_arm(args, rank):
     """CPU arm: the oracle port of the reference's hot path on the host cores."""
     if rank != 0:
         return
+    # torchrun pins OMP_NUM_THREADS=1; the CPU arm is meant to use every host core
+    os.environ["OMP_NUM_THREADS"] = str(os.cpu_count())
     oracle = graft.load_oracle()
     pkg = graft.load_package()
     cores = os.cpu_count()
@@ -156,6 +158,7 @@ def run_reference_arm(args, rank):
 
 
 def cpu_baseline_sample():
+    os.environ.setdefault("OMP_NUM_THREADS", str(os.cpu_count()))
     oracle = graft.load_oracle()
     pkg = graft.load_package()
     t = oracle.trainer(pkg.transformer_base_options(gemm_mode=0, workspace=8192))
@@ -309,8 +312,8 @@ def main():
                                "frac": prof["tflops"] / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk_src,
                                "kernel": "gGemmTf32|gGemmTcgen05 (all Prod/ProdBatched/ProdAffine launches of one step)",
                                "launches_per_step": prof["launches"], "gemm_ms_per_step": prof["ms"], "gflop_per_step": prof["gflop"]}
-        if not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline_sample()
+        if not args.no_cpu_baseline and world == 1:
+            out["cpu_baseline"] = cpu_baseline_sample()  # rank 0 at N=1 only
         print(json.dumps(out))
     if world > 1:
         torch.distributed.destroy_process_group()
