@@ -97,6 +97,11 @@ int mrn_cross_entropy_pick_backward(mrn_tensor out, mrn_tensor adj, mrn_tensor i
 /* LayerNormalization(+Grad): tensor_operators.h:351-364, .cu:1447-1674; beta / grad_beta may be NULL */
 int mrn_layer_norm(mrn_tensor out, mrn_tensor in, mrn_tensor gamma, const mrn_tensor* beta, float eps);
 int mrn_layer_norm_grad(mrn_tensor grad_x, mrn_tensor grad_gamma, const mrn_tensor* grad_beta, mrn_tensor adj, mrn_tensor y, mrn_tensor x, mrn_tensor gamma, const mrn_tensor* beta, float eps);
+/* layer_norm(in + residual): the "add residual, then normalise" tail of a Transformer sub-layer
+ * (src/models/transformer.h:111-123, PlusNodeOp + LayerNormalizationOp in the reference) as one operator;
+ * grad_x and grad_residual both receive d(in + residual) (accumulating). */
+int mrn_residual_layer_norm(mrn_tensor out, mrn_tensor in, mrn_tensor residual, mrn_tensor gamma, mrn_tensor beta, float eps);
+int mrn_residual_layer_norm_grad(mrn_tensor grad_x, mrn_tensor grad_residual, mrn_tensor grad_gamma, mrn_tensor grad_beta, mrn_tensor adj, mrn_tensor y, mrn_tensor x, mrn_tensor residual, mrn_tensor gamma, mrn_tensor beta, float eps);
 /* Fused multi-head attention core = the node sequence of Transformer::MultiHead / Attention
  * (src/models/transformer.h:58-77,153-261: SplitHeads, bdot, + mask, softmax, bdot, JoinHeads).
  * q [B,Tq,d], k/v [B,Tk,d], additive mask with B*Tk or B*Tq*Tk elements (may be NULL),

@@ -49,6 +49,8 @@ _SIGNATURES = {
     "mrn_cross_entropy_pick_backward": [_T, _T, _T, _T],
     "mrn_layer_norm": [_T, _T, _T, _TP, _F],
     "mrn_layer_norm_grad": [_T, _T, _TP, _T, _T, _T, _T, _TP, _F],
+    "mrn_residual_layer_norm": [_T, _T, _T, _T, _T, _F],
+    "mrn_residual_layer_norm_grad": [_T, _T, _T, _T, _T, _T, _T, _T, _T, _T, _F],
     "mrn_multi_head_attention": [_T, _T, _T, _T, _T, _TP, _I, _F],
     "mrn_multi_head_attention_grad": [_T, _T, _T, _T, _T, _T, _T, _T, _T, _I, _F],
     "mrn_att": [_T, _T, _T, _T],

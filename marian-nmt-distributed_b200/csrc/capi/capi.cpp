@@ -213,6 +213,14 @@ int mrn_layer_norm_grad(mrn_tensor gx, mrn_tensor gg, const mrn_tensor* gb, mrn_
     LayerNormalizationGrad(wrap(gx), wrap(gg), wrapOpt(gb), wrap(adj), wrap(y), wrap(x), wrap(gamma), wrapOpt(beta), eps);
   });
 }
+int mrn_residual_layer_norm(mrn_tensor out, mrn_tensor in, mrn_tensor residual, mrn_tensor gamma, mrn_tensor beta, float eps) {
+  return guarded([&] { LayerNormalization(wrap(out), wrap(in), wrap(gamma), wrap(beta), eps, wrap(residual)); });
+}
+int mrn_residual_layer_norm_grad(mrn_tensor gx, mrn_tensor gr, mrn_tensor gg, mrn_tensor gb, mrn_tensor adj, mrn_tensor y, mrn_tensor x, mrn_tensor residual, mrn_tensor gamma, mrn_tensor beta, float eps) {
+  return guarded([&] {
+    LayerNormalizationGrad(wrap(gx), wrap(gg), wrap(gb), wrap(adj), wrap(y), wrap(x), wrap(gamma), wrap(beta), eps, wrap(residual), wrap(gr));
+  });
+}
 int mrn_multi_head_attention(mrn_tensor out, mrn_tensor probs, mrn_tensor q, mrn_tensor k, mrn_tensor v, const mrn_tensor* mask, int heads, float scale) {
   return guarded([&] { MultiHeadAttention(wrap(out), wrap(probs), wrap(q), wrap(k), wrap(v), wrapOpt(mask), heads, scale); });
 }

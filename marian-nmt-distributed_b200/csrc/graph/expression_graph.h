@@ -17,6 +17,7 @@
 // (training/graph_replay.h).
 #pragma once
 
+#include <cstdlib>
 #include <list>
 #include <map>
 #include <unordered_map>
@@ -228,15 +229,43 @@ public:
   void forwardNext() {
     StagingScope scope(staging_.get());
     hashMap_.clear();
+    static const bool sideEnabled = std::getenv("MRN_NO_SIDE_STREAM") == nullptr;
+    bool pending = false;  // side-stream results not yet joined into the main stream
     while(!nodesForward_.empty()) {
       auto v = nodesForward_.front();
       v->allocate();
       v->init();
-      v->forward();
+      if(sideEnabled && v->concurrent() && !v->children().empty()) {
+        // inputs were produced on the main stream before this point (or on the side stream
+        // itself, which is in order): fork, run, hand back
+        device::forkSide();
+        v->forward();
+        device::returnFromSide();
+        v->setSideProduced(true);
+        pending = true;
+      } else {
+        if(pending) {
+          bool fromSide = false;
+          for(auto& c : v->children())
+            fromSide = fromSide || c->sideProduced();
+          if(fromSide) {
+            const std::string t = v->type();
+            if(t == "reshape" || t == "step") {
+              v->setSideProduced(true);  // zero-copy view: no device work, the dependency moves on
+            } else {
+              device::joinSide();  // joins ALL side work
+              pending = false;
+            }
+          }
+        }
+        v->forward();
+      }
       if(inferenceOnly_)
         v->children().clear();
       nodesForward_.pop_front();
     }
+    if(pending)
+      device::joinSide();
   }
 
   void backward() {

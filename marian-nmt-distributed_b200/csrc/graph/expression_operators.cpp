@@ -121,6 +121,10 @@ Expr layer_norm(Expr x, Expr gamma, Expr beta, float eps) {
     nodes.push_back(beta);
   return Expression<LayerNormalizationOp>(nodes, eps);
 }
+Expr residual_layer_norm(Expr x, Expr residual, Expr gamma, Expr beta, float eps) {
+  std::vector<Expr> nodes = {x, residual, gamma, beta};
+  return Expression<ResidualLayerNormOp>(nodes, eps);
+}
 Expr highway(Expr y, Expr x, Expr t) {
   std::vector<Expr> nodes = {y, x, t};
   return Expression<HighwayNodeOp>(nodes);

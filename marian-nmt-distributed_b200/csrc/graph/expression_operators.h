@@ -77,6 +77,8 @@ Expr step(Expr a, int step, int axis);
 Expr shift(Expr a, Shape shift);
 
 Expr layer_norm(Expr x, Expr gamma, Expr beta = nullptr, float eps = 1e-9);
+// layer_norm(x + residual, gamma, beta) as one operator (see ResidualLayerNormOp)
+Expr residual_layer_norm(Expr x, Expr residual, Expr gamma, Expr beta, float eps = 1e-9);
 Expr highway(Expr y, Expr x, Expr t);
 // fused multi-head attention core on [beam, B, T, d] projections; mask additive (may be null)
 Expr multi_head_attention(Expr q, Expr k, Expr v, Expr mask, int heads, float scale);

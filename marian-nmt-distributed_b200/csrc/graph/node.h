@@ -71,6 +71,12 @@ struct Chainable {
 
   virtual size_t hash() = 0;
   virtual bool equal(Expr) = 0;
+
+  // scheduling hints (see Node): forward pass may overlap with the main stream
+  virtual void setConcurrent(bool = true) {}
+  virtual bool concurrent() const { return false; }
+  virtual bool sideProduced() const { return false; }
+  virtual void setSideProduced(bool) {}
 };
 
 class Node : public Chainable<Tensor>, public std::enable_shared_from_this<Node> {
@@ -86,6 +92,8 @@ protected:
   Tensor adj_{nullptr};
   bool markedForDebug_{false};
   std::string debugMessage_;
+  bool concurrent_{false};      // forward pass may run on the side stream (see setConcurrent)
+  bool sideProduced_{false};    // val_ was written on the side stream and not yet joined
 
 public:
   Node(Ptr<ExpressionGraph> graph, const Shape& shape) : graph_(graph), shape_(shape) {}
@@ -146,6 +154,15 @@ public:
 
   virtual std::vector<Expr>& children() { return children_; }
   virtual Expr child(size_t i) { return children_[i]; }
+
+  // Scheduling hint from model code: this node's forward only depends on values that exist when
+  // the previously created node has run, and its result is not needed immediately - e.g. the key
+  // and value projections of an attention block while the query projection runs.  The graph runs
+  // it on the side stream and joins before the first consumer (ExpressionGraph::forwardNext).
+  virtual void setConcurrent(bool c = true) { concurrent_ = c; }
+  virtual bool concurrent() const { return concurrent_; }
+  virtual bool sideProduced() const { return sideProduced_; }
+  virtual void setSideProduced(bool s) { sideProduced_ = s; }
 
   Ptr<Backend> getBackend();
 

@@ -300,6 +300,37 @@ private:
   float eps_;
 };
 
+// layer_norm(x + residual): children {x, residual, gamma, beta}.  The reference builds a
+// PlusNodeOp and a LayerNormalizationOp (Transformer::PostProcess "a" then "n",
+// src/models/transformer.h:111-123); fused here the sum is never written to memory and the
+// backward pass delivers d(x + r) to both inputs from one kernel.
+struct ResidualLayerNormOp : public NaryNodeOp {
+  ResidualLayerNormOp(const std::vector<Expr>& nodes, float eps) : NaryNodeOp(nodes), eps_(eps) {
+    ABORT_IF(nodes.size() != 4, "residual layer-norm expects {x, residual, gamma, beta}");
+    ABORT_IF(nodes[0]->shape() != nodes[1]->shape(), "residual layer-norm: x and residual must have the same shape");
+  }
+  NodeOps forwardOps() {
+    return {NodeOp(LayerNormalization(val_, child(0)->val(), child(2)->val(), child(3)->val(), eps_, child(1)->val()))};
+  }
+  void backward() {
+    bool wantX = child(0)->trainable(), wantR = child(1)->trainable();
+    ABORT_IF(!wantX, "residual layer-norm expects a trainable main input");
+    LayerNormalizationGrad(child(0)->grad(), child(2)->grad(), child(3)->grad(), adj_, val_, child(0)->val(), child(2)->val(), child(3)->val(), eps_,
+                           child(1)->val(), wantR ? child(1)->grad() : Tensor());
+  }
+  virtual size_t hash() {
+    if(!hash_) {
+      hash_ = NaryNodeOp::hash();
+      hash_combine(hash_, eps_);
+    }
+    return hash_;
+  }
+  const std::string type() { return "residual_layer_normalization"; }
+
+private:
+  float eps_;
+};
+
 // Fused multi-head attention core: children {q, k, v[, additive mask]} in [beam, B, T, d]
 // layout.  Replaces the node sequence SplitHeads x3 / bdot / + / softmax / bdot / JoinHeads of
 // the reference's Transformer::MultiHead (src/models/transformer.h:153-261) by one forward and

@@ -482,7 +482,7 @@ __global__ void __launch_bounds__(128) gLayerNormalizationGrad(float* __restrict
 // One warp per row; a lane keeps VPL float4 of the row in registers, so every input is read
 // from HBM exactly once and all row statistics are shuffle reductions (no __syncthreads).
 template <int VPL>
-__global__ void __launch_bounds__(256) gLNormalizationWarp(float* __restrict__ out, const float* __restrict__ in, const float* __restrict__ alpha, const float* __restrict__ beta, int rows, int cols, float eps) {
+__global__ void __launch_bounds__(256) gLNormalizationWarp(float* __restrict__ out, const float* __restrict__ in, const float* __restrict__ res, const float* __restrict__ alpha, const float* __restrict__ beta, int rows, int cols, float eps) {
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   float4 g4[VPL], b4[VPL];
@@ -500,6 +500,13 @@ __global__ void __launch_bounds__(256) gLNormalizationWarp(float* __restrict__ o
     for(int i = 0; i < VPL; ++i) {
       int c = (i * 32 + lane) * 4;
       xv[i] = c < cols ? *reinterpret_cast<const float4*>(sp + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      if(res && c < cols) {  // normalise x + residual (the "a" + "n" steps of a sub-layer in one pass)
+        float4 rv = *reinterpret_cast<const float4*>(res + (size_t)row * cols + c);
+        xv[i].x += rv.x;
+        xv[i].y += rv.y;
+        xv[i].z += rv.z;
+        xv[i].w += rv.w;
+      }
       s += (xv[i].x + xv[i].y) + (xv[i].z + xv[i].w);
     }
     float mean = warpSum(s) / cols;
@@ -551,7 +558,10 @@ __global__ void __launch_bounds__(256) gLayerNormalizationGradWarp(float* __rest
                                                                    int rows,
                                                                    int cols,
                                                                    float eps,
-                                                                   int assignX) {
+                                                                   int assignX,
+                                                                   const float* __restrict__ res,
+                                                                   float* __restrict__ gradRes,
+                                                                   int assignRes) {
   __shared__ float4 red[8][32 * VPL];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -575,6 +585,13 @@ __global__ void __launch_bounds__(256) gLayerNormalizationGradWarp(float* __rest
         int c = (i * 32 + lane) * 4;
         if(c < cols) {
           xv[i] = *reinterpret_cast<const float4*>(x + off + c);
+          if(res) {
+            float4 rv = *reinterpret_cast<const float4*>(res + off + c);
+            xv[i].x += rv.x;
+            xv[i].y += rv.y;
+            xv[i].z += rv.z;
+            xv[i].w += rv.w;
+          }
           float4 yv = *reinterpret_cast<const float4*>(y + off + c);
           av[i] = *reinterpret_cast<const float4*>(adj + off + c);
           xh[i].x = (yv.x - b4[i].x) / g4[i].x;
@@ -611,6 +628,18 @@ __global__ void __launch_bounds__(256) gLayerNormalizationGradWarp(float* __rest
         v.y = lnGradElem(av[i].y, xh[i].y, g4[i].y, sum_adj, sum_adj_x, fcols, sigma);
         v.z = lnGradElem(av[i].z, xh[i].z, g4[i].z, sum_adj, sum_adj_x, fcols, sigma);
         v.w = lnGradElem(av[i].w, xh[i].w, g4[i].w, sum_adj, sum_adj_x, fcols, sigma);
+        if(gradRes) {  // d(x + r)/dr = 1: the residual branch receives the same gradient
+          float4* gr = reinterpret_cast<float4*>(gradRes + off + c);
+          float4 w = v;
+          if(!assignRes) {
+            float4 o = *gr;
+            w.x += o.x;
+            w.y += o.y;
+            w.z += o.z;
+            w.w += o.w;
+          }
+          *gr = w;
+        }
         float4* gx = reinterpret_cast<float4*>(gradX + off + c);
         if(!assignX) {
           float4 o = *gx;
@@ -665,28 +694,34 @@ __global__ void __launch_bounds__(256) gLayerNormalizationGradWarp(float* __rest
 
 }  // namespace
 
-void LayerNormalization(Tensor out, Tensor in, Tensor gamma, Tensor beta, float eps) {
+bool LayerNormResidualFusable(int cols) {
+  return cols % 4 == 0 && cols <= 1024;
+}
+
+void LayerNormalization(Tensor out, Tensor in, Tensor gamma, Tensor beta, float eps, Tensor residual) {
   device::setDevice(out->getDevice());
   int cols = in->shape().back();
   int rows = in->shape().elements() / cols;
   out->takeLazyZero();
   const float* bp = beta ? beta->data() : nullptr;
-  bool aligned = (cols % 4 == 0) && (((uintptr_t)out->data() | (uintptr_t)in->data() | (uintptr_t)gamma->data() | (uintptr_t)bp) & 15) == 0;
+  const float* rp = residual ? residual->data() : nullptr;
+  bool aligned = (cols % 4 == 0) && (((uintptr_t)out->data() | (uintptr_t)in->data() | (uintptr_t)gamma->data() | (uintptr_t)bp | (uintptr_t)rp) & 15) == 0;
   if(aligned && cols <= 1024) {
     int grid = std::max(1, std::min((rows + 7) / 8, kNumSMs * 4));
     auto st = cudaStreamOfEngine();
     if(cols <= 512)
-      gLNormalizationWarp<4><<<grid, 256, 0, st>>>(out->data(), in->data(), gamma->data(), bp, rows, cols, eps);
+      gLNormalizationWarp<4><<<grid, 256, 0, st>>>(out->data(), in->data(), rp, gamma->data(), bp, rows, cols, eps);
     else
-      gLNormalizationWarp<8><<<grid, 256, 0, st>>>(out->data(), in->data(), gamma->data(), bp, rows, cols, eps);
+      gLNormalizationWarp<8><<<grid, 256, 0, st>>>(out->data(), in->data(), rp, gamma->data(), bp, rows, cols, eps);
     CUDA_LAUNCH_CHECK();
     return;
   }
+  ABORT_IF(residual, "LayerNormalization with a fused residual needs 16-byte aligned rows of at most 1024 floats");
   auto l = rowLaunch(rows, cols);
   ROW_DISPATCH(gLNormalization, l, out->data(), in->data(), gamma->data(), bp, rows, cols, eps);
 }
 
-void LayerNormalizationGrad(Tensor gradX, Tensor gradGamma, Tensor gradBeta, Tensor adj, Tensor y, Tensor x, Tensor gamma, Tensor beta, float eps) {
+void LayerNormalizationGrad(Tensor gradX, Tensor gradGamma, Tensor gradBeta, Tensor adj, Tensor y, Tensor x, Tensor gamma, Tensor beta, float eps, Tensor residual, Tensor gradResidual) {
   device::setDevice(adj->getDevice());
   int cols = y->shape().back();
   int rows = y->shape().elements() / cols;
@@ -696,18 +731,23 @@ void LayerNormalizationGrad(Tensor gradX, Tensor gradGamma, Tensor gradBeta, Ten
     float* gbp = gradBeta ? gradBeta->data() : nullptr;
     bool aligned = (cols % 4 == 0)
                    && (((uintptr_t)gradX->memory()->data() | (uintptr_t)adj->data() | (uintptr_t)y->data() | (uintptr_t)x->data() | (uintptr_t)gamma->data() | (uintptr_t)bp) & 15) == 0;
+    const float* rp = residual ? residual->data() : nullptr;
+    aligned = aligned && (((uintptr_t)rp | (uintptr_t)(gradResidual ? gradResidual->memory()->data() : nullptr)) & 15) == 0;
     if(aligned && cols <= 1024) {
       int assignX = gradX->takeLazyZero() ? 1 : 0;
+      int assignRes = (gradResidual && gradResidual->takeLazyZero()) ? 1 : 0;
+      float* grp = gradResidual ? gradResidual->data() : nullptr;
       // few, fat blocks: every block ends with one atomic per column for gamma and beta
       int grid = std::max(1, std::min((rows + 15) / 16, kNumSMs * 2));
       if(cols <= 512)
-        gLayerNormalizationGradWarp<4><<<grid, 256, 0, st>>>(gradX->data(), gradGamma->data(), gbp, adj->data(), y->data(), x->data(), gamma->data(), bp, rows, cols, eps, assignX);
+        gLayerNormalizationGradWarp<4><<<grid, 256, 0, st>>>(gradX->data(), gradGamma->data(), gbp, adj->data(), y->data(), x->data(), gamma->data(), bp, rows, cols, eps, assignX, rp, grp, assignRes);
       else
-        gLayerNormalizationGradWarp<8><<<grid, 256, 0, st>>>(gradX->data(), gradGamma->data(), gbp, adj->data(), y->data(), x->data(), gamma->data(), bp, rows, cols, eps, assignX);
+        gLayerNormalizationGradWarp<8><<<grid, 256, 0, st>>>(gradX->data(), gradGamma->data(), gbp, adj->data(), y->data(), x->data(), gamma->data(), bp, rows, cols, eps, assignX, rp, grp, assignRes);
       CUDA_LAUNCH_CHECK();
       return;
     }
   }
+  ABORT_IF(residual || gradResidual, "LayerNormalizationGrad with a fused residual needs 16-byte aligned rows of at most 1024 floats");
   int grid = std::max(1, std::min(rows, kNumSMs * 4));
 #define LN_BWD(M)                                                                                                                  \
   gLayerNormalizationGrad<M><<<grid, 128, 0, st>>>(gradX->data(), gradGamma->data(), gradBeta ? gradBeta->data() : nullptr, adj->data(), \

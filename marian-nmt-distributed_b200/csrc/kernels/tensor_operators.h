@@ -112,8 +112,12 @@ bool AttentionFusable(int Tq, int Tk, int dimModel, int heads);
 void MultiHeadAttention(Tensor out, Tensor probs, const Tensor q, const Tensor k, const Tensor v, const Tensor mask, int heads, float scale);
 void MultiHeadAttentionGrad(Tensor dq, Tensor dk, Tensor dv, const Tensor adj, const Tensor out, const Tensor probs, const Tensor q, const Tensor k, const Tensor v, int heads, float scale);
 
-void LayerNormalization(Tensor out, Tensor in, Tensor gamma, Tensor beta, float eps = 1e-9);
-void LayerNormalizationGrad(Tensor gradX, Tensor gradGamma, Tensor gradBeta, Tensor adj, Tensor y, Tensor x, Tensor gamma, Tensor beta, float eps = 1e-9);
+// `residual` (optional, this repo's addition): normalise in + residual, i.e. the "add the
+// residual, then layer-norm" tail of every Transformer sub-layer (src/models/transformer.h:97-126)
+// in one pass; the gradient then also flows into gradResidual (accumulating unless lazily zero).
+bool LayerNormResidualFusable(int cols);
+void LayerNormalization(Tensor out, Tensor in, Tensor gamma, Tensor beta, float eps = 1e-9, Tensor residual = nullptr);
+void LayerNormalizationGrad(Tensor gradX, Tensor gradGamma, Tensor gradBeta, Tensor adj, Tensor y, Tensor x, Tensor gamma, Tensor beta, float eps = 1e-9, Tensor residual = nullptr, Tensor gradResidual = nullptr);
 
 void Shift(Tensor out, Tensor in, Shape shift, bool invert = false);
 

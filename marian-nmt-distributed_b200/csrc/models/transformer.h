@@ -31,6 +31,16 @@ struct TransformerSublayers {
     bool fuseAttention() const {
       return options->get<bool>("transformer-fused-attention", std::string(device::backendName()) == "cuda");
     }
+    // key/value projections on the side stream while the query projection runs (tf32 / fp32
+    // GEMM modes only: the packed-operand modes share one scratch cache between streams)
+    bool concurrentProjections() const {
+      auto mode = getGemmMode(graph->getBackend()->getGemmHandle());
+      return std::string(device::backendName()) == "cuda" && (mode == GemmMode::TF32 || mode == GemmMode::FP32)
+             && options->get<bool>("transformer-concurrent-projections", true);
+    }
+    bool fuseResidualNorm() const {
+      return options->get<bool>("transformer-fused-residual-norm", std::string(device::backendName()) == "cuda");
+    }
   };
 
   // [.., T, B, d] <-> [.., B, T, d]
@@ -83,7 +93,18 @@ struct TransformerSublayers {
     using namespace keywords;
     const int width = x->shape()[-1];
     const std::string suffix = residual ? "" : "_pre";
-    for(char step : recipe) {
+    for(size_t pos = 0; pos < recipe.size(); ++pos) {
+      const char step = recipe[pos];
+      // "an": add the residual and normalise in ONE operator (no parameters are created by "a",
+      // so the creation order of the layer-norm parameters is unchanged)
+      if(step == 'a' && residual && pos + 1 < recipe.size() && recipe[pos + 1] == 'n' && env.fuseResidualNorm() && LayerNormResidualFusable(width)
+         && x->shape() == residual->shape()) {
+        auto gain = env.graph->param(prefix + "_ln_scale" + suffix, {1, width}, init = inits::ones);
+        auto shift = env.graph->param(prefix + "_ln_bias" + suffix, {1, width}, init = inits::zeros);
+        x = residual_layer_norm(x, residual, gain, shift, 1e-6);
+        ++pos;
+        continue;
+      }
       switch(step) {
         case 'd':
           if(dropProb > 0.f)
@@ -159,16 +180,41 @@ struct TransformerSublayers {
   // Wk bk Wv bv, then Wo bo (reference :194-261).  Several memories (multi-source) are attended
   // separately and concatenated before Wo.
   static Expr multiHead(const Env& env, const std::string& prefix, int heads, Expr query, const std::vector<Expr>& memories, const std::vector<Expr>& masks) {
+    using namespace keywords;
     const int width = query->shape()[-1];
-    Expr q = linear(env, prefix + "_Wq", prefix + "_bq", query, width, width);
-
-    std::vector<Expr> contexts;
+    // parameters first, in the reference's creation order (it fixes the initialisation stream) ...
+    auto Wq = env.graph->param(prefix + "_Wq", {width, width}, init = inits::glorot_uniform);
+    auto bq = env.graph->param(prefix + "_bq", {1, width}, init = inits::zeros);
+    struct KV {
+      Expr Wk, bk, Wv, bv;
+    };
+    std::vector<KV> kv;
     for(size_t m = 0; m < memories.size(); ++m) {
       std::string p = m == 0 ? prefix : prefix + "_enc" + std::to_string(m + 1);
-      Expr k = linear(env, p + "_Wk", p + "_bk", memories[m], width, width);
-      Expr v = linear(env, p + "_Wv", p + "_bv", memories[m], width, width);
-      contexts.push_back(attend(env, q, k, v, masks[m], heads));
+      KV w;
+      w.Wk = env.graph->param(p + "_Wk", {width, width}, init = inits::glorot_uniform);
+      w.bk = env.graph->param(p + "_bk", {1, width}, init = inits::zeros);
+      w.Wv = env.graph->param(p + "_Wv", {width, width}, init = inits::glorot_uniform);
+      w.bv = env.graph->param(p + "_bv", {1, width}, init = inits::zeros);
+      kv.push_back(w);
     }
+    // ... then the products: keys and values go to the side stream, the query projection runs
+    // concurrently on the main stream, the attention core joins them
+    const bool concurrent = env.concurrentProjections();
+    std::vector<Expr> keys, values;
+    for(size_t m = 0; m < memories.size(); ++m) {
+      Expr k = affine(memories[m], kv[m].Wk, kv[m].bk);
+      Expr v = affine(memories[m], kv[m].Wv, kv[m].bv);
+      k->setConcurrent(concurrent);
+      v->setConcurrent(concurrent);
+      keys.push_back(k);
+      values.push_back(v);
+    }
+    Expr q = affine(query, Wq, bq);
+
+    std::vector<Expr> contexts;
+    for(size_t m = 0; m < memories.size(); ++m)
+      contexts.push_back(attend(env, q, keys[m], values[m], masks[m], heads));
     Expr joined = contexts.size() == 1 ? contexts.front() : concatenate(contexts, keywords::axis = -1);
     return linear(env, prefix + "_Wo", prefix + "_bo", joined, joined->shape()[-1], width);
   }

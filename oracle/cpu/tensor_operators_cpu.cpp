@@ -880,9 +880,25 @@ void MultiHeadAttentionGrad(Tensor dq, Tensor dk, Tensor dv, const Tensor adj, c
 // ---------------------------------------------------------------------------
 // Layer normalisation       reference: :1447-1674
 // ---------------------------------------------------------------------------
-void LayerNormalization(Tensor out, Tensor in, Tensor gamma, Tensor beta, float eps) {
-  int cols = in->shape().back();
-  int rows = in->shape().elements() / cols;
+bool LayerNormResidualFusable(int cols) {
+  return cols > 0;
+}
+
+// `residual`: the operator then normalises in + residual - restated as the reference's
+// PlusNodeOp (node_operators_binary.h:418-436) followed by LayerNormalization.
+void LayerNormalization(Tensor out, Tensor inRaw, Tensor gamma, Tensor beta, float eps, Tensor residual) {
+  int cols = inRaw->shape().back();
+  int rows = inRaw->shape().elements() / cols;
+  std::vector<float> summed;
+  const float* inData = inRaw->data();
+  if(residual) {
+    summed.resize((size_t)rows * cols);
+    for(size_t i = 0; i < summed.size(); ++i)
+      summed[i] = inRaw->data()[i] + residual->data()[i];
+    inData = summed.data();
+  }
+  struct { const float* p; const float* data() const { return p; } } inView{inData};
+  auto in = &inView;
   const float* alpha = gamma->data();
   const float* bet = beta ? beta->data() : nullptr;
 #pragma omp parallel for if((long)rows * cols > 16384)
@@ -908,9 +924,22 @@ void LayerNormalization(Tensor out, Tensor in, Tensor gamma, Tensor beta, float 
   }
 }
 
-void LayerNormalizationGrad(Tensor gradX, Tensor gradGamma, Tensor gradBeta, Tensor adj, Tensor y, Tensor x, Tensor gamma, Tensor beta, float eps) {
+void LayerNormalizationGrad(Tensor gradX, Tensor gradGamma, Tensor gradBeta, Tensor adj, Tensor y, Tensor xRaw, Tensor gamma, Tensor beta, float eps, Tensor residual, Tensor gradResidual) {
   int cols = y->shape().back();
   int rows = y->shape().elements() / cols;
+  // fused residual: x = xRaw + residual; both inputs receive the same gradient (PlusNodeOp backward)
+  std::vector<float> summed, before;
+  const float* xData = xRaw->data();
+  if(residual) {
+    summed.resize((size_t)rows * cols);
+    for(size_t i = 0; i < summed.size(); ++i)
+      summed[i] = xRaw->data()[i] + residual->data()[i];
+    xData = summed.data();
+  }
+  if(gradResidual)
+    before.assign(gradX->data(), gradX->data() + (size_t)rows * cols);
+  struct { const float* p; const float* data() const { return p; } } xView{xData};
+  auto x = &xView;
   const float* g = gamma->data();
   const float* bet = beta ? beta->data() : nullptr;
   std::vector<double> gGamma(cols, 0.0), gBeta(cols, 0.0);
@@ -953,6 +982,12 @@ void LayerNormalizationGrad(Tensor gradX, Tensor gradGamma, Tensor gradBeta, Ten
     gradGamma->data()[id] += (float)gGamma[id];
     if(bet)
       gradBeta->data()[id] += (float)gBeta[id];
+  }
+  if(gradResidual) {
+    float* gr = gradResidual->data();
+    const float* gx = gradX->data();
+    for(size_t i = 0; i < before.size(); ++i)
+      gr[i] += gx[i] - before[i];
   }
 }
 

@@ -77,10 +77,10 @@ def test_graph_replay_equals_eager(cuda, opts):
 
 
 def test_fused_attention_equals_unfused_nodes(cuda):
-    """transformer-fused-attention on/off on the GPU, fp32 GEMM mode: same costs, same parameters."""
+    """Fused attention + fused residual/layer-norm on/off on the GPU, fp32 GEMM mode: same costs, logits, gradients."""
     outs = {}
     for fused in ("true", "false"):
-        outs[fused] = run_steps(cuda, TRANSFORMER + ";transformer-fused-attention=" + fused, 0, steps=3, keep=True)
+        outs[fused] = run_steps(cuda, TRANSFORMER + ";transformer-fused-attention=%s;transformer-fused-residual-norm=%s" % (fused, fused), 0, steps=3, keep=True)
     a, b = outs["true"], outs["false"]
     assert np.allclose(a["costs"], b["costs"], rtol=2e-5), (a["costs"], b["costs"])
     close(a["logits"], b["logits"], 2e-5, "logits")
