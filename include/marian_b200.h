@@ -105,9 +105,10 @@ int mrn_residual_layer_norm_grad(mrn_tensor grad_x, mrn_tensor grad_residual, mr
 /* Fused multi-head attention core = the node sequence of Transformer::MultiHead / Attention
  * (src/models/transformer.h:58-77,153-261: SplitHeads, bdot, + mask, softmax, bdot, JoinHeads).
  * q [B,Tq,d], k/v [B,Tk,d], additive mask with B*Tk or B*Tq*Tk elements (may be NULL),
- * probs [B,heads,Tq,Tk] (softmax output, kept for the backward pass).  The gradients ACCUMULATE. */
-int mrn_multi_head_attention(mrn_tensor out, mrn_tensor probs, mrn_tensor q, mrn_tensor k, mrn_tensor v, const mrn_tensor* mask, int heads, float scale);
-int mrn_multi_head_attention_grad(mrn_tensor dq, mrn_tensor dk, mrn_tensor dv, mrn_tensor adj, mrn_tensor out, mrn_tensor probs, mrn_tensor q, mrn_tensor k, mrn_tensor v, int heads, float scale);
+ * probs [B,heads,Tq,Tk] (softmax output, kept for the backward pass).  The gradients ACCUMULATE.
+ * exact != 0: 3xTF32 products (fp32-grade); exact == 0: plain tf32 operands. */
+int mrn_multi_head_attention(mrn_tensor out, mrn_tensor probs, mrn_tensor q, mrn_tensor k, mrn_tensor v, const mrn_tensor* mask, int heads, float scale, int exact);
+int mrn_multi_head_attention_grad(mrn_tensor dq, mrn_tensor dk, mrn_tensor dv, mrn_tensor adj, mrn_tensor out, mrn_tensor probs, mrn_tensor q, mrn_tensor k, mrn_tensor v, int heads, float scale, int exact);
 /* Att / AttBack: tensor_operators.h:342-349, .cu:1307-1445 */
 int mrn_att(mrn_tensor out, mrn_tensor va, mrn_tensor context, mrn_tensor state);
 int mrn_att_back(mrn_tensor g_va, mrn_tensor g_context, mrn_tensor g_state, mrn_tensor va, mrn_tensor context, mrn_tensor state, mrn_tensor adj);

@@ -51,8 +51,8 @@ _SIGNATURES = {
     "mrn_layer_norm_grad": [_T, _T, _TP, _T, _T, _T, _T, _TP, _F],
     "mrn_residual_layer_norm": [_T, _T, _T, _T, _T, _F],
     "mrn_residual_layer_norm_grad": [_T, _T, _T, _T, _T, _T, _T, _T, _T, _T, _F],
-    "mrn_multi_head_attention": [_T, _T, _T, _T, _T, _TP, _I, _F],
-    "mrn_multi_head_attention_grad": [_T, _T, _T, _T, _T, _T, _T, _T, _T, _I, _F],
+    "mrn_multi_head_attention": [_T, _T, _T, _T, _T, _TP, _I, _F, _I],
+    "mrn_multi_head_attention_grad": [_T, _T, _T, _T, _T, _T, _T, _T, _T, _I, _F, _I],
     "mrn_att": [_T, _T, _T, _T],
     "mrn_att_back": [_T, _T, _T, _T, _T, _T, _T],
     "mrn_gru_fast_forward": [_T, _TP, _I, _I],

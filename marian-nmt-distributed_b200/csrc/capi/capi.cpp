@@ -221,12 +221,12 @@ int mrn_residual_layer_norm_grad(mrn_tensor gx, mrn_tensor gr, mrn_tensor gg, mr
     LayerNormalizationGrad(wrap(gx), wrap(gg), wrap(gb), wrap(adj), wrap(y), wrap(x), wrap(gamma), wrap(beta), eps, wrap(residual), wrap(gr));
   });
 }
-int mrn_multi_head_attention(mrn_tensor out, mrn_tensor probs, mrn_tensor q, mrn_tensor k, mrn_tensor v, const mrn_tensor* mask, int heads, float scale) {
-  return guarded([&] { MultiHeadAttention(wrap(out), wrap(probs), wrap(q), wrap(k), wrap(v), wrapOpt(mask), heads, scale); });
+int mrn_multi_head_attention(mrn_tensor out, mrn_tensor probs, mrn_tensor q, mrn_tensor k, mrn_tensor v, const mrn_tensor* mask, int heads, float scale, int exact) {
+  return guarded([&] { MultiHeadAttention(wrap(out), wrap(probs), wrap(q), wrap(k), wrap(v), wrapOpt(mask), heads, scale, exact != 0); });
 }
-int mrn_multi_head_attention_grad(mrn_tensor dq, mrn_tensor dk, mrn_tensor dv, mrn_tensor adj, mrn_tensor out, mrn_tensor probs, mrn_tensor q, mrn_tensor k, mrn_tensor v, int heads, float scale) {
+int mrn_multi_head_attention_grad(mrn_tensor dq, mrn_tensor dk, mrn_tensor dv, mrn_tensor adj, mrn_tensor out, mrn_tensor probs, mrn_tensor q, mrn_tensor k, mrn_tensor v, int heads, float scale, int exact) {
   return guarded([&] {
-    MultiHeadAttentionGrad(wrap(dq), wrap(dk), wrap(dv), wrap(adj), wrap(out), wrap(probs), wrap(q), wrap(k), wrap(v), heads, scale);
+    MultiHeadAttentionGrad(wrap(dq), wrap(dk), wrap(dv), wrap(adj), wrap(out), wrap(probs), wrap(q), wrap(k), wrap(v), heads, scale, exact != 0);
   });
 }
 int mrn_att(mrn_tensor out, mrn_tensor va, mrn_tensor context, mrn_tensor state) {

@@ -352,13 +352,18 @@ struct MultiHeadAttentionNodeOp : public NaryNodeOp {
     int batch = child(0)->shape().elements() / (Tq * child(0)->shape()[-1]);
     if(!probs_)
       graph()->tensor(probs_, Shape{batch, heads_, Tq, Tk});
-    MultiHeadAttention(val_, probs_, child(0)->val(), child(1)->val(), child(2)->val(), children_.size() > 3 ? child(3)->val() : nullptr, heads_, scale_);
+    MultiHeadAttention(val_, probs_, child(0)->val(), child(1)->val(), child(2)->val(), children_.size() > 3 ? child(3)->val() : nullptr, heads_, scale_, exact());
   }
   void backward() {
     // q, k, v come out of trainable projections in every model; a frozen input would still
     // get a (discarded) adjoint from set_zero_adjoint only if trainable, so require it
     ABORT_IF(!child(0)->trainable() || !child(1)->trainable() || !child(2)->trainable(), "fused attention expects trainable q, k, v");
-    MultiHeadAttentionGrad(child(0)->grad(), child(1)->grad(), child(2)->grad(), adj_, val_, probs_, child(0)->val(), child(1)->val(), child(2)->val(), heads_, scale_);
+    MultiHeadAttentionGrad(child(0)->grad(), child(1)->grad(), child(2)->grad(), adj_, val_, probs_, child(0)->val(), child(1)->val(), child(2)->val(), heads_, scale_, exact());
+  }
+  // fp32-grade products in the exact GEMM modes, plain tf32 in the tf32 / bf16 modes
+  bool exact() {
+    auto mode = getGemmMode(getBackend()->getGemmHandle());
+    return mode == GemmMode::FP32 || mode == GemmMode::BF16X3;
   }
 
   virtual size_t hash() {

@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "kernels/cuda_helpers.h"
 #include "kernels/tensor_operators.h"
@@ -288,6 +289,359 @@ __global__ void __launch_bounds__(kAttnThreads) gAttentionBackward(float* __rest
   tileMulVec(sP, 1, ldS, g.Tk, sQ, ld, g.Tq, g.dk, [&](int j, int c, float4 acc) { emit(dk_ + offK + (size_t)j * d + c, acc, accK != 0); });
 }
 
+
+// ------------------------------------------------------------------------------------------
+// tensor-core variant: the five products of a head on mma.sync m16n8k8 tf32
+// ------------------------------------------------------------------------------------------
+// A head's products are 64x64x64-class: too small for a tcgen05 tile pipeline, but a good fit
+// for warp-level MMAs on shared-memory operands.  Every matrix is zero-padded to multiples of 16
+// in shared memory; row pitches are chosen so that the fragment loads of the m16n8k8 layout are
+// bank-conflict free:  A(m,k) / B(k,n) read "along k"  -> pitch = 4 (mod 32) words,
+//                      B(k,n) read from a [k][n] matrix -> pitch = 8 (mod 32) words.
+// Transposed A operands (P^T, dS^T) are kept as explicit transposed copies instead.
+// X3 = true: 3xTF32 error compensation (a = hi + lo, three MMAs) - fp32-grade accuracy for the
+// exact GEMM modes; X3 = false: plain tf32, the same operand precision as the tf32 GEMMs.
+__device__ __forceinline__ uint32_t toTf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mmaTf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
+__host__ __device__ inline int pad16(int x) {
+  return (x + 15) & ~15;
+}
+// smallest pitch >= n that is congruent to r modulo 32
+__host__ __device__ inline int pitchMod32(int n, int r) {
+  int p = (n / 32) * 32 + r;
+  return p >= n ? p : p + 32;
+}
+
+// D(M x N) = A(M x K) B(K x N); A(m,k) = As[m*lda + k]; B(k,n) = BT ? Bs[n*ldb + k] : Bs[k*ldb + n].
+// M % 16 == 0, N % 8 == 0, K % 8 == 0 (zero padded).  Work items = (m-tile, chunk of <= 4 n-tiles),
+// dealt round-robin to the warps; the A fragment of a k-step is reused by the chunk's n-tiles.
+// epi(row, col, v0, v1) receives the results for (row, col) and (row, col + 1).
+template <bool BT, bool X3, class Epi>
+__device__ __forceinline__ void warpMmaProduct(const float* As, int lda, const float* Bs, int ldb, int M, int N, int K, Epi epi) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int MT = M >> 4, NT = N >> 3, NC = (NT + 3) >> 2;
+  for(int item = warp; item < MT * NC; item += nwarps) {
+    const int mt = item % MT, nc = item / MT;
+    const int m0 = mt << 4, nt0 = nc << 2;
+    const int ntiles = min(4, NT - nt0);
+    float acc[4][4];
+#pragma unroll
+    for(int i = 0; i < 4; ++i)
+#pragma unroll
+      for(int j = 0; j < 4; ++j)
+        acc[i][j] = 0.f;
+    const float* ap = As + (m0 + g) * lda + t;
+    // B fragment base of n-tile i: &B(k = t, n = n0 + g)
+    const float* bp[4];
+#pragma unroll
+    for(int i = 0; i < 4; ++i) {
+      const int n0 = (nt0 + min(i, ntiles - 1)) << 3;
+      bp[i] = BT ? Bs + (n0 + g) * ldb + t : Bs + t * ldb + n0 + g;
+    }
+    const int bk = BT ? 1 : ldb;  // address step of one k
+#pragma unroll 2
+    for(int k0 = 0; k0 < K; k0 += 8) {
+      // all fragment loads of the k-step first (10-12 independent LDS in flight), then the MMAs
+      float af[4] = {ap[k0], ap[k0 + 8 * lda], ap[k0 + 4], ap[k0 + 8 * lda + 4]};
+      float bf[4][2];
+#pragma unroll
+      for(int i = 0; i < 4; ++i) {
+        bf[i][0] = bp[i][k0 * bk];
+        bf[i][1] = bp[i][(k0 + 4) * bk];
+      }
+      uint32_t ahi[4], alo[4];
+#pragma unroll
+      for(int i = 0; i < 4; ++i) {
+        ahi[i] = toTf32(af[i]);
+        if(X3)
+          alo[i] = toTf32(af[i] - __uint_as_float(ahi[i]));
+      }
+#pragma unroll
+      for(int i = 0; i < 4; ++i) {
+        if(i < ntiles) {
+          uint32_t bhi[2] = {toTf32(bf[i][0]), toTf32(bf[i][1])};
+          if(X3) {
+            uint32_t blo[2] = {toTf32(bf[i][0] - __uint_as_float(bhi[0])), toTf32(bf[i][1] - __uint_as_float(bhi[1]))};
+            mmaTf32(acc[i], alo, bhi);  // small terms first
+            mmaTf32(acc[i], ahi, blo);
+          }
+          mmaTf32(acc[i], ahi, bhi);
+        }
+      }
+    }
+#pragma unroll
+    for(int i = 0; i < 4; ++i) {
+      if(i < ntiles) {
+        const int col = ((nt0 + i) << 3) + 2 * t;
+        epi(m0 + g, col, acc[i][0], acc[i][1]);
+        epi(m0 + g + 8, col, acc[i][2], acc[i][3]);
+      }
+    }
+  }
+}
+
+// Asynchronous global -> shared copies (LDGSTS): every thread fires all of its 16-byte pieces
+// and waits ONCE, so a CTA pays one memory round trip for Q, K, V (and dO, P) instead of one per
+// loop iteration of a load/store chain.
+__device__ __forceinline__ void cpAsync16(float* smem, const float* gmem) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cpAsync4(float* smem, const float* gmem) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cpAsyncWaitAll() {
+  asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
+// [T, dk] head slice -> shared memory [Tpad][ld] (asynchronous), rows >= T zero filled
+__device__ __forceinline__ void loadHeadPadded(float* dst, int ld, const float* src, int T, int Tpad, int dk, int d) {
+  const int v4 = dk >> 2;
+  for(int e = threadIdx.x; e < Tpad * v4; e += blockDim.x) {
+    int r = e / v4, c = (e - r * v4) << 2;
+    if(r < T)
+      cpAsync16(dst + r * ld + c, src + (size_t)r * d + c);
+    else
+      *reinterpret_cast<float4*>(dst + r * ld + c) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// shared memory [T][ld] -> [T, dk] head slice of a [B, T, H*dk] tensor, 128-bit coalesced rows
+__device__ __forceinline__ void storeHead(float* dst, const float* src, int ld, int T, int dk, int d, bool accumulate) {
+  const int v4 = dk >> 2;
+  for(int e = threadIdx.x; e < T * v4; e += blockDim.x) {
+    int r = e / v4, c = (e - r * v4) << 2;
+    float4 v = *reinterpret_cast<const float4*>(src + r * ld + c);
+    float* gp = dst + (size_t)r * d + c;
+    if(accumulate) {
+      float4 o = *reinterpret_cast<const float4*>(gp);
+      v.x += o.x;
+      v.y += o.y;
+      v.z += o.z;
+      v.w += o.w;
+    }
+    *reinterpret_cast<float4*>(gp) = v;
+  }
+}
+
+struct MmaLayoutFwd {
+  int TqP, TkP, ldQ, ldK, ldV, ldS;
+  __host__ __device__ MmaLayoutFwd(const AttnGeom& g) {
+    TqP = pad16(g.Tq);
+    TkP = pad16(g.Tk);
+    ldQ = ldK = pitchMod32(g.dk, 4);
+    ldV = pitchMod32(g.dk, 8);
+    ldS = pitchMod32(TkP, 4);
+  }
+  __host__ __device__ size_t floats() const { return (size_t)TqP * ldQ + (size_t)TkP * ldK + (size_t)TkP * ldV + (size_t)TqP * ldS; }
+};
+
+template <bool X3>
+__global__ void __launch_bounds__(kAttnThreads) gAttentionForwardMma(float* __restrict__ out,
+                                                                     float* __restrict__ probs,
+                                                                     const float* __restrict__ q,
+                                                                     const float* __restrict__ k,
+                                                                     const float* __restrict__ v,
+                                                                     const float* __restrict__ mask,
+                                                                     AttnGeom g) {
+  extern __shared__ __align__(16) float smemF[];
+  const MmaLayoutFwd L(g);
+  float* sQ = smemF;
+  float* sK = sQ + L.TqP * L.ldQ;
+  float* sV = sK + L.TkP * L.ldK;
+  float* sS = sV + L.TkP * L.ldV;
+
+  const int b = blockIdx.x / g.H, h = blockIdx.x - b * g.H;
+  const int d = g.H * g.dk;
+  loadHeadPadded(sQ, L.ldQ, q + ((size_t)b * g.Tq) * d + h * g.dk, g.Tq, L.TqP, g.dk, d);
+  loadHeadPadded(sK, L.ldK, k + ((size_t)b * g.Tk) * d + h * g.dk, g.Tk, L.TkP, g.dk, d);
+  loadHeadPadded(sV, L.ldV, v + ((size_t)b * g.Tk) * d + h * g.dk, g.Tk, L.TkP, g.dk, d);
+  cpAsyncWaitAll();
+  __syncthreads();
+
+  // S = scale Q K^T + mask
+  const float* mrow = mask ? mask + (size_t)b * g.maskRows * g.Tk : nullptr;
+  const int maskPitch = g.maskRows > 1 ? g.Tk : 0;
+  warpMmaProduct<true, X3>(sQ, L.ldQ, sK, L.ldK, L.TqP, L.TkP, g.dk, [&](int i, int j, float v0, float v1) {
+    float s0 = v0 * g.scale, s1 = v1 * g.scale;
+    if(mrow && i < g.Tq) {
+      if(j < g.Tk)
+        s0 += mrow[i * maskPitch + j];
+      if(j + 1 < g.Tk)
+        s1 += mrow[i * maskPitch + j + 1];
+    }
+    *reinterpret_cast<float2*>(sS + i * L.ldS + j) = make_float2(s0, s1);
+  });
+  __syncthreads();
+
+  // row softmax over the real columns; padding columns / rows become exact zeros
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for(int i = warp; i < L.TqP; i += nwarps) {
+    float* row = sS + i * L.ldS;
+    if(i >= g.Tq) {
+      for(int j = lane; j < L.TkP; j += 32)
+        row[j] = 0.f;
+      continue;
+    }
+    float m = -3.0e38f;
+    for(int j = lane; j < g.Tk; j += 32)
+      m = fmaxf(m, row[j]);
+    m = warpMax(m);
+    float sum = 0.f;
+    for(int j = lane; j < g.Tk; j += 32) {
+      float e = __expf(row[j] - m);
+      row[j] = e;
+      sum += e;
+    }
+    sum = warpSum(sum);
+    float inv = 1.f / sum;
+    float* prow = probs ? probs + (((size_t)b * g.H + h) * g.Tq + i) * g.Tk : nullptr;
+    for(int j = lane; j < L.TkP; j += 32) {
+      float p = j < g.Tk ? row[j] * inv : 0.f;
+      row[j] = p;
+      if(prow && j < g.Tk)
+        prow[j] = p;
+    }
+  }
+  __syncthreads();
+
+  // O = P V, staged in the (now idle) Q tile and written as coalesced rows of [B, Tq, H*dk]
+  warpMmaProduct<false, X3>(sS, L.ldS, sV, L.ldV, L.TqP, g.dk, L.TkP, [&](int i, int c, float v0, float v1) {
+    *reinterpret_cast<float2*>(sQ + i * L.ldQ + c) = make_float2(v0, v1);
+  });
+  __syncthreads();
+  storeHead(out + ((size_t)b * g.Tq) * d + h * g.dk, sQ, L.ldQ, g.Tq, g.dk, d, false);
+}
+
+struct MmaLayoutBwd {
+  int TqP, TkP, rowsV, ldQ, ldK, ldV, ldO, ldS, ldT;
+  __host__ __device__ MmaLayoutBwd(const AttnGeom& g) {
+    TqP = pad16(g.Tq);
+    TkP = pad16(g.Tk);
+    rowsV = TqP > TkP ? TqP : TkP;  // the V tile doubles as the staging tile of dQ
+    ldQ = ldK = pitchMod32(g.dk, 8);  // B operands read from [k][n] matrices
+    ldV = pitchMod32(g.dk, 4);        // B operand read along k
+    ldO = pitchMod32(g.dk, 12);       // dO is A along k (conflict free) and B from [k][n] (2-way)
+    ldS = pitchMod32(TkP, 4);         // P / dS   [TqP][TkP]
+    ldT = pitchMod32(TqP, 4);         // P^T / dS^T [TkP][TqP]
+  }
+  __host__ __device__ size_t floats() const {
+    return (size_t)TqP * ldQ + (size_t)TkP * ldK + (size_t)rowsV * ldV + (size_t)TqP * ldO + (size_t)TqP * ldS + (size_t)TkP * ldT + TqP;
+  }
+};
+
+__device__ __forceinline__ void emit2(float* p, float v0, float v1, bool accumulate) {
+  float2 v = make_float2(v0, v1);
+  if(accumulate) {
+    float2 o = *reinterpret_cast<const float2*>(p);
+    v.x += o.x;
+    v.y += o.y;
+  }
+  *reinterpret_cast<float2*>(p) = v;
+}
+
+template <bool X3>
+__global__ void __launch_bounds__(kAttnThreads) gAttentionBackwardMma(float* __restrict__ dq,
+                                                                      float* __restrict__ dk_,
+                                                                      float* __restrict__ dv,
+                                                                      const float* __restrict__ dout,
+                                                                      const float* __restrict__ out,
+                                                                      const float* __restrict__ probs,
+                                                                      const float* __restrict__ q,
+                                                                      const float* __restrict__ k,
+                                                                      const float* __restrict__ v,
+                                                                      AttnGeom g,
+                                                                      int accQ,
+                                                                      int accK,
+                                                                      int accV) {
+  extern __shared__ __align__(16) float smemF[];
+  const MmaLayoutBwd L(g);
+  float* sQ = smemF;
+  float* sK = sQ + L.TqP * L.ldQ;
+  float* sV = sK + L.TkP * L.ldK;
+  float* sdO = sV + L.rowsV * L.ldV;
+  float* sP = sdO + L.TqP * L.ldO;   // P, later dS
+  float* sPT = sP + L.TqP * L.ldS;   // P^T, later dS^T
+  float* sD = sPT + L.TkP * L.ldT;
+
+  const int b = blockIdx.x / g.H, h = blockIdx.x - b * g.H;
+  const int d = g.H * g.dk;
+  const size_t offQ = ((size_t)b * g.Tq) * d + h * g.dk;
+  const size_t offK = ((size_t)b * g.Tk) * d + h * g.dk;
+  loadHeadPadded(sQ, L.ldQ, q + offQ, g.Tq, L.TqP, g.dk, d);
+  loadHeadPadded(sK, L.ldK, k + offK, g.Tk, L.TkP, g.dk, d);
+  loadHeadPadded(sV, L.ldV, v + offK, g.Tk, L.TkP, g.dk, d);
+  loadHeadPadded(sdO, L.ldO, dout + offQ, g.Tq, L.TqP, g.dk, d);
+  const float* pb = probs + (((size_t)b * g.H + h) * g.Tq) * g.Tk;
+  for(int e = threadIdx.x; e < L.TqP * L.TkP; e += blockDim.x) {
+    int i = e / L.TkP, j = e - i * L.TkP;
+    if(i < g.Tq && j < g.Tk)
+      cpAsync4(sP + i * L.ldS + j, pb + i * g.Tk + j);
+    else
+      sP[i * L.ldS + j] = 0.f;
+  }
+  cpAsyncWaitAll();
+  __syncthreads();
+  // explicit transposed copy: P^T is the A operand of dV = P^T dO
+  for(int e = threadIdx.x; e < L.TqP * L.TkP; e += blockDim.x) {
+    int j = e / L.TqP, i = e - j * L.TqP;
+    sPT[j * L.ldT + i] = sP[i * L.ldS + j];
+  }
+  // D_i = sum_c dO_ic O_ic (O from global memory)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  __syncthreads();
+  for(int i = warp; i < L.TqP; i += nwarps) {
+    float s = 0.f;
+    if(i < g.Tq) {
+      const float* orow = out + offQ + (size_t)i * d;
+      for(int c = lane; c < g.dk; c += 32)
+        s = fmaf(sdO[i * L.ldO + c], orow[c], s);
+    }
+    s = warpSum(s);
+    if(lane == 0)
+      sD[i] = s;
+  }
+
+  // dV = P^T dO
+  warpMmaProduct<false, X3>(sPT, L.ldT, sdO, L.ldO, L.TkP, g.dk, L.TqP, [&](int j, int c, float v0, float v1) {
+    if(j < g.Tk)
+      emit2(dv + offK + (size_t)j * d + c, v0, v1, accV != 0);
+  });
+  __syncthreads();
+
+  // dS = scale * P o (dO V^T - D), written over P and P^T (each element by its owner thread)
+  warpMmaProduct<true, X3>(sdO, L.ldO, sV, L.ldV, L.TqP, L.TkP, g.dk, [&](int i, int j, float v0, float v1) {
+    float2 p = *reinterpret_cast<const float2*>(sP + i * L.ldS + j);
+    float di = sD[i];
+    float s0 = p.x * (v0 - di) * g.scale, s1 = p.y * (v1 - di) * g.scale;
+    *reinterpret_cast<float2*>(sP + i * L.ldS + j) = make_float2(s0, s1);
+    sPT[j * L.ldT + i] = s0;
+    sPT[(j + 1) * L.ldT + i] = s1;
+  });
+  __syncthreads();
+
+  // dQ = dS K -> staged in the (idle) V tile;  dK = dS^T Q -> staged in the K tile once dQ is done
+  warpMmaProduct<false, X3>(sP, L.ldS, sK, L.ldK, L.TqP, g.dk, L.TkP, [&](int i, int c, float v0, float v1) {
+    *reinterpret_cast<float2*>(sV + i * L.ldV + c) = make_float2(v0, v1);
+  });
+  __syncthreads();
+  storeHead(dq + offQ, sV, L.ldV, g.Tq, g.dk, d, accQ != 0);
+  warpMmaProduct<false, X3>(sPT, L.ldT, sQ, L.ldQ, L.TkP, g.dk, L.TqP, [&](int j, int c, float v0, float v1) {
+    *reinterpret_cast<float2*>(sK + j * L.ldK + c) = make_float2(v0, v1);
+  });
+  __syncthreads();
+  storeHead(dk_ + offK, sK, L.ldK, g.Tk, g.dk, d, accK != 0);
+}
+
 size_t forwardSmem(const AttnGeom& g) {
   return ((size_t)(g.Tq + 2 * g.Tk) * (g.dk + 4) + (size_t)g.Tq * (pad4(g.Tk) + 1)) * sizeof(float);
 }
@@ -329,10 +683,41 @@ bool AttentionFusable(int Tq, int Tk, int dimModel, int heads) {
   return (g.dk % 4 == 0) && backwardSmem(g) <= kSmemLimit;
 }
 
-void MultiHeadAttention(Tensor out, Tensor probs, const Tensor q, const Tensor k, const Tensor v, const Tensor mask, int heads, float scale) {
+namespace {
+template <class Kernel>
+void ensureSmem(Kernel kernel, size_t smem, size_t& configured) {
+  if(smem > configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)std::max(smem, (size_t)48 * 1024)));
+    configured = smem;
+  }
+}
+}  // namespace
+
+// exact = true: 3xTF32 products (fp32-grade, for the fp32 / bf16x3 GEMM modes);
+// exact = false: plain tf32 operands, matching the precision of the tf32 / bf16 GEMM modes
+void MultiHeadAttention(Tensor out, Tensor probs, const Tensor q, const Tensor k, const Tensor v, const Tensor mask, int heads, float scale, bool exact) {
   device::setDevice(out->getDevice());
   out->takeLazyZero();
   AttnGeom g = geometry(q, k, mask, heads, scale);
+  {
+    MmaLayoutFwd L(g);
+    size_t smemMma = L.floats() * sizeof(float);
+    static const bool forceSimt = std::getenv("MRN_ATTENTION_SIMT") != nullptr;
+    if(!forceSimt && g.dk % 8 == 0 && smemMma <= kSmemLimit) {
+      static size_t cfgExact = 0, cfgFast = 0;
+      float* pp = probs ? probs->data() : nullptr;
+      const float* mp = mask ? mask->data() : nullptr;
+      if(exact) {
+        ensureSmem(gAttentionForwardMma<true>, smemMma, cfgExact);
+        gAttentionForwardMma<true><<<g.B * g.H, kAttnThreads, smemMma, cudaStreamOfEngine()>>>(out->data(), pp, q->data(), k->data(), v->data(), mp, g);
+      } else {
+        ensureSmem(gAttentionForwardMma<false>, smemMma, cfgFast);
+        gAttentionForwardMma<false><<<g.B * g.H, kAttnThreads, smemMma, cudaStreamOfEngine()>>>(out->data(), pp, q->data(), k->data(), v->data(), mp, g);
+      }
+      CUDA_LAUNCH_CHECK();
+      return;
+    }
+  }
   size_t smem = forwardSmem(g);
   ABORT_IF(g.dk % 4 != 0 || smem > kSmemLimit, "attention: shape not supported by the fused kernel", g.Tq, g.Tk, g.dk);
   static size_t configured = 0;
@@ -345,7 +730,7 @@ void MultiHeadAttention(Tensor out, Tensor probs, const Tensor q, const Tensor k
   CUDA_LAUNCH_CHECK();
 }
 
-void MultiHeadAttentionGrad(Tensor dq, Tensor dk, Tensor dv, const Tensor adj, const Tensor out, const Tensor probs, const Tensor q, const Tensor k, const Tensor v, int heads, float scale) {
+void MultiHeadAttentionGrad(Tensor dq, Tensor dk, Tensor dv, const Tensor adj, const Tensor out, const Tensor probs, const Tensor q, const Tensor k, const Tensor v, int heads, float scale, bool exact) {
   device::setDevice(adj->getDevice());
   // first writer assigns; tensors that alias (k and v from the same node) are written in the
   // order dV, dQ, dK inside the kernel, separated by block barriers, so the later one accumulates
@@ -353,6 +738,25 @@ void MultiHeadAttentionGrad(Tensor dq, Tensor dk, Tensor dv, const Tensor adj, c
   bool accQ = !dq->takeLazyZero();
   bool accK = !dk->takeLazyZero();
   AttnGeom g = geometry(q, k, nullptr, heads, scale);
+  {
+    MmaLayoutBwd L(g);
+    size_t smemMma = L.floats() * sizeof(float);
+    static const bool forceSimt = std::getenv("MRN_ATTENTION_SIMT") != nullptr;
+    if(!forceSimt && g.dk % 8 == 0 && smemMma <= kSmemLimit) {
+      static size_t cfgExact = 0, cfgFast = 0;
+      if(exact) {
+        ensureSmem(gAttentionBackwardMma<true>, smemMma, cfgExact);
+        gAttentionBackwardMma<true><<<g.B * g.H, kAttnThreads, smemMma, cudaStreamOfEngine()>>>(
+            dq->data(), dk->data(), dv->data(), adj->data(), out->data(), probs->data(), q->data(), k->data(), v->data(), g, accQ, accK, accV);
+      } else {
+        ensureSmem(gAttentionBackwardMma<false>, smemMma, cfgFast);
+        gAttentionBackwardMma<false><<<g.B * g.H, kAttnThreads, smemMma, cudaStreamOfEngine()>>>(
+            dq->data(), dk->data(), dv->data(), adj->data(), out->data(), probs->data(), q->data(), k->data(), v->data(), g, accQ, accK, accV);
+      }
+      CUDA_LAUNCH_CHECK();
+      return;
+    }
+  }
   size_t smem = backwardSmem(g);
   ABORT_IF(g.dk % 4 != 0 || smem > kSmemLimit, "attention backward: shape not supported by the fused kernel", g.Tq, g.Tk, g.dk);
   static size_t configured = 0;

@@ -109,8 +109,10 @@ void AttBack(Tensor gva, Tensor gContext, Tensor gState, Tensor va, Tensor conte
 // for the backward pass (may be null in inference).  Grad ACCUMULATES into dq/dk/dv unless the
 // respective tensor is lazily zero (then it assigns).
 bool AttentionFusable(int Tq, int Tk, int dimModel, int heads);
-void MultiHeadAttention(Tensor out, Tensor probs, const Tensor q, const Tensor k, const Tensor v, const Tensor mask, int heads, float scale);
-void MultiHeadAttentionGrad(Tensor dq, Tensor dk, Tensor dv, const Tensor adj, const Tensor out, const Tensor probs, const Tensor q, const Tensor k, const Tensor v, int heads, float scale);
+// `exact`: the products inside run as 3xTF32 (fp32-grade) when true, as plain tf32 when false
+// (the graph node passes false in the tf32 / bf16 GEMM modes).
+void MultiHeadAttention(Tensor out, Tensor probs, const Tensor q, const Tensor k, const Tensor v, const Tensor mask, int heads, float scale, bool exact = true);
+void MultiHeadAttentionGrad(Tensor dq, Tensor dk, Tensor dv, const Tensor adj, const Tensor out, const Tensor probs, const Tensor q, const Tensor k, const Tensor v, int heads, float scale, bool exact = true);
 
 // `residual` (optional, this repo's addition): normalise in + residual, i.e. the "add the
 // residual, then layer-norm" tail of every Transformer sub-layer (src/models/transformer.h:97-126)

@@ -779,7 +779,7 @@ bool AttentionFusable(int, int, int dimModel, int heads) {
   return heads > 0 && dimModel % heads == 0;
 }
 
-void MultiHeadAttention(Tensor out, Tensor probs, const Tensor q, const Tensor k, const Tensor v, const Tensor mask, int heads, float scale) {
+void MultiHeadAttention(Tensor out, Tensor probs, const Tensor q, const Tensor k, const Tensor v, const Tensor mask, int heads, float scale, bool) {
   AttnDims g = attnDims(q, k, mask, heads);
   const float* Q = q->data();
   const float* K = k->data();
@@ -826,7 +826,7 @@ void MultiHeadAttention(Tensor out, Tensor probs, const Tensor q, const Tensor k
     }
 }
 
-void MultiHeadAttentionGrad(Tensor dq, Tensor dk, Tensor dv, const Tensor adj, const Tensor, const Tensor probs, const Tensor q, const Tensor k, const Tensor v, int heads, float scale) {
+void MultiHeadAttentionGrad(Tensor dq, Tensor dk, Tensor dv, const Tensor adj, const Tensor, const Tensor probs, const Tensor q, const Tensor k, const Tensor v, int heads, float scale, bool) {
   AttnDims g = attnDims(q, k, nullptr, heads);
   const float* Q = q->data();
   const float* K = k->data();

@@ -110,10 +110,10 @@ def _attn_set():
             lib.array(rnd(Bq, Tt, D)), lib.zeros((Bq, Tt, D)), lib.zeros((Bq, Tt, D)), lib.zeros((Bq, Tt, D)))
 amask = lib.array(np.zeros((Bq, 1, 1, Tt), dtype=np.float32))
 pool = pool_of(_attn_set, 9 * R * D * 4)
-mine = timeit(lambda s: lib.call("mrn_multi_head_attention", s[3].t(), s[4].t(), s[0].t(), s[1].t(), s[2].t(), amask.t(), Hh, 0.125), pool)
+mine = timeit(lambda s: lib.call("mrn_multi_head_attention", s[3].t(), s[4].t(), s[0].t(), s[1].t(), s[2].t(), amask.t(), Hh, 0.125, 0), pool)
 # algorithmic bytes: q, k, v in; out and probs out
 report("MultiHeadAttention fwd B64 H8 T50 dk64 (fused; reference = 9 kernels)", (4 * R * D + Bq * Hh * Tt * Tt) * 4, mine, None)
-mine = timeit(lambda s: lib.call("mrn_multi_head_attention_grad", s[6].t(), s[7].t(), s[8].t(), s[5].t(), s[3].t(), s[4].t(), s[0].t(), s[1].t(), s[2].t(), Hh, 0.125), pool)
+mine = timeit(lambda s: lib.call("mrn_multi_head_attention_grad", s[6].t(), s[7].t(), s[8].t(), s[5].t(), s[3].t(), s[4].t(), s[0].t(), s[1].t(), s[2].t(), Hh, 0.125, 0), pool)
 # q, k, v, out, dout, probs in; dq, dk, dv read + written
 report("MultiHeadAttentionGrad B64 H8 T50 dk64 (fused)", (11 * R * D + Bq * Hh * Tt * Tt) * 4, mine, None)
 del pool

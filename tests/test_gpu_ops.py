@@ -264,7 +264,8 @@ def _attention_numpy(q, k, v, mask, heads, scale):
     (2, 16, 80, 80, 64, "causal"),    # config E head shape
     (2, 3, 128, 128, 64, "key"),      # largest supported sequence
 ])
-def test_multi_head_attention(cuda, oracle, B, H, Tq, Tk, dk, mask_kind):
+@pytest.mark.parametrize("exact,tol", [(1, 3e-5), (0, 3e-3)], ids=["3xtf32", "tf32"])
+def test_multi_head_attention(cuda, oracle, B, H, Tq, Tk, dk, mask_kind, exact, tol):
     d = H * dk
     q, k, v = rnd(1, B, Tq, d), rnd(2, B, Tk, d), rnd(3, B, Tk, d)
     adj = rnd(4, B, Tq, d)
@@ -286,18 +287,18 @@ def test_multi_head_attention(cuda, oracle, B, H, Tq, Tk, dk, mask_kind):
         out, probs = lib.zeros((B, Tq, d)), lib.zeros((B, H, Tq, Tk))
         qa, ka, va = lib.array(q), lib.array(k), lib.array(v)
         mt = lib.array(mask).t() if mask is not None else None
-        lib.call("mrn_multi_head_attention", out.t(), probs.t(), qa.t(), ka.t(), va.t(), mt, H, scale)
+        lib.call("mrn_multi_head_attention", out.t(), probs.t(), qa.t(), ka.t(), va.t(), mt, H, scale, exact)
         dq, dk_, dv = lib.array(rnd(6, B, Tq, d)), lib.array(rnd(7, B, Tk, d)), lib.array(rnd(8, B, Tk, d))
-        lib.call("mrn_multi_head_attention_grad", dq.t(), dk_.t(), dv.t(), lib.array(adj).t(), out.t(), probs.t(), qa.t(), ka.t(), va.t(), H, scale)
+        lib.call("mrn_multi_head_attention_grad", dq.t(), dk_.t(), dv.t(), lib.array(adj).t(), out.t(), probs.t(), qa.t(), ka.t(), va.t(), H, scale, exact)
         return {"out": out.numpy(), "probs": probs.numpy(), "dq": dq.numpy(), "dk": dk_.numpy(), "dv": dv.numpy()}
 
     got, exp = both(cuda, oracle, fn)
     for key in exp:
-        close(got[key], exp[key], 3e-5, key)
+        close(got[key], exp[key], tol, key)
     # independent float64 statement
     o, p, (qh, kh, vh) = _attention_numpy(q, k, v, mask, H, scale)
-    close(got["out"], o, 3e-5, "out vs numpy")
-    close(got["probs"], p, 3e-5, "probs vs numpy")
+    close(got["out"], o, tol, "out vs numpy")
+    close(got["probs"], p, tol, "probs vs numpy")
     do = adj.reshape(B, Tq, H, dk).transpose(0, 2, 1, 3).astype(np.float64)
     dv = p.transpose(0, 1, 3, 2) @ do
     dp = do @ vh.transpose(0, 1, 3, 2)
@@ -305,9 +306,9 @@ def test_multi_head_attention(cuda, oracle, B, H, Tq, Tk, dk, mask_kind):
     dq = scale * ds @ kh
     dk_ = scale * ds.transpose(0, 1, 3, 2) @ qh
     join = lambda x, T: x.transpose(0, 2, 1, 3).reshape(B, T, d)  # noqa: E731
-    close(got["dq"], join(dq, Tq) + rnd(6, B, Tq, d), 3e-5, "dq vs numpy")
-    close(got["dk"], join(dk_, Tk) + rnd(7, B, Tk, d), 3e-5, "dk vs numpy")
-    close(got["dv"], join(dv, Tk) + rnd(8, B, Tk, d), 3e-5, "dv vs numpy")
+    close(got["dq"], join(dq, Tq) + rnd(6, B, Tq, d), tol, "dq vs numpy")
+    close(got["dk"], join(dk_, Tk) + rnd(7, B, Tk, d), tol, "dk vs numpy")
+    close(got["dv"], join(dv, Tk) + rnd(8, B, Tk, d), tol, "dv vs numpy")
 
 
 def test_layer_norm_reference_golden_input(cuda, oracle, goldens):
