@@ -454,6 +454,7 @@ __global__ void __launch_bounds__(kAttnThreads) gAttentionForwardMma(float* __re
                                                                      const float* __restrict__ mask,
                                                                      AttnGeom g) {
   extern __shared__ __align__(16) float smemF[];
+  pdlEnter();
   const MmaLayoutFwd L(g);
   float* sQ = smemF;
   float* sK = sQ + L.TqP * L.ldQ;
@@ -564,6 +565,7 @@ __global__ void __launch_bounds__(kAttnThreads) gAttentionBackwardMma(float* __r
                                                                       int accK,
                                                                       int accV) {
   extern __shared__ __align__(16) float smemF[];
+  pdlEnter();
   const MmaLayoutBwd L(g);
   float* sQ = smemF;
   float* sK = sQ + L.TqP * L.ldQ;
@@ -709,10 +711,10 @@ void MultiHeadAttention(Tensor out, Tensor probs, const Tensor q, const Tensor k
       const float* mp = mask ? mask->data() : nullptr;
       if(exact) {
         ensureSmem(gAttentionForwardMma<true>, smemMma, cfgExact);
-        gAttentionForwardMma<true><<<g.B * g.H, kAttnThreads, smemMma, cudaStreamOfEngine()>>>(out->data(), pp, q->data(), k->data(), v->data(), mp, g);
+        launchPdl(gAttentionForwardMma<true>, dim3(g.B * g.H), dim3(kAttnThreads), smemMma, cudaStreamOfEngine(), out->data(), pp, q->data(), k->data(), v->data(), mp, g);
       } else {
         ensureSmem(gAttentionForwardMma<false>, smemMma, cfgFast);
-        gAttentionForwardMma<false><<<g.B * g.H, kAttnThreads, smemMma, cudaStreamOfEngine()>>>(out->data(), pp, q->data(), k->data(), v->data(), mp, g);
+        launchPdl(gAttentionForwardMma<false>, dim3(g.B * g.H), dim3(kAttnThreads), smemMma, cudaStreamOfEngine(), out->data(), pp, q->data(), k->data(), v->data(), mp, g);
       }
       CUDA_LAUNCH_CHECK();
       return;
@@ -746,12 +748,12 @@ void MultiHeadAttentionGrad(Tensor dq, Tensor dk, Tensor dv, const Tensor adj, c
       static size_t cfgExact = 0, cfgFast = 0;
       if(exact) {
         ensureSmem(gAttentionBackwardMma<true>, smemMma, cfgExact);
-        gAttentionBackwardMma<true><<<g.B * g.H, kAttnThreads, smemMma, cudaStreamOfEngine()>>>(
-            dq->data(), dk->data(), dv->data(), adj->data(), out->data(), probs->data(), q->data(), k->data(), v->data(), g, accQ, accK, accV);
+        launchPdl(gAttentionBackwardMma<true>, dim3(g.B * g.H), dim3(kAttnThreads), smemMma, cudaStreamOfEngine(), dq->data(), dk->data(), dv->data(), (const float*)adj->data(),
+                  (const float*)out->data(), (const float*)probs->data(), (const float*)q->data(), (const float*)k->data(), (const float*)v->data(), g, (int)accQ, (int)accK, (int)accV);
       } else {
         ensureSmem(gAttentionBackwardMma<false>, smemMma, cfgFast);
-        gAttentionBackwardMma<false><<<g.B * g.H, kAttnThreads, smemMma, cudaStreamOfEngine()>>>(
-            dq->data(), dk->data(), dv->data(), adj->data(), out->data(), probs->data(), q->data(), k->data(), v->data(), g, accQ, accK, accV);
+        launchPdl(gAttentionBackwardMma<false>, dim3(g.B * g.H), dim3(kAttnThreads), smemMma, cudaStreamOfEngine(), dq->data(), dk->data(), dv->data(), (const float*)adj->data(),
+                  (const float*)out->data(), (const float*)probs->data(), (const float*)q->data(), (const float*)k->data(), (const float*)v->data(), g, (int)accQ, (int)accK, (int)accV);
       }
       CUDA_LAUNCH_CHECK();
       return;

@@ -52,6 +52,7 @@ struct RowGeom {
 // MODE 2: Add into a lazily-zero output, out = scale f(ins) (first writer assigns)
 template <int K, int MODE, bool VEC, class Functor>
 __global__ void __launch_bounds__(256) gElementwise(Functor f, float* __restrict__ out, Operands<K> ops, RowGeom g, float scale) {
+  pdlEnter();
   const int cpr = (g.cols + 3) >> 2;  // 4-element chunks per row
   const long long items = (long long)g.rows * cpr;
   for(long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < items; w += (long long)gridDim.x * blockDim.x) {
@@ -130,6 +131,7 @@ __global__ void __launch_bounds__(256) gElementwise(Functor f, float* __restrict
 // case (1): out[row] += scale * sum_c f(ins[row, c]); one warp per row
 template <int K, class Functor>
 __global__ void __launch_bounds__(256) gAddReduceRows(Functor f, float* __restrict__ out, Operands<K> ops, RowGeom g, float scale, int assign) {
+  pdlEnter();
   int warpsPerBlock = blockDim.x >> 5;
   int lane = threadIdx.x & 31;
   for(int row = blockIdx.x * warpsPerBlock + (threadIdx.x >> 5); row < g.rows; row += gridDim.x * warpsPerBlock) {
@@ -161,6 +163,7 @@ __global__ void __launch_bounds__(256) gAddReduceRows(Functor f, float* __restri
 // and leave through ONE atomicAdd per column and slice.
 template <int K, class Functor>
 __global__ void __launch_bounds__(256) gAddColumns(Functor f, float* __restrict__ out, Operands<K> ops, RowGeom g, float scale, int rowsPerSlice, int assign) {
+  pdlEnter();
   __shared__ float red[8][32][5];
   const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
   const int r0 = blockIdx.y * rowsPerSlice;
@@ -235,6 +238,7 @@ struct FullOperands {
 // case (3): thread per output element, reduced sub-space split over blockIdx.y
 template <int K, class Functor>
 __global__ void __launch_bounds__(128) gAddGeneric(Functor f, float* __restrict__ out, FullOperands<K> ops, GenericGeom g, float scale) {
+  pdlEnter();
   int o = blockIdx.x * blockDim.x + threadIdx.x;
   if(o >= g.outLength)
     return;
@@ -363,9 +367,9 @@ void Element(Functor functor, Tensor out, Tensors... tensors) {
   int grid = gridFor((size_t)items, 256);
   auto stream = cudaStreamOfEngine();
   if(vec)
-    ew::gElementwise<K, 0, true><<<grid, 256, 0, stream>>>(functor, out->data(), ops, g, 1.f);
+    launchPdl(ew::gElementwise<K, 0, true, Functor>, dim3(grid), dim3(256), 0, stream, functor, out->data(), ops, g, 1.f);
   else
-    ew::gElementwise<K, 0, false><<<grid, 256, 0, stream>>>(functor, out->data(), ops, g, 1.f);
+    launchPdl(ew::gElementwise<K, 0, false, Functor>, dim3(grid), dim3(256), 0, stream, functor, out->data(), ops, g, 1.f);
   CUDA_LAUNCH_CHECK();
 }
 
@@ -392,7 +396,7 @@ void Add(Functor functor, float scale, Tensor out, Tensors... tensors) {
     int grid = gridFor((size_t)g.rows * 32, 256);
     (void)warpsPerBlock;
     int assign = out->takeLazyZero() ? 1 : 0;
-    ew::gAddReduceRows<K><<<grid, 256, 0, stream>>>(functor, out->data(), ops, g, scale, assign);
+    launchPdl(ew::gAddReduceRows<K, Functor>, dim3(grid), dim3(256), 0, stream, functor, out->data(), ops, g, scale, assign);
   } else if(outS == full) {
     // (2) element-wise accumulate
     bool broadcast = false;
@@ -409,13 +413,13 @@ void Add(Functor functor, float scale, Tensor out, Tensors... tensors) {
     int grid = gridFor((size_t)items, 256);
     if(assign) {
       if(vec)
-        ew::gElementwise<K, 2, true><<<grid, 256, 0, stream>>>(functor, out->data(), ops, g, scale);
+        launchPdl(ew::gElementwise<K, 2, true, Functor>, dim3(grid), dim3(256), 0, stream, functor, out->data(), ops, g, scale);
       else
-        ew::gElementwise<K, 2, false><<<grid, 256, 0, stream>>>(functor, out->data(), ops, g, scale);
+        launchPdl(ew::gElementwise<K, 2, false, Functor>, dim3(grid), dim3(256), 0, stream, functor, out->data(), ops, g, scale);
     } else if(vec)
-      ew::gElementwise<K, 1, true><<<grid, 256, 0, stream>>>(functor, out->data(), ops, g, scale);
+      launchPdl(ew::gElementwise<K, 1, true, Functor>, dim3(grid), dim3(256), 0, stream, functor, out->data(), ops, g, scale);
     else
-      ew::gElementwise<K, 1, false><<<grid, 256, 0, stream>>>(functor, out->data(), ops, g, scale);
+      launchPdl(ew::gElementwise<K, 1, false, Functor>, dim3(grid), dim3(256), 0, stream, functor, out->data(), ops, g, scale);
   } else if(outS.d[0] == 1 && outS.d[1] == 1 && outS.d[2] == 1 && outS.d[3] == full.d[3] && (full.d[3] & 3) == 0 && ew::aligned16(out->memory()->data())
             && [&] {
                  for(int k = 0; k < K; ++k) {
@@ -435,7 +439,7 @@ void Add(Functor functor, float scale, Tensor out, Tensors... tensors) {
     int rowsPerSlice = (g.rows + slices - 1) / slices;
     slices = (g.rows + rowsPerSlice - 1) / rowsPerSlice;
     int assign = (slices == 1 && out->takeLazyZero()) ? 1 : 0;
-    ew::gAddColumns<K><<<dim3(strips, slices), dim3(32, 8), 0, stream>>>(functor, out->data(), ops, g, scale, rowsPerSlice, assign);
+    launchPdl(ew::gAddColumns<K, Functor>, dim3(strips, slices), dim3(32, 8), 0, stream, functor, out->data(), ops, g, scale, rowsPerSlice, assign);
   } else {
     // (3) generic reduction over the dims where out has extent 1
     ew::FullOperands<K> ops;
@@ -462,7 +466,7 @@ void Add(Functor functor, float scale, Tensor out, Tensors... tensors) {
     g.atomic = slices > 1;
     g.assign = (!g.atomic && out->takeLazyZero()) ? 1 : 0;
     dim3 grid(blocksX, slices);
-    ew::gAddGeneric<K><<<grid, 128, 0, stream>>>(functor, out->data(), ops, g, scale);
+    launchPdl(ew::gAddGeneric<K, Functor>, grid, dim3(128), 0, stream, functor, out->data(), ops, g, scale);
   }
   CUDA_LAUNCH_CHECK();
 }

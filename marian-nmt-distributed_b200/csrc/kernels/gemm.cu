@@ -852,6 +852,7 @@ __global__ void __launch_bounds__(192) gGemmTf32(const __grid_constant__ CUtenso
   uint64_t* tmemFullBar = emptyBar + STAGES;
   uint32_t* tmemHolder = (uint32_t*)(tmemFullBar + 1);
 
+  pdlTrigger();  // the next kernel may start launching; it waits for our completion in its own pdlWait()
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
@@ -880,6 +881,9 @@ __global__ void __launch_bounds__(192) gGemmTf32(const __grid_constant__ CUtenso
   __syncthreads();
   tcgenFenceAfter();
   const uint32_t tmemBase = *tmemHolder;
+  // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the tail
+  // of the previous kernel; operands and C are only touched from here on
+  pdlWait();
 
   if(warp == 0) {
     if(lane == 0) {
@@ -1110,8 +1114,7 @@ void launchTf32(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a,
     configured = true;
   }
   dim3 grid((a.M + BLOCK_M - 1) / BLOCK_M, (a.N + BN - 1) / BN, batches * a.splits);
-  gGemmTf32<BN, STAGES, A_MN, B_MN><<<grid, 192, L::TOTAL, cudaStreamOfEngine()>>>(tmA, tmB, a);
-  CUDA_LAUNCH_CHECK();
+  launchPdl(gGemmTf32<BN, STAGES, A_MN, B_MN>, grid, dim3(192), (size_t)L::TOTAL, cudaStreamOfEngine(), tmA, tmB, a);
 }
 
 template <bool A_MN, bool B_MN>

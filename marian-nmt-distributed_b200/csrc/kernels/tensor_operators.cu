@@ -280,6 +280,7 @@ __device__ __forceinline__ void rowStats(const float* __restrict__ sp, int cols,
 
 template <bool WARP, bool VEC>
 __global__ void gCrossEntropyPick(float* __restrict__ out, const float* __restrict__ in, const float* __restrict__ pick, int rows, int cols) {
+  pdlEnter();
   __shared__ float smem[32];
   typedef RowCtx<WARP> R;
   for(int j = R::firstRow(); j < rows; j += R::rowStride()) {
@@ -297,6 +298,7 @@ __global__ void gCrossEntropyPick(float* __restrict__ out, const float* __restri
 
 template <bool WARP, bool VEC>
 __global__ void gCrossEntropyPickBackward(float* __restrict__ out, const float* __restrict__ adj, const float* __restrict__ in, const float* __restrict__ pick, int rows, int cols, int assign) {
+  pdlEnter();
   __shared__ float smem[32];
   typedef RowCtx<WARP> R;
   for(int j = R::firstRow(); j < rows; j += R::rowStride()) {
@@ -345,7 +347,7 @@ void CrossEntropyPick(Tensor out, Tensor in, Tensor pick) {
   auto l = rowLaunch(rows, cols);
   bool vec = rowsVectorizable(in->data(), nullptr, cols);
   auto st = cudaStreamOfEngine();
-#define CE_FWD(W, V) gCrossEntropyPick<W, V><<<l.grid, l.block, 0, st>>>(out->data(), in->data(), pick->data(), rows, cols)
+#define CE_FWD(W, V) launchPdl(gCrossEntropyPick<W, V>, dim3(l.grid), dim3(l.block), 0, st, out->data(), (const float*)in->data(), (const float*)pick->data(), rows, cols)
   if(l.warp) {
     if(vec) CE_FWD(true, true); else CE_FWD(true, false);
   } else {
@@ -363,7 +365,7 @@ void CrossEntropyPickBackward(Tensor out, Tensor adj, Tensor a, Tensor pick) {
   int assign = out->takeLazyZero() ? 1 : 0;  // first writer of the logits adjoint: no memset, no read-back
   bool vec = rowsVectorizable(a->data(), out->data(), cols);
   auto st = cudaStreamOfEngine();
-#define CE_BWD(W, V) gCrossEntropyPickBackward<W, V><<<l.grid, l.block, 0, st>>>(out->data(), adj->data(), a->data(), pick->data(), rows, cols, assign)
+#define CE_BWD(W, V) launchPdl(gCrossEntropyPickBackward<W, V>, dim3(l.grid), dim3(l.block), 0, st, out->data(), (const float*)adj->data(), (const float*)a->data(), (const float*)pick->data(), rows, cols, assign)
   if(l.warp) {
     if(vec) CE_BWD(true, true); else CE_BWD(true, false);
   } else {
@@ -483,6 +485,7 @@ __global__ void __launch_bounds__(128) gLayerNormalizationGrad(float* __restrict
 // from HBM exactly once and all row statistics are shuffle reductions (no __syncthreads).
 template <int VPL>
 __global__ void __launch_bounds__(256) gLNormalizationWarp(float* __restrict__ out, const float* __restrict__ in, const float* __restrict__ res, const float* __restrict__ alpha, const float* __restrict__ beta, int rows, int cols, float eps) {
+  pdlEnter();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   float4 g4[VPL], b4[VPL];
@@ -562,6 +565,7 @@ __global__ void __launch_bounds__(256) gLayerNormalizationGradWarp(float* __rest
                                                                    const float* __restrict__ res,
                                                                    float* __restrict__ gradRes,
                                                                    int assignRes) {
+  pdlEnter();
   __shared__ float4 red[8][32 * VPL];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -710,9 +714,9 @@ void LayerNormalization(Tensor out, Tensor in, Tensor gamma, Tensor beta, float 
     int grid = std::max(1, std::min((rows + 7) / 8, kNumSMs * 4));
     auto st = cudaStreamOfEngine();
     if(cols <= 512)
-      gLNormalizationWarp<4><<<grid, 256, 0, st>>>(out->data(), in->data(), rp, gamma->data(), bp, rows, cols, eps);
+      launchPdl(gLNormalizationWarp<4>, dim3(grid), dim3(256), 0, st, out->data(), (const float*)in->data(), rp, (const float*)gamma->data(), bp, rows, cols, eps);
     else
-      gLNormalizationWarp<8><<<grid, 256, 0, st>>>(out->data(), in->data(), rp, gamma->data(), bp, rows, cols, eps);
+      launchPdl(gLNormalizationWarp<8>, dim3(grid), dim3(256), 0, st, out->data(), (const float*)in->data(), rp, (const float*)gamma->data(), bp, rows, cols, eps);
     CUDA_LAUNCH_CHECK();
     return;
   }
@@ -740,9 +744,11 @@ void LayerNormalizationGrad(Tensor gradX, Tensor gradGamma, Tensor gradBeta, Ten
       // few, fat blocks: every block ends with one atomic per column for gamma and beta
       int grid = std::max(1, std::min((rows + 15) / 16, kNumSMs * 2));
       if(cols <= 512)
-        gLayerNormalizationGradWarp<4><<<grid, 256, 0, st>>>(gradX->data(), gradGamma->data(), gbp, adj->data(), y->data(), x->data(), gamma->data(), bp, rows, cols, eps, assignX, rp, grp, assignRes);
+        launchPdl(gLayerNormalizationGradWarp<4>, dim3(grid), dim3(256), 0, st, gradX->data(), gradGamma->data(), gbp, (const float*)adj->data(), (const float*)y->data(), (const float*)x->data(),
+                  (const float*)gamma->data(), bp, rows, cols, eps, assignX, rp, grp, assignRes);
       else
-        gLayerNormalizationGradWarp<8><<<grid, 256, 0, st>>>(gradX->data(), gradGamma->data(), gbp, adj->data(), y->data(), x->data(), gamma->data(), bp, rows, cols, eps, assignX, rp, grp, assignRes);
+        launchPdl(gLayerNormalizationGradWarp<8>, dim3(grid), dim3(256), 0, st, gradX->data(), gradGamma->data(), gbp, (const float*)adj->data(), (const float*)y->data(), (const float*)x->data(),
+                  (const float*)gamma->data(), bp, rows, cols, eps, assignX, rp, grp, assignRes);
       CUDA_LAUNCH_CHECK();
       return;
     }
@@ -1273,6 +1279,7 @@ __global__ void gTransposeGeneric(float* __restrict__ out, const float* __restri
 // permutations that keep the last axis (e.g. {0,2,1,3}: head split/join,
 // time<->batch): whole rows move, four floats per thread
 __global__ void gTransposeRows4(float4* __restrict__ out, const float4* __restrict__ in, Shape4 os, Shape4 is, Perm permute, int cols4) {
+  pdlEnter();
   long long items = (long long)os.d[0] * os.d[1] * os.d[2] * cols4;
   for(long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < items; w += (long long)gridDim.x * blockDim.x) {
     int c = (int)(w % cols4);
@@ -1355,6 +1362,7 @@ void copyBlock(float* wide, float* narrow, int rows, int width, int outWidth, in
 
 template <bool SCATTER>
 __global__ void gRows(float* __restrict__ out, const float* __restrict__ in, int cols, const int* __restrict__ idx, int rows) {
+  pdlEnter();
   // one warp per row; SCATTER: out[idx[j]] += in[j] (atomic, rows may repeat)
   int warpsPerBlock = blockDim.x >> 5;
   int lane = threadIdx.x & 31;
@@ -1380,6 +1388,7 @@ __global__ void gRows(float* __restrict__ out, const float* __restrict__ in, int
 }
 
 __global__ void gShift(float* __restrict__ out, const float* __restrict__ in, int length, int offset) {
+  pdlEnter();
   for(int index = blockIdx.x * blockDim.x + threadIdx.x; index < length; index += gridDim.x * blockDim.x) {
     if(index - offset < 0 || index - offset >= length)
       out[index] = 0;
@@ -1447,7 +1456,7 @@ void TransposeND(Tensor out, Tensor in, const std::vector<int>& vAxis) {
   bool swapsLast2 = perm.p[0] == 0 && perm.p[1] == 1 && perm.p[2] == 3 && perm.p[3] == 2;
   if(keepsLast && os.d[3] % 4 == 0 && ((((uintptr_t)out->data()) | ((uintptr_t)in->data())) & 15) == 0) {
     int cols4 = os.d[3] / 4;
-    gTransposeRows4<<<gridFor((size_t)length / 4, 256), 256, 0, st>>>((float4*)out->data(), (const float4*)in->data(), os, is, perm, cols4);
+    launchPdl(gTransposeRows4, dim3(gridFor((size_t)length / 4, 256)), dim3(256), 0, st, (float4*)out->data(), (const float4*)in->data(), os, is, perm, cols4);
   } else if(swapsLast2) {
     int batch = is.d[0] * is.d[1], rows = is.d[2], cols = is.d[3];
     dim3 grid((cols + 31) / 32, (rows + 31) / 32, batch);
@@ -1492,14 +1501,14 @@ void Deconcatenate(std::vector<Tensor>& outputs, const Tensor in, int ax) {
 void CopyRows(Tensor out, const Tensor in, const int* deviceIndices, size_t n) {
   device::setDevice(out->getDevice());
   int cols = in->shape().back();
-  gRows<false><<<gridFor(n * 32, 256), 256, 0, cudaStreamOfEngine()>>>(out->data(), in->data(), cols, deviceIndices, (int)n);
+  launchPdl(gRows<false>, dim3(gridFor(n * 32, 256)), dim3(256), 0, cudaStreamOfEngine(), out->data(), (const float*)in->data(), cols, deviceIndices, (int)n);
   CUDA_LAUNCH_CHECK();
 }
 
 void PasteRows(Tensor out, const Tensor in, const int* deviceIndices, size_t n) {
   device::setDevice(out->getDevice());
   int cols = in->shape().back();
-  gRows<true><<<gridFor(n * 32, 256), 256, 0, cudaStreamOfEngine()>>>(out->data(), in->data(), cols, deviceIndices, (int)n);
+  launchPdl(gRows<true>, dim3(gridFor(n * 32, 256)), dim3(256), 0, cudaStreamOfEngine(), out->data(), (const float*)in->data(), cols, deviceIndices, (int)n);
   CUDA_LAUNCH_CHECK();
 }
 
@@ -1556,7 +1565,7 @@ void Shift(Tensor out, Tensor in, Shape shift, bool invert) {
     offset = -offset;
   out->takeLazyZero();  // assigns every element
   int length = out->shape().elements();
-  gShift<<<gridFor(length, 256), 256, 0, cudaStreamOfEngine()>>>(out->data(), in->data(), length, offset);
+  launchPdl(gShift, dim3(gridFor(length, 256)), dim3(256), 0, cudaStreamOfEngine(), out->data(), (const float*)in->data(), length, offset);
   CUDA_LAUNCH_CHECK();
 }
 
@@ -1568,6 +1577,7 @@ void Shift(Tensor out, Tensor in, Shape shift, bool invert) {
 namespace {
 
 __global__ void __launch_bounds__(256) gSumSquares(float* __restrict__ out, const float* __restrict__ in, size_t n) {
+  pdlEnter();
   __shared__ float smem[32];
   float acc = 0.f;
   size_t n4 = n >> 2;
@@ -1595,6 +1605,7 @@ __device__ __forceinline__ float clipScale(float gradScale, float clipNorm, cons
 }
 
 __global__ void __launch_bounds__(256) gAdam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n, AdamArgs a, const float* __restrict__ normSq) {
+  pdlEnter();
   float scale = clipScale(a.gradScale, a.clipNorm, normSq);
   size_t n4 = n >> 2;
   for(size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
@@ -1669,7 +1680,7 @@ void SumSquares(Tensor outScalar, Tensor in) {
   device::zero(outScalar->data(), sizeof(float));
   ABORT_IF(((uintptr_t)in->data() & 15) != 0, "SumSquares expects a 16-byte aligned tensor");
   int grid = std::max(1, std::min((int)((n / 4 + 255) / 256), kNumSMs * 8));
-  gSumSquares<<<grid, 256, 0, cudaStreamOfEngine()>>>(outScalar->data(), in->data(), n);
+  launchPdl(gSumSquares, dim3(grid), dim3(256), 0, cudaStreamOfEngine(), outScalar->data(), (const float*)in->data(), n);
   CUDA_LAUNCH_CHECK();
 }
 
@@ -1697,7 +1708,7 @@ void AdamUpdate(Tensor params, Tensor grads, Tensor mt, Tensor vt, const AdamArg
   ABORT_IF(grads->size() != n || mt->size() != n || vt->size() != n, "AdamUpdate: size mismatch");
   ABORT_IF(!all16({params->data(), grads->data(), mt->data(), vt->data()}), "AdamUpdate expects 16-byte aligned tensors");
   int grid = std::max(1, std::min((int)((n / 4 + 255) / 256), kNumSMs * 8));
-  gAdam<<<grid, 256, 0, cudaStreamOfEngine()>>>(params->data(), grads->data(), mt->data(), vt->data(), n, args, normSq ? normSq->data() : nullptr);
+  launchPdl(gAdam, dim3(grid), dim3(256), 0, cudaStreamOfEngine(), params->data(), (const float*)grads->data(), mt->data(), vt->data(), n, args, (const float*)(normSq ? normSq->data() : nullptr));
   CUDA_LAUNCH_CHECK();
 }
 
