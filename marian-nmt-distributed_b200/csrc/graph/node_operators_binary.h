@@ -206,16 +206,29 @@ struct DivNodeOp : public ElementBinaryNodeOp {
 // -log softmax(a)[b] per row; labels are a float tensor.  reference: :531-553
 struct CrossEntropyNodeOp : public NaryNodeOp {
   CrossEntropyNodeOp(Expr a, Expr b) : NaryNodeOp({a, b}, newShape(a)) {}
+  ~CrossEntropyNodeOp() {
+    auto g = graph();
+    if(stats_ && g)
+      g->free(stats_);
+  }
   static Shape newShape(Expr a) {
     Shape shape1 = a->shape();
     shape1.set(-1, 1);
     return shape1;
   }
-  NodeOps forwardOps() { return {NodeOp(CrossEntropyPick(val_, child(0)->val(), child(1)->val()))}; }
+  // the forward kernel leaves (max, sum exp) per row for the backward kernel
+  void forward() {
+    if(!stats_)
+      graph()->tensor(stats_, Shape{(int)val_->size(), 2});
+    CrossEntropyPick(val_, child(0)->val(), child(1)->val(), stats_);
+  }
   NodeOps backwardOps() {
-    return {NodeOp(CrossEntropyPickBackward(child(0)->grad(), adj_, child(0)->val(), child(1)->val()))};
+    return {NodeOp(CrossEntropyPickBackward(child(0)->grad(), adj_, child(0)->val(), child(1)->val(), stats_))};
   }
   const std::string type() { return "x-ent"; }
+
+private:
+  Tensor stats_;
 };
 
 // reference: :555-613.  backward() zeroes the child adjoints itself and

@@ -82,6 +82,11 @@ inline void launchPdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t sm
   CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...));
 }
 
+// one 128-bit reduction into L2 instead of four scalar atomics (sm_90+); p must be 16-byte aligned
+__device__ __forceinline__ void redAdd4(float* p, float4 v) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 __device__ __forceinline__ float warpSum(float v) {
 #pragma unroll
   for(int o = 16; o > 0; o >>= 1)

@@ -205,17 +205,20 @@ __global__ void __launch_bounds__(256) gAddColumns(Functor f, float* __restrict_
     red[threadIdx.y][threadIdx.x][e] = acc[e];
   __syncthreads();
   if(threadIdx.y == 0 && c < g.cols) {
+    float sum[4];
 #pragma unroll
     for(int e = 0; e < 4; ++e) {
-      float sum = 0.f;
+      sum[e] = 0.f;
 #pragma unroll
       for(int y = 0; y < 8; ++y)
-        sum += red[y][threadIdx.x][e];
-      if(assign)
-        out[c + e] = sum * scale;
-      else
-        atomicAdd(out + c + e, sum * scale);
+        sum[e] += red[y][threadIdx.x][e];
+      sum[e] *= scale;
     }
+    float4 v = make_float4(sum[0], sum[1], sum[2], sum[3]);
+    if(assign)
+      *reinterpret_cast<float4*>(out + c) = v;
+    else
+      redAdd4(out + c, v);  // out is 16-byte aligned (checked by the launcher)
   }
 }
 

@@ -279,7 +279,7 @@ __device__ __forceinline__ void rowStats(const float* __restrict__ sp, int cols,
 }
 
 template <bool WARP, bool VEC>
-__global__ void gCrossEntropyPick(float* __restrict__ out, const float* __restrict__ in, const float* __restrict__ pick, int rows, int cols) {
+__global__ void gCrossEntropyPick(float* __restrict__ out, const float* __restrict__ in, const float* __restrict__ pick, int rows, int cols, float* __restrict__ stats) {
   pdlEnter();
   __shared__ float smem[32];
   typedef RowCtx<WARP> R;
@@ -292,22 +292,31 @@ __global__ void gCrossEntropyPick(float* __restrict__ out, const float* __restri
     if(R::leader()) {
       int id = (int)pick[j];
       out[j] = logf(s) - sp[id] + M;
+      if(stats) {  // row max and sum of exponentials, reused by the backward pass
+        stats[2 * j] = M;
+        stats[2 * j + 1] = s;
+      }
     }
   }
 }
 
 template <bool WARP, bool VEC>
-__global__ void gCrossEntropyPickBackward(float* __restrict__ out, const float* __restrict__ adj, const float* __restrict__ in, const float* __restrict__ pick, int rows, int cols, int assign) {
+__global__ void gCrossEntropyPickBackward(float* __restrict__ out, const float* __restrict__ adj, const float* __restrict__ in, const float* __restrict__ pick, int rows, int cols, int assign, const float* __restrict__ stats) {
   pdlEnter();
   __shared__ float smem[32];
   typedef RowCtx<WARP> R;
   for(int j = R::firstRow(); j < rows; j += R::rowStride()) {
     const float* sp = in + (size_t)j * cols;
     float* so = out + (size_t)j * cols;
-    float m, s;
-    rowStats<VEC>(sp, cols, R::firstCol(), R::colStride(), m, s);
-    float M = R::max(m, smem);
-    s = R::sum(s * expf(m - M), smem);
+    float m, s, M;
+    if(stats) {  // forward pass left the row statistics: the logits are read once, not twice
+      M = stats[2 * j];
+      s = stats[2 * j + 1];
+    } else {
+      rowStats<VEC>(sp, cols, R::firstCol(), R::colStride(), m, s);
+      M = R::max(m, smem);
+      s = R::sum(s * expf(m - M), smem);
+    }
     int p = (int)pick[j];
     float a = adj[j];
     if(VEC) {
@@ -340,14 +349,15 @@ inline bool rowsVectorizable(const void* a, const void* b, int cols) {
 
 }  // namespace
 
-void CrossEntropyPick(Tensor out, Tensor in, Tensor pick) {
+void CrossEntropyPick(Tensor out, Tensor in, Tensor pick, Tensor stats) {
   device::setDevice(out->getDevice());
+  float* statsPtr = stats ? stats->data() : nullptr;
   int cols = in->shape().back();
   int rows = in->shape().elements() / cols;
   auto l = rowLaunch(rows, cols);
   bool vec = rowsVectorizable(in->data(), nullptr, cols);
   auto st = cudaStreamOfEngine();
-#define CE_FWD(W, V) launchPdl(gCrossEntropyPick<W, V>, dim3(l.grid), dim3(l.block), 0, st, out->data(), (const float*)in->data(), (const float*)pick->data(), rows, cols)
+#define CE_FWD(W, V) launchPdl(gCrossEntropyPick<W, V>, dim3(l.grid), dim3(l.block), 0, st, out->data(), (const float*)in->data(), (const float*)pick->data(), rows, cols, statsPtr)
   if(l.warp) {
     if(vec) CE_FWD(true, true); else CE_FWD(true, false);
   } else {
@@ -357,15 +367,16 @@ void CrossEntropyPick(Tensor out, Tensor in, Tensor pick) {
   CUDA_LAUNCH_CHECK();
 }
 
-void CrossEntropyPickBackward(Tensor out, Tensor adj, Tensor a, Tensor pick) {
+void CrossEntropyPickBackward(Tensor out, Tensor adj, Tensor a, Tensor pick, Tensor stats) {
   device::setDevice(out->getDevice());
+  const float* statsPtr = stats ? stats->data() : nullptr;
   int cols = out->shape().back();
   int rows = out->shape().elements() / cols;
   auto l = rowLaunch(rows, cols);
   int assign = out->takeLazyZero() ? 1 : 0;  // first writer of the logits adjoint: no memset, no read-back
   bool vec = rowsVectorizable(a->data(), out->data(), cols);
   auto st = cudaStreamOfEngine();
-#define CE_BWD(W, V) launchPdl(gCrossEntropyPickBackward<W, V>, dim3(l.grid), dim3(l.block), 0, st, out->data(), (const float*)adj->data(), (const float*)a->data(), (const float*)pick->data(), rows, cols, assign)
+#define CE_BWD(W, V) launchPdl(gCrossEntropyPickBackward<W, V>, dim3(l.grid), dim3(l.block), 0, st, out->data(), (const float*)adj->data(), (const float*)a->data(), (const float*)pick->data(), rows, cols, assign, statsPtr)
   if(l.warp) {
     if(vec) CE_BWD(true, true); else CE_BWD(true, false);
   } else {
@@ -687,10 +698,7 @@ __global__ void __launch_bounds__(256) gLayerNormalizationGradWarp(float* __rest
           sum.z += t.z;
           sum.w += t.w;
         }
-        atomicAdd(dst + c, sum.x);
-        atomicAdd(dst + c + 1, sum.y);
-        atomicAdd(dst + c + 2, sum.z);
-        atomicAdd(dst + c + 3, sum.w);
+        redAdd4(dst + c, sum);  // gamma / beta gradients are 16-byte aligned rows (checked by the launcher)
       }
     }
   }
@@ -736,13 +744,14 @@ void LayerNormalizationGrad(Tensor gradX, Tensor gradGamma, Tensor gradBeta, Ten
     bool aligned = (cols % 4 == 0)
                    && (((uintptr_t)gradX->memory()->data() | (uintptr_t)adj->data() | (uintptr_t)y->data() | (uintptr_t)x->data() | (uintptr_t)gamma->data() | (uintptr_t)bp) & 15) == 0;
     const float* rp = residual ? residual->data() : nullptr;
-    aligned = aligned && (((uintptr_t)rp | (uintptr_t)(gradResidual ? gradResidual->memory()->data() : nullptr)) & 15) == 0;
+    aligned = aligned && (((uintptr_t)rp | (uintptr_t)(gradResidual ? gradResidual->memory()->data() : nullptr) | (uintptr_t)gradGamma->data() | (uintptr_t)gbp) & 15) == 0;
     if(aligned && cols <= 1024) {
       int assignX = gradX->takeLazyZero() ? 1 : 0;
       int assignRes = (gradResidual && gradResidual->takeLazyZero()) ? 1 : 0;
       float* grp = gradResidual ? gradResidual->data() : nullptr;
-      // few, fat blocks: every block ends with one atomic per column for gamma and beta
-      int grid = std::max(1, std::min((rows + 15) / 16, kNumSMs * 2));
+      // few, fat blocks: every block ends with one 128-bit reduction per 4 columns for gamma and
+      // beta; same-address reductions serialise in L2, so one block per SM is the sweet spot
+      int grid = std::max(1, std::min((rows + 15) / 16, kNumSMs));
       if(cols <= 512)
         launchPdl(gLayerNormalizationGradWarp<4>, dim3(grid), dim3(256), 0, st, gradX->data(), gradGamma->data(), gbp, (const float*)adj->data(), (const float*)y->data(), (const float*)x->data(),
                   (const float*)gamma->data(), bp, rows, cols, eps, assignX, rp, grp, assignRes);

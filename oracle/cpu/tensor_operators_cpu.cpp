@@ -218,7 +218,7 @@ void LogSoftmaxGrad(Tensor grad, Tensor adj, Tensor val) {
 // ---------------------------------------------------------------------------
 // Cross entropy      reference: :1115-1283
 // ---------------------------------------------------------------------------
-void CrossEntropyPick(Tensor out, Tensor in, Tensor pick) {
+void CrossEntropyPick(Tensor out, Tensor in, Tensor pick, Tensor) {
   int cols = in->shape().back();
   int rows = in->shape().elements() / cols;
 #pragma omp parallel for if((long)rows * cols > 16384)
@@ -236,7 +236,7 @@ void CrossEntropyPick(Tensor out, Tensor in, Tensor pick) {
   }
 }
 
-void CrossEntropyPickBackward(Tensor out, Tensor adj, Tensor a, Tensor pick) {
+void CrossEntropyPickBackward(Tensor out, Tensor adj, Tensor a, Tensor pick, Tensor) {
   int cols = out->shape().back();
   int rows = out->shape().elements() / cols;
 #pragma omp parallel for if((long)rows * cols > 16384)

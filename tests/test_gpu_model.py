@@ -149,3 +149,24 @@ def test_transformer_base_full_size_properties(cuda, pkg):
     assert np.allclose(costs[1], costs[2], rtol=2e-2), costs
     # tf32 (headline mode) vs bf16x3
     assert np.allclose(costs[3], costs[2], rtol=2e-3), costs
+
+
+def test_deep_gru_s2s_full_size_properties(cuda):
+    """BASELINE.json config[2] at full size: deep GRU s2s (4+4, dim-emb 512, dim-rnn 1024, V = 32000),
+    64 x 50 batches, tf32 GEMMs, graph replay.  ~10^4 kernels per step (GRU cells, Bahdanau attention,
+    per-step GEMMs): checks the RNN rows of the scope table at the size the survey names."""
+    opts = ("type=s2s;dim-vocabs=32000,32000;dim-emb=512;dim-rnn=1024;enc-depth=4;dec-depth=4;enc-cell=gru;dec-cell=gru;"
+            "cost-type=ce-mean;learn-rate=0.0001;clip-norm=1;seed=1234;workspace=8192;gemm-mode=3;graph-replay=true")
+    t = cuda.trainer(opts)
+    costs = []
+    for s in range(5):
+        t.next_synthetic_batch(64, 50, 50, padded=False)
+        t.compute_gradients()
+        t.update()
+        costs.append(t.cost())
+    st = t.stats()
+    t.close()
+    assert all(np.isfinite(costs)), costs
+    assert abs(costs[0] - 50 * np.log(32000)) < 0.05 * 50 * np.log(32000), costs
+    assert costs[-1] < costs[0], costs
+    assert st["plans"] == 1 and st["replays"] >= 2, st
