@@ -433,16 +433,23 @@ __device__ __forceinline__ void storeHead(float* dst, const float* src, int ld, 
   }
 }
 
+// Forward shared-memory plan: three tiles only, so that FOUR CTAs fit on an SM and the 512 heads
+// of a config-B block run as a single wave:
+//   tile A: Q, later reused for V (loaded asynchronously WHILE the softmax runs)
+//   tile B: K, later the staging tile of the output O
+//   tile S: scores / probabilities
 struct MmaLayoutFwd {
-  int TqP, TkP, ldQ, ldK, ldV, ldS;
+  int TqP, TkP, rowsA, rowsB, ldQ, ldK, ldV, ldS;
   __host__ __device__ MmaLayoutFwd(const AttnGeom& g) {
     TqP = pad16(g.Tq);
     TkP = pad16(g.Tk);
+    rowsA = TqP > TkP ? TqP : TkP;
+    rowsB = rowsA;
     ldQ = ldK = pitchMod32(g.dk, 4);
     ldV = pitchMod32(g.dk, 8);
     ldS = pitchMod32(TkP, 4);
   }
-  __host__ __device__ size_t floats() const { return (size_t)TqP * ldQ + (size_t)TkP * ldK + (size_t)TkP * ldV + (size_t)TqP * ldS; }
+  __host__ __device__ size_t floats() const { return (size_t)rowsA * ldV + (size_t)rowsB * ldK + (size_t)TqP * ldS; }
 };
 
 template <bool X3>
@@ -456,16 +463,16 @@ __global__ void __launch_bounds__(kAttnThreads) gAttentionForwardMma(float* __re
   extern __shared__ __align__(16) float smemF[];
   pdlEnter();
   const MmaLayoutFwd L(g);
-  float* sQ = smemF;
-  float* sK = sQ + L.TqP * L.ldQ;
-  float* sV = sK + L.TkP * L.ldK;
-  float* sS = sV + L.TkP * L.ldV;
+  float* sQ = smemF;                 // tile A (pitch ldQ while it holds Q, ldV while it holds V)
+  float* sV = smemF;
+  float* sK = sQ + L.rowsA * L.ldV;  // tile B
+  float* sO = sK;
+  float* sS = sK + L.rowsB * L.ldK;
 
   const int b = blockIdx.x / g.H, h = blockIdx.x - b * g.H;
   const int d = g.H * g.dk;
   loadHeadPadded(sQ, L.ldQ, q + ((size_t)b * g.Tq) * d + h * g.dk, g.Tq, L.TqP, g.dk, d);
   loadHeadPadded(sK, L.ldK, k + ((size_t)b * g.Tk) * d + h * g.dk, g.Tk, L.TkP, g.dk, d);
-  loadHeadPadded(sV, L.ldV, v + ((size_t)b * g.Tk) * d + h * g.dk, g.Tk, L.TkP, g.dk, d);
   cpAsyncWaitAll();
   __syncthreads();
 
@@ -483,6 +490,9 @@ __global__ void __launch_bounds__(kAttnThreads) gAttentionForwardMma(float* __re
     *reinterpret_cast<float2*>(sS + i * L.ldS + j) = make_float2(s0, s1);
   });
   __syncthreads();
+
+  // Q is dead: V streams into its tile while the softmax runs
+  loadHeadPadded(sV, L.ldV, v + ((size_t)b * g.Tk) * d + h * g.dk, g.Tk, L.TkP, g.dk, d);
 
   // row softmax over the real columns; padding columns / rows become exact zeros
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
@@ -513,31 +523,37 @@ __global__ void __launch_bounds__(kAttnThreads) gAttentionForwardMma(float* __re
         prow[j] = p;
     }
   }
+  cpAsyncWaitAll();
   __syncthreads();
 
-  // O = P V, staged in the (now idle) Q tile and written as coalesced rows of [B, Tq, H*dk]
+  // O = P V, staged in the (now idle) K tile and written as coalesced rows of [B, Tq, H*dk]
   warpMmaProduct<false, X3>(sS, L.ldS, sV, L.ldV, L.TqP, g.dk, L.TkP, [&](int i, int c, float v0, float v1) {
-    *reinterpret_cast<float2*>(sQ + i * L.ldQ + c) = make_float2(v0, v1);
+    *reinterpret_cast<float2*>(sO + i * L.ldK + c) = make_float2(v0, v1);
   });
   __syncthreads();
-  storeHead(out + ((size_t)b * g.Tq) * d + h * g.dk, sQ, L.ldQ, g.Tq, g.dk, d, false);
+  storeHead(out + ((size_t)b * g.Tq) * d + h * g.dk, sO, L.ldK, g.Tq, g.dk, d, false);
 }
 
+// Backward shared-memory plan: four tiles (+ D), three CTAs per SM at the config-B shape:
+//   tile 1: dO (phases dV, dP), then Q (phase dK)          tile 2: V (phase dP), then K (phase dQ),
+//   tile P: P -> dS                                          tile PT: P^T -> dS^T
+// K and Q arrive (cp.async) once dO and V are dead; dQ / dK / dV go straight to global memory.
 struct MmaLayoutBwd {
-  int TqP, TkP, rowsV, ldQ, ldK, ldV, ldO, ldS, ldT;
+  int TqP, TkP, rows1, rows2, ld1, ld2, ldQ, ldK, ldV, ldO, ldS, ldT;
   __host__ __device__ MmaLayoutBwd(const AttnGeom& g) {
     TqP = pad16(g.Tq);
     TkP = pad16(g.Tk);
-    rowsV = TqP > TkP ? TqP : TkP;  // the V tile doubles as the staging tile of dQ
     ldQ = ldK = pitchMod32(g.dk, 8);  // B operands read from [k][n] matrices
     ldV = pitchMod32(g.dk, 4);        // B operand read along k
     ldO = pitchMod32(g.dk, 12);       // dO is A along k (conflict free) and B from [k][n] (2-way)
     ldS = pitchMod32(TkP, 4);         // P / dS   [TqP][TkP]
     ldT = pitchMod32(TqP, 4);         // P^T / dS^T [TkP][TqP]
+    rows1 = TqP;                      // dO [TqP], Q [TqP]
+    ld1 = ldO > ldQ ? ldO : ldQ;
+    rows2 = TkP;                      // V [TkP], K [TkP]
+    ld2 = ldV > ldK ? ldV : ldK;
   }
-  __host__ __device__ size_t floats() const {
-    return (size_t)TqP * ldQ + (size_t)TkP * ldK + (size_t)rowsV * ldV + (size_t)TqP * ldO + (size_t)TqP * ldS + (size_t)TkP * ldT + TqP;
-  }
+  __host__ __device__ size_t floats() const { return (size_t)rows1 * ld1 + (size_t)rows2 * ld2 + (size_t)TqP * ldS + (size_t)TkP * ldT + TqP; }
 };
 
 __device__ __forceinline__ void emit2(float* p, float v0, float v1, bool accumulate) {
@@ -567,22 +583,20 @@ __global__ void __launch_bounds__(kAttnThreads) gAttentionBackwardMma(float* __r
   extern __shared__ __align__(16) float smemF[];
   pdlEnter();
   const MmaLayoutBwd L(g);
-  float* sQ = smemF;
-  float* sK = sQ + L.TqP * L.ldQ;
-  float* sV = sK + L.TkP * L.ldK;
-  float* sdO = sV + L.rowsV * L.ldV;
-  float* sP = sdO + L.TqP * L.ldO;   // P, later dS
-  float* sPT = sP + L.TqP * L.ldS;   // P^T, later dS^T
+  float* t1 = smemF;                    // dO, later Q
+  float* t2 = t1 + L.rows1 * L.ld1;     // V, later K
+  float* sP = t2 + L.rows2 * L.ld2;     // P, later dS
+  float* sPT = sP + L.TqP * L.ldS;      // P^T, later dS^T
   float* sD = sPT + L.TkP * L.ldT;
+  float* sdO = t1;
+  float* sV = t2;
 
   const int b = blockIdx.x / g.H, h = blockIdx.x - b * g.H;
   const int d = g.H * g.dk;
   const size_t offQ = ((size_t)b * g.Tq) * d + h * g.dk;
   const size_t offK = ((size_t)b * g.Tk) * d + h * g.dk;
-  loadHeadPadded(sQ, L.ldQ, q + offQ, g.Tq, L.TqP, g.dk, d);
-  loadHeadPadded(sK, L.ldK, k + offK, g.Tk, L.TkP, g.dk, d);
-  loadHeadPadded(sV, L.ldV, v + offK, g.Tk, L.TkP, g.dk, d);
   loadHeadPadded(sdO, L.ldO, dout + offQ, g.Tq, L.TqP, g.dk, d);
+  loadHeadPadded(sV, L.ldV, v + offK, g.Tk, L.TkP, g.dk, d);
   const float* pb = probs + (((size_t)b * g.H + h) * g.Tq) * g.Tk;
   for(int e = threadIdx.x; e < L.TqP * L.TkP; e += blockDim.x) {
     int i = e / L.TkP, j = e - i * L.TkP;
@@ -600,7 +614,6 @@ __global__ void __launch_bounds__(kAttnThreads) gAttentionBackwardMma(float* __r
   }
   // D_i = sum_c dO_ic O_ic (O from global memory)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  __syncthreads();
   for(int i = warp; i < L.TqP; i += nwarps) {
     float s = 0.f;
     if(i < g.Tq) {
@@ -612,6 +625,7 @@ __global__ void __launch_bounds__(kAttnThreads) gAttentionBackwardMma(float* __r
     if(lane == 0)
       sD[i] = s;
   }
+  __syncthreads();
 
   // dV = P^T dO
   warpMmaProduct<false, X3>(sPT, L.ldT, sdO, L.ldO, L.TkP, g.dk, L.TqP, [&](int j, int c, float v0, float v1) {
@@ -631,17 +645,23 @@ __global__ void __launch_bounds__(kAttnThreads) gAttentionBackwardMma(float* __r
   });
   __syncthreads();
 
-  // dQ = dS K -> staged in the (idle) V tile;  dK = dS^T Q -> staged in the K tile once dQ is done
+  // dO and V are dead: K and Q stream into their tiles
+  float* sK = t2;
+  float* sQ = t1;
+  loadHeadPadded(sK, L.ldK, k + offK, g.Tk, L.TkP, g.dk, d);
+  loadHeadPadded(sQ, L.ldQ, q + offQ, g.Tq, L.TqP, g.dk, d);
+  cpAsyncWaitAll();
+  __syncthreads();
+
+  // dQ = dS K,  dK = dS^T Q  (written straight to global memory: no idle tile left to stage in)
   warpMmaProduct<false, X3>(sP, L.ldS, sK, L.ldK, L.TqP, g.dk, L.TkP, [&](int i, int c, float v0, float v1) {
-    *reinterpret_cast<float2*>(sV + i * L.ldV + c) = make_float2(v0, v1);
+    if(i < g.Tq)
+      emit2(dq + offQ + (size_t)i * d + c, v0, v1, accQ != 0);
   });
-  __syncthreads();
-  storeHead(dq + offQ, sV, L.ldV, g.Tq, g.dk, d, accQ != 0);
   warpMmaProduct<false, X3>(sPT, L.ldT, sQ, L.ldQ, L.TkP, g.dk, L.TqP, [&](int j, int c, float v0, float v1) {
-    *reinterpret_cast<float2*>(sK + j * L.ldK + c) = make_float2(v0, v1);
+    if(j < g.Tk)
+      emit2(dk_ + offK + (size_t)j * d + c, v0, v1, accK != 0);
   });
-  __syncthreads();
-  storeHead(dk_ + offK, sK, L.ldK, g.Tk, g.dk, d, accK != 0);
 }
 
 size_t forwardSmem(const AttnGeom& g) {

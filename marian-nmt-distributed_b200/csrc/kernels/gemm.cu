@@ -1173,6 +1173,10 @@ bool runTf32(GemmHandle h, const GemmProblem& p) {
   if(!batched && tiles <= kNumSMs && a.kBlocks >= 32) {
     splits = (int)std::min<long>((kNumSMs * 2 + tiles - 1) / tiles, a.kBlocks / 8);
     splits = std::max(1, std::min(splits, 32));
+  } else if(!batched && tiles < 2 * kNumSMs && a.kBlocks >= 256) {
+    // a wave and a bit of very long CTAs (logits dX: 200 tiles x 1000 k-blocks): cut them so the
+    // tail wave is short
+    splits = (int)((4 * kNumSMs + tiles - 1) / tiles);
   }
   a.kBlocksPerSplit = (a.kBlocks + splits - 1) / splits;
   splits = (a.kBlocks + a.kBlocksPerSplit - 1) / a.kBlocksPerSplit;
