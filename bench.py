@@ -185,6 +185,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--gemm-mode", type=int, default=3, help="3 = tf32 on the fp32 tensors (headline), 1 = packed bf16, 2 = bf16x3, 0 = fp32 SIMT")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="N > 1: gradient exchange by peer-memory kernels over NVLink (default) or NCCL reduce-scatter / all-gather")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -218,7 +220,8 @@ def main():
         import torch.distributed as dist
 
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-        sync = pkg.SyncTrainer(lib, opts, local_rank, rank, world, pkg.TorchExchange())
+        # gradient exchange: native peer-memory kernels (default) or NCCL collectives (--exchange nccl)
+        sync = pkg.SyncTrainer(lib, opts, local_rank, rank, world, pkg.TorchExchange(), peer=(args.exchange == "peer"))
         trainer = sync.trainer
         step = sync.step
         barrier = dist.barrier
@@ -286,7 +289,8 @@ def main():
 
     stats = trainer.stats()
     graph_kernels = trainer.graph_kernels()
-    launches = graph_kernels + 2 + (2 if world > 1 else 0)  # + sum-of-squares, Adam (+ NCCL RS/AG)
+    # + sum-of-squares, Adam (+ NCCL RS/AG), or with the peer exchange: 2 barriers, gather-reduce, Adam
+    launches = graph_kernels + (2 if world == 1 else 4)
 
     if rank == 0:
         pk, pk_src = peaks()
@@ -298,6 +302,7 @@ def main():
             "dtype": {0: "f32", 1: "bf16", 2: "bf16x3", 3: "tf32"}[args.gemm_mode], "data": "synthetic",
             "config": {"workload": "Transformer-base (6+6, d=512, 8 heads, ffn 2048, V=32000) training step, dense 64x50-token bitext per GPU",
                        "global_batch": world * BATCH, "seq_len": LEN, "parallelism": "dp%d" % world,
+                       "exchange": (args.exchange if world > 1 else None),
                        "l2": "working set per step (373 MB params + 373 MB grads + activations) >> 126 MB L2; no explicit flush",
                        "gemm_mode": args.gemm_mode, "graph_replay": stats["plans"] > 0},
             "clocks": clocks,

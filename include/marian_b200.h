@@ -175,6 +175,16 @@ int mrn_trainer_update(void* trainer);
  * (mrn_trainer_shard_grads_ptr), then invalidates packed weights. Asynchronous. */
 int mrn_trainer_update_shard(void* trainer);
 /* blocking: waits for the stream, returns the cost of the last batch */
+/* Peer-memory exchange (replaces the reference's gather / add / update / scatter loop of
+ * SyncGraphGroup::execute, src/training/graph_group_sync.cu:125-151, for ranks on one node):
+ * every rank exports CUDA IPC handles of {parameter arena, gradient arena, signal pad}
+ * (3 x 64 bytes), the host exchanges them (any transport), every rank imports all of them
+ * (nranks x 3 x 64 bytes, rank-major), then mrn_trainer_update_peer() runs
+ * {barrier, gather-reduce by peer loads, clip + Adam with peer stores, barrier} on the engine
+ * stream after mrn_trainer_compute_gradients().  Adam only. */
+int mrn_trainer_ipc_export(void* trainer, unsigned char* handles, size_t capacity);
+int mrn_trainer_ipc_import(void* trainer, const unsigned char* all_handles, int nranks);
+int mrn_trainer_update_peer(void* trainer);
 int mrn_trainer_cost(void* trainer, float* cost);
 
 /* flat arenas (src/graph/parameters.h:58-80): device pointers + element counts */

@@ -21,6 +21,7 @@ CUDA_SOURCES = [
     "kernels/tensor_operators.cu",
     "kernels/gemm.cu",
     "kernels/attention.cu",
+    "kernels/exchange.cu",
 ]
 # host graph code: instantiates the Element/Add kernel templates, hence nvcc -x cu
 ENGINE_SOURCES = [

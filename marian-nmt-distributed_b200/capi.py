@@ -78,6 +78,9 @@ _SIGNATURES = {
     "mrn_trainer_compute_gradients": [_V, _I],
     "mrn_trainer_update": [_V],
     "mrn_trainer_update_shard": [_V],
+    "mrn_trainer_ipc_export": [_V, ctypes.c_char_p, _SZ],
+    "mrn_trainer_ipc_import": [_V, ctypes.c_char_p, _I],
+    "mrn_trainer_update_peer": [_V],
     "mrn_trainer_cost": [_V, c_float_p],
     "mrn_trainer_params": [_V, ctypes.POINTER(_V), ctypes.POINTER(_SZ)],
     "mrn_trainer_grads": [_V, ctypes.POINTER(_V), ctypes.POINTER(_SZ)],
@@ -297,6 +300,21 @@ class Trainer:
 
     def update_shard(self):
         self.lib._ck(self.lib.c.mrn_trainer_update_shard(self.h))
+
+    # ---- peer-memory exchange (CUDA IPC) ----
+    IPC_BYTES = 3 * 64
+
+    def ipc_export(self):
+        buf = ctypes.create_string_buffer(self.IPC_BYTES)
+        self.lib._ck(self.lib.c.mrn_trainer_ipc_export(self.h, buf, self.IPC_BYTES))
+        return buf.raw
+
+    def ipc_import(self, all_handles, nranks):
+        assert len(all_handles) == nranks * self.IPC_BYTES
+        self.lib._ck(self.lib.c.mrn_trainer_ipc_import(self.h, all_handles, nranks))
+
+    def update_peer(self):
+        self.lib._ck(self.lib.c.mrn_trainer_update_peer(self.h))
 
     def cost(self):
         c = ctypes.c_float()

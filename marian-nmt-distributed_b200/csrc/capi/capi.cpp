@@ -408,6 +408,40 @@ int mrn_trainer_update_shard(void* trainer) {
     t->sync->updateShard();
   });
 }
+// ---- peer-memory exchange: CUDA IPC handles of {parameter arena, gradient arena, signal pad} ----
+int mrn_trainer_ipc_export(void* trainer, unsigned char* handles, size_t capacity) {
+  return guarded([&] {
+    auto t = (Trainer*)trainer;
+    ABORT_IF(!t->sync, "mrn_trainer_ipc_export needs nranks > 1");
+    ABORT_IF(capacity < 3 * device::ipcHandleBytes(), "mrn_trainer_ipc_export: buffer too small");
+    device::setDevice(t->device);
+    void* ptrs[3] = {t->sync->flatParams()->data(), t->sync->flatGrads()->data(), t->sync->signalPad()};
+    for(int i = 0; i < 3; ++i)
+      device::ipcExport(ptrs[i], handles + i * device::ipcHandleBytes());
+  });
+}
+int mrn_trainer_ipc_import(void* trainer, const unsigned char* allHandles, int nranks) {
+  return guarded([&] {
+    auto t = (Trainer*)trainer;
+    ABORT_IF(!t->sync || nranks != t->nranks || nranks > 8, "mrn_trainer_ipc_import: rank count mismatch (max 8 ranks per node)");
+    device::setDevice(t->device);
+    PeerTable tab[3] = {};
+    void* own[3] = {t->sync->flatParams()->data(), t->sync->flatGrads()->data(), t->sync->signalPad()};
+    size_t hb = device::ipcHandleBytes();
+    for(int r = 0; r < nranks; ++r)
+      for(int i = 0; i < 3; ++i)
+        tab[i].ptr[r] = r == t->rank ? own[i] : device::ipcOpen(allHandles + ((size_t)r * 3 + i) * hb);
+    t->sync->setPeers(tab[0], tab[1], tab[2]);
+  });
+}
+int mrn_trainer_update_peer(void* trainer) {
+  return guarded([&] {
+    auto t = (Trainer*)trainer;
+    ABORT_IF(!t->sync, "mrn_trainer_update_peer needs nranks > 1");
+    t->sync->exchangeUpdatePeer();
+  });
+}
+
 int mrn_trainer_cost(void* trainer, float* cost) {
   return guarded([&] { *cost = ((Trainer*)trainer)->worker().cost(); });
 }

@@ -1,0 +1,88 @@
+// Sharded gradient exchange over NVLink peer memory, fused with the optimizer step.
+//
+// Reference: SyncGraphGroup::execute (src/training/graph_group_sync.cu:125-151): for every shard
+// its owner copies the shard of every other GPU's gradient into a scratch tensor (blocking
+// cudaMemcpy), adds it with an Element kernel, runs the optimizer on the shard and copies the
+// updated parameters back to every GPU - 2N blocking peer copies + N adds per shard, serialised
+// on a host thread pool.
+//
+// Here, one process per GPU.  Every rank maps the parameter and gradient arenas of all ranks
+// (CUDA IPC) and an update is three kernels on the engine stream, no host involvement:
+//
+//   gPeerBarrier      all ranks have finished backward (flags in peer memory)
+//   gGatherReduce     shard_sum[i] = sum_r grads_r[shard_offset + i]   (peer LOADS over NVLink),
+//                     sum of squares of the shard for the clipping norm in the same pass
+//   gAdam(+peers)     clip factor, 1/N, Adam moments, new parameters written to the local arena
+//                     AND to the same range of every peer's arena (peer STORES over NVLink)
+//   gPeerBarrier      all parameter shards have landed everywhere
+//
+// i.e. reduce-scatter + optimizer + all-gather without intermediate copies: the owner reads each
+// remote gradient element once and writes each parameter element once per peer.  Per rank and
+// step: (N-1)/N * P * 4 bytes in each direction over NVLink, 4 * shard streams of HBM traffic.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+
+#include "kernels/cuda_helpers.h"
+#include "kernels/tensor_operators.h"
+
+namespace marian {
+
+namespace {
+
+// Epoch barrier across the ranks of one node.  pad[r] of rank q = "rank r has reached epoch e".
+// Thread t signals peer t, then waits for peer t's signal in the own pad.
+__global__ void gPeerBarrier(PeerTable pads, int rank, int nranks, int epoch) {
+  int t = threadIdx.x;
+  if(t < nranks) {
+    __threadfence_system();  // everything this GPU wrote before is visible to the peers first
+    volatile int* remote = reinterpret_cast<volatile int*>(pads.ptr[t]) + rank;
+    *remote = epoch;
+    volatile int* own = reinterpret_cast<volatile int*>(pads.ptr[rank]) + t;
+    while(*own < epoch) {
+    }
+    __threadfence_system();
+  }
+}
+
+// out[i] = sum over ranks of grads_r[offset + i]; *normSq += sum out[i]^2
+__global__ void __launch_bounds__(256) gGatherReduce(float* __restrict__ out, float* __restrict__ normSq, PeerTable grads, int nranks, size_t offset, size_t n) {
+  __shared__ float smem[32];
+  float sq = 0.f;
+  size_t n4 = n >> 2;
+  for(size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+    for(int r = 0; r < nranks; ++r) {
+      float4 g = __ldcg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(grads.ptr[r]) + offset) + i);
+      acc.x += g.x;
+      acc.y += g.y;
+      acc.z += g.z;
+      acc.w += g.w;
+    }
+    reinterpret_cast<float4*>(out)[i] = acc;
+    sq += (acc.x * acc.x + acc.y * acc.y) + (acc.z * acc.z + acc.w * acc.w);
+  }
+  sq = blockSum(sq, smem);
+  if(threadIdx.x == 0)
+    atomicAdd(normSq, sq);
+}
+
+}  // namespace
+
+void PeerBarrier(const PeerTable& pads, int rank, int nranks, int epoch) {
+  gPeerBarrier<<<1, 32, 0, cudaStreamOfEngine()>>>(pads, rank, nranks, epoch);
+  CUDA_LAUNCH_CHECK();
+}
+
+void PeerGatherReduce(Tensor shardSum, Tensor normSq, const PeerTable& grads, int nranks, size_t offset) {
+  device::setDevice(shardSum->getDevice());
+  size_t n = shardSum->size();
+  ABORT_IF(n % 4 != 0 || offset % 4 != 0, "peer exchange expects 16-byte aligned shards");
+  normSq->set(0);
+  int grid = std::max(1, std::min((int)((n / 4 + 255) / 256), kNumSMs * 8));
+  gGatherReduce<<<grid, 256, 0, cudaStreamOfEngine()>>>(shardSum->data(), normSq->data(), grads, nranks, offset, n);
+  CUDA_LAUNCH_CHECK();
+}
+
+}  // namespace marian

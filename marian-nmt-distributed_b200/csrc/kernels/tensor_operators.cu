@@ -1613,7 +1613,7 @@ __device__ __forceinline__ float clipScale(float gradScale, float clipNorm, cons
   return scale;
 }
 
-__global__ void __launch_bounds__(256) gAdam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n, AdamArgs a, const float* __restrict__ normSq) {
+__global__ void __launch_bounds__(256) gAdam(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, size_t n, AdamArgs a, const float* __restrict__ normSq, PeerStores peers) {
   pdlEnter();
   float scale = clipScale(a.gradScale, a.clipNorm, normSq);
   size_t n4 = n >> 2;
@@ -1636,12 +1636,19 @@ __global__ void __launch_bounds__(256) gAdam(float* __restrict__ p, const float*
     reinterpret_cast<float4*>(p)[i] = pp;
     reinterpret_cast<float4*>(m)[i] = mm;
     reinterpret_cast<float4*>(v)[i] = vv;
+    // all-gather by peer stores: the owner writes the new values into every replica
+    for(int r = 0; r < peers.nranks; ++r)
+      if(r != peers.self)
+        reinterpret_cast<float4*>(reinterpret_cast<float*>(peers.params.ptr[r]) + peers.offset)[i] = pp;
   }
   for(size_t i = (n4 << 2) + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     float gi = g[i] * scale;
     m[i] = (a.beta1 * m[i]) + ((1 - a.beta1) * gi);
     v[i] = (a.beta2 * v[i]) + ((1 - a.beta2) * (gi * gi));
     p[i] = p[i] - a.eta * (m[i] / a.denom1) / (sqrtf(v[i] / a.denom2) + a.eps);
+    for(int r = 0; r < peers.nranks; ++r)
+      if(r != peers.self)
+        (reinterpret_cast<float*>(peers.params.ptr[r]) + peers.offset)[i] = p[i];
   }
 }
 
@@ -1711,13 +1718,13 @@ void Dropout(Tensor mask, float dropProb, uint64_t seed) {
   CUDA_LAUNCH_CHECK();
 }
 
-void AdamUpdate(Tensor params, Tensor grads, Tensor mt, Tensor vt, const AdamArgs& args, Tensor normSq) {
+void AdamUpdate(Tensor params, Tensor grads, Tensor mt, Tensor vt, const AdamArgs& args, Tensor normSq, const PeerStores* peers) {
   device::setDevice(params->getDevice());
   size_t n = params->size();
   ABORT_IF(grads->size() != n || mt->size() != n || vt->size() != n, "AdamUpdate: size mismatch");
   ABORT_IF(!all16({params->data(), grads->data(), mt->data(), vt->data()}), "AdamUpdate expects 16-byte aligned tensors");
   int grid = std::max(1, std::min((int)((n / 4 + 255) / 256), kNumSMs * 8));
-  launchPdl(gAdam, dim3(grid), dim3(256), 0, cudaStreamOfEngine(), params->data(), (const float*)grads->data(), mt->data(), vt->data(), n, args, (const float*)(normSq ? normSq->data() : nullptr));
+  launchPdl(gAdam, dim3(grid), dim3(256), 0, cudaStreamOfEngine(), params->data(), (const float*)grads->data(), mt->data(), vt->data(), n, args, (const float*)(normSq ? normSq->data() : nullptr), peers ? *peers : PeerStores());
   CUDA_LAUNCH_CHECK();
 }
 

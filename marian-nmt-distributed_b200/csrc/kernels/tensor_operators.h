@@ -144,7 +144,24 @@ struct AdamArgs {
   float gradScale;       // multiplies every gradient before use
   float clipNorm;        // <= 0: no clipping
 };
-void AdamUpdate(Tensor params, Tensor grads, Tensor mt, Tensor vt, const AdamArgs& args, Tensor normSq = nullptr);
+// Peer-memory exchange (kernels/exchange.cu).  A PeerTable holds, per rank of the node, the
+// address at which THIS process sees that rank's buffer (own buffer: the local pointer).
+struct PeerTable {
+  void* ptr[8];
+};
+// Where an optimizer kernel additionally stores the updated parameters: element i of the shard
+// goes to ptr[r] + offset + i for every rank r != self (all-gather by peer stores).
+struct PeerStores {
+  PeerTable params;
+  int nranks{0};
+  int self{0};
+  size_t offset{0};
+};
+void PeerBarrier(const PeerTable& pads, int rank, int nranks, int epoch);
+// shardSum[i] = sum_r grads_r[offset + i];  normSq = sum_i shardSum[i]^2 (same pass)
+void PeerGatherReduce(Tensor shardSum, Tensor normSq, const PeerTable& grads, int nranks, size_t offset);
+
+void AdamUpdate(Tensor params, Tensor grads, Tensor mt, Tensor vt, const AdamArgs& args, Tensor normSq = nullptr, const PeerStores* peers = nullptr);
 void SgdUpdate(Tensor params, Tensor grads, float eta, float gradScale, float clipNorm, Tensor normSq = nullptr);
 void AdagradUpdate(Tensor params, Tensor grads, Tensor gt, float eta, float eps, float gradScale, float clipNorm, Tensor normSq = nullptr);
 

@@ -43,7 +43,20 @@ public:
       SumSquares(normSq_, grads);
       normSq = normSq_;
     }
-    updateImpl(params, grads, gradScale, normSq);
+    updateImpl(params, grads, gradScale, normSq, nullptr);
+  }
+
+  // Peer-memory exchange variant (training/graph_group.h, kernels/exchange.cu): `grads` is the
+  // summed gradient shard and normSqScratch() already holds its sum of squares (both produced by
+  // PeerGatherReduce); the update kernel also stores the new parameters into the peers' arenas.
+  void updateShardWithPeers(Tensor params, Tensor grads, float gradScale, const PeerStores& peers) {
+    multiplyFactor_ = 1.f;
+    ensureScratch(params->getDevice());
+    updateImpl(params, grads, gradScale, clipNorm_ > 0 ? normSq_ : nullptr, &peers);
+  }
+  Tensor normSqScratch(int device) {
+    ensureScratch(device);
+    return normSq_;
   }
 
   void setLearnRate(float eta) { eta_ = eta; }
@@ -53,7 +66,7 @@ public:
   Tensor lastNormSq() { return normSq_; }
 
 protected:
-  virtual void updateImpl(Tensor params, Tensor grads, float gradScale, Tensor normSq) = 0;
+  virtual void updateImpl(Tensor params, Tensor grads, float gradScale, Tensor normSq, const PeerStores* peers) = 0;
 
   void ensureScratch(int device) {
     if(!normSq_) {
@@ -75,7 +88,8 @@ public:
   Sgd(float eta, float clipNorm) : OptimizerBase(eta, clipNorm) {}
 
 private:
-  void updateImpl(Tensor params, Tensor grads, float gradScale, Tensor normSq) {
+  void updateImpl(Tensor params, Tensor grads, float gradScale, Tensor normSq, const PeerStores* peers) {
+    ABORT_IF(peers, "the peer-memory exchange is fused with Adam only; use the collective exchange with sgd");
     SgdUpdate(params, grads, multiplyFactor_ * eta_, gradScale, clipNorm_, normSq);
   }
 };
@@ -85,7 +99,8 @@ public:
   Adagrad(float eta, float clipNorm, float eps = 1e-8f) : OptimizerBase(eta, clipNorm), eps_(eps) {}
 
 private:
-  void updateImpl(Tensor params, Tensor grads, float gradScale, Tensor normSq) {
+  void updateImpl(Tensor params, Tensor grads, float gradScale, Tensor normSq, const PeerStores* peers) {
+    ABORT_IF(peers, "the peer-memory exchange is fused with Adam only; use the collective exchange with adagrad");
     if(!gt_) {
       alloc_ = New<TensorAllocator>(params->getDevice());
       alloc_->reserveExact(params->memory()->size());
@@ -109,7 +124,7 @@ public:
   size_t steps() const { return t_; }
 
 private:
-  void updateImpl(Tensor params, Tensor grads, float gradScale, Tensor normSq) {
+  void updateImpl(Tensor params, Tensor grads, float gradScale, Tensor normSq, const PeerStores* peers) {
     if(!mt_) {
       alloc_ = New<TensorAllocator>(params->getDevice());
       alloc_->reserveExact(2 * alloc_->capacity(Shape{1, (int)params->size()}));
@@ -128,7 +143,7 @@ private:
     a.denom2 = (float)(1 - std::pow((double)beta2_, (double)t_));
     a.gradScale = gradScale;
     a.clipNorm = clipNorm_;
-    AdamUpdate(params, grads, mt_, vt_, a, normSq);
+    AdamUpdate(params, grads, mt_, vt_, a, normSq, peers);
   }
 
   float beta1_, beta2_, eps_;

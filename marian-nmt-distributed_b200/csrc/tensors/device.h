@@ -78,6 +78,13 @@ void forkSide();
 void returnFromSide();
 void joinSide();
 
+// ---- inter-process device memory (peer-memory gradient exchange) -----------------------------
+size_t ipcHandleBytes();
+// handle of the allocation that STARTS at ptr (arenas and the signal pad are whole allocations)
+void ipcExport(void* ptr, unsigned char* handleOut);
+// maps another process' allocation into this one (enables peer access lazily)
+void* ipcOpen(const unsigned char* handle);
+
 // "cuda" for the product, "cpu-oracle" for the test oracle.
 const char* backendName();
 

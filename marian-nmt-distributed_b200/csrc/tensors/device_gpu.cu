@@ -234,6 +234,22 @@ void joinSide() {
   tctx.nextEvent = 0;
 }
 
+size_t ipcHandleBytes() {
+  return sizeof(cudaIpcMemHandle_t);
+}
+void ipcExport(void* ptr, unsigned char* handleOut) {
+  cudaIpcMemHandle_t h;
+  CUDA_CHECK(cudaIpcGetMemHandle(&h, ptr));
+  std::copy((unsigned char*)&h, (unsigned char*)&h + sizeof(h), handleOut);
+}
+void* ipcOpen(const unsigned char* handle) {
+  cudaIpcMemHandle_t h;
+  std::copy(handle, handle + sizeof(h), (unsigned char*)&h);
+  void* p = nullptr;
+  CUDA_CHECK(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+  return p;
+}
+
 const char* backendName() {
   return "cuda";
 }

@@ -178,6 +178,46 @@ public:
     gemmInvalidateCache(worker_.graph()->getBackend()->getGemmHandle());
   }
 
+  // ---- peer-memory exchange (kernels/exchange.cu): reduce-scatter + Adam + all-gather as
+  //      {barrier, gather-reduce by peer loads, Adam with peer stores, barrier} ----------------
+  // signalPad(): 256 bytes of device memory other ranks write their barrier flags into
+  void* signalPad() {
+    if(!pad_) {
+      device::setDevice((int)worker_.graph()->getDevice());
+      pad_ = device::mallocDevice(256);
+      device::zero(pad_, 256);
+      device::synchronize();
+    }
+    return pad_;
+  }
+  // tables: address of every rank's parameter arena / gradient arena / signal pad as mapped into
+  // THIS process (own entries = local pointers)
+  void setPeers(const PeerTable& params, const PeerTable& grads, const PeerTable& pads) {
+    peerParams_ = params;
+    peerGrads_ = grads;
+    peerPads_ = pads;
+    peersSet_ = true;
+  }
+  bool peersSet() const { return peersSet_; }
+
+  // after computeGradients(): everything else of the update, on the engine stream
+  void exchangeUpdatePeer() {
+    ABORT_IF(!peersSet_, "exchangeUpdatePeer: peers have not been mapped");
+    ensureShard();
+    int device = (int)worker_.graph()->getDevice();
+    PeerBarrier(peerPads_, rank_, nranks_, ++epoch_);  // every rank finished backward
+    PeerGatherReduce(shardGrads_, opt_->normSqScratch(device), peerGrads_, nranks_, (size_t)rank_ * shardSize_);
+    auto p = flatParams()->subtensor((int)(rank_ * shardSize_), (int)shardSize_);
+    PeerStores stores;
+    stores.params = peerParams_;
+    stores.nranks = nranks_;
+    stores.self = rank_;
+    stores.offset = (size_t)rank_ * shardSize_;
+    opt_->updateShardWithPeers(p, shardGrads_, 1.f / (float)nranks_, stores);
+    PeerBarrier(peerPads_, rank_, nranks_, ++epoch_);  // every shard has landed everywhere
+    gemmInvalidateCache(worker_.graph()->getBackend()->getGemmHandle());
+  }
+
   float cost() {
     float c = worker_.cost();
     return exchange_ ? exchange_->meanCost(c) : c;
@@ -219,6 +259,11 @@ private:
   size_t shardSize_{0};
   Ptr<TensorAllocator> shardAlloc_;
   Tensor shardGrads_;
+  // peer-memory exchange
+  PeerTable peerParams_{}, peerGrads_{}, peerPads_{};
+  bool peersSet_{false};
+  int epoch_{0};
+  void* pad_{nullptr};
 };
 
 }  // namespace marian

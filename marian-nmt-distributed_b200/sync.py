@@ -65,7 +65,13 @@ class TorchExchange:
 
 
 class SyncTrainer:
-    def __init__(self, lib, options, device, rank, nranks, exchange):
+    """peer=True (CUDA, ranks on one node, Adam): the update after backward is the native
+    peer-memory exchange - {barrier, gather-reduce by peer loads over NVLink, clip + Adam with peer
+    stores, barrier}, csrc/kernels/exchange.cu - instead of NCCL reduce-scatter / all-gather around
+    the shard update.  torch.distributed then only carries the 64-byte IPC handles at start-up,
+    the first-step parameter broadcast and the cost mean."""
+
+    def __init__(self, lib, options, device, rank, nranks, exchange, peer=False):
         import torch
 
         self.torch = torch
@@ -86,6 +92,8 @@ class SyncTrainer:
         self.trainer = lib.trainer(options, device=device, rank=rank, nranks=nranks)
         self.first = True
         self._views = None
+        self.peer = bool(peer) and self.cuda and nranks > 1
+        self._peers_mapped = False
 
     def _tensor(self, ptr, n):
         if self.cuda:
@@ -102,6 +110,14 @@ class SyncTrainer:
             self._views = (self._tensor(p, n), self._tensor(g, ng), self._tensor(s, ns), ns)
         return self._views
 
+    def _map_peers(self):
+        """Exchanges the CUDA IPC handles of {params, grads, signal pad} and maps the peers."""
+        mine = self.trainer.ipc_export()
+        gathered = [None] * self.nranks
+        self.exchange.dist.all_gather_object(gathered, mine, group=self.exchange.group)
+        self.trainer.ipc_import(b"".join(gathered), self.nranks)
+        self._peers_mapped = True
+
     def step(self):
         """One update on the trainer's current batch (set via self.trainer.*batch*)."""
         self.trainer.compute_gradients()
@@ -109,6 +125,11 @@ class SyncTrainer:
         if self.first:
             self.exchange.broadcast(params)  # reference :46-53: replicas start from graph 0
             self.first = False
+        if self.peer:
+            if not self._peers_mapped:
+                self._map_peers()
+            self.trainer.update_peer()
+            return
         self.exchange.reduce_scatter(shard, grads)
         self.trainer.update_shard()
         self.exchange.all_gather(params, ns)

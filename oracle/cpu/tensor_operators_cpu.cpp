@@ -1073,7 +1073,14 @@ static float clipFactor(float gradScale, float clipNorm, Tensor normSq) {
   return scale;
 }
 
-void AdamUpdate(Tensor params, Tensor grads, Tensor mt, Tensor vt, const AdamArgs& a, Tensor normSq) {
+void PeerBarrier(const PeerTable&, int, int, int) {
+  ABORT("peer-memory exchange is a CUDA feature");
+}
+void PeerGatherReduce(Tensor, Tensor, const PeerTable&, int, size_t) {
+  ABORT("peer-memory exchange is a CUDA feature");
+}
+
+void AdamUpdate(Tensor params, Tensor grads, Tensor mt, Tensor vt, const AdamArgs& a, Tensor normSq, const PeerStores*) {
   // reference: Adam::updateImpl (optimizers/optimizers.cu:43-73)
   float scale = clipFactor(a.gradScale, a.clipNorm, normSq);
   size_t n = params->size();
