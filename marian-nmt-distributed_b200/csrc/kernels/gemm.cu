@@ -1141,12 +1141,39 @@ bool runTf32(GemmHandle h, const GemmProblem& p) {
   const bool aMN = p.transA;   // stored [K, M]: M contiguous
   const bool bMN = !p.transB;  // stored [K, N]: N contiguous
 
-  // The config-B products are LATENCY bound (one wave of CTAs, each a serial chain prologue ->
-  // first TMA round trip -> 16 k-blocks -> epilogue; measured in-graph: 128x128 tiles 19.8 us vs
-  // 128x64 tiles 16 us for 3200x512x512): prefer more, narrower CTAs until the wide tiles
-  // alone fill the machine.
-  long tiles128 = (long)((M + BLOCK_M - 1) / BLOCK_M) * ((N + 127) / 128) * p.batches;
-  int BN = (tiles128 >= kNumSMs && N > 64) ? 128 : 64;
+  // Tile width and split-K are picked together by a small cost model calibrated on this GPU
+  // (scripts/gemm_probe.py, in-graph timings in profiles/): a CTA costs a fixed prologue, its
+  // k-blocks (operand traffic L2 -> smem: 24 KB per block at BN=64, 32 KB at BN=128), an epilogue
+  // proportional to the tile; CTAs run 2 per SM in waves of 296; splitting K adds the red.add
+  // traffic and, when C is not being accumulated into, a memset.
+  const int kBlocksAll = (K + TF_BLOCK_K - 1) / TF_BLOCK_K;
+  int BN = 64, splits = 1;
+  {
+    const long mTiles = (M + BLOCK_M - 1) / BLOCK_M;
+    double best = 1e30;
+    for(int bn : {64, 128}) {
+      if(bn == 128 && N <= 64)
+        continue;
+      const long tiles = mTiles * ((N + bn - 1) / bn) * p.batches;
+      const int maxSplits = (batched || kBlocksAll < 32) ? 1 : std::min(32, kBlocksAll / 8);
+      for(int sp = 1; sp <= maxSplits; ++sp) {
+        const long ctas = tiles * sp;
+        const double waves = (double)((ctas + 2 * kNumSMs - 1) / (2 * kNumSMs));
+        const double kb = (double)((kBlocksAll + sp - 1) / sp);
+        double cta = 3.0 + kb * (bn == 128 ? 0.333 : 0.25) + (bn == 128 ? 3.0 : 1.5);
+        double cost = waves * cta;
+        if(sp > 1)
+          cost += 3.0 + 0.3 * sp + (p.beta == 1.f ? 0.0 : 3.0);
+        if(cost < best) {
+          best = cost;
+          BN = bn;
+          splits = sp;
+        }
+      }
+    }
+  }
+  if(const char* forced = std::getenv("MRN_GEMM_BN"))  // tuning aid (scripts/gemm_probe.py)
+    BN = std::atoi(forced) == 128 ? 128 : 64;
 
   uint64_t batchesA = p.strideA ? p.batches : 1, batchesB = p.strideB ? p.batches : 1;
   // stored matrices are [rows, cols] row-major: inner = cols, outer = rows
@@ -1166,18 +1193,10 @@ bool runTf32(GemmHandle h, const GemmProblem& p) {
   a.alpha = p.alpha;
   a.beta = p.beta;
 
-  // split-K: fewer tiles than SMs and a long reduction -> slices of >= 8 k-blocks (256 elements)
-  // up to about two CTAs per SM; partial sums meet in L2 through red.add
   long tiles = (long)((M + BLOCK_M - 1) / BLOCK_M) * ((N + BN - 1) / BN) * p.batches;
-  int splits = 1;
-  if(!batched && tiles <= kNumSMs && a.kBlocks >= 32) {
-    splits = (int)std::min<long>((kNumSMs * 2 + tiles - 1) / tiles, a.kBlocks / 8);
-    splits = std::max(1, std::min(splits, 32));
-  } else if(!batched && tiles < 2 * kNumSMs && a.kBlocks >= 256) {
-    // a wave and a bit of very long CTAs (logits dX: 200 tiles x 1000 k-blocks): cut them so the
-    // tail wave is short
-    splits = (int)((4 * kNumSMs + tiles - 1) / tiles);
-  }
+  (void)tiles;
+  if(const char* forced = std::getenv("MRN_GEMM_SPLITS"))
+    splits = std::max(1, std::min(std::atoi(forced), a.kBlocks));
   a.kBlocksPerSplit = (a.kBlocks + splits - 1) / splits;
   splits = (a.kBlocks + a.kBlocksPerSplit - 1) / a.kBlocksPerSplit;
   a.splits = splits;

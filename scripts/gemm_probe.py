@@ -1,29 +1,40 @@
-"""GEMM timing probe: one shape, beta 0/1, modes, with CUDA events (engine on a torch side stream)."""
-import ctypes, json, os, sys
+"""GEMM tuning probe (tf32 mode): the step's product shapes under forced tile width / split-K
+(MRN_GEMM_BN, MRN_GEMM_SPLITS), timed back to back with CUDA events on rotating buffers."""
+import json, os, sys
 import numpy as np, torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import __graft_entry__ as graft
 pkg = graft.load_package(); lib = pkg.load()
-s = torch.cuda.Stream()
-torch.cuda.set_stream(s)
-lib.set_stream(s.cuda_stream)
-def t(fn, iters=20, warm=3):
-    for _ in range(warm): fn()
+s = torch.cuda.Stream(); torch.cuda.set_stream(s); lib.set_stream(s.cuda_stream)
+g = lib.gemm(3)
+rs = np.random.RandomState(0)
+def t(fn, n, iters=40, warm=5):
+    for i in range(warm): fn(i % n)
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(s)
-    for _ in range(iters): fn()
+    for i in range(iters): fn(i % n)
     e1.record(s); torch.cuda.synchronize()
-    return e0.elapsed_time(e1) / iters * 1000  # us
-rs = np.random.RandomState(0)
-shapes = [(3200, 512, 512), (3200, 512, 2048), (3200, 2048, 512), (3200, 512, 32000), (512, 3200, 512), (512, 3200, 32000), (3200, 32000, 512)]
-quick = len(sys.argv) > 1
-for (M, K, N) in (shapes[:2] if quick else shapes):
-    A = lib.array(rs.standard_normal((M, K)).astype(np.float32)); B = lib.array(rs.standard_normal((K, N)).astype(np.float32)); C = lib.zeros((M, N))
-    for mode in (1,) if quick else (1, 2):
-        g = lib.gemm(mode)
-        for beta in (0.0, 1.0):
-            us = t(lambda: lib.call("mrn_prod", g.h, C.t(), A.t(), B.t(), 0, 0, beta, 1.0))
-            print(json.dumps({"M": M, "K": K, "N": N, "mode": mode, "beta": beta, "us_incl_pack": us, "tflops": 2.0 * M * N * K / us / 1e6}), flush=True)
+    return e0.elapsed_time(e1) / iters * 1000
+# (rowsA, colsA, rowsB, colsB, tA, tB, beta, label)
+R, D, F = 3200, 512, 2048
+cases = [(R, D, D, D, 0, 0, 0.0, "proj fwd"), (R, D, D, D, 0, 1, 1.0, "proj dX"), (R, D, R, D, 1, 0, 1.0, "proj dW"),
+         (R, D, D, F, 0, 0, 0.0, "ffn1 fwd"), (R, F, F, D, 0, 0, 0.0, "ffn2 fwd"), (R, D, F, D, 0, 1, 0.0, "ffn2 dX"), (R, F, D, F, 0, 1, 1.0, "ffn1 dX"),
+         (R, D, R, F, 1, 0, 1.0, "ffn1 dW"), (R, F, R, D, 1, 0, 1.0, "ffn2 dW")]
+for (ra, ca, rb, cb, tA, tB, beta, label) in cases:
+    M = ca if tA else ra; K = ra if tA else ca; N = rb if tB else cb
+    n = 4
+    A = [lib.array(rs.standard_normal((ra, ca)).astype(np.float32)) for _ in range(n)]
+    B = [lib.array(rs.standard_normal((rb, cb)).astype(np.float32)) for _ in range(n)]
+    C = [lib.zeros((M, N)) for _ in range(n)]
+    row = {"case": label, "M": M, "N": N, "K": K}
+    for bn in ("64", "128"):
+        for sp in ("auto", "1", "2", "4"):
+            os.environ["MRN_GEMM_BN"] = bn
+            if sp == "auto": os.environ.pop("MRN_GEMM_SPLITS", None)
+            else: os.environ["MRN_GEMM_SPLITS"] = sp
+            us = t(lambda i: lib.call("mrn_prod", g.h, C[i].t(), A[i].t(), B[i].t(), tA, tB, beta, 1.0), n)
+            row["bn%s_sp%s" % (bn, sp)] = round(us, 1)
+    print(json.dumps(row), flush=True)
     del A, B, C
