@@ -111,12 +111,30 @@ class SyncTrainer:
         return self._views
 
     def _map_peers(self):
-        """Exchanges the CUDA IPC handles of {params, grads, signal pad} and maps the peers."""
-        mine = self.trainer.ipc_export()
+        """Exchanges the CUDA IPC handles of {params, grads, signal pad} and maps the peers.
+        Every rank takes part in both collectives whatever happens locally; returns True only if
+        ALL ranks mapped all peers."""
+        dist, group = self.exchange.dist, self.exchange.group
+        err = None
+        try:
+            mine = self.trainer.ipc_export()
+        except Exception as e:  # noqa: BLE001
+            mine, err = None, e
         gathered = [None] * self.nranks
-        self.exchange.dist.all_gather_object(gathered, mine, group=self.exchange.group)
-        self.trainer.ipc_import(b"".join(gathered), self.nranks)
+        dist.all_gather_object(gathered, mine, group=group)
+        if err is None and all(h is not None for h in gathered):
+            try:
+                self.trainer.ipc_import(b"".join(gathered), self.nranks)
+            except Exception as e:  # noqa: BLE001
+                err = e
+        elif err is None:
+            err = RuntimeError("a peer could not export its IPC handles")
+        if err is not None:
+            print("[marian_b200] rank %d: peer-memory exchange unavailable (%s); using collectives" % (self.rank, err), flush=True)
+        flag = self.torch.tensor([0 if err else 1], dtype=self.torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)
         self._peers_mapped = True
+        return bool(int(flag.item()))
 
     def step(self):
         """One update on the trainer's current batch (set via self.trainer.*batch*)."""
@@ -125,9 +143,11 @@ class SyncTrainer:
         if self.first:
             self.exchange.broadcast(params)  # reference :46-53: replicas start from graph 0
             self.first = False
+        if self.peer and not self._peers_mapped:
+            # all ranks must agree: if any rank cannot map its peers (no P2P between the GPUs, IPC
+            # disabled in the container) everybody falls back to the collective exchange - loudly
+            self.peer = self._map_peers()
         if self.peer:
-            if not self._peers_mapped:
-                self._map_peers()
             self.trainer.update_peer()
             return
         self.exchange.reduce_scatter(shard, grads)
