@@ -302,7 +302,7 @@ def main():
             "dtype": {0: "f32", 1: "bf16", 2: "bf16x3", 3: "tf32"}[args.gemm_mode], "data": "synthetic",
             "config": {"workload": "Transformer-base (6+6, d=512, 8 heads, ffn 2048, V=32000) training step, dense 64x50-token bitext per GPU",
                        "global_batch": world * BATCH, "seq_len": LEN, "parallelism": "dp%d" % world,
-                       "exchange": (args.exchange if world > 1 else None),
+                       "exchange": (("peer-memory kernels over NVLink" if sync.peer else "NCCL reduce-scatter / all-gather") if world > 1 else None),
                        "l2": "working set per step (373 MB params + 373 MB grads + activations) >> 126 MB L2; no explicit flush",
                        "gemm_mode": args.gemm_mode, "graph_replay": stats["plans"] > 0},
             "clocks": clocks,

@@ -185,6 +185,18 @@ int mrn_trainer_update_shard(void* trainer);
 int mrn_trainer_ipc_export(void* trainer, unsigned char* handles, size_t capacity);
 int mrn_trainer_ipc_import(void* trainer, const unsigned char* all_handles, int nranks);
 int mrn_trainer_update_peer(void* trainer);
+/* Asynchronous SGD with a sharded parameter server = the reference's AsyncGraphGroup
+ * (src/training/graph_group_async.cu:16-250; fetchParams / pushGradients under per-shard locks) for
+ * one process per GPU: create the trainer with "graph-group=async[;optimizer-delay=tau]", set a batch,
+ * mrn_trainer_async_init() (builds the parameters, allocates this rank's master shard), exchange the
+ * 64-byte IPC handles (export / import, rank-major), then every mrn_trainer_async_update() is
+ * {fetch every tau steps, forward+backward, push every tau steps}.  nranks = 1 works without peers
+ * after importing the own handle.  Adam only. */
+int mrn_trainer_async_init(void* trainer);
+int mrn_trainer_async_export(void* trainer, unsigned char* handle, size_t capacity);
+int mrn_trainer_async_import(void* trainer, const unsigned char* all_handles, int nranks);
+int mrn_trainer_async_update(void* trainer);
+int mrn_trainer_async_fetch(void* trainer);
 int mrn_trainer_cost(void* trainer, float* cost);
 
 /* flat arenas (src/graph/parameters.h:58-80): device pointers + element counts */

@@ -43,4 +43,4 @@ def transformer_base_options(vocab=32000, gemm_mode=3, **extra):
     return o
 
 
-from .sync import SyncTrainer, TorchExchange  # noqa: E402,F401
+from .sync import AsyncTrainer, SyncTrainer, TorchExchange  # noqa: E402,F401

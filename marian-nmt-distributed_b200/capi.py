@@ -81,6 +81,11 @@ _SIGNATURES = {
     "mrn_trainer_ipc_export": [_V, ctypes.c_char_p, _SZ],
     "mrn_trainer_ipc_import": [_V, ctypes.c_char_p, _I],
     "mrn_trainer_update_peer": [_V],
+    "mrn_trainer_async_init": [_V],
+    "mrn_trainer_async_export": [_V, ctypes.c_char_p, _SZ],
+    "mrn_trainer_async_import": [_V, ctypes.c_char_p, _I],
+    "mrn_trainer_async_update": [_V],
+    "mrn_trainer_async_fetch": [_V],
     "mrn_trainer_cost": [_V, c_float_p],
     "mrn_trainer_params": [_V, ctypes.POINTER(_V), ctypes.POINTER(_SZ)],
     "mrn_trainer_grads": [_V, ctypes.POINTER(_V), ctypes.POINTER(_SZ)],
@@ -315,6 +320,25 @@ class Trainer:
 
     def update_peer(self):
         self.lib._ck(self.lib.c.mrn_trainer_update_peer(self.h))
+
+    # ---- asynchronous parameter server (options "graph-group=async") ----
+    def async_init(self):
+        self.lib._ck(self.lib.c.mrn_trainer_async_init(self.h))
+
+    def async_export(self):
+        buf = ctypes.create_string_buffer(64)
+        self.lib._ck(self.lib.c.mrn_trainer_async_export(self.h, buf, 64))
+        return buf.raw
+
+    def async_import(self, all_handles, nranks):
+        assert len(all_handles) == nranks * 64
+        self.lib._ck(self.lib.c.mrn_trainer_async_import(self.h, all_handles, nranks))
+
+    def async_update(self):
+        self.lib._ck(self.lib.c.mrn_trainer_async_update(self.h))
+
+    def async_fetch(self):
+        self.lib._ck(self.lib.c.mrn_trainer_async_fetch(self.h))
 
     def cost(self):
         c = ctypes.c_float()

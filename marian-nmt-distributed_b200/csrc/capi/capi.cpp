@@ -56,11 +56,12 @@ struct Trainer {
   int device{0}, rank{0}, nranks{1};
   Ptr<SingletonGraph> single;
   Ptr<SyncGraphGroup> sync;
+  Ptr<AsyncGraphGroup> async;
   Ptr<data::CorpusBatch> batch;
   Ptr<data::SyntheticCorpus> corpus;
   size_t replays{0};
 
-  GradientWorker& worker() { return single ? single->worker() : sync->worker(); }
+  GradientWorker& worker() { return single ? single->worker() : (sync ? sync->worker() : async->worker()); }
 };
 
 }  // namespace
@@ -330,7 +331,9 @@ int mrn_trainer_create(void** trainer, const char* options, int dev, int rank, i
     t->nranks = nranks;
     Config::seed = t->options->get<size_t>("seed");
     device::setDevice(dev);
-    if(nranks > 1)
+    if(t->options->get<std::string>("graph-group", "sync") == "async")
+      t->async = New<AsyncGraphGroup>(t->options, dev, rank, nranks);
+    else if(nranks > 1)
       t->sync = New<SyncGraphGroup>(t->options, dev, rank, nranks);
     else
       t->single = New<SingletonGraph>(t->options, dev);
@@ -439,6 +442,49 @@ int mrn_trainer_update_peer(void* trainer) {
     auto t = (Trainer*)trainer;
     ABORT_IF(!t->sync, "mrn_trainer_update_peer needs nranks > 1");
     t->sync->exchangeUpdatePeer();
+  });
+}
+
+// ---- asynchronous parameter server (AsyncGraphGroup; options "graph-group=async") ----
+int mrn_trainer_async_init(void* trainer) {
+  return guarded([&] {
+    auto t = (Trainer*)trainer;
+    ABORT_IF(!t->async || !t->batch, "mrn_trainer_async_init needs graph-group=async and a current batch");
+    t->async->init(t->batch);
+  });
+}
+int mrn_trainer_async_export(void* trainer, unsigned char* handle, size_t capacity) {
+  return guarded([&] {
+    auto t = (Trainer*)trainer;
+    ABORT_IF(!t->async || !t->async->masterBlock(), "mrn_trainer_async_export: call mrn_trainer_async_init first");
+    ABORT_IF(capacity < device::ipcHandleBytes(), "mrn_trainer_async_export: buffer too small");
+    device::setDevice(t->device);
+    device::ipcExport(t->async->masterBlock(), handle);
+  });
+}
+int mrn_trainer_async_import(void* trainer, const unsigned char* allHandles, int nranks) {
+  return guarded([&] {
+    auto t = (Trainer*)trainer;
+    ABORT_IF(!t->async || nranks != t->nranks || nranks > 8, "mrn_trainer_async_import: rank count mismatch (max 8 ranks per node)");
+    device::setDevice(t->device);
+    PeerTable tab = {};
+    for(int r = 0; r < nranks; ++r)
+      tab.ptr[r] = r == t->rank ? t->async->masterBlock() : device::ipcOpen(allHandles + (size_t)r * device::ipcHandleBytes());
+    t->async->setPeers(tab);
+  });
+}
+int mrn_trainer_async_update(void* trainer) {
+  return guarded([&] {
+    auto t = (Trainer*)trainer;
+    ABORT_IF(!t->async || !t->batch, "mrn_trainer_async_update needs graph-group=async and a current batch");
+    t->async->update(t->batch);
+  });
+}
+int mrn_trainer_async_fetch(void* trainer) {
+  return guarded([&] {
+    auto t = (Trainer*)trainer;
+    ABORT_IF(!t->async, "mrn_trainer_async_fetch needs graph-group=async");
+    t->async->fetchParams();
   });
 }
 

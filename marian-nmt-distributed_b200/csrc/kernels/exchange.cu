@@ -68,7 +68,85 @@ __global__ void __launch_bounds__(256) gGatherReduce(float* __restrict__ out, fl
     atomicAdd(normSq, sq);
 }
 
+// ---- asynchronous sharded parameter server (AsyncGraphGroup) -------------------------------
+// A master block lives on its owner GPU:  [int lock | int steps | pad to 256 B][p | m | v], each
+// of `shard` floats.  Any rank may fetch a shard or push a gradient slice into it at any time;
+// a per-shard spin lock in the owner's memory (system-scope atomics over NVLink) replaces the
+// reference's std::mutex shardSync_[idx] (src/training/graph_group_async.cu:16-71).
+__global__ void gShardLock(int* lock, int* steps, int* stepsOut) {
+  if(threadIdx.x == 0) {
+    while(atomicCAS_system(lock, 0, 1) != 0) {
+    }
+    __threadfence_system();
+    if(steps) {  // a push: this update's Adam step number
+      int t = *reinterpret_cast<volatile int*>(steps) + 1;
+      *reinterpret_cast<volatile int*>(steps) = t;
+      *stepsOut = t;
+    }
+  }
+}
+__global__ void gShardUnlock(int* lock) {
+  if(threadIdx.x == 0) {
+    __threadfence_system();
+    atomicExch_system(lock, 0);
+  }
+}
+
+// Adam on a REMOTE master shard with a LOCAL gradient slice: p, m, v are peer memory (read and
+// written over NVLink), g and the clipping norm are local.  Formula of optimizers.cu:43-73 with
+// the shard's own step counter for the bias correction.
+__global__ void __launch_bounds__(256) gAdamRemote(float* p, float* m, float* v, const float* __restrict__ g, size_t n, AdamArgs a, const int* __restrict__ steps, const float* __restrict__ normSq) {
+  float scale = a.gradScale;
+  if(normSq && a.clipNorm > 0.f) {
+    float norm = sqrtf(*normSq) * fabsf(a.gradScale);
+    if(norm >= a.clipNorm)
+      scale *= a.clipNorm / norm;
+  }
+  const float t = (float)*steps;
+  const float denom1 = 1.f - powf(a.beta1, t), denom2 = 1.f - powf(a.beta2, t);
+  size_t n4 = n >> 2;
+  for(size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    float4 gg = reinterpret_cast<const float4*>(g)[i];
+    float4 mm = reinterpret_cast<float4*>(m)[i];
+    float4 vv = reinterpret_cast<float4*>(v)[i];
+    float* P = &pp.x;
+    float* G = &gg.x;
+    float* M = &mm.x;
+    float* V = &vv.x;
+#pragma unroll
+    for(int e = 0; e < 4; ++e) {
+      float gi = G[e] * scale;
+      M[e] = (a.beta1 * M[e]) + ((1 - a.beta1) * gi);
+      V[e] = (a.beta2 * V[e]) + ((1 - a.beta2) * (gi * gi));
+      P[e] = P[e] - a.eta * (M[e] / denom1) / (sqrtf(V[e] / denom2) + a.eps);
+    }
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m)[i] = mm;
+    reinterpret_cast<float4*>(v)[i] = vv;
+  }
+}
+
 }  // namespace
+
+void ShardLock(void* masterBlock, bool countStep, int* stepsOut) {
+  int* hdr = reinterpret_cast<int*>(masterBlock);
+  gShardLock<<<1, 32, 0, cudaStreamOfEngine()>>>(hdr, countStep ? hdr + 1 : nullptr, stepsOut);
+  CUDA_LAUNCH_CHECK();
+}
+void ShardUnlock(void* masterBlock) {
+  gShardUnlock<<<1, 32, 0, cudaStreamOfEngine()>>>(reinterpret_cast<int*>(masterBlock));
+  CUDA_LAUNCH_CHECK();
+}
+void AdamUpdateRemote(void* masterBlock, size_t shardElements, const float* gradSlice, const AdamArgs& args, const int* steps, Tensor normSq) {
+  ABORT_IF(shardElements % 4 != 0 || (((uintptr_t)gradSlice) & 15) != 0, "AdamUpdateRemote expects 16-byte aligned shards");
+  float* p = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(masterBlock) + 256);
+  float* m = p + shardElements;
+  float* v = m + shardElements;
+  int grid = std::max(1, std::min((int)((shardElements / 4 + 255) / 256), kNumSMs * 8));
+  gAdamRemote<<<grid, 256, 0, cudaStreamOfEngine()>>>(p, m, v, gradSlice, shardElements, args, steps, normSq ? normSq->data() : nullptr);
+  CUDA_LAUNCH_CHECK();
+}
 
 void PeerBarrier(const PeerTable& pads, int rank, int nranks, int epoch) {
   gPeerBarrier<<<1, 32, 0, cudaStreamOfEngine()>>>(pads, rank, nranks, epoch);

@@ -161,6 +161,16 @@ void PeerBarrier(const PeerTable& pads, int rank, int nranks, int epoch);
 // shardSum[i] = sum_r grads_r[offset + i];  normSq = sum_i shardSum[i]^2 (same pass)
 void PeerGatherReduce(Tensor shardSum, Tensor normSq, const PeerTable& grads, int nranks, size_t offset);
 
+// Asynchronous parameter server (training/graph_group.h AsyncGraphGroup, kernels/exchange.cu).
+// A master block = [int lock, int steps, pad to 256 B][p | m | v] with `shard` floats each, on
+// its owner GPU, mapped into every rank.  ShardLock spins on the lock with system-scope atomics;
+// countStep also increments the shard's Adam step counter and leaves it in *stepsOut (local).
+void ShardLock(void* masterBlock, bool countStep, int* stepsOut);
+void ShardUnlock(void* masterBlock);
+// clip (by *normSq, the squared norm of the local slice) + Adam on the remote master shard;
+// args.denom1/denom2 are ignored: the bias correction uses the shard's own step counter *steps.
+void AdamUpdateRemote(void* masterBlock, size_t shardElements, const float* gradSlice, const AdamArgs& args, const int* steps, Tensor normSq);
+
 void AdamUpdate(Tensor params, Tensor grads, Tensor mt, Tensor vt, const AdamArgs& args, Tensor normSq = nullptr, const PeerStores* peers = nullptr);
 void SgdUpdate(Tensor params, Tensor grads, float eta, float gradScale, float clipNorm, Tensor normSq = nullptr);
 void AdagradUpdate(Tensor params, Tensor grads, Tensor gt, float eta, float eps, float gradScale, float clipNorm, Tensor normSq = nullptr);

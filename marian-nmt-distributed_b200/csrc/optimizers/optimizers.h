@@ -122,6 +122,18 @@ public:
   Tensor mt() { return mt_; }
   Tensor vt() { return vt_; }
   size_t steps() const { return t_; }
+  // hyper-parameters for update kernels that keep their own state (asynchronous parameter server)
+  AdamArgs hyper(float gradScale = 1.f) const {
+    AdamArgs a;
+    a.eta = eta_;
+    a.beta1 = beta1_;
+    a.beta2 = beta2_;
+    a.eps = eps_;
+    a.denom1 = a.denom2 = 1.f;
+    a.gradScale = gradScale;
+    a.clipNorm = clipNorm_;
+    return a;
+  }
 
 private:
   void updateImpl(Tensor params, Tensor grads, float gradScale, Tensor normSq, const PeerStores* peers) {

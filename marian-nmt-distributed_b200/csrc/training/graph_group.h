@@ -266,4 +266,139 @@ private:
   void* pad_{nullptr};
 };
 
+// Asynchronous SGD with a sharded parameter server - the reference's AsyncGraphGroup
+// (src/training/graph_group_async.{h,cu}) re-cut for ONE PROCESS PER GPU over peer memory.
+//
+// Reference: a host thread per GPU; every update it (a) every tau steps fetches all parameter
+// shards from their owner devices under a per-shard mutex, (b) runs forward/backward on its own
+// batch, (c) pushes its gradient, shard by shard, to the owner device where that shard's optimizer
+// updates the master copy under the same mutex.  No barrier between workers: stale gradients.
+//
+// Here rank r owns master shard r = one device allocation [lock, steps | p | m | v] mapped into
+// every rank (CUDA IPC).  A worker step is a sequence of kernels on its own engine stream:
+//   fetch  (every tau):  for each shard s: ShardLock(s) -> copy master_s.p into the local replica
+//                        (peer read over NVLink) -> ShardUnlock(s)
+//   computeGradients     CUDA-graph replay of forward + backward
+//   push   (every tau):  for each shard s: sum of squares of the local slice, ShardLock(s, count
+//                        the Adam step) -> AdamUpdateRemote (clip by the SLICE's norm + Adam on
+//                        the owner's p, m, v through peer loads/stores) -> ShardUnlock(s)
+// The spin lock lives in the owner's memory and is taken with system-scope atomics, so the
+// pusher updates the master shard directly - the owner process is not involved.  Locks are
+// taken one at a time in shard order: no hold-and-wait, no deadlock.  Adam only.
+// Not carried over: exponential smoothing, learning-rate scaling by batch words (both off by
+// default), scheduler quiescing for save/validate (control plane, out of scope).
+class AsyncGraphGroup : public GraphGroup {
+public:
+  AsyncGraphGroup(Ptr<Options> options, int device, int rank, int nranks)
+      : GraphGroup(options), worker_(options, device), rank_(rank), nranks_(nranks), tau_(std::max<size_t>(1, options->get<size_t>("optimizer-delay", 1))) {
+    worker_.graph()->params()->setShardCount(nranks);
+    adam_ = std::dynamic_pointer_cast<Adam>(opt_);
+    ABORT_IF(!adam_, "AsyncGraphGroup: the remote shard update is implemented for adam");
+  }
+  ~AsyncGraphGroup() {
+    if(master_)
+      device::freeDevice(master_);
+  }
+
+  // Builds the tape once (parameters initialised from the shared seed, identical on all ranks),
+  // allocates this rank's master block and seeds it with its shard (reference init(): :96-147).
+  void init(Ptr<data::CorpusBatch> batch) {
+    if(master_)
+      return;
+    worker_.computeGradients(batch);  // eager first pass: parameters exist, gradients allocated
+    device::setDevice((int)worker_.graph()->getDevice());
+    size_t total = flatParams()->size();
+    ABORT_IF(total % nranks_ != 0, "parameter arena is not divisible into shards");
+    shardSize_ = total / nranks_;
+    masterBytes_ = 256 + 3 * shardSize_ * sizeof(float);
+    master_ = device::mallocDevice(masterBytes_);
+    device::zero(master_, masterBytes_);
+    device::copyD2D((uint8_t*)master_ + 256, flatParams()->data() + (size_t)rank_ * shardSize_, shardSize_ * sizeof(float));
+    scratch_ = New<TensorAllocator>((int)worker_.graph()->getDevice());
+    scratch_->reserveExact(512);
+    scratch_->allocate(normSq_, Shape{1, 1});
+    scratch_->allocate(steps_, Shape{1, 1});  // int32 step number of the shard being updated
+    if(tau_ > 1) {
+      accAlloc_ = New<TensorAllocator>((int)worker_.graph()->getDevice());
+      accAlloc_->reserveExact(total * sizeof(float));
+      accAlloc_->allocate(accGrads_, Shape{1, (int)total});
+      accGrads_->set(0);
+    }
+    device::synchronize();
+  }
+  void* masterBlock() { return master_; }
+  size_t masterBytes() const { return masterBytes_; }
+  void setPeers(const PeerTable& masters) {
+    masters_ = masters;
+    peersSet_ = true;
+  }
+
+  void fetchParams() {
+    ABORT_IF(!peersSet_, "AsyncGraphGroup: master shards have not been mapped");
+    device::setDevice((int)worker_.graph()->getDevice());
+    for(int s = 0; s < nranks_; ++s) {
+      ShardLock(masters_.ptr[s], false, nullptr);
+      device::copyD2D(flatParams()->data() + (size_t)s * shardSize_, (uint8_t*)masters_.ptr[s] + 256, shardSize_ * sizeof(float));
+      ShardUnlock(masters_.ptr[s]);
+    }
+    gemmInvalidateCache(worker_.graph()->getBackend()->getGemmHandle());
+  }
+
+  void pushGradients(Tensor gradients) {
+    ABORT_IF(!peersSet_, "AsyncGraphGroup: master shards have not been mapped");
+    device::setDevice((int)worker_.graph()->getDevice());
+    AdamArgs a = adam_->hyper();
+    for(int s = 0; s < nranks_; ++s) {
+      auto slice = gradients->subtensor((int)((size_t)s * shardSize_), (int)shardSize_);
+      if(a.clipNorm > 0)
+        SumSquares(normSq_, slice);  // the reference clips with the pushed shard's own norm
+      ShardLock(masters_.ptr[s], true, (int*)steps_->data());
+      AdamUpdateRemote(masters_.ptr[s], shardSize_, slice->data(), a, (const int*)steps_->data(), a.clipNorm > 0 ? normSq_ : nullptr);
+      ShardUnlock(masters_.ptr[s]);
+    }
+  }
+
+  // reference execute(): :150-215
+  void update(Ptr<data::CorpusBatch> batch) {
+    init(batch);
+    if(t_ % tau_ == 0)
+      fetchParams();
+    worker_.computeGradients(batch);
+    Tensor gradients = flatGrads();
+    if(tau_ > 1) {
+      using namespace functional;
+      Element(_1 += _2, accGrads_, flatGrads());
+      gradients = accGrads_;
+    }
+    t_++;
+    if(t_ % tau_ == 0) {
+      pushGradients(gradients);
+      if(tau_ > 1)
+        accGrads_->set(0);
+    }
+  }
+
+  float cost() { return worker_.cost(); }
+  Tensor flatParams() { return worker_.graph()->params()->vals(); }
+  Tensor flatGrads() { return worker_.graph()->params()->grads(); }
+  GradientWorker& worker() { return worker_; }
+  size_t shardSize() const { return shardSize_; }
+  int rank() const { return rank_; }
+  int nranks() const { return nranks_; }
+
+private:
+  GradientWorker worker_;
+  int rank_, nranks_;
+  size_t tau_;
+  size_t t_{0};
+  Ptr<Adam> adam_;
+  void* master_{nullptr};
+  size_t masterBytes_{0};
+  size_t shardSize_{0};
+  PeerTable masters_{};
+  bool peersSet_{false};
+  Ptr<TensorAllocator> scratch_, accAlloc_;
+  Tensor normSq_, steps_, accGrads_;
+};
+
 }  // namespace marian

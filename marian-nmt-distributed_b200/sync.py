@@ -156,3 +156,47 @@ class SyncTrainer:
 
     def cost(self):
         return self.exchange.mean_cost(self.trainer.cost(), self.device)
+
+
+class AsyncTrainer:
+    """Host-side mirror of AsyncGraphGroup for one process per GPU (csrc/training/graph_group.h).
+
+    Reference: src/training/graph_group_async.cu.  Every rank trains on its own stream of batches
+    with NO synchronisation with the others: it fetches the parameter shards from their owners,
+    runs forward/backward, and pushes its gradient slices into the owners' master shards, all by
+    kernels over peer memory under per-shard device locks.  torch.distributed is only used to
+    exchange the 64-byte IPC handles at start-up (nranks == 1 needs no process group)."""
+
+    def __init__(self, lib, options, device, rank=0, nranks=1, dist=None, group=None):
+        if isinstance(options, dict):
+            options = dict(options, **{"graph-group": "async"})
+        else:
+            options = options + ";graph-group=async"
+        self.rank, self.nranks = rank, nranks
+        self.trainer = lib.trainer(options, device=device, rank=rank, nranks=nranks)
+        self.dist, self.group = dist, group
+        self._ready = False
+
+    def _start(self):
+        """Needs a current batch (parameters are created by building the tape once)."""
+        self.trainer.async_init()
+        mine = self.trainer.async_export()
+        if self.nranks > 1:
+            gathered = [None] * self.nranks
+            self.dist.all_gather_object(gathered, mine, group=self.group)
+            self.trainer.async_import(b"".join(gathered), self.nranks)
+            self.dist.barrier(group=self.group)  # every master shard is seeded before anyone pushes
+        else:
+            self.trainer.async_import(mine, 1)
+        self._ready = True
+
+    def step(self):
+        if not self._ready:
+            self._start()
+        self.trainer.async_update()
+
+    def fetch(self):
+        self.trainer.async_fetch()
+
+    def cost(self):
+        return self.trainer.cost()

@@ -1073,6 +1073,15 @@ static float clipFactor(float gradScale, float clipNorm, Tensor normSq) {
   return scale;
 }
 
+void ShardLock(void*, bool, int*) {
+  ABORT("the asynchronous parameter server is a CUDA feature");
+}
+void ShardUnlock(void*) {
+  ABORT("the asynchronous parameter server is a CUDA feature");
+}
+void AdamUpdateRemote(void*, size_t, const float*, const AdamArgs&, const int*, Tensor) {
+  ABORT("the asynchronous parameter server is a CUDA feature");
+}
 void PeerBarrier(const PeerTable&, int, int, int) {
   ABORT("peer-memory exchange is a CUDA feature");
 }

@@ -170,3 +170,46 @@ def test_deep_gru_s2s_full_size_properties(cuda):
     assert abs(costs[0] - 50 * np.log(32000)) < 0.05 * 50 * np.log(32000), costs
     assert costs[-1] < costs[0], costs
     assert st["plans"] == 1 and st["replays"] >= 2, st
+
+
+def test_async_group_single_rank_equals_singleton(cuda, pkg):
+    """AsyncGraphGroup with one rank (fetch from / push into its own master shard through the same
+    lock + remote-Adam kernels the multi-GPU path uses) must reproduce SingletonGraph: same costs,
+    same parameters (bias corrections computed with powf on the device: 1e-6 agreement)."""
+    opts = TRANSFORMER + ";gemm-mode=0;graph-replay=true;learn-rate=0.001"
+    costs = {"ref": [], "async": []}
+    # one trainer after the other: parameter initialisation draws from a process-wide seed counter
+    ref = cuda.trainer(opts)
+    for s in range(5):
+        ref.next_synthetic_batch(8, 11, 13, padded=True)
+        ref.compute_gradients()
+        ref.update()
+        costs["ref"].append(ref.cost())
+    pr = ref.arena_numpy("params")
+    ref.close()
+    a = pkg.AsyncTrainer(cuda, opts, 0)
+    for s in range(5):
+        a.trainer.next_synthetic_batch(8, 11, 13, padded=True)
+        a.step()
+        costs["async"].append(a.cost())
+    a.fetch()  # replica <- master shards
+    cuda.synchronize()
+    pa = a.trainer.arena_numpy("params")
+    a.trainer.close()
+    assert np.allclose(costs["async"], costs["ref"], rtol=2e-5), costs
+    diff = np.abs(pa - pr)
+    assert np.mean(diff > 2e-5) < 0.01 and np.median(diff) < 2e-6, (diff.max(), np.mean(diff > 2e-5))
+
+
+def test_async_group_optimizer_delay(cuda, pkg):
+    """optimizer-delay tau = 2: gradients of two batches are accumulated and pushed once
+    (reference graph_group_async.cu:186-215); costs stay finite and fall."""
+    a = pkg.AsyncTrainer(cuda, TRANSFORMER + ";gemm-mode=2;graph-replay=true;learn-rate=0.002;optimizer-delay=2", 0)
+    costs = []
+    for s in range(12):
+        a.trainer.next_synthetic_batch(8, 11, 13, padded=False)
+        a.step()
+        costs.append(a.cost())
+    a.trainer.close()
+    assert all(np.isfinite(costs)), costs
+    assert np.mean(costs[-3:]) < np.mean(costs[:3]), costs
