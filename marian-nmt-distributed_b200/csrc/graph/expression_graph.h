@@ -218,6 +218,7 @@ public:
   void forward() {
     device::setDevice(device_);
     params_->allocateForward();
+    backend_->newForwardPass();
     gemmInvalidateCache(backend_->getGemmHandle());
     if(params_->size() > 0) {
       auto vals = params_->vals();

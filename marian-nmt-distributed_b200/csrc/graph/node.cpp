@@ -108,7 +108,7 @@ Ptr<MemoryPiece> ExpressionGraph::uploadIndices(size_t n, BatchFillI fill, Ptr<d
 
 Expr ExpressionGraph::dropout(float prob, Shape shape) {
   auto backend = backend_;
-  auto init = [prob, backend](Tensor t) { Dropout(t, prob, backend->nextDropoutSeed()); };
+  auto init = [prob, backend](Tensor t) { Dropout(t, prob, backend->nextDropoutSeed(), backend->dropoutEpoch()); };
   return constant(shape, keywords::init = std::function<void(Tensor)>(init));
 }
 

@@ -1673,7 +1673,13 @@ __device__ __forceinline__ uint64_t mix64(uint64_t z) {
   z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
   return z ^ (z >> 31);
 }
-__global__ void gDropout(float* mask, size_t n, float p, float scale, uint64_t seed) {
+__global__ void gDropoutEpochBump(uint64_t* epoch) {
+  if(threadIdx.x == 0 && blockIdx.x == 0)
+    *epoch += 1;
+}
+__global__ void gDropout(float* mask, size_t n, float p, float scale, uint64_t seed, const uint64_t* epoch) {
+  if(epoch)
+    seed = mix64(seed ^ (*epoch * 0xD6E8FEB86659FD93ULL));
   for(size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
     uint64_t h = mix64(seed + 0x9E3779B97F4A7C15ULL * (i + 1));
     float u = (float)(h >> 40) * (1.0f / 16777216.0f);  // [0,1)
@@ -1711,10 +1717,14 @@ float L2Norm(Tensor in) {
   return sqrtf(v);
 }
 
-void Dropout(Tensor mask, float dropProb, uint64_t seed) {
+void Dropout(Tensor mask, float dropProb, uint64_t seed, const uint64_t* epoch) {
   device::setDevice(mask->getDevice());
   size_t n = mask->size();
-  gDropout<<<gridFor(n, 256), 256, 0, cudaStreamOfEngine()>>>(mask->data(), n, dropProb, 1.f / (1.f - dropProb), seed);
+  gDropout<<<gridFor(n, 256), 256, 0, cudaStreamOfEngine()>>>(mask->data(), n, dropProb, 1.f / (1.f - dropProb), seed, epoch);
+  CUDA_LAUNCH_CHECK();
+}
+void DropoutEpochBump(uint64_t* epoch) {
+  gDropoutEpochBump<<<1, 32, 0, cudaStreamOfEngine()>>>(epoch);
   CUDA_LAUNCH_CHECK();
 }
 

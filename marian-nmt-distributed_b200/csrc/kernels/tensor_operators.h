@@ -130,7 +130,11 @@ void HighwayBackward(Tensor out1, Tensor out2, Tensor outt, const Tensor in1, co
 
 // Inverted-dropout mask: Bernoulli(1-p)/(1-p) (reference: kernels/dropout.cu:34-42,
 // cuRAND XORWOW there; here a counter-based Philox-style hash keyed by `seed`).
-void Dropout(Tensor mask, float dropProb, uint64_t seed);
+// `epoch` (optional): device counter mixed into the seed.  A step that is captured once and
+// replayed as a CUDA graph has its seeds baked in; the graph bumps *epoch once per forward pass
+// (DropoutEpochBump, also captured), so every replay draws fresh masks.
+void Dropout(Tensor mask, float dropProb, uint64_t seed, const uint64_t* epoch = nullptr);
+void DropoutEpochBump(uint64_t* epoch);
 
 // Fused optimizer kernels over flat parameter tensors (reference:
 // src/optimizers/optimizers.cu:7-73 issues 1-3 Element passes per update and

@@ -1052,7 +1052,11 @@ float L2Norm(Tensor in) {
   return sqrtf((float)s);
 }
 
-void Dropout(Tensor mask, float dropProb, uint64_t seed) {
+void DropoutEpochBump(uint64_t* epoch) {
+  if(epoch)
+    *epoch += 1;
+}
+void Dropout(Tensor mask, float dropProb, uint64_t seed, const uint64_t*) {
   // reference: kernels/dropout.cu:25-42 - uniform(0,1] from cuRAND, then
   // mask = (u >= p) / (1 - p).  The random stream itself is unpinned.
   std::mt19937_64 rng(seed);

@@ -213,3 +213,25 @@ def test_async_group_optimizer_delay(cuda, pkg):
     a.trainer.close()
     assert all(np.isfinite(costs)), costs
     assert np.mean(costs[-3:]) < np.mean(costs[:3]), costs
+
+
+def test_dropout_draws_fresh_masks_on_every_replay(cuda):
+    """Dropout inside a captured step: the seeds are baked into the CUDA graph, a device epoch
+    counter bumped by the graph itself makes every replay draw new masks.  With frozen parameters
+    (learn-rate 0) and the same batch, replayed costs must differ from step to step."""
+    opts = TRANSFORMER + ";gemm-mode=0;graph-replay=true;transformer-dropout=0.3;learn-rate=0"
+    t = cuda.trainer(opts)
+    rs = np.random.RandomState(3)
+    src, trg = rs.randint(2, 200, size=(9, 6)), rs.randint(2, 220, size=(10, 6))
+    ones_s, ones_t = np.ones((9, 6), np.float32), np.ones((10, 6), np.float32)
+    costs = []
+    for s in range(6):
+        t.set_batch(src, ones_s, trg, ones_t)
+        t.compute_gradients()
+        t.update()
+        costs.append(t.cost())
+    st = t.stats()
+    t.close()
+    assert st["replays"] >= 3, st
+    assert len(set(np.round(costs[2:], 4))) == len(costs[2:]), costs   # replays: all different
+    assert np.std(costs) < 0.05 * np.mean(costs), costs               # ... but the same model
