@@ -17,6 +17,9 @@
 // (training/graph_replay.h).
 #pragma once
 
+#include <algorithm>
+#include <chrono>
+#include <cstdio>
 #include <cstdlib>
 #include <list>
 #include <map>
@@ -244,6 +247,10 @@ public:
         device::returnFromSide();
         v->setSideProduced(true);
         pending = true;
+      } else if(nodeTiming()) {
+        auto t0 = std::chrono::steady_clock::now();
+        v->forward();
+        timing_["fwd " + v->type()] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
       } else {
         if(pending) {
           bool fromSide = false;
@@ -291,14 +298,41 @@ public:
       auto v = nodesBackward_.back();
       nodesBackward_.pop_back();
 
-      for(auto&& child : v->children())
-        if(child->trainable())
-          child->set_zero_adjoint();
+      {
+        auto tz = std::chrono::steady_clock::now();
+        for(auto&& child : v->children())
+          if(child->trainable())
+            child->set_zero_adjoint();
+        if(nodeTiming())
+          timing_["(zero adjoints)"] += std::chrono::duration<double>(std::chrono::steady_clock::now() - tz).count();
+      }
 
-      if(v->trainable())
-        v->backward();
+      if(v->trainable()) {
+        if(nodeTiming()) {
+          auto t0 = std::chrono::steady_clock::now();
+          v->backward();
+          timing_["bwd " + v->type()] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        } else {
+          v->backward();
+        }
+      }
 
-      v->children().clear();
+      {
+        auto tz = std::chrono::steady_clock::now();
+        v->children().clear();
+        if(nodeTiming())
+          timing_["(release children)"] += std::chrono::duration<double>(std::chrono::steady_clock::now() - tz).count();
+      }
+    }
+    if(nodeTiming()) {
+      // host wall time per node type: meaningful on the synchronous CPU oracle (MRN_NODE_TIMING=1)
+      std::vector<std::pair<double, std::string>> rows;
+      for(auto& kv : timing_)
+        rows.push_back({kv.second, kv.first});
+      std::sort(rows.rbegin(), rows.rend());
+      for(size_t i = 0; i < rows.size() && i < 14; ++i)
+        fprintf(stderr, "[node-timing] %-40s %8.3f s\n", rows[i].second.c_str(), rows[i].first);
+      timing_.clear();
     }
     device::joinSide();
     tensors_->allocator()->deferFrees(false);
@@ -421,6 +455,11 @@ public:
   };
 
 private:
+  static bool nodeTiming() {
+    static const bool on = std::getenv("MRN_NODE_TIMING") != nullptr;
+    return on;
+  }
+  std::map<std::string, double> timing_;
   size_t count_{0};
   std::list<Expr> nodesForward_;
   std::list<Expr> nodesBackward_;

@@ -18,6 +18,10 @@
 // sentence counts; clipping uses the SHARD's norm; cost is the mean over ranks.
 #pragma once
 
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+
 #include "data/batch.h"
 #include "graph/expression_graph.h"
 #include "models/model_factory.h"
@@ -72,14 +76,23 @@ public:
     }
     lastReplayed_ = false;
     bool capture = !keepLogits && replay_.shouldCapture(key);
+    static const bool timing = std::getenv("MRN_NODE_TIMING") != nullptr;
+    auto t0 = std::chrono::steady_clock::now();
     auto costNode = builder_->build(graph_, batch);
+    auto t1 = std::chrono::steady_clock::now();
     if(capture)
       device::beginCapture();
     graph_->forward();
+    auto t2 = std::chrono::steady_clock::now();
     device::copyD2H(pinnedCost_, costNode->val()->data(), sizeof(float));
     if(keepLogits)
       logits_ = builder_->lastLogits();
     graph_->backward();
+    if(timing) {
+      auto t3 = std::chrono::steady_clock::now();
+      auto sec = [](std::chrono::steady_clock::time_point a, std::chrono::steady_clock::time_point b) { return std::chrono::duration<double>(b - a).count(); };
+      fprintf(stderr, "[node-timing] build %.3f s, forward %.3f s, backward %.3f s (host wall time)\n", sec(t0, t1), sec(t1, t2), sec(t2, t3));
+    }
     if(capture) {
       void* exec = device::endCapture();
       ABORT_IF(!exec, "CUDA graph capture of the training step failed");

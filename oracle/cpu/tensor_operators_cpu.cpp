@@ -19,6 +19,8 @@
 // libm calls as the reference's device code (expf/tanhf/logf/sqrtf); the
 // reference is compiled with --use_fast_math, i.e. its __expf/__logf differ
 // from these by ~1e-6 relative - inside every tolerance used.
+#include <immintrin.h>
+
 #include <cmath>
 #include <cstring>
 #include <random>
@@ -267,48 +269,77 @@ void CrossEntropyPickBackward(Tensor out, Tensor adj, Tensor a, Tensor pick, Ten
 namespace {
 
 // C[M,N] (ldc) (+)= alpha * A[M,K] (lda) * B[K,N] (ldb), all row-major.
+// C[M,N] = alpha * A[M,K] B[K,N] + beta * C, row-major.  Register-blocked 6 x 16 AVX2/FMA
+// micro-kernel (12 accumulator registers) over a B panel packed contiguously per column block;
+// tiles of 96 x 16 outputs are dealt to the OpenMP team.  fp32 accumulation over k in order, like
+// a plain SGEMM; the summation ORDER differs from cuBLAS' (tolerances in the tests absorb it).
 void sgemm_nn(int M, int N, int K, float alpha, const float* A, int lda, const float* B, int ldb, float beta, float* C, int ldc, bool parallel) {
-  constexpr int BM = 8, BN = 64;
-  int mBlocks = (M + BM - 1) / BM, nBlocks = (N + BN - 1) / BN;
-#pragma omp parallel for collapse(2) schedule(static) if(parallel && (long)M * N * K > (1L << 20))
-  for(int mb = 0; mb < mBlocks; ++mb)
-    for(int nb = 0; nb < nBlocks; ++nb) {
-      int i0 = mb * BM, j0 = nb * BN;
-      int im = std::min(BM, M - i0), jn = std::min(BN, N - j0);
-      float acc[BM][BN];
-      for(int i = 0; i < BM; ++i)
-        for(int j = 0; j < BN; ++j)
-          acc[i][j] = 0.f;
-      if(im == BM && jn == BN) {
+  constexpr int MR = 6, NR = 16, MB = 96;
+  const int mBlocks = (M + MB - 1) / MB, nBlocks = (N + NR - 1) / NR;
+#pragma omp parallel if(parallel && (long)M * N * K > (1L << 20))
+  {
+    std::vector<float> panel((size_t)K * NR);
+#pragma omp for collapse(2) schedule(dynamic, 1)
+    for(int nb = 0; nb < nBlocks; ++nb)
+      for(int mb = 0; mb < mBlocks; ++mb) {
+        const int j0 = nb * NR, jn = std::min(NR, N - j0);
+        // pack B[:, j0 .. j0+16) (zero padded) - K x 16 floats, re-used by the 16 micro rows of the tile
         for(int k = 0; k < K; ++k) {
-          const float* b = B + (size_t)k * ldb + j0;
-          for(int i = 0; i < BM; ++i) {
-            float a = A[(size_t)(i0 + i) * lda + k];
-#pragma omp simd
-            for(int j = 0; j < BN; ++j)
-              acc[i][j] += a * b[j];
-          }
+          const float* bsrc = B + (size_t)k * ldb + j0;
+          float* bdst = panel.data() + (size_t)k * NR;
+          for(int j = 0; j < jn; ++j)
+            bdst[j] = bsrc[j];
+          for(int j = jn; j < NR; ++j)
+            bdst[j] = 0.f;
         }
-      } else {
-        for(int k = 0; k < K; ++k) {
-          const float* b = B + (size_t)k * ldb + j0;
+        const int iEnd = std::min(M, (mb + 1) * MB);
+        for(int i0 = mb * MB; i0 < iEnd; i0 += MR) {
+          const int im = std::min(MR, iEnd - i0);
+          float acc[MR][NR];
+          if(im == MR) {
+            __m256 c[MR][2];
+            for(int i = 0; i < MR; ++i)
+              c[i][0] = c[i][1] = _mm256_setzero_ps();
+            const float* a0 = A + (size_t)i0 * lda;
+            for(int k = 0; k < K; ++k) {
+              const __m256 b0 = _mm256_loadu_ps(panel.data() + (size_t)k * NR);
+              const __m256 b1 = _mm256_loadu_ps(panel.data() + (size_t)k * NR + 8);
+#pragma GCC unroll 6
+              for(int i = 0; i < MR; ++i) {
+                const __m256 av = _mm256_broadcast_ss(a0 + (size_t)i * lda + k);
+                c[i][0] = _mm256_fmadd_ps(av, b0, c[i][0]);
+                c[i][1] = _mm256_fmadd_ps(av, b1, c[i][1]);
+              }
+            }
+            for(int i = 0; i < MR; ++i) {
+              _mm256_storeu_ps(acc[i], c[i][0]);
+              _mm256_storeu_ps(acc[i] + 8, c[i][1]);
+            }
+          } else {
+            for(int i = 0; i < im; ++i)
+              for(int j = 0; j < NR; ++j)
+                acc[i][j] = 0.f;
+            for(int k = 0; k < K; ++k) {
+              const float* bp = panel.data() + (size_t)k * NR;
+              for(int i = 0; i < im; ++i) {
+                float av = A[(size_t)(i0 + i) * lda + k];
+                for(int j = 0; j < NR; ++j)
+                  acc[i][j] += av * bp[j];
+              }
+            }
+          }
           for(int i = 0; i < im; ++i) {
-            float a = A[(size_t)(i0 + i) * lda + k];
-            for(int j = 0; j < jn; ++j)
-              acc[i][j] += a * b[j];
+            float* crow = C + (size_t)(i0 + i) * ldc + j0;
+            if(beta == 0.f)
+              for(int j = 0; j < jn; ++j)
+                crow[j] = alpha * acc[i][j];
+            else
+              for(int j = 0; j < jn; ++j)
+                crow[j] = alpha * acc[i][j] + beta * crow[j];
           }
         }
       }
-      for(int i = 0; i < im; ++i) {
-        float* c = C + (size_t)(i0 + i) * ldc + j0;
-        if(beta == 0.f)
-          for(int j = 0; j < jn; ++j)
-            c[j] = alpha * acc[i][j];
-        else
-          for(int j = 0; j < jn; ++j)
-            c[j] = alpha * acc[i][j] + beta * c[j];
-      }
-    }
+  }
 }
 
 void transposeInto(std::vector<float>& dst, const float* src, int rows, int cols) {
