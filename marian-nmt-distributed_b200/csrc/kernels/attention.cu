@@ -390,6 +390,16 @@ __device__ __forceinline__ void warpMmaProduct(const float* As, int lda, const f
   }
 }
 
+// e / n and e % n with a shift when n is a power of two (dk / 4 = 16 and the padded sequence
+// lengths 64 / 128 are): integer division costs ~20 instructions per element otherwise
+struct FastDiv {
+  int n, sh;
+  bool p2;
+  __device__ __forceinline__ explicit FastDiv(int n_) : n(n_), sh(31 - __builtin_clz((unsigned)n_)), p2((1 << (31 - __builtin_clz((unsigned)n_))) == n_) {}
+  __device__ __forceinline__ int div(int e) const { return p2 ? (e >> sh) : (e / n); }
+  __device__ __forceinline__ int mod(int e, int q) const { return p2 ? (e & (n - 1)) : (e - q * n); }
+};
+
 // Asynchronous global -> shared copies (LDGSTS): every thread fires all of its 16-byte pieces
 // and waits ONCE, so a CTA pays one memory round trip for Q, K, V (and dO, P) instead of one per
 // loop iteration of a load/store chain.
@@ -406,8 +416,9 @@ __device__ __forceinline__ void cpAsyncWaitAll() {
 // [T, dk] head slice -> shared memory [Tpad][ld] (asynchronous), rows >= T zero filled
 __device__ __forceinline__ void loadHeadPadded(float* dst, int ld, const float* src, int T, int Tpad, int dk, int d) {
   const int v4 = dk >> 2;
+  const FastDiv fd(v4);
   for(int e = threadIdx.x; e < Tpad * v4; e += blockDim.x) {
-    int r = e / v4, c = (e - r * v4) << 2;
+    int r = fd.div(e), c = fd.mod(e, r) << 2;
     if(r < T)
       cpAsync16(dst + r * ld + c, src + (size_t)r * d + c);
     else
@@ -418,8 +429,9 @@ __device__ __forceinline__ void loadHeadPadded(float* dst, int ld, const float* 
 // shared memory [T][ld] -> [T, dk] head slice of a [B, T, H*dk] tensor, 128-bit coalesced rows
 __device__ __forceinline__ void storeHead(float* dst, const float* src, int ld, int T, int dk, int d, bool accumulate) {
   const int v4 = dk >> 2;
+  const FastDiv fd(v4);
   for(int e = threadIdx.x; e < T * v4; e += blockDim.x) {
-    int r = e / v4, c = (e - r * v4) << 2;
+    int r = fd.div(e), c = fd.mod(e, r) << 2;
     float4 v = *reinterpret_cast<const float4*>(src + r * ld + c);
     float* gp = dst + (size_t)r * d + c;
     if(accumulate) {
@@ -598,32 +610,43 @@ __global__ void __launch_bounds__(kAttnThreads) gAttentionBackwardMma(float* __r
   loadHeadPadded(sdO, L.ldO, dout + offQ, g.Tq, L.TqP, g.dk, d);
   loadHeadPadded(sV, L.ldV, v + offK, g.Tk, L.TkP, g.dk, d);
   const float* pb = probs + (((size_t)b * g.H + h) * g.Tq) * g.Tk;
+  const FastDiv fdk(L.TkP), fdq(L.TqP);
   for(int e = threadIdx.x; e < L.TqP * L.TkP; e += blockDim.x) {
-    int i = e / L.TkP, j = e - i * L.TkP;
+    int i = fdk.div(e), j = fdk.mod(e, i);
     if(i < g.Tq && j < g.Tk)
       cpAsync4(sP + i * L.ldS + j, pb + i * g.Tk + j);
     else
       sP[i * L.ldS + j] = 0.f;
   }
+  // the forward output O (only needed for D_i) rides along into the tile that will hold P^T
+  float* sO = sPT;
+  const int ldOut = g.dk;  // dense rows: dk <= ldT * TkP / TqP is checked by the launcher
+  {
+    const int v4 = g.dk >> 2;
+    const FastDiv fd(v4);
+    for(int e = threadIdx.x; e < g.Tq * v4; e += blockDim.x) {
+      int r = fd.div(e), c = fd.mod(e, r) << 2;
+      cpAsync16(sO + r * ldOut + c, out + offQ + (size_t)r * d + c);
+    }
+  }
   cpAsyncWaitAll();
   __syncthreads();
-  // explicit transposed copy: P^T is the A operand of dV = P^T dO
-  for(int e = threadIdx.x; e < L.TqP * L.TkP; e += blockDim.x) {
-    int j = e / L.TqP, i = e - j * L.TqP;
-    sPT[j * L.ldT + i] = sP[i * L.ldS + j];
-  }
-  // D_i = sum_c dO_ic O_ic (O from global memory)
+  // D_i = sum_c dO_ic O_ic
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for(int i = warp; i < L.TqP; i += nwarps) {
     float s = 0.f;
-    if(i < g.Tq) {
-      const float* orow = out + offQ + (size_t)i * d;
+    if(i < g.Tq)
       for(int c = lane; c < g.dk; c += 32)
-        s = fmaf(sdO[i * L.ldO + c], orow[c], s);
-    }
+        s = fmaf(sdO[i * L.ldO + c], sO[i * ldOut + c], s);
     s = warpSum(s);
     if(lane == 0)
       sD[i] = s;
+  }
+  __syncthreads();
+  // explicit transposed copy (over O): P^T is the A operand of dV = P^T dO
+  for(int e = threadIdx.x; e < L.TqP * L.TkP; e += blockDim.x) {
+    int j = fdq.div(e), i = fdq.mod(e, j);
+    sPT[j * L.ldT + i] = sP[i * L.ldS + j];
   }
   __syncthreads();
 
@@ -764,7 +787,7 @@ void MultiHeadAttentionGrad(Tensor dq, Tensor dk, Tensor dv, const Tensor adj, c
     MmaLayoutBwd L(g);
     size_t smemMma = L.floats() * sizeof(float);
     static const bool forceSimt = std::getenv("MRN_ATTENTION_SIMT") != nullptr;
-    if(!forceSimt && g.dk % 8 == 0 && smemMma <= kSmemLimit) {
+    if(!forceSimt && g.dk % 8 == 0 && smemMma <= kSmemLimit && (size_t)g.Tq * g.dk <= (size_t)L.TkP * L.ldT) {
       static size_t cfgExact = 0, cfgFast = 0;
       if(exact) {
         ensureSmem(gAttentionBackwardMma<true>, smemMma, cfgExact);
