@@ -317,8 +317,19 @@ def main():
             "source_words_per_s": value / 2,
         }
         if prof:
+            # DRAM bytes of the same kernel family from the committed ncu pass (profiles/gemm_dram_rNN.json,
+            # dram__bytes_read.sum + dram__bytes_write.sum over all GEMM launches of one step), per launch
+            traffic = None
+            try:
+                import glob
+                latest = sorted(glob.glob(os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "gemm_dram_r*.json")))[-1]
+                dj = json.load(open(latest))
+                traffic = (dj["dram_read_bytes_per_step"] + dj["dram_write_bytes_per_step"]) / dj["launches_per_step"]
+            except Exception:
+                pass
             out["roofline"] = {"bound": "tensor", "achieved": prof["tflops"], "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                               "frac": prof["tflops"] / pk["bf16_tflops_sustained"], "traffic": None, "peak_source": pk_src,
+                               "frac": prof["tflops"] / pk["bf16_tflops_sustained"], "traffic": traffic, "traffic_unit": "DRAM bytes per launch (mean over the step's launches)",
+                               "algorithmic_flop_per_launch": prof["gflop"] * 1e9 / prof["launches"], "peak_source": pk_src,
                                "kernel": "gGemmTf32|gGemmTcgen05 (all Prod/ProdBatched/ProdAffine launches of one step)",
                                "launches_per_step": prof["launches"], "gemm_ms_per_step": prof["ms"], "gflop_per_step": prof["gflop"]}
         if not args.no_cpu_baseline and world == 1:

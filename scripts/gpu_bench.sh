@@ -11,9 +11,11 @@ if [ -n "$NCU" ]; then
 timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 20000 --csv --log-file gpurun_out/launches.csv python scripts/profile_step.py 2 $MODE > gpurun_out/profile_step.log 2>&1; echo "ncu list rc=$?"; tail -3 gpurun_out/profile_step.log
 fi
 if [ -n "$NCUFULL" ]; then
-# one full capture per kernel family named in $NCUFULL (space separated regexes), a few launches each from the 2nd step
-for k in $NCUFULL; do
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s ${NCUSKIP:-300} -c ${NCUCOUNT:-6} -o gpurun_out/prof_$k -f python scripts/profile_step.py 2 $MODE > gpurun_out/ncu_$k.log 2>&1; echo "ncu $k rc=$?"; tail -2 gpurun_out/ncu_$k.log
+# one full capture per entry of $NCUFULL: "kernelRegex[:skip[:count]]" (space separated)
+for spec in $NCUFULL; do
+  k=${spec%%:*}; rest=${spec#*:}; skip=${NCUSKIP:-100}; cnt=${NCUCOUNT:-4}
+  if [ "$rest" != "$spec" ]; then skip=${rest%%:*}; r2=${rest#*:}; if [ "$r2" != "$rest" ]; then cnt=$r2; fi; fi
+  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$k -s $skip -c $cnt -o gpurun_out/prof_$k -f python scripts/profile_step.py 2 $MODE > gpurun_out/ncu_$k.log 2>&1; echo "ncu $k rc=$?"; tail -2 gpurun_out/ncu_$k.log
 done
 fi
 if [ -n "$NCUDRAM" ]; then
