@@ -1,6 +1,8 @@
-// RNN encoder-decoder with attention ("s2s"; deep variants = Edinburgh/Nematus
-// style stacks).  Layer composition, parameter prefixes and creation order
-// follow the reference's src/models/s2s.h:7-371.
+// RNN encoder-decoder with attention ("s2s"; the deep variants are the Edinburgh / Nematus style
+// stacks).  Behavioural contract = the reference's src/models/s2s.h:7-371: the same layer
+// composition, parameter prefixes and parameter creation order (the order fixes the random
+// initialisation stream).  Organisation is this repo's own: stack recipes are written as small
+// tables (S2SRecipes) that one routine turns into rnn:: factories.
 #pragma once
 
 #include "models/encdec.h"
@@ -8,104 +10,103 @@
 
 namespace marian {
 
+// Shared helpers of encoder and decoder.
+struct S2SRecipes {
+  // factory of one RNN with the model-wide cell options
+  static rnn::rnn stackFactory(Ptr<ExpressionGraph> graph, Ptr<Options> o, const std::string& cellKey, int dimInput, float dropProb) {
+    auto f = rnn::rnn(graph);
+    f("type", o->get<std::string>(cellKey));
+    f("dimInput", dimInput);
+    f("dimState", o->get<int>("dim-rnn"));
+    f("dropout", dropProb);
+    f("layer-normalization", o->get<bool>("layer-normalization"));
+    f("skip", o->get<bool>("skip"));
+    return f;
+  }
+
+  // word-level dropout of an embedding sequence [T, B, d] (one Bernoulli per word)
+  static Expr dropWords(Ptr<ExpressionGraph> graph, Expr sequence, float prob) {
+    if(!prob)
+      return sequence;
+    int words = sequence->shape()[-3];
+    return dropout(sequence, keywords::mask = graph->dropout(prob, {words, 1, 1}));
+  }
+
+  static std::string embeddingName(Ptr<Options> o, const std::string& own, bool sourceSide) {
+    bool all = o->get<bool>("tied-embeddings-all");
+    bool shared = sourceSide ? (o->get<bool>("tied-embeddings-src") || all) : (all || o->get<bool>("tied-embeddings-src"));
+    return shared ? std::string("Wemb") : own + "_Wemb";
+  }
+};
+
 class EncoderS2S : public EncoderBase {
 public:
   EncoderS2S(Ptr<Options> options) : EncoderBase(options) {}
 
-  // reference: s2s.h:9-99
-  Expr applyEncoderRNN(Ptr<ExpressionGraph> graph, Expr embeddings, Expr mask, std::string type) {
+  // enc-type "bidirectional" / "alternating": two full-depth stacks run in opposite directions,
+  // top outputs concatenated.  Otherwise ("bi-unidirectional"): ONE bidirectional layer, then
+  // enc-depth - 1 unidirectional layers over the concatenation.        (reference :9-99)
+  Expr encode(Ptr<ExpressionGraph> graph, Expr embeddings, Expr mask) {
     using namespace keywords;
-    int first, second;
-    if(type == "bidirectional" || type == "alternating") {
-      // build two separate stacks, concatenate top outputs
-      first = opt<int>("enc-depth");
-      second = 0;
-    } else {
-      // one bidirectional layer, then unidirectional layers on top
-      first = 1;
-      second = opt<int>("enc-depth") - first;
-    }
+    const std::string kind = opt<std::string>("enc-type");
+    const bool twoStacks = kind == "bidirectional" || kind == "alternating";
+    const int depth = opt<int>("enc-depth");
+    const int biLayers = twoStacks ? depth : 1;
+    const int cellDepth = opt<int>("enc-cell-depth");
+    const float dropProb = inference_ ? 0 : opt<float>("dropout-rnn");
 
-    auto forward = type == "alternating" ? rnn::dir::alternating_forward : rnn::dir::forward;
-    auto backward = type == "alternating" ? rnn::dir::alternating_backward : rnn::dir::backward;
-
-    float dropoutRnn = inference_ ? 0 : opt<float>("dropout-rnn");
-
-    auto makeStack = [&](rnn::dir direction, const std::string& base) {
-      auto r = rnn::rnn(graph)("type", opt<std::string>("enc-cell"))("direction", direction)(
-          "dimInput", embeddings->shape()[-1])("dimState", opt<int>("dim-rnn"))("dropout", dropoutRnn)(
-          "layer-normalization", opt<bool>("layer-normalization"))("skip", opt<bool>("skip"));
-      for(int i = 1; i <= first; ++i) {
-        auto stacked = rnn::stacked_cell(graph);
-        for(int j = 1; j <= opt<int>("enc-cell-depth"); ++j) {
-          std::string paramPrefix = base;
-          if(i > 1)
-            paramPrefix += "_l" + std::to_string(i);
-          if(i > 1 || j > 1)
-            paramPrefix += "_cell" + std::to_string(j);
-          bool transition = (j > 1);
-          stacked.push_back(rnn::cell(graph)("prefix", paramPrefix)("transition", transition));
-        }
-        r.push_back(stacked);
+    // cell names of layer i, position j of a directional stack rooted at `base`
+    auto cellName = [](const std::string& base, int layer, int pos) {
+      std::string n = base;
+      if(layer > 1)
+        n += "_l" + std::to_string(layer);
+      if(layer > 1 || pos > 1)
+        n += "_cell" + std::to_string(pos);
+      return n;
+    };
+    auto directional = [&](rnn::dir direction, const std::string& base) {
+      auto f = S2SRecipes::stackFactory(graph, options_, "enc-cell", embeddings->shape()[-1], dropProb);
+      f("direction", direction);
+      for(int layer = 1; layer <= biLayers; ++layer) {
+        auto cells = rnn::stacked_cell(graph);
+        for(int pos = 1; pos <= cellDepth; ++pos)
+          cells.push_back(rnn::cell(graph)("prefix", cellName(base, layer, pos))("transition", pos > 1));
+        f.push_back(cells);
       }
-      return r;
+      return f;
     };
 
-    auto rnnFw = makeStack(forward, prefix_ + "_bi");
-    auto rnnBw = makeStack(backward, prefix_ + "_bi_r");
+    const bool alternate = kind == "alternating";
+    auto left = directional(alternate ? rnn::dir::alternating_forward : rnn::dir::forward, prefix_ + "_bi");
+    auto right = directional(alternate ? rnn::dir::alternating_backward : rnn::dir::backward, prefix_ + "_bi_r");
+    // forward stack first: its parameters are created (and seeded) before the backward stack's
+    Expr fw = left->transduce(embeddings, mask);
+    Expr bw = right->transduce(embeddings, mask);
+    Expr context = concatenate({fw, bw}, axis = -1);
 
-    // NB: C++ leaves the evaluation order of the two transduce() calls inside
-    // the reference's braced list well-defined (left to right): forward first.
-    auto fw = rnnFw->transduce(embeddings, mask);
-    auto bw = rnnBw->transduce(embeddings, mask);
-    auto context = concatenate({fw, bw}, axis = -1);
-
-    if(second > 0) {
-      auto rnnUni = rnn::rnn(graph)("type", opt<std::string>("enc-cell"))("dimInput", 2 * opt<int>("dim-rnn"))(
-          "dimState", opt<int>("dim-rnn"))("dropout", dropoutRnn)("layer-normalization",
-                                                                    opt<bool>("layer-normalization"))("skip", opt<bool>("skip"));
-      for(int i = first + 1; i <= second + first; ++i) {
-        auto stacked = rnn::stacked_cell(graph);
-        for(int j = 1; j <= opt<int>("enc-cell-depth"); ++j) {
-          std::string paramPrefix = prefix_ + "_l" + std::to_string(i) + "_cell" + std::to_string(j);
-          stacked.push_back(rnn::cell(graph)("prefix", paramPrefix));
-        }
-        rnnUni.push_back(stacked);
+    if(!twoStacks && depth > 1) {
+      auto upper = S2SRecipes::stackFactory(graph, options_, "enc-cell", 2 * opt<int>("dim-rnn"), dropProb);
+      for(int layer = 2; layer <= depth; ++layer) {
+        auto cells = rnn::stacked_cell(graph);
+        for(int pos = 1; pos <= cellDepth; ++pos)
+          cells.push_back(rnn::cell(graph)("prefix", prefix_ + "_l" + std::to_string(layer) + "_cell" + std::to_string(pos)));
+        upper.push_back(cells);
       }
-      context = rnnUni->transduce(context);
+      context = upper->transduce(context);
     }
     return context;
   }
 
-  Expr buildSourceEmbeddings(Ptr<ExpressionGraph> graph) {
-    int dimVoc = opt<std::vector<int>>("dim-vocabs")[batchIndex_];
-    int dimEmb = opt<int>("dim-emb");
-    auto embFactory = embedding(graph)("dimVocab", dimVoc)("dimEmb", dimEmb);
-    if(opt<bool>("tied-embeddings-src") || opt<bool>("tied-embeddings-all"))
-      embFactory("prefix", "Wemb");
-    else
-      embFactory("prefix", prefix_ + "_Wemb");
-    if(options_->has("embedding-fix-src"))
-      embFactory("fixed", opt<bool>("embedding-fix-src"));
-    return embFactory.construct();
-  }
-
   virtual Ptr<EncoderState> build(Ptr<ExpressionGraph> graph, Ptr<data::CorpusBatch> batch) {
-    using namespace keywords;
-    auto embeddings = buildSourceEmbeddings(graph);
+    auto table = embedding(graph)("dimVocab", opt<std::vector<int>>("dim-vocabs")[batchIndex_])("dimEmb", opt<int>("dim-emb"));
+    table("prefix", S2SRecipes::embeddingName(options_, prefix_, true));
+    if(options_->has("embedding-fix-src"))
+      table("fixed", opt<bool>("embedding-fix-src"));
 
-    Expr batchEmbeddings, batchMask;
-    std::tie(batchEmbeddings, batchMask) = EncoderBase::lookup(embeddings, batch);
-
-    float dropProb = inference_ ? 0 : opt<float>("dropout-src");
-    if(dropProb) {
-      int srcWords = batchEmbeddings->shape()[-3];
-      auto dropMask = graph->dropout(dropProb, {srcWords, 1, 1});
-      batchEmbeddings = dropout(batchEmbeddings, mask = dropMask);
-    }
-
-    Expr context = applyEncoderRNN(graph, batchEmbeddings, batchMask, opt<std::string>("enc-type"));
-    return New<EncoderState>(context, batchMask, batch);
+    Expr words, padding;
+    std::tie(words, padding) = EncoderBase::lookup(table.construct(), batch);
+    words = S2SRecipes::dropWords(graph, words, inference_ ? 0 : opt<float>("dropout-src"));
+    return New<EncoderState>(encode(graph, words, padding), padding, batch);
   }
 
   void clear() {}
@@ -115,134 +116,86 @@ class DecoderS2S : public DecoderBase {
 private:
   Ptr<rnn::RNN> rnn_;
 
-  // reference: s2s.h:178-234
-  Ptr<rnn::RNN> constructDecoderRNN(Ptr<ExpressionGraph> graph, Ptr<DecoderState> state) {
-    float dropoutRnn = inference_ ? 0 : opt<float>("dropout-rnn");
-    auto rnn = rnn::rnn(graph)("type", opt<std::string>("dec-cell"))("dimInput", opt<int>("dim-emb"))(
-        "dimState", opt<int>("dim-rnn"))("dropout", dropoutRnn)("layer-normalization", opt<bool>("layer-normalization"))(
-        "skip", opt<bool>("skip"));
+  // Layer 1 is the conditional cell: cell1 -> one attention per encoder -> cell2 [-> transition
+  // cells]; layers 2.. are plain stacks of dec-cell-high-depth cells.     (reference :178-234)
+  Ptr<rnn::RNN> makeRnn(Ptr<ExpressionGraph> graph, Ptr<DecoderState> state) {
+    auto f = S2SRecipes::stackFactory(graph, options_, "dec-cell", opt<int>("dim-emb"), inference_ ? 0 : opt<float>("dropout-rnn"));
+    const auto& encoders = state->getEncoderStates();
 
-    size_t decoderLayers = opt<size_t>("dec-depth");
-    size_t decoderBaseDepth = opt<size_t>("dec-cell-base-depth");
-    size_t decoderHighDepth = opt<size_t>("dec-cell-high-depth");
-
-    // conditional GRU: cell1 -> attention -> cell2 [-> transition cells]
-    auto baseCell = rnn::stacked_cell(graph);
-    for(size_t i = 1; i <= decoderBaseDepth; ++i) {
-      bool transition = (i > 2);
-      auto paramPrefix = prefix_ + "_cell" + std::to_string(i);
-      baseCell.push_back(rnn::cell(graph)("prefix", paramPrefix)("final", i > 1)("transition", transition));
-      if(i == 1) {
-        for(size_t k = 0; k < state->getEncoderStates().size(); ++k) {
-          auto attPrefix = prefix_;
-          if(state->getEncoderStates().size() > 1)
-            attPrefix += "_att" + std::to_string(k + 1);
-          auto encState = state->getEncoderStates()[k];
-          baseCell.push_back(rnn::attention(graph)("prefix", attPrefix).set_state(encState));
-        }
+    auto conditional = rnn::stacked_cell(graph);
+    const size_t baseDepth = opt<size_t>("dec-cell-base-depth");
+    for(size_t pos = 1; pos <= baseDepth; ++pos) {
+      conditional.push_back(rnn::cell(graph)("prefix", prefix_ + "_cell" + std::to_string(pos))("final", pos > 1)("transition", pos > 2));
+      if(pos != 1)
+        continue;
+      for(size_t e = 0; e < encoders.size(); ++e) {
+        std::string name = encoders.size() > 1 ? prefix_ + "_att" + std::to_string(e + 1) : prefix_;
+        conditional.push_back(rnn::attention(graph)("prefix", name).set_state(encoders[e]));
       }
     }
-    rnn.push_back(baseCell);
+    f.push_back(conditional);
 
-    for(size_t i = 2; i <= decoderLayers; ++i) {
-      auto highCell = rnn::stacked_cell(graph);
-      for(size_t j = 1; j <= decoderHighDepth; j++) {
-        auto paramPrefix = prefix_ + "_l" + std::to_string(i) + "_cell" + std::to_string(j);
-        highCell.push_back(rnn::cell(graph)("prefix", paramPrefix));
-      }
-      rnn.push_back(highCell);
+    const size_t layers = opt<size_t>("dec-depth"), highDepth = opt<size_t>("dec-cell-high-depth");
+    for(size_t layer = 2; layer <= layers; ++layer) {
+      auto cells = rnn::stacked_cell(graph);
+      for(size_t pos = 1; pos <= highDepth; ++pos)
+        cells.push_back(rnn::cell(graph)("prefix", prefix_ + "_l" + std::to_string(layer) + "_cell" + std::to_string(pos)));
+      f.push_back(cells);
     }
-    return rnn.construct();
+    return f.construct();
   }
+
+  Ptr<rnn::Attention> attentionOf(size_t encoder) { return rnn_->at(0)->as<rnn::StackedCell>()->at((int)encoder + 1)->as<rnn::Attention>(); }
 
 public:
   DecoderS2S(Ptr<Options> options) : DecoderBase(options) {}
 
-  // reference: s2s.h:239-277
-  virtual Ptr<DecoderState> startState(Ptr<ExpressionGraph> graph,
-                                       Ptr<data::CorpusBatch> batch,
-                                       std::vector<Ptr<EncoderState>>& encStates) {
+  // start state = tanh(W mean_t(context) + b) for every layer (zeros without an encoder)   (:239-277)
+  virtual Ptr<DecoderState> startState(Ptr<ExpressionGraph> graph, Ptr<data::CorpusBatch> batch, std::vector<Ptr<EncoderState>>& encStates) {
     using namespace keywords;
-
-    std::vector<Expr> meanContexts;
-    for(auto& encState : encStates)
-      meanContexts.push_back(weighted_average(encState->getContext(), encState->getMask(), axis = -3));
-
     Expr start;
-    if(!meanContexts.empty()) {
-      auto mlp = mlp::mlp(graph).push_back(mlp::dense(graph)("prefix", prefix_ + "_ff_state")("dim", opt<int>("dim-rnn"))(
-          "activation", mlp::act::tanh)("layer-normalization", opt<bool>("layer-normalization")));
-      auto built = mlp.construct();
-      start = meanContexts.size() == 1 ? built->apply(meanContexts[0]) : Expr();
-      ABORT_IF(!start, "multi-encoder start state is not supported");
+    if(encStates.empty()) {
+      start = graph->constant({(int)batch->size(), opt<int>("dim-rnn")}, init = inits::zeros);
     } else {
-      int dimBatch = (int)batch->size();
-      int dimRnn = opt<int>("dim-rnn");
-      start = graph->constant({dimBatch, dimRnn}, init = inits::zeros);
+      ABORT_IF(encStates.size() != 1, "multi-encoder start state is not supported");
+      Expr meanContext = weighted_average(encStates[0]->getContext(), encStates[0]->getMask(), axis = -3);
+      auto bridge = mlp::dense(graph)("prefix", prefix_ + "_ff_state")("dim", opt<int>("dim-rnn"))("activation", mlp::act::tanh)(
+          "layer-normalization", opt<bool>("layer-normalization"));
+      start = mlp::mlp(graph).push_back(bridge).construct()->apply(meanContext);
     }
-
-    rnn::States startStates(opt<size_t>("dec-depth"), {start, start});
-    return New<DecoderState>(startStates, nullptr, encStates);
+    return New<DecoderState>(rnn::States(opt<size_t>("dec-depth"), {start, start}), nullptr, encStates);
   }
 
-  // reference: s2s.h:279-361
+  // all target positions at once in training; logits = W2 tanh(W1 [embedding; state; context])   (:279-361)
   virtual Ptr<DecoderState> step(Ptr<ExpressionGraph> graph, Ptr<DecoderState> state) {
     using namespace keywords;
-
-    auto embeddings = state->getTargetEmbeddings();
-
-    float dropoutTrg = inference_ ? 0 : opt<float>("dropout-trg");
-    if(dropoutTrg) {
-      int trgWords = embeddings->shape()[-3];
-      auto trgWordDrop = graph->dropout(dropoutTrg, {trgWords, 1, 1});
-      embeddings = dropout(embeddings, mask = trgWordDrop);
-    }
-
+    Expr words = S2SRecipes::dropWords(graph, state->getTargetEmbeddings(), inference_ ? 0 : opt<float>("dropout-trg"));
     if(!rnn_)
-      rnn_ = constructDecoderRNN(graph, state);
+      rnn_ = makeRnn(graph, state);
 
-    auto decoderContext = rnn_->transduce(embeddings, state->getStates());
-    rnn::States decoderStates = rnn_->lastCellStates();
+    Expr states = rnn_->transduce(words, state->getStates());
+    rnn::States carried = rnn_->lastCellStates();
 
-    std::vector<Expr> alignedContexts;
-    for(size_t k = 0; k < state->getEncoderStates().size(); ++k) {
-      auto att = rnn_->at(0)->as<rnn::StackedCell>()->at((int)k + 1)->as<rnn::Attention>();
-      alignedContexts.push_back(att->getContext());
-    }
+    std::vector<Expr> contexts;
+    for(size_t e = 0; e < state->getEncoderStates().size(); ++e)
+      contexts.push_back(attentionOf(e)->getContext());
 
-    Expr alignedContext;
-    if(alignedContexts.size() > 1)
-      alignedContext = concatenate(alignedContexts, axis = -1);
-    else if(alignedContexts.size() == 1)
-      alignedContext = alignedContexts[0];
-
-    auto layer1 = mlp::dense(graph)("prefix", prefix_ + "_ff_logit_l1")("dim", opt<int>("dim-emb"))(
-        "activation", mlp::act::tanh)("layer-normalization", opt<bool>("layer-normalization"));
-
-    int dimTrgVoc = opt<std::vector<int>>("dim-vocabs")[batchIndex_];
-    auto layer2 = mlp::dense(graph)("prefix", prefix_ + "_ff_logit_l2")("dim", dimTrgVoc);
-    if(opt<bool>("tied-embeddings") || opt<bool>("tied-embeddings-all")) {
-      std::string tiedPrefix = prefix_ + "_Wemb";
-      if(opt<bool>("tied-embeddings-all") || opt<bool>("tied-embeddings-src"))
-        tiedPrefix = "Wemb";
-      layer2.tie_transposed("W", tiedPrefix);
-    }
-
-    auto output = mlp::mlp(graph).push_back(layer1).push_back(layer2);
+    auto hidden = mlp::dense(graph)("prefix", prefix_ + "_ff_logit_l1")("dim", opt<int>("dim-emb"))("activation", mlp::act::tanh)(
+        "layer-normalization", opt<bool>("layer-normalization"));
+    auto vocabulary = mlp::dense(graph)("prefix", prefix_ + "_ff_logit_l2")("dim", opt<std::vector<int>>("dim-vocabs")[batchIndex_]);
+    if(opt<bool>("tied-embeddings") || opt<bool>("tied-embeddings-all"))
+      vocabulary.tie_transposed("W", S2SRecipes::embeddingName(options_, prefix_, false));
+    auto readout = mlp::mlp(graph).push_back(hidden).push_back(vocabulary);
 
     Expr logits;
-    if(alignedContext)
-      logits = output->apply(embeddings, decoderContext, alignedContext);
+    if(contexts.empty())
+      logits = readout->apply(words, states);
     else
-      logits = output->apply(embeddings, decoderContext);
-
-    return New<DecoderState>(decoderStates, logits, state->getEncoderStates());
+      logits = readout->apply(words, states, contexts.size() == 1 ? contexts[0] : concatenate(contexts, axis = -1));
+    return New<DecoderState>(carried, logits, state->getEncoderStates());
   }
 
-  virtual const std::vector<Expr> getAlignments(int i = 0) {
-    auto att = rnn_->at(0)->as<rnn::StackedCell>()->at(i + 1)->as<rnn::Attention>();
-    return att->getAlignments();
-  }
+  virtual const std::vector<Expr> getAlignments(int i = 0) { return attentionOf((size_t)i)->getAlignments(); }
 
   void clear() { rnn_ = nullptr; }
 };
