@@ -300,6 +300,14 @@ def main():
         pk, pk_src = peaks()
         # roofline of the tensor-core GEMM family: algorithmic flops of one step / their device time
         prof = gemm_profile(lib, pkg, args.gemm_mode, local_rank) if world == 1 else None
+        # same replayed step without event nodes: per-launch kernel execution spans from %globaltimer
+        spans = None
+        if world == 1 and prof:
+            os.environ["MRN_GEMM_SPANS"] = "1"
+            try:
+                spans = gemm_profile(lib, pkg, args.gemm_mode, local_rank)
+            finally:
+                os.environ.pop("MRN_GEMM_SPANS", None)
         out = {
             "metric": METRIC, "value": value, "unit": "words/s", "n_gpus": world, "steps": K, "warmup": W,
             "ms_per_step": ms / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -327,11 +335,21 @@ def main():
                 traffic = (dj["dram_read_bytes_per_step"] + dj["dram_write_bytes_per_step"]) / dj["launches_per_step"]
             except Exception:
                 pass
-            out["roofline"] = {"bound": "tensor", "achieved": prof["tflops"], "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
-                               "frac": prof["tflops"] / pk["bf16_tflops_sustained"], "traffic": traffic, "traffic_unit": "DRAM bytes per launch (mean over the step's launches)",
+            # Primary duration = kernel execution span inside the replayed graph (first CTA start .. last CTA
+            # end from %globaltimer, folded per launch by the kernel itself; no extra graph nodes).  CUDA event
+            # pairs recorded around each launch inside the graph are reported next to it: an external
+            # event-record node costs ~3.3 us on this GPU (profiles/graph_gap_probe_r01.json), i.e. the event
+            # figure charges ~6.7 us of graph-node latency to every launch.
+            main = spans if spans else prof
+            out["roofline"] = {"bound": "tensor", "achieved": main["tflops"], "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                               "frac": main["tflops"] / pk["bf16_tflops_sustained"], "traffic": traffic,
+                               "traffic_unit": "DRAM bytes per launch (mean over the step's launches)",
                                "algorithmic_flop_per_launch": prof["gflop"] * 1e9 / prof["launches"], "peak_source": pk_src,
-                               "kernel": "gGemmTf32|gGemmTcgen05 (all Prod/ProdBatched/ProdAffine launches of one step)",
-                               "launches_per_step": prof["launches"], "gemm_ms_per_step": prof["ms"], "gflop_per_step": prof["gflop"]}
+                               "kernel": "gGemmTf32 (all Prod/ProdBatched/ProdAffine launches of one replayed step)",
+                               "duration_source": "in-kernel %globaltimer spans" if spans else "CUDA event pairs inside the graph",
+                               "launches_per_step": prof["launches"], "gemm_ms_per_step": main["ms"], "gflop_per_step": prof["gflop"],
+                               "cuda_event_pairs": {"gemm_ms_per_step": prof["ms"], "achieved": prof["tflops"], "frac": prof["tflops"] / pk["bf16_tflops_sustained"],
+                                                    "note": "each pair includes ~6.7 us of event-record node latency"}}
         if not args.no_cpu_baseline and world == 1:
             out["cpu_baseline"] = cpu_baseline_sample()  # rank 0 at N=1 only
         print(json.dumps(out))

@@ -67,6 +67,8 @@ int mrn_gemm_set_mode(void* handle, int mode);
  * CUDA events on the engine stream; enable == 0 stops and returns total ms, algorithmic
  * flops (2MNK) and launch count.  Eager steps only (not inside a replayed graph). */
 int mrn_gemm_profile(int enable, double* ms, double* flops, size_t* launches);
+/* tuning aid: per-CTA timestamps (5 x uint64 per CTA) of the next tf32 GEMM launches; NULL disarms */
+int mrn_gemm_debug_stamps(void* device_buffer);
 
 /* Prod / ProdBatched: tensor_operators.h:295-311, .cu:543-654 */
 int mrn_prod(void* gemm, mrn_tensor C, mrn_tensor A, mrn_tensor B, int transA, int transB, float beta, float scalar);

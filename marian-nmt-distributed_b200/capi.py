@@ -35,6 +35,7 @@ _SIGNATURES = {
     "mrn_gemm_create": [ctypes.POINTER(_V), _I],
     "mrn_gemm_destroy": [_V],
     "mrn_gemm_set_mode": [_V, _I],
+    "mrn_gemm_debug_stamps": [_V],
     "mrn_gemm_profile": [_I, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(_SZ)],
     "mrn_prod": [_V, _T, _T, _T, _I, _I, _F, _F],
     "mrn_prod_batched": [_V, _T, _T, _T, _I, _I, _F, _F],

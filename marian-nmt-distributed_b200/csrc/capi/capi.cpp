@@ -115,6 +115,9 @@ int mrn_gemm_set_mode(void* handle, int mode) {
   return guarded([&] { setGemmMode((GemmHandle)handle, (GemmMode)mode); });
 }
 
+int mrn_gemm_debug_stamps(void* deviceBuffer) {
+  return guarded([&] { gemmDebugStamps((unsigned long long*)deviceBuffer); });
+}
 int mrn_gemm_profile(int enable, double* ms, double* flops, size_t* launches) {
   return guarded([&] { gemmProfile(enable, ms, flops, launches); });
 }

@@ -136,11 +136,26 @@ void gemmSetStableRange(GemmHandle h, const void* lo, size_t bytes) {
 
 // ---- optional per-launch timing of the tensor-core kernel (bench.py roofline) ----
 namespace {
+unsigned long long* g_stampBuffer = nullptr;
+}
+// tuning aid: per-CTA timestamps of the next tf32 launches are written to `deviceBuffer`
+// (5 x u64 per CTA: start, prologue done, first operands, accumulator complete, end); null disarms
+void gemmDebugStamps(unsigned long long* deviceBuffer) {
+  g_stampBuffer = deviceBuffer;
+}
+namespace {
 struct GemmProfile {
   bool enabled{false};
   double flops{0};
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> events;
   std::vector<std::string> labels;  // one per event pair: "M,N,K,batches,layout,splits"
+  // span mode (MRN_GEMM_SPANS=1): no event nodes; every CTA of a profiled launch folds its
+  // %globaltimer start / end into per-launch min / max slots -> pure kernel execution spans
+  bool spans{false};
+  unsigned long long* spanMin{nullptr};
+  unsigned long long* spanMax{nullptr};
+  size_t spanCount{0};
+  static constexpr size_t kMaxSpans = 8192;
 };
 GemmProfile g_profile;
 }  // namespace
@@ -158,6 +173,12 @@ void gemmProfile(int enable, double* ms, double* flops, size_t* launches) {
     g_profile.labels.clear();
     g_profile.flops = 0;
     g_profile.enabled = true;
+    g_profile.spans = std::getenv("MRN_GEMM_SPANS") != nullptr;
+    g_profile.spanCount = 0;
+    if(g_profile.spans && !g_profile.spanMin) {
+      g_profile.spanMin = (unsigned long long*)device::mallocDevice(GemmProfile::kMaxSpans * 8);
+      g_profile.spanMax = (unsigned long long*)device::mallocDevice(GemmProfile::kMaxSpans * 8);
+    }
     *ms = 0;
     *flops = 0;
     *launches = 0;
@@ -169,7 +190,27 @@ void gemmProfile(int enable, double* ms, double* flops, size_t* launches) {
   // MRN_GEMM_PROFILE_DUMP=<file>: one CSV line per launch (shape, layout, in-graph microseconds)
   FILE* dump = nullptr;
   if(const char* path = std::getenv("MRN_GEMM_PROFILE_DUMP"))
-    dump = fopen(path, "w");
+    dump = fopen((std::string(path) + (g_profile.spans ? ".spans" : "")).c_str(), "w");
+  if(g_profile.spans) {
+    size_t n = std::min(g_profile.spanCount, GemmProfile::kMaxSpans);
+    std::vector<unsigned long long> mn(n), mx(n);
+    if(n) {
+      CUDA_CHECK(cudaMemcpy(mn.data(), g_profile.spanMin, n * 8, cudaMemcpyDeviceToHost));
+      CUDA_CHECK(cudaMemcpy(mx.data(), g_profile.spanMax, n * 8, cudaMemcpyDeviceToHost));
+    }
+    for(size_t i = 0; i < n; ++i) {
+      double us = mx[i] > mn[i] ? (double)(mx[i] - mn[i]) / 1000.0 : 0.0;
+      total += us / 1000.0;
+      if(dump)
+        fprintf(dump, "%s,%.2f\n", i < g_profile.labels.size() ? g_profile.labels[i].c_str() : "?", us);
+    }
+    if(dump)
+      fclose(dump);
+    *ms = total;
+    *flops = g_profile.flops;
+    *launches = n;
+    return;
+  }
   for(size_t i = 0; i < g_profile.events.size(); ++i) {
     auto& e = g_profile.events[i];
     float t = 0;
@@ -193,10 +234,26 @@ namespace {
 struct ProfileScope {
   cudaEvent_t e0{nullptr}, e1{nullptr};
   bool on{false};
+  unsigned long long* spanMin{nullptr};
+  unsigned long long* spanMax{nullptr};
   explicit ProfileScope(double flops) {
     on = g_profile.enabled;
     if(!on)
       return;
+    if(g_profile.spans) {
+      if(g_profile.spanCount == 0) {
+        // (re)armed at the first profiled launch of a step - inside the captured graph too
+        CUDA_CHECK(cudaMemsetAsync(g_profile.spanMin, 0xFF, GemmProfile::kMaxSpans * 8, cudaStreamOfEngine()));
+        CUDA_CHECK(cudaMemsetAsync(g_profile.spanMax, 0x00, GemmProfile::kMaxSpans * 8, cudaStreamOfEngine()));
+      }
+      if(g_profile.spanCount < GemmProfile::kMaxSpans) {
+        spanMin = g_profile.spanMin + g_profile.spanCount;
+        spanMax = g_profile.spanMax + g_profile.spanCount;
+      }
+      g_profile.spanCount++;
+      g_profile.flops += flops;
+      return;
+    }
     CUDA_CHECK(cudaEventCreate(&e0));
     CUDA_CHECK(cudaEventCreate(&e1));
     record(e0);
@@ -205,6 +262,10 @@ struct ProfileScope {
   void finish(const std::string& label = std::string()) {
     if(!on)
       return;
+    if(g_profile.spans) {
+      g_profile.labels.push_back(label);
+      return;
+    }
     record(e1);
     g_profile.events.push_back({e0, e1});
     g_profile.labels.push_back(label);
@@ -549,6 +610,9 @@ struct TcArgs {
   size_t strideC;
   float alpha, beta;
   int atomicOut;  // combine with red.add (split-K)
+  unsigned long long* stamps;  // tuning aid: per-CTA %globaltimer stamps (5 per CTA), or null
+  unsigned long long* spanMin;  // profiling: per-launch min(start) / max(end) over the CTAs, or null
+  unsigned long long* spanMax;
 };
 
 template <int BN>
@@ -855,6 +919,16 @@ __global__ void __launch_bounds__(192) gGemmTf32(const __grid_constant__ CUtenso
   pdlTrigger();  // the next kernel may start launching; it waits for our completion in its own pdlWait()
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  unsigned long long* stamp = a.stamps ? a.stamps + 5 * ((size_t)blockIdx.x + (size_t)gridDim.x * (blockIdx.y + (size_t)gridDim.y * blockIdx.z)) : nullptr;
+  auto now = [] {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+  };
+  if(stamp && threadIdx.x == 0)
+    stamp[0] = now();  // CTA start
+  if(a.spanMin && threadIdx.x == 0)
+    atomicMin(a.spanMin, now());
 
   const int m0 = blockIdx.x * BLOCK_M;
   const int n0 = blockIdx.y * BN;
@@ -884,6 +958,8 @@ __global__ void __launch_bounds__(192) gGemmTf32(const __grid_constant__ CUtenso
   // everything above (barrier init, TMEM allocation, descriptor prefetch) overlapped the tail
   // of the previous kernel; operands and C are only touched from here on
   pdlWait();
+  if(stamp && threadIdx.x == 0)
+    stamp[1] = now();  // prologue done (barriers, TMEM, descriptors)
 
   if(warp == 0) {
     if(lane == 0) {
@@ -924,6 +1000,8 @@ __global__ void __launch_bounds__(192) gGemmTf32(const __grid_constant__ CUtenso
         int s = i % STAGES;
         uint32_t phase = (uint32_t)(i / STAGES) & 1u;
         mbarWait(fullBar + s, phase);
+        if(stamp && i == 0)
+          stamp[2] = now();  // first operands landed
         tcgenFenceAfter();
         uint32_t sa = smemAddr(smem + s * L::STAGE_BYTES);
         uint32_t sb = sa + L::A_BYTES;
@@ -938,11 +1016,19 @@ __global__ void __launch_bounds__(192) gGemmTf32(const __grid_constant__ CUtenso
     }
   } else {
     float* stage = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * kStagePitch);
+    if(stamp && threadIdx.x == 64) {
+      mbarWait(tmemFullBar, 0);
+      stamp[3] = now();  // accumulator complete
+    }
     epilogueTile<BN>(a, tmemBase, tmemFullBar, stage, warp, lane, m0, n0, batch, split);
   }
 
   tcgenFenceBefore();
   __syncthreads();
+  if(stamp && threadIdx.x == 0)
+    stamp[4] = now();  // epilogue done
+  if(a.spanMax && threadIdx.x == 0)
+    atomicMax(a.spanMax, now());
   if(warp == 1) {
     __syncwarp();
     tcgenFenceAfter();
@@ -1052,6 +1138,8 @@ void runTensorCore(GemmHandle h, const GemmProblem& p) {
   a.strideC = (size_t)M * N;
   a.alpha = p.alpha;
   a.beta = p.beta;
+  a.stamps = nullptr;
+  a.spanMin = a.spanMax = nullptr;
 
   // split-K when the tile grid cannot fill the SMs but K is long (weight gradients)
   long tiles = (long)((M + BLOCK_M - 1) / BLOCK_M) * ((N + BN - 1) / BN) * p.batches;
@@ -1174,6 +1262,15 @@ bool runTf32(GemmHandle h, const GemmProblem& p) {
   }
   if(const char* forced = std::getenv("MRN_GEMM_BN"))  // tuning aid (scripts/gemm_probe.py)
     BN = std::atoi(forced) == 128 ? 128 : 64;
+  // tuning aid: "MRN_GEMM_TRY=M,N,K,beta,BN,splits" overrides the choice for one problem shape
+  if(const char* t = std::getenv("MRN_GEMM_TRY")) {
+    int m, n, k, bn, sp;
+    float be;
+    if(sscanf(t, "%d,%d,%d,%f,%d,%d", &m, &n, &k, &be, &bn, &sp) == 6 && m == M && n == N && k == K && be == p.beta && !batched) {
+      BN = bn == 128 ? 128 : 64;
+      splits = std::max(1, sp);
+    }
+  }
 
   uint64_t batchesA = p.strideA ? p.batches : 1, batchesB = p.strideB ? p.batches : 1;
   // stored matrices are [rows, cols] row-major: inner = cols, outer = rows
@@ -1187,6 +1284,7 @@ bool runTf32(GemmHandle h, const GemmProblem& p) {
   a.N = N;
   a.ldc = N;
   a.kBlocks = (K + TF_BLOCK_K - 1) / TF_BLOCK_K;
+  a.stamps = g_stampBuffer;  // null unless gemmDebugStamps() armed it
   a.rowsPerBatchA = (batched && p.strideA) ? 1 : 0;  // batched-operand flags for the producer
   a.rowsPerBatchB = (batched && p.strideB) ? 1 : 0;
   a.strideC = (size_t)M * N;
@@ -1210,6 +1308,8 @@ bool runTf32(GemmHandle h, const GemmProblem& p) {
   }
 
   ProfileScope prof(2.0 * M * N * K * p.batches);
+  a.spanMin = prof.spanMin;
+  a.spanMax = prof.spanMax;
   if(aMN && bMN)
     launchTf32Tile<true, true>(BN, tmA, tmB, a, p.batches);
   else if(aMN)

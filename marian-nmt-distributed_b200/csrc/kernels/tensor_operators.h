@@ -48,6 +48,8 @@ void gemmInvalidateCache(GemmHandle);
 // step: their bf16 copies survive until the next gemmInvalidateCache().
 void gemmSetStableRange(GemmHandle, const void* ptr, size_t bytes);
 
+// Tuning aid (scripts/gemm_stamps.py): per-CTA %globaltimer stamps of the tf32 kernel.
+void gemmDebugStamps(unsigned long long* deviceBuffer);
 // Per-launch CUDA-event timing of the tensor-core GEMM (eager steps only).
 void gemmProfile(int enable, double* ms, double* flops, size_t* launches);
 

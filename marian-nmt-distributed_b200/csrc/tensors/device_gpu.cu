@@ -9,6 +9,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "common/definitions.h"
@@ -184,6 +185,16 @@ void* endCapture() {
         cudaGraphNodeType type;
         if(cudaGraphNodeGetType(node, &type) == cudaSuccess && type == cudaGraphNodeTypeKernel)
           tctx.lastKernelCount++;
+        if(std::getenv("MRN_GRAPH_STATS") && cudaGraphNodeGetType(node, &type) == cudaSuccess) {
+          static int counts[16];
+          if(node == nodes.front())
+            for(int& c : counts) c = 0;
+          counts[(int)type < 16 ? (int)type : 15]++;
+          if(node == nodes.back())
+            fprintf(stderr, "[marian_b200] captured graph: %d kernel, %d memcpy, %d memset, %d event-record, %d event-wait, %d other nodes\n", counts[cudaGraphNodeTypeKernel],
+                    counts[cudaGraphNodeTypeMemcpy], counts[cudaGraphNodeTypeMemset], counts[cudaGraphNodeTypeEventRecord], counts[cudaGraphNodeTypeWaitEvent],
+                    (int)n - counts[cudaGraphNodeTypeKernel] - counts[cudaGraphNodeTypeMemcpy] - counts[cudaGraphNodeTypeMemset] - counts[cudaGraphNodeTypeEventRecord] - counts[cudaGraphNodeTypeWaitEvent]);
+        }
       }
     }
   }

@@ -33,13 +33,22 @@ if os.path.exists(os.path.join(OUT, "launches.csv")):
           "Per-launch times under ncu are serialised and cold-cache: read the SHARES.  The replayed step itself is timed by bench.py.\n\n" + body)
 
 # 2. in-graph GEMM table
+p = os.path.join(OUT, "gemm_dump_side.csv.spans")
+if os.path.exists(p):
+    body = run([sys.executable, os.path.join(ROOT, "scripts", "summarize_gemm_dump.py"), p])
+    write("gemm_kernel_spans_%s.md" % tag, "# Tensor-core GEMM launches of ONE replayed step: kernel execution spans\n\n"
+          "`MRN_GEMM_PROFILE_DUMP=gpurun_out/gemm_dump_side.csv python bench.py` (second profiling pass, MRN_GEMM_SPANS): every CTA of a launch folds\n"
+          "its %globaltimer start / end into a per-launch min / max slot (csrc/kernels/gemm.cu), so the duration is first-CTA-start ..\n"
+          "last-CTA-end INSIDE the replayed graph, with the side stream running concurrently and no extra graph nodes.  This is the\n"
+          "duration bench.py's `roofline` uses.  Weight-gradient products (op(A)=T) run on the side stream.\n\n" + body)
 for f in ("gemm_dump_side.csv",):
     p = os.path.join(OUT, f)
     if os.path.exists(p):
         body = run([sys.executable, os.path.join(ROOT, "scripts", "summarize_gemm_dump.py"), p])
         write("gemm_in_graph_%s.md" % tag, "# Tensor-core GEMM launches of ONE replayed step, timed inside the CUDA graph\n\n"
               "`MRN_GEMM_PROFILE_DUMP=gpurun_out/gemm_dump_side.csv python bench.py` - CUDA events recorded as external event nodes around\n"
-              "every launch of the captured step (csrc/kernels/gemm.cu ProfileScope); this is what bench.py's `roofline` sums.\n"
+              "every launch of the captured step (csrc/kernels/gemm.cu ProfileScope).  Each pair includes ~6.7 us of event-record node\n"
+              "latency (profiles/graph_gap_probe_r01.json): compare with gemm_kernel_spans_rNN.md.\n"
               "Weight-gradient products (op(A)=T) run on the side stream, concurrently with the main chain.\n\n" + body)
 
 # 3. DRAM traffic of the GEMM family
