@@ -319,6 +319,7 @@ __global__ void gCrossEntropyPickBackward(float* __restrict__ out, const float* 
     }
     int p = (int)pick[j];
     float a = adj[j];
+    const float invS = 1.0f / s;  // one division per row instead of one per element
     if(VEC) {
       const float4* p4 = reinterpret_cast<const float4*>(sp);
       float4* o4 = reinterpret_cast<float4*>(so);
@@ -327,16 +328,16 @@ __global__ void gCrossEntropyPickBackward(float* __restrict__ out, const float* 
         float4 x = p4[i];
         float4 g = assign ? make_float4(0.f, 0.f, 0.f, 0.f) : o4[i];
         int id = i << 2;
-        g.x += a * (expf(x.x - M) / s - (float)(id == p));
-        g.y += a * (expf(x.y - M) / s - (float)(id + 1 == p));
-        g.z += a * (expf(x.z - M) / s - (float)(id + 2 == p));
-        g.w += a * (expf(x.w - M) / s - (float)(id + 3 == p));
+        g.x += a * (expf(x.x - M) * invS - (float)(id == p));
+        g.y += a * (expf(x.y - M) * invS - (float)(id + 1 == p));
+        g.z += a * (expf(x.z - M) * invS - (float)(id + 2 == p));
+        g.w += a * (expf(x.w - M) * invS - (float)(id + 3 == p));
         o4[i] = g;
       }
     } else {
       for(int id = R::firstCol(); id < cols; id += R::colStride()) {
         float sub = (float)(id == p);
-        float gval = a * (expf(sp[id] - M) / s - sub);
+        float gval = a * (expf(sp[id] - M) * invS - sub);
         so[id] = assign ? gval : so[id] + gval;
       }
     }
