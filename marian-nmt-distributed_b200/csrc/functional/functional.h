@@ -59,10 +59,18 @@ namespace op {
 // Two-branch sigmoid, as the reference's `logit` functor and stableLogit()
 // (src/functional/predicates.h:92, src/kernels/tensor_operators.cu:15-23).
 MRN_HD float sigmoid(float x) {
+#if defined(__CUDA_ARCH__)
+  // one exponential of a non-positive argument, branch free; ex2.approx / rcp.approx as the
+  // reference's release build (--use_fast_math, CMakeLists.txt:37) compiles its functor
+  float z = __expf(-fabsf(x));
+  float r = __fdividef(1.f, 1.f + z);
+  return x > 0.f ? r : z * r;
+#else
   if(x > 0.f)
     return 1.f / (1.f + expf(-x));
   float z = expf(x);
   return z / (1.f + z);
+#endif
 }
 struct Plus { MRN_HD static float apply(float a, float b) { return a + b; } };
 struct Minus { MRN_HD static float apply(float a, float b) { return a - b; } };

@@ -546,6 +546,193 @@ __global__ void __launch_bounds__(kAttnThreads) gAttentionForwardMma(float* __re
   storeHead(out + ((size_t)b * g.Tq) * d + h * g.dk, sO, L.ldK, g.Tq, g.dk, d, false);
 }
 
+// ------------------------------------------------------------------------------------------
+// forward, warp-private formulation: ONE block barrier
+// ------------------------------------------------------------------------------------------
+// A CTA of 4 warps owns 64 query rows of one (sentence, head); warp w owns rows 16w..16w+15:
+//   S strip (16 x Tk) = Q_w K^T stays in the warp's accumulator registers, the row softmax runs on
+//   those registers (a row lives in the 4 lanes of a quad: two shuffles per reduction), P goes to
+//   global memory (for the backward pass) and into the warp's OWN 16 rows of the Q tile (Q is dead
+//   after the strip: its A fragments were consumed), O strip = P_w V, written out by the warp.
+// K and V are the only data shared by the warps -> one __syncthreads after the cp.async loads,
+// afterwards only __syncwarp.  Three shared-memory tiles (Q/P, K, V) -> 4 CTAs per SM.
+// NTS = number of 8-wide score tiles the registers are sized for (Tk <= 8 NTS), dk <= 64.
+template <bool X3>
+__device__ __forceinline__ void mmaSplit(float (&d)[4], const float (&af)[4], const uint32_t (&ahi)[4], float b0, float b1) {
+  uint32_t bhi[2] = {toTf32(b0), toTf32(b1)};
+  if(X3) {
+    uint32_t alo[4], blo[2] = {toTf32(b0 - __uint_as_float(bhi[0])), toTf32(b1 - __uint_as_float(bhi[1]))};
+#pragma unroll
+    for(int i = 0; i < 4; ++i)
+      alo[i] = toTf32(af[i] - __uint_as_float(ahi[i]));
+    mmaTf32(d, alo, bhi);
+    mmaTf32(d, ahi, blo);
+  }
+  mmaTf32(d, ahi, bhi);
+}
+
+template <bool X3, int NTS>
+__global__ void __launch_bounds__(128) gAttentionForwardWarp(float* __restrict__ out,
+                                                             float* __restrict__ probs,
+                                                             const float* __restrict__ q,
+                                                             const float* __restrict__ k,
+                                                             const float* __restrict__ v,
+                                                             const float* __restrict__ mask,
+                                                             AttnGeom g) {
+  extern __shared__ __align__(16) float smemF[];
+  pdlEnter();
+  const int TkP = pad16(g.Tk);
+  const int ldQ = pitchMod32(g.dk > TkP ? g.dk : TkP, 4);  // Q rows are later overwritten by P rows (TkP wide)
+  const int ldK = pitchMod32(g.dk, 4), ldV = pitchMod32(g.dk, 8);
+  float* sQ = smemF;            // [64][ldQ]
+  float* sK = sQ + 64 * ldQ;    // [TkP][ldK]
+  float* sV = sK + TkP * ldK;   // [TkP][ldV]
+
+  const int bh = blockIdx.x, b = bh / g.H, h = bh - b * g.H;
+  const int row0 = blockIdx.y * 64;  // first query row of this CTA
+  const int d = g.H * g.dk;
+  const int rowsHere = min(64, g.Tq - row0);
+  loadHeadPadded(sQ, ldQ, q + ((size_t)b * g.Tq + row0) * d + h * g.dk, rowsHere, 64, g.dk, d);
+  loadHeadPadded(sK, ldK, k + ((size_t)b * g.Tk) * d + h * g.dk, g.Tk, TkP, g.dk, d);
+  loadHeadPadded(sV, ldV, v + ((size_t)b * g.Tk) * d + h * g.dk, g.Tk, TkP, g.dk, d);
+  cpAsyncWaitAll();
+  __syncthreads();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, t = lane & 3;
+  const int m0 = warp * 16;
+  if(m0 >= rowsHere)
+    return;  // whole strip is padding (no further block barriers below)
+  const int nts = TkP >> 3;
+
+  // ---- S strip = Q_w K^T ----
+  float acc[NTS][4];
+#pragma unroll
+  for(int i = 0; i < NTS; ++i)
+    acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  {
+    const float* ap = sQ + (m0 + gq) * ldQ + t;
+    for(int k0 = 0; k0 < g.dk; k0 += 8) {
+      float af[4] = {ap[k0], ap[k0 + 8 * ldQ], ap[k0 + 4], ap[k0 + 8 * ldQ + 4]};
+      uint32_t ahi[4] = {toTf32(af[0]), toTf32(af[1]), toTf32(af[2]), toTf32(af[3])};
+#pragma unroll
+      for(int i = 0; i < NTS; ++i)
+        if(i < nts) {
+          const float* bp = sK + (i * 8 + gq) * ldK + k0 + t;
+          mmaSplit<X3>(acc[i], af, ahi, bp[0], bp[4]);
+        }
+    }
+  }
+  __syncwarp();  // every lane of the warp is done reading its Q rows: they become the P strip
+
+  // ---- scale, mask, row softmax on the accumulators (rows gq and gq + 8 of the strip) ----
+  const int iLo = row0 + m0 + gq, iHi = iLo + 8;
+  const float* mLo = nullptr;
+  const float* mHi = nullptr;
+  if(mask) {
+    const float* mb = mask + (size_t)b * g.maskRows * g.Tk;
+    mLo = mb + (g.maskRows > 1 ? (size_t)min(iLo, g.Tq - 1) * g.Tk : 0);
+    mHi = mb + (g.maskRows > 1 ? (size_t)min(iHi, g.Tq - 1) * g.Tk : 0);
+  }
+  float mxLo = -3.0e38f, mxHi = -3.0e38f;
+#pragma unroll
+  for(int i = 0; i < NTS; ++i)
+    if(i < nts) {
+#pragma unroll
+      for(int e = 0; e < 2; ++e) {
+        int j = i * 8 + 2 * t + e;
+        bool real = j < g.Tk;
+        float lo = real ? acc[i][e] * g.scale + (mLo ? mLo[j] : 0.f) : -3.0e38f;
+        float hi = real ? acc[i][2 + e] * g.scale + (mHi ? mHi[j] : 0.f) : -3.0e38f;
+        acc[i][e] = lo;
+        acc[i][2 + e] = hi;
+        mxLo = fmaxf(mxLo, lo);
+        mxHi = fmaxf(mxHi, hi);
+      }
+    }
+  mxLo = fmaxf(mxLo, __shfl_xor_sync(0xffffffffu, mxLo, 1));
+  mxLo = fmaxf(mxLo, __shfl_xor_sync(0xffffffffu, mxLo, 2));
+  mxHi = fmaxf(mxHi, __shfl_xor_sync(0xffffffffu, mxHi, 1));
+  mxHi = fmaxf(mxHi, __shfl_xor_sync(0xffffffffu, mxHi, 2));
+  float sumLo = 0.f, sumHi = 0.f;
+#pragma unroll
+  for(int i = 0; i < NTS; ++i)
+    if(i < nts) {
+#pragma unroll
+      for(int e = 0; e < 2; ++e) {
+        int j = i * 8 + 2 * t + e;
+        float lo = j < g.Tk ? __expf(acc[i][e] - mxLo) : 0.f;
+        float hi = j < g.Tk ? __expf(acc[i][2 + e] - mxHi) : 0.f;
+        acc[i][e] = lo;
+        acc[i][2 + e] = hi;
+        sumLo += lo;
+        sumHi += hi;
+      }
+    }
+  sumLo += __shfl_xor_sync(0xffffffffu, sumLo, 1);
+  sumLo += __shfl_xor_sync(0xffffffffu, sumLo, 2);
+  sumHi += __shfl_xor_sync(0xffffffffu, sumHi, 1);
+  sumHi += __shfl_xor_sync(0xffffffffu, sumHi, 2);
+  const float invLo = 1.f / sumLo, invHi = 1.f / sumHi;
+
+  // ---- P strip -> global (backward pass) and -> the warp's rows of the Q tile (A operand of P V) ----
+  float* sP = sQ + m0 * ldQ;
+  float* pLo = (probs && iLo < g.Tq) ? probs + (((size_t)b * g.H + h) * g.Tq + iLo) * g.Tk : nullptr;
+  float* pHi = (probs && iHi < g.Tq) ? probs + (((size_t)b * g.H + h) * g.Tq + iHi) * g.Tk : nullptr;
+#pragma unroll
+  for(int i = 0; i < NTS; ++i)
+    if(i < nts) {
+      int j = i * 8 + 2 * t;
+      float l0 = acc[i][0] * invLo, l1 = acc[i][1] * invLo, h0 = acc[i][2] * invHi, h1 = acc[i][3] * invHi;
+      *reinterpret_cast<float2*>(sP + gq * ldQ + j) = make_float2(l0, l1);
+      *reinterpret_cast<float2*>(sP + (gq + 8) * ldQ + j) = make_float2(h0, h1);
+      if(pLo) {
+        if(j < g.Tk)
+          pLo[j] = l0;
+        if(j + 1 < g.Tk)
+          pLo[j + 1] = l1;
+      }
+      if(pHi) {
+        if(j < g.Tk)
+          pHi[j] = h0;
+        if(j + 1 < g.Tk)
+          pHi[j + 1] = h1;
+      }
+    }
+  __syncwarp();
+
+  // ---- O strip = P_w V ----
+  const int nto = g.dk >> 3;
+  float o[8][4];
+#pragma unroll
+  for(int i = 0; i < 8; ++i)
+    o[i][0] = o[i][1] = o[i][2] = o[i][3] = 0.f;
+  {
+    const float* ap = sP + gq * ldQ + t;
+    for(int k0 = 0; k0 < TkP; k0 += 8) {
+      float af[4] = {ap[k0], ap[k0 + 8 * ldQ], ap[k0 + 4], ap[k0 + 8 * ldQ + 4]};
+      uint32_t ahi[4] = {toTf32(af[0]), toTf32(af[1]), toTf32(af[2]), toTf32(af[3])};
+#pragma unroll
+      for(int i = 0; i < 8; ++i)
+        if(i < nto) {
+          const float* bp = sV + (k0 + t) * ldV + i * 8 + gq;
+          mmaSplit<X3>(o[i], af, ahi, bp[0], bp[4 * ldV]);
+        }
+    }
+  }
+  float* oLo = iLo < g.Tq ? out + ((size_t)b * g.Tq + iLo) * d + h * g.dk : nullptr;
+  float* oHi = iHi < g.Tq ? out + ((size_t)b * g.Tq + iHi) * d + h * g.dk : nullptr;
+#pragma unroll
+  for(int i = 0; i < 8; ++i)
+    if(i < nto) {
+      int c = i * 8 + 2 * t;
+      if(oLo)
+        *reinterpret_cast<float2*>(oLo + c) = make_float2(o[i][0], o[i][1]);
+      if(oHi)
+        *reinterpret_cast<float2*>(oHi + c) = make_float2(o[i][2], o[i][3]);
+    }
+}
+
+
 // Backward shared-memory plan: four tiles (+ D), three CTAs per SM at the config-B shape:
 //   tile 1: dO (phases dV, dP), then Q (phase dK)          tile 2: V (phase dP), then K (phase dQ),
 //   tile P: P -> dS                                          tile PT: P^T -> dS^T
@@ -744,6 +931,38 @@ void MultiHeadAttention(Tensor out, Tensor probs, const Tensor q, const Tensor k
   device::setDevice(out->getDevice());
   out->takeLazyZero();
   AttnGeom g = geometry(q, k, mask, heads, scale);
+  {
+    // warp-private kernel: dk <= 64, Tk <= 128
+    static const bool noWarp = std::getenv("MRN_ATTENTION_NO_WARP") != nullptr;
+    const int TkP = pad16(g.Tk);
+    if(!noWarp && g.dk % 8 == 0 && g.dk <= 64 && TkP <= 128) {
+      const int ldQ = pitchMod32(g.dk > TkP ? g.dk : TkP, 4);
+      size_t smemW = ((size_t)64 * ldQ + (size_t)TkP * pitchMod32(g.dk, 4) + (size_t)TkP * pitchMod32(g.dk, 8)) * sizeof(float);
+      float* pp = probs ? probs->data() : nullptr;
+      const float* mp = mask ? mask->data() : nullptr;
+      dim3 grid(g.B * g.H, (g.Tq + 63) / 64);
+      static size_t cfg[4] = {0, 0, 0, 0};
+#define LAUNCH_WARP(X3, NTS, slot)                                                                                                      \
+  do {                                                                                                                                  \
+    ensureSmem(gAttentionForwardWarp<X3, NTS>, smemW, cfg[slot]);                                                                        \
+    launchPdl(gAttentionForwardWarp<X3, NTS>, grid, dim3(128), smemW, cudaStreamOfEngine(), out->data(), pp, q->data(), k->data(), v->data(), mp, g); \
+  } while(0)
+      if(TkP <= 64) {
+        if(exact)
+          LAUNCH_WARP(true, 8, 0);
+        else
+          LAUNCH_WARP(false, 8, 1);
+      } else {
+        if(exact)
+          LAUNCH_WARP(true, 16, 2);
+        else
+          LAUNCH_WARP(false, 16, 3);
+      }
+#undef LAUNCH_WARP
+      CUDA_LAUNCH_CHECK();
+      return;
+    }
+  }
   {
     MmaLayoutFwd L(g);
     size_t smemMma = L.floats() * sizeof(float);

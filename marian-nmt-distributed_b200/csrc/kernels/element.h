@@ -50,18 +50,20 @@ struct RowGeom {
 
 // MODE 0: Element (operand 0 is `out`, out = f(...));  MODE 1: Add, out += scale f(ins);
 // MODE 2: Add into a lazily-zero output, out = scale f(ins) (first writer assigns)
-template <int K, int MODE, bool VEC, class Functor>
+// FLAT: every operand has exactly the iteration shape (one long row, g.rows == 1): no index
+// decode at all, the kernel is a pure 128-bit stream.
+template <int K, int MODE, bool VEC, class Functor, bool FLAT = false>
 __global__ void __launch_bounds__(256) gElementwise(Functor f, float* __restrict__ out, Operands<K> ops, RowGeom g, float scale) {
   pdlEnter();
-  const int cpr = (g.cols + 3) >> 2;  // 4-element chunks per row
-  const long long items = (long long)g.rows * cpr;
-  for(long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < items; w += (long long)gridDim.x * blockDim.x) {
-    int row = (int)(w / cpr);
-    int c = (int)(w - (long long)row * cpr) << 2;
-    int o2 = row % g.d2;
-    int t = row / g.d2;
-    int o1 = t % g.d1;
-    int o0 = t / g.d1;
+  const unsigned cpr = (unsigned)(g.cols + 3) >> 2;  // 4-element chunks per row
+  const unsigned items = (unsigned)g.rows * cpr;     // < 2^31 (checked by the launchers)
+  for(unsigned w = blockIdx.x * blockDim.x + threadIdx.x; w < items; w += gridDim.x * blockDim.x) {
+    int row = FLAT ? 0 : (int)(w / cpr);
+    int c = FLAT ? (int)(w << 2) : (int)(w - (unsigned)row * cpr) << 2;
+    int o2 = FLAT ? 0 : row % g.d2;
+    int t = FLAT ? 0 : row / g.d2;
+    int o1 = FLAT ? 0 : t % g.d1;
+    int o0 = FLAT ? 0 : t / g.d1;
 
     float v[K][4];
 #pragma unroll
@@ -71,8 +73,8 @@ __global__ void __launch_bounds__(256) gElementwise(Functor f, float* __restrict
         v[k][0] = v[k][1] = v[k][2] = v[k][3] = 0.f;
         continue;
       }
-      const float* base = ops.p[k] + (size_t)o0 * ops.rb[k][0] + (size_t)o1 * ops.rb[k][1] + (size_t)o2 * ops.rb[k][2];
-      if(ops.cs[k] == 0) {
+      const float* base = FLAT ? ops.p[k] : ops.p[k] + (size_t)o0 * ops.rb[k][0] + (size_t)o1 * ops.rb[k][1] + (size_t)o2 * ops.rb[k][2];
+      if(!FLAT && ops.cs[k] == 0) {
         float s = __ldg(base);
         v[k][0] = v[k][1] = v[k][2] = v[k][3] = s;
       } else if(VEC) {
@@ -367,9 +369,12 @@ void Element(Functor functor, Tensor out, Tensors... tensors) {
     return;
 
   long long items = (long long)g.rows * ((g.cols + 3) / 4);
+  ABORT_IF(items >= (1ll << 31), "Element: more than 2^33 elements");
   int grid = gridFor((size_t)items, 256);
   auto stream = cudaStreamOfEngine();
-  if(vec)
+  if(vec && !broadcast)
+    launchPdl(ew::gElementwise<K, 0, true, Functor, true>, dim3(grid), dim3(256), 0, stream, functor, out->data(), ops, g, 1.f);
+  else if(vec)
     launchPdl(ew::gElementwise<K, 0, true, Functor>, dim3(grid), dim3(256), 0, stream, functor, out->data(), ops, g, 1.f);
   else
     launchPdl(ew::gElementwise<K, 0, false, Functor>, dim3(grid), dim3(256), 0, stream, functor, out->data(), ops, g, 1.f);
@@ -413,8 +418,14 @@ void Add(Functor functor, float scale, Tensor out, Tensors... tensors) {
     if(!ew::aligned16(out->data()))
       vec = false;
     long long items = (long long)g.rows * ((g.cols + 3) / 4);
+    ABORT_IF(items >= (1ll << 31), "Add: more than 2^33 elements");
     int grid = gridFor((size_t)items, 256);
-    if(assign) {
+    if(vec && !broadcast) {
+      if(assign)
+        launchPdl(ew::gElementwise<K, 2, true, Functor, true>, dim3(grid), dim3(256), 0, stream, functor, out->data(), ops, g, scale);
+      else
+        launchPdl(ew::gElementwise<K, 1, true, Functor, true>, dim3(grid), dim3(256), 0, stream, functor, out->data(), ops, g, scale);
+    } else if(assign) {
       if(vec)
         launchPdl(ew::gElementwise<K, 2, true, Functor>, dim3(grid), dim3(256), 0, stream, functor, out->data(), ops, g, scale);
       else

@@ -595,25 +595,29 @@ __global__ void __launch_bounds__(256) gLayerNormalizationGradWarp(float* __rest
     float4 xh[VPL], av[VPL];
     float sum_x = 0.f, sum_adj = 0.f, sum_adj_x = 0.f, sq = 0.f;
     {
-      float4 xv[VPL];
+      // all loads of the row are issued before the first use: ONE memory round trip per row
+      float4 xv[VPL], yv[VPL], rv[VPL];
+#pragma unroll
+      for(int i = 0; i < VPL; ++i) {
+        int c = (i * 32 + lane) * 4;
+        const size_t o = off + (c < cols ? c : 0);  // clamped: the load is unconditional, the value masked below
+        xv[i] = *reinterpret_cast<const float4*>(x + o);
+        yv[i] = *reinterpret_cast<const float4*>(y + o);
+        av[i] = *reinterpret_cast<const float4*>(adj + o);
+        rv[i] = res ? *reinterpret_cast<const float4*>(res + o) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
 #pragma unroll
       for(int i = 0; i < VPL; ++i) {
         int c = (i * 32 + lane) * 4;
         if(c < cols) {
-          xv[i] = *reinterpret_cast<const float4*>(x + off + c);
-          if(res) {
-            float4 rv = *reinterpret_cast<const float4*>(res + off + c);
-            xv[i].x += rv.x;
-            xv[i].y += rv.y;
-            xv[i].z += rv.z;
-            xv[i].w += rv.w;
-          }
-          float4 yv = *reinterpret_cast<const float4*>(y + off + c);
-          av[i] = *reinterpret_cast<const float4*>(adj + off + c);
-          xh[i].x = (yv.x - b4[i].x) / g4[i].x;
-          xh[i].y = (yv.y - b4[i].y) / g4[i].y;
-          xh[i].z = (yv.z - b4[i].z) / g4[i].z;
-          xh[i].w = (yv.w - b4[i].w) / g4[i].w;
+          xv[i].x += rv[i].x;
+          xv[i].y += rv[i].y;
+          xv[i].z += rv[i].z;
+          xv[i].w += rv[i].w;
+          xh[i].x = (yv[i].x - b4[i].x) / g4[i].x;
+          xh[i].y = (yv[i].y - b4[i].y) / g4[i].y;
+          xh[i].z = (yv[i].z - b4[i].z) / g4[i].z;
+          xh[i].w = (yv[i].w - b4[i].w) / g4[i].w;
         } else {
           xv[i] = xh[i] = av[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
