@@ -409,6 +409,13 @@ __device__ __forceinline__ void cpAsync16(float* smem, const float* gmem) {
 __device__ __forceinline__ void cpAsync4(float* smem, const float* gmem) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(smem)), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void cpAsyncCommit() {
+  asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void cpAsyncWaitGroup() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ void cpAsyncWaitAll() {
   asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
 }
@@ -874,6 +881,261 @@ __global__ void __launch_bounds__(kAttnThreads) gAttentionBackwardMma(float* __r
   });
 }
 
+// Stores a 16 x dk accumulator strip (rows lo / hi of a lane) to [.., d]-pitched global memory.
+// Accumulating: all old values are loaded before the first store (one memory round trip, not 2 nto).
+__device__ __forceinline__ void storeStrip(float* lo, float* hi, float (&o)[8][4], int nto, int t, bool accumulate) {
+  if(accumulate) {
+#pragma unroll
+    for(int n = 0; n < 8; ++n)
+      if(n < nto) {
+        if(lo) {
+          float2 x = *reinterpret_cast<const float2*>(lo + n * 8 + 2 * t);
+          o[n][0] += x.x;
+          o[n][1] += x.y;
+        }
+        if(hi) {
+          float2 x = *reinterpret_cast<const float2*>(hi + n * 8 + 2 * t);
+          o[n][2] += x.x;
+          o[n][3] += x.y;
+        }
+      }
+  }
+#pragma unroll
+  for(int n = 0; n < 8; ++n)
+    if(n < nto) {
+      if(lo)
+        *reinterpret_cast<float2*>(lo + n * 8 + 2 * t) = make_float2(o[n][0], o[n][1]);
+      if(hi)
+        *reinterpret_cast<float2*>(hi + n * 8 + 2 * t) = make_float2(o[n][2], o[n][3]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// backward, warp-private formulation (Tq, Tk <= 64, dk == 64): four tiles, three block barriers
+// ------------------------------------------------------------------------------------------
+// Phase 1, warp w owns QUERY rows 16w..16w+15, everything in registers:
+//   dP strip = dO_w V^T;  P strip straight from global memory in the accumulator layout;
+//   D_i = sum_j P_ij dP_ij (quad shuffles);  dS = scale P o (dP - D);
+//   dQ strip = dS_w K with the A operand taken FROM THE ACCUMULATOR REGISTERS: the contraction
+//   index may be permuted freely, so k-slot t of step i stands for key 8i+2t and slot t+4 for key
+//   8i+2t+1 - exactly the two columns a lane holds - and the B fragment reads K rows 8i+2t, 8i+2t+1.
+// Phase 2, warp w owns KEY rows 16w..16w+15: dV = P^T dO and dK = dS^T Q read P / dS (stored by the
+//   phase-1 owners over the dead V / K tiles) as transposed A operands with the same slot permutation.
+// Tiles are [R][64] floats WITHOUT padding, column index XOR-swizzled with 4 (row mod 8): every
+// fragment load above is bank-conflict free, 16-byte chunks stay contiguous (cp.async), and at
+// R = 56 rows (T <= 56) the four tiles take exactly 56 KB -> FOUR CTAs per SM, so the 512 heads of
+// a config-B block run as one wave (with padded 68-float pitches: three CTAs, 444 slots, a tail wave).
+// The forward output O is not needed (D_i comes from P and dP).
+__device__ __forceinline__ int swz(int row) {
+  return (row & 7) << 2;
+}
+
+// [T, 64] head slice -> swizzled [R][64] tile (asynchronous), rows >= T zero filled
+__device__ __forceinline__ void loadHeadSwizzled(float* dst, const float* src, int T, int R, int d) {
+  for(int e = threadIdx.x; e < R * 16; e += blockDim.x) {
+    int r = e >> 4, c = (e & 15) << 2;
+    float* dp = dst + r * 64 + (c ^ swz(r));
+    if(r < T)
+      cpAsync16(dp, src + (size_t)r * d + c);
+    else
+      *reinterpret_cast<float4*>(dp) = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+template <bool X3>
+__global__ void __launch_bounds__(128) gAttentionBackwardWarp(float* __restrict__ dq,
+                                                              float* __restrict__ dk_,
+                                                              float* __restrict__ dv,
+                                                              const float* __restrict__ dout,
+                                                              const float* __restrict__ probs,
+                                                              const float* __restrict__ q,
+                                                              const float* __restrict__ k,
+                                                              const float* __restrict__ v,
+                                                              AttnGeom g,
+                                                              int R,
+                                                              int accQ,
+                                                              int accK,
+                                                              int accV) {
+  extern __shared__ __align__(16) float smemF[];
+  pdlEnter();
+  const int TILE = R * 64;
+  float* sdO = smemF;  // A rows beyond R (the padding part of the last strip) read into sV: finite, never stored
+  float* sV = sdO + TILE;
+  float* sK = sV + TILE;
+  float* sQ = sK + TILE;
+  float* sP = sV;   // P over V (after barrier A)
+  float* sdS = sK;  // dS over K (after barrier A2)
+
+  const int b = blockIdx.x / g.H, h = blockIdx.x - b * g.H;
+  const int d = g.H * 64;
+  const size_t offQ = ((size_t)b * g.Tq) * d + h * 64;
+  const size_t offK = ((size_t)b * g.Tk) * d + h * 64;
+  loadHeadSwizzled(sdO, dout + offQ, g.Tq, R, d);
+  loadHeadSwizzled(sV, v + offK, g.Tk, R, d);
+  cpAsyncCommit();
+  loadHeadSwizzled(sK, k + offK, g.Tk, R, d);
+  loadHeadSwizzled(sQ, q + offQ, g.Tq, R, d);
+  cpAsyncCommit();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, t = lane & 3;
+  const int m0 = warp * 16;
+  const int nts = (g.Tk + 7) >> 3;  // 8-wide key tiles that hold real keys
+  const int nqs = (g.Tq + 7) >> 3;  // 8-deep query steps that hold real queries
+  const int iLo = m0 + gq, iHi = iLo + 8;
+
+  // ---- P strip from global memory, in the accumulator layout (zero outside Tq x Tk) ----
+  float p[8][4];
+  {
+    const float* pb = probs + (((size_t)b * g.H + h) * g.Tq) * g.Tk;
+    const bool pair = (g.Tk & 1) == 0;
+#pragma unroll
+    for(int i = 0; i < 8; ++i) {
+      const int j = i * 8 + 2 * t;
+      p[i][0] = p[i][1] = p[i][2] = p[i][3] = 0.f;
+      if(pair) {
+        if(j < g.Tk) {
+          if(iLo < g.Tq) {
+            float2 x = *reinterpret_cast<const float2*>(pb + (size_t)iLo * g.Tk + j);
+            p[i][0] = x.x;
+            p[i][1] = x.y;
+          }
+          if(iHi < g.Tq) {
+            float2 x = *reinterpret_cast<const float2*>(pb + (size_t)iHi * g.Tk + j);
+            p[i][2] = x.x;
+            p[i][3] = x.y;
+          }
+        }
+      } else {
+#pragma unroll
+        for(int e = 0; e < 2; ++e)
+          if(j + e < g.Tk) {
+            if(iLo < g.Tq)
+              p[i][e] = pb[(size_t)iLo * g.Tk + j + e];
+            if(iHi < g.Tq)
+              p[i][2 + e] = pb[(size_t)iHi * g.Tk + j + e];
+          }
+      }
+    }
+  }
+  cpAsyncWaitGroup<1>();
+  __syncthreads();  // dO and V have landed
+
+  // rows m0+gq, m0+gq+8 and 8i+gq all have (row mod 8) == gq: one swizzle term for A and NT-B reads
+  const int cA = t ^ (gq << 2);
+  // ---- dP strip = dO_w V^T ----
+  float acc[8][4];
+#pragma unroll
+  for(int i = 0; i < 8; ++i)
+    acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  {
+    const float* ap = sdO + iLo * 64;
+    const float* bp0 = sV + gq * 64;
+#pragma unroll 2
+    for(int k0 = 0; k0 < 64; k0 += 8) {
+      const int c0 = k0 ^ cA, c1 = c0 ^ 4;
+      float af[4] = {ap[c0], ap[c0 + 8 * 64], ap[c1], ap[c1 + 8 * 64]};
+      uint32_t ahi[4] = {toTf32(af[0]), toTf32(af[1]), toTf32(af[2]), toTf32(af[3])};
+#pragma unroll
+      for(int i = 0; i < 8; ++i)
+        if(i < nts)
+          mmaSplit<X3>(acc[i], af, ahi, bp0[i * 512 + c0], bp0[i * 512 + c1]);
+    }
+  }
+  // ---- D_i and dS (over the dP registers) ----
+  {
+    float dLo = 0.f, dHi = 0.f;
+#pragma unroll
+    for(int i = 0; i < 8; ++i) {
+      dLo = fmaf(p[i][0], acc[i][0], fmaf(p[i][1], acc[i][1], dLo));
+      dHi = fmaf(p[i][2], acc[i][2], fmaf(p[i][3], acc[i][3], dHi));
+    }
+    dLo += __shfl_xor_sync(0xffffffffu, dLo, 1);
+    dLo += __shfl_xor_sync(0xffffffffu, dLo, 2);
+    dHi += __shfl_xor_sync(0xffffffffu, dHi, 1);
+    dHi += __shfl_xor_sync(0xffffffffu, dHi, 2);
+#pragma unroll
+    for(int i = 0; i < 8; ++i) {
+      acc[i][0] = p[i][0] * (acc[i][0] - dLo) * g.scale;
+      acc[i][1] = p[i][1] * (acc[i][1] - dLo) * g.scale;
+      acc[i][2] = p[i][2] * (acc[i][2] - dHi) * g.scale;
+      acc[i][3] = p[i][3] * (acc[i][3] - dHi) * g.scale;
+    }
+  }
+  cpAsyncWaitGroup<0>();
+  __syncthreads();  // barrier A: V is dead, K and Q have landed
+
+  // P strip -> V tile (read transposed in phase 2); rows >= R are zero and never read
+  {
+    float* lo = sP + iLo * 64;
+    const int cw = (2 * t) ^ (gq << 2);
+#pragma unroll
+    for(int i = 0; i < 8; ++i) {
+      if(iLo < R)
+        *reinterpret_cast<float2*>(lo + ((i * 8) ^ cw)) = make_float2(p[i][0], p[i][1]);
+      if(iHi < R)
+        *reinterpret_cast<float2*>(lo + 8 * 64 + ((i * 8) ^ cw)) = make_float2(p[i][2], p[i][3]);
+    }
+  }
+
+  // permuted [k][n] reads: rows 8s+2t (swizzle 8t) and 8s+2t+1 (swizzle 8t+4), column 8n+gq
+  const int cE = gq ^ (t << 3), cO = cE ^ 4;
+  float o[8][4];
+  // ---- dQ strip = dS_w K, A operand from the dS registers ----
+#pragma unroll
+  for(int n = 0; n < 8; ++n)
+    o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+#pragma unroll
+  for(int i = 0; i < 8; ++i)
+    if(i < nts) {
+      float af[4] = {acc[i][0], acc[i][2], acc[i][1], acc[i][3]};
+      uint32_t ahi[4] = {toTf32(af[0]), toTf32(af[1]), toTf32(af[2]), toTf32(af[3])};
+      const float* kp = sK + (i * 8 + 2 * t) * 64;
+#pragma unroll
+      for(int n = 0; n < 8; ++n)
+        mmaSplit<X3>(o[n], af, ahi, kp[(n * 8) ^ cE], kp[64 + ((n * 8) ^ cO)]);
+    }
+  storeStrip(iLo < g.Tq ? dq + offQ + (size_t)iLo * d : nullptr, iHi < g.Tq ? dq + offQ + (size_t)iHi * d : nullptr, o, 8, t, accQ != 0);
+  __syncthreads();  // barrier A2: K is dead, the P tile is complete
+
+  // dS strip -> K tile
+  {
+    float* lo = sdS + iLo * 64;
+    const int cw = (2 * t) ^ (gq << 2);
+#pragma unroll
+    for(int i = 0; i < 8; ++i) {
+      if(iLo < R)
+        *reinterpret_cast<float2*>(lo + ((i * 8) ^ cw)) = make_float2(acc[i][0], acc[i][1]);
+      if(iHi < R)
+        *reinterpret_cast<float2*>(lo + 8 * 64 + ((i * 8) ^ cw)) = make_float2(acc[i][2], acc[i][3]);
+    }
+  }
+
+  // ---- phase 2: the warp owns keys m0..m0+15 (= rows iLo / iHi).  dV = P^T dO, then dK = dS^T Q ----
+#pragma unroll 1
+  for(int pass = 0; pass < 2; ++pass) {
+    const float* sA = pass == 0 ? sP : sdS;
+    const float* sB = pass == 0 ? sdO : sQ;
+    if(pass == 1)
+      __syncthreads();  // barrier B: the dS tile is complete
+#pragma unroll
+    for(int n = 0; n < 8; ++n)
+      o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+    const int aE = iLo ^ (t << 3), aO = aE ^ 4;  // columns m0+gq (and +8) of rows 8s+2t / 8s+2t+1
+#pragma unroll 2
+    for(int s8 = 0; s8 < nqs * 8; s8 += 8) {
+      const float* pa = sA + (s8 + 2 * t) * 64;
+      float af[4] = {pa[aE], pa[aE ^ 8], pa[64 + aO], pa[64 + (aO ^ 8)]};
+      uint32_t ahi[4] = {toTf32(af[0]), toTf32(af[1]), toTf32(af[2]), toTf32(af[3])};
+      const float* bp = sB + (s8 + 2 * t) * 64;
+#pragma unroll
+      for(int n = 0; n < 8; ++n)
+        mmaSplit<X3>(o[n], af, ahi, bp[(n * 8) ^ cE], bp[64 + ((n * 8) ^ cO)]);
+    }
+    float* dst = pass == 0 ? dv : dk_;
+    storeStrip(iLo < g.Tk ? dst + offK + (size_t)iLo * d : nullptr, iHi < g.Tk ? dst + offK + (size_t)iHi * d : nullptr, o, 8, t, (pass == 0 ? accV : accK) != 0);
+  }
+}
+
 size_t forwardSmem(const AttnGeom& g) {
   return ((size_t)(g.Tq + 2 * g.Tk) * (g.dk + 4) + (size_t)g.Tq * (pad4(g.Tk) + 1)) * sizeof(float);
 }
@@ -996,12 +1258,39 @@ void MultiHeadAttention(Tensor out, Tensor probs, const Tensor q, const Tensor k
 
 void MultiHeadAttentionGrad(Tensor dq, Tensor dk, Tensor dv, const Tensor adj, const Tensor out, const Tensor probs, const Tensor q, const Tensor k, const Tensor v, int heads, float scale, bool exact) {
   device::setDevice(adj->getDevice());
+  AttnGeom g = geometry(q, k, nullptr, heads, scale);
+  static const bool noWarp = std::getenv("MRN_ATTENTION_NO_WARP") != nullptr;
+  if(!noWarp && g.dk == 64 && g.Tq <= 64 && g.Tk <= 64) {
+    // first writer assigns; tensors that alias (q, k, v from the same node) are written in the order
+    // dQ, dV, dK by the SAME thread of the kernel (same row -> same warp and lane), so the later
+    // ones accumulate in program order
+    bool accQ = !dq->takeLazyZero();
+    bool accV = !dv->takeLazyZero();
+    bool accK = !dk->takeLazyZero();
+    const int R = 8 * ((std::max(g.Tq, g.Tk) + 7) / 8);  // tile rows: 56 -> 4 x 14 KB = 56 KB, four CTAs per SM
+    const size_t smemW = (size_t)4 * R * 64 * sizeof(float);
+    static bool configured = false;
+    if(!configured) {
+      CUDA_CHECK(cudaFuncSetAttribute(gAttentionBackwardWarp<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 64 * 64 * (int)sizeof(float)));
+      CUDA_CHECK(cudaFuncSetAttribute(gAttentionBackwardWarp<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 4 * 64 * 64 * (int)sizeof(float)));
+      CUDA_CHECK(cudaFuncSetAttribute(gAttentionBackwardWarp<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      CUDA_CHECK(cudaFuncSetAttribute(gAttentionBackwardWarp<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+      configured = true;
+    }
+    if(exact)
+      launchPdl(gAttentionBackwardWarp<true>, dim3(g.B * g.H), dim3(128), smemW, cudaStreamOfEngine(), dq->data(), dk->data(), dv->data(), (const float*)adj->data(), (const float*)probs->data(),
+                (const float*)q->data(), (const float*)k->data(), (const float*)v->data(), g, R, (int)accQ, (int)accK, (int)accV);
+    else
+      launchPdl(gAttentionBackwardWarp<false>, dim3(g.B * g.H), dim3(128), smemW, cudaStreamOfEngine(), dq->data(), dk->data(), dv->data(), (const float*)adj->data(), (const float*)probs->data(),
+                (const float*)q->data(), (const float*)k->data(), (const float*)v->data(), g, R, (int)accQ, (int)accK, (int)accV);
+    CUDA_LAUNCH_CHECK();
+    return;
+  }
   // first writer assigns; tensors that alias (k and v from the same node) are written in the
   // order dV, dQ, dK inside the kernel, separated by block barriers, so the later one accumulates
   bool accV = !dv->takeLazyZero();
   bool accQ = !dq->takeLazyZero();
   bool accK = !dk->takeLazyZero();
-  AttnGeom g = geometry(q, k, nullptr, heads, scale);
   {
     MmaLayoutBwd L(g);
     size_t smemMma = L.floats() * sizeof(float);
