@@ -1136,6 +1136,181 @@ __global__ void __launch_bounds__(128) gAttentionBackwardWarp(float* __restrict_
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// forward, warp-private, dk == 64 and Tk <= 64: swizzled tiles, P never leaves the registers
+// ------------------------------------------------------------------------------------------
+// Same strip ownership as gAttentionForwardWarp; additionally the P strip is used as the A operand
+// of O = P V straight from the accumulator registers (permuted contraction slots, see the backward
+// kernel), the pitch is the compile-time constant 64 (fragment addresses fold into the LDS
+// immediates) and the key mask row is fetched once per lane while the tiles are in flight.
+template <bool X3>
+__global__ void __launch_bounds__(128) gAttentionForwardWarp64(float* __restrict__ out,
+                                                               float* __restrict__ probs,
+                                                               const float* __restrict__ q,
+                                                               const float* __restrict__ k,
+                                                               const float* __restrict__ v,
+                                                               const float* __restrict__ mask,
+                                                               AttnGeom g,
+                                                               int Rq,
+                                                               int Rk) {
+  extern __shared__ __align__(16) float smemF[];
+  pdlEnter();
+  float* sQ = smemF;          // [Rq][64]; A rows beyond Rq read into sK: finite, never stored
+  float* sK = sQ + Rq * 64;   // [Rk][64]
+  float* sV = sK + Rk * 64;   // [Rk][64]
+
+  const int bh = blockIdx.x, b = bh / g.H, h = bh - b * g.H;
+  const int row0 = blockIdx.y * 64;
+  const int d = g.H * 64;
+  const int rowsHere = min(64, g.Tq - row0);
+  loadHeadSwizzled(sQ, q + ((size_t)b * g.Tq + row0) * d + h * 64, rowsHere, Rq, d);
+  loadHeadSwizzled(sK, k + ((size_t)b * g.Tk) * d + h * 64, g.Tk, Rk, d);
+  loadHeadSwizzled(sV, v + ((size_t)b * g.Tk) * d + h * 64, g.Tk, Rk, d);
+  cpAsyncCommit();
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, gq = lane >> 2, t = lane & 3;
+  const int m0 = warp * 16;
+  const int nts = (g.Tk + 7) >> 3;
+  const int iLo = row0 + m0 + gq, iHi = iLo + 8;  // query rows of this lane (global index)
+  const bool pair = (g.Tk & 1) == 0;
+
+  // additive mask values of the lane's columns (rows lo / hi differ only for per-query masks)
+  float mk[8][4];
+  {
+    const float* mb = mask ? mask + (size_t)b * g.maskRows * g.Tk : nullptr;
+    const float* mLo = mb ? mb + (g.maskRows > 1 ? (size_t)min(iLo, g.Tq - 1) * g.Tk : 0) : nullptr;
+    const float* mHi = mb ? mb + (g.maskRows > 1 ? (size_t)min(iHi, g.Tq - 1) * g.Tk : 0) : nullptr;
+#pragma unroll
+    for(int i = 0; i < 8; ++i) {
+      const int j = i * 8 + 2 * t;
+      mk[i][0] = mk[i][1] = mk[i][2] = mk[i][3] = 0.f;
+      if(mb && j < g.Tk) {
+        if(pair) {
+          float2 x = *reinterpret_cast<const float2*>(mLo + j);
+          mk[i][0] = x.x;
+          mk[i][1] = x.y;
+          if(g.maskRows > 1)
+            x = *reinterpret_cast<const float2*>(mHi + j);
+          mk[i][2] = x.x;
+          mk[i][3] = x.y;
+        } else {
+          mk[i][0] = mLo[j];
+          mk[i][2] = mHi[j];
+          if(j + 1 < g.Tk) {
+            mk[i][1] = mLo[j + 1];
+            mk[i][3] = mHi[j + 1];
+          }
+        }
+      }
+    }
+  }
+  cpAsyncWaitGroup<0>();
+  __syncthreads();
+  if(m0 >= rowsHere)
+    return;  // the whole strip is padding (no block barrier below)
+
+  // ---- S strip = Q_w K^T ----
+  const int cA = t ^ (gq << 2);
+  float acc[8][4];
+#pragma unroll
+  for(int i = 0; i < 8; ++i)
+    acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+  {
+    const float* ap = sQ + (m0 + gq) * 64;
+    const float* bp0 = sK + gq * 64;
+#pragma unroll 2
+    for(int k0 = 0; k0 < 64; k0 += 8) {
+      const int c0 = k0 ^ cA, c1 = c0 ^ 4;
+      float af[4] = {ap[c0], ap[c0 + 8 * 64], ap[c1], ap[c1 + 8 * 64]};
+      uint32_t ahi[4] = {toTf32(af[0]), toTf32(af[1]), toTf32(af[2]), toTf32(af[3])};
+#pragma unroll
+      for(int i = 0; i < 8; ++i)
+        if(i < nts)
+          mmaSplit<X3>(acc[i], af, ahi, bp0[i * 512 + c0], bp0[i * 512 + c1]);
+    }
+  }
+
+  // ---- scale, mask, row softmax on the accumulators ----
+  float mxLo = -3.0e38f, mxHi = -3.0e38f;
+#pragma unroll
+  for(int i = 0; i < 8; ++i)
+#pragma unroll
+    for(int e = 0; e < 2; ++e) {
+      const bool real = i * 8 + 2 * t + e < g.Tk;
+      acc[i][e] = real ? fmaf(acc[i][e], g.scale, mk[i][e]) : -3.0e38f;
+      acc[i][2 + e] = real ? fmaf(acc[i][2 + e], g.scale, mk[i][2 + e]) : -3.0e38f;
+      mxLo = fmaxf(mxLo, acc[i][e]);
+      mxHi = fmaxf(mxHi, acc[i][2 + e]);
+    }
+  mxLo = fmaxf(mxLo, __shfl_xor_sync(0xffffffffu, mxLo, 1));
+  mxLo = fmaxf(mxLo, __shfl_xor_sync(0xffffffffu, mxLo, 2));
+  mxHi = fmaxf(mxHi, __shfl_xor_sync(0xffffffffu, mxHi, 1));
+  mxHi = fmaxf(mxHi, __shfl_xor_sync(0xffffffffu, mxHi, 2));
+  float sumLo = 0.f, sumHi = 0.f;
+#pragma unroll
+  for(int i = 0; i < 8; ++i)
+#pragma unroll
+    for(int e = 0; e < 2; ++e) {
+      const bool real = i * 8 + 2 * t + e < g.Tk;
+      acc[i][e] = real ? __expf(acc[i][e] - mxLo) : 0.f;
+      acc[i][2 + e] = real ? __expf(acc[i][2 + e] - mxHi) : 0.f;
+      sumLo += acc[i][e];
+      sumHi += acc[i][2 + e];
+    }
+  sumLo += __shfl_xor_sync(0xffffffffu, sumLo, 1);
+  sumLo += __shfl_xor_sync(0xffffffffu, sumLo, 2);
+  sumHi += __shfl_xor_sync(0xffffffffu, sumHi, 1);
+  sumHi += __shfl_xor_sync(0xffffffffu, sumHi, 2);
+  const float invLo = 1.f / sumLo, invHi = 1.f / sumHi;
+  float* pLo = (probs && iLo < g.Tq) ? probs + (((size_t)b * g.H + h) * g.Tq + iLo) * g.Tk : nullptr;
+  float* pHi = (probs && iHi < g.Tq) ? probs + (((size_t)b * g.H + h) * g.Tq + iHi) * g.Tk : nullptr;
+#pragma unroll
+  for(int i = 0; i < 8; ++i) {
+    const int j = i * 8 + 2 * t;
+    acc[i][0] *= invLo;
+    acc[i][1] *= invLo;
+    acc[i][2] *= invHi;
+    acc[i][3] *= invHi;
+    if(j < g.Tk) {
+      if(pair) {
+        if(pLo)
+          *reinterpret_cast<float2*>(pLo + j) = make_float2(acc[i][0], acc[i][1]);
+        if(pHi)
+          *reinterpret_cast<float2*>(pHi + j) = make_float2(acc[i][2], acc[i][3]);
+      } else {
+        if(pLo) {
+          pLo[j] = acc[i][0];
+          if(j + 1 < g.Tk)
+            pLo[j + 1] = acc[i][1];
+        }
+        if(pHi) {
+          pHi[j] = acc[i][2];
+          if(j + 1 < g.Tk)
+            pHi[j + 1] = acc[i][3];
+        }
+      }
+    }
+  }
+
+  // ---- O strip = P_w V, A operand from the P registers (slot t <-> key 8i+2t, slot t+4 <-> key 8i+2t+1) ----
+  const int cE = gq ^ (t << 3), cO = cE ^ 4;
+  float o[8][4];
+#pragma unroll
+  for(int n = 0; n < 8; ++n)
+    o[n][0] = o[n][1] = o[n][2] = o[n][3] = 0.f;
+#pragma unroll
+  for(int i = 0; i < 8; ++i)
+    if(i < nts) {
+      float af[4] = {acc[i][0], acc[i][2], acc[i][1], acc[i][3]};
+      uint32_t ahi[4] = {toTf32(af[0]), toTf32(af[1]), toTf32(af[2]), toTf32(af[3])};
+      const float* vp = sV + (i * 8 + 2 * t) * 64;
+#pragma unroll
+      for(int n = 0; n < 8; ++n)
+        mmaSplit<X3>(o[n], af, ahi, vp[(n * 8) ^ cE], vp[64 + ((n * 8) ^ cO)]);
+    }
+  storeStrip(iLo < g.Tq ? out + ((size_t)b * g.Tq + iLo) * d + h * 64 : nullptr, iHi < g.Tq ? out + ((size_t)b * g.Tq + iHi) * d + h * 64 : nullptr, o, 8, t, false);
+}
+
 size_t forwardSmem(const AttnGeom& g) {
   return ((size_t)(g.Tq + 2 * g.Tk) * (g.dk + 4) + (size_t)g.Tq * (pad4(g.Tk) + 1)) * sizeof(float);
 }
@@ -1194,9 +1369,31 @@ void MultiHeadAttention(Tensor out, Tensor probs, const Tensor q, const Tensor k
   out->takeLazyZero();
   AttnGeom g = geometry(q, k, mask, heads, scale);
   {
-    // warp-private kernel: dk <= 64, Tk <= 128
+    // warp-private kernels: dk == 64 and Tk <= 64 (swizzled tiles, register-resident P), else dk <= 64, Tk <= 128
     static const bool noWarp = std::getenv("MRN_ATTENTION_NO_WARP") != nullptr;
     const int TkP = pad16(g.Tk);
+    if(!noWarp && g.dk == 64 && g.Tk <= 64) {
+      const int Rk = 8 * ((g.Tk + 7) / 8);
+      const int Rq = g.Tq >= 64 ? 64 : 8 * ((g.Tq + 7) / 8);
+      const size_t smemW = (size_t)(Rq + 2 * Rk) * 64 * sizeof(float);
+      static bool configured = false;
+      if(!configured) {
+        CUDA_CHECK(cudaFuncSetAttribute(gAttentionForwardWarp64<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 64 * 64 * (int)sizeof(float)));
+        CUDA_CHECK(cudaFuncSetAttribute(gAttentionForwardWarp64<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 3 * 64 * 64 * (int)sizeof(float)));
+        CUDA_CHECK(cudaFuncSetAttribute(gAttentionForwardWarp64<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        CUDA_CHECK(cudaFuncSetAttribute(gAttentionForwardWarp64<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        configured = true;
+      }
+      float* pp = probs ? probs->data() : nullptr;
+      const float* mp = mask ? mask->data() : nullptr;
+      dim3 grid(g.B * g.H, (g.Tq + 63) / 64);
+      if(exact)
+        launchPdl(gAttentionForwardWarp64<true>, grid, dim3(128), smemW, cudaStreamOfEngine(), out->data(), pp, (const float*)q->data(), (const float*)k->data(), (const float*)v->data(), mp, g, Rq, Rk);
+      else
+        launchPdl(gAttentionForwardWarp64<false>, grid, dim3(128), smemW, cudaStreamOfEngine(), out->data(), pp, (const float*)q->data(), (const float*)k->data(), (const float*)v->data(), mp, g, Rq, Rk);
+      CUDA_LAUNCH_CHECK();
+      return;
+    }
     if(!noWarp && g.dk % 8 == 0 && g.dk <= 64 && TkP <= 128) {
       const int ldQ = pitchMod32(g.dk > TkP ? g.dk : TkP, 4);
       size_t smemW = ((size_t)64 * ldQ + (size_t)TkP * pitchMod32(g.dk, 4) + (size_t)TkP * pitchMod32(g.dk, 8)) * sizeof(float);
