@@ -263,15 +263,29 @@ __device__ __forceinline__ void rowStats(const float* __restrict__ sp, int cols,
   m = -3.4e38f;
   s = 0.f;
   if(VEC) {
+    // one rescale per 128-bit chunk, ex2.approx exponentials (the reference's release build is
+    // compiled with --use_fast_math): the full-precision expf made this HBM stream issue-bound.
+    // Four independent 128-bit loads are in flight per thread.
     const float4* p4 = reinterpret_cast<const float4*>(sp);
-    int n4 = cols >> 2;
-    for(int i = first; i < n4; i += stride) {
-      float4 q = p4[i];
-      onlineUpdate(m, s, q.x);
-      onlineUpdate(m, s, q.y);
-      onlineUpdate(m, s, q.z);
-      onlineUpdate(m, s, q.w);
+    const int n4 = cols >> 2;
+    auto fold = [&](const float4& q) {
+      float mx = fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w));
+      if(mx > m) {
+        s *= __expf(m - mx);
+        m = mx;
+      }
+      s += (__expf(q.x - m) + __expf(q.y - m)) + (__expf(q.z - m) + __expf(q.w - m));
+    };
+    int i = first;
+    for(; i + 3 * stride < n4; i += 4 * stride) {
+      float4 q0 = p4[i], q1 = p4[i + stride], q2 = p4[i + 2 * stride], q3 = p4[i + 3 * stride];
+      fold(q0);
+      fold(q1);
+      fold(q2);
+      fold(q3);
     }
+    for(; i < n4; i += stride)
+      fold(p4[i]);
   } else {
     for(int id = first; id < cols; id += stride)
       onlineUpdate(m, s, sp[id]);
@@ -328,10 +342,10 @@ __global__ void gCrossEntropyPickBackward(float* __restrict__ out, const float* 
         float4 x = p4[i];
         float4 g = assign ? make_float4(0.f, 0.f, 0.f, 0.f) : o4[i];
         int id = i << 2;
-        g.x += a * (expf(x.x - M) * invS - (float)(id == p));
-        g.y += a * (expf(x.y - M) * invS - (float)(id + 1 == p));
-        g.z += a * (expf(x.z - M) * invS - (float)(id + 2 == p));
-        g.w += a * (expf(x.w - M) * invS - (float)(id + 3 == p));
+        g.x += a * (__expf(x.x - M) * invS - (float)(id == p));
+        g.y += a * (__expf(x.y - M) * invS - (float)(id + 1 == p));
+        g.z += a * (__expf(x.z - M) * invS - (float)(id + 2 == p));
+        g.w += a * (__expf(x.w - M) * invS - (float)(id + 3 == p));
         o4[i] = g;
       }
     } else {
@@ -561,8 +575,11 @@ __device__ __forceinline__ float lnGradElem(float a, float x_hat, float g, float
   return fabsf(valX) > 1000.f ? sign * 1000.f : valX;  // clip kept from the reference
 }
 
-template <int VPL>
-__global__ void __launch_bounds__(256) gLayerNormalizationGradWarp(float* __restrict__ gradX,
+// WARPS = 16 (rows of up to 512 floats), one block per SM: twice the rows in flight of an 8-warp block
+// at the same number of block-level column reductions (same-address red.add serialise in L2); beta is
+// then re-read (L1) instead of cached, to stay within 128 registers
+template <int VPL, int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, 1) gLayerNormalizationGradWarp(float* __restrict__ gradX,
                                                                    float* __restrict__ gradGamma,
                                                                    float* __restrict__ gradBeta,
                                                                    const float* __restrict__ adj,
@@ -578,7 +595,7 @@ __global__ void __launch_bounds__(256) gLayerNormalizationGradWarp(float* __rest
                                                                    float* __restrict__ gradRes,
                                                                    int assignRes) {
   pdlEnter();
-  __shared__ float4 red[8][32 * VPL];
+  __shared__ float4 red[WARPS][32 * VPL];
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   float4 g4[VPL], b4[VPL], accG[VPL], accB[VPL];
@@ -590,7 +607,7 @@ __global__ void __launch_bounds__(256) gLayerNormalizationGradWarp(float* __rest
     accG[i] = accB[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   const float fcols = (float)cols;
-  for(int row = blockIdx.x * 8 + warp; row < rows; row += gridDim.x * 8) {
+  for(int row = blockIdx.x * WARPS + warp; row < rows; row += gridDim.x * WARPS) {
     const size_t off = (size_t)row * cols;
     float4 xh[VPL], av[VPL];
     float sum_x = 0.f, sum_adj = 0.f, sum_adj_x = 0.f, sq = 0.f;
@@ -614,10 +631,12 @@ __global__ void __launch_bounds__(256) gLayerNormalizationGradWarp(float* __rest
           xv[i].y += rv[i].y;
           xv[i].z += rv[i].z;
           xv[i].w += rv[i].w;
-          xh[i].x = (yv[i].x - b4[i].x) / g4[i].x;
-          xh[i].y = (yv[i].y - b4[i].y) / g4[i].y;
-          xh[i].z = (yv[i].z - b4[i].z) / g4[i].z;
-          xh[i].w = (yv[i].w - b4[i].w) / g4[i].w;
+          const float4 bv = WARPS > 8 ? (beta ? *reinterpret_cast<const float4*>(beta + c) : make_float4(0.f, 0.f, 0.f, 0.f)) : b4[i];
+          const float4 gv = WARPS > 8 ? *reinterpret_cast<const float4*>(gamma + c) : g4[i];
+          xh[i].x = (yv[i].x - bv.x) / gv.x;
+          xh[i].y = (yv[i].y - bv.y) / gv.y;
+          xh[i].z = (yv[i].z - bv.z) / gv.z;
+          xh[i].w = (yv[i].w - bv.w) / gv.w;
         } else {
           xv[i] = xh[i] = av[i] = make_float4(0.f, 0.f, 0.f, 0.f);
         }
@@ -644,10 +663,11 @@ __global__ void __launch_bounds__(256) gLayerNormalizationGradWarp(float* __rest
       int c = (i * 32 + lane) * 4;
       if(c < cols) {
         float4 v;
-        v.x = lnGradElem(av[i].x, xh[i].x, g4[i].x, sum_adj, sum_adj_x, fcols, sigma);
-        v.y = lnGradElem(av[i].y, xh[i].y, g4[i].y, sum_adj, sum_adj_x, fcols, sigma);
-        v.z = lnGradElem(av[i].z, xh[i].z, g4[i].z, sum_adj, sum_adj_x, fcols, sigma);
-        v.w = lnGradElem(av[i].w, xh[i].w, g4[i].w, sum_adj, sum_adj_x, fcols, sigma);
+        const float4 gv = WARPS > 8 ? *reinterpret_cast<const float4*>(gamma + c) : g4[i];
+        v.x = lnGradElem(av[i].x, xh[i].x, gv.x, sum_adj, sum_adj_x, fcols, sigma);
+        v.y = lnGradElem(av[i].y, xh[i].y, gv.y, sum_adj, sum_adj_x, fcols, sigma);
+        v.z = lnGradElem(av[i].z, xh[i].z, gv.z, sum_adj, sum_adj_x, fcols, sigma);
+        v.w = lnGradElem(av[i].w, xh[i].w, gv.w, sum_adj, sum_adj_x, fcols, sigma);
         if(gradRes) {  // d(x + r)/dr = 1: the residual branch receives the same gradient
           float4* gr = reinterpret_cast<float4*>(gradRes + off + c);
           float4 w = v;
@@ -680,7 +700,7 @@ __global__ void __launch_bounds__(256) gLayerNormalizationGradWarp(float* __rest
       }
     }
   }
-  // column sums of the block: 8 warps meet in shared memory, ONE atomic per block and column
+  // column sums of the block: the warps meet in shared memory, ONE atomic per block and column
 #pragma unroll 1
   for(int pass = 0; pass < 2; ++pass) {
     float* dst = pass == 0 ? gradGamma : gradBeta;
@@ -696,7 +716,7 @@ __global__ void __launch_bounds__(256) gLayerNormalizationGradWarp(float* __rest
       if(c < cols) {
         float4 sum = red[0][e];
 #pragma unroll
-        for(int w = 1; w < 8; ++w) {
+        for(int w = 1; w < WARPS; ++w) {
           float4 t = red[w][e];
           sum.x += t.x;
           sum.y += t.y;
@@ -756,13 +776,15 @@ void LayerNormalizationGrad(Tensor gradX, Tensor gradGamma, Tensor gradBeta, Ten
       float* grp = gradResidual ? gradResidual->data() : nullptr;
       // few, fat blocks: every block ends with one 128-bit reduction per 4 columns for gamma and
       // beta; same-address reductions serialise in L2, so one block per SM is the sweet spot
-      int grid = std::max(1, std::min((rows + 15) / 16, kNumSMs));
-      if(cols <= 512)
-        launchPdl(gLayerNormalizationGradWarp<4>, dim3(grid), dim3(256), 0, st, gradX->data(), gradGamma->data(), gbp, (const float*)adj->data(), (const float*)y->data(), (const float*)x->data(),
+      if(cols <= 512) {
+        int grid = std::max(1, std::min((rows + 15) / 16, kNumSMs));
+        launchPdl(gLayerNormalizationGradWarp<4, 16>, dim3(grid), dim3(512), 0, st, gradX->data(), gradGamma->data(), gbp, (const float*)adj->data(), (const float*)y->data(), (const float*)x->data(),
                   (const float*)gamma->data(), bp, rows, cols, eps, assignX, rp, grp, assignRes);
-      else
-        launchPdl(gLayerNormalizationGradWarp<8>, dim3(grid), dim3(256), 0, st, gradX->data(), gradGamma->data(), gbp, (const float*)adj->data(), (const float*)y->data(), (const float*)x->data(),
+      } else {
+        int grid = std::max(1, std::min((rows + 15) / 16, kNumSMs));
+        launchPdl(gLayerNormalizationGradWarp<8, 8>, dim3(grid), dim3(256), 0, st, gradX->data(), gradGamma->data(), gbp, (const float*)adj->data(), (const float*)y->data(), (const float*)x->data(),
                   (const float*)gamma->data(), bp, rows, cols, eps, assignX, rp, grp, assignRes);
+      }
       CUDA_LAUNCH_CHECK();
       return;
     }
