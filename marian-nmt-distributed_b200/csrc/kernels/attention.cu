@@ -959,7 +959,7 @@ __global__ void __launch_bounds__(128) gAttentionBackwardWarp(float* __restrict_
   extern __shared__ __align__(16) float smemF[];
   pdlEnter();
   const int TILE = R * 64;
-  float* sdO = smemF;  // A rows beyond R (the padding part of the last strip) read into sV: finite, never stored
+  float* sdO = smemF;
   float* sV = sdO + TILE;
   float* sK = sV + TILE;
   float* sQ = sK + TILE;
@@ -1028,12 +1028,15 @@ __global__ void __launch_bounds__(128) gAttentionBackwardWarp(float* __restrict_
   for(int i = 0; i < 8; ++i)
     acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
   {
-    const float* ap = sdO + iLo * 64;
+    // strips beyond the tile (pure padding, results never stored) re-read rows gq of the tile: the
+    // row index keeps (row mod 8) == gq, so the swizzle term is unchanged
+    const float* ap = sdO + (iLo < R ? iLo : gq) * 64;
+    const int hiOff = ((iHi < R ? iHi : gq) - (iLo < R ? iLo : gq)) * 64;
     const float* bp0 = sV + gq * 64;
 #pragma unroll 2
     for(int k0 = 0; k0 < 64; k0 += 8) {
       const int c0 = k0 ^ cA, c1 = c0 ^ 4;
-      float af[4] = {ap[c0], ap[c0 + 8 * 64], ap[c1], ap[c1 + 8 * 64]};
+      float af[4] = {ap[c0], ap[c0 + hiOff], ap[c1], ap[c1 + hiOff]};
       uint32_t ahi[4] = {toTf32(af[0]), toTf32(af[1]), toTf32(af[2]), toTf32(af[3])};
 #pragma unroll
       for(int i = 0; i < 8; ++i)

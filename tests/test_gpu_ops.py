@@ -263,6 +263,13 @@ def _attention_numpy(q, k, v, mask, heads, scale):
     (3, 2, 33, 7, 32, "none"),
     (2, 16, 80, 80, 64, "causal"),    # config E head shape
     (2, 3, 128, 128, 64, "key"),      # largest supported sequence
+    # warp-private dk = 64 kernels (swizzled tiles, register-resident strips): ragged edges
+    (4, 4, 37, 64, 64, "key"),        # Tq != Tk, full 64-key tile
+    (3, 2, 33, 51, 64, "none"),       # odd Tk: scalar probs / mask accesses
+    (2, 2, 100, 40, 64, "key"),       # two 64-row query blocks forward, generic kernel backward
+    (2, 8, 64, 64, 64, "causal"),     # exactly one full tile, per-query mask
+    (3, 1, 5, 7, 64, "key"),          # a single partly filled strip
+    (2, 2, 56, 49, 64, "key"),        # 56-row tiles (four CTAs per SM), odd Tk
 ])
 @pytest.mark.parametrize("exact,tol", [(1, 3e-5), (0, 3e-3)], ids=["3xtf32", "tf32"])
 def test_multi_head_attention(cuda, oracle, B, H, Tq, Tk, dk, mask_kind, exact, tol):
@@ -309,6 +316,33 @@ def test_multi_head_attention(cuda, oracle, B, H, Tq, Tk, dk, mask_kind, exact, 
     close(got["dq"], join(dq, Tq) + rnd(6, B, Tq, d), tol, "dq vs numpy")
     close(got["dk"], join(dk_, Tk) + rnd(7, B, Tk, d), tol, "dk vs numpy")
     close(got["dv"], join(dv, Tk) + rnd(8, B, Tk, d), tol, "dv vs numpy")
+
+
+@pytest.mark.parametrize("B,H,T,dk", [(3, 4, 50, 64), (2, 2, 80, 64), (2, 2, 21, 32)])
+def test_multi_head_attention_aliased_gradients(cuda, oracle, B, H, T, dk):
+    # keys and values from the SAME tensor (attention without projections): the gradient tensor is
+    # shared too, the kernels must accumulate both contributions into it
+    d = H * dk
+    q, kv, adj = rnd(11, B, T, d), rnd(12, B, T, d), rnd(13, B, T, d)
+    scale = 1.0 / np.sqrt(dk)
+
+    def fn(lib):
+        out, probs = lib.zeros((B, T, d)), lib.zeros((B, H, T, T))
+        qa, ka = lib.array(q), lib.array(kv)
+        lib.call("mrn_multi_head_attention", out.t(), probs.t(), qa.t(), ka.t(), ka.t(), None, H, scale, 1)
+        dq, dkv = lib.zeros((B, T, d)), lib.zeros((B, T, d))
+        lib.call("mrn_multi_head_attention_grad", dq.t(), dkv.t(), dkv.t(), lib.array(adj).t(), out.t(), probs.t(), qa.t(), ka.t(), ka.t(), H, scale, 1)
+        return {"out": out.numpy(), "dq": dq.numpy(), "dkv": dkv.numpy()}
+
+    got, exp = both(cuda, oracle, fn)
+    for key in exp:
+        close(got[key], exp[key], 3e-5, key)
+    o, p, (qh, kh, vh) = _attention_numpy(q, kv, kv, None, H, scale)
+    do = adj.reshape(B, T, H, dk).transpose(0, 2, 1, 3).astype(np.float64)
+    dp = do @ vh.transpose(0, 1, 3, 2)
+    ds = p * (dp - (dp * p).sum(-1, keepdims=True))
+    dkv = p.transpose(0, 1, 3, 2) @ do + scale * ds.transpose(0, 1, 3, 2) @ qh
+    close(got["dkv"], dkv.transpose(0, 2, 1, 3).reshape(B, T, d), 3e-5, "dK + dV vs numpy")
 
 
 def test_layer_norm_reference_golden_input(cuda, oracle, goldens):
