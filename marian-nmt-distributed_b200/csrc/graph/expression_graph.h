@@ -308,6 +308,12 @@ public:
       }
 
       if(v->trainable()) {
+        {
+          std::vector<Expr> upcoming;
+          for(auto it = nodesBackward_.rbegin(); it != nodesBackward_.rend() && upcoming.size() < 2; ++it)
+            upcoming.push_back(*it);
+          v->fuseBackward(upcoming);
+        }
         if(nodeTiming()) {
           auto t0 = std::chrono::steady_clock::now();
           v->backward();

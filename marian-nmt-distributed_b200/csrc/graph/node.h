@@ -39,6 +39,7 @@ struct Chainable {
 
   virtual void forward() = 0;
   virtual void backward() = 0;
+  virtual void fuseBackward(const std::vector<std::shared_ptr<Chainable<DataType>>>& /*upcoming*/) {}
   virtual NodeOps forwardOps() = 0;
   virtual NodeOps backwardOps() = 0;
 
@@ -123,6 +124,10 @@ public:
 
   virtual void forward() { runForward(forwardOps()); }
   virtual void backward() { runBackward(backwardOps()); }
+  // Peephole of the backward sweep: `upcoming` holds the nodes that run right after this one (next
+  // first).  Their adjoints are complete (all their consumers precede them in the sweep and this
+  // node is none of them), so a node may take over part of their backward work and mark them.
+  virtual void fuseBackward(const std::vector<Expr>& /*upcoming*/) {}
 
   virtual bool trainable() { return trainable_; }
   virtual void setTrainable(bool trainable) { trainable_ = trainable; }

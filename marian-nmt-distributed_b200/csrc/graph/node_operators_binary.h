@@ -111,10 +111,40 @@ struct AffineNodeOp : public NaryNodeOp {
   NodeOps forwardOps() {
     return {NodeOp(ProdAffine(getBackend()->getGemmHandle(), val_, child(0)->val(), child(1)->val(), child(2)->val()))};
   }
+  // Projections of the SAME input that follow each other in the backward sweep (query / key / value
+  // of an attention block): dX = sum_g adj_g W_g^T is issued as one K-grouped product instead of a
+  // chain of dependent accumulating products (kernels/gemm.cu ProdGroupedNT); the partners are
+  // marked so that their own input-gradient closure does nothing.
+  bool inputGradDone_{false};
+  void fuseBackward(const std::vector<Expr>& upcoming) {
+    static const bool enabled = std::getenv("MRN_NO_GROUPED_DX") == nullptr;
+    if(!enabled || inputGradDone_ || !child(0)->trainable())
+      return;
+    std::vector<AffineNodeOp*> group{this};
+    for(auto& u : upcoming) {
+      auto* a = dynamic_cast<AffineNodeOp*>(u.get());
+      if(!a || a->child(0) != child(0) || !a->trainable() || a->inputGradDone_ || a->shape() != shape() || a->child(1)->shape() != child(1)->shape())
+        break;
+      group.push_back(a);
+    }
+    if(group.size() < 2)
+      return;
+    std::vector<Tensor> adjs, weights;
+    for(auto* a : group) {
+      adjs.push_back(a->adj_);
+      weights.push_back(a->child(1)->val());
+    }
+    ProdGroupedNT(getBackend()->getGemmHandle(), child(0)->grad(), adjs, weights, 1.0);
+    for(auto* a : group)
+      a->inputGradDone_ = true;
+  }
   NodeOps backwardOps() {
     using namespace functional;
     // dW and db hang off the backward chain: side stream when W / b are parameters
-    return {NodeOp(offCriticalPath(child(0), [&] { Prod(getBackend()->getGemmHandle(), child(0)->grad(), adj_, child(1)->val(), false, true, 1.0); })),
+    return {NodeOp(offCriticalPath(child(0), [&] {
+              if(!inputGradDone_)
+                Prod(getBackend()->getGemmHandle(), child(0)->grad(), adj_, child(1)->val(), false, true, 1.0);
+            })),
             NodeOp(offCriticalPath(child(1), [&] { Prod(getBackend()->getGemmHandle(), child(1)->grad(), child(0)->val(), adj_, true, false, 1.0); })),
             NodeOp(offCriticalPath(child(2), [&] { Add(_1, child(2)->grad(), adj_); }))};
   }

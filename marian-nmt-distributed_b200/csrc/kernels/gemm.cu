@@ -605,6 +605,7 @@ struct TcArgs {
   int ldc;
   int kBlocks;          // total 64-wide K blocks
   int kBlocksPerSplit;  // blocks handled by one z-slice
+  int kBlocksGroup;     // K-grouped products: k-blocks per (A_g, B_g) pair; kBlocks = groups * kBlocksGroup
   int splits;
   int rowsPerBatchA, rowsPerBatchB;  // row pitch between batches in the packed operands (0 = shared)
   size_t strideC;
@@ -906,8 +907,17 @@ __device__ __forceinline__ void epilogueTile(const TcArgs& a, uint32_t tmemBase,
   }
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
-__global__ void __launch_bounds__(192) gGemmTf32(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, TcArgs a) {
+// Operand descriptors of a launch.  G > 1: K-grouped product C = sum_g A_g op(B_g) over G separate
+// tensor pairs (the input gradient of several projections of the same tensor: dX = dQ Wq^T + dK Wk^T +
+// dV Wv^T is ONE launch whose CTAs walk 3 x K/32 k-blocks instead of three dependent launches).
+template <int G>
+struct alignas(64) TfMaps {
+  CUtensorMap a[G];
+  CUtensorMap b[G];
+};
+
+template <int BN, int STAGES, bool A_MN, bool B_MN, int G = 1>
+__global__ void __launch_bounds__(192) gGemmTf32(const __grid_constant__ TfMaps<G> tm, TcArgs a) {
   typedef TfSmem<BN, STAGES> L;
   extern __shared__ uint8_t smemRaw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smemRaw + 1023) & ~(uintptr_t)1023);
@@ -938,8 +948,11 @@ __global__ void __launch_bounds__(192) gGemmTf32(const __grid_constant__ CUtenso
   const int nkb = min(a.kBlocksPerSplit, a.kBlocks - kb0);
 
   if(warp == 0 && lane == 0) {
-    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmA) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tmB) : "memory");
+#pragma unroll
+    for(int g = 0; g < G; ++g) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm.a[g]) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm.b[g]) : "memory");
+    }
     for(int s = 0; s < STAGES; ++s) {
       mbarInit(fullBar + s, 1);
       mbarInit(emptyBar + s, 1);
@@ -973,20 +986,24 @@ __global__ void __launch_bounds__(192) gGemmTf32(const __grid_constant__ CUtenso
         mbarExpectTx(fullBar + s, (uint32_t)L::STAGE_BYTES);
         uint8_t* sa = smem + s * L::STAGE_BYTES;
         uint8_t* sb = sa + L::A_BYTES;
-        int kc = (kb0 + i) * TF_BLOCK_K;
+        const int kAbs = kb0 + i;
+        const int grp = G == 1 ? 0 : kAbs / a.kBlocksGroup;
+        const int kc = (G == 1 ? kAbs : kAbs - grp * a.kBlocksGroup) * TF_BLOCK_K;
+        const CUtensorMap* tmA = &tm.a[grp];
+        const CUtensorMap* tmB = &tm.b[grp];
         if(A_MN) {
 #pragma unroll
           for(int c = 0; c < BLOCK_M / 32; ++c)
-            tmaLoad3D(&tmA, fullBar + s, sa + c * 4096, m0 + 32 * c, kc, batchA);
+            tmaLoad3D(tmA, fullBar + s, sa + c * 4096, m0 + 32 * c, kc, batchA);
         } else {
-          tmaLoad3D(&tmA, fullBar + s, sa, kc, m0, batchA);
+          tmaLoad3D(tmA, fullBar + s, sa, kc, m0, batchA);
         }
         if(B_MN) {
 #pragma unroll
           for(int c = 0; c < BN / 32; ++c)
-            tmaLoad3D(&tmB, fullBar + s, sb + c * 4096, n0 + 32 * c, kc, batchB);
+            tmaLoad3D(tmB, fullBar + s, sb + c * 4096, n0 + 32 * c, kc, batchB);
         } else {
-          tmaLoad3D(&tmB, fullBar + s, sb, kc, n0, batchB);
+          tmaLoad3D(tmB, fullBar + s, sb, kc, n0, batchB);
         }
       }
     }
@@ -1074,6 +1091,7 @@ struct GemmProblem {
   size_t strideA, strideB;  // 0 when the operand is shared by all batches
   bool transA, transB;
   float beta, alpha;
+  std::vector<Tensor> moreA, moreB;  // K-grouped product: further (A_g, B_g) pairs of the same shapes
 };
 
 void runSimt(const GemmProblem& p) {
@@ -1193,16 +1211,33 @@ CUtensorMap makeTensorMapF32(GemmHandle h, const float* base, uint64_t inner, ui
   return map;
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN>
-void launchTf32(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, int batches) {
+template <int BN, int STAGES, bool A_MN, bool B_MN, int G>
+void launchTf32Maps(const TfMaps<G>& tm, const TcArgs& a, int batches) {
   typedef TfSmem<BN, STAGES> L;
   static bool configured = false;
   if(!configured) {
-    CUDA_CHECK(cudaFuncSetAttribute(gGemmTf32<BN, STAGES, A_MN, B_MN>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    CUDA_CHECK(cudaFuncSetAttribute(gGemmTf32<BN, STAGES, A_MN, B_MN, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
   dim3 grid((a.M + BLOCK_M - 1) / BLOCK_M, (a.N + BN - 1) / BN, batches * a.splits);
-  launchPdl(gGemmTf32<BN, STAGES, A_MN, B_MN>, grid, dim3(192), (size_t)L::TOTAL, cudaStreamOfEngine(), tmA, tmB, a);
+  launchPdl(gGemmTf32<BN, STAGES, A_MN, B_MN, G>, grid, dim3(192), (size_t)L::TOTAL, cudaStreamOfEngine(), tm, a);
+}
+
+template <int BN, int STAGES, bool A_MN, bool B_MN>
+void launchTf32(const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a, int batches) {
+  TfMaps<1> tm;
+  tm.a[0] = tmA;
+  tm.b[0] = tmB;
+  launchTf32Maps<BN, STAGES, A_MN, B_MN, 1>(tm, a, batches);
+}
+
+// K-grouped launch (both operands K-major: C = sum_g A_g B_g^T)
+template <int G>
+void launchTf32Grouped(int BN, const TfMaps<G>& tm, const TcArgs& a) {
+  if(BN == 128)
+    launchTf32Maps<128, 3, false, false, G>(tm, a, 1);
+  else
+    launchTf32Maps<64, 4, false, false, G>(tm, a, 1);
 }
 
 template <bool A_MN, bool B_MN>
@@ -1228,13 +1263,23 @@ bool runTf32(GemmHandle h, const GemmProblem& p) {
   bool batched = p.batches > 1;
   const bool aMN = p.transA;   // stored [K, M]: M contiguous
   const bool bMN = !p.transB;  // stored [K, N]: N contiguous
+  const int G = 1 + (int)p.moreA.size();
+  if(G > 1) {
+    // K-grouped: both operands K-major, whole k-blocks per group, identical shapes, at most 3 pairs
+    if(aMN || bMN || batched || G > 3 || (K % TF_BLOCK_K) != 0 || p.moreB.size() != p.moreA.size())
+      return false;
+    for(int g = 0; g + 1 < G; ++g)
+      if(p.moreA[g]->shape() != p.A->shape() || p.moreB[g]->shape() != p.B->shape() || !tmaUsable(p.moreA[g]->data(), p.colsA, 0) || !tmaUsable(p.moreB[g]->data(), p.colsB, 0))
+        return false;
+  }
+  const int kGroup = (K + TF_BLOCK_K - 1) / TF_BLOCK_K;  // k-blocks of one (A, B) pair
 
   // Tile width and split-K are picked together by a small cost model calibrated on this GPU
   // (scripts/gemm_probe.py, in-graph timings in profiles/): a CTA costs a fixed prologue, its
   // k-blocks (operand traffic L2 -> smem: 24 KB per block at BN=64, 32 KB at BN=128), an epilogue
   // proportional to the tile; CTAs run 2 per SM in waves of 296; splitting K adds the red.add
   // traffic and, when C is not being accumulated into, a memset.
-  const int kBlocksAll = (K + TF_BLOCK_K - 1) / TF_BLOCK_K;
+  const int kBlocksAll = G * kGroup;
   int BN = 64, splits = 1;
   {
     const long mTiles = (M + BLOCK_M - 1) / BLOCK_M;
@@ -1266,7 +1311,7 @@ bool runTf32(GemmHandle h, const GemmProblem& p) {
   if(const char* t = std::getenv("MRN_GEMM_TRY")) {
     int m, n, k, bn, sp;
     float be;
-    if(sscanf(t, "%d,%d,%d,%f,%d,%d", &m, &n, &k, &be, &bn, &sp) == 6 && m == M && n == N && k == K && be == p.beta && !batched) {
+    if(sscanf(t, "%d,%d,%d,%f,%d,%d", &m, &n, &k, &be, &bn, &sp) == 6 && m == M && n == N && k == K * G && be == p.beta && !batched) {
       BN = bn == 128 ? 128 : 64;
       splits = std::max(1, sp);
     }
@@ -1283,7 +1328,8 @@ bool runTf32(GemmHandle h, const GemmProblem& p) {
   a.M = M;
   a.N = N;
   a.ldc = N;
-  a.kBlocks = (K + TF_BLOCK_K - 1) / TF_BLOCK_K;
+  a.kBlocks = kBlocksAll;
+  a.kBlocksGroup = kGroup;
   a.stamps = g_stampBuffer;  // null unless gemmDebugStamps() armed it
   a.rowsPerBatchA = (batched && p.strideA) ? 1 : 0;  // batched-operand flags for the producer
   a.rowsPerBatchB = (batched && p.strideB) ? 1 : 0;
@@ -1307,10 +1353,28 @@ bool runTf32(GemmHandle h, const GemmProblem& p) {
       Element(_1 = p.beta * _1, p.C);
   }
 
-  ProfileScope prof(2.0 * M * N * K * p.batches);
+  ProfileScope prof(2.0 * M * N * K * G * p.batches);
   a.spanMin = prof.spanMin;
   a.spanMax = prof.spanMax;
-  if(aMN && bMN)
+  if(G > 1) {
+    TfMaps<3> tm3;
+    tm3.a[0] = tmA;
+    tm3.b[0] = tmB;
+    for(int g = 1; g < G; ++g) {
+      tm3.a[g] = makeTensorMapF32(h, p.moreA[g - 1]->data(), (uint64_t)p.colsA, (uint64_t)p.rowsA, 1, (uint64_t)p.colsA, 0, BLOCK_M, false);
+      tm3.b[g] = makeTensorMapF32(h, p.moreB[g - 1]->data(), (uint64_t)p.colsB, (uint64_t)p.rowsB, 1, (uint64_t)p.colsB, 0, (uint32_t)BN, false);
+    }
+    if(G == 2) {
+      TfMaps<2> tm2;
+      for(int g = 0; g < 2; ++g) {
+        tm2.a[g] = tm3.a[g];
+        tm2.b[g] = tm3.b[g];
+      }
+      launchTf32Grouped<2>(BN, tm2, a);
+    } else {
+      launchTf32Grouped<3>(BN, tm3, a);
+    }
+  } else if(aMN && bMN)
     launchTf32Tile<true, true>(BN, tmA, tmB, a, p.batches);
   else if(aMN)
     launchTf32Tile<true, false>(BN, tmA, tmB, a, p.batches);
@@ -1319,7 +1383,7 @@ bool runTf32(GemmHandle h, const GemmProblem& p) {
   else
     launchTf32Tile<false, false>(BN, tmA, tmB, a, p.batches);
   if(prof.on)
-    prof.finish(std::to_string(M) + "," + std::to_string(N) + "," + std::to_string(K) + "," + std::to_string(p.batches) + "," + (aMN ? "T" : "N") + (bMN ? "N" : "T") + ","
+    prof.finish(std::to_string(M) + "," + std::to_string(N) + "," + std::to_string(K * G) + "," + std::to_string(p.batches) + "," + (aMN ? "T" : "N") + (bMN ? "N" : "T") + ","
                 + std::to_string(BN) + "," + std::to_string(splits) + "," + std::to_string(p.beta));
   return true;
 }
@@ -1349,6 +1413,45 @@ void runGemm(GemmHandle h, const GemmProblem& problem) {
 }
 
 }  // namespace
+
+// C = beta C + sum_g A_g B_g^T in one launch (K-grouped tcgen05 product) when the tf32 path can
+// take it, otherwise as the chain of accumulating products it replaces.
+void ProdGroupedNT(GemmHandle h, Tensor C, const std::vector<Tensor>& As, const std::vector<Tensor>& Bs, float beta) {
+  ABORT_IF(As.empty() || As.size() != Bs.size(), "ProdGroupedNT: need matching operand lists");
+  if(As.size() > 1 && As.size() <= 3 && h->mode == GemmMode::TF32) {
+    GemmProblem p;
+    p.C = C;
+    p.A = As[0];
+    p.B = Bs[0];
+    p.bias = nullptr;
+    p.colsA = p.A->shape().back();
+    p.rowsA = p.A->shape().elements() / p.colsA;
+    p.colsB = p.B->shape().back();
+    p.rowsB = p.B->shape().elements() / p.colsB;
+    p.batches = 1;
+    p.strideA = p.strideB = 0;
+    p.transA = false;
+    p.transB = true;
+    p.beta = beta;
+    p.alpha = 1.f;
+    p.moreA.assign(As.begin() + 1, As.end());
+    p.moreB.assign(Bs.begin() + 1, Bs.end());
+    device::setDevice(C->getDevice());
+    ABORT_IF(p.colsA != p.colsB, "matrix product requires dimensions to match", p.colsA, p.colsB);
+    ABORT_IF((long)C->size() != (long)p.rowsA * p.rowsB, "ProdGroupedNT: output tensor has the wrong size");
+    const bool wasLazy = C->takeLazyZero();
+    if(wasLazy)
+      p.beta = 0.f;
+    if(p.rowsA == 0 || p.rowsB == 0)
+      return;
+    if(runTf32(h, p))
+      return;
+    if(wasLazy)
+      beta = 0.f;  // the mark is consumed: the first product of the chain assigns
+  }
+  for(size_t g = 0; g < As.size(); ++g)
+    Prod(h, C, As[g], Bs[g], false, true, g == 0 ? beta : 1.f, 1.f);
+}
 
 void Prod(GemmHandle h, Tensor C, const Tensor A, const Tensor B, bool transA, bool transB, float beta, float scalar) {
   GemmProblem p;

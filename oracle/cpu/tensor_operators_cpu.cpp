@@ -380,6 +380,12 @@ void Prod(GemmHandle, Tensor C, const Tensor A, const Tensor B, bool transA, boo
   gemmRaw(C->data(), A->data(), B->data(), rowsA, colsA, rowsB, colsB, transA, transB, beta, scalar, true);
 }
 
+// CPU statement of the K-grouped product: the chain of accumulating products it stands for
+void ProdGroupedNT(GemmHandle h, Tensor C, const std::vector<Tensor>& As, const std::vector<Tensor>& Bs, float beta) {
+  for(size_t g = 0; g < As.size(); ++g)
+    Prod(h, C, As[g], Bs[g], false, true, g == 0 ? beta : 1.f, 1.f);
+}
+
 void ProdAffine(GemmHandle h, Tensor C, const Tensor A, const Tensor B, const Tensor bias) {
   // reference AffineNodeOp::forwardOps (node_operators_binary.h:172-186): Prod, then Add(_1, val, bias)
   using namespace functional;
