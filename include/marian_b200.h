@@ -73,6 +73,11 @@ int mrn_gemm_debug_stamps(void* device_buffer);
 /* Prod / ProdBatched: tensor_operators.h:295-311, .cu:543-654 */
 int mrn_prod(void* gemm, mrn_tensor C, mrn_tensor A, mrn_tensor B, int transA, int transB, float beta, float scalar);
 int mrn_prod_batched(void* gemm, mrn_tensor C, mrn_tensor A, mrn_tensor B, int transA, int transB, float beta, float scalar);
+/* C = beta C + sum_g A_g B_g^T (n <= 3 pairs of identical shapes run as ONE K-grouped tensor-core launch in
+ * tf32 mode, otherwise as the chain of accumulating products).  Replaces the chain of Prod(..., beta = 1)
+ * calls the reference issues when several projections share their input (AffineNodeOp::backwardOps,
+ * src/graph/node_operators_binary.h:197-214, once per q/k/v projection of Transformer::MultiHead). */
+int mrn_prod_grouped_nt(void* gemm, mrn_tensor C, const mrn_tensor* As, const mrn_tensor* Bs, int n, float beta);
 /* AffineNodeOp forward (Prod + Add(_1, val, bias)): node_operators_binary.h:172-186 */
 int mrn_prod_affine(void* gemm, mrn_tensor C, mrn_tensor A, mrn_tensor B, mrn_tensor bias);
 

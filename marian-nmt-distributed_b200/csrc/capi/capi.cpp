@@ -134,6 +134,12 @@ int mrn_prod_batched(void* g, mrn_tensor C, mrn_tensor A, mrn_tensor B, int tA, 
     ProdBatched((GemmHandle)g, wrap(C), wrap(A), wrap(B), tA, tB, beta, scalar);
   });
 }
+int mrn_prod_grouped_nt(void* g, mrn_tensor C, const mrn_tensor* As, const mrn_tensor* Bs, int n, float beta) {
+  return guarded([&] {
+    gemmInvalidateCache((GemmHandle)g);
+    ProdGroupedNT((GemmHandle)g, wrap(C), wrapAll(As, n), wrapAll(Bs, n), beta);
+  });
+}
 int mrn_prod_affine(void* g, mrn_tensor C, mrn_tensor A, mrn_tensor B, mrn_tensor bias) {
   return guarded([&] {
     gemmInvalidateCache((GemmHandle)g);

@@ -68,6 +68,35 @@ def test_prod(cuda, oracle, mode, sa, sb, tA, tB, beta, alpha):
         close(run(oracle, 0), exp, 1e-5, "oracle vs float64")
 
 
+@pytest.mark.parametrize("mode", [0, 3])
+@pytest.mark.parametrize("M,N,K,G", [
+    (3200, 512, 512, 3),   # dX of the q/k/v projections (config B): one K-grouped launch in mode 3
+    (3200, 512, 512, 2),   # key/value pair of a cross-attention block
+    (300, 72, 96, 3),      # ragged M / N, whole k-blocks
+    (129, 64, 40, 2),      # K not a multiple of the k-block: falls back to the chain of products
+    (64, 64, 64, 1),
+])
+@pytest.mark.parametrize("beta", [0.0, 1.0])
+def test_prod_grouped_nt(cuda, oracle, mode, M, N, K, G, beta):
+    As = [rnd(10 + g, M, K) for g in range(G)]
+    Bs = [rnd(20 + g, N, K) for g in range(G)]
+    C0 = rnd(3, M, N)
+    exp = beta * C0.astype(np.float64) + sum(a.astype(np.float64) @ b.astype(np.float64).T for a, b in zip(As, Bs))
+
+    def run(lib):
+        g = lib.gemm(mode)
+        c = lib.array(C0)
+        a = [lib.array(x) for x in As]
+        b = [lib.array(x) for x in Bs]
+        lib.call("mrn_prod_grouped_nt", g.h, c.t(), lib.tensor_list([x.t() for x in a]), lib.tensor_list([x.t() for x in b]), G, beta)
+        lib.synchronize()
+        return c.numpy()
+
+    close(run(cuda), exp, TOL[mode], "cuda vs float64")
+    if mode == 0:
+        close(run(oracle), exp, 1e-5, "oracle vs float64")
+
+
 @pytest.mark.parametrize("mode", [0, 1, 2, 3])
 @pytest.mark.parametrize("sa,sb,tA,tB", [
     ((64, 8, 50, 64), (64, 8, 50, 64), False, True),    # Q K^T  (config B)
