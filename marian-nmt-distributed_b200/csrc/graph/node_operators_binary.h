@@ -5,6 +5,7 @@
 #include "graph/backend.h"
 #include "graph/expression_graph.h"
 #include "graph/node.h"
+#include "graph/node_operators_unary.h"
 #include "kernels/tensor_operators.h"
 
 namespace marian {
@@ -117,8 +118,24 @@ struct AffineNodeOp : public NaryNodeOp {
   // marked so that their own input-gradient closure does nothing.
   bool inputGradDone_{false};
   void fuseBackward(const std::vector<Expr>& upcoming) {
+    if(inputGradDone_ || !child(0)->trainable())
+      return;
+    // affine AFTER swish (second layer of the feed-forward block), the swish node runs next and nothing
+    // else has contributed to its adjoint: dH (+)= (adj W^T) o swish'(H) comes out of the product's
+    // epilogue; the swish node's adjoint and its element-wise backward kernel are skipped.
+    if(!upcoming.empty() && upcoming[0] == child(0)) {
+      auto* sw = dynamic_cast<SwishNodeOp*>(child(0).get());
+      if(sw && !sw->backwardDone_ && sw->child(0)->trainable() && sw->grad() && sw->grad()->isLazyZero()
+         && ProdSwishGradFusable(getBackend()->getGemmHandle(), sw->child(0)->val(), adj_, child(1)->val(), sw->child(0)->val())) {
+        sw->child(0)->set_zero_adjoint();
+        ProdSwishGradNT(getBackend()->getGemmHandle(), sw->child(0)->grad(), adj_, child(1)->val(), sw->child(0)->val(), 1.0);
+        sw->backwardDone_ = true;
+        inputGradDone_ = true;
+        return;
+      }
+    }
     static const bool enabled = std::getenv("MRN_NO_GROUPED_DX") == nullptr;
-    if(!enabled || inputGradDone_ || !child(0)->trainable())
+    if(!enabled)
       return;
     std::vector<AffineNodeOp*> group{this};
     for(auto& u : upcoming) {

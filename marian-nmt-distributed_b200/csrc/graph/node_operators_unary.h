@@ -140,10 +140,13 @@ struct SwishNodeOp : public UnaryNodeOp {
     using namespace functional;
     return {NodeOp(Element(_1 = _2 * logit(_2), val_, child(0)->val()))};
   }
+  // set by the consumer that delivered the gradient of the pre-activation itself
+  // (AffineNodeOp::fuseBackward: swish' applied in the epilogue of its input-gradient product)
+  bool backwardDone_{false};
   NodeOps backwardOps() {
     using namespace functional;
     // dJ/dx += dJ/df * (f(x) + sigma(x) * (1 - f(x)))
-    return {NodeOp(Add(_1 * (_3 + logit(_2) * (1.f - _3)), child(0)->grad(), adj_, child(0)->val(), val_))};
+    return {NodeOp(if(!backwardDone_) Add(_1 * (_3 + logit(_2) * (1.f - _3)), child(0)->grad(), adj_, child(0)->val(), val_))};
   }
   const std::string type() { return "swish"; }
 };

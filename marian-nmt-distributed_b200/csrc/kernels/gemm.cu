@@ -611,12 +611,13 @@ struct TcArgs {
   size_t strideC;
   float alpha, beta;
   int atomicOut;  // combine with red.add (split-K)
+  const float* gate;  // GATE kernels: pre-activation h, same layout as C; the product is scaled by swish'(h)
   unsigned long long* stamps;  // tuning aid: per-CTA %globaltimer stamps (5 per CTA), or null
   unsigned long long* spanMin;  // profiling: per-launch min(start) / max(end) over the CTAs, or null
   unsigned long long* spanMax;
 };
 
-template <int BN>
+template <int BN, bool GATE = false>
 __device__ __forceinline__ void epilogueTile(const TcArgs& a, uint32_t tmemBase, uint64_t* tmemFullBar, float* stage, int warp, int lane, int m0, int n0, int batch, int split);
 
 template <int BN, int STAGES>
@@ -799,10 +800,21 @@ struct TfSmem {
 // beta != 0 (gradient accumulation): the old C values of a 32-column block are requested BEFORE
 // the accumulator is waited for / read back, so their latency hides behind the main loop's tail
 // and the TMEM read of the previous block.
-template <int BN>
+// d swish(h) / dh = s (1 + h (1 - s)), s = sigmoid(h); ex2.approx / rcp.approx like the element-wise functor
+__device__ __forceinline__ float swishGrad(float h) {
+  float z = __expf(-fabsf(h));
+  float r = __fdividef(1.f, 1.f + z);
+  float sg = h > 0.f ? r : z * r;
+  return sg * (1.f + h * (1.f - sg));
+}
+
+// GATE: C = beta C + (alpha acc + bias) o swish'(gate) - the backward pass of "affine after swish"
+// (dH = (dY W^T) o swish'(H)) without the intermediate adjoint and its element-wise kernel.
+template <int BN, bool GATE>
 __device__ __forceinline__ void epilogueTile(const TcArgs& a, uint32_t tmemBase, uint64_t* tmemFullBar, float* stage, int warp, int lane, int m0, int n0, int batch, int split) {
   const int q = warp & 3;  // TMEM lane quarter this warp may access
   float* Cb = a.C + (size_t)batch * a.strideC;
+  const float* Gb = GATE ? a.gate + (size_t)batch * a.strideC : nullptr;
   const bool addBias = a.bias != nullptr && split == 0;
   const int rowBase = m0 + q * 32;
   const int sub = lane >> 3;      // row within a group of 4
@@ -821,7 +833,19 @@ __device__ __forceinline__ void epilogueTile(const TcArgs& a, uint32_t tmemBase,
     }
   };
 
+  float4 gatev[GATE ? 8 : 1];
+  auto prefetchGate = [&](int col0) {
+    if(!GATE || col0 >= a.N || rowBase >= a.M || !isVec(col0) || (((uintptr_t)(Gb + col0)) & 15) != 0)
+      return;
+#pragma unroll
+    for(int i = 0; i < (GATE ? 8 : 1); ++i) {
+      int grow = rowBase + i * 4 + sub;
+      gatev[i] = grow < a.M ? *reinterpret_cast<const float4*>(Gb + (size_t)grow * a.ldc + col0 + cq) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+
   prefetchOld(n0);
+  prefetchGate(n0);
   mbarWait(tmemFullBar, 0);
   tcgenFenceAfter();
 #pragma unroll 1
@@ -849,7 +873,7 @@ __device__ __forceinline__ void epilogueTile(const TcArgs& a, uint32_t tmemBase,
     }
     __syncwarp();
     const int ncols = min(32, a.N - col0);
-    if(isVec(col0)) {
+    if(isVec(col0) && (!GATE || (((uintptr_t)(Gb + col0)) & 15) == 0)) {
       float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
       if(addBias)
         bq = *reinterpret_cast<const float4*>(a.bias + col0 + cq);
@@ -862,6 +886,13 @@ __device__ __forceinline__ void epilogueTile(const TcArgs& a, uint32_t tmemBase,
         v.y = a.alpha * acc.y + bq.y;
         v.z = a.alpha * acc.z + bq.z;
         v.w = a.alpha * acc.w + bq.w;
+        if(GATE) {
+          const float4 gv = gatev[GATE ? i : 0];
+          v.x *= swishGrad(gv.x);
+          v.y *= swishGrad(gv.y);
+          v.z *= swishGrad(gv.z);
+          v.w *= swishGrad(gv.w);
+        }
         if(readOld) {
           v.x += a.beta * oldv[i].x;
           v.y += a.beta * oldv[i].y;
@@ -871,6 +902,7 @@ __device__ __forceinline__ void epilogueTile(const TcArgs& a, uint32_t tmemBase,
         outv[i] = v;
       }
       prefetchOld(col0 + 32);  // next block's old values travel while this one is stored
+      prefetchGate(col0 + 32);
 #pragma unroll
       for(int i = 0; i < 8; ++i) {
         int grow = rowBase + i * 4 + sub;
@@ -891,6 +923,8 @@ __device__ __forceinline__ void epilogueTile(const TcArgs& a, uint32_t tmemBase,
         int rmax = min(32, a.M - rowBase);
         for(int rloc = 0; rloc < rmax; ++rloc) {
           float v = a.alpha * stage[rloc * kStagePitch + lane] + bv;
+          if(GATE)
+            v *= swishGrad(Gb[(size_t)(rowBase + rloc) * a.ldc + col0 + lane]);
           float* cp = Cb + (size_t)(rowBase + rloc) * a.ldc + col0 + lane;
           if(a.atomicOut) {
             atomicAdd(cp, v);
@@ -902,6 +936,7 @@ __device__ __forceinline__ void epilogueTile(const TcArgs& a, uint32_t tmemBase,
         }
       }
       prefetchOld(col0 + 32);
+      prefetchGate(col0 + 32);
     }
     __syncwarp();  // staging buffer is reused by the next 32-column block
   }
@@ -916,8 +951,8 @@ struct alignas(64) TfMaps {
   CUtensorMap b[G];
 };
 
-template <int BN, int STAGES, bool A_MN, bool B_MN, int G = 1>
-__global__ void __launch_bounds__(192) gGemmTf32(const __grid_constant__ TfMaps<G> tm, TcArgs a) {
+template <int BN, int STAGES, bool A_MN, bool B_MN, int G = 1, bool GATE = false>
+__global__ void __launch_bounds__(192, GATE ? 2 : 1) gGemmTf32(const __grid_constant__ TfMaps<G> tm, TcArgs a) {
   typedef TfSmem<BN, STAGES> L;
   extern __shared__ uint8_t smemRaw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smemRaw + 1023) & ~(uintptr_t)1023);
@@ -1037,7 +1072,7 @@ __global__ void __launch_bounds__(192) gGemmTf32(const __grid_constant__ TfMaps<
       mbarWait(tmemFullBar, 0);
       stamp[3] = now();  // accumulator complete
     }
-    epilogueTile<BN>(a, tmemBase, tmemFullBar, stage, warp, lane, m0, n0, batch, split);
+    epilogueTile<BN, GATE>(a, tmemBase, tmemFullBar, stage, warp, lane, m0, n0, batch, split);
   }
 
   tcgenFenceBefore();
@@ -1092,6 +1127,7 @@ struct GemmProblem {
   bool transA, transB;
   float beta, alpha;
   std::vector<Tensor> moreA, moreB;  // K-grouped product: further (A_g, B_g) pairs of the same shapes
+  Tensor gate;                       // swish'-gated epilogue: pre-activation with the shape of C
 };
 
 void runSimt(const GemmProblem& p) {
@@ -1211,16 +1247,27 @@ CUtensorMap makeTensorMapF32(GemmHandle h, const float* base, uint64_t inner, ui
   return map;
 }
 
-template <int BN, int STAGES, bool A_MN, bool B_MN, int G>
+template <int BN, int STAGES, bool A_MN, bool B_MN, int G, bool GATE = false>
 void launchTf32Maps(const TfMaps<G>& tm, const TcArgs& a, int batches) {
   typedef TfSmem<BN, STAGES> L;
   static bool configured = false;
   if(!configured) {
-    CUDA_CHECK(cudaFuncSetAttribute(gGemmTf32<BN, STAGES, A_MN, B_MN, G>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    CUDA_CHECK(cudaFuncSetAttribute(gGemmTf32<BN, STAGES, A_MN, B_MN, G, GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
   dim3 grid((a.M + BLOCK_M - 1) / BLOCK_M, (a.N + BN - 1) / BN, batches * a.splits);
-  launchPdl(gGemmTf32<BN, STAGES, A_MN, B_MN, G>, grid, dim3(192), (size_t)L::TOTAL, cudaStreamOfEngine(), tm, a);
+  launchPdl(gGemmTf32<BN, STAGES, A_MN, B_MN, G, GATE>, grid, dim3(192), (size_t)L::TOTAL, cudaStreamOfEngine(), tm, a);
+}
+
+// swish'-gated epilogue (both operands K-major)
+inline void launchTf32Gated(int BN, const CUtensorMap& tmA, const CUtensorMap& tmB, const TcArgs& a) {
+  TfMaps<1> tm;
+  tm.a[0] = tmA;
+  tm.b[0] = tmB;
+  if(BN == 128)
+    launchTf32Maps<128, 3, false, false, 1, true>(tm, a, 1);
+  else
+    launchTf32Maps<64, 4, false, false, 1, true>(tm, a, 1);
 }
 
 template <int BN, int STAGES, bool A_MN, bool B_MN>
@@ -1272,6 +1319,8 @@ bool runTf32(GemmHandle h, const GemmProblem& p) {
       if(p.moreA[g]->shape() != p.A->shape() || p.moreB[g]->shape() != p.B->shape() || !tmaUsable(p.moreA[g]->data(), p.colsA, 0) || !tmaUsable(p.moreB[g]->data(), p.colsB, 0))
         return false;
   }
+  if(p.gate && (aMN || bMN || batched || G > 1))
+    return false;
   const int kGroup = (K + TF_BLOCK_K - 1) / TF_BLOCK_K;  // k-blocks of one (A, B) pair
 
   // Tile width and split-K are picked together by a small cost model calibrated on this GPU
@@ -1330,6 +1379,7 @@ bool runTf32(GemmHandle h, const GemmProblem& p) {
   a.ldc = N;
   a.kBlocks = kBlocksAll;
   a.kBlocksGroup = kGroup;
+  a.gate = p.gate ? p.gate->data() : nullptr;
   a.stamps = g_stampBuffer;  // null unless gemmDebugStamps() armed it
   a.rowsPerBatchA = (batched && p.strideA) ? 1 : 0;  // batched-operand flags for the producer
   a.rowsPerBatchB = (batched && p.strideB) ? 1 : 0;
@@ -1356,7 +1406,9 @@ bool runTf32(GemmHandle h, const GemmProblem& p) {
   ProfileScope prof(2.0 * M * N * K * G * p.batches);
   a.spanMin = prof.spanMin;
   a.spanMax = prof.spanMax;
-  if(G > 1) {
+  if(p.gate) {
+    launchTf32Gated(BN, tmA, tmB, a);
+  } else if(G > 1) {
     TfMaps<3> tm3;
     tm3.a[0] = tmA;
     tm3.b[0] = tmB;
@@ -1451,6 +1503,40 @@ void ProdGroupedNT(GemmHandle h, Tensor C, const std::vector<Tensor>& As, const 
   }
   for(size_t g = 0; g < As.size(); ++g)
     Prod(h, C, As[g], Bs[g], false, true, g == 0 ? beta : 1.f, 1.f);
+}
+
+// dH = beta dH + (A B^T) o swish'(H): input gradient of an affine layer whose input is swish(H), written
+// straight into the adjoint of H.  Only the tf32 tensor-core path implements it.
+bool ProdSwishGradFusable(GemmHandle h, const Tensor C, const Tensor A, const Tensor B, const Tensor H) {
+  if(h->mode != GemmMode::TF32 || std::getenv("MRN_NO_SWISH_FUSION"))
+    return false;
+  int colsA = A->shape().back(), colsB = B->shape().back();
+  return colsA == colsB && C->shape().elements() == H->shape().elements() && tmaUsable(A->data(), colsA, 0) && tmaUsable(B->data(), colsB, 0) && (((uintptr_t)H->data()) & 15) == 0
+         && (int)(B->shape().elements() / colsB) % 4 == 0;
+}
+
+void ProdSwishGradNT(GemmHandle h, Tensor C, const Tensor A, const Tensor B, const Tensor H, float beta) {
+  GemmProblem p;
+  p.C = C;
+  p.A = A;
+  p.B = B;
+  p.bias = nullptr;
+  p.gate = H;
+  p.colsA = A->shape().back();
+  p.rowsA = A->shape().elements() / p.colsA;
+  p.colsB = B->shape().back();
+  p.rowsB = B->shape().elements() / p.colsB;
+  p.batches = 1;
+  p.strideA = p.strideB = 0;
+  p.transA = false;
+  p.transB = true;
+  p.beta = beta;
+  p.alpha = 1.f;
+  device::setDevice(C->getDevice());
+  ABORT_IF((long)C->size() != (long)p.rowsA * p.rowsB || C->size() != H->size(), "ProdSwishGradNT: shapes do not match");
+  if(C->takeLazyZero())
+    p.beta = 0.f;
+  ABORT_IF(h->mode != GemmMode::TF32 || !runTf32(h, p), "ProdSwishGradNT: not supported for these operands (check ProdSwishGradFusable first)");
 }
 
 void Prod(GemmHandle h, Tensor C, const Tensor A, const Tensor B, bool transA, bool transB, float beta, float scalar) {

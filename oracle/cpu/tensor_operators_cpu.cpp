@@ -380,6 +380,14 @@ void Prod(GemmHandle, Tensor C, const Tensor A, const Tensor B, bool transA, boo
   gemmRaw(C->data(), A->data(), B->data(), rowsA, colsA, rowsB, colsB, transA, transB, beta, scalar, true);
 }
 
+// the fused swish-gradient epilogue exists on the tensor-core path only: the CPU graph keeps the two-step form
+bool ProdSwishGradFusable(GemmHandle, const Tensor, const Tensor, const Tensor, const Tensor) {
+  return false;
+}
+void ProdSwishGradNT(GemmHandle, Tensor, const Tensor, const Tensor, const Tensor, float) {
+  ABORT("ProdSwishGradNT is not available on the CPU oracle");
+}
+
 // CPU statement of the K-grouped product: the chain of accumulating products it stands for
 void ProdGroupedNT(GemmHandle h, Tensor C, const std::vector<Tensor>& As, const std::vector<Tensor>& Bs, float beta) {
   for(size_t g = 0; g < As.size(); ++g)
