@@ -78,6 +78,11 @@ int mrn_prod_batched(void* gemm, mrn_tensor C, mrn_tensor A, mrn_tensor B, int t
  * calls the reference issues when several projections share their input (AffineNodeOp::backwardOps,
  * src/graph/node_operators_binary.h:197-214, once per q/k/v projection of Transformer::MultiHead). */
 int mrn_prod_grouped_nt(void* gemm, mrn_tensor C, const mrn_tensor* As, const mrn_tensor* Bs, int n, float beta);
+/* C = beta C + (A B^T) o swish'(H), swish'(h) = s(h) (1 + h (1 - s(h))): the input gradient of an affine layer
+ * applied to swish(H), delivered straight into the adjoint of H.  Replaces Prod(..., false, true, 1.0) of
+ * AffineNodeOp::backwardOps followed by SwishNodeOp::backwardOps (src/graph/node_operators_unary.h, the
+ * "swish" functor of src/functional/predicates.h).  tf32 mode only; returns an error otherwise. */
+int mrn_prod_swish_grad_nt(void* gemm, mrn_tensor C, mrn_tensor A, mrn_tensor B, mrn_tensor H, float beta);
 /* AffineNodeOp forward (Prod + Add(_1, val, bias)): node_operators_binary.h:172-186 */
 int mrn_prod_affine(void* gemm, mrn_tensor C, mrn_tensor A, mrn_tensor B, mrn_tensor bias);
 

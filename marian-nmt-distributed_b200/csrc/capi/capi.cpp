@@ -140,6 +140,13 @@ int mrn_prod_grouped_nt(void* g, mrn_tensor C, const mrn_tensor* As, const mrn_t
     ProdGroupedNT((GemmHandle)g, wrap(C), wrapAll(As, n), wrapAll(Bs, n), beta);
   });
 }
+int mrn_prod_swish_grad_nt(void* g, mrn_tensor C, mrn_tensor A, mrn_tensor B, mrn_tensor H, float beta) {
+  return guarded([&] {
+    gemmInvalidateCache((GemmHandle)g);
+    ABORT_IF(!ProdSwishGradFusable((GemmHandle)g, wrap(C), wrap(A), wrap(B), wrap(H)), "mrn_prod_swish_grad_nt: needs the tf32 mode and 16-byte aligned operands");
+    ProdSwishGradNT((GemmHandle)g, wrap(C), wrap(A), wrap(B), wrap(H), beta);
+  });
+}
 int mrn_prod_affine(void* g, mrn_tensor C, mrn_tensor A, mrn_tensor B, mrn_tensor bias) {
   return guarded([&] {
     gemmInvalidateCache((GemmHandle)g);

@@ -68,6 +68,27 @@ def test_prod(cuda, oracle, mode, sa, sb, tA, tB, beta, alpha):
         close(run(oracle, 0), exp, 1e-5, "oracle vs float64")
 
 
+@pytest.mark.parametrize("M,N,K", [(3200, 2048, 512), (300, 72, 96), (129, 68, 40), (64, 2048, 64)])
+@pytest.mark.parametrize("beta", [0.0, 1.0])
+def test_prod_swish_grad_nt(cuda, M, N, K, beta):
+    # dH = beta dH + (dY W^T) o swish'(H) in the epilogue of the tf32 product (feed-forward backward pass)
+    A, B, H, C0 = rnd(1, M, K), rnd(2, N, K), 2.5 * rnd(3, M, N), rnd(4, M, N)
+    h = H.astype(np.float64)
+    sg = 1.0 / (1.0 + np.exp(-h))
+    exp = beta * C0 + (A.astype(np.float64) @ B.astype(np.float64).T) * (sg * (1.0 + h * (1.0 - sg)))
+    g = cuda.gemm(3)
+    c = cuda.array(C0)
+    cuda.call("mrn_prod_swish_grad_nt", g.h, c.t(), cuda.array(A).t(), cuda.array(B).t(), cuda.array(H).t(), beta)
+    cuda.synchronize()
+    close(c.numpy(), exp, TOL[3], "gated product vs float64")
+    # and against the two-step form on the same GPU path (product, then the element-wise swish backward)
+    t = cuda.zeros((M, N))
+    cuda.call("mrn_prod", g.h, t.t(), cuda.array(A).t(), cuda.array(B).t(), 0, 1, 0.0, 1.0)
+    cuda.synchronize()
+    two = beta * C0 + t.numpy().astype(np.float64) * (sg * (1.0 + h * (1.0 - sg)))
+    close(c.numpy(), two, 2e-5, "gated product vs product + swish'")
+
+
 @pytest.mark.parametrize("mode", [0, 3])
 @pytest.mark.parametrize("M,N,K,G", [
     (3200, 512, 512, 3),   # dX of the q/k/v projections (config B): one K-grouped launch in mode 3
