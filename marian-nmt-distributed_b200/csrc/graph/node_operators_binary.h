@@ -117,6 +117,8 @@ struct AffineNodeOp : public NaryNodeOp {
   // chain of dependent accumulating products (kernels/gemm.cu ProdGroupedNT); the partners are
   // marked so that their own input-gradient closure does nothing.
   bool inputGradDone_{false};
+  bool biasGradDone_{false};  // the input-gradient product also delivered the column sums of adj (= the bias gradient)
+  bool fuseBias() { return child(2)->trainable() && ProdColumnSumsFusable(getBackend()->getGemmHandle(), adj_); }
   void fuseBackward(const std::vector<Expr>& upcoming) {
     if(inputGradDone_ || !child(0)->trainable())
       return;
@@ -128,7 +130,8 @@ struct AffineNodeOp : public NaryNodeOp {
       if(sw && !sw->backwardDone_ && sw->child(0)->trainable() && sw->grad() && sw->grad()->isLazyZero()
          && ProdSwishGradFusable(getBackend()->getGemmHandle(), sw->child(0)->val(), adj_, child(1)->val(), sw->child(0)->val())) {
         sw->child(0)->set_zero_adjoint();
-        ProdSwishGradNT(getBackend()->getGemmHandle(), sw->child(0)->grad(), adj_, child(1)->val(), sw->child(0)->val(), 1.0);
+        biasGradDone_ = fuseBias();
+        ProdSwishGradNT(getBackend()->getGemmHandle(), sw->child(0)->grad(), adj_, child(1)->val(), sw->child(0)->val(), 1.0, biasGradDone_ ? child(2)->grad() : nullptr);
         sw->backwardDone_ = true;
         inputGradDone_ = true;
         return;
@@ -146,24 +149,40 @@ struct AffineNodeOp : public NaryNodeOp {
     }
     if(group.size() < 2)
       return;
-    std::vector<Tensor> adjs, weights;
+    std::vector<Tensor> adjs, weights, biasGrads;
+    bool allBias = true;
     for(auto* a : group) {
       adjs.push_back(a->adj_);
       weights.push_back(a->child(1)->val());
+      allBias = allBias && a->fuseBias();
     }
-    ProdGroupedNT(getBackend()->getGemmHandle(), child(0)->grad(), adjs, weights, 1.0);
-    for(auto* a : group)
+    if(allBias)
+      for(auto* a : group)
+        biasGrads.push_back(a->child(2)->grad());
+    ProdGroupedNT(getBackend()->getGemmHandle(), child(0)->grad(), adjs, weights, 1.0, biasGrads);
+    for(auto* a : group) {
       a->inputGradDone_ = true;
+      a->biasGradDone_ = allBias;
+    }
   }
   NodeOps backwardOps() {
     using namespace functional;
     // dW and db hang off the backward chain: side stream when W / b are parameters
     return {NodeOp(offCriticalPath(child(0), [&] {
-              if(!inputGradDone_)
+              if(inputGradDone_)
+                return;
+              if(fuseBias()) {  // single projection: same product, bias gradient from its A tiles
+                ProdGroupedNT(getBackend()->getGemmHandle(), child(0)->grad(), {adj_}, {child(1)->val()}, 1.0, {child(2)->grad()});
+                biasGradDone_ = true;
+              } else {
                 Prod(getBackend()->getGemmHandle(), child(0)->grad(), adj_, child(1)->val(), false, true, 1.0);
+              }
             })),
             NodeOp(offCriticalPath(child(1), [&] { Prod(getBackend()->getGemmHandle(), child(1)->grad(), child(0)->val(), adj_, true, false, 1.0); })),
-            NodeOp(offCriticalPath(child(2), [&] { Add(_1, child(2)->grad(), adj_); }))};
+            NodeOp(offCriticalPath(child(2), [&] {
+              if(!biasGradDone_)
+                Add(_1, child(2)->grad(), adj_);
+            }))};
   }
   const std::string type() { return "affine"; }
 };

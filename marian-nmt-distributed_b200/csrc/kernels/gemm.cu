@@ -531,6 +531,9 @@ __device__ __forceinline__ void mbarInit(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbarExpectTx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smemAddr(bar)), "r"(bytes) : "memory");
 }
+__device__ __forceinline__ void mbarArrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smemAddr(bar)) : "memory");
+}
 __device__ __forceinline__ void mbarWait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
@@ -611,6 +614,8 @@ struct TcArgs {
   size_t strideC;
   float alpha, beta;
   int atomicOut;  // combine with red.add (split-K)
+  float* colSum[3];   // != null: column sums of the (K-major) A operand of group g are red.add-ed here (bias gradients)
+  int colSumLen;      // columns of one A operand
   const float* gate;  // GATE kernels: pre-activation h, same layout as C; the product is scaled by swish'(h)
   unsigned long long* stamps;  // tuning aid: per-CTA %globaltimer stamps (5 per CTA), or null
   unsigned long long* spanMin;  // profiling: per-launch min(start) / max(end) over the CTAs, or null
@@ -981,6 +986,10 @@ __global__ void __launch_bounds__(192, GATE ? 2 : 1) gGemmTf32(const __grid_cons
   const int split = blockIdx.z - batch * a.splits;
   const int kb0 = split * a.kBlocksPerSplit;
   const int nkb = min(a.kBlocksPerSplit, a.kBlocks - kb0);
+  // Bias gradients for free: the CTAs of the first tile column also sum the columns of every A tile
+  // they stream (A = the adjoint whose column sums are the bias gradient) with the four warps that
+  // otherwise idle until the epilogue.
+  const bool doSums = !A_MN && a.colSum[0] != nullptr && blockIdx.y == 0;
 
   if(warp == 0 && lane == 0) {
 #pragma unroll
@@ -990,7 +999,7 @@ __global__ void __launch_bounds__(192, GATE ? 2 : 1) gGemmTf32(const __grid_cons
     }
     for(int s = 0; s < STAGES; ++s) {
       mbarInit(fullBar + s, 1);
-      mbarInit(emptyBar + s, 1);
+      mbarInit(emptyBar + s, doSums ? 5 : 1);  // + the four warps that read the A tile for its column sums
     }
     mbarInit(tmemFullBar, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1072,6 +1081,33 @@ __global__ void __launch_bounds__(192, GATE ? 2 : 1) gGemmTf32(const __grid_cons
       mbarWait(tmemFullBar, 0);
       stamp[3] = now();  // accumulator complete
     }
+    if(doSums) {
+      // K-major SWIZZLE_128B tile: row R at (R / 8) * 1024 + (R % 8) * 128 bytes, its 16-byte chunk c at
+      // position c ^ (R % 8).  lane = column of the k-block, warp = 32 rows: conflict-free LDS.32.
+      const int rw = (warp - 2) * 32;
+      for(int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        mbarWait(fullBar + s, (uint32_t)(i / STAGES) & 1u);
+        const float* sa = reinterpret_cast<const float*>(smem + s * L::STAGE_BYTES);
+        float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+        for(int r = 0; r < 32; r += 2) {
+          const int R0 = rw + r, R1 = R0 + 1;
+          acc0 += sa[(R0 >> 3) * 256 + (R0 & 7) * 32 + ((((lane >> 2) ^ (R0 & 7)) << 2) | (lane & 3))];
+          acc1 += sa[(R1 >> 3) * 256 + (R1 & 7) * 32 + ((((lane >> 2) ^ (R1 & 7)) << 2) | (lane & 3))];
+        }
+        const int kAbs = kb0 + i;
+        const int grp = G == 1 ? 0 : kAbs / a.kBlocksGroup;
+        const int col = (G == 1 ? kAbs : kAbs - grp * a.kBlocksGroup) * TF_BLOCK_K + lane;
+        if(col < a.colSumLen)
+          atomicAdd(a.colSum[grp] + col, acc0 + acc1);
+        __syncwarp();
+        if(lane == 0)
+          mbarArrive(emptyBar + s);
+      }
+      // the epilogue stages its tile over stage 0: every reader must be done with it
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     epilogueTile<BN, GATE>(a, tmemBase, tmemFullBar, stage, warp, lane, m0, n0, batch, split);
   }
 
@@ -1128,6 +1164,7 @@ struct GemmProblem {
   float beta, alpha;
   std::vector<Tensor> moreA, moreB;  // K-grouped product: further (A_g, B_g) pairs of the same shapes
   Tensor gate;                       // swish'-gated epilogue: pre-activation with the shape of C
+  std::vector<Tensor> colSums;       // per (A_g): receives += column sums of A_g (bias gradient), K-major A only
 };
 
 void runSimt(const GemmProblem& p) {
@@ -1180,7 +1217,7 @@ void runTensorCore(GemmHandle h, const GemmProblem& p) {
   CUtensorMap tmA = makeTensorMap(h, pa.data, (uint64_t)pa.rowsPad * batchesA, (uint64_t)pa.Ktotal, BLOCK_M);
   CUtensorMap tmB = makeTensorMap(h, pb.data, (uint64_t)pb.rowsPad * batchesB, (uint64_t)pb.Ktotal, (uint32_t)BN);
 
-  TcArgs a;
+  TcArgs a = {};
   a.C = p.C->data();
   a.bias = p.bias ? p.bias->data() : nullptr;
   a.M = M;
@@ -1371,7 +1408,7 @@ bool runTf32(GemmHandle h, const GemmProblem& p) {
   CUtensorMap tmA = makeTensorMapF32(h, p.A->data(), (uint64_t)p.colsA, (uint64_t)p.rowsA, batchesA, (uint64_t)p.colsA, p.strideA, aMN ? TF_BLOCK_K : BLOCK_M, aMN);
   CUtensorMap tmB = makeTensorMapF32(h, p.B->data(), (uint64_t)p.colsB, (uint64_t)p.rowsB, batchesB, (uint64_t)p.colsB, p.strideB, bMN ? TF_BLOCK_K : (uint32_t)BN, bMN);
 
-  TcArgs a;
+  TcArgs a = {};
   a.C = p.C->data();
   a.bias = p.bias ? p.bias->data() : nullptr;
   a.M = M;
@@ -1380,6 +1417,15 @@ bool runTf32(GemmHandle h, const GemmProblem& p) {
   a.kBlocks = kBlocksAll;
   a.kBlocksGroup = kGroup;
   a.gate = p.gate ? p.gate->data() : nullptr;
+  a.colSum[0] = a.colSum[1] = a.colSum[2] = nullptr;
+  a.colSumLen = K;
+  if(!p.colSums.empty()) {
+    ABORT_IF(aMN || batched || (int)p.colSums.size() != G, "column sums need a K-major, unbatched A operand per group");
+    for(int g = 0; g < G; ++g) {
+      ABORT_IF((int)p.colSums[g]->size() != K, "column-sum target has the wrong length");
+      a.colSum[g] = p.colSums[g]->data();
+    }
+  }
   a.stamps = g_stampBuffer;  // null unless gemmDebugStamps() armed it
   a.rowsPerBatchA = (batched && p.strideA) ? 1 : 0;  // batched-operand flags for the producer
   a.rowsPerBatchB = (batched && p.strideB) ? 1 : 0;
@@ -1468,9 +1514,24 @@ void runGemm(GemmHandle h, const GemmProblem& problem) {
 
 // C = beta C + sum_g A_g B_g^T in one launch (K-grouped tcgen05 product) when the tf32 path can
 // take it, otherwise as the chain of accumulating products it replaces.
-void ProdGroupedNT(GemmHandle h, Tensor C, const std::vector<Tensor>& As, const std::vector<Tensor>& Bs, float beta) {
+bool ProdColumnSumsFusable(GemmHandle h, const Tensor A) {
+  static const bool enabled = std::getenv("MRN_NO_FUSE_BIAS_GRAD") == nullptr;
+  return enabled && h->mode == GemmMode::TF32 && tmaUsable(A->data(), A->shape().back(), 0);
+}
+
+namespace {
+// column sums the tensor-core path did not deliver (fallback products): the plain reduction
+void addColumnSums(const std::vector<Tensor>& As, const std::vector<Tensor>& colSums) {
+  using namespace functional;
+  for(size_t g = 0; g < colSums.size(); ++g)
+    Add(_1, colSums[g], As[g]);
+}
+}  // namespace
+
+void ProdGroupedNT(GemmHandle h, Tensor C, const std::vector<Tensor>& As, const std::vector<Tensor>& Bs, float beta, const std::vector<Tensor>& colSums) {
   ABORT_IF(As.empty() || As.size() != Bs.size(), "ProdGroupedNT: need matching operand lists");
-  if(As.size() > 1 && As.size() <= 3 && h->mode == GemmMode::TF32) {
+  ABORT_IF(!colSums.empty() && colSums.size() != As.size(), "ProdGroupedNT: one column-sum target per operand pair");
+  if(As.size() <= 3 && h->mode == GemmMode::TF32 && (As.size() > 1 || !colSums.empty())) {
     GemmProblem p;
     p.C = C;
     p.A = As[0];
@@ -1488,6 +1549,7 @@ void ProdGroupedNT(GemmHandle h, Tensor C, const std::vector<Tensor>& As, const 
     p.alpha = 1.f;
     p.moreA.assign(As.begin() + 1, As.end());
     p.moreB.assign(Bs.begin() + 1, Bs.end());
+    p.colSums = colSums;
     device::setDevice(C->getDevice());
     ABORT_IF(p.colsA != p.colsB, "matrix product requires dimensions to match", p.colsA, p.colsB);
     ABORT_IF((long)C->size() != (long)p.rowsA * p.rowsB, "ProdGroupedNT: output tensor has the wrong size");
@@ -1503,6 +1565,7 @@ void ProdGroupedNT(GemmHandle h, Tensor C, const std::vector<Tensor>& As, const 
   }
   for(size_t g = 0; g < As.size(); ++g)
     Prod(h, C, As[g], Bs[g], false, true, g == 0 ? beta : 1.f, 1.f);
+  addColumnSums(As, colSums);
 }
 
 // dH = beta dH + (A B^T) o swish'(H): input gradient of an affine layer whose input is swish(H), written
@@ -1515,13 +1578,15 @@ bool ProdSwishGradFusable(GemmHandle h, const Tensor C, const Tensor A, const Te
          && (int)(B->shape().elements() / colsB) % 4 == 0;
 }
 
-void ProdSwishGradNT(GemmHandle h, Tensor C, const Tensor A, const Tensor B, const Tensor H, float beta) {
+void ProdSwishGradNT(GemmHandle h, Tensor C, const Tensor A, const Tensor B, const Tensor H, float beta, Tensor colSum) {
   GemmProblem p;
   p.C = C;
   p.A = A;
   p.B = B;
   p.bias = nullptr;
   p.gate = H;
+  if(colSum)
+    p.colSums = {colSum};
   p.colsA = A->shape().back();
   p.rowsA = A->shape().elements() / p.colsA;
   p.colsB = B->shape().back();

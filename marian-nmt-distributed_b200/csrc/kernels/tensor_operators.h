@@ -79,10 +79,12 @@ void CrossEntropyPickBackward(Tensor out, Tensor adj, Tensor a, Tensor pick, Ten
 
 void Prod(GemmHandle handle, Tensor C, const Tensor A, const Tensor B, bool transA, bool transB, float beta = 0, float scalar = 1);
 // C = beta C + sum_g A_g B_g^T: the input gradient of several projections of one tensor, as ONE K-grouped launch
-void ProdGroupedNT(GemmHandle handle, Tensor C, const std::vector<Tensor>& As, const std::vector<Tensor>& Bs, float beta = 0);
+// colSums (optional, one per pair): colSums[g] += column sums of A_g - the bias gradients, summed from the A tiles the product streams anyway
+void ProdGroupedNT(GemmHandle handle, Tensor C, const std::vector<Tensor>& As, const std::vector<Tensor>& Bs, float beta = 0, const std::vector<Tensor>& colSums = {});
+bool ProdColumnSumsFusable(GemmHandle handle, const Tensor A);
 // C = beta C + (A B^T) o swish'(H): "affine after swish" backward in the product's epilogue (tf32 tensor-core path only)
 bool ProdSwishGradFusable(GemmHandle handle, const Tensor C, const Tensor A, const Tensor B, const Tensor H);
-void ProdSwishGradNT(GemmHandle handle, Tensor C, const Tensor A, const Tensor B, const Tensor H, float beta = 0);
+void ProdSwishGradNT(GemmHandle handle, Tensor C, const Tensor A, const Tensor B, const Tensor H, float beta = 0, Tensor colSum = nullptr);
 void ProdBatched(GemmHandle handle, Tensor C, const Tensor A, const Tensor B, bool transA, bool transB, float beta = 0, float scalar = 1);
 // Affine = Prod + bias row broadcast in the GEMM epilogue (the reference's
 // AffineNodeOp issues Prod then Add(_1, val, bias): node_operators_binary.h:172-186).

@@ -384,14 +384,20 @@ void Prod(GemmHandle, Tensor C, const Tensor A, const Tensor B, bool transA, boo
 bool ProdSwishGradFusable(GemmHandle, const Tensor, const Tensor, const Tensor, const Tensor) {
   return false;
 }
-void ProdSwishGradNT(GemmHandle, Tensor, const Tensor, const Tensor, const Tensor, float) {
+bool ProdColumnSumsFusable(GemmHandle, const Tensor) {
+  return false;
+}
+void ProdSwishGradNT(GemmHandle, Tensor, const Tensor, const Tensor, const Tensor, float, Tensor) {
   ABORT("ProdSwishGradNT is not available on the CPU oracle");
 }
 
 // CPU statement of the K-grouped product: the chain of accumulating products it stands for
-void ProdGroupedNT(GemmHandle h, Tensor C, const std::vector<Tensor>& As, const std::vector<Tensor>& Bs, float beta) {
+void ProdGroupedNT(GemmHandle h, Tensor C, const std::vector<Tensor>& As, const std::vector<Tensor>& Bs, float beta, const std::vector<Tensor>& colSums) {
   for(size_t g = 0; g < As.size(); ++g)
     Prod(h, C, As[g], Bs[g], false, true, g == 0 ? beta : 1.f, 1.f);
+  using namespace functional;
+  for(size_t g = 0; g < colSums.size(); ++g)
+    Add(_1, colSums[g], As[g]);
 }
 
 void ProdAffine(GemmHandle h, Tensor C, const Tensor A, const Tensor B, const Tensor bias) {
