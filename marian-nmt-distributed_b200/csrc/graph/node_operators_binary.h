@@ -159,6 +159,9 @@ struct AffineNodeOp : public NaryNodeOp {
     if(allBias)
       for(auto* a : group)
         biasGrads.push_back(a->child(2)->grad());
+    static const bool trace = std::getenv("MRN_PEEPHOLE_TRACE") != nullptr;
+    if(trace)
+      fprintf(stderr, "[peephole] grouped input gradient of %d projections of node %zu\n", (int)group.size(), (size_t)child(0)->getId());
     ProdGroupedNT(getBackend()->getGemmHandle(), child(0)->grad(), adjs, weights, 1.0, biasGrads);
     for(auto* a : group) {
       a->inputGradDone_ = true;
