@@ -1129,14 +1129,39 @@ static float clipFactor(float gradScale, float clipNorm, Tensor normSq) {
   return scale;
 }
 
-void ShardLock(void*, bool, int*) {
-  ABORT("the asynchronous parameter server is a CUDA feature");
+// Asynchronous parameter server (reference: training/graph_group_async.cu:16-250): CPU statement of the
+// shard protocol for ranks that live in THIS process (host memory instead of peer memory).  A master
+// block is [lock:int, steps:int | pad to 256 B | p | m | v]; the lock is the reference's per-shard mutex,
+// `steps` the shard's own Adam step counter.
+void ShardLock(void* masterBlock, bool countStep, int* stepsOut) {
+  int* hdr = reinterpret_cast<int*>(masterBlock);
+  while(__sync_val_compare_and_swap(hdr, 0, 1) != 0) {
+  }
+  __sync_synchronize();
+  if(countStep) {
+    hdr[1] += 1;
+    *stepsOut = hdr[1];
+  }
 }
-void ShardUnlock(void*) {
-  ABORT("the asynchronous parameter server is a CUDA feature");
+void ShardUnlock(void* masterBlock) {
+  __sync_synchronize();
+  __sync_lock_release(reinterpret_cast<int*>(masterBlock));
 }
-void AdamUpdateRemote(void*, size_t, const float*, const AdamArgs&, const int*, Tensor) {
-  ABORT("the asynchronous parameter server is a CUDA feature");
+void AdamUpdateRemote(void* masterBlock, size_t shardElements, const float* gradSlice, const AdamArgs& a, const int* steps, Tensor normSq) {
+  // formula of optimizers.cu:43-73, bias corrections from the shard's own step counter
+  float scale = clipFactor(a.gradScale, a.clipNorm, normSq);
+  float* p = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(masterBlock) + 256);
+  float* m = p + shardElements;
+  float* v = m + shardElements;
+  const float t = (float)*steps;
+  const float denom1 = 1.f - powf(a.beta1, t), denom2 = 1.f - powf(a.beta2, t);
+#pragma omp parallel for if(shardElements > 65536)
+  for(size_t i = 0; i < shardElements; ++i) {
+    float gi = gradSlice[i] * scale;
+    m[i] = (a.beta1 * m[i]) + ((1 - a.beta1) * gi);
+    v[i] = (a.beta2 * v[i]) + ((1 - a.beta2) * (gi * gi));
+    p[i] = p[i] - a.eta * (m[i] / denom1) / (sqrtf(v[i] / denom2) + a.eps);
+  }
 }
 void PeerBarrier(const PeerTable&, int, int, int) {
   ABORT("peer-memory exchange is a CUDA feature");
