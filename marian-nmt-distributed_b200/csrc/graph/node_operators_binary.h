@@ -120,7 +120,7 @@ struct AffineNodeOp : public NaryNodeOp {
   bool biasGradDone_{false};  // the input-gradient product also delivered the column sums of adj (= the bias gradient)
   bool fuseBias() { return child(2)->trainable() && ProdColumnSumsFusable(getBackend()->getGemmHandle(), adj_); }
   void fuseBackward(const std::vector<Expr>& upcoming) {
-    if(inputGradDone_ || !child(0)->trainable())
+    if(inputGradDone_ || !adj_ || !child(0)->trainable())
       return;
     // affine AFTER swish (second layer of the feed-forward block), the swish node runs next and nothing
     // else has contributed to its adjoint: dH (+)= (adj W^T) o swish'(H) comes out of the product's
@@ -143,7 +143,7 @@ struct AffineNodeOp : public NaryNodeOp {
     std::vector<AffineNodeOp*> group{this};
     for(auto& u : upcoming) {
       auto* a = dynamic_cast<AffineNodeOp*>(u.get());
-      if(!a || a->child(0) != child(0) || !a->trainable() || a->inputGradDone_ || a->shape() != shape() || a->child(1)->shape() != child(1)->shape())
+      if(!a || !a->adj_ || a->child(0) != child(0) || !a->trainable() || a->inputGradDone_ || a->shape() != shape() || a->child(1)->shape() != child(1)->shape())
         break;
       group.push_back(a);
     }
