@@ -35,3 +35,22 @@ def test_fused_operators_equal_reference_node_sequences(oracle):
         err = float(np.abs(a["grads"][name] - g).max())
         assert err <= 2e-5 * max(float(np.abs(g).max()), 1e-2 * gscale), (name, err)
     assert np.abs(a["params"] - b["params"]).max() <= 2.1e-4  # one Adam step of lr 1e-4: sign flips of ~0 gradients only
+
+
+def test_grouped_product_statement(oracle):
+    """mrn_prod_grouped_nt on the oracle: C = beta C + sum_g A_g B_g^T, the chain of accumulating products the
+    K-grouped tensor-core launch replaces (AffineNodeOp backward of projections that share their input)."""
+    rs = np.random.RandomState(7)
+    M, N, K = 37, 24, 40
+    for G in (1, 2, 3):
+        for beta in (0.0, 1.0):
+            As = [rs.standard_normal((M, K)).astype(np.float32) for _ in range(G)]
+            Bs = [rs.standard_normal((N, K)).astype(np.float32) for _ in range(G)]
+            C0 = rs.standard_normal((M, N)).astype(np.float32)
+            exp = beta * C0.astype(np.float64) + sum(a.astype(np.float64) @ b.astype(np.float64).T for a, b in zip(As, Bs))
+            g = oracle.gemm(0)
+            c = oracle.array(C0)
+            a = [oracle.array(x) for x in As]
+            b = [oracle.array(x) for x in Bs]
+            oracle.call("mrn_prod_grouped_nt", g.h, c.t(), oracle.tensor_list([x.t() for x in a]), oracle.tensor_list([x.t() for x in b]), G, beta)
+            assert np.abs(c.numpy() - exp).max() <= 1e-5 * np.abs(exp).max(), (G, beta)
