@@ -1077,7 +1077,7 @@ __global__ void __launch_bounds__(192, GATE ? 2 : 1) gGemmTf32(const __grid_cons
     }
   } else {
     float* stage = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * kStagePitch);
-    if(stamp && threadIdx.x == 64) {
+    if(stamp && threadIdx.x == 64 && !doSums) {  // (with column sums the readers must not stall: the stages wait for them)
       mbarWait(tmemFullBar, 0);
       stamp[3] = now();  // accumulator complete
     }
