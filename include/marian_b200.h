@@ -58,14 +58,19 @@ int mrn_memcpy_d2h(void* dst, const void* src, size_t bytes); /* blocking */
 int mrn_memset_zero(void* dst, size_t bytes);
 
 /* ---- GEMM context: replaces cublasHandle_t of Prod/ProdBatched --------- */
-/* mode: 0 = fp32 SIMT (exact), 1 = bf16 tcgen05, 2 = bf16x3 split tcgen05 */
+/* mode: 0 = fp32 SIMT (exact), 1 = packed bf16 tcgen05, 2 = bf16x3 split tcgen05 (fp32-grade, parity runs),
+ *       3 = tf32 tcgen05 straight on the fp32 tensors (TMA-direct, no packing pass),
+ *       4 = bf16 tcgen05 on bf16 shadow copies of the operands (written by the producing kernels /
+ *           the optimizer, TMA-direct for all four transpose cases; fp32 accumulate and fp32 storage) */
 int mrn_gemm_create(void** handle, int device);
 int mrn_gemm_destroy(void* handle);
 int mrn_gemm_set_mode(void* handle, int mode);
 
-/* measurement hook: enable != 0 resets and starts timing every tensor-core GEMM launch with
- * CUDA events on the engine stream; enable == 0 stops and returns total ms, algorithmic
- * flops (2MNK) and launch count.  Eager steps only (not inside a replayed graph). */
+/* measurement hook: enable != 0 resets and starts timing every tensor-core GEMM launch (CUDA event
+ * pairs on the engine stream - external event-record nodes when the step is being captured, so
+ * every replay re-stamps them - or, with MRN_GEMM_SPANS=1 in the environment, in-kernel
+ * %globaltimer spans); enable == 0 stops and returns total ms, algorithmic flops (2MNK) and the
+ * launch count of the last eager step or graph replay. */
 int mrn_gemm_profile(int enable, double* ms, double* flops, size_t* launches);
 /* tuning aid: per-CTA timestamps (5 x uint64 per CTA) of the next tf32 GEMM launches; NULL disarms */
 int mrn_gemm_debug_stamps(void* device_buffer);
@@ -158,6 +163,13 @@ int mrn_l2norm(mrn_tensor in, float* result);
  * t = 1-based step; grad_scale multiplies every gradient (1/N of a summed shard);
  * clip_norm <= 0 disables clipping. */
 int mrn_adam_step(mrn_tensor params, mrn_tensor grads, mrn_tensor mt, mrn_tensor vt, float eta, float beta1, float beta2, float eps, int t, float grad_scale, float clip_norm);
+/* Norm::clip + Sgd::updateImpl / Adagrad::updateImpl fused: optimizers/optimizers.cu:7-41
+ * (p -= eta g;   gt += g^2, p -= eta / (sqrt(gt) + eps) g), same grad_scale / clip_norm meaning. */
+int mrn_sgd_step(mrn_tensor params, mrn_tensor grads, float eta, float grad_scale, float clip_norm);
+int mrn_adagrad_step(mrn_tensor params, mrn_tensor grads, mrn_tensor gt, float eta, float eps, float grad_scale, float clip_norm);
+/* Dropout mask: kernels/dropout.cu:25-42 (Bernoulli(1 - p) keep mask scaled by 1 / (1 - p)); the VALUES
+ * come from this library's counter-based generator (the reference pins no cuRAND values). */
+int mrn_dropout(mrn_tensor mask, float drop_prob, unsigned long long seed);
 
 /* ======================================================================== */
 /* Training-step driver: ExpressionGraph + model + GraphGroup behind a handle

@@ -74,6 +74,9 @@ _SIGNATURES = {
     "mrn_shift": [_T, _T, ctypes.POINTER(_I), _I],
     "mrn_l2norm": [_T, c_float_p],
     "mrn_adam_step": [_T, _T, _T, _T, _F, _F, _F, _F, _I, _F, _F],
+    "mrn_sgd_step": [_T, _T, _F, _F, _F],
+    "mrn_adagrad_step": [_T, _T, _T, _F, _F, _F, _F],
+    "mrn_dropout": [_T, _F, ctypes.c_ulonglong],
     "mrn_trainer_create": [ctypes.POINTER(_V), ctypes.c_char_p, _I, _I, _I],
     "mrn_trainer_destroy": [_V],
     "mrn_trainer_set_batch": [_V, _I, _I, _V, _V, _I, _V, _V],

@@ -333,6 +333,42 @@ int mrn_adam_step(mrn_tensor params, mrn_tensor grads, mrn_tensor mt, mrn_tensor
   });
 }
 
+namespace {
+// clip-norm scratch of the stand-alone optimizer entry points
+struct NormScratch {
+  Ptr<TensorAllocator> alloc;
+  Tensor normSq;
+  NormScratch(Tensor grads, float clipNorm) {
+    if(clipNorm > 0) {
+      alloc = New<TensorAllocator>(device::getDevice());
+      alloc->reserveExact(256);
+      alloc->allocate(normSq, Shape{1, 1});
+      SumSquares(normSq, grads);
+    }
+  }
+  ~NormScratch() {
+    if(alloc)
+      device::synchronize();  // scratch is released on return
+  }
+};
+}  // namespace
+
+int mrn_sgd_step(mrn_tensor params, mrn_tensor grads, float eta, float grad_scale, float clip_norm) {
+  return guarded([&] {
+    NormScratch ns(wrap(grads), clip_norm);
+    SgdUpdate(wrap(params), wrap(grads), eta, grad_scale, clip_norm, ns.normSq);
+  });
+}
+int mrn_adagrad_step(mrn_tensor params, mrn_tensor grads, mrn_tensor gt, float eta, float eps, float grad_scale, float clip_norm) {
+  return guarded([&] {
+    NormScratch ns(wrap(grads), clip_norm);
+    AdagradUpdate(wrap(params), wrap(grads), wrap(gt), eta, eps, grad_scale, clip_norm, ns.normSq);
+  });
+}
+int mrn_dropout(mrn_tensor mask, float drop_prob, unsigned long long seed) {
+  return guarded([&] { Dropout(wrap(mask), drop_prob, (uint64_t)seed, nullptr); });
+}
+
 // ---------------------------------------------------------------------------
 // training-step driver
 // ---------------------------------------------------------------------------

@@ -166,9 +166,12 @@ public:
     ABORT_IF(!exchange_, "SyncGraphGroup::update needs a ShardExchange");
     computeGradients(batch);
     if(first_) {
-      // reference :46-53: all replicas start from graph 0's parameters
+      // reference :46-53: all replicas start from graph 0's parameters before any gradient is
+      // computed.  The pass above created and initialised the parameters; broadcast, then take
+      // the first gradients again at the common parameter point.
       exchange_->broadcast(flatParams()->data(), flatParams()->size());
       first_ = false;
+      computeGradients(batch);
     }
     exchange_->reduceScatter(flatGrads()->data(), shardGrads()->data(), shardSize());
     updateShard();

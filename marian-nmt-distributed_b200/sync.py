@@ -141,8 +141,13 @@ class SyncTrainer:
         self.trainer.compute_gradients()
         params, grads, shard, ns = self._arenas()
         if self.first:
-            self.exchange.broadcast(params)  # reference :46-53: replicas start from graph 0
+            # reference :46-53: replicas start from graph 0's parameters BEFORE any gradient is
+            # taken.  Parameters only exist once the tape has been built and run, so the first
+            # pass above serves as the initialisation pass: broadcast, then recompute the first
+            # gradients at the common parameter point.
+            self.exchange.broadcast(params)
             self.first = False
+            self.trainer.compute_gradients()
         if self.peer and not self._peers_mapped:
             # all ranks must agree: if any rank cannot map its peers (no P2P between the GPUs, IPC
             # disabled in the container) everybody falls back to the collective exchange - loudly

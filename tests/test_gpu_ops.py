@@ -523,3 +523,66 @@ def test_l2norm_and_adam(cuda, oracle):
         return {"norm": np.array([norm.value]), "p": p.numpy(), "m": m.numpy(), "v": v.numpy()}
 
     compare(cuda, oracle, fn, rtol=2e-5)
+
+
+def test_sgd_and_adagrad_steps(cuda, oracle):
+    """gSgd / gAdagrad (reference optimizers/optimizers.cu:7-41) with and without norm clipping:
+    CUDA vs the oracle and vs a float64 restatement of the reference's update sequence."""
+    n = 50_001 * 4
+    P, G = rnd(1, 1, n), rnd(2, 1, n, scale=0.01)
+
+    for clip in (0.0, 0.5):
+        def fn(lib):
+            p, g, gt = lib.array(P), lib.array(G), lib.zeros((1, n))
+            p2 = lib.array(P)
+            for _ in range(3):
+                lib.call("mrn_sgd_step", p.t(), g.t(), 0.05, 0.5, clip)
+                lib.call("mrn_adagrad_step", p2.t(), g.t(), gt.t(), 0.05, 1e-8, 0.5, clip)
+            lib.synchronize()
+            return {"sgd": p.numpy(), "adagrad": p2.numpy(), "gt": gt.numpy()}
+
+        compare(cuda, oracle, fn, rtol=2e-5)
+        # float64 restatement: Norm::clip(g * scale) then the plain updates
+        g = G.astype(np.float64) * 0.5
+        norm = np.sqrt((g * g).sum())
+        if clip > 0 and norm >= clip:
+            g = g * (clip / norm)
+        p, p2, gt = P.astype(np.float64), P.astype(np.float64), np.zeros_like(g)
+        for _ in range(3):
+            p = p - 0.05 * g
+            gt = gt + g * g
+            p2 = p2 - 0.05 / (np.sqrt(gt) + 1e-8) * g
+        got = fn(cuda)
+        close(got["sgd"], p, 2e-5, "sgd vs float64")
+        close(got["adagrad"], p2, 2e-5, "adagrad vs float64")
+        close(got["gt"], gt, 2e-5, "adagrad accumulator vs float64")
+
+
+@pytest.mark.parametrize("p", [0.1, 0.3, 0.5])
+def test_dropout_statistics(cuda, oracle, p):
+    """Dropout mask (reference kernels/dropout.cu:25-42): values are exactly {0, 1/(1-p)}, the keep
+    rate is 1-p within 5 sigma, E[mask] = 1, different seeds give different masks, no visible
+    correlation between neighbours.  The oracle's mask obeys the same law (the stream itself is unpinned)."""
+    n = 1 << 20
+    for lib in (cuda, oracle):
+        m = lib.zeros((1, n))
+        lib.call("mrn_dropout", m.t(), p, 1234)
+        lib.synchronize()
+        a = m.numpy().ravel()
+        scale = np.float32(1.0) / (np.float32(1.0) - np.float32(p))
+        keep = a != 0
+        assert np.all(np.isclose(a[keep], scale, rtol=1e-6)), "kept entries must equal 1/(1-p)"
+        sigma = np.sqrt(p * (1 - p) / n)
+        assert abs(keep.mean() - (1 - p)) < 5 * sigma, (keep.mean(), 1 - p)
+        assert abs(a.mean() - 1.0) < 5 * sigma * scale
+        # lag-1 and lag-32 autocorrelation of the keep indicator
+        k = keep.astype(np.float64) - keep.mean()
+        for lag in (1, 32, 1024):
+            c = float((k[:-lag] * k[lag:]).mean() / k.var())
+            assert abs(c) < 6.0 / np.sqrt(n), (lag, c)
+        m2 = lib.zeros((1, n))
+        lib.call("mrn_dropout", m2.t(), p, 1235)
+        lib.synchronize()
+        b = m2.numpy().ravel() != 0
+        agree = (b == keep).mean()
+        assert abs(agree - (p * p + (1 - p) * (1 - p))) < 6.0 / np.sqrt(n) + 1e-3, agree
