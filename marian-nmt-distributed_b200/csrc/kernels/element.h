@@ -31,6 +31,7 @@
 #include "common/shape.h"
 #include "functional/functional.h"
 #include "kernels/cuda_helpers.h"
+#include "kernels/shadow.h"
 #include "tensors/tensor.h"
 
 namespace marian {
@@ -53,7 +54,7 @@ struct RowGeom {
 // FLAT: every operand has exactly the iteration shape (one long row, g.rows == 1): no index
 // decode at all, the kernel is a pure 128-bit stream.
 template <int K, int MODE, bool VEC, class Functor, bool FLAT = false>
-__global__ void __launch_bounds__(256) gElementwise(Functor f, float* __restrict__ out, Operands<K> ops, RowGeom g, float scale) {
+__global__ void __launch_bounds__(256) gElementwise(Functor f, float* __restrict__ out, Operands<K> ops, RowGeom g, float scale, __nv_bfloat16* __restrict__ outShadow) {
   pdlEnter();
   const unsigned cpr = (unsigned)(g.cols + 3) >> 2;  // 4-element chunks per row
   const unsigned items = (unsigned)g.rows * cpr;     // < 2^31 (checked by the launchers)
@@ -115,6 +116,7 @@ __global__ void __launch_bounds__(256) gElementwise(Functor f, float* __restrict
         q = make_float4(r[0], r[1], r[2], r[3]);
       }
       *reinterpret_cast<float4*>(o) = q;
+      shadow::store4(outShadow, (size_t)row * g.cols + c, q);  // bf16 copy when `out` feeds a tensor-core product (BF16S)
     } else {
 #pragma unroll
       for(int e = 0; e < 4; ++e)
@@ -372,12 +374,14 @@ void Element(Functor functor, Tensor out, Tensors... tensors) {
   ABORT_IF(items >= (1ll << 31), "Element: more than 2^33 elements");
   int grid = gridFor((size_t)items, 256);
   auto stream = cudaStreamOfEngine();
+  // every element of `out` is (re)written: the vector kernels also leave its bf16 shadow when one is wanted
+  __nv_bfloat16* osh = vec ? shadow::produce(out) : nullptr;
   if(vec && !broadcast)
-    launchPdl(ew::gElementwise<K, 0, true, Functor, true>, dim3(grid), dim3(256), 0, stream, functor, out->data(), ops, g, 1.f);
+    launchPdl(ew::gElementwise<K, 0, true, Functor, true>, dim3(grid), dim3(256), 0, stream, functor, out->data(), ops, g, 1.f, osh);
   else if(vec)
-    launchPdl(ew::gElementwise<K, 0, true, Functor>, dim3(grid), dim3(256), 0, stream, functor, out->data(), ops, g, 1.f);
+    launchPdl(ew::gElementwise<K, 0, true, Functor>, dim3(grid), dim3(256), 0, stream, functor, out->data(), ops, g, 1.f, osh);
   else
-    launchPdl(ew::gElementwise<K, 0, false, Functor>, dim3(grid), dim3(256), 0, stream, functor, out->data(), ops, g, 1.f);
+    launchPdl(ew::gElementwise<K, 0, false, Functor>, dim3(grid), dim3(256), 0, stream, functor, out->data(), ops, g, 1.f, osh);
   CUDA_LAUNCH_CHECK();
 }
 
@@ -417,23 +421,24 @@ void Add(Functor functor, float scale, Tensor out, Tensors... tensors) {
     bool assign = out->takeLazyZero();
     if(!ew::aligned16(out->data()))
       vec = false;
+    __nv_bfloat16* const nosh = nullptr;  // an accumulating pass is not the adjoint's only writer: no shadow
     long long items = (long long)g.rows * ((g.cols + 3) / 4);
     ABORT_IF(items >= (1ll << 31), "Add: more than 2^33 elements");
     int grid = gridFor((size_t)items, 256);
     if(vec && !broadcast) {
       if(assign)
-        launchPdl(ew::gElementwise<K, 2, true, Functor, true>, dim3(grid), dim3(256), 0, stream, functor, out->data(), ops, g, scale);
+        launchPdl(ew::gElementwise<K, 2, true, Functor, true>, dim3(grid), dim3(256), 0, stream, functor, out->data(), ops, g, scale, shadow::produce(out));
       else
-        launchPdl(ew::gElementwise<K, 1, true, Functor, true>, dim3(grid), dim3(256), 0, stream, functor, out->data(), ops, g, scale);
+        launchPdl(ew::gElementwise<K, 1, true, Functor, true>, dim3(grid), dim3(256), 0, stream, functor, out->data(), ops, g, scale, nosh);
     } else if(assign) {
       if(vec)
-        launchPdl(ew::gElementwise<K, 2, true, Functor>, dim3(grid), dim3(256), 0, stream, functor, out->data(), ops, g, scale);
+        launchPdl(ew::gElementwise<K, 2, true, Functor>, dim3(grid), dim3(256), 0, stream, functor, out->data(), ops, g, scale, shadow::produce(out));
       else
-        launchPdl(ew::gElementwise<K, 2, false, Functor>, dim3(grid), dim3(256), 0, stream, functor, out->data(), ops, g, scale);
+        launchPdl(ew::gElementwise<K, 2, false, Functor>, dim3(grid), dim3(256), 0, stream, functor, out->data(), ops, g, scale, nosh);
     } else if(vec)
-      launchPdl(ew::gElementwise<K, 1, true, Functor>, dim3(grid), dim3(256), 0, stream, functor, out->data(), ops, g, scale);
+      launchPdl(ew::gElementwise<K, 1, true, Functor>, dim3(grid), dim3(256), 0, stream, functor, out->data(), ops, g, scale, nosh);
     else
-      launchPdl(ew::gElementwise<K, 1, false, Functor>, dim3(grid), dim3(256), 0, stream, functor, out->data(), ops, g, scale);
+      launchPdl(ew::gElementwise<K, 1, false, Functor>, dim3(grid), dim3(256), 0, stream, functor, out->data(), ops, g, scale, nosh);
   } else if(outS.d[0] == 1 && outS.d[1] == 1 && outS.d[2] == 1 && outS.d[3] == full.d[3] && (full.d[3] & 3) == 0 && ew::aligned16(out->memory()->data())
             && [&] {
                  for(int k = 0; k < K; ++k) {

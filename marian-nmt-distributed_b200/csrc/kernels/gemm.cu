@@ -16,8 +16,12 @@
 //           so one pass over K' = 3K accumulates hi*hi + lo*hi + hi*lo in fp32
 //           (~2^-16 relative operand error; used for the 1e-4 parity runs)
 //   FP32    tiled SIMT fp32 kernel (exact-mode fallback and debugging aid)
+//   BF16S   tcgen05.mma kind::f16 on bf16 SHADOW copies of the fp32 tensors (kernels/shadow.h):
+//           written by the producing kernels / the optimizer (or by one flat conversion pass),
+//           read by TMA in all four transpose cases like the tf32 path - half the operand bytes
+//           L2 -> shared memory and twice the MMA rate of tf32            [throughput, headline]
 //
-// The tensor-core kernel computes  C[M,N] (+)= alpha * A[M,K] B[N,K]^T (+ bias)
+// The PACKED tensor-core kernel (modes BF16 / BF16X3) computes  C[M,N] (+)= alpha * A[M,K] B[N,K]^T (+ bias)
 // with BOTH operands K-major.  The four transpose cases of the reference API,
 // the fp32 -> bf16 conversion and the hi/lo split are all handled by ONE
 // packing pass per operand (read fp32 once, write bf16 once; weights are
@@ -43,8 +47,10 @@
 #include <cstdlib>
 #include <string>
 #include <unordered_map>
+#include <unordered_set>
 
 #include "kernels/cuda_helpers.h"
+#include "kernels/shadow.h"
 #include "kernels/tensor_operators.h"
 
 namespace marian {
@@ -78,6 +84,12 @@ struct GemmContext {
     }
   };
   std::unordered_map<Key, void*, KeyHash> cache;
+
+  // BF16S: bf16 copy of the parameter arena (same element order as [stableLo, stableHi))
+  __nv_bfloat16* paramShadow{nullptr};
+  size_t paramShadowElems{0};
+  bool paramFresh{false};                         // the whole copy matches the fp32 arena
+  std::unordered_set<const void*> paramConverted;  // tensors converted one by one since the last invalidate
 
   typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
   EncodeTiledFn encodeTiled{nullptr};
@@ -116,23 +128,188 @@ void destroyGemmContext(GemmHandle h) {
     return;
   for(auto& c : h->chunks)
     device::freeDevice(c.base);
+  if(h->paramShadow)
+    device::freeDevice(h->paramShadow);
   delete h;
 }
 void setGemmMode(GemmHandle h, GemmMode m) {
   h->mode = m;
+  shadow::setEnabled(m == GemmMode::BF16S);
 }
 GemmMode getGemmMode(GemmHandle h) {
   return h->mode;
 }
+// ---- bf16 shadows of activations / adjoints: one bump arena per process (one process per GPU),
+//      rewound whenever a new tape starts; a generation counter invalidates what tensors of an
+//      older tape may still point to -------------------------------------------------------------
+namespace {
+struct ShadowPool {
+  struct Chunk {
+    uint8_t* base;
+    size_t size;
+  };
+  std::vector<Chunk> chunks;
+  size_t cur{0}, off{0};
+  uint32_t generation{1};
+  bool enabled{false};
+  void* take(size_t bytes) {
+    bytes = (bytes + 1023) & ~size_t(1023);
+    while(true) {
+      if(cur < chunks.size() && off + bytes <= chunks[cur].size) {
+        void* p = chunks[cur].base + off;
+        off += bytes;
+        return p;
+      }
+      if(cur + 1 < chunks.size()) {
+        ++cur;
+        off = 0;
+        continue;
+      }
+      size_t sz = std::max(bytes, (size_t)256 << 20);
+      Chunk c;
+      c.base = (uint8_t*)device::mallocDevice(sz);
+      c.size = sz;
+      chunks.push_back(c);
+      cur = chunks.size() - 1;
+      off = 0;
+    }
+  }
+  void rewind() {
+    cur = 0;
+    off = 0;
+    ++generation;
+  }
+};
+ShadowPool g_shadows;
+
+// fp32 -> bf16, flat; 8 elements per thread where alignment allows
+__global__ void __launch_bounds__(256) gToBf16(__nv_bfloat16* __restrict__ dst, const float* __restrict__ src, size_t n) {
+  const size_t n8 = n >> 3;
+  for(size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (size_t)gridDim.x * blockDim.x) {
+    const float4 a = reinterpret_cast<const float4*>(src)[2 * i];
+    const float4 b = reinterpret_cast<const float4*>(src)[2 * i + 1];
+    __nv_bfloat162 p0 = __floats2bfloat162_rn(a.x, a.y), p1 = __floats2bfloat162_rn(a.z, a.w);
+    __nv_bfloat162 p2 = __floats2bfloat162_rn(b.x, b.y), p3 = __floats2bfloat162_rn(b.z, b.w);
+    uint4 u;
+    u.x = *reinterpret_cast<uint32_t*>(&p0);
+    u.y = *reinterpret_cast<uint32_t*>(&p1);
+    u.z = *reinterpret_cast<uint32_t*>(&p2);
+    u.w = *reinterpret_cast<uint32_t*>(&p3);
+    reinterpret_cast<uint4*>(dst)[i] = u;
+  }
+  if(blockIdx.x == 0 && threadIdx.x < (n & 7)) {
+    const size_t i = (n8 << 3) + threadIdx.x;
+    dst[i] = __float2bfloat16_rn(src[i]);
+  }
+}
+
+// Conversion pass on the MAIN stream: a shadow converted on the side stream could be picked up by a
+// later main-stream product without any ordering.  Called from the side stream it steps back, converts,
+// and forks again (the side stream then waits for the conversion).
+void convertToBf16(__nv_bfloat16* dst, const float* src, size_t n) {
+  const bool side = device::onSide();
+  if(side)
+    device::returnFromSide();
+  ABORT_IF((((uintptr_t)src) & 15) != 0 || (((uintptr_t)dst) & 15) != 0, "bf16 conversion expects 16-byte aligned buffers");
+  gToBf16<<<gridFor((n + 7) / 8, 256), 256, 0, cudaStreamOfEngine()>>>(dst, src, n);
+  CUDA_LAUNCH_CHECK();
+  if(side)
+    device::forkSide();
+}
+}  // namespace
+
+namespace shadow {
+bool enabled() {
+  return g_shadows.enabled;
+}
+void setEnabled(bool on) {
+  g_shadows.enabled = on;
+}
+__nv_bfloat16* produce(const Tensor& t) {
+  if(!g_shadows.enabled || !t)
+    return nullptr;
+  MemoryPiece& m = *t->memory();
+  if(!m.shadowWanted || (uint8_t*)t->rawData() != m.data() || (m.size() & 15) != 0)
+    return nullptr;
+  if(!m.shadow || m.shadowGen != g_shadows.generation) {
+    m.shadow = g_shadows.take(m.size() / 2);
+    m.shadowGen = g_shadows.generation;
+  }
+  m.shadowValid = true;
+  return (__nv_bfloat16*)m.shadow;
+}
+}  // namespace shadow
+
 void gemmInvalidateCache(GemmHandle h) {
   h->cache.clear();
   h->cur = 0;
   h->off = 0;
+  h->paramConverted.clear();
+  g_shadows.rewind();
 }
 void gemmSetStableRange(GemmHandle h, const void* lo, size_t bytes) {
+  if(h->stableLo != (const uint8_t*)lo || (size_t)(h->stableHi - h->stableLo) != bytes)
+    h->paramFresh = false;
   h->stableLo = (const uint8_t*)lo;
   h->stableHi = h->stableLo + bytes;
+  if(h->mode == GemmMode::BF16S && h->paramShadowElems != bytes / sizeof(float)) {
+    if(h->paramShadow)
+      device::freeDevice(h->paramShadow);
+    h->paramShadowElems = bytes / sizeof(float);
+    h->paramShadow = (__nv_bfloat16*)device::mallocDevice(h->paramShadowElems * sizeof(__nv_bfloat16) + 1024);
+    h->paramFresh = false;
+  }
 }
+void* gemmParamShadowFor(GemmHandle h, const Tensor& t) {
+  if(h->mode != GemmMode::BF16S || !h->paramShadow || !t)
+    return nullptr;
+  const uint8_t* p = (const uint8_t*)t->rawData();
+  if(p < h->stableLo || p + t->size() * sizeof(float) > h->stableHi)
+    return nullptr;
+  return h->paramShadow + (p - h->stableLo) / sizeof(float);
+}
+void gemmParamsUpdated(GemmHandle h, bool shadowWritten) {
+  h->paramFresh = shadowWritten && h->mode == GemmMode::BF16S && h->paramShadow != nullptr;
+  h->paramConverted.clear();
+}
+void gemmPrepareStep(GemmHandle h) {
+  if(h->mode != GemmMode::BF16S || !h->paramShadow || h->paramFresh || !h->stableLo)
+    return;
+  convertToBf16(h->paramShadow, (const float*)h->stableLo, h->paramShadowElems);
+  h->paramFresh = true;
+}
+
+namespace {
+// bf16 copy of operand `t` for the BF16S product: the parameter-arena copy, the shadow its producer
+// wrote, or a conversion now (kept on the memory piece when `t` covers it, so that the forward value
+// converted here is found again by the weight-gradient product of the backward pass).
+const __nv_bfloat16* ensureShadow(GemmHandle h, const Tensor& t) {
+  const float* src = t->data();  // materialises a lazily-zero tensor
+  const uint8_t* p = (const uint8_t*)src;
+  const size_t n = t->size();
+  if(h->paramShadow && p >= h->stableLo && p + n * sizeof(float) <= h->stableHi) {
+    __nv_bfloat16* dst = h->paramShadow + (p - h->stableLo) / sizeof(float);
+    if(!h->paramFresh && !h->paramConverted.count(p)) {
+      convertToBf16(dst, src, n);
+      h->paramConverted.insert(p);
+    }
+    return dst;
+  }
+  MemoryPiece& m = *t->memory();
+  const size_t off = (size_t)(p - m.data()) / sizeof(float);
+  if(m.shadowValid && m.shadow && m.shadowGen == g_shadows.generation)
+    return (const __nv_bfloat16*)m.shadow + off;
+  const bool whole = off == 0 && n * sizeof(float) == m.size();
+  __nv_bfloat16* dst = (__nv_bfloat16*)g_shadows.take(n * sizeof(__nv_bfloat16));
+  convertToBf16(dst, src, n);
+  if(whole) {
+    m.shadow = dst;
+    m.shadowGen = g_shadows.generation;
+    m.shadowValid = true;
+  }
+  return dst;
+}
+}  // namespace
 
 // ---- optional per-launch timing of the tensor-core kernel (bench.py roofline) ----
 namespace {
@@ -617,6 +794,7 @@ struct TcArgs {
   float* colSum[3];   // != null: column sums of the (K-major) A operand of group g are red.add-ed here (bias gradients)
   int colSumLen;      // columns of one A operand
   const float* gate;  // GATE kernels: pre-activation h, same layout as C; the product is scaled by swish'(h)
+  __nv_bfloat16* shadowC;  // != null: bf16 copy of the final C values (BF16S: C is itself a product operand later)
   unsigned long long* stamps;  // tuning aid: per-CTA %globaltimer stamps (5 per CTA), or null
   unsigned long long* spanMin;  // profiling: per-launch min(start) / max(end) over the CTAs, or null
   unsigned long long* spanMax;
@@ -918,6 +1096,7 @@ __device__ __forceinline__ void epilogueTile(const TcArgs& a, uint32_t tmemBase,
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp), "f"(outv[i].x), "f"(outv[i].y), "f"(outv[i].z), "f"(outv[i].w) : "memory");
           } else {
             *reinterpret_cast<float4*>(cp) = outv[i];
+            shadow::store4(a.shadowC, (size_t)batch * a.strideC + (size_t)grow * a.ldc + col0 + cq, outv[i]);
           }
         }
       }
@@ -937,6 +1116,7 @@ __device__ __forceinline__ void epilogueTile(const TcArgs& a, uint32_t tmemBase,
             if(a.beta != 0.f)
               v += a.beta * *cp;
             *cp = v;
+            shadow::store1(a.shadowC, (size_t)batch * a.strideC + (size_t)(rowBase + rloc) * a.ldc + col0 + lane, v);
           }
         }
       }
@@ -1192,7 +1372,7 @@ void runSimt(const GemmProblem& p) {
 }
 
 void runTensorCore(GemmHandle h, const GemmProblem& p) {
-  const bool x3 = h->mode == GemmMode::BF16X3 || h->mode == GemmMode::TF32;
+  const bool x3 = h->mode == GemmMode::BF16X3 || h->mode == GemmMode::TF32;  // (BF16S falls back to plain bf16)
   int M = p.transA ? p.colsA : p.rowsA;
   int K = p.transA ? p.rowsA : p.colsA;
   int N = p.transB ? p.rowsB : p.colsB;
@@ -1486,6 +1666,385 @@ bool runTf32(GemmHandle h, const GemmProblem& p) {
   return true;
 }
 
+
+// =============================================================================
+// bf16 kernel on shadow operands (GemmMode::BF16S)
+// =============================================================================
+// Same anatomy as gGemmTf32 (TMA producer warp, single-thread MMA issuer, four epilogue warps that
+// double as column-sum readers, K-grouped and swish'-gated variants), on 2-byte operands:
+//   k-block  = 64 reduction elements = 128 bytes per operand row -> half the bytes per MAC of the
+//              tf32 path, kind::f16 MMAs (K = 16 per instruction) at twice the tf32 rate;
+//   K-major  operand (reduction dim contiguous): ONE TMA box {64 k, ROWS}, SWIZZLE_128B rows of 128 B,
+//              descriptor SBO = 1024 B (8 rows), k-step (16 bf16 = 32 B) advances the start address;
+//   MN-major operand (M / N dim contiguous: weights in the forward product, both operands of
+//              dW = X^T dY): ROWS/64 TMA boxes {64 mn, 64 k}; each box is 64 k-rows of 128 bytes,
+//              SWIZZLE_128B, i.e. 8 canonical MN-major atoms (64 mn x 8 k) stacked along k;
+//              descriptor LBO = 8192 B (next 64 mn = next box), SBO = 1024 B (next 8 k-rows),
+//              k-step (16 k-rows) = 2048 B.
+constexpr int BF_BLOCK_K = 64;
+
+template <bool MN>
+__device__ __forceinline__ uint64_t makeSmemDescBf16(uint32_t saddr) {
+  uint64_t d = (uint64_t)((saddr & 0x3FFFF) >> 4);
+  if(MN)
+    d |= (uint64_t)(8192 >> 4) << 16;  // LBO: next group of 64 mn
+  else
+    d |= (uint64_t)1 << 16;            // unused for K-major SWIZZLE_128B
+  d |= (uint64_t)(1024 >> 4) << 32;    // SBO: next 8 rows (K-major) / next 8 k-rows (MN-major)
+  d |= (uint64_t)1 << 46;              // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;              // SWIZZLE_128B
+  return d;
+}
+__host__ __device__ constexpr uint32_t makeInstrDescBf16(int M, int N, bool aMN, bool bMN) {
+  return (1u << 4)     // c_format = F32
+         | (1u << 7)   // a_format = BF16
+         | (1u << 10)  // b_format = BF16
+         | ((aMN ? 1u : 0u) << 15) | ((bMN ? 1u : 0u) << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+template <int BN, int STAGES, bool A_MN, bool B_MN, int G = 1, bool GATE = false>
+__global__ void __launch_bounds__(192, GATE ? 2 : 1) gGemmBf16(const __grid_constant__ TfMaps<G> tm, TcArgs a) {
+  typedef TfSmem<BN, STAGES> L;  // 128 bytes per operand row and stage, as in the tf32 kernel
+  extern __shared__ uint8_t smemRaw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smemRaw + 1023) & ~(uintptr_t)1023);
+  uint64_t* fullBar = (uint64_t*)(smem + L::BAR_OFFSET);
+  uint64_t* emptyBar = fullBar + STAGES;
+  uint64_t* tmemFullBar = emptyBar + STAGES;
+  uint32_t* tmemHolder = (uint32_t*)(tmemFullBar + 1);
+
+  pdlTrigger();
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  auto now = [] {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+  };
+  if(a.spanMin && threadIdx.x == 0)
+    atomicMin(a.spanMin, now());
+
+  const int m0 = blockIdx.x * BLOCK_M;
+  const int n0 = blockIdx.y * BN;
+  const int batch = blockIdx.z / a.splits;
+  const int split = blockIdx.z - batch * a.splits;
+  const int kb0 = split * a.kBlocksPerSplit;
+  const int nkb = min(a.kBlocksPerSplit, a.kBlocks - kb0);
+  const bool doSums = !A_MN && a.colSum[0] != nullptr && blockIdx.y == 0;
+
+  if(warp == 0 && lane == 0) {
+#pragma unroll
+    for(int g = 0; g < G; ++g) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm.a[g]) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm.b[g]) : "memory");
+    }
+    for(int s = 0; s < STAGES; ++s) {
+      mbarInit(fullBar + s, 1);
+      mbarInit(emptyBar + s, doSums ? 5 : 1);
+    }
+    mbarInit(tmemFullBar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if(warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smemAddr(tmemHolder)), "r"((uint32_t)BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgenFenceBefore();
+  __syncthreads();
+  tcgenFenceAfter();
+  const uint32_t tmemBase = *tmemHolder;
+  pdlWait();
+
+  if(warp == 0) {
+    if(lane == 0) {
+      // ---------------- TMA producer ----------------
+      const int batchA = a.rowsPerBatchA ? batch : 0;
+      const int batchB = a.rowsPerBatchB ? batch : 0;
+      for(int i = 0; i < nkb; ++i) {
+        int s = i % STAGES;
+        uint32_t phase = (uint32_t)(i / STAGES) & 1u;
+        mbarWait(emptyBar + s, phase ^ 1u);
+        mbarExpectTx(fullBar + s, (uint32_t)L::STAGE_BYTES);
+        uint8_t* sa = smem + s * L::STAGE_BYTES;
+        uint8_t* sb = sa + L::A_BYTES;
+        const int kAbs = kb0 + i;
+        const int grp = G == 1 ? 0 : kAbs / a.kBlocksGroup;
+        const int kc = (G == 1 ? kAbs : kAbs - grp * a.kBlocksGroup) * BF_BLOCK_K;
+        const CUtensorMap* tmA = &tm.a[grp];
+        const CUtensorMap* tmB = &tm.b[grp];
+        if(A_MN) {
+#pragma unroll
+          for(int c = 0; c < BLOCK_M / 64; ++c)
+            tmaLoad3D(tmA, fullBar + s, sa + c * 8192, m0 + 64 * c, kc, batchA);
+        } else {
+          tmaLoad3D(tmA, fullBar + s, sa, kc, m0, batchA);
+        }
+        if(B_MN) {
+#pragma unroll
+          for(int c = 0; c < BN / 64; ++c)
+            tmaLoad3D(tmB, fullBar + s, sb + c * 8192, n0 + 64 * c, kc, batchB);
+        } else {
+          tmaLoad3D(tmB, fullBar + s, sb, kc, n0, batchB);
+        }
+      }
+    }
+  } else if(warp == 1) {
+    if(lane == 0) {
+      // ---------------- MMA issuer (single thread) ----------------
+      constexpr uint32_t idesc = makeInstrDescBf16(BLOCK_M, BN, A_MN, B_MN);
+      constexpr uint32_t stepA = A_MN ? (2048 >> 4) : (32 >> 4);
+      constexpr uint32_t stepB = B_MN ? (2048 >> 4) : (32 >> 4);
+      for(int i = 0; i < nkb; ++i) {
+        int s = i % STAGES;
+        uint32_t phase = (uint32_t)(i / STAGES) & 1u;
+        mbarWait(fullBar + s, phase);
+        tcgenFenceAfter();
+        uint32_t sa = smemAddr(smem + s * L::STAGE_BYTES);
+        uint32_t sb = sa + L::A_BYTES;
+        uint64_t descA = makeSmemDescBf16<A_MN>(sa);
+        uint64_t descB = makeSmemDescBf16<B_MN>(sb);
+#pragma unroll
+        for(int k = 0; k < BF_BLOCK_K / UMMA_K; ++k)
+          umma(tmemBase, descA + (uint64_t)(k * stepA), descB + (uint64_t)(k * stepB), idesc, (uint32_t)((i | k) != 0));
+        ummaCommit(emptyBar + s);
+      }
+      ummaCommit(tmemFullBar);
+    }
+  } else {
+    float* stage = reinterpret_cast<float*>(smem) + (warp - 2) * (32 * kStagePitch);
+    if(doSums) {
+      // K-major SWIZZLE_128B tile of bf16: row R at (R / 8) * 1024 + (R % 8) * 128 bytes, its 16-byte chunk c
+      // at position c ^ (R % 8).  lane = two neighbouring columns (one 32-bit word), warp = 32 rows.
+      const int rw = (warp - 2) * 32;
+      for(int i = 0; i < nkb; ++i) {
+        const int s = i % STAGES;
+        mbarWait(fullBar + s, (uint32_t)(i / STAGES) & 1u);
+        const uint32_t* sa = reinterpret_cast<const uint32_t*>(smem + s * L::STAGE_BYTES);
+        float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+        for(int r = 0; r < 32; ++r) {
+          const int R = rw + r;
+          const uint32_t w = sa[(R >> 3) * 256 + (R & 7) * 32 + ((((lane >> 2) ^ (R & 7)) << 2) | (lane & 3))];
+          acc0 += __uint_as_float(w << 16);
+          acc1 += __uint_as_float(w & 0xffff0000u);
+        }
+        const int kAbs = kb0 + i;
+        const int grp = G == 1 ? 0 : kAbs / a.kBlocksGroup;
+        const int col = (G == 1 ? kAbs : kAbs - grp * a.kBlocksGroup) * BF_BLOCK_K + 2 * lane;
+        if(col < a.colSumLen)
+          atomicAdd(a.colSum[grp] + col, acc0);
+        if(col + 1 < a.colSumLen)
+          atomicAdd(a.colSum[grp] + col + 1, acc1);
+        __syncwarp();
+        if(lane == 0)
+          mbarArrive(emptyBar + s);
+      }
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
+    epilogueTile<BN, GATE>(a, tmemBase, tmemFullBar, stage, warp, lane, m0, n0, batch, split);
+  }
+
+  tcgenFenceBefore();
+  __syncthreads();
+  if(a.spanMax && threadIdx.x == 0)
+    atomicMax(a.spanMax, now());
+  if(warp == 1) {
+    __syncwarp();
+    tcgenFenceAfter();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "r"((uint32_t)BN));
+  }
+}
+
+// dims (innermost first): {inner, outer, batch}; box {64, boxOuter, 1}
+CUtensorMap makeTensorMapBf16(GemmHandle h, const __nv_bfloat16* base, uint64_t inner, uint64_t outer, uint64_t batches, uint64_t pitchElems, uint64_t batchStrideElems, uint32_t boxOuter) {
+  if(!h->encodeTiled) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    ABORT_IF(!fn || qres != cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled is not available from the driver");
+    h->encodeTiled = (GemmContext::EncodeTiledFn)fn;
+  }
+  CUtensorMap map;
+  cuuint64_t gdim[3] = {inner, outer, batches};
+  cuuint64_t gstride[2] = {pitchElems * sizeof(__nv_bfloat16), (batches > 1 ? batchStrideElems : pitchElems * outer) * sizeof(__nv_bfloat16)};
+  cuuint32_t box[3] = {(cuuint32_t)BF_BLOCK_K, boxOuter, 1};
+  cuuint32_t estride[3] = {1, 1, 1};
+  CUresult rc = h->encodeTiled(&map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)base, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ABORT_IF(rc != CUDA_SUCCESS, "cuTensorMapEncodeTiled (bf16) failed with code", (int)rc);
+  return map;
+}
+
+template <int BN, int STAGES, bool A_MN, bool B_MN, int G, bool GATE = false>
+void launchBf16Maps(const TfMaps<G>& tm, const TcArgs& a, int batches) {
+  typedef TfSmem<BN, STAGES> L;
+  static bool configured = false;
+  if(!configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(gGemmBf16<BN, STAGES, A_MN, B_MN, G, GATE>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  dim3 grid((a.M + BLOCK_M - 1) / BLOCK_M, (a.N + BN - 1) / BN, batches * a.splits);
+  launchPdl(gGemmBf16<BN, STAGES, A_MN, B_MN, G, GATE>, grid, dim3(192), (size_t)L::TOTAL, cudaStreamOfEngine(), tm, a);
+}
+
+template <bool A_MN, bool B_MN, int G, bool GATE = false>
+void launchBf16Tile(int BN, const TfMaps<G>& tm, const TcArgs& a, int batches) {
+  if(BN == 128)
+    launchBf16Maps<128, 3, A_MN, B_MN, G, GATE>(tm, a, batches);
+  else
+    launchBf16Maps<64, 4, A_MN, B_MN, G, GATE>(tm, a, batches);
+}
+
+// a bf16 operand (row pitch = cols elements) can be described by a tensor map
+inline bool tmaUsableBf16(const float* p, int cols, size_t batchStride) {
+  return (((uintptr_t)p) & 31) == 0 && (cols & 7) == 0 && (batchStride & 7) == 0;
+}
+
+// Returns false when an operand cannot be described by a tensor map; the caller then takes the packed path.
+bool runBf16(GemmHandle h, const GemmProblem& p) {
+  if(!tmaUsableBf16(p.A->rawData(), p.colsA, p.strideA) || !tmaUsableBf16(p.B->rawData(), p.colsB, p.strideB))
+    return false;
+  int M = p.transA ? p.colsA : p.rowsA;
+  int K = p.transA ? p.rowsA : p.colsA;
+  int N = p.transB ? p.rowsB : p.colsB;
+  bool batched = p.batches > 1;
+  const bool aMN = p.transA;   // stored [K, M]: M contiguous
+  const bool bMN = !p.transB;  // stored [K, N]: N contiguous
+  const int G = 1 + (int)p.moreA.size();
+  if(G > 1) {
+    if(aMN || bMN || batched || G > 3 || (K % BF_BLOCK_K) != 0 || p.moreB.size() != p.moreA.size())
+      return false;
+    for(int g = 0; g + 1 < G; ++g)
+      if(p.moreA[g]->shape() != p.A->shape() || p.moreB[g]->shape() != p.B->shape() || !tmaUsableBf16(p.moreA[g]->rawData(), p.colsA, 0) || !tmaUsableBf16(p.moreB[g]->rawData(), p.colsB, 0))
+        return false;
+  }
+  if(p.gate && (aMN || bMN || batched || G > 1))
+    return false;
+  const int kGroup = (K + BF_BLOCK_K - 1) / BF_BLOCK_K;
+  const int kBlocksAll = G * kGroup;
+
+  // tile width / split-K: the cost model of the tf32 path (a k-block moves the same bytes here)
+  int BN = 64, splits = 1;
+  {
+    const long mTiles = (M + BLOCK_M - 1) / BLOCK_M;
+    double best = 1e30;
+    for(int bn : {64, 128}) {
+      if(bn == 128 && N <= 64)
+        continue;
+      const long tiles = mTiles * ((N + bn - 1) / bn) * p.batches;
+      const int maxSplits = (batched || kBlocksAll < 16) ? 1 : std::min(32, kBlocksAll / 4);
+      for(int sp = 1; sp <= maxSplits; ++sp) {
+        const long ctas = tiles * sp;
+        const double waves = (double)((ctas + 2 * kNumSMs - 1) / (2 * kNumSMs));
+        const double kb = (double)((kBlocksAll + sp - 1) / sp);
+        double cta = 3.0 + kb * (bn == 128 ? 0.333 : 0.25) + (bn == 128 ? 3.0 : 1.5);
+        double cost = waves * cta;
+        if(sp > 1)
+          cost += 3.0 + 0.3 * sp + (p.beta == 1.f ? 0.0 : 3.0);
+        if(cost < best) {
+          best = cost;
+          BN = bn;
+          splits = sp;
+        }
+      }
+    }
+  }
+  if(const char* forced = std::getenv("MRN_GEMM_BN"))
+    BN = std::atoi(forced) == 128 ? 128 : 64;
+  if(const char* t = std::getenv("MRN_GEMM_TRY")) {
+    int m, n, k, bn, sp;
+    float be;
+    if(sscanf(t, "%d,%d,%d,%f,%d,%d", &m, &n, &k, &be, &bn, &sp) == 6 && m == M && n == N && k == K * G && be == p.beta && !batched) {
+      BN = bn == 128 ? 128 : 64;
+      splits = std::max(1, sp);
+    }
+  }
+  if(const char* forced = std::getenv("MRN_GEMM_SPLITS"))
+    splits = std::max(1, std::min(std::atoi(forced), kBlocksAll));
+
+  // bf16 operands: shadows written by the producers, the parameter-arena copy, or converted now
+  const __nv_bfloat16* a16 = ensureShadow(h, p.A);
+  const __nv_bfloat16* b16 = ensureShadow(h, p.B);
+  uint64_t batchesA = p.strideA ? p.batches : 1, batchesB = p.strideB ? p.batches : 1;
+  TfMaps<3> tm3;
+  tm3.a[0] = makeTensorMapBf16(h, a16, (uint64_t)p.colsA, (uint64_t)p.rowsA, batchesA, (uint64_t)p.colsA, p.strideA, aMN ? BF_BLOCK_K : BLOCK_M);
+  tm3.b[0] = makeTensorMapBf16(h, b16, (uint64_t)p.colsB, (uint64_t)p.rowsB, batchesB, (uint64_t)p.colsB, p.strideB, bMN ? BF_BLOCK_K : (uint32_t)BN);
+  for(int g = 1; g < G; ++g) {
+    tm3.a[g] = makeTensorMapBf16(h, ensureShadow(h, p.moreA[g - 1]), (uint64_t)p.colsA, (uint64_t)p.rowsA, 1, (uint64_t)p.colsA, 0, BLOCK_M);
+    tm3.b[g] = makeTensorMapBf16(h, ensureShadow(h, p.moreB[g - 1]), (uint64_t)p.colsB, (uint64_t)p.rowsB, 1, (uint64_t)p.colsB, 0, (uint32_t)BN);
+  }
+
+  TcArgs a = {};
+  a.C = p.C->data();
+  a.bias = p.bias ? p.bias->data() : nullptr;
+  a.M = M;
+  a.N = N;
+  a.ldc = N;
+  a.kBlocks = kBlocksAll;
+  a.kBlocksGroup = kGroup;
+  a.gate = p.gate ? p.gate->data() : nullptr;
+  a.colSumLen = K;
+  if(!p.colSums.empty()) {
+    ABORT_IF(aMN || batched || (int)p.colSums.size() != G, "column sums need a K-major, unbatched A operand per group");
+    for(int g = 0; g < G; ++g) {
+      ABORT_IF((int)p.colSums[g]->size() != K, "column-sum target has the wrong length");
+      a.colSum[g] = p.colSums[g]->data();
+    }
+  }
+  a.rowsPerBatchA = (batched && p.strideA) ? 1 : 0;
+  a.rowsPerBatchB = (batched && p.strideB) ? 1 : 0;
+  a.strideC = (size_t)M * N;
+  a.alpha = p.alpha;
+  a.beta = p.beta;
+  a.kBlocksPerSplit = (a.kBlocks + splits - 1) / splits;
+  splits = (a.kBlocks + a.kBlocksPerSplit - 1) / a.kBlocksPerSplit;
+  a.splits = splits;
+  a.atomicOut = splits > 1;
+  if(a.atomicOut && p.beta != 1.f) {
+    using namespace functional;
+    if(p.beta == 0.f)
+      p.C->set(0);
+    else
+      Element(_1 = p.beta * _1, p.C);
+  }
+  // C itself a later product operand (and written here in one piece): leave its bf16 copy as well
+  a.shadowC = a.atomicOut ? nullptr : shadow::produce(p.C);
+
+  ProfileScope prof(2.0 * M * N * K * G * p.batches);
+  a.spanMin = prof.spanMin;
+  a.spanMax = prof.spanMax;
+  if(p.gate) {
+    TfMaps<1> tm;
+    tm.a[0] = tm3.a[0];
+    tm.b[0] = tm3.b[0];
+    launchBf16Tile<false, false, 1, true>(BN, tm, a, 1);
+  } else if(G == 3) {
+    launchBf16Tile<false, false, 3>(BN, tm3, a, 1);
+  } else if(G == 2) {
+    TfMaps<2> tm2;
+    for(int g = 0; g < 2; ++g) {
+      tm2.a[g] = tm3.a[g];
+      tm2.b[g] = tm3.b[g];
+    }
+    launchBf16Tile<false, false, 2>(BN, tm2, a, 1);
+  } else {
+    TfMaps<1> tm;
+    tm.a[0] = tm3.a[0];
+    tm.b[0] = tm3.b[0];
+    if(aMN && bMN)
+      launchBf16Tile<true, true, 1>(BN, tm, a, p.batches);
+    else if(aMN)
+      launchBf16Tile<true, false, 1>(BN, tm, a, p.batches);
+    else if(bMN)
+      launchBf16Tile<false, true, 1>(BN, tm, a, p.batches);
+    else
+      launchBf16Tile<false, false, 1>(BN, tm, a, p.batches);
+  }
+  if(prof.on)
+    prof.finish(std::to_string(M) + "," + std::to_string(N) + "," + std::to_string(K * G) + "," + std::to_string(p.batches) + "," + (aMN ? "T" : "N") + (bMN ? "N" : "T") + ","
+                + std::to_string(BN) + "," + std::to_string(splits) + "," + std::to_string(p.beta));
+  return true;
+}
+
 void runGemm(GemmHandle h, const GemmProblem& problem) {
   GemmProblem p = problem;
   device::setDevice(p.C->getDevice());
@@ -1506,8 +2065,22 @@ void runGemm(GemmHandle h, const GemmProblem& problem) {
   else if(h->mode == GemmMode::TF32) {
     if(!runTf32(h, p))
       runTensorCore(h, p);  // operand not TMA-addressable: packed hi/lo bf16 path (at least as precise)
+  } else if(h->mode == GemmMode::BF16S) {
+    if(!runBf16(h, p))
+      runTensorCore(h, p);  // operand not TMA-addressable: packed bf16 path (same arithmetic)
   } else
     runTensorCore(h, p);
+}
+
+// TMA-direct tensor-core modes: the fused variants (K-grouped, gated, column sums) exist for both
+inline bool directMode(GemmHandle h) {
+  return h->mode == GemmMode::TF32 || h->mode == GemmMode::BF16S;
+}
+inline bool directUsable(GemmHandle h, const Tensor& t, int cols) {
+  return h->mode == GemmMode::BF16S ? tmaUsableBf16(t->rawData(), cols, 0) : tmaUsable(t->rawData(), cols, 0);
+}
+inline bool runDirect(GemmHandle h, const GemmProblem& p) {
+  return h->mode == GemmMode::BF16S ? runBf16(h, p) : runTf32(h, p);
 }
 
 }  // namespace
@@ -1516,7 +2089,7 @@ void runGemm(GemmHandle h, const GemmProblem& problem) {
 // take it, otherwise as the chain of accumulating products it replaces.
 bool ProdColumnSumsFusable(GemmHandle h, const Tensor A) {
   static const bool enabled = std::getenv("MRN_NO_FUSE_BIAS_GRAD") == nullptr;
-  return enabled && h->mode == GemmMode::TF32 && tmaUsable(A->data(), A->shape().back(), 0);
+  return enabled && directMode(h) && directUsable(h, A, A->shape().back());
 }
 
 namespace {
@@ -1531,7 +2104,7 @@ void addColumnSums(const std::vector<Tensor>& As, const std::vector<Tensor>& col
 void ProdGroupedNT(GemmHandle h, Tensor C, const std::vector<Tensor>& As, const std::vector<Tensor>& Bs, float beta, const std::vector<Tensor>& colSums) {
   ABORT_IF(As.empty() || As.size() != Bs.size(), "ProdGroupedNT: need matching operand lists");
   ABORT_IF(!colSums.empty() && colSums.size() != As.size(), "ProdGroupedNT: one column-sum target per operand pair");
-  if(As.size() <= 3 && h->mode == GemmMode::TF32 && (As.size() > 1 || !colSums.empty())) {
+  if(As.size() <= 3 && directMode(h) && (As.size() > 1 || !colSums.empty())) {
     GemmProblem p;
     p.C = C;
     p.A = As[0];
@@ -1558,7 +2131,7 @@ void ProdGroupedNT(GemmHandle h, Tensor C, const std::vector<Tensor>& As, const 
       p.beta = 0.f;
     if(p.rowsA == 0 || p.rowsB == 0)
       return;
-    if(runTf32(h, p))
+    if(runDirect(h, p))
       return;
     if(wasLazy)
       beta = 0.f;  // the mark is consumed: the first product of the chain assigns
@@ -1571,10 +2144,10 @@ void ProdGroupedNT(GemmHandle h, Tensor C, const std::vector<Tensor>& As, const 
 // dH = beta dH + (A B^T) o swish'(H): input gradient of an affine layer whose input is swish(H), written
 // straight into the adjoint of H.  Only the tf32 tensor-core path implements it.
 bool ProdSwishGradFusable(GemmHandle h, const Tensor C, const Tensor A, const Tensor B, const Tensor H) {
-  if(h->mode != GemmMode::TF32 || std::getenv("MRN_NO_SWISH_FUSION"))
+  if(!directMode(h) || std::getenv("MRN_NO_SWISH_FUSION"))
     return false;
   int colsA = A->shape().back(), colsB = B->shape().back();
-  return colsA == colsB && C->shape().elements() == H->shape().elements() && tmaUsable(A->data(), colsA, 0) && tmaUsable(B->data(), colsB, 0) && (((uintptr_t)H->data()) & 15) == 0
+  return colsA == colsB && C->shape().elements() == H->shape().elements() && directUsable(h, A, colsA) && directUsable(h, B, colsB) && (((uintptr_t)H->data()) & 15) == 0
          && (int)(B->shape().elements() / colsB) % 4 == 0;
 }
 
@@ -1601,7 +2174,7 @@ void ProdSwishGradNT(GemmHandle h, Tensor C, const Tensor A, const Tensor B, con
   ABORT_IF((long)C->size() != (long)p.rowsA * p.rowsB || C->size() != H->size(), "ProdSwishGradNT: shapes do not match");
   if(C->takeLazyZero())
     p.beta = 0.f;
-  ABORT_IF(h->mode != GemmMode::TF32 || !runTf32(h, p), "ProdSwishGradNT: not supported for these operands (check ProdSwishGradFusable first)");
+  ABORT_IF(!directMode(h) || !runDirect(h, p), "ProdSwishGradNT: not supported for these operands (check ProdSwishGradFusable first)");
 }
 
 void Prod(GemmHandle h, Tensor C, const Tensor A, const Tensor B, bool transA, bool transB, float beta, float scalar) {

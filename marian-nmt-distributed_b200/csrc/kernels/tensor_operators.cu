@@ -23,6 +23,7 @@
 #include <algorithm>
 
 #include "kernels/cuda_helpers.h"
+#include "kernels/shadow.h"
 #include "kernels/tensor_operators.h"
 
 namespace marian {
@@ -510,7 +511,7 @@ __global__ void __launch_bounds__(128) gLayerNormalizationGrad(float* __restrict
 // One warp per row; a lane keeps VPL float4 of the row in registers, so every input is read
 // from HBM exactly once and all row statistics are shuffle reductions (no __syncthreads).
 template <int VPL>
-__global__ void __launch_bounds__(256) gLNormalizationWarp(float* __restrict__ out, const float* __restrict__ in, const float* __restrict__ res, const float* __restrict__ alpha, const float* __restrict__ beta, int rows, int cols, float eps) {
+__global__ void __launch_bounds__(256) gLNormalizationWarp(float* __restrict__ out, const float* __restrict__ in, const float* __restrict__ res, const float* __restrict__ alpha, const float* __restrict__ beta, int rows, int cols, float eps, __nv_bfloat16* __restrict__ outShadow) {
   pdlEnter();
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
@@ -560,6 +561,7 @@ __global__ void __launch_bounds__(256) gLNormalizationWarp(float* __restrict__ o
         t.z = g4[i].z * ((xv[i].z - mean) / sigma) + b4[i].z;
         t.w = g4[i].w * ((xv[i].w - mean) / sigma) + b4[i].w;
         *reinterpret_cast<float4*>(so + c) = t;
+        shadow::store4(outShadow, (size_t)row * cols + c, t);  // bf16 copy for the products that consume the output
       }
     }
   }
@@ -593,7 +595,8 @@ __global__ void __launch_bounds__(32 * WARPS, 1) gLayerNormalizationGradWarp(flo
                                                                    int assignX,
                                                                    const float* __restrict__ res,
                                                                    float* __restrict__ gradRes,
-                                                                   int assignRes) {
+                                                                   int assignRes,
+                                                                   __nv_bfloat16* __restrict__ gradXShadow) {
   pdlEnter();
   __shared__ float4 red[WARPS][32 * VPL];
   const int lane = threadIdx.x & 31;
@@ -689,6 +692,7 @@ __global__ void __launch_bounds__(32 * WARPS, 1) gLayerNormalizationGradWarp(flo
           v.w += o.w;
         }
         *gx = v;
+        shadow::store4(gradXShadow, off + c, v);  // only handed in when this kernel is the adjoint's one writer
         accG[i].x += av[i].x * xh[i].x;
         accG[i].y += av[i].y * xh[i].y;
         accG[i].z += av[i].z * xh[i].z;
@@ -746,10 +750,11 @@ void LayerNormalization(Tensor out, Tensor in, Tensor gamma, Tensor beta, float 
   if(aligned && cols <= 1024) {
     int grid = std::max(1, std::min((rows + 7) / 8, kNumSMs * 4));
     auto st = cudaStreamOfEngine();
+    __nv_bfloat16* osh = shadow::produce(out);
     if(cols <= 512)
-      launchPdl(gLNormalizationWarp<4>, dim3(grid), dim3(256), 0, st, out->data(), (const float*)in->data(), rp, (const float*)gamma->data(), bp, rows, cols, eps);
+      launchPdl(gLNormalizationWarp<4>, dim3(grid), dim3(256), 0, st, out->data(), (const float*)in->data(), rp, (const float*)gamma->data(), bp, rows, cols, eps, osh);
     else
-      launchPdl(gLNormalizationWarp<8>, dim3(grid), dim3(256), 0, st, out->data(), (const float*)in->data(), rp, (const float*)gamma->data(), bp, rows, cols, eps);
+      launchPdl(gLNormalizationWarp<8>, dim3(grid), dim3(256), 0, st, out->data(), (const float*)in->data(), rp, (const float*)gamma->data(), bp, rows, cols, eps, osh);
     CUDA_LAUNCH_CHECK();
     return;
   }
@@ -774,16 +779,17 @@ void LayerNormalizationGrad(Tensor gradX, Tensor gradGamma, Tensor gradBeta, Ten
       int assignX = gradX->takeLazyZero() ? 1 : 0;
       int assignRes = (gradResidual && gradResidual->takeLazyZero()) ? 1 : 0;
       float* grp = gradResidual ? gradResidual->data() : nullptr;
+      __nv_bfloat16* gxs = assignX ? shadow::produce(gradX) : nullptr;
       // few, fat blocks: every block ends with one 128-bit reduction per 4 columns for gamma and
       // beta; same-address reductions serialise in L2, so one block per SM is the sweet spot
       if(cols <= 512) {
         int grid = std::max(1, std::min((rows + 15) / 16, kNumSMs));
         launchPdl(gLayerNormalizationGradWarp<4, 16>, dim3(grid), dim3(512), 0, st, gradX->data(), gradGamma->data(), gbp, (const float*)adj->data(), (const float*)y->data(), (const float*)x->data(),
-                  (const float*)gamma->data(), bp, rows, cols, eps, assignX, rp, grp, assignRes);
+                  (const float*)gamma->data(), bp, rows, cols, eps, assignX, rp, grp, assignRes, gxs);
       } else {
         int grid = std::max(1, std::min((rows + 15) / 16, kNumSMs));
         launchPdl(gLayerNormalizationGradWarp<8, 8>, dim3(grid), dim3(256), 0, st, gradX->data(), gradGamma->data(), gbp, (const float*)adj->data(), (const float*)y->data(), (const float*)x->data(),
-                  (const float*)gamma->data(), bp, rows, cols, eps, assignX, rp, grp, assignRes);
+                  (const float*)gamma->data(), bp, rows, cols, eps, assignX, rp, grp, assignRes, gxs);
       }
       CUDA_LAUNCH_CHECK();
       return;
@@ -1663,6 +1669,7 @@ __global__ void __launch_bounds__(256) gAdam(float* __restrict__ p, const float*
     reinterpret_cast<float4*>(p)[i] = pp;
     reinterpret_cast<float4*>(m)[i] = mm;
     reinterpret_cast<float4*>(v)[i] = vv;
+    shadow::store4((__nv_bfloat16*)a.shadow, i << 2, pp);  // bf16 copy for the tensor-core products (BF16S mode)
     // all-gather by peer stores: the owner writes the new values into every replica
     for(int r = 0; r < peers.nranks; ++r)
       if(r != peers.self)
@@ -1673,6 +1680,7 @@ __global__ void __launch_bounds__(256) gAdam(float* __restrict__ p, const float*
     m[i] = (a.beta1 * m[i]) + ((1 - a.beta1) * gi);
     v[i] = (a.beta2 * v[i]) + ((1 - a.beta2) * (gi * gi));
     p[i] = p[i] - a.eta * (m[i] / a.denom1) / (sqrtf(v[i] / a.denom2) + a.eps);
+    shadow::store1((__nv_bfloat16*)a.shadow, i, p[i]);
     for(int r = 0; r < peers.nranks; ++r)
       if(r != peers.self)
         (reinterpret_cast<float*>(peers.params.ptr[r]) + peers.offset)[i] = p[i];

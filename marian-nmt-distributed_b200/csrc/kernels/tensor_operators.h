@@ -33,6 +33,8 @@ enum class GemmMode : int {
   BF16 = 1,    // tcgen05 bf16 operands, fp32 accumulate in TMEM (throughput mode)
   BF16X3 = 2,  // tcgen05 with hi/lo bf16 split operands (3 products), ~fp32 accuracy
   TF32 = 3,    // tcgen05 kind::tf32 directly on the fp32 tensors (no packing pass; throughput mode)
+  BF16S = 4,   // tcgen05 kind::f16 on bf16 SHADOW copies of the operands, TMA-direct in all four
+               // transpose cases (kernels/shadow.h); fp32 storage and accumulation (headline mode)
 };
 struct GemmContext;
 typedef GemmContext* GemmHandle;
@@ -47,6 +49,16 @@ void gemmInvalidateCache(GemmHandle);
 // Sources inside [ptr, ptr+bytes) (the parameter arena) are packed once per
 // step: their bf16 copies survive until the next gemmInvalidateCache().
 void gemmSetStableRange(GemmHandle, const void* ptr, size_t bytes);
+// BF16S mode keeps a bf16 copy of the whole parameter arena (the stable range).
+//   gemmParamShadowFor(h, t): where an optimizer kernel should store the bf16 copy of parameter
+//       tensor / shard `t` (nullptr when the mode is off or t is not inside the arena);
+//   gemmParamsUpdated(h, shadowWritten): the parameters changed; shadowWritten = the update wrote
+//       the bf16 copy of the WHOLE arena itself;
+//   gemmPrepareStep(h): before a forward pass / graph replay: refreshes the bf16 arena copy by one
+//       flat conversion pass if it is stale.  All three are no-ops in the other modes and on the oracle.
+void* gemmParamShadowFor(GemmHandle, const Tensor& t);
+void gemmParamsUpdated(GemmHandle, bool shadowWritten);
+void gemmPrepareStep(GemmHandle);
 
 // Tuning aid (scripts/gemm_stamps.py): per-CTA %globaltimer stamps of the tf32 kernel.
 void gemmDebugStamps(unsigned long long* deviceBuffer);
@@ -156,6 +168,7 @@ struct AdamArgs {
   float denom1, denom2;  // 1 - beta1^t, 1 - beta2^t
   float gradScale;       // multiplies every gradient before use
   float clipNorm;        // <= 0: no clipping
+  void* shadow{nullptr};  // != null: bf16 copy of the updated parameters is stored here as well (BF16S mode)
 };
 // Peer-memory exchange (kernels/exchange.cu).  A PeerTable holds, per rank of the node, the
 // address at which THIS process sees that rank's buffer (own buffer: the local pointer).

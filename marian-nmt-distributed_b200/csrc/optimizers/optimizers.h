@@ -29,7 +29,15 @@ public:
   void update(Ptr<ExpressionGraph> graph, float multiplyFactor = 1.0f) {
     Tensor p = graph->params()->vals();
     Tensor g = graph->params()->grads();
+    // BF16S GEMM mode: the update kernel also refreshes the bf16 copy of the parameter arena the
+    // tensor-core products read (kernels/shadow.h); optimizers that cannot leave it stale and the
+    // next step converts the arena in one pass (gemmPrepareStep)
+    auto gemm = graph->getBackend()->getGemmHandle();
+    shadowOut_ = gemmParamShadowFor(gemm, p);
+    shadowWritten_ = false;
     update(p, g, multiplyFactor);
+    gemmParamsUpdated(gemm, shadowWritten_);
+    shadowOut_ = nullptr;
   }
 
   // gradScale multiplies every gradient element first (1/N averaging of a
@@ -79,6 +87,8 @@ protected:
   float eta_;
   float clipNorm_;
   float multiplyFactor_{1.f};
+  void* shadowOut_{nullptr};   // bf16 destination for the updated parameters (whole-arena updates only)
+  bool shadowWritten_{false};  // set by an updateImpl that honoured shadowOut_
   Ptr<TensorAllocator> scratch_;
   Tensor normSq_;
 };
@@ -155,6 +165,8 @@ private:
     a.denom2 = (float)(1 - std::pow((double)beta2_, (double)t_));
     a.gradScale = gradScale;
     a.clipNorm = clipNorm_;
+    a.shadow = shadowOut_;
+    shadowWritten_ = shadowOut_ != nullptr;
     AdamUpdate(params, grads, mt_, vt_, a, normSq, peers);
   }
 

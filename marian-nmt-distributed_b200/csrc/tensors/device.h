@@ -77,6 +77,8 @@ void destroyGraph(void* exec);
 void forkSide();
 void returnFromSide();
 void joinSide();
+// true between forkSide() and returnFromSide()/joinSide()
+bool onSide();
 
 // ---- inter-process device memory (peer-memory gradient exchange) -----------------------------
 size_t ipcHandleBytes();

@@ -234,6 +234,9 @@ void forkSide() {
 void returnFromSide() {
   tctx.onSide = false;
 }
+bool onSide() {
+  return tctx.onSide;
+}
 void joinSide() {
   tctx.onSide = false;
   if(tctx.sideDirty) {

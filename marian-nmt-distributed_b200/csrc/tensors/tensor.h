@@ -31,6 +31,14 @@ public:
   }
   // see TensorBase::data(): shared by every tensor view over this piece (reshape nodes)
   mutable bool lazyZero{false};
+  // bf16 shadow copy for the tensor-core GEMM (GemmMode::BF16S, kernels/shadow.h).  The GRAPH sets
+  // shadowWanted on values / adjoints that will be GEMM operands (and, for adjoints, have exactly one
+  // writer); the operator that writes the fp32 tensor then also writes the bf16 copy (`shadow`,
+  // same element order) and sets shadowValid; the GEMM converts itself when nobody did.
+  mutable void* shadow{nullptr};
+  mutable bool shadowWanted{false};
+  mutable bool shadowValid{false};
+  mutable uint32_t shadowGen{0};  // pool generation the buffer belongs to (stale buffers are ignored)
 
 private:
   uint8_t* data_;
@@ -60,6 +68,8 @@ public:
     }
     return (float*)memory_->data();
   }
+  // the bytes as they are: no lazy-zero materialisation (for code that is about to overwrite them)
+  float* rawData() const { return (float*)memory_->data(); }
   void setLazyZero() {
 #ifdef MRN_ORACLE_CPU
     // the CPU oracle keeps the reference's memset-then-accumulate (its operators also call

@@ -66,6 +66,7 @@ public:
   // Enqueues forward+backward on the engine stream; cost lands in pinned memory.
   void computeGradients(Ptr<data::CorpusBatch> batch, bool keepLogits = false) {
     device::setDevice((int)graph_->getDevice());
+    gemmPrepareStep(graph_->getBackend()->getGemmHandle());  // BF16S mode: bf16 copy of the parameters up to date
     auto key = batch->shapeKey();
     if(!keepLogits) {
       if(auto plan = replay_.find(key)) {
@@ -192,6 +193,7 @@ public:
     auto p = flatParams()->subtensor((int)(rank_ * shardSize_), (int)shardSize_);
     opt_->update(p, shardGrads_, 1.f, 1.f / (float)nranks_);
     gemmInvalidateCache(worker_.graph()->getBackend()->getGemmHandle());
+    gemmParamsUpdated(worker_.graph()->getBackend()->getGemmHandle(), false);  // replicas / shards changed: bf16 arena copy is stale
   }
 
   // ---- peer-memory exchange (kernels/exchange.cu): reduce-scatter + Adam + all-gather as
@@ -232,6 +234,7 @@ public:
     opt_->updateShardWithPeers(p, shardGrads_, 1.f / (float)nranks_, stores);
     PeerBarrier(peerPads_, rank_, nranks_, ++epoch_);  // every shard has landed everywhere
     gemmInvalidateCache(worker_.graph()->getBackend()->getGemmHandle());
+    gemmParamsUpdated(worker_.graph()->getBackend()->getGemmHandle(), false);  // replicas / shards changed: bf16 arena copy is stale
   }
 
   float cost() {
@@ -358,6 +361,7 @@ public:
       ShardUnlock(masters_.ptr[s]);
     }
     gemmInvalidateCache(worker_.graph()->getBackend()->getGemmHandle());
+    gemmParamsUpdated(worker_.graph()->getBackend()->getGemmHandle(), false);  // replicas / shards changed: bf16 arena copy is stale
   }
 
   void pushGradients(Tensor gradients) {

@@ -51,6 +51,7 @@ void* ipcOpen(const unsigned char*) { return nullptr; }
 void forkSide() {}
 void returnFromSide() {}
 void joinSide() {}
+bool onSide() { return false; }
 bool capturing() { return false; }
 
 bool captureSupported() { return false; }

@@ -39,6 +39,9 @@ GemmMode getGemmMode(GemmHandle h) { return h->mode; }
 void gemmDebugStamps(unsigned long long*) {}
 void gemmInvalidateCache(GemmHandle) {}
 void gemmSetStableRange(GemmHandle, const void*, size_t) {}
+void* gemmParamShadowFor(GemmHandle, const Tensor&) { return nullptr; }
+void gemmParamsUpdated(GemmHandle, bool) {}
+void gemmPrepareStep(GemmHandle) {}
 void gemmProfile(int, double* ms, double* flops, size_t* launches) {
   *ms = 0;
   *flops = 0;
