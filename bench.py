@@ -289,8 +289,9 @@ def main():
     ap.add_argument("--model", default="transformer-base", choices=["transformer-base", "transformer-big", "s2s-deep-gru"])
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--padded", action="store_true", help="sentence lengths uniform in [T/2, T] (mask path) instead of dense batches")
-    ap.add_argument("--gemm-mode", type=int, default=int(os.environ.get("MRN_BENCH_GEMM_MODE", "3")),
+    ap.add_argument("--gemm-mode", type=int, default=int(os.environ.get("MRN_BENCH_GEMM_MODE", "4")),
                     help="3 = tf32 on the fp32 tensors, 4 = bf16 operands (shadow copies), 1 = packed bf16, 2 = bf16x3, 0 = fp32 SIMT")
+    ap.add_argument("--no-graph-replay", action="store_true", help="eager tape every step (profiling aid: every kernel is an ordinary launch)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
@@ -327,6 +328,8 @@ def main():
     W = max(3, args.warmup)
     K = args.steps
     opts, BATCH, LEN, label = model_config(args.model, pkg, args.gemm_mode)
+    if args.no_graph_replay:
+        opts["graph-replay"] = "false"
     strong = args.scaling == "strong" and world > 1
     # strong scaling: every rank draws the SAME global batch and keeps split(N)[rank]
     opts["data-seed"] = 1111 if strong else 1111 + rank

@@ -31,7 +31,7 @@ def load():
     return _lib
 
 
-def transformer_base_options(vocab=32000, gemm_mode=3, **extra):
+def transformer_base_options(vocab=32000, gemm_mode=4, **extra):
     """BASELINE.json config[1]: Transformer-base (6+6, d=512, 8 heads, ffn 2048)."""
     o = {
         "type": "transformer", "dim-vocabs": [vocab, vocab], "dim-emb": 512, "enc-depth": 6, "dec-depth": 6,

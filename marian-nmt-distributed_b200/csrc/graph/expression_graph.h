@@ -409,6 +409,9 @@ public:
     }
     hashMap_[hash].push_back(node);
     node->setId(count_++);
+    if(!node->isView())  // a view hands its consumers through to the node it aliases
+      for(auto& child : node->children())
+        child->addConsumer();
 
     nodesForward_.push_back(node);
     if(!inferenceOnly_ && node->trainable()) {

@@ -21,6 +21,8 @@ size_t Node::allocate() {
   if(!val_) {
     graph()->tensor(val_, shape_);
     elements = val_->shape().elements();
+    if(wantValShadow_)
+      val_->memory()->shadowWanted = true;
   }
   return elements;
 }
@@ -53,6 +55,9 @@ void Node::set_zero_adjoint() {
       adj_->set(0);
     else
       adj_->setLazyZero();
+    // one consumer = one writer: that writer may leave the bf16 copy the backward products read
+    if(wantAdjShadow_ && consumers_ == 1)
+      adj_->memory()->shadowWanted = true;
   }
 }
 

@@ -78,6 +78,15 @@ struct Chainable {
   virtual bool concurrent() const { return false; }
   virtual bool sideProduced() const { return false; }
   virtual void setSideProduced(bool) {}
+
+  // bf16 shadows of GEMM operands (kernels/shadow.h, GemmMode::BF16S).  A product node asks its
+  // operand nodes for a bf16 copy of their VALUE and is itself marked as wanting one of its ADJOINT
+  // (the A / B operand of its two backward products).  The graph counts the consumers of every node
+  // when they are added to the tape: an adjoint shadow is only requested for nodes with exactly one
+  // consumer, i.e. one writer of the adjoint.  Views forward all three to the node they alias.
+  virtual void requestValShadow() {}
+  virtual void addConsumer() {}
+  virtual bool isView() const { return false; }
 };
 
 class Node : public Chainable<Tensor>, public std::enable_shared_from_this<Node> {
@@ -95,6 +104,9 @@ protected:
   std::string debugMessage_;
   bool concurrent_{false};      // forward pass may run on the side stream (see setConcurrent)
   bool sideProduced_{false};    // val_ was written on the side stream and not yet joined
+  bool wantValShadow_{false};   // a product reads val_: producers leave a bf16 copy (BF16S GEMM mode)
+  bool wantAdjShadow_{false};   // this node is a product: its adjoint is an operand of the backward products
+  int consumers_{0};            // nodes on the tape that have this node as a child
 
 public:
   Node(Ptr<ExpressionGraph> graph, const Shape& shape) : graph_(graph), shape_(shape) {}
@@ -168,6 +180,13 @@ public:
   virtual bool concurrent() const { return concurrent_; }
   virtual bool sideProduced() const { return sideProduced_; }
   virtual void setSideProduced(bool s) { sideProduced_ = s; }
+
+  virtual void requestValShadow() {
+    wantValShadow_ = true;
+    if(val_)
+      val_->memory()->shadowWanted = true;
+  }
+  virtual void addConsumer() { ++consumers_; }
 
   Ptr<Backend> getBackend();
 

@@ -48,7 +48,11 @@ protected:
 
 public:
   DotNodeOp(Expr a, Expr b, bool transA, bool transB, float scalar)
-      : NaryNodeOp({a, b}, detail::dotShape(a, b, transA, transB)), transA_(transA), transB_(transB), scalar_(scalar) {}
+      : NaryNodeOp({a, b}, detail::dotShape(a, b, transA, transB)), transA_(transA), transB_(transB), scalar_(scalar) {
+    a->requestValShadow();  // BF16S GEMM mode: operands and this node's adjoint as bf16 copies
+    b->requestValShadow();
+    wantAdjShadow_ = true;
+  }
 
   NodeOps forwardOps() { return {NodeOp(prod(val_, child(0)->val(), child(1)->val(), transA_, transB_, 0.f))}; }
 
@@ -99,7 +103,11 @@ public:
 // here the bias is applied in the GEMM epilogue).  Backward: dx += D W^T,
 // dW += x^T D, db += column sums of D.
 struct AffineNodeOp : public NaryNodeOp {
-  AffineNodeOp(const std::vector<Expr>& nodes) : NaryNodeOp(nodes, newShape(nodes)) {}
+  AffineNodeOp(const std::vector<Expr>& nodes) : NaryNodeOp(nodes, newShape(nodes)) {
+    nodes[0]->requestValShadow();  // BF16S GEMM mode: operands and this node's adjoint as bf16 copies
+    nodes[1]->requestValShadow();
+    wantAdjShadow_ = true;
+  }
 
   static Shape newShape(const std::vector<Expr>& nodes) {
     Shape shape1 = nodes[0]->shape();

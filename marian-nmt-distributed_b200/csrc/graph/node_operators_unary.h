@@ -488,6 +488,10 @@ public:
   void backward() {}
   void init_dependent() { reshapee_->init_dependent(); }
   void set_zero_adjoint() { reshapee_->set_zero_adjoint(); }
+  // value and adjoint alias the reshapee's: shadow requests and consumer counts belong there
+  void requestValShadow() { reshapee_->requestValShadow(); }
+  void addConsumer() { reshapee_->addConsumer(); }
+  bool isView() const { return true; }
 
   Tensor& val() {
     auto childVal = reshapee_->val();

@@ -24,6 +24,7 @@
 #include <cstdlib>
 
 #include "kernels/cuda_helpers.h"
+#include "kernels/shadow.h"
 #include "kernels/tensor_operators.h"
 
 namespace marian {
@@ -883,7 +884,8 @@ __global__ void __launch_bounds__(kAttnThreads) gAttentionBackwardMma(float* __r
 
 // Stores a 16 x dk accumulator strip (rows lo / hi of a lane) to [.., d]-pitched global memory.
 // Accumulating: all old values are loaded before the first store (one memory round trip, not 2 nto).
-__device__ __forceinline__ void storeStrip(float* lo, float* hi, float (&o)[8][4], int nto, int t, bool accumulate) {
+// slo / shi (optional): the same rows of the tensor's bf16 shadow (BF16S GEMM mode), written with the final values.
+__device__ __forceinline__ void storeStrip(float* lo, float* hi, float (&o)[8][4], int nto, int t, bool accumulate, __nv_bfloat16* slo = nullptr, __nv_bfloat16* shi = nullptr) {
   if(accumulate) {
 #pragma unroll
     for(int n = 0; n < 8; ++n)
@@ -907,6 +909,10 @@ __device__ __forceinline__ void storeStrip(float* lo, float* hi, float (&o)[8][4
         *reinterpret_cast<float2*>(lo + n * 8 + 2 * t) = make_float2(o[n][0], o[n][1]);
       if(hi)
         *reinterpret_cast<float2*>(hi + n * 8 + 2 * t) = make_float2(o[n][2], o[n][3]);
+      if(slo)
+        *reinterpret_cast<__nv_bfloat162*>(slo + n * 8 + 2 * t) = __floats2bfloat162_rn(o[n][0], o[n][1]);
+      if(shi)
+        *reinterpret_cast<__nv_bfloat162*>(shi + n * 8 + 2 * t) = __floats2bfloat162_rn(o[n][2], o[n][3]);
     }
 }
 
@@ -955,7 +961,10 @@ __global__ void __launch_bounds__(128) gAttentionBackwardWarp(float* __restrict_
                                                               int R,
                                                               int accQ,
                                                               int accK,
-                                                              int accV) {
+                                                              int accV,
+                                                              __nv_bfloat16* __restrict__ dqS,
+                                                              __nv_bfloat16* __restrict__ dkS,
+                                                              __nv_bfloat16* __restrict__ dvS) {
   extern __shared__ __align__(16) float smemF[];
   pdlEnter();
   const int TILE = R * 64;
@@ -1097,7 +1106,8 @@ __global__ void __launch_bounds__(128) gAttentionBackwardWarp(float* __restrict_
       for(int n = 0; n < 8; ++n)
         mmaSplit<X3>(o[n], af, ahi, kp[(n * 8) ^ cE], kp[64 + ((n * 8) ^ cO)]);
     }
-  storeStrip(iLo < g.Tq ? dq + offQ + (size_t)iLo * d : nullptr, iHi < g.Tq ? dq + offQ + (size_t)iHi * d : nullptr, o, 8, t, accQ != 0);
+  storeStrip(iLo < g.Tq ? dq + offQ + (size_t)iLo * d : nullptr, iHi < g.Tq ? dq + offQ + (size_t)iHi * d : nullptr, o, 8, t, accQ != 0,
+             (dqS && iLo < g.Tq) ? dqS + offQ + (size_t)iLo * d : nullptr, (dqS && iHi < g.Tq) ? dqS + offQ + (size_t)iHi * d : nullptr);
   __syncthreads();  // barrier A2: K is dead, the P tile is complete
 
   // dS strip -> K tile
@@ -1135,7 +1145,9 @@ __global__ void __launch_bounds__(128) gAttentionBackwardWarp(float* __restrict_
         mmaSplit<X3>(o[n], af, ahi, bp[(n * 8) ^ cE], bp[64 + ((n * 8) ^ cO)]);
     }
     float* dst = pass == 0 ? dv : dk_;
-    storeStrip(iLo < g.Tk ? dst + offK + (size_t)iLo * d : nullptr, iHi < g.Tk ? dst + offK + (size_t)iHi * d : nullptr, o, 8, t, (pass == 0 ? accV : accK) != 0);
+    __nv_bfloat16* dstS = pass == 0 ? dvS : dkS;
+    storeStrip(iLo < g.Tk ? dst + offK + (size_t)iLo * d : nullptr, iHi < g.Tk ? dst + offK + (size_t)iHi * d : nullptr, o, 8, t, (pass == 0 ? accV : accK) != 0,
+               (dstS && iLo < g.Tk) ? dstS + offK + (size_t)iLo * d : nullptr, (dstS && iHi < g.Tk) ? dstS + offK + (size_t)iHi * d : nullptr);
   }
 }
 
@@ -1155,7 +1167,8 @@ __global__ void __launch_bounds__(128) gAttentionForwardWarp64(float* __restrict
                                                                const float* __restrict__ mask,
                                                                AttnGeom g,
                                                                int Rq,
-                                                               int Rk) {
+                                                               int Rk,
+                                                               __nv_bfloat16* __restrict__ outS) {
   extern __shared__ __align__(16) float smemF[];
   pdlEnter();
   float* sQ = smemF;          // [Rq][64]; A rows beyond Rq read into sK: finite, never stored
@@ -1311,7 +1324,8 @@ __global__ void __launch_bounds__(128) gAttentionForwardWarp64(float* __restrict
       for(int n = 0; n < 8; ++n)
         mmaSplit<X3>(o[n], af, ahi, vp[(n * 8) ^ cE], vp[64 + ((n * 8) ^ cO)]);
     }
-  storeStrip(iLo < g.Tq ? out + ((size_t)b * g.Tq + iLo) * d + h * 64 : nullptr, iHi < g.Tq ? out + ((size_t)b * g.Tq + iHi) * d + h * 64 : nullptr, o, 8, t, false);
+  storeStrip(iLo < g.Tq ? out + ((size_t)b * g.Tq + iLo) * d + h * 64 : nullptr, iHi < g.Tq ? out + ((size_t)b * g.Tq + iHi) * d + h * 64 : nullptr, o, 8, t, false,
+             (outS && iLo < g.Tq) ? outS + ((size_t)b * g.Tq + iLo) * d + h * 64 : nullptr, (outS && iHi < g.Tq) ? outS + ((size_t)b * g.Tq + iHi) * d + h * 64 : nullptr);
 }
 
 size_t forwardSmem(const AttnGeom& g) {
@@ -1390,10 +1404,11 @@ void MultiHeadAttention(Tensor out, Tensor probs, const Tensor q, const Tensor k
       float* pp = probs ? probs->data() : nullptr;
       const float* mp = mask ? mask->data() : nullptr;
       dim3 grid(g.B * g.H, (g.Tq + 63) / 64);
+      __nv_bfloat16* outS = shadow::produce(out);  // the output projection reads the context as a bf16 operand (BF16S mode)
       if(exact)
-        launchPdl(gAttentionForwardWarp64<true>, grid, dim3(128), smemW, cudaStreamOfEngine(), out->data(), pp, (const float*)q->data(), (const float*)k->data(), (const float*)v->data(), mp, g, Rq, Rk);
+        launchPdl(gAttentionForwardWarp64<true>, grid, dim3(128), smemW, cudaStreamOfEngine(), out->data(), pp, (const float*)q->data(), (const float*)k->data(), (const float*)v->data(), mp, g, Rq, Rk, outS);
       else
-        launchPdl(gAttentionForwardWarp64<false>, grid, dim3(128), smemW, cudaStreamOfEngine(), out->data(), pp, (const float*)q->data(), (const float*)k->data(), (const float*)v->data(), mp, g, Rq, Rk);
+        launchPdl(gAttentionForwardWarp64<false>, grid, dim3(128), smemW, cudaStreamOfEngine(), out->data(), pp, (const float*)q->data(), (const float*)k->data(), (const float*)v->data(), mp, g, Rq, Rk, outS);
       CUDA_LAUNCH_CHECK();
       return;
     }
@@ -1477,12 +1492,18 @@ void MultiHeadAttentionGrad(Tensor dq, Tensor dk, Tensor dv, const Tensor adj, c
       CUDA_CHECK(cudaFuncSetAttribute(gAttentionBackwardWarp<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
       configured = true;
     }
+    // adjoints of the q / k / v projections with this kernel as their one writer: leave the bf16 shadows the
+    // input- and weight-gradient products read (BF16S mode); never for aliased or accumulated-into tensors
+    const bool distinct = dq->rawData() != dk->rawData() && dq->rawData() != dv->rawData() && dk->rawData() != dv->rawData();
+    __nv_bfloat16* dqS = (!accQ && distinct) ? shadow::produce(dq) : nullptr;
+    __nv_bfloat16* dkS = (!accK && distinct) ? shadow::produce(dk) : nullptr;
+    __nv_bfloat16* dvS = (!accV && distinct) ? shadow::produce(dv) : nullptr;
     if(exact)
       launchPdl(gAttentionBackwardWarp<true>, dim3(g.B * g.H), dim3(128), smemW, cudaStreamOfEngine(), dq->data(), dk->data(), dv->data(), (const float*)adj->data(), (const float*)probs->data(),
-                (const float*)q->data(), (const float*)k->data(), (const float*)v->data(), g, R, (int)accQ, (int)accK, (int)accV);
+                (const float*)q->data(), (const float*)k->data(), (const float*)v->data(), g, R, (int)accQ, (int)accK, (int)accV, dqS, dkS, dvS);
     else
       launchPdl(gAttentionBackwardWarp<false>, dim3(g.B * g.H), dim3(128), smemW, cudaStreamOfEngine(), dq->data(), dk->data(), dv->data(), (const float*)adj->data(), (const float*)probs->data(),
-                (const float*)q->data(), (const float*)k->data(), (const float*)v->data(), g, R, (int)accQ, (int)accK, (int)accV);
+                (const float*)q->data(), (const float*)k->data(), (const float*)v->data(), g, R, (int)accQ, (int)accK, (int)accV, dqS, dkS, dvS);
     CUDA_LAUNCH_CHECK();
     return;
   }

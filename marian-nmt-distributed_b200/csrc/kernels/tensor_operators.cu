@@ -316,7 +316,7 @@ __global__ void gCrossEntropyPick(float* __restrict__ out, const float* __restri
 }
 
 template <bool WARP, bool VEC>
-__global__ void gCrossEntropyPickBackward(float* __restrict__ out, const float* __restrict__ adj, const float* __restrict__ in, const float* __restrict__ pick, int rows, int cols, int assign, const float* __restrict__ stats) {
+__global__ void gCrossEntropyPickBackward(float* __restrict__ out, const float* __restrict__ adj, const float* __restrict__ in, const float* __restrict__ pick, int rows, int cols, int assign, const float* __restrict__ stats, __nv_bfloat16* __restrict__ outShadow) {
   pdlEnter();
   __shared__ float smem[32];
   typedef RowCtx<WARP> R;
@@ -348,6 +348,7 @@ __global__ void gCrossEntropyPickBackward(float* __restrict__ out, const float* 
         g.z += a * (__expf(x.z - M) * invS - (float)(id + 2 == p));
         g.w += a * (__expf(x.w - M) * invS - (float)(id + 3 == p));
         o4[i] = g;
+        shadow::store4(outShadow, (size_t)j * cols + id, g);  // bf16 copy of the logits adjoint for the two products that read it
       }
     } else {
       for(int id = R::firstCol(); id < cols; id += R::colStride()) {
@@ -392,7 +393,8 @@ void CrossEntropyPickBackward(Tensor out, Tensor adj, Tensor a, Tensor pick, Ten
   int assign = out->takeLazyZero() ? 1 : 0;  // first writer of the logits adjoint: no memset, no read-back
   bool vec = rowsVectorizable(a->data(), out->data(), cols);
   auto st = cudaStreamOfEngine();
-#define CE_BWD(W, V) launchPdl(gCrossEntropyPickBackward<W, V>, dim3(l.grid), dim3(l.block), 0, st, out->data(), (const float*)adj->data(), (const float*)a->data(), (const float*)pick->data(), rows, cols, assign, statsPtr)
+  __nv_bfloat16* osh = (assign && vec) ? shadow::produce(out) : nullptr;
+#define CE_BWD(W, V) launchPdl(gCrossEntropyPickBackward<W, V>, dim3(l.grid), dim3(l.block), 0, st, out->data(), (const float*)adj->data(), (const float*)a->data(), (const float*)pick->data(), rows, cols, assign, statsPtr, osh)
   if(l.warp) {
     if(vec) CE_BWD(true, true); else CE_BWD(true, false);
   } else {
@@ -1320,7 +1322,7 @@ __global__ void gTransposeGeneric(float* __restrict__ out, const float* __restri
 
 // permutations that keep the last axis (e.g. {0,2,1,3}: head split/join,
 // time<->batch): whole rows move, four floats per thread
-__global__ void gTransposeRows4(float4* __restrict__ out, const float4* __restrict__ in, Shape4 os, Shape4 is, Perm permute, int cols4) {
+__global__ void gTransposeRows4(float4* __restrict__ out, const float4* __restrict__ in, Shape4 os, Shape4 is, Perm permute, int cols4, __nv_bfloat16* __restrict__ outShadow) {
   pdlEnter();
   long long items = (long long)os.d[0] * os.d[1] * os.d[2] * cols4;
   for(long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < items; w += (long long)gridDim.x * blockDim.x) {
@@ -1336,7 +1338,9 @@ __global__ void gTransposeRows4(float4* __restrict__ out, const float4* __restri
     for(int i = 0; i < 4; ++i)
       pDims[permute.p[i]] = oDims[i];
     size_t src = ((size_t)pDims[0] * is.st[0] + (size_t)pDims[1] * is.st[1] + (size_t)pDims[2] * is.st[2]) / 4;
-    out[w] = in[src + c];
+    const float4 v = in[src + c];
+    out[w] = v;
+    shadow::store4(outShadow, (size_t)w << 2, v);  // bf16 copy when the transposed tensor feeds a product (BF16S)
   }
 }
 
@@ -1498,7 +1502,7 @@ void TransposeND(Tensor out, Tensor in, const std::vector<int>& vAxis) {
   bool swapsLast2 = perm.p[0] == 0 && perm.p[1] == 1 && perm.p[2] == 3 && perm.p[3] == 2;
   if(keepsLast && os.d[3] % 4 == 0 && ((((uintptr_t)out->data()) | ((uintptr_t)in->data())) & 15) == 0) {
     int cols4 = os.d[3] / 4;
-    launchPdl(gTransposeRows4, dim3(gridFor((size_t)length / 4, 256)), dim3(256), 0, st, (float4*)out->data(), (const float4*)in->data(), os, is, perm, cols4);
+    launchPdl(gTransposeRows4, dim3(gridFor((size_t)length / 4, 256)), dim3(256), 0, st, (float4*)out->data(), (const float4*)in->data(), os, is, perm, cols4, shadow::produce(out));
   } else if(swapsLast2) {
     int batch = is.d[0] * is.d[1], rows = is.d[2], cols = is.d[3];
     dim3 grid((cols + 31) / 32, (rows + 31) / 32, batch);

@@ -4,6 +4,8 @@ bf16 and hi/lo-split bf16x3) and the fp32 SIMT path against the CPU oracle and f
 Tolerances (relative to the output magnitude):
   fp32 SIMT  1e-5      bf16x3  5e-5 (operands carry 16 mantissa bits)      bf16  1e-2
   tf32  2e-3 (operands carry 11 mantissa bits)
+Mode 4 (bf16 SHADOW operands read by TMA in all four transpose cases) has the arithmetic of mode 1
+(packed bf16): it is checked against float64 at the bf16 tolerance AND against mode 1 at 2e-5.
 """
 import numpy as np
 import pytest
@@ -12,7 +14,7 @@ from test_gpu_ops import close, rnd
 
 pytestmark = pytest.mark.gpu
 
-TOL = {0: 1e-5, 2: 5e-5, 1: 1.5e-2, 3: 2e-3}
+TOL = {0: 1e-5, 2: 5e-5, 1: 1.5e-2, 3: 2e-3, 4: 1.5e-2}
 
 
 def ref_prod(A, B, tA, tB, beta, alpha, C0):
@@ -45,7 +47,7 @@ SHAPES = [  # (A shape, B shape, transA, transB)
 ]
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("sa,sb,tA,tB", SHAPES)
 @pytest.mark.parametrize("beta,alpha", [(0.0, 1.0), (1.0, 0.125)])
 def test_prod(cuda, oracle, mode, sa, sb, tA, tB, beta, alpha):
@@ -68,19 +70,20 @@ def test_prod(cuda, oracle, mode, sa, sb, tA, tB, beta, alpha):
         close(run(oracle, 0), exp, 1e-5, "oracle vs float64")
 
 
-@pytest.mark.parametrize("M,N,K", [(3200, 2048, 512), (300, 72, 96), (129, 68, 40), (64, 2048, 64)])
+@pytest.mark.parametrize("mode", [3, 4])
+@pytest.mark.parametrize("M,N,K", [(3200, 2048, 512), (304, 72, 96), (136, 72, 40), (64, 2048, 64)])
 @pytest.mark.parametrize("beta", [0.0, 1.0])
-def test_prod_swish_grad_nt(cuda, M, N, K, beta):
+def test_prod_swish_grad_nt(cuda, mode, M, N, K, beta):
     # dH = beta dH + (dY W^T) o swish'(H) in the epilogue of the tf32 product (feed-forward backward pass)
     A, B, H, C0 = rnd(1, M, K), rnd(2, N, K), 2.5 * rnd(3, M, N), rnd(4, M, N)
     h = H.astype(np.float64)
     sg = 1.0 / (1.0 + np.exp(-h))
     exp = beta * C0 + (A.astype(np.float64) @ B.astype(np.float64).T) * (sg * (1.0 + h * (1.0 - sg)))
-    g = cuda.gemm(3)
+    g = cuda.gemm(mode)
     c = cuda.array(C0)
     cuda.call("mrn_prod_swish_grad_nt", g.h, c.t(), cuda.array(A).t(), cuda.array(B).t(), cuda.array(H).t(), beta)
     cuda.synchronize()
-    close(c.numpy(), exp, TOL[3], "gated product vs float64")
+    close(c.numpy(), exp, TOL[mode], "gated product vs float64")
     # and against the two-step form on the same GPU path (product, then the element-wise swish backward)
     t = cuda.zeros((M, N))
     cuda.call("mrn_prod", g.h, t.t(), cuda.array(A).t(), cuda.array(B).t(), 0, 1, 0.0, 1.0)
@@ -89,7 +92,7 @@ def test_prod_swish_grad_nt(cuda, M, N, K, beta):
     close(c.numpy(), two, 2e-5, "gated product vs product + swish'")
 
 
-@pytest.mark.parametrize("mode", [0, 3])
+@pytest.mark.parametrize("mode", [0, 3, 4])
 @pytest.mark.parametrize("M,N,K,G", [
     (3200, 512, 512, 3),   # dX of the q/k/v projections (config B): one K-grouped launch in mode 3
     (3200, 512, 512, 2),   # key/value pair of a cross-attention block
@@ -118,7 +121,7 @@ def test_prod_grouped_nt(cuda, oracle, mode, M, N, K, G, beta):
         close(run(oracle), exp, 1e-5, "oracle vs float64")
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("sa,sb,tA,tB", [
     ((64, 8, 50, 64), (64, 8, 50, 64), False, True),    # Q K^T  (config B)
     ((64, 8, 50, 50), (64, 8, 50, 64), False, False),   # P V
@@ -149,7 +152,7 @@ def test_prod_batched(cuda, oracle, mode, sa, sb, tA, tB):
     close(c.numpy(), exp, TOL[mode], "batched")
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("M,K,N", [(3200, 512, 2048), (130, 70, 50), (320, 512, 32000)])
 def test_prod_affine(cuda, mode, M, K, N):
     A, B, bias = rnd(1, M, K), rnd(2, K, N), rnd(3, 1, N)
@@ -178,3 +181,60 @@ def test_gemm_linearity_full_size(cuda):
         outs[mode] = c12.numpy()
         close(c1.numpy() + c2.numpy(), outs[mode], 5e-5, "linearity mode %d" % mode)
     close(outs[2], outs[0], 5e-5, "bf16x3 vs fp32")
+
+
+BF16_SHAPES = [  # 16-byte aligned bf16 rows (cols % 8 == 0): the TMA-direct bf16 kernel, all four layouts
+    ((3200, 512), (512, 512), False, False),
+    ((3200, 512), (512, 2048), False, False),
+    ((3200, 512), (512, 512), False, True),
+    ((3200, 2048), (512, 2048), False, True),
+    ((3200, 512), (3200, 512), True, False),     # dW (split-K), both operands MN-major
+    ((3200, 512), (3200, 2048), True, False),
+    ((304, 72), (72, 136), False, False),         # ragged M / N / K tails through TMA zero fill
+    ((136, 72), (40, 72), False, True),
+    ((72, 136), (72, 40), True, False),
+    ((80, 40), (96, 80), True, True),
+    ((64, 1024), (1024, 3072), False, False),    # RNN step shape
+]
+
+
+@pytest.mark.parametrize("sa,sb,tA,tB", BF16_SHAPES)
+@pytest.mark.parametrize("beta", [0.0, 1.0])
+def test_bf16_shadow_mode_equals_packed_bf16(cuda, sa, sb, tA, tB, beta):
+    """Mode 4 reads bf16 copies of the row-major operands directly (K-major and MN-major shared-memory
+    descriptors); mode 1 packs every operand into K-major bf16 first.  Same rounded operands, same fp32
+    accumulation: the results agree to accumulation-order noise."""
+    A, B = rnd(1, *sa), rnd(2, *sb)
+    m = (np.prod(sa) // sa[-1]) if not tA else sa[-1]
+    n = sb[-1] if not tB else (np.prod(sb) // sb[-1])
+    C0 = rnd(3, int(m), int(n))
+    out = {}
+    for mode in (1, 4):
+        g = cuda.gemm(mode)
+        a, b, c = cuda.array(A), cuda.array(B), cuda.array(C0)
+        cuda.call("mrn_prod", g.h, c.t(), a.t(), b.t(), int(tA), int(tB), beta, 0.5)
+        cuda.synchronize()
+        out[mode] = c.numpy()
+    close(out[4], out[1], 2e-5, "bf16 shadows vs packed bf16")
+
+
+def test_gemm_full_size_logits_shapes_throughput_modes(cuda):
+    """The three logits-sized products of config B (forward NN, input gradient NT, weight gradient TN with
+    split-K) in the throughput modes 3 (tf32) and 4 (bf16) against the fp32 SIMT kernel."""
+    M, K, N = 3200, 512, 32000
+    X, W, D = rnd(1, M, K), rnd(2, K, N, scale=0.05), rnd(3, M, N, scale=0.02)
+    ref = {}
+    for mode in (0, 3, 4):
+        g = cuda.gemm(mode)
+        x, w, d = cuda.array(X), cuda.array(W), cuda.array(D)
+        y, dx, dw = cuda.zeros((M, N)), cuda.zeros((M, K)), cuda.zeros((K, N))
+        cuda.call("mrn_prod", g.h, y.t(), x.t(), w.t(), 0, 0, 0.0, 1.0)
+        cuda.call("mrn_prod", g.h, dx.t(), d.t(), w.t(), 0, 1, 0.0, 1.0)
+        cuda.call("mrn_prod", g.h, dw.t(), x.t(), d.t(), 1, 0, 0.0, 1.0)
+        cuda.synchronize()
+        got = {"y": y.numpy(), "dx": dx.numpy(), "dw": dw.numpy()}
+        if mode == 0:
+            ref = got
+        else:
+            for k in got:
+                close(got[k], ref[k], TOL[mode], "mode %d %s" % (mode, k))
