@@ -223,6 +223,16 @@ int mrn_trainer_async_update(void* trainer);
 int mrn_trainer_async_fetch(void* trainer);
 int mrn_trainer_cost(void* trainer, float* cost);
 
+/* Checkpoint / resume in the reference's wire format (ExpressionGraph::save / load,
+ * src/graph/expression_graph.h:442-502; EncoderDecoder::save, src/models/encdec.h:201-229): one .npz with
+ * every parameter as float32 under its Marian name + the char array "special:model.yml".  load() goes into a
+ * FRESH trainer before its first step (the parameters are created from the file, the model code finds them by
+ * name) and checks the stored model description against the trainer's options.  with_optimizer != 0 also
+ * writes / reads "<path>.optimizer.npz" (Adam moments per parameter name + step counter; the reference has no
+ * optimizer checkpoint).  Blocking. */
+int mrn_trainer_save(void* trainer, const char* path, int with_optimizer);
+int mrn_trainer_load(void* trainer, const char* path, int with_optimizer);
+
 /* flat arenas (src/graph/parameters.h:58-80): device pointers + element counts */
 int mrn_trainer_params(void* trainer, float** ptr, size_t* elements);
 int mrn_trainer_grads(void* trainer, float** ptr, size_t* elements);

@@ -93,6 +93,8 @@ _SIGNATURES = {
     "mrn_trainer_async_update": [_V],
     "mrn_trainer_async_fetch": [_V],
     "mrn_trainer_cost": [_V, c_float_p],
+    "mrn_trainer_save": [_V, ctypes.c_char_p, _I],
+    "mrn_trainer_load": [_V, ctypes.c_char_p, _I],
     "mrn_trainer_params": [_V, ctypes.POINTER(_V), ctypes.POINTER(_SZ)],
     "mrn_trainer_grads": [_V, ctypes.POINTER(_V), ctypes.POINTER(_SZ)],
     "mrn_trainer_shard_grads": [_V, ctypes.POINTER(_V), ctypes.POINTER(_SZ)],
@@ -345,6 +347,12 @@ class Trainer:
 
     def async_fetch(self):
         self.lib._ck(self.lib.c.mrn_trainer_async_fetch(self.h))
+
+    def save(self, path, with_optimizer=False):
+        self.lib._ck(self.lib.c.mrn_trainer_save(self.h, str(path).encode(), int(with_optimizer)))
+
+    def load(self, path, with_optimizer=False):
+        self.lib._ck(self.lib.c.mrn_trainer_load(self.h, str(path).encode(), int(with_optimizer)))
 
     def cost(self):
         c = ctypes.c_float()

@@ -10,6 +10,7 @@
 
 #include "data/batch.h"
 #include "kernels/tensor_operators.h"
+#include "training/checkpoint.h"
 #include "training/graph_group.h"
 
 using namespace marian;
@@ -537,6 +538,44 @@ int mrn_trainer_async_fetch(void* trainer) {
     auto t = (Trainer*)trainer;
     ABORT_IF(!t->async, "mrn_trainer_async_fetch needs graph-group=async");
     t->async->fetchParams();
+  });
+}
+
+// ---- checkpoint / resume (training/checkpoint.h; reference expression_graph.h:442-502, encdec.h:201-229) ----
+int mrn_trainer_save(void* trainer, const char* path, int withOptimizer) {
+  return guarded([&] {
+    auto t = (Trainer*)trainer;
+    device::setDevice(t->device);
+    device::synchronize();
+    auto graph = t->worker().graph();
+    ABORT_IF(graph->params()->size() == 0, "mrn_trainer_save: the model has no parameters yet (run a step or load a checkpoint first)");
+    checkpoint::saveModel(graph, t->options, path);
+    if(withOptimizer) {
+      ABORT_IF(!t->single, "mrn_trainer_save: optimizer state is saved by the single-process trainer (shard optimizers keep per-rank state)");
+      auto adam = std::dynamic_pointer_cast<Adam>(t->single->optimizer());
+      ABORT_IF(!adam, "mrn_trainer_save: optimizer state is implemented for adam");
+      checkpoint::saveAdam(graph, adam, std::string(path) + ".optimizer.npz");
+    }
+  });
+}
+int mrn_trainer_load(void* trainer, const char* path, int withOptimizer) {
+  return guarded([&] {
+    auto t = (Trainer*)trainer;
+    device::setDevice(t->device);
+    auto graph = t->worker().graph();
+    ABORT_IF(graph->params()->size() != 0, "mrn_trainer_load: load a checkpoint into a fresh trainer, before its first step");
+    Options stored = checkpoint::loadModel(graph, path);
+    // the stored model description must describe the model this trainer builds
+    for(auto& key : checkpoint::modelFeatures())
+      if(stored.has(key) && t->options->has(key))
+        ABORT_IF(stored.get<std::string>(key) != t->options->get<std::string>(key), "mrn_trainer_load: checkpoint was trained with a different", key, ":",
+                 stored.get<std::string>(key), "vs", t->options->get<std::string>(key));
+    if(withOptimizer) {
+      ABORT_IF(!t->single, "mrn_trainer_load: optimizer state is restored by the single-process trainer");
+      auto adam = std::dynamic_pointer_cast<Adam>(t->single->optimizer());
+      ABORT_IF(!adam, "mrn_trainer_load: optimizer state is implemented for adam");
+      checkpoint::loadAdam(graph, adam, std::string(path) + ".optimizer.npz");
+    }
   });
 }
 

@@ -14,6 +14,7 @@
 #pragma once
 
 #include <cmath>
+#include <functional>
 
 #include "common/options.h"
 #include "graph/expression_graph.h"
@@ -132,6 +133,16 @@ public:
   Tensor mt() { return mt_; }
   Tensor vt() { return vt_; }
   size_t steps() const { return t_; }
+  // resume (training/checkpoint.h): `fill` writes the saved moments once the flat state exists
+  void restoreOnAllocation(size_t steps, std::function<void(Tensor, Tensor)> fill) {
+    pendingSteps_ = steps;
+    pendingFill_ = fill;
+    if(mt_) {
+      pendingFill_(mt_, vt_);
+      t_ = pendingSteps_;
+      pendingFill_ = nullptr;
+    }
+  }
   // hyper-parameters for update kernels that keep their own state (asynchronous parameter server)
   AdamArgs hyper(float gradScale = 1.f) const {
     AdamArgs a;
@@ -154,6 +165,11 @@ private:
       mt_->set(0);
       alloc_->allocate(vt_, Shape{1, (int)params->size()});
       vt_->set(0);
+      if(pendingFill_) {
+        pendingFill_(mt_, vt_);
+        t_ = pendingSteps_;
+        pendingFill_ = nullptr;
+      }
     }
     t_++;
     AdamArgs a;
@@ -175,6 +191,8 @@ private:
   Ptr<TensorAllocator> alloc_;
   Tensor mt_;
   Tensor vt_;
+  size_t pendingSteps_{0};
+  std::function<void(Tensor, Tensor)> pendingFill_;
 };
 
 // reference: optimizers.cu:85-107

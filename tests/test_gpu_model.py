@@ -254,3 +254,39 @@ def test_dropout_draws_fresh_masks_on_every_replay(cuda):
     assert st["replays"] >= 3, st
     assert len(set(np.round(costs[2:], 4))) == len(costs[2:]), costs   # replays: all different
     assert np.std(costs) < 0.05 * np.mean(costs), costs               # ... but the same model
+
+
+def test_checkpoint_round_trip_between_gpu_and_oracle(cuda, oracle, tmp_path):
+    """A model trained and saved on the GPU (reference .npz format, csrc/training/checkpoint.h) resumes on the GPU
+    with its Adam state, and loads into the CPU oracle: same next-batch cost within the exact-mode tolerance."""
+    opts = TRANSFORMER + ";gemm-mode=2;graph-replay=false;learn-rate=0.001"
+
+    def steps(t, n, skip=0):
+        for _ in range(skip):
+            t.next_synthetic_batch(8, 11, 13, padded=True)
+        out = []
+        for _ in range(n):
+            t.next_synthetic_batch(8, 11, 13, padded=True)
+            t.compute_gradients()
+            t.update()
+            out.append(t.cost())
+        return out
+
+    ref = cuda.trainer(opts)
+    want = steps(ref, 5)
+    ref.close()
+    a = cuda.trainer(opts)
+    first = steps(a, 3)
+    path = tmp_path / "gpu.npz"
+    a.save(path, with_optimizer=True)
+    a.close()
+    b = cuda.trainer(opts)
+    b.load(path, with_optimizer=True)
+    rest = steps(b, 2, skip=3)
+    b.close()
+    assert np.allclose(first + rest, want, rtol=2e-5), (first + rest, want)
+    o = oracle.trainer(opts.replace("gemm-mode=2", "gemm-mode=0"))
+    o.load(path, with_optimizer=True)
+    cpu = steps(o, 2, skip=3)
+    o.close()
+    assert np.allclose(cpu, want[3:], rtol=1e-4), (cpu, want[3:])
