@@ -801,7 +801,7 @@ struct TcArgs {
 };
 
 template <int BN, bool GATE = false>
-__device__ __forceinline__ void epilogueTile(const TcArgs& a, uint32_t tmemBase, uint64_t* tmemFullBar, float* stage, int warp, int lane, int m0, int n0, int batch, int split);
+__device__ __forceinline__ void epilogueTile(const TcArgs& a, uint32_t tmemBase, uint64_t* tmemFullBar, float* stage, int warp, int lane, int m0, int n0, int batch, int split, uint32_t parity = 0);
 
 template <int BN, int STAGES>
 struct TcSmem {
@@ -994,7 +994,7 @@ __device__ __forceinline__ float swishGrad(float h) {
 // GATE: C = beta C + (alpha acc + bias) o swish'(gate) - the backward pass of "affine after swish"
 // (dH = (dY W^T) o swish'(H)) without the intermediate adjoint and its element-wise kernel.
 template <int BN, bool GATE>
-__device__ __forceinline__ void epilogueTile(const TcArgs& a, uint32_t tmemBase, uint64_t* tmemFullBar, float* stage, int warp, int lane, int m0, int n0, int batch, int split) {
+__device__ __forceinline__ void epilogueTile(const TcArgs& a, uint32_t tmemBase, uint64_t* tmemFullBar, float* stage, int warp, int lane, int m0, int n0, int batch, int split, uint32_t parity) {
   const int q = warp & 3;  // TMEM lane quarter this warp may access
   float* Cb = a.C + (size_t)batch * a.strideC;
   const float* Gb = GATE ? a.gate + (size_t)batch * a.strideC : nullptr;
@@ -1029,7 +1029,7 @@ __device__ __forceinline__ void epilogueTile(const TcArgs& a, uint32_t tmemBase,
 
   prefetchOld(n0);
   prefetchGate(n0);
-  mbarWait(tmemFullBar, 0);
+  mbarWait(tmemFullBar, parity);
   tcgenFenceAfter();
 #pragma unroll 1
   for(int c0 = 0; c0 < BN; c0 += 32) {
@@ -1854,6 +1854,237 @@ __global__ void __launch_bounds__(192, GATE ? 2 : 1) gGemmBf16(const __grid_cons
   }
 }
 
+
+// ---- persistent variant: one CTA per SM walks a static list of 128 x BN output tiles ----------------
+// For products with many tiles (feed-forward layers: 400, vocabulary projection: 6250 / 1000) the
+// one-tile-per-CTA kernel pays its serial chain (prologue, first TMA round trip, epilogue) per tile
+// and runs in ragged waves.  Here the three roles loop over the tiles independently:
+//   producer   streams k-blocks of tile after tile through ONE smem ring (no drain between tiles);
+//   MMA issuer accumulates tile j into TMEM buffer j & 1 (2 x BN columns allocated) - it only waits
+//              for the epilogue of tile j - 2;
+//   epilogue   warps drain buffer j & 1 (own staging memory, the ring stays live) while the main
+//              loop of tile j + 1 runs, then hand the buffer back (tmemEmpty).
+// Tiles are numbered m-fastest, so the CTAs running at the same time share B tiles through L2.
+template <int BN, int STAGES>
+struct BfPersistSmem {
+  static constexpr int A_BYTES = BLOCK_M * 128;
+  static constexpr int B_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGING_OFFSET = STAGES * STAGE_BYTES;
+  static constexpr int STAGING_BYTES = 4 * 32 * kStagePitch * 4;
+  static constexpr int BAR_OFFSET = STAGING_OFFSET + STAGING_BYTES;
+  static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;
+};
+
+// SUMS: two more warps follow the ring and, on the tiles of the first tile column, add the column sums of the
+// (K-major) A tiles into a.colSum[0] - the bias gradient, as in the one-tile kernels (there the idle epilogue
+// warps do it; here they are busy with the previous tile).  They acknowledge every stage (emptyBar counts 3).
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool GATE = false, bool SUMS = false>
+__global__ void __launch_bounds__(SUMS ? 256 : 192, 1) gGemmBf16Persistent(const __grid_constant__ TfMaps<1> tm, TcArgs a) {
+  typedef BfPersistSmem<BN, STAGES> L;
+  extern __shared__ uint8_t smemRaw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smemRaw + 1023) & ~(uintptr_t)1023);
+  uint64_t* fullBar = (uint64_t*)(smem + L::BAR_OFFSET);
+  uint64_t* emptyBar = fullBar + STAGES;
+  uint64_t* tmemFullBar = emptyBar + STAGES;  // [2]
+  uint64_t* tmemEmptyBar = tmemFullBar + 2;   // [2]
+  uint32_t* tmemHolder = (uint32_t*)(tmemEmptyBar + 2);
+
+  pdlTrigger();
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  auto now = [] {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+  };
+  if(a.spanMin && threadIdx.x == 0)
+    atomicMin(a.spanMin, now());
+
+  const int mTiles = (a.M + BLOCK_M - 1) / BLOCK_M;
+  const int nTiles = (a.N + BN - 1) / BN;
+  const int numTiles = mTiles * nTiles;
+  const int nkb = a.kBlocks;
+  // tuning aid (scripts/gemm_stamps_bf16.py): 64 slots per CTA - [0] start, [1] prologue done, then per tile j < 10:
+  // [2+6j] first TMA issued, [+1] first operands seen by the MMA thread, [+2] last MMA issued, [+3] accumulator
+  // complete (epilogue woke up), [+4] epilogue done, [+5] last TMA issued; [63] end
+  unsigned long long* stamp = a.stamps ? a.stamps + 64 * (size_t)blockIdx.x : nullptr;
+  if(stamp && threadIdx.x == 0)
+    stamp[0] = now();
+
+  if(warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm.a[0]) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm.b[0]) : "memory");
+    for(int s = 0; s < STAGES; ++s) {
+      mbarInit(fullBar + s, 1);
+      mbarInit(emptyBar + s, SUMS ? 3 : 1);
+    }
+    for(int b = 0; b < 2; ++b) {
+      mbarInit(tmemFullBar + b, 1);
+      mbarInit(tmemEmptyBar + b, 4);  // one arrival per epilogue warp
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if(warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smemAddr(tmemHolder)), "r"((uint32_t)(2 * BN)));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgenFenceBefore();
+  __syncthreads();
+  tcgenFenceAfter();
+  const uint32_t tmemBase = *tmemHolder;
+  pdlWait();
+  if(stamp && threadIdx.x == 0)
+    stamp[1] = now();
+
+  if(warp == 0) {
+    if(lane == 0) {
+      // ---------------- TMA producer: one stream of k-blocks over all tiles of this CTA ----------------
+      uint32_t it = 0, jt = 0;
+      for(int tile = blockIdx.x; tile < numTiles; tile += gridDim.x, ++jt) {
+        const int m0 = (tile % mTiles) * BLOCK_M;
+        const int n0 = (tile / mTiles) * BN;
+        for(int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t phase = (it / STAGES) & 1u;
+          mbarWait(emptyBar + s, phase ^ 1u);
+          if(stamp && jt < 10 && (i == 0 || i == nkb - 1))
+            stamp[2 + 6 * jt + (i == 0 ? 0 : 5)] = now();
+          mbarExpectTx(fullBar + s, (uint32_t)L::STAGE_BYTES);
+          uint8_t* sa = smem + s * L::STAGE_BYTES;
+          uint8_t* sb = sa + L::A_BYTES;
+          const int kc = i * BF_BLOCK_K;
+          if(A_MN) {
+#pragma unroll
+            for(int c = 0; c < BLOCK_M / 64; ++c)
+              tmaLoad3D(&tm.a[0], fullBar + s, sa + c * 8192, m0 + 64 * c, kc, 0);
+          } else {
+            tmaLoad3D(&tm.a[0], fullBar + s, sa, kc, m0, 0);
+          }
+          if(B_MN) {
+#pragma unroll
+            for(int c = 0; c < BN / 64; ++c)
+              tmaLoad3D(&tm.b[0], fullBar + s, sb + c * 8192, n0 + 64 * c, kc, 0);
+          } else {
+            tmaLoad3D(&tm.b[0], fullBar + s, sb, kc, n0, 0);
+          }
+        }
+      }
+    }
+  } else if(warp == 1) {
+    if(lane == 0) {
+      // ---------------- MMA issuer ----------------
+      constexpr uint32_t idesc = makeInstrDescBf16(BLOCK_M, BN, A_MN, B_MN);
+      constexpr uint32_t stepA = A_MN ? (2048 >> 4) : (32 >> 4);
+      constexpr uint32_t stepB = B_MN ? (2048 >> 4) : (32 >> 4);
+      uint32_t it = 0, j = 0;
+      for(int tile = blockIdx.x; tile < numTiles; tile += gridDim.x, ++j) {
+        const uint32_t buf = j & 1u, use = j >> 1;
+        mbarWait(tmemEmptyBar + buf, (use & 1u) ^ 1u);  // the epilogue of tile j - 2 has drained this buffer
+        tcgenFenceAfter();
+        const uint32_t tmemD = tmemBase + buf * BN;
+        for(int i = 0; i < nkb; ++i, ++it) {
+          const int s = it % STAGES;
+          const uint32_t phase = (it / STAGES) & 1u;
+          mbarWait(fullBar + s, phase);
+          if(stamp && j < 10 && i == 0)
+            stamp[2 + 6 * j + 1] = now();
+          tcgenFenceAfter();
+          const uint32_t sa = smemAddr(smem + s * L::STAGE_BYTES);
+          const uint32_t sb = sa + L::A_BYTES;
+          const uint64_t descA = makeSmemDescBf16<A_MN>(sa);
+          const uint64_t descB = makeSmemDescBf16<B_MN>(sb);
+#pragma unroll
+          for(int k = 0; k < BF_BLOCK_K / UMMA_K; ++k)
+            umma(tmemD, descA + (uint64_t)(k * stepA), descB + (uint64_t)(k * stepB), idesc, (uint32_t)((i | k) != 0));
+          ummaCommit(emptyBar + s);
+        }
+        ummaCommit(tmemFullBar + buf);  // accumulator of this tile complete
+        if(stamp && j < 10)
+          stamp[2 + 6 * j + 2] = now();
+      }
+    }
+  } else if(SUMS && warp >= 6) {
+    // ---------------- column-sum warps (rows 64 (warp - 6) .. + 63 of every A tile of the first tile column) ----------------
+    static_assert(!SUMS || !A_MN, "column sums read K-major A tiles");
+    const int rw = (warp - 6) * 64;
+    uint32_t it = 0;
+    for(int tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
+      const bool sumTile = tile < mTiles && a.colSum[0] != nullptr;  // tile column 0
+      for(int i = 0; i < nkb; ++i, ++it) {
+        const int s = it % STAGES;
+        mbarWait(fullBar + s, (it / STAGES) & 1u);
+        if(sumTile) {
+          // K-major SWIZZLE_128B bf16 tile: row R at (R / 8) * 1024 + (R % 8) * 128 bytes, 16-byte chunk c at c ^ (R % 8)
+          const uint32_t* sa = reinterpret_cast<const uint32_t*>(smem + s * L::STAGE_BYTES);
+          float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 16
+          for(int r = 0; r < 64; ++r) {
+            const int R = rw + r;
+            const uint32_t w = sa[(R >> 3) * 256 + (R & 7) * 32 + ((((lane >> 2) ^ (R & 7)) << 2) | (lane & 3))];
+            acc0 += __uint_as_float(w << 16);
+            acc1 += __uint_as_float(w & 0xffff0000u);
+          }
+          const int col = i * BF_BLOCK_K + 2 * lane;
+          if(col < a.colSumLen)
+            atomicAdd(a.colSum[0] + col, acc0);
+          if(col + 1 < a.colSumLen)
+            atomicAdd(a.colSum[0] + col + 1, acc1);
+        }
+        __syncwarp();
+        if(lane == 0)
+          mbarArrive(emptyBar + s);
+      }
+    }
+  } else {
+    // ---------------- epilogue warps ----------------
+    float* stage = reinterpret_cast<float*>(smem + L::STAGING_OFFSET) + (warp - 2) * (32 * kStagePitch);
+    uint32_t j = 0;
+    for(int tile = blockIdx.x; tile < numTiles; tile += gridDim.x, ++j) {
+      const int m0 = (tile % mTiles) * BLOCK_M;
+      const int n0 = (tile / mTiles) * BN;
+      const uint32_t buf = j & 1u, use = j >> 1;
+      if(stamp && j < 10 && threadIdx.x == 64) {  // (costs this warp one extra wait; tuning runs only)
+        mbarWait(tmemFullBar + buf, use & 1u);
+        stamp[2 + 6 * j + 3] = now();
+      }
+      epilogueTile<BN, GATE>(a, tmemBase + buf * BN, tmemFullBar + buf, stage, warp, lane, m0, n0, 0, 0, use & 1u);
+      tcgenFenceBefore();
+      __syncwarp();
+      if(lane == 0)
+        mbarArrive(tmemEmptyBar + buf);
+      if(stamp && j < 10 && threadIdx.x == 64)
+        stamp[2 + 6 * j + 4] = now();
+    }
+  }
+
+  tcgenFenceBefore();
+  __syncthreads();
+  if(a.spanMax && threadIdx.x == 0)
+    atomicMax(a.spanMax, now());
+  if(stamp && threadIdx.x == 0)
+    stamp[63] = now();
+  if(warp == 1) {
+    __syncwarp();
+    tcgenFenceAfter();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "r"((uint32_t)(2 * BN)));
+  }
+}
+
+template <bool A_MN, bool B_MN, bool GATE, bool SUMS = false>
+void launchBf16Persistent(const TfMaps<1>& tm, const TcArgs& a) {
+  constexpr int BN = 128, STAGES = 6;
+  typedef BfPersistSmem<BN, STAGES> L;
+  static bool configured = false;
+  if(!configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(gGemmBf16Persistent<BN, STAGES, A_MN, B_MN, GATE, SUMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  const int tiles = ((a.M + BLOCK_M - 1) / BLOCK_M) * ((a.N + BN - 1) / BN);
+  dim3 grid(std::min(tiles, kNumSMs));
+  launchPdl(gGemmBf16Persistent<BN, STAGES, A_MN, B_MN, GATE, SUMS>, grid, dim3(SUMS ? 256 : 192), (size_t)L::TOTAL, cudaStreamOfEngine(), tm, a);
+}
+
 // dims (innermost first): {inner, outer, batch}; box {64, boxOuter, 1}
 CUtensorMap makeTensorMapBf16(GemmHandle h, const __nv_bfloat16* base, uint64_t inner, uint64_t outer, uint64_t batches, uint64_t pitchElems, uint64_t batchStrideElems, uint32_t boxOuter) {
   if(!h->encodeTiled) {
@@ -1960,6 +2191,16 @@ bool runBf16(GemmHandle h, const GemmProblem& p) {
   }
   if(const char* forced = std::getenv("MRN_GEMM_SPLITS"))
     splits = std::max(1, std::min(std::atoi(forced), kBlocksAll));
+  // many tiles (feed-forward, vocabulary projection): the persistent kernel - one CTA per SM, tile loop with a
+  // double-buffered accumulator
+  static const bool noPersistent = std::getenv("MRN_GEMM_NO_PERSISTENT") != nullptr;
+  static const int persistMinTiles = std::getenv("MRN_GEMM_PERSIST_TILES") ? std::atoi(std::getenv("MRN_GEMM_PERSIST_TILES")) : 2 * kNumSMs;
+  const long tiles128 = (long)((M + BLOCK_M - 1) / BLOCK_M) * ((N + 127) / 128);
+  const bool persistent = !noPersistent && !batched && G == 1 && (p.colSums.empty() || (!aMN && !bMN)) && N >= 128 && tiles128 >= persistMinTiles && (splits == 1 || tiles128 >= 4 * kNumSMs);
+  if(persistent) {
+    BN = 128;
+    splits = 1;
+  }
 
   // bf16 operands: shadows written by the producers, the parameter-arena copy, or converted now
   const __nv_bfloat16* a16 = ensureShadow(h, p.A);
@@ -1995,6 +2236,7 @@ bool runBf16(GemmHandle h, const GemmProblem& p) {
   a.strideC = (size_t)M * N;
   a.alpha = p.alpha;
   a.beta = p.beta;
+  a.stamps = persistent ? g_stampBuffer : nullptr;  // null unless gemmDebugStamps() armed it
   a.kBlocksPerSplit = (a.kBlocks + splits - 1) / splits;
   splits = (a.kBlocks + a.kBlocksPerSplit - 1) / a.kBlocksPerSplit;
   a.splits = splits;
@@ -2012,7 +2254,25 @@ bool runBf16(GemmHandle h, const GemmProblem& p) {
   ProfileScope prof(2.0 * M * N * K * G * p.batches);
   a.spanMin = prof.spanMin;
   a.spanMax = prof.spanMax;
-  if(p.gate) {
+  if(persistent) {
+    TfMaps<1> tm;
+    tm.a[0] = tm3.a[0];
+    tm.b[0] = tm3.b[0];
+    if(p.gate && a.colSum[0])
+      launchBf16Persistent<false, false, true, true>(tm, a);
+    else if(p.gate)
+      launchBf16Persistent<false, false, true>(tm, a);
+    else if(a.colSum[0])
+      launchBf16Persistent<false, false, false, true>(tm, a);
+    else if(aMN && bMN)
+      launchBf16Persistent<true, true, false>(tm, a);
+    else if(aMN)
+      launchBf16Persistent<true, false, false>(tm, a);
+    else if(bMN)
+      launchBf16Persistent<false, true, false>(tm, a);
+    else
+      launchBf16Persistent<false, false, false>(tm, a);
+  } else if(p.gate) {
     TfMaps<1> tm;
     tm.a[0] = tm3.a[0];
     tm.b[0] = tm3.b[0];
@@ -2041,7 +2301,7 @@ bool runBf16(GemmHandle h, const GemmProblem& p) {
   }
   if(prof.on)
     prof.finish(std::to_string(M) + "," + std::to_string(N) + "," + std::to_string(K * G) + "," + std::to_string(p.batches) + "," + (aMN ? "T" : "N") + (bMN ? "N" : "T") + ","
-                + std::to_string(BN) + "," + std::to_string(splits) + "," + std::to_string(p.beta));
+                + std::to_string(persistent ? -BN : BN) + "," + std::to_string(splits) + "," + std::to_string(p.beta));
   return true;
 }
 
