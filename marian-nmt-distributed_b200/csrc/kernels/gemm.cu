@@ -795,6 +795,7 @@ struct TcArgs {
   int colSumLen;      // columns of one A operand
   const float* gate;  // GATE kernels: pre-activation h, same layout as C; the product is scaled by swish'(h)
   __nv_bfloat16* shadowC;  // != null: bf16 copy of the final C values (BF16S: C is itself a product operand later)
+  int tmaStore;            // bf16 kernels: 1 = epilogue leaves through TMA tensor stores, 2 = through TMA reduce-add (C += tile)
   unsigned long long* stamps;  // tuning aid: per-CTA %globaltimer stamps (5 per CTA), or null
   unsigned long long* spanMin;  // profiling: per-launch min(start) / max(end) over the CTAs, or null
   unsigned long long* spanMax;
@@ -802,6 +803,8 @@ struct TcArgs {
 
 template <int BN, bool GATE = false>
 __device__ __forceinline__ void epilogueTile(const TcArgs& a, uint32_t tmemBase, uint64_t* tmemFullBar, float* stage, int warp, int lane, int m0, int n0, int batch, int split, uint32_t parity = 0);
+template <int BN, bool GATE = false>
+__device__ __forceinline__ void epilogueTileTma(const TcArgs& a, const CUtensorMap* tmC, uint32_t tmemBase, uint64_t* tmemFullBar, uint8_t* sbuf, int warp, int lane, int m0, int n0, int batch, int split, uint32_t parity = 0);
 
 template <int BN, int STAGES>
 struct TcSmem {
@@ -1127,6 +1130,99 @@ __device__ __forceinline__ void epilogueTile(const TcArgs& a, uint32_t tmemBase,
   }
 }
 
+
+// ---- epilogue through TMA tensor stores -------------------------------------------------------------
+// The register -> staging -> 128-bit global store epilogue above costs ~1 us per 32-column block and warp
+// (measured with the stamps of the persistent kernel: 4 us per 128 x 128 tile against a 2 us main loop).
+// Here a lane keeps ITS ROW of the block (tcgen05.ld 32x32b: lane = row, registers = 32 columns), applies
+// alpha / bias (/ swish'(H)), writes the row into a 4 KB shared-memory tile in the 128-byte-swizzled layout
+// the C tensor map describes (16-byte chunk j of row r at j ^ (r % 8): conflict free), and ONE thread hands
+// the tile to the copy engine: cp.async.bulk.tensor store, or cp.reduce.async.bulk.tensor .add for C += tile
+// (accumulating products and split-K partial sums - no read of the old C by the SM at all).  The copy engine
+// clips rows / columns beyond the tensor, so ragged tiles need no special path.  Two tiles per warp alternate.
+__device__ __forceinline__ void tmaStoreTile(const CUtensorMap* map, const void* src, int c0, int c1, int c2, bool reduceAdd) {
+  if(reduceAdd)
+    asm volatile("cp.reduce.async.bulk.tensor.3d.global.shared::cta.add.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"((uint64_t)map), "r"(smemAddr(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+  else
+    asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"((uint64_t)map), "r"(smemAddr(src)), "r"(c0), "r"(c1), "r"(c2) : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+
+__device__ __forceinline__ void tmemLoad32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]),
+        "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]),
+        "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]),
+        "=r"(r[31])
+      : "r"(taddr));
+}
+
+// The 32-column blocks of a tile are software pipelined: the TMEM read of block c + 1 is in flight while block c is
+// scaled, written to shared memory and handed to the copy engine (fully unrolled: two register sets alternate).
+template <int BN, bool GATE>
+__device__ __forceinline__ void epilogueTileTma(const TcArgs& a, const CUtensorMap* tmC, uint32_t tmemBase, uint64_t* tmemFullBar, uint8_t* sbuf, int warp, int lane, int m0, int n0, int batch, int split, uint32_t parity) {
+  static_assert(!GATE, "the gated epilogue takes the staging path");
+  constexpr int NB = BN / 32;
+  const int q = warp & 3;
+  const int rowBase = m0 + q * 32;
+  const bool addBias = a.bias != nullptr && split == 0;
+  const bool reduceAdd = a.tmaStore == 2;
+  const uint32_t tbase = tmemBase + ((uint32_t)(q * 32) << 16);
+
+  mbarWait(tmemFullBar, parity);
+  tcgenFenceAfter();
+  if(rowBase >= a.M)
+    return;
+  uint32_t r[2][32];
+  tmemLoad32(tbase, r[0]);
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for(int c = 0; c < NB; ++c) {
+    const int col0 = n0 + c * 32;
+    if(col0 < a.N) {  // (warp-uniform)
+      if(c + 1 < NB && col0 + 32 < a.N)
+        tmemLoad32(tbase + (uint32_t)((c + 1) * 32), r[(c + 1) & 1]);  // lands while this block is processed
+      // the tile buffer used two blocks ago must have been read by the copy engine
+      uint8_t* tile = sbuf + (c & 1) * 4096;
+      if(c >= 2) {
+        if(lane == 0)
+          asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+        __syncwarp();
+      }
+      const uint32_t rowAddr = smemAddr(tile) + (uint32_t)lane * 128u;
+#pragma unroll
+      for(int j = 0; j < 8; ++j) {
+        float4 v;
+        v.x = a.alpha * __uint_as_float(r[c & 1][4 * j]);
+        v.y = a.alpha * __uint_as_float(r[c & 1][4 * j + 1]);
+        v.z = a.alpha * __uint_as_float(r[c & 1][4 * j + 2]);
+        v.w = a.alpha * __uint_as_float(r[c & 1][4 * j + 3]);
+        if(addBias && col0 + 4 * j < a.N) {
+          const float4 b = __ldg(reinterpret_cast<const float4*>(a.bias + col0 + 4 * j));
+          v.x += b.x;
+          v.y += b.y;
+          v.z += b.z;
+          v.w += b.w;
+        }
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(rowAddr + (uint32_t)((j ^ (lane & 7)) << 4)), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy writes -> visible to the copy engine
+      __syncwarp();
+      if(lane == 0)
+        tmaStoreTile(tmC, tile, col0, rowBase, batch, reduceAdd);
+      if(c + 1 < NB && col0 + 32 < a.N)
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    }
+  }
+  // shared memory must stay intact until the copy engine has read the last tiles
+  if(lane == 0)
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  __syncwarp();
+}
+
 // Operand descriptors of a launch.  G > 1: K-grouped product C = sum_g A_g op(B_g) over G separate
 // tensor pairs (the input gradient of several projections of the same tensor: dX = dQ Wq^T + dK Wk^T +
 // dV Wv^T is ONE launch whose CTAs walk 3 x K/32 k-blocks instead of three dependent launches).
@@ -1134,6 +1230,7 @@ template <int G>
 struct alignas(64) TfMaps {
   CUtensorMap a[G];
   CUtensorMap b[G];
+  CUtensorMap c;  // fp32 output tile map {32 columns, 32 rows}, SWIZZLE_128B (bf16 kernels, TcArgs::tmaStore)
 };
 
 template <int BN, int STAGES, bool A_MN, bool B_MN, int G = 1, bool GATE = false>
@@ -1840,7 +1937,10 @@ __global__ void __launch_bounds__(192, GATE ? 2 : 1) gGemmBf16(const __grid_cons
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
-    epilogueTile<BN, GATE>(a, tmemBase, tmemFullBar, stage, warp, lane, m0, n0, batch, split);
+    if(!GATE && a.tmaStore)  // (the tile buffers overlay the first ring stages: dead once the accumulator is complete)
+      epilogueTileTma<BN, false>(a, &tm.c, tmemBase, tmemFullBar, smem + (warp - 2) * 8192, warp, lane, m0, n0, batch, split);
+    else
+      epilogueTile<BN, GATE>(a, tmemBase, tmemFullBar, stage, warp, lane, m0, n0, batch, split);
   }
 
   tcgenFenceBefore();
@@ -1871,7 +1971,7 @@ struct BfPersistSmem {
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGING_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int STAGING_BYTES = 4 * 32 * kStagePitch * 4;
+  static constexpr int STAGING_BYTES = 4 * 8192;  // per epilogue warp: two 4 KB tiles for the TMA stores (>= the 32 x kStagePitch floats of the plain epilogue)
   static constexpr int BAR_OFFSET = STAGING_OFFSET + STAGING_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;
 };
@@ -2048,7 +2148,10 @@ __global__ void __launch_bounds__(SUMS ? 256 : 192, 1) gGemmBf16Persistent(const
         mbarWait(tmemFullBar + buf, use & 1u);
         stamp[2 + 6 * j + 3] = now();
       }
-      epilogueTile<BN, GATE>(a, tmemBase + buf * BN, tmemFullBar + buf, stage, warp, lane, m0, n0, 0, 0, use & 1u);
+      if(!GATE && a.tmaStore)
+        epilogueTileTma<BN, false>(a, &tm.c, tmemBase + buf * BN, tmemFullBar + buf, smem + L::STAGING_OFFSET + (warp - 2) * 8192, warp, lane, m0, n0, 0, 0, use & 1u);
+      else
+        epilogueTile<BN, GATE>(a, tmemBase + buf * BN, tmemFullBar + buf, stage, warp, lane, m0, n0, 0, 0, use & 1u);
       tcgenFenceBefore();
       __syncwarp();
       if(lane == 0)
@@ -2123,6 +2226,19 @@ void launchBf16Tile(int BN, const TfMaps<G>& tm, const TcArgs& a, int batches) {
     launchBf16Maps<128, 3, A_MN, B_MN, G, GATE>(tm, a, batches);
   else
     launchBf16Maps<64, 4, A_MN, B_MN, G, GATE>(tm, a, batches);
+}
+
+// fp32 output [batches, rows, cols] as 32 x 32 tiles, 128-byte swizzle (rows of a tile = 128 bytes)
+CUtensorMap makeTensorMapC(GemmHandle h, const float* base, uint64_t cols, uint64_t rows, uint64_t batches) {
+  CUtensorMap map;
+  cuuint64_t gdim[3] = {cols, rows, batches};
+  cuuint64_t gstride[2] = {cols * sizeof(float), cols * rows * sizeof(float)};
+  cuuint32_t box[3] = {32, 32, 1};
+  cuuint32_t estride[3] = {1, 1, 1};
+  CUresult rc = h->encodeTiled(&map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, gdim, gstride, box, estride, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                               CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  ABORT_IF(rc != CUDA_SUCCESS, "cuTensorMapEncodeTiled (fp32 output) failed with code", (int)rc);
+  return map;
 }
 
 // a bf16 operand (row pitch = cols elements) can be described by a tensor map
@@ -2250,6 +2366,12 @@ bool runBf16(GemmHandle h, const GemmProblem& p) {
   }
   // C itself a later product operand (and written here in one piece): leave its bf16 copy as well
   a.shadowC = a.atomicOut ? nullptr : shadow::produce(p.C);
+  // epilogue through the copy engine: plain store, or reduce-add for C += tile (beta = 1, split-K partial sums)
+  static const bool noTmaStore = std::getenv("MRN_GEMM_NO_TMA_STORE") != nullptr;
+  if(!noTmaStore && !a.shadowC && !p.gate && (N & 3) == 0 && (((uintptr_t)a.C) & 15) == 0 && (p.beta == 0.f || p.beta == 1.f || a.atomicOut)) {
+    a.tmaStore = (a.atomicOut || p.beta == 1.f) ? 2 : 1;
+    tm3.c = makeTensorMapC(h, a.C, (uint64_t)N, (uint64_t)M, (uint64_t)p.batches);
+  }
 
   ProfileScope prof(2.0 * M * N * K * G * p.batches);
   a.spanMin = prof.spanMin;
@@ -2258,6 +2380,7 @@ bool runBf16(GemmHandle h, const GemmProblem& p) {
     TfMaps<1> tm;
     tm.a[0] = tm3.a[0];
     tm.b[0] = tm3.b[0];
+    tm.c = tm3.c;
     if(p.gate && a.colSum[0])
       launchBf16Persistent<false, false, true, true>(tm, a);
     else if(p.gate)
@@ -2276,6 +2399,7 @@ bool runBf16(GemmHandle h, const GemmProblem& p) {
     TfMaps<1> tm;
     tm.a[0] = tm3.a[0];
     tm.b[0] = tm3.b[0];
+    tm.c = tm3.c;
     launchBf16Tile<false, false, 1, true>(BN, tm, a, 1);
   } else if(G == 3) {
     launchBf16Tile<false, false, 3>(BN, tm3, a, 1);
@@ -2285,11 +2409,13 @@ bool runBf16(GemmHandle h, const GemmProblem& p) {
       tm2.a[g] = tm3.a[g];
       tm2.b[g] = tm3.b[g];
     }
+    tm2.c = tm3.c;
     launchBf16Tile<false, false, 2>(BN, tm2, a, 1);
   } else {
     TfMaps<1> tm;
     tm.a[0] = tm3.a[0];
     tm.b[0] = tm3.b[0];
+    tm.c = tm3.c;
     if(aMN && bMN)
       launchBf16Tile<true, true, 1>(BN, tm, a, p.batches);
     else if(aMN)
