@@ -1006,6 +1006,7 @@ __device__ __forceinline__ void epilogueTile(const TcArgs& a, uint32_t tmemBase,
   const int sub = lane >> 3;      // row within a group of 4
   const int cq = (lane & 7) * 4;  // first of this lane's 4 columns
   const bool readOld = a.beta != 0.f && !a.atomicOut;
+  const uint32_t stageAddr = smemAddr(stage);
 
   auto isVec = [&](int col0) { return col0 + 32 <= a.N && ((a.ldc & 3) == 0) && ((((uintptr_t)(Cb + col0)) & 15) == 0); };
   float4 oldv[8];
@@ -1052,10 +1053,11 @@ __device__ __forceinline__ void epilogueTile(const TcArgs& a, uint32_t tmemBase,
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
     {
-      float4* srow = reinterpret_cast<float4*>(stage + lane * kStagePitch);
+      // explicit shared-space accesses: through the generic pointer these compile to generic ST.E / LD.E
+      const uint32_t srow = stageAddr + (uint32_t)(lane * kStagePitch * 4);
 #pragma unroll
       for(int j = 0; j < 8; ++j)
-        srow[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]), __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(srow + 16u * j), "r"(r[4 * j]), "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3]) : "memory");
     }
     __syncwarp();
     const int ncols = min(32, a.N - col0);
@@ -1066,7 +1068,8 @@ __device__ __forceinline__ void epilogueTile(const TcArgs& a, uint32_t tmemBase,
       float4 outv[8];
 #pragma unroll
       for(int i = 0; i < 8; ++i) {
-        float4 acc = *reinterpret_cast<const float4*>(stage + (i * 4 + sub) * kStagePitch + cq);
+        float4 acc;
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(acc.x), "=f"(acc.y), "=f"(acc.z), "=f"(acc.w) : "r"(stageAddr + (uint32_t)(((i * 4 + sub) * kStagePitch + cq) * 4)));
         float4 v;
         v.x = a.alpha * acc.x + bq.x;
         v.y = a.alpha * acc.y + bq.y;
