@@ -409,9 +409,11 @@ public:
     }
     hashMap_[hash].push_back(node);
     node->setId(count_++);
-    if(!node->isView())  // a view hands its consumers through to the node it aliases
+    if(!node->isView()) {  // a view hands its consumers through to the node it aliases
+      size_t i = 0;
       for(auto& child : node->children())
-        child->addConsumer();
+        child->addConsumer(node->readsChildViaProduct(i++));
+    }
 
     nodesForward_.push_back(node);
     if(!inferenceOnly_ && node->trainable()) {

@@ -85,8 +85,11 @@ struct Chainable {
   // when they are added to the tape: an adjoint shadow is only requested for nodes with exactly one
   // consumer, i.e. one writer of the adjoint.  Views forward all three to the node they alias.
   virtual void requestValShadow() {}
-  virtual void addConsumer() {}
+  // `viaProduct`: the consumer reads this node's value only as a tensor-core product operand (through the bf16 copy)
+  virtual void addConsumer(bool /*viaProduct*/ = false) {}
   virtual bool isView() const { return false; }
+  // child i of this node is read only as a product operand (Affine / Dot nodes: their two matrix arguments)
+  virtual bool readsChildViaProduct(size_t /*i*/) const { return false; }
 };
 
 class Node : public Chainable<Tensor>, public std::enable_shared_from_this<Node> {
@@ -107,6 +110,7 @@ protected:
   bool wantValShadow_{false};   // a product reads val_: producers leave a bf16 copy (BF16S GEMM mode)
   bool wantAdjShadow_{false};   // this node is a product: its adjoint is an operand of the backward products
   int consumers_{0};            // nodes on the tape that have this node as a child
+  int productConsumers_{0};     // ... of which read the value only as a product operand
 
 public:
   Node(Ptr<ExpressionGraph> graph, const Shape& shape) : graph_(graph), shape_(shape) {}
@@ -186,7 +190,11 @@ public:
     if(val_)
       val_->memory()->shadowWanted = true;
   }
-  virtual void addConsumer() { ++consumers_; }
+  virtual void addConsumer(bool viaProduct = false) {
+    ++consumers_;
+    if(viaProduct)
+      ++productConsumers_;
+  }
 
   Ptr<Backend> getBackend();
 

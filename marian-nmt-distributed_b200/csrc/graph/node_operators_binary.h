@@ -55,6 +55,7 @@ public:
   }
 
   NodeOps forwardOps() { return {NodeOp(prod(val_, child(0)->val(), child(1)->val(), transA_, transB_, 0.f))}; }
+  bool readsChildViaProduct(size_t) const { return true; }
 
   NodeOps backwardOps() {
     // D = adj, A = child0, B = child1
@@ -127,6 +128,18 @@ struct AffineNodeOp : public NaryNodeOp {
   bool inputGradDone_{false};
   bool biasGradDone_{false};  // the input-gradient product also delivered the column sums of adj (= the bias gradient)
   bool fuseBias() { return child(2)->trainable() && ProdColumnSumsFusable(getBackend()->getGemmHandle(), adj_); }
+  bool readsChildViaProduct(size_t i) const { return i < 2; }
+  // BF16S GEMM mode: the adjoint of a projection with ONE consumer is written once and read only by this node's own
+  // backward products (input gradient, weight gradient, bias gradient from the streamed bf16 tiles) - its writer may
+  // then leave just the bf16 copy (kernels/shadow.h: shadowOnly).  Needs every one of those products on the direct
+  // bf16 path (16-byte rows) and both gradients actually taken from the products.
+  void set_zero_adjoint() {
+    const bool fresh = !adj_;
+    Node::set_zero_adjoint();
+    if(fresh && adj_ && consumers_ == 1 && getGemmMode(getBackend()->getGemmHandle()) == GemmMode::BF16S && child(0)->trainable() && child(1)->trainable()
+       && fuseBias() && (child(0)->shape()[-1] % 8) == 0 && (shape_[-1] % 8) == 0)
+      adj_->memory()->shadowOnly = true;
+  }
   void fuseBackward(const std::vector<Expr>& upcoming) {
     if(inputGradDone_ || !adj_ || !child(0)->trainable())
       return;
@@ -191,8 +204,10 @@ struct AffineNodeOp : public NaryNodeOp {
             })),
             NodeOp(offCriticalPath(child(1), [&] { Prod(getBackend()->getGemmHandle(), child(1)->grad(), child(0)->val(), adj_, true, false, 1.0); })),
             NodeOp(offCriticalPath(child(2), [&] {
-              if(!biasGradDone_)
+              if(!biasGradDone_) {
+                ABORT_IF(adj_->memory()->fp32Skipped, "affine: bias gradient needs the fp32 adjoint, but only its bf16 copy was written");
                 Add(_1, child(2)->grad(), adj_);
+              }
             }))};
   }
   const std::string type() { return "affine"; }

@@ -143,10 +143,24 @@ struct SwishNodeOp : public UnaryNodeOp {
   // set by the consumer that delivered the gradient of the pre-activation itself
   // (AffineNodeOp::fuseBackward: swish' applied in the epilogue of its input-gradient product)
   bool backwardDone_{false};
+  // BF16S GEMM mode: when every consumer of swish(x) is a product, only its bf16 copy is written (the fp32 tensor
+  // is half of the feed-forward block's forward write traffic and nobody reads it); the unfused backward pass then
+  // recomputes f(x) = x sigma(x) from x instead of reading it.
+  size_t allocate() {
+    size_t n = Node::allocate();
+    if(val_ && wantValShadow_ && consumers_ > 0 && productConsumers_ == consumers_ && (shape_[-1] % 8) == 0)
+      val_->memory()->shadowOnly = true;
+    return n;
+  }
   NodeOps backwardOps() {
     using namespace functional;
     // dJ/dx += dJ/df * (f(x) + sigma(x) * (1 - f(x)))
-    return {NodeOp(if(!backwardDone_) Add(_1 * (_3 + logit(_2) * (1.f - _3)), child(0)->grad(), adj_, child(0)->val(), val_))};
+    return {NodeOp(if(!backwardDone_) {
+      if(val_->memory()->fp32Skipped)
+        Add(_1 * (_2 * logit(_2) + logit(_2) * (1.f - _2 * logit(_2))), child(0)->grad(), adj_, child(0)->val());
+      else
+        Add(_1 * (_3 + logit(_2) * (1.f - _3)), child(0)->grad(), adj_, child(0)->val(), val_);
+    })};
   }
   const std::string type() { return "swish"; }
 };
@@ -490,7 +504,7 @@ public:
   void set_zero_adjoint() { reshapee_->set_zero_adjoint(); }
   // value and adjoint alias the reshapee's: shadow requests and consumer counts belong there
   void requestValShadow() { reshapee_->requestValShadow(); }
-  void addConsumer() { reshapee_->addConsumer(); }
+  void addConsumer(bool viaProduct = false) { reshapee_->addConsumer(viaProduct); }
   bool isView() const { return true; }
 
   Tensor& val() {

@@ -1106,7 +1106,7 @@ __global__ void __launch_bounds__(128) gAttentionBackwardWarp(float* __restrict_
       for(int n = 0; n < 8; ++n)
         mmaSplit<X3>(o[n], af, ahi, kp[(n * 8) ^ cE], kp[64 + ((n * 8) ^ cO)]);
     }
-  storeStrip(iLo < g.Tq ? dq + offQ + (size_t)iLo * d : nullptr, iHi < g.Tq ? dq + offQ + (size_t)iHi * d : nullptr, o, 8, t, accQ != 0,
+  storeStrip((dq && iLo < g.Tq) ? dq + offQ + (size_t)iLo * d : nullptr, (dq && iHi < g.Tq) ? dq + offQ + (size_t)iHi * d : nullptr, o, 8, t, accQ != 0,
              (dqS && iLo < g.Tq) ? dqS + offQ + (size_t)iLo * d : nullptr, (dqS && iHi < g.Tq) ? dqS + offQ + (size_t)iHi * d : nullptr);
   __syncthreads();  // barrier A2: K is dead, the P tile is complete
 
@@ -1146,7 +1146,7 @@ __global__ void __launch_bounds__(128) gAttentionBackwardWarp(float* __restrict_
     }
     float* dst = pass == 0 ? dv : dk_;
     __nv_bfloat16* dstS = pass == 0 ? dvS : dkS;
-    storeStrip(iLo < g.Tk ? dst + offK + (size_t)iLo * d : nullptr, iHi < g.Tk ? dst + offK + (size_t)iHi * d : nullptr, o, 8, t, (pass == 0 ? accV : accK) != 0,
+    storeStrip((dst && iLo < g.Tk) ? dst + offK + (size_t)iLo * d : nullptr, (dst && iHi < g.Tk) ? dst + offK + (size_t)iHi * d : nullptr, o, 8, t, (pass == 0 ? accV : accK) != 0,
                (dstS && iLo < g.Tk) ? dstS + offK + (size_t)iLo * d : nullptr, (dstS && iHi < g.Tk) ? dstS + offK + (size_t)iHi * d : nullptr);
   }
 }
@@ -1498,11 +1498,15 @@ void MultiHeadAttentionGrad(Tensor dq, Tensor dk, Tensor dv, const Tensor adj, c
     __nv_bfloat16* dqS = (!accQ && distinct) ? shadow::produce(dq) : nullptr;
     __nv_bfloat16* dkS = (!accK && distinct) ? shadow::produce(dk) : nullptr;
     __nv_bfloat16* dvS = (!accV && distinct) ? shadow::produce(dv) : nullptr;
+    // shadow-only adjoints (all their readers are products): the fp32 strips are not written at all
+    float* dqP = shadow::fp32Target(dq, dqS);
+    float* dkP = shadow::fp32Target(dk, dkS);
+    float* dvP = shadow::fp32Target(dv, dvS);
     if(exact)
-      launchPdl(gAttentionBackwardWarp<true>, dim3(g.B * g.H), dim3(128), smemW, cudaStreamOfEngine(), dq->data(), dk->data(), dv->data(), (const float*)adj->data(), (const float*)probs->data(),
+      launchPdl(gAttentionBackwardWarp<true>, dim3(g.B * g.H), dim3(128), smemW, cudaStreamOfEngine(), dqP, dkP, dvP, (const float*)adj->data(), (const float*)probs->data(),
                 (const float*)q->data(), (const float*)k->data(), (const float*)v->data(), g, R, (int)accQ, (int)accK, (int)accV, dqS, dkS, dvS);
     else
-      launchPdl(gAttentionBackwardWarp<false>, dim3(g.B * g.H), dim3(128), smemW, cudaStreamOfEngine(), dq->data(), dk->data(), dv->data(), (const float*)adj->data(), (const float*)probs->data(),
+      launchPdl(gAttentionBackwardWarp<false>, dim3(g.B * g.H), dim3(128), smemW, cudaStreamOfEngine(), dqP, dkP, dvP, (const float*)adj->data(), (const float*)probs->data(),
                 (const float*)q->data(), (const float*)k->data(), (const float*)v->data(), g, R, (int)accQ, (int)accK, (int)accV, dqS, dkS, dvS);
     CUDA_LAUNCH_CHECK();
     return;

@@ -115,7 +115,8 @@ __global__ void __launch_bounds__(256) gElementwise(Functor f, float* __restrict
       } else {
         q = make_float4(r[0], r[1], r[2], r[3]);
       }
-      *reinterpret_cast<float4*>(o) = q;
+      if(out)  // (null: shadow-only output, see shadow::fp32Target)
+        *reinterpret_cast<float4*>(o) = q;
       shadow::store4(outShadow, (size_t)row * g.cols + c, q);  // bf16 copy when `out` feeds a tensor-core product (BF16S)
     } else {
 #pragma unroll
@@ -376,10 +377,12 @@ void Element(Functor functor, Tensor out, Tensors... tensors) {
   auto stream = cudaStreamOfEngine();
   // every element of `out` is (re)written: the vector kernels also leave its bf16 shadow when one is wanted
   __nv_bfloat16* osh = vec ? shadow::produce(out) : nullptr;
+  // a shadow-only output (all readers are products) of a functor that does not read `out`: no fp32 stores
+  float* outp = (osh && !functional::Reads<Functor, 1>::value) ? shadow::fp32Target(out, osh) : out->data();
   if(vec && !broadcast)
-    launchPdl(ew::gElementwise<K, 0, true, Functor, true>, dim3(grid), dim3(256), 0, stream, functor, out->data(), ops, g, 1.f, osh);
+    launchPdl(ew::gElementwise<K, 0, true, Functor, true>, dim3(grid), dim3(256), 0, stream, functor, outp, ops, g, 1.f, osh);
   else if(vec)
-    launchPdl(ew::gElementwise<K, 0, true, Functor>, dim3(grid), dim3(256), 0, stream, functor, out->data(), ops, g, 1.f, osh);
+    launchPdl(ew::gElementwise<K, 0, true, Functor>, dim3(grid), dim3(256), 0, stream, functor, outp, ops, g, 1.f, osh);
   else
     launchPdl(ew::gElementwise<K, 0, false, Functor>, dim3(grid), dim3(256), 0, stream, functor, out->data(), ops, g, 1.f, osh);
   CUDA_LAUNCH_CHECK();

@@ -238,6 +238,21 @@ __nv_bfloat16* produce(const Tensor& t) {
   m.shadowValid = true;
   return (__nv_bfloat16*)m.shadow;
 }
+namespace {
+bool g_skipFp32 = std::getenv("MRN_SHADOW_KEEP_FP32") == nullptr;
+}
+void setSkipFp32(bool on) {
+  g_skipFp32 = on && std::getenv("MRN_SHADOW_KEEP_FP32") == nullptr;
+}
+float* fp32Target(const Tensor& t, const __nv_bfloat16* producedShadow) {
+  MemoryPiece& m = *t->memory();
+  if(producedShadow && g_skipFp32 && m.shadowOnly) {
+    m.fp32Skipped = true;
+    m.lazyZero = false;
+    return nullptr;
+  }
+  return t->data();
+}
 }  // namespace shadow
 
 void gemmInvalidateCache(GemmHandle h) {
@@ -259,6 +274,9 @@ void gemmSetStableRange(GemmHandle h, const void* lo, size_t bytes) {
     h->paramShadow = (__nv_bfloat16*)device::mallocDevice(h->paramShadowElems * sizeof(__nv_bfloat16) + 1024);
     h->paramFresh = false;
   }
+}
+void gemmAllowShadowOnly(GemmHandle, bool allow) {
+  shadow::setSkipFp32(allow);
 }
 void* gemmParamShadowFor(GemmHandle h, const Tensor& t) {
   if(h->mode != GemmMode::BF16S || !h->paramShadow || !t)
@@ -284,6 +302,13 @@ namespace {
 // wrote, or a conversion now (kept on the memory piece when `t` covers it, so that the forward value
 // converted here is found again by the weight-gradient product of the backward pass).
 const __nv_bfloat16* ensureShadow(GemmHandle h, const Tensor& t) {
+  {
+    MemoryPiece& m0 = *t->memory();
+    if(m0.fp32Skipped) {  // only the bf16 copy exists
+      ABORT_IF(!(m0.shadowValid && m0.shadow && m0.shadowGen == g_shadows.generation), "shadow-only tensor without a valid bf16 copy");
+      return (const __nv_bfloat16*)m0.shadow + (size_t)((const uint8_t*)t->rawData() - m0.data()) / sizeof(float);
+    }
+  }
   const float* src = t->data();  // materialises a lazily-zero tensor
   const uint8_t* p = (const uint8_t*)src;
   const size_t n = t->size();
@@ -1008,7 +1033,7 @@ __device__ __forceinline__ void epilogueTile(const TcArgs& a, uint32_t tmemBase,
   const bool readOld = a.beta != 0.f && !a.atomicOut;
   const uint32_t stageAddr = smemAddr(stage);
 
-  auto isVec = [&](int col0) { return col0 + 32 <= a.N && ((a.ldc & 3) == 0) && ((((uintptr_t)(Cb + col0)) & 15) == 0); };
+  auto isVec = [&](int col0) { return col0 + 32 <= a.N && ((a.ldc & 3) == 0) && (((((uintptr_t)(Cb + col0)) & 15) == 0) || !a.C); };
   float4 oldv[8];
   auto prefetchOld = [&](int col0) {
     if(!readOld || col0 >= a.N || rowBase >= a.M || !isVec(col0))
@@ -1101,7 +1126,8 @@ __device__ __forceinline__ void epilogueTile(const TcArgs& a, uint32_t tmemBase,
             // split-K partial sums: vector reduction straight into L2 (sm_90+)
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cp), "f"(outv[i].x), "f"(outv[i].y), "f"(outv[i].z), "f"(outv[i].w) : "memory");
           } else {
-            *reinterpret_cast<float4*>(cp) = outv[i];
+            if(a.C)  // (null: shadow-only output, every reader takes the bf16 copy)
+              *reinterpret_cast<float4*>(cp) = outv[i];
             shadow::store4(a.shadowC, (size_t)batch * a.strideC + (size_t)grow * a.ldc + col0 + cq, outv[i]);
           }
         }
@@ -1121,7 +1147,8 @@ __device__ __forceinline__ void epilogueTile(const TcArgs& a, uint32_t tmemBase,
           } else {
             if(a.beta != 0.f)
               v += a.beta * *cp;
-            *cp = v;
+            if(a.C)
+              *cp = v;
             shadow::store1(a.shadowC, (size_t)batch * a.strideC + (size_t)(rowBase + rloc) * a.ldc + col0 + lane, v);
           }
         }
@@ -1472,6 +1499,7 @@ void runSimt(const GemmProblem& p) {
 }
 
 void runTensorCore(GemmHandle h, const GemmProblem& p) {
+  ABORT_IF(p.A->memory()->fp32Skipped || p.B->memory()->fp32Skipped, "packed GEMM path reached with a shadow-only operand (only its bf16 copy exists)");
   const bool x3 = h->mode == GemmMode::BF16X3 || h->mode == GemmMode::TF32;  // (BF16S falls back to plain bf16)
   int M = p.transA ? p.colsA : p.rowsA;
   int K = p.transA ? p.rowsA : p.colsA;
@@ -2334,7 +2362,7 @@ bool runBf16(GemmHandle h, const GemmProblem& p) {
   }
 
   TcArgs a = {};
-  a.C = p.C->data();
+  a.C = p.C->rawData();  // (replaced below once split-K / shadow-only output are decided)
   a.bias = p.bias ? p.bias->data() : nullptr;
   a.M = M;
   a.N = N;
@@ -2367,11 +2395,13 @@ bool runBf16(GemmHandle h, const GemmProblem& p) {
     else
       Element(_1 = p.beta * _1, p.C);
   }
-  // C itself a later product operand (and written here in one piece): leave its bf16 copy as well
+  // C itself a later product operand (and written here in one piece): leave its bf16 copy as well - and ONLY the
+  // bf16 copy when nobody reads the fp32 tensor (shadow-only adjoints: the swish'-gated dH of the feed-forward block)
   a.shadowC = a.atomicOut ? nullptr : shadow::produce(p.C);
+  a.C = (a.shadowC && p.beta == 0.f) ? shadow::fp32Target(p.C, a.shadowC) : p.C->data();
   // epilogue through the copy engine: plain store, or reduce-add for C += tile (beta = 1, split-K partial sums)
   static const bool noTmaStore = std::getenv("MRN_GEMM_NO_TMA_STORE") != nullptr;
-  if(!noTmaStore && !a.shadowC && !p.gate && (N & 3) == 0 && (((uintptr_t)a.C) & 15) == 0 && (p.beta == 0.f || p.beta == 1.f || a.atomicOut)) {
+  if(!noTmaStore && !a.shadowC && !p.gate && a.C && (N & 3) == 0 && (((uintptr_t)a.C) & 15) == 0 && (p.beta == 0.f || p.beta == 1.f || a.atomicOut)) {
     a.tmaStore = (a.atomicOut || p.beta == 1.f) ? 2 : 1;
     tm3.c = makeTensorMapC(h, a.C, (uint64_t)N, (uint64_t)M, (uint64_t)p.batches);
   }

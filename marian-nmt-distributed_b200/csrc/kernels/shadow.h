@@ -29,6 +29,11 @@ bool enabled();
 void setEnabled(bool on);
 // Buffer to fill for `t` (whole memory piece, element i of the piece at [i]) or nullptr.
 __nv_bfloat16* produce(const Tensor& t);
+// After produce(t) returned a buffer: may the producer skip the fp32 stores of `t` altogether?  (The graph marked
+// the tensor shadowOnly: all its readers are products.)  Returns the fp32 destination to use - nullptr = skip.
+float* fp32Target(const Tensor& t, const __nv_bfloat16* producedShadow);
+// MRN_SHADOW_KEEP_FP32=1 (or setSkipFp32(false)) keeps every fp32 tensor complete (debugging, tensors fetched by the host)
+void setSkipFp32(bool on);
 
 #if defined(__CUDACC__)
 // 4 consecutive elements (8-byte store); sh may be null

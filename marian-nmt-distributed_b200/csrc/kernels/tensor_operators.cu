@@ -347,7 +347,8 @@ __global__ void gCrossEntropyPickBackward(float* __restrict__ out, const float* 
         g.y += a * (__expf(x.y - M) * invS - (float)(id + 1 == p));
         g.z += a * (__expf(x.z - M) * invS - (float)(id + 2 == p));
         g.w += a * (__expf(x.w - M) * invS - (float)(id + 3 == p));
-        o4[i] = g;
+        if(out)  // (null: shadow-only adjoint - its readers are the two products that take the bf16 copy)
+          o4[i] = g;
         shadow::store4(outShadow, (size_t)j * cols + id, g);  // bf16 copy of the logits adjoint for the two products that read it
       }
     } else {
@@ -394,7 +395,8 @@ void CrossEntropyPickBackward(Tensor out, Tensor adj, Tensor a, Tensor pick, Ten
   bool vec = rowsVectorizable(a->data(), out->data(), cols);
   auto st = cudaStreamOfEngine();
   __nv_bfloat16* osh = (assign && vec) ? shadow::produce(out) : nullptr;
-#define CE_BWD(W, V) launchPdl(gCrossEntropyPickBackward<W, V>, dim3(l.grid), dim3(l.block), 0, st, out->data(), (const float*)adj->data(), (const float*)a->data(), (const float*)pick->data(), rows, cols, assign, statsPtr, osh)
+  float* outp = shadow::fp32Target(out, osh);
+#define CE_BWD(W, V) launchPdl(gCrossEntropyPickBackward<W, V>, dim3(l.grid), dim3(l.block), 0, st, outp, (const float*)adj->data(), (const float*)a->data(), (const float*)pick->data(), rows, cols, assign, statsPtr, osh)
   if(l.warp) {
     if(vec) CE_BWD(true, true); else CE_BWD(true, false);
   } else {
@@ -693,7 +695,8 @@ __global__ void __launch_bounds__(32 * WARPS, 1) gLayerNormalizationGradWarp(flo
           v.z += o.z;
           v.w += o.w;
         }
-        *gx = v;
+        if(gradX)  // (null with assignX: shadow-only adjoint)
+          *gx = v;
         shadow::store4(gradXShadow, off + c, v);  // only handed in when this kernel is the adjoint's one writer
         accG[i].x += av[i].x * xh[i].x;
         accG[i].y += av[i].y * xh[i].y;
@@ -782,15 +785,16 @@ void LayerNormalizationGrad(Tensor gradX, Tensor gradGamma, Tensor gradBeta, Ten
       int assignRes = (gradResidual && gradResidual->takeLazyZero()) ? 1 : 0;
       float* grp = gradResidual ? gradResidual->data() : nullptr;
       __nv_bfloat16* gxs = assignX ? shadow::produce(gradX) : nullptr;
+      float* gxp = assignX ? shadow::fp32Target(gradX, gxs) : gradX->data();
       // few, fat blocks: every block ends with one 128-bit reduction per 4 columns for gamma and
       // beta; same-address reductions serialise in L2, so one block per SM is the sweet spot
       if(cols <= 512) {
         int grid = std::max(1, std::min((rows + 15) / 16, kNumSMs));
-        launchPdl(gLayerNormalizationGradWarp<4, 16>, dim3(grid), dim3(512), 0, st, gradX->data(), gradGamma->data(), gbp, (const float*)adj->data(), (const float*)y->data(), (const float*)x->data(),
+        launchPdl(gLayerNormalizationGradWarp<4, 16>, dim3(grid), dim3(512), 0, st, gxp, gradGamma->data(), gbp, (const float*)adj->data(), (const float*)y->data(), (const float*)x->data(),
                   (const float*)gamma->data(), bp, rows, cols, eps, assignX, rp, grp, assignRes, gxs);
       } else {
         int grid = std::max(1, std::min((rows + 15) / 16, kNumSMs));
-        launchPdl(gLayerNormalizationGradWarp<8, 8>, dim3(grid), dim3(256), 0, st, gradX->data(), gradGamma->data(), gbp, (const float*)adj->data(), (const float*)y->data(), (const float*)x->data(),
+        launchPdl(gLayerNormalizationGradWarp<8, 8>, dim3(grid), dim3(256), 0, st, gxp, gradGamma->data(), gbp, (const float*)adj->data(), (const float*)y->data(), (const float*)x->data(),
                   (const float*)gamma->data(), bp, rows, cols, eps, assignX, rp, grp, assignRes, gxs);
       }
       CUDA_LAUNCH_CHECK();

@@ -56,6 +56,9 @@ void gemmSetStableRange(GemmHandle, const void* ptr, size_t bytes);
 //       the bf16 copy of the WHOLE arena itself;
 //   gemmPrepareStep(h): before a forward pass / graph replay: refreshes the bf16 arena copy by one
 //       flat conversion pass if it is stale.  All three are no-ops in the other modes and on the oracle.
+// shadow-only tensors (kernels/shadow.h): allow = false keeps every fp32 tensor complete for this step (a step whose
+// logits / adjoints the host wants to read back)
+void gemmAllowShadowOnly(GemmHandle, bool allow);
 void* gemmParamShadowFor(GemmHandle, const Tensor& t);
 void gemmParamsUpdated(GemmHandle, bool shadowWritten);
 void gemmPrepareStep(GemmHandle);

@@ -39,6 +39,11 @@ public:
   mutable bool shadowWanted{false};
   mutable bool shadowValid{false};
   mutable uint32_t shadowGen{0};  // pool generation the buffer belongs to (stale buffers are ignored)
+  // shadowOnly: every reader of this tensor is a tensor-core product (graph analysis, see Node): a producer that
+  // writes the bf16 shadow may leave the fp32 bytes unwritten (half of the step's activation write traffic goes
+  // to fp32 tensors nobody reads).  fp32Skipped records that one did - fp32 readers must not appear after that.
+  mutable bool shadowOnly{false};
+  mutable bool fp32Skipped{false};
 
 private:
   uint8_t* data_;

@@ -67,6 +67,7 @@ public:
   void computeGradients(Ptr<data::CorpusBatch> batch, bool keepLogits = false) {
     device::setDevice((int)graph_->getDevice());
     gemmPrepareStep(graph_->getBackend()->getGemmHandle());  // BF16S mode: bf16 copy of the parameters up to date
+    gemmAllowShadowOnly(graph_->getBackend()->getGemmHandle(), !keepLogits);  // a kept step leaves every fp32 tensor readable
     auto key = batch->shapeKey();
     if(!keepLogits) {
       if(auto plan = replay_.find(key)) {

@@ -39,6 +39,7 @@ GemmMode getGemmMode(GemmHandle h) { return h->mode; }
 void gemmDebugStamps(unsigned long long*) {}
 void gemmInvalidateCache(GemmHandle) {}
 void gemmSetStableRange(GemmHandle, const void*, size_t) {}
+void gemmAllowShadowOnly(GemmHandle, bool) {}
 void* gemmParamShadowFor(GemmHandle, const Tensor&) { return nullptr; }
 void gemmParamsUpdated(GemmHandle, bool) {}
 void gemmPrepareStep(GemmHandle) {}
