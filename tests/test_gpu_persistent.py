@@ -50,7 +50,8 @@ print(json.dumps(out))
 def test_shadow_only_tensors_change_nothing(cuda):
     """Adjoints / activations whose only readers are products are written as bf16 copies only (kernels/shadow.h,
     shadowOnly).  With MRN_SHADOW_KEEP_FP32=1 every fp32 tensor is written as well: the arithmetic is the same, so
-    the costs of four updates must be IDENTICAL - eager and replayed, tiny model and Transformer-base 64 x 50."""
+    the costs of four updates must agree to the run-to-run noise of the atomic reductions (split-K, column sums):
+    exactly for the tiny model, 2e-5 for Transformer-base 64 x 50 - eager and replayed."""
     import json
 
     res = {}
@@ -61,4 +62,8 @@ def test_shadow_only_tensors_change_nothing(cuda):
         r = subprocess.run([sys.executable, "-c", SNIPPET % ROOT], cwd=ROOT, env=env, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
         res[keep] = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
-    assert res["0"] == res["1"], res
+    import numpy as np
+
+    for key in res["0"]:
+        assert np.allclose(res["0"][key], res["1"][key], rtol=2e-5, atol=0), (key, res["0"][key], res["1"][key])
+    assert res["0"]["tiny-false"] == res["1"]["tiny-false"], res
