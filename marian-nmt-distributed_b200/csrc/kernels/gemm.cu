@@ -827,7 +827,7 @@ struct TcArgs {
 };
 
 template <int BN, bool GATE = false>
-__device__ __forceinline__ void epilogueTile(const TcArgs& a, uint32_t tmemBase, uint64_t* tmemFullBar, float* stage, int warp, int lane, int m0, int n0, int batch, int split, uint32_t parity = 0);
+__device__ __forceinline__ void epilogueTile(const TcArgs& a, uint32_t tmemBase, uint64_t* tmemFullBar, float* stage, int warp, int lane, int m0, int n0, int batch, int split, uint32_t parity = 0, int cBegin = 0, int cEnd = BN);
 template <int BN, bool GATE = false>
 __device__ __forceinline__ void epilogueTileTma(const TcArgs& a, const CUtensorMap* tmC, uint32_t tmemBase, uint64_t* tmemFullBar, uint8_t* sbuf, int warp, int lane, int m0, int n0, int batch, int split, uint32_t parity = 0);
 
@@ -1022,7 +1022,8 @@ __device__ __forceinline__ float swishGrad(float h) {
 // GATE: C = beta C + (alpha acc + bias) o swish'(gate) - the backward pass of "affine after swish"
 // (dH = (dY W^T) o swish'(H)) without the intermediate adjoint and its element-wise kernel.
 template <int BN, bool GATE>
-__device__ __forceinline__ void epilogueTile(const TcArgs& a, uint32_t tmemBase, uint64_t* tmemFullBar, float* stage, int warp, int lane, int m0, int n0, int batch, int split, uint32_t parity) {
+__device__ __forceinline__ void epilogueTile(const TcArgs& a, uint32_t tmemBase, uint64_t* tmemFullBar, float* stage, int warp, int lane, int m0, int n0, int batch, int split, uint32_t parity, int cBegin, int cEnd) {
+  // [cBegin, cEnd): the 32-column blocks of the tile this warp handles (two warps may share a TMEM lane quarter)
   const int q = warp & 3;  // TMEM lane quarter this warp may access
   float* Cb = a.C + (size_t)batch * a.strideC;
   const float* Gb = GATE ? a.gate + (size_t)batch * a.strideC : nullptr;
@@ -1056,18 +1057,16 @@ __device__ __forceinline__ void epilogueTile(const TcArgs& a, uint32_t tmemBase,
     }
   };
 
-  prefetchOld(n0);
-  prefetchGate(n0);
+  prefetchOld(n0 + cBegin);
+  prefetchGate(n0 + cBegin);
   // bias of this lane's four columns in every 32-column block, requested before the accumulator wait (next to no
   // L1 under the maximal shared-memory carve-out: inside the loop each load is an exposed L2 round trip)
-  float4 biasv[BN / 32];
-#pragma unroll
-  for(int c = 0; c < BN / 32; ++c)
-    biasv[c] = (addBias && isVec(n0 + c * 32)) ? *reinterpret_cast<const float4*>(a.bias + n0 + c * 32 + cq) : make_float4(0.f, 0.f, 0.f, 0.f);
+  auto biasOf = [&](int col0) { return (addBias && col0 < a.N && isVec(col0)) ? *reinterpret_cast<const float4*>(a.bias + col0 + cq) : make_float4(0.f, 0.f, 0.f, 0.f); };
+  float4 bq = biasOf(n0 + cBegin);
   mbarWait(tmemFullBar, parity);
   tcgenFenceAfter();
-#pragma unroll
-  for(int c0 = 0; c0 < BN; c0 += 32) {
+#pragma unroll 1
+  for(int c0 = cBegin; c0 < cEnd; c0 += 32) {
     const int col0 = n0 + c0;
     if(col0 >= a.N || rowBase >= a.M)
       break;
@@ -1093,7 +1092,6 @@ __device__ __forceinline__ void epilogueTile(const TcArgs& a, uint32_t tmemBase,
     __syncwarp();
     const int ncols = min(32, a.N - col0);
     if(isVec(col0) && (!GATE || (((uintptr_t)(Gb + col0)) & 15) == 0)) {
-      const float4 bq = biasv[c0 / 32];
       float4 outv[8];
 #pragma unroll
       for(int i = 0; i < 8; ++i) {
@@ -1121,6 +1119,7 @@ __device__ __forceinline__ void epilogueTile(const TcArgs& a, uint32_t tmemBase,
       }
       prefetchOld(col0 + 32);  // next block's old values travel while this one is stored
       prefetchGate(col0 + 32);
+      bq = biasOf(col0 + 32);
 #pragma unroll
       for(int i = 0; i < 8; ++i) {
         int grow = rowBase + i * 4 + sub;
@@ -2013,7 +2012,9 @@ struct BfPersistSmem {
   static constexpr int B_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
   static constexpr int STAGING_OFFSET = STAGES * STAGE_BYTES;
-  static constexpr int STAGING_BYTES = 4 * 8192;  // per epilogue warp: two 4 KB tiles for the TMA stores (>= the 32 x kStagePitch floats of the plain epilogue)
+  // per epilogue warp: two 4 KB tiles for the TMA stores (>= the 32 x kStagePitch floats of the plain epilogue);
+  // five-stage rings leave room for the eight staging areas of the EPI = 8 variant
+  static constexpr int STAGING_BYTES = STAGES >= 6 ? 4 * 8192 : 8 * 32 * kStagePitch * 4 + 4096;
   static constexpr int BAR_OFFSET = STAGING_OFFSET + STAGING_BYTES;
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;
 };
@@ -2021,9 +2022,13 @@ struct BfPersistSmem {
 // SUMS: two more warps follow the ring and, on the tiles of the first tile column, add the column sums of the
 // (K-major) A tiles into a.colSum[0] - the bias gradient, as in the one-tile kernels (there the idle epilogue
 // warps do it; here they are busy with the previous tile).  They acknowledge every stage (emptyBar counts 3).
-template <int BN, int STAGES, bool A_MN, bool B_MN, bool GATE = false, bool SUMS = false>
-__global__ void __launch_bounds__(SUMS ? 256 : 192, 1) gGemmBf16Persistent(const __grid_constant__ TfMaps<1> tm, TcArgs a) {
+// EPI = 8: two epilogue warps per TMEM lane quarter, each takes half of the tile's columns (the gated epilogue
+// evaluates swish'(H) for every element: with four warps it is 4x the main loop).
+template <int BN, int STAGES, bool A_MN, bool B_MN, bool GATE = false, bool SUMS = false, int EPI = 4>
+__global__ void __launch_bounds__(64 + 32 * EPI + (SUMS ? 64 : 0), 1) gGemmBf16Persistent(const __grid_constant__ TfMaps<1> tm, TcArgs a) {
   typedef BfPersistSmem<BN, STAGES> L;
+  static_assert(EPI == 4 || EPI == 8, "four or eight epilogue warps");
+  static_assert(EPI * 32 * kStagePitch * 4 <= L::STAGING_BYTES, "staging area too small");
   extern __shared__ uint8_t smemRaw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smemRaw + 1023) & ~(uintptr_t)1023);
   uint64_t* fullBar = (uint64_t*)(smem + L::BAR_OFFSET);
@@ -2063,7 +2068,7 @@ __global__ void __launch_bounds__(SUMS ? 256 : 192, 1) gGemmBf16Persistent(const
     }
     for(int b = 0; b < 2; ++b) {
       mbarInit(tmemFullBar + b, 1);
-      mbarInit(tmemEmptyBar + b, 4);  // one arrival per epilogue warp
+      mbarInit(tmemEmptyBar + b, EPI);  // one arrival per epilogue warp
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -2146,10 +2151,10 @@ __global__ void __launch_bounds__(SUMS ? 256 : 192, 1) gGemmBf16Persistent(const
           stamp[2 + 6 * j + 2] = now();
       }
     }
-  } else if(SUMS && warp >= 6) {
-    // ---------------- column-sum warps (rows 64 (warp - 6) .. + 63 of every A tile of the first tile column) ----------------
+  } else if(SUMS && warp >= 2 + EPI) {
+    // ---------------- column-sum warps (rows 64 (warp - first) .. + 63 of every A tile of the first tile column) ----------------
     static_assert(!SUMS || !A_MN, "column sums read K-major A tiles");
-    const int rw = (warp - 6) * 64;
+    const int rw = (warp - (2 + EPI)) * 64;
     uint32_t it = 0;
     for(int tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
       const bool sumTile = tile < mTiles && a.colSum[0] != nullptr;  // tile column 0
@@ -2190,8 +2195,10 @@ __global__ void __launch_bounds__(SUMS ? 256 : 192, 1) gGemmBf16Persistent(const
         mbarWait(tmemFullBar + buf, use & 1u);
         stamp[2 + 6 * j + 3] = now();
       }
-      if(!GATE && a.tmaStore)
+      if(!GATE && EPI == 4 && a.tmaStore)
         epilogueTileTma<BN, false>(a, &tm.c, tmemBase + buf * BN, tmemFullBar + buf, smem + L::STAGING_OFFSET + (warp - 2) * 8192, warp, lane, m0, n0, 0, 0, use & 1u);
+      else if(EPI == 8)  // warps 2..5 take the first half of the columns, warps 6..9 the second
+        epilogueTile<BN, GATE>(a, tmemBase + buf * BN, tmemFullBar + buf, stage, warp, lane, m0, n0, 0, 0, use & 1u, warp < 6 ? 0 : BN / 2, warp < 6 ? BN / 2 : BN);
       else
         epilogueTile<BN, GATE>(a, tmemBase + buf * BN, tmemFullBar + buf, stage, warp, lane, m0, n0, 0, 0, use & 1u);
       tcgenFenceBefore();
@@ -2218,16 +2225,18 @@ __global__ void __launch_bounds__(SUMS ? 256 : 192, 1) gGemmBf16Persistent(const
 
 template <bool A_MN, bool B_MN, bool GATE, bool SUMS = false>
 void launchBf16Persistent(const TfMaps<1>& tm, const TcArgs& a) {
-  constexpr int BN = 128, STAGES = 6;
+  constexpr int BN = 128;
+  constexpr int EPI = GATE ? 8 : 4;      // the gated epilogue is compute heavy: eight warps
+  constexpr int STAGES = GATE ? 5 : 6;
   typedef BfPersistSmem<BN, STAGES> L;
   static bool configured = false;
   if(!configured) {
-    CUDA_CHECK(cudaFuncSetAttribute(gGemmBf16Persistent<BN, STAGES, A_MN, B_MN, GATE, SUMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    CUDA_CHECK(cudaFuncSetAttribute(gGemmBf16Persistent<BN, STAGES, A_MN, B_MN, GATE, SUMS, EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
     configured = true;
   }
   const int tiles = ((a.M + BLOCK_M - 1) / BLOCK_M) * ((a.N + BN - 1) / BN);
   dim3 grid(std::min(tiles, kNumSMs));
-  launchPdl(gGemmBf16Persistent<BN, STAGES, A_MN, B_MN, GATE, SUMS>, grid, dim3(SUMS ? 256 : 192), (size_t)L::TOTAL, cudaStreamOfEngine(), tm, a);
+  launchPdl(gGemmBf16Persistent<BN, STAGES, A_MN, B_MN, GATE, SUMS, EPI>, grid, dim3(64 + 32 * EPI + (SUMS ? 64 : 0)), (size_t)L::TOTAL, cudaStreamOfEngine(), tm, a);
 }
 
 // dims (innermost first): {inner, outer, batch}; box {64, boxOuter, 1}

@@ -9,16 +9,23 @@ pkg = graft.load_package(); lib = pkg.load()
 st = torch.cuda.Stream(); torch.cuda.set_stream(st); lib.set_stream(st.cuda_stream)
 g = lib.gemm(4)
 rs = np.random.RandomState(0)
-cases = [(3200, 512, 512, 2048, 0, 0, 0.0, "ffn up fwd"), (3200, 512, 512, 32000, 0, 0, 0.0, "logits fwd"), (3200, 512, 3200, 32000, 1, 0, 1.0, "logits dW")]
+cases = [(3200, 512, 2048, 512, 0, 1, 0.0, "ffn gated dH"), (3200, 512, 512, 2048, 0, 0, 0.0, "ffn up fwd"), (3200, 512, 512, 32000, 0, 0, 0.0, "logits fwd"), (3200, 512, 3200, 32000, 1, 0, 1.0, "logits dW")]
 for (ra, ca, rb, cb, tA, tB, beta, label) in cases:
     M = ca if tA else ra; N = rb if tB else cb
     A = lib.array(rs.standard_normal((ra, ca)).astype(np.float32)); B = lib.array(rs.standard_normal((rb, cb)).astype(np.float32)); C = lib.zeros((M, N))
+    gated = "gated" in label
+    H = lib.array(rs.standard_normal((M, N)).astype(np.float32)) if gated else None
+    def run():
+        if gated:
+            lib.call("mrn_prod_swish_grad_nt", g.h, C.t(), A.t(), B.t(), H.t(), beta)
+        else:
+            lib.call("mrn_prod", g.h, C.t(), A.t(), B.t(), tA, tB, beta, 1.0)
     stamps = torch.zeros(64 * 148, dtype=torch.int64, device="cuda")
     for _ in range(3):
-        lib.call("mrn_prod", g.h, C.t(), A.t(), B.t(), tA, tB, beta, 1.0)
+        run()
     torch.cuda.synchronize()
     lib.call("mrn_gemm_debug_stamps", stamps.data_ptr())
-    lib.call("mrn_prod", g.h, C.t(), A.t(), B.t(), tA, tB, beta, 1.0)
+    run()
     lib.call("mrn_gemm_debug_stamps", None)
     torch.cuda.synchronize()
     s = stamps.cpu().numpy().reshape(-1, 64).astype(np.float64)
