@@ -1,7 +1,17 @@
 // reference: src/models/model_factory.cpp:61-192
 #include "models/model_factory.h"
+// MRN_REFERENCE_MODELS (oracle/Makefile, target refmodels - TEST INFRASTRUCTURE): the encoder / decoder classes come
+// from the REFERENCE's own src/models/{transformer,s2s}.h, compiled where they lie against this repo's graph /
+// operator / layer / rnn API (their "marian.h" umbrella is redirected by oracle/ref_shims/marian.h).  That is the
+// north-star's "models compile unchanged" boundary as a build target; tests/test_reference_models.py runs both
+// model codes on the same batches and compares cost, logits and every gradient.
+#ifdef MRN_REFERENCE_MODELS
+#include MRN_REFERENCE_S2S_H
+#include MRN_REFERENCE_TRANSFORMER_H
+#else
 #include "models/s2s.h"
 #include "models/transformer.h"
+#endif
 
 namespace marian {
 namespace models {
