@@ -190,6 +190,19 @@ int mrn_trainer_set_batch(void* trainer, int batch_size, int src_len, const int6
  * both builds): padded = 0 dense / 1 padded+sorted.  Advances the corpus. */
 int mrn_trainer_next_synthetic_batch(void* trainer, int batch_size, int max_len_src, int max_len_trg, int padded, int split_rank, int split_n);
 
+/* Text corpus in front of the hot path (reference: Vocab src/data/vocab.cpp, Corpus src/data/corpus.cpp:30-230,
+ * BatchGenerator src/data/batch_generator.h:39-160): one text file per side, vocabularies as YAML maps word -> id
+ * ("</s>" = 0, "<unk>" = 1; NULL or "" = <corpus>.yml, created from the corpus by falling frequency if missing),
+ * options "mini-batch=64;maxi-batch=100;maxi-batch-sort=trg|src|none;mini-batch-words=0;max-length=50;
+ * max-length-crop=false;right-left=false;shuffle=true;seed=1234".  A host thread reads, sorts and assembles the
+ * mini-batches two ahead of the device.  next_corpus_batch makes the next mini-batch the current batch (this rank's
+ * split when nranks > 1); *has_batch = 0 marks the end of an epoch. */
+int mrn_trainer_open_corpus(void* trainer, const char* src_path, const char* trg_path, const char* vocab_src, const char* vocab_trg, const char* options);
+int mrn_trainer_next_corpus_batch(void* trainer, int* has_batch);
+/* the current batch as host arrays in the SubBatch layout (time-major [T, B]); side 0 = source, 1 = target;
+ * indices / mask may be NULL to query batch_size and width */
+int mrn_trainer_get_batch(void* trainer, int side, int64_t* indices, float* mask, size_t capacity, int* batch_size, int* width);
+
 /* forward + backward of the current batch (CUDA-graph replay after the first
  * occurrences of a shape).  Asynchronous. keep_logits != 0 keeps the logits node. */
 int mrn_trainer_compute_gradients(void* trainer, int keep_logits);

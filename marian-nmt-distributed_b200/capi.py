@@ -81,6 +81,9 @@ _SIGNATURES = {
     "mrn_trainer_destroy": [_V],
     "mrn_trainer_set_batch": [_V, _I, _I, _V, _V, _I, _V, _V],
     "mrn_trainer_next_synthetic_batch": [_V, _I, _I, _I, _I, _I, _I],
+    "mrn_trainer_open_corpus": [_V, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p],
+    "mrn_trainer_next_corpus_batch": [_V, ctypes.POINTER(_I)],
+    "mrn_trainer_get_batch": [_V, _I, _V, _V, _SZ, ctypes.POINTER(_I), ctypes.POINTER(_I)],
     "mrn_trainer_compute_gradients": [_V, _I],
     "mrn_trainer_update": [_V],
     "mrn_trainer_update_shard": [_V],
@@ -304,6 +307,25 @@ class Trainer:
 
     def next_synthetic_batch(self, batch_size, len_src, len_trg, padded=False, split_rank=0, split_n=1):
         self.lib._ck(self.lib.c.mrn_trainer_next_synthetic_batch(self.h, batch_size, len_src, len_trg, int(padded), split_rank, split_n))
+
+    def open_corpus(self, src_path, trg_path, vocab_src=None, vocab_trg=None, options=""):
+        enc = lambda x: None if x is None else str(x).encode()
+        self.lib._ck(self.lib.c.mrn_trainer_open_corpus(self.h, enc(src_path), enc(trg_path), enc(vocab_src), enc(vocab_trg), options.encode()))
+
+    def next_corpus_batch(self):
+        """Makes the next mini-batch of the text corpus current; False at the end of an epoch."""
+        has = ctypes.c_int()
+        self.lib._ck(self.lib.c.mrn_trainer_next_corpus_batch(self.h, ctypes.byref(has)))
+        return bool(has.value)
+
+    def get_batch(self, side):
+        """(indices [T, B] int64, mask [T, B] float32) of the current batch."""
+        b, w = ctypes.c_int(), ctypes.c_int()
+        self.lib._ck(self.lib.c.mrn_trainer_get_batch(self.h, side, None, None, 0, ctypes.byref(b), ctypes.byref(w)))
+        idx = np.empty((w.value, b.value), dtype=np.int64)
+        mask = np.empty((w.value, b.value), dtype=np.float32)
+        self.lib._ck(self.lib.c.mrn_trainer_get_batch(self.h, side, idx.ctypes.data, mask.ctypes.data, idx.size, ctypes.byref(b), ctypes.byref(w)))
+        return idx, mask
 
     def compute_gradients(self, keep_logits=False):
         self.lib._ck(self.lib.c.mrn_trainer_compute_gradients(self.h, int(keep_logits)))

@@ -9,6 +9,7 @@
 #include <string>
 
 #include "data/batch.h"
+#include "data/corpus.h"
 #include "kernels/tensor_operators.h"
 #include "training/checkpoint.h"
 #include "training/graph_group.h"
@@ -60,6 +61,7 @@ struct Trainer {
   Ptr<AsyncGraphGroup> async;
   Ptr<data::CorpusBatch> batch;
   Ptr<data::SyntheticCorpus> corpus;
+  Ptr<data::PrefetchingBatchGenerator> textBatches;  // mrn_trainer_open_corpus
   size_t replays{0};
 
   GradientWorker& worker() { return single ? single->worker() : (sync ? sync->worker() : async->worker()); }
@@ -433,6 +435,59 @@ int mrn_trainer_next_synthetic_batch(void* trainer, int B, int Ls, int Lt, int p
       t->batch = full->split(splitN)[splitRank];
     else
       t->batch = full;
+  });
+}
+
+// ---- text corpus in front of the hot path (data/corpus.h; reference src/data/{vocab,corpus}.cpp, batch_generator.h) ----
+int mrn_trainer_open_corpus(void* trainer, const char* srcPath, const char* trgPath, const char* vocabSrc, const char* vocabTrg, const char* options) {
+  return guarded([&] {
+    auto t = (Trainer*)trainer;
+    auto o = t->options->clone();
+    o->overwrite(Options(options ? options : ""));
+    std::vector<std::string> paths{srcPath, trgPath};
+    std::vector<std::string> vocabPaths{vocabSrc ? vocabSrc : "", vocabTrg ? vocabTrg : ""};
+    auto dims = t->options->get<std::vector<int>>("dim-vocabs");
+    std::vector<Ptr<data::Vocab>> vocabs;
+    for(size_t i = 0; i < 2; ++i) {
+      auto v = New<data::Vocab>();
+      int size = v->loadOrCreate(vocabPaths[i], paths[i], dims[i]);  // ids >= dim-vocabs[i] are dropped (-> <unk>), as in the reference
+      ABORT_IF(size > dims[i], "vocabulary", i, "has", size, "entries, the model was created with dim-vocabs", dims[i]);
+      vocabs.push_back(v);
+    }
+    t->textBatches = New<data::PrefetchingBatchGenerator>(New<data::Corpus>(paths, vocabs, o), o);
+  });
+}
+// *hasBatch = 0 at the end of an epoch (the generator restarts: the next call begins the next epoch)
+int mrn_trainer_next_corpus_batch(void* trainer, int* hasBatch) {
+  return guarded([&] {
+    auto t = (Trainer*)trainer;
+    ABORT_IF(!t->textBatches, "mrn_trainer_next_corpus_batch: call mrn_trainer_open_corpus first");
+    auto b = t->textBatches->next();
+    if(b) {
+      t->batch = t->nranks > 1 ? b->split(t->nranks)[t->rank] : b;
+      *hasBatch = 1;
+    } else {
+      t->textBatches->restart();
+      *hasBatch = 0;
+    }
+  });
+}
+// current batch as host arrays (time-major [T, B], the SubBatch layout); side 0 = source, 1 = target
+int mrn_trainer_get_batch(void* trainer, int side, int64_t* indices, float* mask, size_t capacity, int* batchSize, int* width) {
+  return guarded([&] {
+    auto t = (Trainer*)trainer;
+    ABORT_IF(!t->batch || side < 0 || side >= (int)t->batch->sets(), "mrn_trainer_get_batch: no such sub-batch");
+    auto sb = (*t->batch)[side];
+    *batchSize = (int)sb->batchSize();
+    *width = (int)sb->batchWidth();
+    size_t n = sb->batchSize() * sb->batchWidth();
+    if(indices && mask) {
+      ABORT_IF(capacity < n, "mrn_trainer_get_batch: buffer too small");
+      for(size_t i = 0; i < n; ++i) {
+        indices[i] = (int64_t)sb->indices()[i];
+        mask[i] = sb->mask()[i];
+      }
+    }
   });
 }
 
