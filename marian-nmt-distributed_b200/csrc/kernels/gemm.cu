@@ -2320,10 +2320,7 @@ bool runBf16(GemmHandle h, const GemmProblem& p) {
   const int kGroup = (K + BF_BLOCK_K - 1) / BF_BLOCK_K;
   const int kBlocksAll = G * kGroup;
 
-  // Tile width and split-K from an INGEST model (measured with the kernel stamps, profiles/gemm_timeline_r02.md): an SM
-  // takes operand bytes from L2 at ~64 B/clk (~122 KB/us) whatever the tile shape, and the tensor pipe waits for them.
-  // A launch therefore lasts about  fixed + (CTAs per SM) x (bytes one CTA streams) / 122 KB/us + its epilogue:
-  // 128-wide tiles stream 32 KB per k-block for twice the MACs of a 64-wide tile's 24 KB, but halve the CTA count.
+  // tile width / split-K: the cost model of the tf32 path (a k-block moves the same bytes here)
   int BN = 64, splits = 1;
   {
     const long mTiles = (M + BLOCK_M - 1) / BLOCK_M;
@@ -2335,12 +2332,12 @@ bool runBf16(GemmHandle h, const GemmProblem& p) {
       const int maxSplits = (batched || kBlocksAll < 16) ? 1 : std::min(32, kBlocksAll / 4);
       for(int sp = 1; sp <= maxSplits; ++sp) {
         const long ctas = tiles * sp;
-        const double perSm = (double)((ctas + kNumSMs - 1) / kNumSMs);
+        const double waves = (double)((ctas + 2 * kNumSMs - 1) / (2 * kNumSMs));
         const double kb = (double)((kBlocksAll + sp - 1) / sp);
-        const double stageKB = bn == 128 ? 32.0 : 24.0;
-        double cost = 2.5 + perSm * (kb * stageKB / 122.0) + (bn == 128 ? 1.8 : 1.0);
+        double cta = 3.0 + kb * (bn == 128 ? 0.333 : 0.25) + (bn == 128 ? 3.0 : 1.5);
+        double cost = waves * cta;
         if(sp > 1)
-          cost += 0.5 + 0.1 * sp + (p.beta == 1.f ? 0.0 : 3.0);  // reduce-add traffic; a memset when C is not accumulated into
+          cost += 3.0 + 0.3 * sp + (p.beta == 1.f ? 0.0 : 3.0);
         if(cost < best) {
           best = cost;
           BN = bn;

@@ -67,6 +67,14 @@ size_t lastCaptureKernelCount();
 void launchGraph(void* exec);
 void destroyGraph(void* exec);
 
+// ---- host-visible progress markers ------------------------------------------------------------
+// recordMarker(m): records "everything issued so far on currentStream()" into marker m (a fresh one when m is
+// null) and returns it; waitMarker(m) blocks the host until that point has been reached.  Used to keep the host
+// from refilling pinned staging that uploads of an earlier, still queued step have not read yet.
+void* recordMarker(void* marker);
+void waitMarker(void* marker);
+void freeMarker(void* marker);
+
 // ---- side stream: work off the critical path ---------------------------------
 // The backward sweep is a long dependency chain of small kernels; weight and bias gradients
 // hang off that chain (nothing reads them before the optimizer).  forkSide() routes the engine

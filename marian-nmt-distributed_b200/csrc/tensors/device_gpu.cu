@@ -219,6 +219,22 @@ void destroyGraph(void* exec) {
     cudaGraphExecDestroy((cudaGraphExec_t)exec);
 }
 
+void* recordMarker(void* marker) {
+  cudaEvent_t e = (cudaEvent_t)marker;
+  if(!e)
+    CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  CUDA_CHECK(cudaEventRecord(e, mainStream()));
+  return e;
+}
+void waitMarker(void* marker) {
+  if(marker)
+    CUDA_CHECK(cudaEventSynchronize((cudaEvent_t)marker));
+}
+void freeMarker(void* marker) {
+  if(marker)
+    cudaEventDestroy((cudaEvent_t)marker);
+}
+
 void forkSide() {
   if(tctx.onSide)
     return;

@@ -57,6 +57,7 @@ public:
   ~GradientWorker() {
     replay_.clear();
     device::freePinned(pinnedCost_);
+    device::freeMarker(eagerDone_);
   }
 
   Ptr<ExpressionGraph> graph() { return graph_; }
@@ -77,6 +78,9 @@ public:
       }
     }
     lastReplayed_ = false;
+    // an eager build resets and refills the graph's own pinned staging: uploads of the previous eager step must
+    // have executed (see StepReplay::replay)
+    device::waitMarker(eagerDone_);
     bool capture = !keepLogits && replay_.shouldCapture(key);
     static const bool timing = std::getenv("MRN_NODE_TIMING") != nullptr;
     auto t0 = std::chrono::steady_clock::now();
@@ -99,8 +103,9 @@ public:
       void* exec = device::endCapture();
       ABORT_IF(!exec, "CUDA graph capture of the training step failed");
       auto& plan = replay_.store(key, exec, graph_);
-      device::launchGraph(plan.exec);
-      plan.launches++;
+      replay_.launch(plan);
+    } else {
+      eagerDone_ = device::recordMarker(eagerDone_);
     }
   }
 
@@ -121,6 +126,7 @@ private:
   float* pinnedCost_;
   Expr logits_;
   bool lastReplayed_{false};
+  void* eagerDone_{nullptr};  // marker behind the latest eager step (its uploads have read the graph's staging)
 };
 
 class SingletonGraph : public GraphGroup {

@@ -32,14 +32,17 @@ public:
     std::vector<BatchUpload> uploads;
     size_t launches{0};
     size_t kernels{0};  // kernel nodes recorded in the graph
+    void* done{nullptr};  // marker behind the plan's latest launch: its upload nodes have read the pinned staging
   };
 
   ~StepReplay() { clear(); }
 
   void clear() {
-    for(auto& it : plans_)
+    for(auto& it : plans_) {
       if(it.second.exec)
         device::destroyGraph(it.second.exec);
+      device::freeMarker(it.second.done);
+    }
     plans_.clear();
     seen_.clear();
   }
@@ -61,10 +64,19 @@ public:
     return seen_[key]++ >= 1;
   }
 
+  // The graph's memcpy nodes read the plan's pinned staging when they EXECUTE: the host must not refill it for the
+  // next batch while an earlier launch of the same plan is still queued (the host runs several steps ahead of the
+  // device when nobody reads the cost back).  The optimizer step that follows each launch keeps the device busy
+  // while the host waits here, so this costs no device time.
   void replay(Plan& plan, const data::CorpusBatch& batch) {
+    device::waitMarker(plan.done);
     for(auto& u : plan.uploads)
       u.refill(u.pinned, batch);
+    launch(plan);
+  }
+  void launch(Plan& plan) {
     device::launchGraph(plan.exec);
+    plan.done = device::recordMarker(plan.done);
     plan.launches++;
   }
 

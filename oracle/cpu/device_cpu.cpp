@@ -52,6 +52,9 @@ void forkSide() {}
 void returnFromSide() {}
 void joinSide() {}
 bool onSide() { return false; }
+void* recordMarker(void*) { return nullptr; }
+void waitMarker(void*) {}
+void freeMarker(void*) {}
 bool capturing() { return false; }
 
 bool captureSupported() { return false; }

@@ -290,3 +290,28 @@ def test_checkpoint_round_trip_between_gpu_and_oracle(cuda, oracle, tmp_path):
     cpu = steps(o, 2, skip=3)
     o.close()
     assert np.allclose(cpu, want[3:], rtol=1e-4), (cpu, want[3:])
+
+
+@pytest.mark.parametrize("padded", [False, True], ids=["dense", "padded"])
+def test_host_running_ahead_does_not_mix_batches(cuda, padded):
+    """bench.py never reads the cost inside its timed loop: the host enqueues steps far ahead of the device.  The
+    pinned staging a replayed graph uploads from (and the eager tape's staging for new shapes) must not be refilled
+    before the queued step has read it - otherwise steps train on the wrong batch or gather rows with torn indices
+    (an illegal address in the padded bench of this round).  Same 40 updates with and without a host sync per step."""
+    opts = TRANSFORMER + ";gemm-mode=0;graph-replay=true;learn-rate=0.002"
+    out = []
+    for sync in (True, False):
+        t = cuda.trainer(opts)
+        for s in range(40):
+            shape = [(8, 11, 13), (8, 9, 7), (8, 12, 13)][s % 3] if padded else (8, 11, 13)
+            t.next_synthetic_batch(shape[0], shape[1], shape[2], padded=padded)
+            t.compute_gradients()
+            t.update()
+            if sync:
+                t.cost()
+        last = t.cost()
+        out.append((last, t.arena_numpy("params")))
+        t.close()
+    assert abs(out[0][0] - out[1][0]) <= 1e-4 * abs(out[0][0]), (out[0][0], out[1][0])
+    diff = np.abs(out[0][1] - out[1][1])
+    assert np.mean(diff > 1e-4) < 0.01, (diff.max(), np.mean(diff > 1e-4))
