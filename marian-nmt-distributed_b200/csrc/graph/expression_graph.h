@@ -294,7 +294,16 @@ public:
     topNodes_.clear();
     hashMap_.clear();
 
+    // optional split of the sweep (training/graph_group.h: gradient exchange overlapped with the rest of the sweep)
+    size_t splitAfter = (size_t)-1, swept = 0;
+    if(backwardSplitChooser_)
+      splitAfter = backwardSplitChooser_(nodesBackward_);
+
     while(!nodesBackward_.empty()) {
+      if(swept++ == splitAfter && backwardSplitHook_) {
+        device::joinSide();  // weight gradients issued so far are part of "before the split"
+        backwardSplitHook_();
+      }
       auto v = nodesBackward_.back();
       nodesBackward_.pop_back();
 
@@ -397,6 +406,14 @@ public:
 
   Ptr<Parameters>& params() { return params_; }
 
+  // Backward split: `chooser` sees the tape (forward order; the sweep runs it back to front) and returns after how
+  // many swept nodes `hook` is to be called (or size_t(-1): never).  The side stream is joined before the hook.
+  typedef std::function<size_t(const std::list<Expr>&)> SplitChooser;
+  void setBackwardSplit(SplitChooser chooser, std::function<void()> hook) {
+    backwardSplitChooser_ = chooser;
+    backwardSplitHook_ = hook;
+  }
+
   Expr add(Expr node) {
     size_t hash = node->hash();
     auto it = hashMap_.find(hash);
@@ -474,6 +491,8 @@ private:
   size_t count_{0};
   std::list<Expr> nodesForward_;
   std::list<Expr> nodesBackward_;
+  SplitChooser backwardSplitChooser_;
+  std::function<void()> backwardSplitHook_;
   std::unordered_set<Expr> topNodes_;
   Ptr<Parameters> params_;
   Ptr<TensorAllocator> tensors_;

@@ -22,6 +22,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "kernels/cuda_helpers.h"
 #include "kernels/tensor_operators.h"
@@ -66,6 +67,90 @@ __global__ void __launch_bounds__(256) gGatherReduce(float* __restrict__ out, fl
   sq = blockSum(sq, smem);
   if(threadIdx.x == 0)
     atomicAdd(normSq, sq);
+}
+
+// ---- piece-wise exchange: the same reduce-scatter + Adam + all-gather, cut into phases that can run while the
+//      backward sweep is still producing the gradients of the other phase (training/graph_group.h) ----------------
+// blockIdx.y = piece.  Grids are kept small (the kernels are NVLink bound and share the GPU with the backward sweep).
+__global__ void __launch_bounds__(256) gGatherReducePieces(float* __restrict__ sums, float* __restrict__ partialSq, PeerTable grads, int nranks, PieceList pl) {
+  __shared__ float smem[32];
+  const int k = blockIdx.y;
+  const size_t off = pl.off[k];
+  float* out = sums + pl.state[k];
+  float sq = 0.f;
+  const size_t n4 = pl.len >> 2;
+  for(size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    // all peer loads of an element are in flight together: few blocks must cover the NVLink latency (~2 us)
+    float4 g[8];
+#pragma unroll
+    for(int r = 0; r < 8; ++r)
+      g[r] = r < nranks ? __ldcg(reinterpret_cast<const float4*>(reinterpret_cast<const float*>(grads.ptr[r]) + off) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+    float4 acc = g[0];
+#pragma unroll
+    for(int r = 1; r < 8; ++r) {  // rank order, as the collective sum of the other exchange path
+      acc.x += g[r].x;
+      acc.y += g[r].y;
+      acc.z += g[r].z;
+      acc.w += g[r].w;
+    }
+    reinterpret_cast<float4*>(out)[i] = acc;
+    sq += (acc.x * acc.x + acc.y * acc.y) + (acc.z * acc.z + acc.w * acc.w);
+  }
+  sq = blockSum(sq, smem);
+  if(threadIdx.x == 0)
+    atomicAdd(partialSq + pl.shard[k], sq);
+}
+
+__global__ void gPublishPartials(const float* __restrict__ partialSq, PeerTable pads, int rank, int nranks, int phase) {
+  // thread (peer, shard): slot [phase][rank][shard] of the peer's pad
+  const int peer = threadIdx.x >> 3, s = threadIdx.x & 7;
+  if(peer < nranks && s < nranks) {
+    volatile float* slot = reinterpret_cast<volatile float*>(reinterpret_cast<uint8_t*>(pads.ptr[peer]) + 1024) + (phase * 8 + rank) * 8 + s;
+    *slot = partialSq[s];
+  }
+  __threadfence_system();
+}
+
+__global__ void __launch_bounds__(256) gAdamPieces(PeerTable params, const float* __restrict__ ownPad, int rank, int nranks, int phase, const float* __restrict__ sums, float* __restrict__ m,
+                                                   float* __restrict__ v, AdamArgs a, PieceList pl) {
+  const int k = blockIdx.y;
+  // norm of the whole reference shard: partial sums of squares of all its pieces, published by their owners
+  float scale = a.gradScale;
+  if(a.clipNorm > 0.f) {
+    const float* part = reinterpret_cast<const float*>(reinterpret_cast<const uint8_t*>(ownPad) + 1024) + (size_t)phase * 64 + pl.shard[k];
+    float normSq = 0.f;
+    for(int r = 0; r < nranks; ++r)
+      normSq += part[r * 8];
+    const float norm = sqrtf(normSq) * fabsf(a.gradScale);
+    if(norm >= a.clipNorm)
+      scale *= a.clipNorm / norm;
+  }
+  const size_t off = pl.off[k], so = pl.state[k];
+  float* p = reinterpret_cast<float*>(params.ptr[rank]) + off;
+  const size_t n4 = pl.len >> 2;
+  for(size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
+    float4 pp = reinterpret_cast<float4*>(p)[i];
+    float4 gg = reinterpret_cast<const float4*>(sums + so)[i];
+    float4 mm = reinterpret_cast<float4*>(m + so)[i];
+    float4 vv = reinterpret_cast<float4*>(v + so)[i];
+    float* P = &pp.x;
+    float* G = &gg.x;
+    float* M = &mm.x;
+    float* V = &vv.x;
+#pragma unroll
+    for(int e = 0; e < 4; ++e) {
+      float gi = G[e] * scale;
+      M[e] = (a.beta1 * M[e]) + ((1 - a.beta1) * gi);
+      V[e] = (a.beta2 * V[e]) + ((1 - a.beta2) * (gi * gi));
+      P[e] = P[e] - a.eta * (M[e] / a.denom1) / (sqrtf(V[e] / a.denom2) + a.eps);
+    }
+    reinterpret_cast<float4*>(p)[i] = pp;
+    reinterpret_cast<float4*>(m + so)[i] = mm;
+    reinterpret_cast<float4*>(v + so)[i] = vv;
+    for(int r = 0; r < nranks; ++r)  // all-gather by peer stores
+      if(r != rank)
+        reinterpret_cast<float4*>(reinterpret_cast<float*>(params.ptr[r]) + off)[i] = pp;
+  }
 }
 
 // ---- asynchronous sharded parameter server (AsyncGraphGroup) -------------------------------
@@ -145,6 +230,35 @@ void AdamUpdateRemote(void* masterBlock, size_t shardElements, const float* grad
   float* v = m + shardElements;
   int grid = std::max(1, std::min((int)((shardElements / 4 + 255) / 256), kNumSMs * 8));
   gAdamRemote<<<grid, 256, 0, cudaStreamOfEngine()>>>(p, m, v, gradSlice, shardElements, args, steps, normSq ? normSq->data() : nullptr);
+  CUDA_LAUNCH_CHECK();
+}
+
+namespace {
+// few blocks per piece: the kernels run next to the backward sweep and only have to keep NVLink busy
+inline dim3 pieceGrid(const PieceList& pl) {
+  static const int budget = std::getenv("MRN_EXCHANGE_BLOCKS") ? std::atoi(std::getenv("MRN_EXCHANGE_BLOCKS")) : 96;
+  int gx = std::max(1, std::min((int)((pl.len / 4 + 255) / 256), std::max(4, budget / std::max(1, pl.count))));
+  return dim3(gx, pl.count);
+}
+}  // namespace
+
+void PeerGatherReducePieces(Tensor sums, float* partialSq, const PeerTable& grads, int nranks, const PieceList& pl) {
+  device::setDevice(sums->getDevice());
+  if(pl.count == 0)
+    return;
+  ABORT_IF(pl.len % 4 != 0, "peer exchange expects 16-byte aligned pieces");
+  gGatherReducePieces<<<pieceGrid(pl), 256, 0, cudaStreamOfEngine()>>>(sums->data(), partialSq, grads, nranks, pl);
+  CUDA_LAUNCH_CHECK();
+}
+void PeerPublishPartials(const float* partialSq, const PeerTable& pads, int rank, int nranks, int phase) {
+  gPublishPartials<<<1, 64, 0, cudaStreamOfEngine()>>>(partialSq, pads, rank, nranks, phase);
+  CUDA_LAUNCH_CHECK();
+}
+void AdamUpdatePieces(const PeerTable& params, void* ownPad, int rank, int nranks, int phase, Tensor sums, Tensor mt, Tensor vt, const AdamArgs& args, const PieceList& pl) {
+  device::setDevice(sums->getDevice());
+  if(pl.count == 0)
+    return;
+  gAdamPieces<<<pieceGrid(pl), 256, 0, cudaStreamOfEngine()>>>(params, (const float*)ownPad, rank, nranks, phase, sums->data(), mt->data(), vt->data(), args, pl);
   CUDA_LAUNCH_CHECK();
 }
 

@@ -186,6 +186,28 @@ struct PeerStores {
   int self{0};
   size_t offset{0};
 };
+// Piece-wise exchange (overlapped with the backward sweep, training/graph_group.h): every rank owns piece `rank` of
+// EVERY reference shard (a reference shard = one contiguous 1/N of the arena, the unit the reference clips by).
+// A PieceList names the pieces a rank handles in one phase: piece k covers arena elements [off[k], off[k] + len)
+// of reference shard shard[k]; its summed gradient and Adam state live at element state[k] of the rank-local
+// scratch / moment tensors.
+struct PieceList {
+  size_t off[8];
+  size_t state[8];
+  int shard[8];
+  int count{0};
+  size_t len{0};
+};
+// Signal pad layout (4 KB per rank, mapped into all ranks): ints [0, 8) barrier epochs; floats at byte 1024:
+// partial sums of squares [phase 2][source rank 8][reference shard 8].
+constexpr size_t kSignalPadBytes = 4096;
+// sums[state[k] + i] = sum_r grads_r[off[k] + i]; partialSq[shard[k]] += sum of squares of piece k (local device floats)
+void PeerGatherReducePieces(Tensor sums, float* partialSq, const PeerTable& grads, int nranks, const PieceList& pieces);
+// every rank's partialSq[0..nranks) -> slot [phase][rank][*] of every rank's signal pad (peer stores)
+void PeerPublishPartials(const float* partialSq, const PeerTable& pads, int rank, int nranks, int phase);
+// clip by the norm of the whole reference shard (sum over source ranks of the published partials in the OWN pad), 1/N,
+// Adam on the pieces; new parameters to the local arena and by peer stores into every replica
+void AdamUpdatePieces(const PeerTable& params, void* ownPad, int rank, int nranks, int phase, Tensor sums, Tensor mt, Tensor vt, const AdamArgs& args, const PieceList& pieces);
 void PeerBarrier(const PeerTable& pads, int rank, int nranks, int epoch);
 // shardSum[i] = sum_r grads_r[offset + i];  normSq = sum_i shardSum[i]^2 (same pass)
 void PeerGatherReduce(Tensor shardSum, Tensor normSq, const PeerTable& grads, int nranks, size_t offset);

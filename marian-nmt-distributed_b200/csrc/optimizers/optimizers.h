@@ -133,6 +133,24 @@ public:
   Tensor mt() { return mt_; }
   Tensor vt() { return vt_; }
   size_t steps() const { return t_; }
+  // Piece-wise shard updates (SyncGraphGroup's overlapped exchange): ONE call per update - allocates the moments for
+  // `stateElements` parameters, counts the step and returns the arguments for AdamUpdatePieces of all phases.
+  AdamArgs beginPieceStep(size_t stateElements, int device, float gradScale) {
+    if(!mt_) {
+      alloc_ = New<TensorAllocator>(device);
+      alloc_->reserveExact(2 * alloc_->capacity(Shape{1, (int)stateElements}));
+      alloc_->allocate(mt_, Shape{1, (int)stateElements});
+      mt_->set(0);
+      alloc_->allocate(vt_, Shape{1, (int)stateElements});
+      vt_->set(0);
+    }
+    ABORT_IF(mt_->size() != stateElements, "Adam state has a different size than the shard");
+    t_++;
+    AdamArgs a = hyper(gradScale);
+    a.denom1 = (float)(1 - std::pow((double)beta1_, (double)t_));
+    a.denom2 = (float)(1 - std::pow((double)beta2_, (double)t_));
+    return a;
+  }
   // resume (training/checkpoint.h): `fill` writes the saved moments once the flat state exists
   void restoreOnAllocation(size_t steps, std::function<void(Tensor, Tensor)> fill) {
     pendingSteps_ = steps;

@@ -19,6 +19,7 @@
 #pragma once
 
 #include <chrono>
+#include <map>
 #include <cstdio>
 #include <cstdlib>
 
@@ -63,6 +64,8 @@ public:
   Ptr<ExpressionGraph> graph() { return graph_; }
   Ptr<EncoderDecoder> builder() { return builder_; }
   StepReplay& replay() { return replay_; }
+  // hook between the two halves of the backward sweep (SyncGraphGroup: first phase of the gradient exchange)
+  void setMidStep(StepReplay::MidStep* mid) { mid_ = mid; }
 
   // Enqueues forward+backward on the engine stream; cost lands in pinned memory.
   void computeGradients(Ptr<data::CorpusBatch> batch, bool keepLogits = false) {
@@ -72,7 +75,7 @@ public:
     auto key = batch->shapeKey();
     if(!keepLogits) {
       if(auto plan = replay_.find(key)) {
-        replay_.replay(*plan, *batch);
+        replay_.replay(*plan, *batch, mid_);
         lastReplayed_ = true;
         return;
       }
@@ -86,6 +89,26 @@ public:
     auto t0 = std::chrono::steady_clock::now();
     auto costNode = builder_->build(graph_, batch);
     auto t1 = std::chrono::steady_clock::now();
+    // split step: the group's hook runs between the two halves of the backward sweep - directly when the step is
+    // eager, between the two graphs when it is captured (the capture is cut in two at the same point)
+    void* execFirst = nullptr;
+    size_t kernelsFirst = 0;
+    if(mid_) {
+      auto* mid = mid_;
+      graph_->setBackwardSplit([mid](const std::list<Expr>& tape) { return mid->choose(tape); },
+                               [mid, capture, &execFirst, &kernelsFirst]() {
+                                 if(capture) {
+                                   execFirst = device::endCapture();
+                                   ABORT_IF(!execFirst, "CUDA graph capture of the first half of the training step failed");
+                                   kernelsFirst = device::lastCaptureKernelCount();
+                                   device::beginCapture();
+                                 } else {
+                                   mid->run();
+                                 }
+                               });
+    } else {
+      graph_->setBackwardSplit(nullptr, nullptr);
+    }
     if(capture)
       device::beginCapture();
     graph_->forward();
@@ -102,8 +125,8 @@ public:
     if(capture) {
       void* exec = device::endCapture();
       ABORT_IF(!exec, "CUDA graph capture of the training step failed");
-      auto& plan = replay_.store(key, exec, graph_);
-      replay_.launch(plan);
+      auto& plan = execFirst ? replay_.store(key, execFirst, graph_, exec, mid_->tag(), kernelsFirst) : replay_.store(key, exec, graph_);
+      replay_.launch(plan, mid_);
     } else {
       eagerDone_ = device::recordMarker(eagerDone_);
     }
@@ -127,6 +150,7 @@ private:
   Expr logits_;
   bool lastReplayed_{false};
   void* eagerDone_{nullptr};  // marker behind the latest eager step (its uploads have read the graph's staging)
+  StepReplay::MidStep* mid_{nullptr};
 };
 
 class SingletonGraph : public GraphGroup {
@@ -159,11 +183,22 @@ struct ShardExchange {
   virtual float meanCost(float localCost) = 0;
 };
 
-class SyncGraphGroup : public GraphGroup {
+class SyncGraphGroup : public GraphGroup, public StepReplay::MidStep {
 public:
   SyncGraphGroup(Ptr<Options> options, int device, int rank, int nranks, Ptr<ShardExchange> exchange = nullptr)
       : GraphGroup(options), worker_(options, device), rank_(rank), nranks_(nranks), exchange_(exchange) {
     worker_.graph()->params()->setShardCount(nranks);
+    adam_ = std::dynamic_pointer_cast<Adam>(opt_);
+    // piece-wise exchange overlapped with the backward sweep: ranks in powers of two (equal 16-byte aligned pieces)
+    overlap_ = adam_ && (nranks == 2 || nranks == 4 || nranks == 8) && options->get<bool>("exchange-overlap", true) && std::getenv("MRN_NO_EXCHANGE_OVERLAP") == nullptr;
+  }
+  ~SyncGraphGroup() {
+    worker_.setMidStep(nullptr);
+    if(partials_) {
+      device::setDevice((int)worker_.graph()->getDevice());
+      device::synchronize();
+      device::freeDevice(partials_);
+    }
   }
 
   void setExchange(Ptr<ShardExchange> e) { exchange_ = e; }
@@ -209,8 +244,8 @@ public:
   void* signalPad() {
     if(!pad_) {
       device::setDevice((int)worker_.graph()->getDevice());
-      pad_ = device::mallocDevice(256);
-      device::zero(pad_, 256);
+      pad_ = device::mallocDevice(kSignalPadBytes);
+      device::zero(pad_, kSignalPadBytes);
       device::synchronize();
     }
     return pad_;
@@ -222,13 +257,86 @@ public:
     peerGrads_ = grads;
     peerPads_ = pads;
     peersSet_ = true;
+    if(overlap_) {
+      device::setDevice((int)worker_.graph()->getDevice());
+      partials_ = (float*)device::mallocDevice(256);
+      device::zero(partials_, 256);
+      worker_.setMidStep(this);  // steps built from now on are split where the upper shards' gradients are final
+    }
   }
+  bool overlapped() const { return overlap_ && peersSet_; }
+
+  // ---- overlapped, piece-wise exchange --------------------------------------------------------------------
+  // The arena keeps the reference's N contiguous shards as the units of the clipping norm (graph_group_sync.cu:
+  // 130-142), but every rank owns PIECE `rank` of EVERY shard (and the Adam moments of those pieces).  The backward
+  // sweep produces the gradients of the arena's tail first (decoder, output layer) and of its head last (encoder,
+  // source embeddings): once every parameter at or above shard s0 is final the sweep is cut (StepReplay::MidStep),
+  // and while its rest runs, the side stream exchanges shards [s0, N):
+  //   barrier (all ranks are past the cut) -> gather-reduce of the own pieces by peer loads -> partial sums of squares
+  //   to all ranks -> barrier -> clip by the shard norm + Adam + peer stores of the new parameters.
+  // Shards [0, s0) follow after the sweep, then one barrier ends the update.
+  size_t choose(const std::list<Expr>& tape) {
+    split_ = -1;
+    auto params = worker_.graph()->params();
+    if(!overlapped() || params->size() == 0)
+      return (size_t)-1;
+    // last position in the sweep (0 = first node swept = last node of the tape) at which a parameter still receives gradient
+    std::map<Chainable<Tensor>*, size_t> lastUse;
+    size_t pos = 0;
+    for(auto it = tape.rbegin(); it != tape.rend(); ++it, ++pos)
+      if((*it)->trainable())
+        for(auto& c : (*it)->children())
+          if(c->type() == "param" && c->trainable())
+            lastUse[c.get()] = pos;
+    const size_t sweep = pos;
+    const float* base = params->grads()->data();
+    const size_t total = params->grads()->size(), shard = total / nranks_;
+    // finalAt[s] = sweep position after which every parameter overlapping [s * shard, total) is final
+    std::vector<size_t> finalAt(nranks_, 0);
+    for(auto p : *params) {
+      auto it = lastUse.find(p.get());
+      if(it == lastUse.end() || !p->grad())
+        continue;
+      size_t end = (size_t)(p->grad()->data() - base) + p->grad()->size();
+      for(int s = 0; s < nranks_; ++s)
+        if(end > (size_t)s * shard)
+          finalAt[s] = std::max(finalAt[s], it->second + 1);
+    }
+    // the lowest shard boundary whose tail is final with at least a fifth of the sweep still to run
+    for(int s0 = 1; s0 < nranks_; ++s0)
+      if(finalAt[s0] > 0 && finalAt[s0] * 5 <= sweep * 4) {
+        split_ = s0;
+        return finalAt[s0];
+      }
+    return (size_t)-1;
+  }
+  int tag() { return split_; }
+  void restore(int tag) { split_ = tag; }
+  void run() {  // between the two halves of the sweep: shards [split_, N) on the side stream
+    if(split_ <= 0)
+      return;
+    device::forkSide();
+    exchangePhase(0, split_, nranks_);
+    device::returnFromSide();
+    midRan_ = true;
+  }
+
   bool peersSet() const { return peersSet_; }
 
   // after computeGradients(): everything else of the update, on the engine stream
   void exchangeUpdatePeer() {
     ABORT_IF(!peersSet_, "exchangeUpdatePeer: peers have not been mapped");
     ensureShard();
+    if(overlap_) {
+      device::joinSide();  // the first phase (if the step was split) is done before the second starts
+      exchangePhase(1, 0, midRan_ ? split_ : nranks_);
+      PeerBarrier(peerPads_, rank_, nranks_, ++epoch_);  // every piece has landed everywhere
+      midRan_ = false;
+      stepBegun_ = false;
+      gemmInvalidateCache(worker_.graph()->getBackend()->getGemmHandle());
+      gemmParamsUpdated(worker_.graph()->getBackend()->getGemmHandle(), false);
+      return;
+    }
     int device = (int)worker_.graph()->getDevice();
     PeerBarrier(peerPads_, rank_, nranks_, ++epoch_);  // every rank finished backward
     PeerGatherReduce(shardGrads_, opt_->normSqScratch(device), peerGrads_, nranks_, (size_t)rank_ * shardSize_);
@@ -266,6 +374,33 @@ public:
   Ptr<OptimizerBase> optimizer() { return opt_; }
 
 private:
+  // one phase of the piece-wise exchange for reference shards [sa, sb), on the current stream
+  void exchangePhase(int phase, int sa, int sb) {
+    ensureShard();
+    int device = (int)worker_.graph()->getDevice();
+    if(!stepBegun_) {  // once per update: Adam step counter and bias corrections
+      pieceArgs_ = adam_->beginPieceStep(shardSize_, device, 1.f / (float)nranks_);
+      stepBegun_ = true;
+    }
+    PieceList pl;
+    pl.len = shardSize_ / nranks_;
+    for(int s = sa; s < sb; ++s) {
+      pl.off[pl.count] = (size_t)s * shardSize_ + (size_t)rank_ * pl.len;
+      pl.state[pl.count] = (size_t)s * pl.len;
+      pl.shard[pl.count] = s;
+      pl.count++;
+    }
+    PeerBarrier(peerPads_, rank_, nranks_, ++epoch_);  // every rank's gradients of these shards are final
+    if(pl.count > 0) {
+      device::zero(partials_ + phase * 8, 8 * sizeof(float));
+      PeerGatherReducePieces(shardGrads_, partials_ + phase * 8, peerGrads_, nranks_, pl);
+    }
+    PeerPublishPartials(partials_ + phase * 8, peerPads_, rank_, nranks_, phase);
+    PeerBarrier(peerPads_, rank_, nranks_, ++epoch_);  // all partial sums of squares are visible
+    if(pl.count > 0)
+      AdamUpdatePieces(peerParams_, pad_, rank_, nranks_, phase, shardGrads_, adam_->mt(), adam_->vt(), pieceArgs_, pl);
+  }
+
   void ensureShard() {
     if(shardGrads_)
       return;
@@ -290,6 +425,13 @@ private:
   bool peersSet_{false};
   int epoch_{0};
   void* pad_{nullptr};
+  // overlapped piece-wise exchange
+  Ptr<Adam> adam_;
+  bool overlap_{false};
+  int split_{-1};          // first reference shard of the early phase (-1: this step is not split)
+  bool midRan_{false}, stepBegun_{false};
+  float* partials_{nullptr};  // [phase 2][shard 8] sums of squares of the own pieces
+  AdamArgs pieceArgs_;
 };
 
 // Asynchronous SGD with a sharded parameter server - the reference's AsyncGraphGroup

@@ -33,6 +33,19 @@ public:
     size_t launches{0};
     size_t kernels{0};  // kernel nodes recorded in the graph
     void* done{nullptr};  // marker behind the plan's latest launch: its upload nodes have read the pinned staging
+    // split step (gradient exchange overlapped with the backward sweep): `exec` ends at the split of the sweep,
+    // `exec2` is the rest; `midTag` is what the group decided at the split (restored before its hook runs)
+    void* exec2{nullptr};
+    int midTag{-1};
+  };
+
+  // what runs between the two halves of a split step
+  struct MidStep {
+    virtual ~MidStep() {}
+    virtual size_t choose(const std::list<Expr>& tape) = 0;  // after how many swept nodes (size_t(-1): no split); remembers the decision
+    virtual int tag() = 0;
+    virtual void restore(int tag) = 0;
+    virtual void run() = 0;
   };
 
   ~StepReplay() { clear(); }
@@ -41,6 +54,8 @@ public:
     for(auto& it : plans_) {
       if(it.second.exec)
         device::destroyGraph(it.second.exec);
+      if(it.second.exec2)
+        device::destroyGraph(it.second.exec2);
       device::freeMarker(it.second.done);
     }
     plans_.clear();
@@ -68,23 +83,31 @@ public:
   // next batch while an earlier launch of the same plan is still queued (the host runs several steps ahead of the
   // device when nobody reads the cost back).  The optimizer step that follows each launch keeps the device busy
   // while the host waits here, so this costs no device time.
-  void replay(Plan& plan, const data::CorpusBatch& batch) {
+  void replay(Plan& plan, const data::CorpusBatch& batch, MidStep* mid = nullptr) {
     device::waitMarker(plan.done);
     for(auto& u : plan.uploads)
       u.refill(u.pinned, batch);
-    launch(plan);
+    launch(plan, mid);
   }
-  void launch(Plan& plan) {
+  void launch(Plan& plan, MidStep* mid = nullptr) {
     device::launchGraph(plan.exec);
+    if(plan.exec2) {
+      ABORT_IF(!mid, "a split step needs its mid-step hook");
+      mid->restore(plan.midTag);
+      mid->run();
+      device::launchGraph(plan.exec2);
+    }
     plan.done = device::recordMarker(plan.done);
     plan.launches++;
   }
 
   // Takes ownership of the recorded graph and of the tape's staging/uploads.
-  Plan& store(const std::vector<int>& key, void* exec, Ptr<ExpressionGraph> graph) {
+  Plan& store(const std::vector<int>& key, void* exec, Ptr<ExpressionGraph> graph, void* exec2 = nullptr, int midTag = -1, size_t kernelsFirst = 0) {
     Plan& p = plans_[key];
     p.exec = exec;
-    p.kernels = device::lastCaptureKernelCount();
+    p.exec2 = exec2;
+    p.midTag = midTag;
+    p.kernels = device::lastCaptureKernelCount() + kernelsFirst;
     lastKernels_ = p.kernels;
     p.uploads = graph->batchUploads();
     p.staging = graph->detachStaging();

@@ -140,6 +140,7 @@ class SyncTrainer:
         """One update on the trainer's current batch (set via self.trainer.*batch*)."""
         self.trainer.compute_gradients()
         params, grads, shard, ns = self._arenas()
+        redo = self.first
         if self.first:
             # reference :46-53: replicas start from graph 0's parameters BEFORE any gradient is
             # taken.  Parameters only exist once the tape has been built and run, so the first
@@ -147,11 +148,14 @@ class SyncTrainer:
             # gradients at the common parameter point.
             self.exchange.broadcast(params)
             self.first = False
-            self.trainer.compute_gradients()
         if self.peer and not self._peers_mapped:
             # all ranks must agree: if any rank cannot map its peers (no P2P between the GPUs, IPC
-            # disabled in the container) everybody falls back to the collective exchange - loudly
+            # disabled in the container) everybody falls back to the collective exchange - loudly.
+            # (Mapped BEFORE the recomputation below: steps built with mapped peers are split so that
+            # the gradient exchange of the upper shards overlaps the rest of the backward sweep.)
             self.peer = self._map_peers()
+        if redo:
+            self.trainer.compute_gradients()
         if self.peer:
             self.trainer.update_peer()
             return

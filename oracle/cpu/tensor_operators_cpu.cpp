@@ -1167,6 +1167,15 @@ void AdamUpdateRemote(void* masterBlock, size_t shardElements, const float* grad
     p[i] = p[i] - a.eta * (m[i] / denom1) / (sqrtf(v[i] / denom2) + a.eps);
   }
 }
+void PeerGatherReducePieces(Tensor, float*, const PeerTable&, int, const PieceList&) {
+  ABORT("the peer-memory exchange needs the CUDA build");
+}
+void PeerPublishPartials(const float*, const PeerTable&, int, int, int) {
+  ABORT("the peer-memory exchange needs the CUDA build");
+}
+void AdamUpdatePieces(const PeerTable&, void*, int, int, int, Tensor, Tensor, Tensor, const AdamArgs&, const PieceList&) {
+  ABORT("the peer-memory exchange needs the CUDA build");
+}
 void PeerBarrier(const PeerTable&, int, int, int) {
   ABORT("peer-memory exchange is a CUDA feature");
 }
