@@ -234,31 +234,33 @@ void AdamUpdateRemote(void* masterBlock, size_t shardElements, const float* grad
 }
 
 namespace {
-// few blocks per piece: the kernels run next to the backward sweep and only have to keep NVLink busy
-inline dim3 pieceGrid(const PieceList& pl) {
-  static const int budget = std::getenv("MRN_EXCHANGE_BLOCKS") ? std::atoi(std::getenv("MRN_EXCHANGE_BLOCKS")) : 96;
+// blocks over all pieces of a phase: the phase that runs next to the backward sweep gets about two per SM (enough loads in
+// flight for NVLink / HBM, most of the machine left to the sweep), the exposed phase the whole machine
+inline dim3 pieceGrid(const PieceList& pl, bool background) {
+  static const int bgBudget = std::getenv("MRN_EXCHANGE_BLOCKS") ? std::atoi(std::getenv("MRN_EXCHANGE_BLOCKS")) : 2 * kNumSMs;
+  const int budget = background ? bgBudget : 8 * kNumSMs;
   int gx = std::max(1, std::min((int)((pl.len / 4 + 255) / 256), std::max(4, budget / std::max(1, pl.count))));
   return dim3(gx, pl.count);
 }
 }  // namespace
 
-void PeerGatherReducePieces(Tensor sums, float* partialSq, const PeerTable& grads, int nranks, const PieceList& pl) {
+void PeerGatherReducePieces(Tensor sums, float* partialSq, const PeerTable& grads, int nranks, const PieceList& pl, bool background) {
   device::setDevice(sums->getDevice());
   if(pl.count == 0)
     return;
   ABORT_IF(pl.len % 4 != 0, "peer exchange expects 16-byte aligned pieces");
-  gGatherReducePieces<<<pieceGrid(pl), 256, 0, cudaStreamOfEngine()>>>(sums->data(), partialSq, grads, nranks, pl);
+  gGatherReducePieces<<<pieceGrid(pl, background), 256, 0, cudaStreamOfEngine()>>>(sums->data(), partialSq, grads, nranks, pl);
   CUDA_LAUNCH_CHECK();
 }
 void PeerPublishPartials(const float* partialSq, const PeerTable& pads, int rank, int nranks, int phase) {
   gPublishPartials<<<1, 64, 0, cudaStreamOfEngine()>>>(partialSq, pads, rank, nranks, phase);
   CUDA_LAUNCH_CHECK();
 }
-void AdamUpdatePieces(const PeerTable& params, void* ownPad, int rank, int nranks, int phase, Tensor sums, Tensor mt, Tensor vt, const AdamArgs& args, const PieceList& pl) {
+void AdamUpdatePieces(const PeerTable& params, void* ownPad, int rank, int nranks, int phase, Tensor sums, Tensor mt, Tensor vt, const AdamArgs& args, const PieceList& pl, bool background) {
   device::setDevice(sums->getDevice());
   if(pl.count == 0)
     return;
-  gAdamPieces<<<pieceGrid(pl), 256, 0, cudaStreamOfEngine()>>>(params, (const float*)ownPad, rank, nranks, phase, sums->data(), mt->data(), vt->data(), args, pl);
+  gAdamPieces<<<pieceGrid(pl, background), 256, 0, cudaStreamOfEngine()>>>(params, (const float*)ownPad, rank, nranks, phase, sums->data(), mt->data(), vt->data(), args, pl);
   CUDA_LAUNCH_CHECK();
 }
 

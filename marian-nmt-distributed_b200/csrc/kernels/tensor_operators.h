@@ -202,12 +202,13 @@ struct PieceList {
 // partial sums of squares [phase 2][source rank 8][reference shard 8].
 constexpr size_t kSignalPadBytes = 4096;
 // sums[state[k] + i] = sum_r grads_r[off[k] + i]; partialSq[shard[k]] += sum of squares of piece k (local device floats)
-void PeerGatherReducePieces(Tensor sums, float* partialSq, const PeerTable& grads, int nranks, const PieceList& pieces);
+// background: the phase runs next to the backward sweep (small grids) instead of alone on the device
+void PeerGatherReducePieces(Tensor sums, float* partialSq, const PeerTable& grads, int nranks, const PieceList& pieces, bool background);
 // every rank's partialSq[0..nranks) -> slot [phase][rank][*] of every rank's signal pad (peer stores)
 void PeerPublishPartials(const float* partialSq, const PeerTable& pads, int rank, int nranks, int phase);
 // clip by the norm of the whole reference shard (sum over source ranks of the published partials in the OWN pad), 1/N,
 // Adam on the pieces; new parameters to the local arena and by peer stores into every replica
-void AdamUpdatePieces(const PeerTable& params, void* ownPad, int rank, int nranks, int phase, Tensor sums, Tensor mt, Tensor vt, const AdamArgs& args, const PieceList& pieces);
+void AdamUpdatePieces(const PeerTable& params, void* ownPad, int rank, int nranks, int phase, Tensor sums, Tensor mt, Tensor vt, const AdamArgs& args, const PieceList& pieces, bool background);
 void PeerBarrier(const PeerTable& pads, int rank, int nranks, int epoch);
 // shardSum[i] = sum_r grads_r[offset + i];  normSq = sum_i shardSum[i]^2 (same pass)
 void PeerGatherReduce(Tensor shardSum, Tensor normSq, const PeerTable& grads, int nranks, size_t offset);

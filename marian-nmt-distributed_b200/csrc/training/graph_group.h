@@ -393,12 +393,12 @@ private:
     PeerBarrier(peerPads_, rank_, nranks_, ++epoch_);  // every rank's gradients of these shards are final
     if(pl.count > 0) {
       device::zero(partials_ + phase * 8, 8 * sizeof(float));
-      PeerGatherReducePieces(shardGrads_, partials_ + phase * 8, peerGrads_, nranks_, pl);
+      PeerGatherReducePieces(shardGrads_, partials_ + phase * 8, peerGrads_, nranks_, pl, phase == 0);
     }
     PeerPublishPartials(partials_ + phase * 8, peerPads_, rank_, nranks_, phase);
     PeerBarrier(peerPads_, rank_, nranks_, ++epoch_);  // all partial sums of squares are visible
     if(pl.count > 0)
-      AdamUpdatePieces(peerParams_, pad_, rank_, nranks_, phase, shardGrads_, adam_->mt(), adam_->vt(), pieceArgs_, pl);
+      AdamUpdatePieces(peerParams_, pad_, rank_, nranks_, phase, shardGrads_, adam_->mt(), adam_->vt(), pieceArgs_, pl, phase == 0);
   }
 
   void ensureShard() {

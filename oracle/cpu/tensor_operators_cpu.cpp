@@ -1167,13 +1167,13 @@ void AdamUpdateRemote(void* masterBlock, size_t shardElements, const float* grad
     p[i] = p[i] - a.eta * (m[i] / denom1) / (sqrtf(v[i] / denom2) + a.eps);
   }
 }
-void PeerGatherReducePieces(Tensor, float*, const PeerTable&, int, const PieceList&) {
+void PeerGatherReducePieces(Tensor, float*, const PeerTable&, int, const PieceList&, bool) {
   ABORT("the peer-memory exchange needs the CUDA build");
 }
 void PeerPublishPartials(const float*, const PeerTable&, int, int, int) {
   ABORT("the peer-memory exchange needs the CUDA build");
 }
-void AdamUpdatePieces(const PeerTable&, void*, int, int, int, Tensor, Tensor, Tensor, const AdamArgs&, const PieceList&) {
+void AdamUpdatePieces(const PeerTable&, void*, int, int, int, Tensor, Tensor, Tensor, const AdamArgs&, const PieceList&, bool) {
   ABORT("the peer-memory exchange needs the CUDA build");
 }
 void PeerBarrier(const PeerTable&, int, int, int) {
