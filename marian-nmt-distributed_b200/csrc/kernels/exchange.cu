@@ -264,6 +264,18 @@ void AdamUpdatePieces(const PeerTable& params, void* ownPad, int rank, int nrank
   CUDA_LAUNCH_CHECK();
 }
 
+namespace {
+__global__ void gTimeStamp(unsigned long long* slot) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  *slot = t;
+}
+}  // namespace
+void DeviceTimeStamp(unsigned long long* slot) {
+  gTimeStamp<<<1, 1, 0, cudaStreamOfEngine()>>>(slot);
+  CUDA_LAUNCH_CHECK();
+}
+
 void PeerBarrier(const PeerTable& pads, int rank, int nranks, int epoch) {
   gPeerBarrier<<<1, 32, 0, cudaStreamOfEngine()>>>(pads, rank, nranks, epoch);
   CUDA_LAUNCH_CHECK();

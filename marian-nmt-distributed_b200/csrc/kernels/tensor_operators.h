@@ -210,6 +210,8 @@ void PeerPublishPartials(const float* partialSq, const PeerTable& pads, int rank
 // Adam on the pieces; new parameters to the local arena and by peer stores into every replica
 void AdamUpdatePieces(const PeerTable& params, void* ownPad, int rank, int nranks, int phase, Tensor sums, Tensor mt, Tensor vt, const AdamArgs& args, const PieceList& pieces, bool background);
 void PeerBarrier(const PeerTable& pads, int rank, int nranks, int epoch);
+// tuning aid: one thread writes %globaltimer (ns) to *slot on the current stream
+void DeviceTimeStamp(unsigned long long* slot);
 // shardSum[i] = sum_r grads_r[offset + i];  normSq = sum_i shardSum[i]^2 (same pass)
 void PeerGatherReduce(Tensor shardSum, Tensor normSq, const PeerTable& grads, int nranks, size_t offset);
 

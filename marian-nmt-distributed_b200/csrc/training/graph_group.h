@@ -22,6 +22,7 @@
 #include <map>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 #include "data/batch.h"
 #include "graph/expression_graph.h"
@@ -194,6 +195,13 @@ public:
   }
   ~SyncGraphGroup() {
     worker_.setMidStep(nullptr);
+    if(stampCount_ > 0 && rank_ == 0) {
+      double n = (double)stampCount_;
+      fprintf(stderr, "[exchange timing, rank 0, us, mean of %d sampled steps] early phase: barrier %.1f gather %.1f publish+barrier %.1f adam+stores %.1f | "
+                      "late phase: barrier %.1f gather %.1f publish+barrier %.1f adam+stores %.1f | early start -> sweep end %.1f, early phase past sweep end %.1f, sweep end -> update end %.1f\n",
+              stampCount_, stampSum_[0] / n, stampSum_[1] / n, stampSum_[2] / n, stampSum_[3] / n, stampSum_[4] / n, stampSum_[5] / n, stampSum_[6] / n, stampSum_[7] / n, stampSum_[8] / n,
+              stampSum_[9] / n, stampSum_[10] / n);
+    }
     if(partials_) {
       device::setDevice((int)worker_.graph()->getDevice());
       device::synchronize();
@@ -328,9 +336,13 @@ public:
     ABORT_IF(!peersSet_, "exchangeUpdatePeer: peers have not been mapped");
     ensureShard();
     if(overlap_) {
+      stamp(10);
       device::joinSide();  // the first phase (if the step was split) is done before the second starts
       exchangePhase(1, 0, midRan_ ? split_ : nranks_);
       PeerBarrier(peerPads_, rank_, nranks_, ++epoch_);  // every piece has landed everywhere
+      stamp(11);
+      if(stamps_ && (++stampEvery_ % 8) == 0)
+        collectStamps();
       midRan_ = false;
       stepBegun_ = false;
       gemmInvalidateCache(worker_.graph()->getBackend()->getGemmHandle());
@@ -390,15 +402,53 @@ private:
       pl.shard[pl.count] = s;
       pl.count++;
     }
+    stamp(phase * 5 + 0);
     PeerBarrier(peerPads_, rank_, nranks_, ++epoch_);  // every rank's gradients of these shards are final
+    stamp(phase * 5 + 1);
     if(pl.count > 0) {
       device::zero(partials_ + phase * 8, 8 * sizeof(float));
       PeerGatherReducePieces(shardGrads_, partials_ + phase * 8, peerGrads_, nranks_, pl, phase == 0);
     }
+    stamp(phase * 5 + 2);
     PeerPublishPartials(partials_ + phase * 8, peerPads_, rank_, nranks_, phase);
     PeerBarrier(peerPads_, rank_, nranks_, ++epoch_);  // all partial sums of squares are visible
+    stamp(phase * 5 + 3);
     if(pl.count > 0)
       AdamUpdatePieces(peerParams_, pad_, rank_, nranks_, phase, shardGrads_, adam_->mt(), adam_->vt(), pieceArgs_, pl, phase == 0);
+    stamp(phase * 5 + 4);
+  }
+  // tuning aid (MRN_EXCHANGE_TIMING=1): device time stamps around the pieces of the exchange; averages printed by rank 0
+  // when the group is destroyed.  Slots: phase p -> 5p + {0 start, 1 after barrier, 2 after gather-reduce, 3 after publish +
+  // barrier, 4 after Adam + peer stores}; 10 = second half of the sweep done (main stream), 11 = after the final barrier.
+  void stamp(int slot) {
+    static const bool on = std::getenv("MRN_EXCHANGE_TIMING") != nullptr;
+    if(!on)
+      return;
+    if(!stamps_) {
+      stamps_ = (unsigned long long*)device::mallocDevice(16 * 8);
+      device::zero(stamps_, 16 * 8);
+    }
+    DeviceTimeStamp(stamps_ + slot);
+  }
+  void collectStamps() {
+    if(!stamps_)
+      return;
+    unsigned long long h[16];
+    device::synchronize();
+    void* pin = device::pinnedScratch(sizeof(h));
+    device::copyD2H(pin, stamps_, sizeof(h));
+    device::synchronize();
+    std::memcpy(h, pin, sizeof(h));
+    if(h[10] && h[11] && h[5] && h[9]) {
+      auto d = [&](int a, int b) { return h[a] && h[b] && h[b] >= h[a] ? (double)(h[b] - h[a]) / 1000.0 : 0.0; };
+      double v[8] = {d(0, 1), d(1, 2), d(2, 3), d(3, 4), d(5, 6), d(6, 7), d(7, 8), d(8, 9)};
+      for(int i = 0; i < 8; ++i)
+        stampSum_[i] += v[i];
+      stampSum_[8] += h[0] ? d(0, 10) : 0.0;   // start of the early phase .. end of the sweep
+      stampSum_[9] += h[0] ? (h[4] > h[10] ? (double)(h[4] - h[10]) / 1000.0 : 0.0) : 0.0;  // early phase running past the sweep
+      stampSum_[10] += d(10, 11);              // end of the sweep .. end of the update
+      stampCount_++;
+    }
   }
 
   void ensureShard() {
@@ -431,6 +481,9 @@ private:
   int split_{-1};          // first reference shard of the early phase (-1: this step is not split)
   bool midRan_{false}, stepBegun_{false};
   float* partials_{nullptr};  // [phase 2][shard 8] sums of squares of the own pieces
+  unsigned long long* stamps_{nullptr};
+  double stampSum_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  int stampCount_{0}, stampEvery_{0};
   AdamArgs pieceArgs_;
 };
 

@@ -1176,6 +1176,7 @@ void PeerPublishPartials(const float*, const PeerTable&, int, int, int) {
 void AdamUpdatePieces(const PeerTable&, void*, int, int, int, Tensor, Tensor, Tensor, const AdamArgs&, const PieceList&, bool) {
   ABORT("the peer-memory exchange needs the CUDA build");
 }
+void DeviceTimeStamp(unsigned long long*) {}
 void PeerBarrier(const PeerTable&, int, int, int) {
   ABORT("peer-memory exchange is a CUDA feature");
 }
