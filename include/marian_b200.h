@@ -88,6 +88,12 @@ int mrn_prod_grouped_nt(void* gemm, mrn_tensor C, const mrn_tensor* As, const mr
  * AffineNodeOp::backwardOps followed by SwishNodeOp::backwardOps (src/graph/node_operators_unary.h, the
  * "swish" functor of src/functional/predicates.h).  tf32 mode only; returns an error otherwise. */
 int mrn_prod_swish_grad_nt(void* gemm, mrn_tensor C, mrn_tensor A, mrn_tensor B, mrn_tensor H, float beta);
+/* C_i = beta C_i + op(A) B_i (+ bias_i), i < n <= 3: products that share their A operand - the query / key / value
+ * projections of Transformer::MultiHead (src/models/transformer.h:194-261: three affine() calls on the same input) and
+ * their weight gradients (AffineNodeOp::backwardOps, three Prod(.., true, false, 1.0) with the same x) - as ONE launch in
+ * the bf16 shadow mode (*fused = 1), otherwise as the n single products the reference issues (*fused = 0).
+ * biases may be NULL. */
+int mrn_prod_shared_a(void* gemm, const mrn_tensor* Cs, mrn_tensor A, const mrn_tensor* Bs, const mrn_tensor* biases, int n, int transA, float beta, int* fused);
 /* AffineNodeOp forward (Prod + Add(_1, val, bias)): node_operators_binary.h:172-186 */
 int mrn_prod_affine(void* gemm, mrn_tensor C, mrn_tensor A, mrn_tensor B, mrn_tensor bias);
 

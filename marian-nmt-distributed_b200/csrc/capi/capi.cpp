@@ -143,6 +143,29 @@ int mrn_prod_grouped_nt(void* g, mrn_tensor C, const mrn_tensor* As, const mrn_t
     ProdGroupedNT((GemmHandle)g, wrap(C), wrapAll(As, n), wrapAll(Bs, n), beta);
   });
 }
+int mrn_prod_shared_a(void* g, const mrn_tensor* Cs, mrn_tensor A, const mrn_tensor* Bs, const mrn_tensor* biases, int n, int tA, float beta, int* fused) {
+  return guarded([&] {
+    gemmInvalidateCache((GemmHandle)g);
+    auto cs = wrapAll(Cs, n), bs = wrapAll(Bs, n);
+    std::vector<Tensor> bias;
+    if(biases)
+      bias = wrapAll(biases, n);
+    Tensor a = wrap(A);
+    bool done = ProdSharedA((GemmHandle)g, cs, a, bs, bias, tA != 0, beta);
+    if(!done) {  // the products one by one, as callers of ProdSharedA do
+      for(int i = 0; i < n; ++i) {
+        if(!bias.empty() && !tA && beta == 0.f)
+          ProdAffine((GemmHandle)g, cs[i], a, bs[i], bias[i]);
+        else {
+          ABORT_IF(!bias.empty(), "mrn_prod_shared_a: a bias needs a non-transposed, non-accumulating product");
+          Prod((GemmHandle)g, cs[i], a, bs[i], tA != 0, false, beta, 1.f);
+        }
+      }
+    }
+    if(fused)
+      *fused = done ? 1 : 0;
+  });
+}
 int mrn_prod_swish_grad_nt(void* g, mrn_tensor C, mrn_tensor A, mrn_tensor B, mrn_tensor H, float beta) {
   return guarded([&] {
     gemmInvalidateCache((GemmHandle)g);

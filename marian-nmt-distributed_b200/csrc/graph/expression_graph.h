@@ -266,6 +266,13 @@ public:
             }
           }
         }
+        if(!pending) {  // (a node computed together with its successors must not race with side-stream producers)
+          std::vector<Expr> upcoming;
+          auto it = nodesForward_.begin();
+          for(++it; it != nodesForward_.end() && upcoming.size() < 2; ++it)
+            upcoming.push_back(*it);
+          v->fuseForward(upcoming);
+        }
         v->forward();
       }
       if(inferenceOnly_)

@@ -40,6 +40,7 @@ struct Chainable {
   virtual void forward() = 0;
   virtual void backward() = 0;
   virtual void fuseBackward(const std::vector<std::shared_ptr<Chainable<DataType>>>& /*upcoming*/) {}
+  virtual void fuseForward(const std::vector<std::shared_ptr<Chainable<DataType>>>& /*upcoming*/) {}
   virtual NodeOps forwardOps() = 0;
   virtual NodeOps backwardOps() = 0;
 
@@ -144,6 +145,9 @@ public:
   // first).  Their adjoints are complete (all their consumers precede them in the sweep and this
   // node is none of them), so a node may take over part of their backward work and mark them.
   virtual void fuseBackward(const std::vector<Expr>& /*upcoming*/) {}
+  // Peephole of the forward pass: `upcoming` holds the nodes that run right after this one (next first); a node may
+  // compute their values together with its own (after allocating them) and mark them done.
+  virtual void fuseForward(const std::vector<Expr>& /*upcoming*/) {}
 
   virtual bool trainable() { return trainable_; }
   virtual void setTrainable(bool trainable) { trainable_ = trainable; }

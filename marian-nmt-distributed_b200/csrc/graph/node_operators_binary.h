@@ -119,7 +119,41 @@ struct AffineNodeOp : public NaryNodeOp {
   }
 
   NodeOps forwardOps() {
-    return {NodeOp(ProdAffine(getBackend()->getGemmHandle(), val_, child(0)->val(), child(1)->val(), child(2)->val()))};
+    return {NodeOp(if(!forwardDone_) ProdAffine(getBackend()->getGemmHandle(), val_, child(0)->val(), child(1)->val(), child(2)->val()))};
+  }
+  // Projections of the SAME input that follow each other on the tape (key / value / query of an attention block): their
+  // values come out of ONE product launch (kernels/gemm.cu ProdSharedA); the partners are allocated here and marked done.
+  bool forwardDone_{false};
+  bool weightGradDone_{false};
+  static std::vector<AffineNodeOp*> sameInputGroup(AffineNodeOp* first, const std::vector<Expr>& upcoming) {
+    std::vector<AffineNodeOp*> group{first};
+    for(auto& u : upcoming) {
+      auto* a = dynamic_cast<AffineNodeOp*>(u.get());
+      if(!a || a->child(0) != first->child(0) || a->shape() != first->shape() || a->child(1)->shape() != first->child(1)->shape() || a->child(2)->shape() != first->child(2)->shape())
+        break;
+      group.push_back(a);
+    }
+    return group;
+  }
+  void fuseForward(const std::vector<Expr>& upcoming) {
+    if(forwardDone_)
+      return;
+    auto group = sameInputGroup(this, upcoming);
+    if(group.size() < 2)
+      return;
+    for(auto* a : group)
+      if(a->forwardDone_ || a->concurrent() || !a->child(1)->val() || !a->child(2)->val())
+        return;
+    std::vector<Tensor> vals, weights, biases;
+    for(auto* a : group) {
+      a->allocate();
+      vals.push_back(a->val_);
+      weights.push_back(a->child(1)->val());
+      biases.push_back(a->child(2)->val());
+    }
+    if(ProdSharedA(getBackend()->getGemmHandle(), vals, child(0)->val(), weights, biases, false, 0.f))
+      for(auto* a : group)
+        a->forwardDone_ = true;
   }
   // Projections of the SAME input that follow each other in the backward sweep (query / key / value
   // of an attention block): dX = sum_g adj_g W_g^T is issued as one K-grouped product instead of a
@@ -188,6 +222,21 @@ struct AffineNodeOp : public NaryNodeOp {
       a->inputGradDone_ = true;
       a->biasGradDone_ = allBias;
     }
+    // ... and their weight gradients dW_g += X^T adj_g as one launch as well (off the critical path)
+    bool allWeights = true;
+    std::vector<Tensor> weightGrads;
+    for(auto* a : group) {
+      allWeights = allWeights && a->child(1)->trainable() && a->child(1)->type() == "param" && !a->weightGradDone_;
+      if(allWeights)
+        weightGrads.push_back(a->child(1)->grad());
+    }
+    if(allWeights) {
+      bool done = false;
+      offCriticalPath(child(1), [&] { done = ProdSharedA(getBackend()->getGemmHandle(), weightGrads, child(0)->val(), adjs, {}, true, 1.f); });
+      if(done)
+        for(auto* a : group)
+          a->weightGradDone_ = true;
+    }
   }
   NodeOps backwardOps() {
     using namespace functional;
@@ -202,7 +251,10 @@ struct AffineNodeOp : public NaryNodeOp {
                 Prod(getBackend()->getGemmHandle(), child(0)->grad(), adj_, child(1)->val(), false, true, 1.0);
               }
             })),
-            NodeOp(offCriticalPath(child(1), [&] { Prod(getBackend()->getGemmHandle(), child(1)->grad(), child(0)->val(), adj_, true, false, 1.0); })),
+            NodeOp(offCriticalPath(child(1), [&] {
+              if(!weightGradDone_)
+                Prod(getBackend()->getGemmHandle(), child(1)->grad(), child(0)->val(), adj_, true, false, 1.0);
+            })),
             NodeOp(offCriticalPath(child(2), [&] {
               if(!biasGradDone_) {
                 ABORT_IF(adj_->memory()->fp32Skipped, "affine: bias gradient needs the fp32 adjoint, but only its bf16 copy was written");

@@ -47,6 +47,7 @@
 #include <cstdlib>
 #include <string>
 #include <unordered_map>
+#include <type_traits>
 #include <unordered_set>
 
 #include "kernels/cuda_helpers.h"
@@ -2297,6 +2298,147 @@ inline bool tmaUsableBf16(const float* p, int cols, size_t batchStride) {
   return (((uintptr_t)p) & 31) == 0 && (cols & 7) == 0 && (batchStride & 7) == 0;
 }
 
+
+// ---- products that share their A operand, in one launch ("N-grouped") ---------------------------------------------
+// The query / key / value projections of an attention block multiply the SAME activations by three weight matrices, and
+// their weight gradients multiply the same X^T by three adjoints: three launches of 200 (160) CTAs each, the two extra
+// ones on the side stream.  Here the tile columns of ONE grid walk the groups: group g = its own B tensor map, bias and
+// C tensor map (outputs stay separate tensors); B is always MN-major (a weight [K, N] or an adjoint [rows, N]), A is
+// K-major (forward) or MN-major (weight gradient, split-K with TMA reduce-add).  Epilogue: TMA stores only.
+template <int NG>
+struct alignas(64) NGroupMaps {
+  CUtensorMap a;
+  CUtensorMap b[NG];
+  CUtensorMap c[NG];
+};
+struct NGroupArgs {
+  const float* bias[3];
+  int groupN;         // columns of one group
+  int tilesPerGroup;  // ceil(groupN / BN)
+};
+
+template <int BN, int STAGES, bool A_MN, int NG>
+__global__ void __launch_bounds__(192, 1) gGemmBf16NGroup(const __grid_constant__ NGroupMaps<NG> tm, TcArgs a, NGroupArgs ga) {
+  typedef TfSmem<BN, STAGES> L;
+  extern __shared__ uint8_t smemRaw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smemRaw + 1023) & ~(uintptr_t)1023);
+  uint64_t* fullBar = (uint64_t*)(smem + L::BAR_OFFSET);
+  uint64_t* emptyBar = fullBar + STAGES;
+  uint64_t* tmemFullBar = emptyBar + STAGES;
+  uint32_t* tmemHolder = (uint32_t*)(tmemFullBar + 1);
+
+  pdlTrigger();
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  auto now = [] {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+  };
+  if(a.spanMin && threadIdx.x == 0)
+    atomicMin(a.spanMin, now());
+
+  const int m0 = blockIdx.x * BLOCK_M;
+  const int grp = blockIdx.y / ga.tilesPerGroup;
+  const int n0 = (blockIdx.y - grp * ga.tilesPerGroup) * BN;  // column inside the group
+  const int split = blockIdx.z;
+  const int kb0 = split * a.kBlocksPerSplit;
+  const int nkb = min(a.kBlocksPerSplit, a.kBlocks - kb0);
+
+  if(warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm.a) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm.b[grp]) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"((uint64_t)&tm.c[grp]) : "memory");
+    for(int s = 0; s < STAGES; ++s) {
+      mbarInit(fullBar + s, 1);
+      mbarInit(emptyBar + s, 1);
+    }
+    mbarInit(tmemFullBar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if(warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smemAddr(tmemHolder)), "r"((uint32_t)BN));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tcgenFenceBefore();
+  __syncthreads();
+  tcgenFenceAfter();
+  const uint32_t tmemBase = *tmemHolder;
+  pdlWait();
+
+  if(warp == 0) {
+    if(lane == 0) {
+      for(int i = 0; i < nkb; ++i) {
+        int s = i % STAGES;
+        uint32_t phase = (uint32_t)(i / STAGES) & 1u;
+        mbarWait(emptyBar + s, phase ^ 1u);
+        mbarExpectTx(fullBar + s, (uint32_t)L::STAGE_BYTES);
+        uint8_t* sa = smem + s * L::STAGE_BYTES;
+        uint8_t* sb = sa + L::A_BYTES;
+        const int kc = (kb0 + i) * BF_BLOCK_K;
+        if(A_MN) {
+#pragma unroll
+          for(int c = 0; c < BLOCK_M / 64; ++c)
+            tmaLoad3D(&tm.a, fullBar + s, sa + c * 8192, m0 + 64 * c, kc, 0);
+        } else {
+          tmaLoad3D(&tm.a, fullBar + s, sa, kc, m0, 0);
+        }
+#pragma unroll
+        for(int c = 0; c < BN / 64; ++c)
+          tmaLoad3D(&tm.b[grp], fullBar + s, sb + c * 8192, n0 + 64 * c, kc, 0);
+      }
+    }
+  } else if(warp == 1) {
+    if(lane == 0) {
+      constexpr uint32_t idesc = makeInstrDescBf16(BLOCK_M, BN, A_MN, true);
+      constexpr uint32_t stepA = A_MN ? (2048 >> 4) : (32 >> 4);
+      constexpr uint32_t stepB = 2048 >> 4;
+      for(int i = 0; i < nkb; ++i) {
+        int s = i % STAGES;
+        uint32_t phase = (uint32_t)(i / STAGES) & 1u;
+        mbarWait(fullBar + s, phase);
+        tcgenFenceAfter();
+        uint32_t sa = smemAddr(smem + s * L::STAGE_BYTES);
+        uint32_t sb = sa + L::A_BYTES;
+        uint64_t descA = makeSmemDescBf16<A_MN>(sa);
+        uint64_t descB = makeSmemDescBf16<true>(sb);
+#pragma unroll
+        for(int k = 0; k < BF_BLOCK_K / UMMA_K; ++k)
+          umma(tmemBase, descA + (uint64_t)(k * stepA), descB + (uint64_t)(k * stepB), idesc, (uint32_t)((i | k) != 0));
+        ummaCommit(emptyBar + s);
+      }
+      ummaCommit(tmemFullBar);
+    }
+  } else {
+    TcArgs al = a;  // this group's view: its bias, its column count (the C tensor map clips the rest)
+    al.bias = ga.bias[grp];
+    al.N = ga.groupN;
+    epilogueTileTma<BN, false>(al, &tm.c[grp], tmemBase, tmemFullBar, smem + (warp - 2) * 8192, warp, lane, m0, n0, 0, split);
+  }
+
+  tcgenFenceBefore();
+  __syncthreads();
+  if(a.spanMax && threadIdx.x == 0)
+    atomicMax(a.spanMax, now());
+  if(warp == 1) {
+    __syncwarp();
+    tcgenFenceAfter();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmemBase), "r"((uint32_t)BN));
+  }
+}
+
+template <int BN, int STAGES, bool A_MN, int NG>
+void launchBf16NGroup(const NGroupMaps<NG>& tm, const TcArgs& a, const NGroupArgs& ga) {
+  typedef TfSmem<BN, STAGES> L;
+  static bool configured = false;
+  if(!configured) {
+    CUDA_CHECK(cudaFuncSetAttribute(gGemmBf16NGroup<BN, STAGES, A_MN, NG>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL));
+    configured = true;
+  }
+  dim3 grid((a.M + BLOCK_M - 1) / BLOCK_M, NG * ga.tilesPerGroup, a.splits);
+  launchPdl(gGemmBf16NGroup<BN, STAGES, A_MN, NG>, grid, dim3(192), (size_t)L::TOTAL, cudaStreamOfEngine(), tm, a, ga);
+}
+
 // Returns false when an operand cannot be described by a tensor map; the caller then takes the packed path.
 bool runBf16(GemmHandle h, const GemmProblem& p) {
   if(!tmaUsableBf16(p.A->rawData(), p.colsA, p.strideA) || !tmaUsableBf16(p.B->rawData(), p.colsB, p.strideB))
@@ -2614,6 +2756,91 @@ void ProdSwishGradNT(GemmHandle h, Tensor C, const Tensor A, const Tensor B, con
   if(C->takeLazyZero())
     p.beta = 0.f;
   ABORT_IF(!directMode(h) || !runDirect(h, p), "ProdSwishGradNT: not supported for these operands (check ProdSwishGradFusable first)");
+}
+
+// C_g = beta C_g + op(A) B_g (+ bias_g) for 2 or 3 products that share A, as ONE launch (bf16 shadow mode, TMA epilogue).
+// Returns false (nothing done) when the operands do not fit; the caller then issues the products one by one.
+bool ProdSharedA(GemmHandle h, const std::vector<Tensor>& Cs, const Tensor A, const std::vector<Tensor>& Bs, const std::vector<Tensor>& biases, bool transA, float beta) {
+  static const bool disabled = std::getenv("MRN_NO_NGROUP") != nullptr;
+  const int NG = (int)Cs.size();
+  if(disabled || h->mode != GemmMode::BF16S || NG < 2 || NG > 3 || Bs.size() != Cs.size() || (!biases.empty() && biases.size() != Cs.size()) || (beta != 0.f && beta != 1.f))
+    return false;
+  const int colsA = A->shape().back(), rowsA = (int)(A->shape().elements() / colsA);
+  const int M = transA ? colsA : rowsA, K = transA ? rowsA : colsA;
+  const int N = Bs[0]->shape().back(), rowsB = (int)(Bs[0]->shape().elements() / N);
+  if(rowsB != K || (N & 7) != 0 || (colsA & 7) != 0 || !tmaUsableBf16(A->rawData(), colsA, 0))
+    return false;
+  for(int g = 0; g < NG; ++g) {
+    if(Bs[g]->shape() != Bs[0]->shape() || (long)Cs[g]->size() != (long)M * N || Cs[g]->isLazyZero() || !tmaUsableBf16(Bs[g]->rawData(), N, 0) || (((uintptr_t)Cs[g]->rawData()) & 15) != 0
+       || Cs[g]->memory()->shadowWanted)
+      return false;
+    if(!biases.empty() && (int)biases[g]->size() != N)
+      return false;
+  }
+  device::setDevice(Cs[0]->getDevice());
+  const int kBlocks = (K + BF_BLOCK_K - 1) / BF_BLOCK_K;
+  const long mTiles = (M + BLOCK_M - 1) / BLOCK_M;
+  // one wave of two CTAs per SM where possible: 64-wide tiles unless they overflow it, split-K for short grids (weight gradients)
+  int BN = (mTiles * NG * ((N + 63) / 64) > 2 * kNumSMs && N >= 128) ? 128 : 64;
+  const long tiles = mTiles * NG * ((N + BN - 1) / BN);
+  int splits = 1;
+  if(beta == 1.f && kBlocks >= 16 && tiles * 2 <= 2 * kNumSMs)
+    splits = (int)std::max<long>(1, std::min<long>((2 * kNumSMs) / tiles, kBlocks / 4));
+
+  NGroupMaps<3> tm3;
+  tm3.a = makeTensorMapBf16(h, ensureShadow(h, A), (uint64_t)colsA, (uint64_t)rowsA, 1, (uint64_t)colsA, 0, transA ? BF_BLOCK_K : BLOCK_M);
+  NGroupArgs ga = {};
+  ga.groupN = N;
+  ga.tilesPerGroup = (N + BN - 1) / BN;
+  for(int g = 0; g < NG; ++g) {
+    tm3.b[g] = makeTensorMapBf16(h, ensureShadow(h, Bs[g]), (uint64_t)N, (uint64_t)K, 1, (uint64_t)N, 0, BF_BLOCK_K);
+    tm3.c[g] = makeTensorMapC(h, Cs[g]->data(), (uint64_t)N, (uint64_t)M, 1);
+    ga.bias[g] = biases.empty() ? nullptr : biases[g]->data();
+  }
+  TcArgs a = {};
+  a.M = M;
+  a.N = N;
+  a.ldc = N;
+  a.kBlocks = kBlocks;
+  a.kBlocksGroup = kBlocks;
+  a.kBlocksPerSplit = (kBlocks + splits - 1) / splits;
+  splits = (kBlocks + a.kBlocksPerSplit - 1) / a.kBlocksPerSplit;
+  a.splits = splits;
+  a.atomicOut = splits > 1;
+  a.alpha = 1.f;
+  a.beta = beta;
+  a.tmaStore = (beta == 1.f || splits > 1) ? 2 : 1;
+  ABORT_IF(splits > 1 && beta != 1.f, "ProdSharedA: split-K needs an accumulating product");
+  ProfileScope prof(2.0 * M * N * K * NG);
+  a.spanMin = prof.spanMin;
+  a.spanMax = prof.spanMax;
+  auto launch = [&](auto ngTag) {
+    constexpr int G = decltype(ngTag)::value;
+    NGroupMaps<G> tm;
+    tm.a = tm3.a;
+    for(int g = 0; g < G; ++g) {
+      tm.b[g] = tm3.b[g];
+      tm.c[g] = tm3.c[g];
+    }
+    if(BN == 128) {
+      if(transA)
+        launchBf16NGroup<128, 3, true, G>(tm, a, ga);
+      else
+        launchBf16NGroup<128, 3, false, G>(tm, a, ga);
+    } else {
+      if(transA)
+        launchBf16NGroup<64, 4, true, G>(tm, a, ga);
+      else
+        launchBf16NGroup<64, 4, false, G>(tm, a, ga);
+    }
+  };
+  if(NG == 2)
+    launch(std::integral_constant<int, 2>());
+  else
+    launch(std::integral_constant<int, 3>());
+  if(prof.on)
+    prof.finish(std::to_string(M) + "," + std::to_string(N * NG) + "," + std::to_string(K) + ",1," + (transA ? "T" : "N") + "N," + std::to_string(BN) + "," + std::to_string(splits) + "," + std::to_string(beta));
+  return true;
 }
 
 void Prod(GemmHandle h, Tensor C, const Tensor A, const Tensor B, bool transA, bool transB, float beta, float scalar) {

@@ -96,6 +96,9 @@ void Prod(GemmHandle handle, Tensor C, const Tensor A, const Tensor B, bool tran
 // C = beta C + sum_g A_g B_g^T: the input gradient of several projections of one tensor, as ONE K-grouped launch
 // colSums (optional, one per pair): colSums[g] += column sums of A_g - the bias gradients, summed from the A tiles the product streams anyway
 void ProdGroupedNT(GemmHandle handle, Tensor C, const std::vector<Tensor>& As, const std::vector<Tensor>& Bs, float beta = 0, const std::vector<Tensor>& colSums = {});
+// C_g = beta C_g + op(A) B_g (+ bias_g): 2 or 3 products that share their A operand as ONE launch (the q / k / v projections of
+// an attention block, their weight gradients).  false = not applicable here, nothing was done (issue them one by one).
+bool ProdSharedA(GemmHandle handle, const std::vector<Tensor>& Cs, const Tensor A, const std::vector<Tensor>& Bs, const std::vector<Tensor>& biases, bool transA, float beta);
 bool ProdColumnSumsFusable(GemmHandle handle, const Tensor A);
 // C = beta C + (A B^T) o swish'(H): "affine after swish" backward in the product's epilogue (tf32 tensor-core path only)
 bool ProdSwishGradFusable(GemmHandle handle, const Tensor C, const Tensor A, const Tensor B, const Tensor H);

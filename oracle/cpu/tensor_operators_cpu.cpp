@@ -391,6 +391,9 @@ bool ProdSwishGradFusable(GemmHandle, const Tensor, const Tensor, const Tensor, 
 bool ProdColumnSumsFusable(GemmHandle, const Tensor) {
   return false;
 }
+bool ProdSharedA(GemmHandle, const std::vector<Tensor>&, const Tensor, const std::vector<Tensor>&, const std::vector<Tensor>&, bool, float) {
+  return false;  // the oracle issues the reference's products one by one
+}
 void ProdSwishGradNT(GemmHandle, Tensor, const Tensor, const Tensor, const Tensor, float, Tensor) {
   ABORT("ProdSwishGradNT is not available on the CPU oracle");
 }

@@ -238,3 +238,40 @@ def test_gemm_full_size_logits_shapes_throughput_modes(cuda):
         else:
             for k in got:
                 close(got[k], ref[k], TOL[mode], "mode %d %s" % (mode, k))
+
+
+@pytest.mark.parametrize("M,K,N,n,tA,beta,bias", [
+    (3200, 512, 512, 3, False, 0.0, True),    # q / k / v projections of config B
+    (3200, 512, 512, 2, False, 0.0, True),    # key / value of a cross-attention block
+    (3200, 512, 512, 3, True, 1.0, False),    # their weight gradients: X^T adj_g, split-K with TMA reduce-add
+    (304, 72, 136, 3, False, 0.0, True),      # ragged tiles
+    (304, 72, 136, 2, True, 1.0, False),
+    (2560, 1024, 1024, 3, False, 0.0, True),  # Transformer-big geometry: 128-wide tiles
+])
+def test_prod_shared_a(cuda, M, K, N, n, tA, beta, bias):
+    """Products that share their A operand as one launch (bf16 shadow mode) vs float64 and vs the single products."""
+    import ctypes
+
+    A = rnd(1, K, M) if tA else rnd(1, M, K)
+    Bs = [rnd(10 + i, (M if tA else K), N) for i in range(n)]
+    rows = K if tA else M                      # C = op(A) B: [K, N] for the weight-gradient form
+    Cs0 = [rnd(20 + i, rows, N) for i in range(n)]
+    bs = [rnd(30 + i, 1, N) for i in range(n)] if bias else None
+    a64 = A.astype(np.float64)
+    exp = [beta * Cs0[i] + (a64.T if tA else a64) @ Bs[i].astype(np.float64) + (bs[i] if bias else 0.0) for i in range(n)]
+    out = {}
+    for mode in (4, 1):
+        g = cuda.gemm(mode)
+        cs = [cuda.array(c) for c in Cs0]
+        b = [cuda.array(x) for x in Bs]
+        bb = [cuda.array(x) for x in bs] if bias else None
+        fused = ctypes.c_int(-1)
+        cuda.call("mrn_prod_shared_a", g.h, cuda.tensor_list([c.t() for c in cs]), cuda.array(A).t(), cuda.tensor_list([x.t() for x in b]),
+                  cuda.tensor_list([x.t() for x in bb]) if bias else None, n, int(tA), beta, ctypes.byref(fused))
+        cuda.synchronize()
+        out[mode] = [c.numpy() for c in cs]
+        assert fused.value == (1 if mode == 4 else 0)
+        for i in range(n):
+            close(out[mode][i], exp[i], TOL[mode], "shared-A product %d, mode %d" % (i, mode))
+    for i in range(n):
+        close(out[4][i], out[1][i], 2e-5, "one launch vs single packed products")
