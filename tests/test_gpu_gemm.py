@@ -252,7 +252,7 @@ def test_prod_shared_a(cuda, M, K, N, n, tA, beta, bias):
     """Products that share their A operand as one launch (bf16 shadow mode) vs float64 and vs the single products."""
     import ctypes
 
-    A = rnd(1, K, M) if tA else rnd(1, M, K)
+    A = rnd(1, M, K)                           # stored [M, K]; the weight-gradient form contracts over its rows (op(A) = A^T)
     Bs = [rnd(10 + i, (M if tA else K), N) for i in range(n)]
     rows = K if tA else M                      # C = op(A) B: [K, N] for the weight-gradient form
     Cs0 = [rnd(20 + i, rows, N) for i in range(n)]
