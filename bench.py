@@ -297,10 +297,15 @@ def main():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="N > 1: gradient exchange by peer-memory kernels over NVLink (default) or NCCL reduce-scatter / all-gather")
     ap.add_argument("--oracle-child", default=None, help=argparse.SUPPRESS)
+    ap.add_argument("--traffic-child", action="store_true", help=argparse.SUPPRESS)
+    ap.add_argument("--no-traffic", action="store_true", help="skip the ncu pass that measures the GEMM family's DRAM traffic")
     args = ap.parse_args()
 
     if args.oracle_child:
         oracle_child(args.oracle_child)
+        return
+    if args.traffic_child:
+        traffic_child(args)
         return
 
     rank = int(os.environ.get("RANK", "0"))
@@ -460,14 +465,17 @@ def main():
             main_ = spans if spans else prof
             out["roofline"] = {"bound": "tensor", "achieved": main_["tflops"], "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
                                "frac": main_["tflops"] / pk["bf16_tflops_sustained"],
-                               "traffic": None,
-                               "traffic_note": "not measured inside this run (needs an ncu pass): see profiles/gemm_dram_r*.md for the committed capture",
+                               "traffic": None, "traffic_unit": "DRAM bytes per launch (mean over the step's GEMM launches)",
                                "algorithmic_flop_per_launch": prof["gflop"] * 1e9 / prof["launches"], "peak_source": pk_src,
                                "kernel": "tcgen05 GEMM family (all Prod/ProdBatched/ProdAffine launches of one replayed step)",
                                "duration_source": "in-kernel %globaltimer spans" if spans else "CUDA event pairs inside the graph",
                                "launches_per_step": prof["launches"], "gemm_ms_per_step": main_["ms"], "gflop_per_step": prof["gflop"],
                                "cuda_event_pairs": {"gemm_ms_per_step": prof["ms"], "achieved": prof["tflops"], "frac": prof["tflops"] / pk["bf16_tflops_sustained"],
                                                     "note": "each pair includes ~6.7 us of event-record node latency"}}
+        if prof and not args.no_traffic:
+            traffic, detail = measure_gemm_traffic(args, prof["launches"])
+            out["roofline"]["traffic"] = traffic
+            out["roofline"]["traffic_detail"] = detail
         # ---- CPU oracle (child process): parity vectors of step 1 + the timed CPU baseline ----
         if world == 1 and not (args.no_cpu_baseline and args.no_parity):
             dump = os.path.join(tempfile.gettempdir(), "mrn_oracle_logits_%d.npy" % os.getpid())
@@ -489,6 +497,62 @@ def main():
         print(json.dumps(out))
     if world > 1:
         torch.distributed.destroy_process_group()
+
+
+def traffic_child(args):
+    """Runs under ncu (measure_gemm_traffic): two EAGER steps of the benchmarked configuration - every GEMM is an
+    ordinary launch; the parent takes the launches of the second step."""
+    pkg = graft.load_package()
+    lib = pkg.load()
+    opts, B, L, _ = model_config(args.model, pkg, args.gemm_mode)
+    opts["graph-replay"] = "false"
+    t = lib.trainer(opts)
+    for _ in range(2):
+        t.next_synthetic_batch(B, L, L, padded=False)
+        t.compute_gradients()
+        t.update()
+        t.cost()
+    t.close()
+
+
+def measure_gemm_traffic(args, launches_per_step):
+    """DRAM bytes of the GEMM family, measured in THIS run: one `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum`
+    pass over the GEMM kernels of an eager step in a child process.  Returns (mean bytes per launch, detail) or
+    (None, reason) when ncu is unavailable / fails / takes too long."""
+    import csv
+    import shutil
+
+    ncu = shutil.which("ncu") or ("/usr/local/cuda/bin/ncu" if os.path.exists("/usr/local/cuda/bin/ncu") else None)
+    if not ncu:
+        return None, "ncu not found"
+    log = os.path.join(tempfile.gettempdir(), "mrn_gemm_traffic_%d.csv" % os.getpid())
+    cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k", "regex:gGemm", "--csv", "--log-file", log,
+           sys.executable, os.path.abspath(__file__), "--traffic-child", "--model", args.model, "--gemm-mode", str(args.gemm_mode)]
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=float(os.environ.get("MRN_TRAFFIC_BUDGET_S", "150")))
+    except subprocess.TimeoutExpired:
+        return None, "ncu pass exceeded its wall budget"
+    if r.returncode != 0 or not os.path.exists(log):
+        return None, "ncu pass failed (rc %d)" % r.returncode
+    per_id = {}
+    with open(log, newline="") as fh:
+        lines = [ln for ln in fh if not ln.startswith("==")]
+    for row in csv.DictReader(lines):
+        if row.get("Metric Name") not in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            continue
+        v = float(row["Metric Value"].replace(",", "")) * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(row.get("Metric Unit", "byte"), 1)
+        per_id.setdefault(int(row["ID"]), [0.0, 0.0])[0 if row["Metric Name"].endswith("read.sum") else 1] += v
+    try:
+        os.unlink(log)
+    except OSError:
+        pass
+    ids = sorted(per_id)
+    if len(ids) < 2:
+        return None, "ncu pass saw no GEMM launches"
+    step = ids[len(ids) // 2:]  # second of the two eager steps
+    rd, wr = sum(per_id[i][0] for i in step), sum(per_id[i][1] for i in step)
+    return (rd + wr) / len(step), {"launches": len(step), "dram_read_bytes_per_step": rd, "dram_write_bytes_per_step": wr,
+                                    "source": "ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum -k regex:gGemm over an eager step, measured in this run"}
 
 
 def parity_vs_oracle(lib, opts, B, L, padded, device, cost_ref, logits_ref, row_stride, mode):

@@ -205,6 +205,13 @@ int mrn_trainer_next_synthetic_batch(void* trainer, int batch_size, int max_len_
  * split when nranks > 1); *has_batch = 0 marks the end of an epoch. */
 int mrn_trainer_open_corpus(void* trainer, const char* src_path, const char* trg_path, const char* vocab_src, const char* vocab_trg, const char* options);
 int mrn_trainer_next_corpus_batch(void* trainer, int* has_batch);
+/* Cross-entropy validation (reference CrossEntropyValidator, src/training/validator.h:108-176): forward passes of an
+ * inference-mode model (no dropout, cost-type ce-sum) over a held-out text corpus on the trainer's own parameters;
+ * *metric follows "cost-type" of the options (cross-entropy / ce-mean: cost per sentence, ce-mean-words, perplexity,
+ * ce-sum); cost_sum / sentences / target_words receive the totals (may be NULL).  options as for
+ * mrn_trainer_open_corpus plus "valid-mini-batch", "valid-max-length".  Blocking; parameters are not changed. */
+int mrn_trainer_validate(void* trainer, const char* src_path, const char* trg_path, const char* vocab_src, const char* vocab_trg, const char* options, float* metric, float* cost_sum,
+                         size_t* sentences, size_t* target_words);
 /* the current batch as host arrays in the SubBatch layout (time-major [T, B]); side 0 = source, 1 = target;
  * indices / mask may be NULL to query batch_size and width */
 int mrn_trainer_get_batch(void* trainer, int side, int64_t* indices, float* mask, size_t capacity, int* batch_size, int* width);

@@ -85,6 +85,7 @@ _SIGNATURES = {
     "mrn_trainer_open_corpus": [_V, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p],
     "mrn_trainer_next_corpus_batch": [_V, ctypes.POINTER(_I)],
     "mrn_trainer_get_batch": [_V, _I, _V, _V, _SZ, ctypes.POINTER(_I), ctypes.POINTER(_I)],
+    "mrn_trainer_validate": [_V, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, c_float_p, c_float_p, ctypes.POINTER(_SZ), ctypes.POINTER(_SZ)],
     "mrn_trainer_compute_gradients": [_V, _I],
     "mrn_trainer_update": [_V],
     "mrn_trainer_update_shard": [_V],
@@ -318,6 +319,15 @@ class Trainer:
         has = ctypes.c_int()
         self.lib._ck(self.lib.c.mrn_trainer_next_corpus_batch(self.h, ctypes.byref(has)))
         return bool(has.value)
+
+    def validate(self, src_path, trg_path, vocab_src=None, vocab_trg=None, options=""):
+        """Cross-entropy validation on a held-out corpus: {"metric", "cost_sum", "sentences", "target_words"}."""
+        enc = lambda x: None if x is None else str(x).encode()
+        m, c = ctypes.c_float(), ctypes.c_float()
+        n, w = ctypes.c_size_t(), ctypes.c_size_t()
+        self.lib._ck(self.lib.c.mrn_trainer_validate(self.h, enc(src_path), enc(trg_path), enc(vocab_src), enc(vocab_trg), options.encode(), ctypes.byref(m), ctypes.byref(c),
+                                                     ctypes.byref(n), ctypes.byref(w)))
+        return {"metric": m.value, "cost_sum": c.value, "sentences": n.value, "target_words": w.value}
 
     def get_batch(self, side):
         """(indices [T, B] int64, mask [T, B] float32) of the current batch."""

@@ -13,6 +13,7 @@
 #include "kernels/tensor_operators.h"
 #include "training/checkpoint.h"
 #include "training/graph_group.h"
+#include "training/validator.h"
 
 using namespace marian;
 
@@ -493,6 +494,36 @@ int mrn_trainer_next_corpus_batch(void* trainer, int* hasBatch) {
       t->textBatches->restart();
       *hasBatch = 0;
     }
+  });
+}
+// cross-entropy validation on a held-out corpus (training/validator.h; reference training/validator.h:108-176)
+int mrn_trainer_validate(void* trainer, const char* srcPath, const char* trgPath, const char* vocabSrc, const char* vocabTrg, const char* options, float* metric, float* costSum,
+                         size_t* sentences, size_t* targetWords) {
+  return guarded([&] {
+    auto t = (Trainer*)trainer;
+    auto graph = t->worker().graph();
+    ABORT_IF(graph->params()->size() == 0, "mrn_trainer_validate: the model has no parameters yet (run a step or load a checkpoint first)");
+    auto o = t->options->clone();
+    o->overwrite(Options(options ? options : ""));
+    std::vector<std::string> paths{srcPath, trgPath};
+    std::vector<std::string> vocabPaths{vocabSrc ? vocabSrc : "", vocabTrg ? vocabTrg : ""};
+    auto dims = t->options->get<std::vector<int>>("dim-vocabs");
+    std::vector<Ptr<data::Vocab>> vocabs;
+    for(size_t i = 0; i < 2; ++i) {
+      auto v = New<data::Vocab>();
+      v->loadOrCreate(vocabPaths[i], paths[i], dims[i]);
+      vocabs.push_back(v);
+    }
+    CrossEntropyValidator validator(vocabs, o);
+    float sum = 0;
+    size_t n = 0, w = 0;
+    *metric = validator.validate(graph, paths, &sum, &n, &w);
+    if(costSum)
+      *costSum = sum;
+    if(sentences)
+      *sentences = n;
+    if(targetWords)
+      *targetWords = w;
   });
 }
 // current batch as host arrays (time-major [T, B], the SubBatch layout); side 0 = source, 1 = target

@@ -124,3 +124,42 @@ def test_training_on_text_batches_learns(oracle, tmp_path):
             costs.append(t.cost() / max(1, t.batch_words()[1]))
     assert np.mean(costs[-6:]) < 0.8 * np.mean(costs[:6]), (costs[:6], costs[-6:])
     t.close()
+
+
+def test_cross_entropy_validation(oracle, tmp_path):
+    """CrossEntropyValidator (csrc/training/validator.h; reference src/training/validator.h:108-176): forward-only
+    passes over a held-out corpus on the trainer's parameters, reported per cost-type; training goes on unchanged."""
+    write_corpus(tmp_path, n=96, max_len=8)
+    dev = tmp_path / "dev"
+    dev.mkdir()
+    write_corpus(dev, n=40, seed=11, max_len=8)
+    vs, vt = str(tmp_path / "train.src") + ".yml", str(tmp_path / "train.trg") + ".yml"
+
+    def train(t, epochs):
+        for _ in range(epochs):
+            while t.next_corpus_batch():
+                t.compute_gradients()
+                t.update()
+                t.cost()
+
+    t = oracle.trainer(OPTS)
+    t.open_corpus(tmp_path / "train.src", tmp_path / "train.trg", options="mini-batch=16;maxi-batch=6;shuffle=false")
+    train(t, 1)
+    before = t.validate(dev / "train.src", dev / "train.trg", vs, vt, "valid-mini-batch=8")
+    p0 = t.arena_numpy("params")
+    again = t.validate(dev / "train.src", dev / "train.trg", vs, vt, "valid-mini-batch=8")
+    assert np.array_equal(p0, t.arena_numpy("params"))                      # validation does not touch the parameters
+    assert again["metric"] == before["metric"]
+    assert before["sentences"] == 40 and before["target_words"] > 40
+    assert abs(before["metric"] - before["cost_sum"] / 40) < 1e-4 * abs(before["metric"])   # ce-mean: cost per sentence
+    words = t.validate(dev / "train.src", dev / "train.trg", vs, vt, "cost-type=ce-mean-words")
+    ppl = t.validate(dev / "train.src", dev / "train.trg", vs, vt, "cost-type=perplexity")
+    assert abs(words["metric"] - words["cost_sum"] / words["target_words"]) < 1e-5 * words["metric"]
+    assert abs(ppl["metric"] - np.exp(words["metric"])) < 1e-3 * ppl["metric"]
+    # batching does not change the summed cost (up to fp32 summation order)
+    other = t.validate(dev / "train.src", dev / "train.trg", vs, vt, "valid-mini-batch=3;cost-type=ce-sum")
+    assert abs(other["metric"] - before["cost_sum"]) < 2e-5 * before["cost_sum"]
+    train(t, 5)
+    after = t.validate(dev / "train.src", dev / "train.trg", vs, vt, "valid-mini-batch=8")
+    assert after["metric"] < 0.9 * before["metric"], (before, after)            # the copy-like task generalises to the dev set
+    t.close()

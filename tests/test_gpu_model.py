@@ -315,3 +315,34 @@ def test_host_running_ahead_does_not_mix_batches(cuda, padded):
     assert abs(out[0][0] - out[1][0]) <= 1e-4 * abs(out[0][0]), (out[0][0], out[1][0])
     diff = np.abs(out[0][1] - out[1][1])
     assert np.mean(diff > 1e-4) < 0.01, (diff.max(), np.mean(diff > 1e-4))
+
+
+def test_text_corpus_training_and_validation_on_gpu(cuda, oracle, tmp_path):
+    """Text corpus -> prefetched mini-batches -> replayed training steps on the GPU, with cross-entropy validation in
+    between (forward-only eager builds on the same graph): the validation result matches the oracle's on the same
+    parameters (checkpoint round trip), and the replayed steps continue undisturbed."""
+    import test_corpus as tc
+
+    tc.write_corpus(tmp_path, n=96, max_len=8)
+    vs, vt = str(tmp_path / "train.src") + ".yml", str(tmp_path / "train.trg") + ".yml"
+    opts = tc.OPTS.replace("gemm-mode=0;graph-replay=false", "gemm-mode=2;graph-replay=true")
+    t = cuda.trainer(opts)
+    t.open_corpus(tmp_path / "train.src", tmp_path / "train.trg", options="mini-batch=16;maxi-batch=6;shuffle=false")
+    costs = []
+    for ep in range(4):
+        while t.next_corpus_batch():
+            t.compute_gradients()
+            t.update()
+            costs.append(t.cost())
+        v = t.validate(tmp_path / "train.src", tmp_path / "train.trg", vs, vt, "valid-mini-batch=8")
+        costs.append(v["metric"])
+    assert t.stats()["replays"] >= 6, t.stats()
+    path = tmp_path / "m.npz"
+    t.save(path)
+    t.close()
+    o = oracle.trainer(tc.OPTS)
+    o.load(path)
+    ref = o.validate(tmp_path / "train.src", tmp_path / "train.trg", vs, vt, "valid-mini-batch=8")
+    o.close()
+    assert abs(v["metric"] - ref["metric"]) <= 1e-4 * abs(ref["metric"]), (v, ref)
+    assert v["metric"] < costs[6], costs   # validation cost after four epochs below the first epoch's
