@@ -569,7 +569,10 @@ def parity_vs_oracle(lib, opts, B, L, padded, device, cost_ref, logits_ref, row_
     t.close()
     scale = max(1e-6, float(np.abs(logits_ref).max()))
     err = float(np.abs(logits.astype(np.float64) - logits_ref).max()) / scale
+    tol = {0: 1e-4, 2: 1e-4, 3: 3e-3}.get(mode, 2e-2)  # the tolerances of tests/test_gpu_fullsize.py
+    rel = abs(cost - cost_ref) / abs(cost_ref)
     return {"mode": MODE_NAMES[mode], "against": "CPU oracle, identical batch and initialisation, step 1",
+            "tolerance": tol, "ok": bool(rel <= tol and err <= tol),
             "cost": cost, "cost_oracle": cost_ref, "cost_rel_err": abs(cost - cost_ref) / abs(cost_ref),
             "logits_max_rel_err": err, "logits_rows_compared": int(logits_ref.shape[0]), "logits_row_stride": row_stride,
             "bar": "1e-4 for the exact modes (f32, bf16x3: tests/test_gpu_fullsize.py); throughput modes report their error"}
