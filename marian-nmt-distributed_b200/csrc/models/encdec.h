@@ -152,6 +152,20 @@ public:
     return std::make_tuple(yMask, yIdx);
   }
 
+  // Decoding: the embeddings of the words chosen in the previous beam-search step become the decoder input,
+  // [beam, 1, batch, dimEmb]; no words yet (first step) = zeros [1, 1, batch, dimEmb].   reference: encdec.h:123-153
+  virtual void selectEmbeddings(Ptr<ExpressionGraph> graph, Ptr<DecoderState> state, const std::vector<size_t>& words, int dimBatch, int dimBeam) {
+    using namespace keywords;
+    const int dimEmb = opt<int>("dim-emb");
+    auto table = embedding(graph)("dimVocab", opt<std::vector<int>>("dim-vocabs")[batchIndex_])("dimEmb", dimEmb);
+    const bool shared = opt<bool>("tied-embeddings-src") || opt<bool>("tied-embeddings-all");
+    table("prefix", shared ? std::string("Wemb") : prefix_ + "_Wemb");
+    Expr E = table.construct();
+    Expr chosen = words.empty() ? graph->constant({1, 1, dimBatch, dimEmb}, init = inits::zeros)
+                                : reshape(rows(E, words), {dimBeam, 1, dimBatch, dimEmb});
+    state->setTargetEmbeddings(chosen);
+  }
+
   virtual const std::vector<Expr> getAlignments(int i = 0) { return {}; }
 
   template <typename T>
@@ -195,6 +209,24 @@ public:
 
   virtual Ptr<DecoderState> step(Ptr<ExpressionGraph> graph, Ptr<DecoderState> state) {
     return decoders_[0]->step(graph, state);
+  }
+
+  // One beam-search step: carry over the states of the surviving hypotheses (`hypIndices`, beam-major rows of the
+  // previous step), feed the words they chose, run the decoder for ONE position, return log-probabilities.
+  // reference: encdec.h:316-335
+  virtual Ptr<DecoderState> step(Ptr<ExpressionGraph> graph, Ptr<DecoderState> state, const std::vector<size_t>& hypIndices,
+                                 const std::vector<size_t>& embIndices, int dimBatch, int beamSize, bool normalized = true) {
+    auto chosen = hypIndices.empty() ? state : state->select(hypIndices, beamSize);
+    selectEmbeddings(graph, chosen, embIndices, dimBatch, beamSize);
+    chosen->setSingleStep(true);
+    auto next = step(graph, chosen);
+    if(normalized)  // the fused top-N kernel normalises the rows itself and wants the raw logits
+      next->setProbs(logsoftmax(next->getProbs()));
+    return next;
+  }
+
+  virtual void selectEmbeddings(Ptr<ExpressionGraph> graph, Ptr<DecoderState> state, const std::vector<size_t>& words, int dimBatch, int beamSize) {
+    decoders_[0]->selectEmbeddings(graph, state, words, dimBatch, beamSize);
   }
 
   // Also exposes the logits node of the last build (parity checks compare logits).

@@ -44,6 +44,14 @@ public:
 
   virtual const rnn::States& getStates() { return states_; }
 
+  // Beam search: the state of the hypotheses `selIdx` (rows of the [beam, batch] layout, beam-major) re-packed as
+  // [beamSize, .., batch, ..].  reference: states.h:52-54
+  virtual Ptr<DecoderState> select(const std::vector<size_t>& selIdx, int beamSize) {
+    return New<DecoderState>(states_.select(selIdx, beamSize), probs_, encStates_);
+  }
+  // hook for decoders that forbid words at some positions (reference: states.h:75); none of the models here does
+  virtual void blacklist(Expr /*totalCosts*/, Ptr<data::CorpusBatch> /*batch*/) {}
+
   virtual Expr getTargetEmbeddings() { return targetEmbeddings_; }
   virtual void setTargetEmbeddings(Expr targetEmbeddings) { targetEmbeddings_ = targetEmbeddings; }
 

@@ -300,6 +300,23 @@ class TransformerState : public DecoderState {
 public:
   TransformerState(const rnn::States& states, Expr probs, std::vector<Ptr<EncoderState>>& encStates)
       : DecoderState(states, probs, encStates) {}
+
+  // The cached layer inputs [beam, batch, time, d] of the chosen hypotheses: hypothesis h owns rows
+  // h*time .. h*time+time-1 of the flattened cache.   reference: transformer.h:461-480
+  virtual Ptr<DecoderState> select(const std::vector<size_t>& selIdx, int beamSize) {
+    const int width = states_[0].output->shape()[-1];
+    const int steps = states_[0].output->shape()[-2];
+    const int sentences = (int)selIdx.size() / beamSize;
+    std::vector<size_t> cacheRows;
+    cacheRows.reserve(selIdx.size() * steps);
+    for(size_t h : selIdx)
+      for(int t = 0; t < steps; ++t)
+        cacheRows.push_back(h * steps + t);
+    rnn::States picked;
+    for(auto& layer : states_)
+      picked.push_back({reshape(rows(flatten_2d(layer.output), cacheRows), {beamSize, sentences, steps, width}), nullptr});
+    return New<TransformerState>(picked, probs_, encStates_);
+  }
 };
 
 class DecoderTransformer : public DecoderBase {
