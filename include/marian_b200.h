@@ -212,6 +212,26 @@ int mrn_trainer_next_corpus_batch(void* trainer, int* has_batch);
  * mrn_trainer_open_corpus plus "valid-mini-batch", "valid-max-length".  Blocking; parameters are not changed. */
 int mrn_trainer_validate(void* trainer, const char* src_path, const char* trg_path, const char* vocab_src, const char* vocab_trg, const char* options, float* metric, float* cost_sum,
                          size_t* sentences, size_t* target_words);
+/* Beam-search decoding on the trainer's parameters (inference mode: no dropout).
+ * Replaces BeamSearch::search + History::NBest (src/translator/beam_search.h:91-225, src/translator/history.h:36-66)
+ * with NthElement::getNBestList (src/translator/nth_element.cu:270-402) underneath.
+ * options: "beam-size=12;normalize=0;allow-unk=false;beam-fused-nth=true" (the reference's option names; beam-fused-nth
+ * selects the fused logsoftmax + n-best kernel instead of the reference's node sequence - same result).
+ * mrn_trainer_translate: SOURCE side of the current batch; for sentence s and rank r < n_best, slot = s*n_best + r:
+ * lengths[slot] words (incl. the final </s> = 0; -1 if there are fewer than n_best hypotheses) at words[slot*max_len ...],
+ * scores[slot] = log-probability / length^normalize, raw_scores[slot] (may be NULL) = log-probability. */
+int mrn_trainer_translate(void* trainer, const char* options, int n_best, int max_len, int64_t* words, int* lengths, float* scores, float* raw_scores);
+/* Text file -> translations, one line per input line in corpus order ("n-best=true": "id ||| words ||| F0= cost ||| cost"
+ * lines), as Translate<BeamSearch>::run does (src/translator/translator.h:22-108, output_collector.cpp).  Further
+ * options: "mini-batch=1;maxi-batch=1;max-length=1000". */
+int mrn_trainer_translate_file(void* trainer, const char* src_path, const char* vocab_src, const char* vocab_trg, const char* options, const char* out_path, size_t* sentences);
+/* n best (value, flat index) pairs of every range [range_first[i], range_first[i+1]) of a device array, best first
+ * (NthElement::getNBestList, src/translator/nth_element.cu:343-361); n_i = cum_n[i+1]-cum_n[i].  Blocking. */
+int mrn_nth_element_ranges(mrn_tensor scores, const int* range_first, const int* cum_n, int ranges, float* out_costs, unsigned* out_keys);
+/* The same selection fused with log-softmax, previous-cost add and per-sentence regrouping, from raw logits
+ * [beam, 1, batch, V] (kernels/nth_element.cu): replaces the node sequence of src/translator/beam_search.h:163-196. */
+int mrn_nth_element_logsoftmax(mrn_tensor logits, const float* prev_costs, int dim_batch, int beam, int n, int first, int suppress_word, float* out_costs, unsigned* out_keys);
+
 /* the current batch as host arrays in the SubBatch layout (time-major [T, B]); side 0 = source, 1 = target;
  * indices / mask may be NULL to query batch_size and width */
 int mrn_trainer_get_batch(void* trainer, int side, int64_t* indices, float* mask, size_t capacity, int* batch_size, int* width);

@@ -22,6 +22,7 @@ CUDA_SOURCES = [
     "kernels/gemm.cu",
     "kernels/attention.cu",
     "kernels/exchange.cu",
+    "kernels/nth_element.cu",
 ]
 # host graph code: instantiates the Element/Add kernel templates, hence nvcc -x cu
 ENGINE_SOURCES = [

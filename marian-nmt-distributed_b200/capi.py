@@ -86,6 +86,10 @@ _SIGNATURES = {
     "mrn_trainer_next_corpus_batch": [_V, ctypes.POINTER(_I)],
     "mrn_trainer_get_batch": [_V, _I, _V, _V, _SZ, ctypes.POINTER(_I), ctypes.POINTER(_I)],
     "mrn_trainer_validate": [_V, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, c_float_p, c_float_p, ctypes.POINTER(_SZ), ctypes.POINTER(_SZ)],
+    "mrn_trainer_translate": [_V, ctypes.c_char_p, _I, _I, _V, _V, _V, _V],
+    "mrn_trainer_translate_file": [_V, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_char_p, ctypes.POINTER(_SZ)],
+    "mrn_nth_element_ranges": [_T, _V, _V, _I, _V, _V],
+    "mrn_nth_element_logsoftmax": [_T, _V, _I, _I, _I, _I, _I, _V, _V],
     "mrn_trainer_compute_gradients": [_V, _I],
     "mrn_trainer_update": [_V],
     "mrn_trainer_update_shard": [_V],
@@ -248,6 +252,23 @@ class Library:
     def gemm(self, mode=0, device=0):
         return Gemm(self, mode, device)
 
+    def nth_element_ranges(self, scores, range_first, cum_n):
+        """(costs, keys): cum_n[i+1]-cum_n[i] best (value, flat index) pairs of every range, best first."""
+        first = np.ascontiguousarray(range_first, dtype=np.int32)
+        cum = np.ascontiguousarray(cum_n, dtype=np.int32)
+        costs = np.zeros(int(cum[-1]), dtype=np.float32)
+        keys = np.zeros(int(cum[-1]), dtype=np.uint32)
+        self._ck(self.c.mrn_nth_element_ranges(scores, first.ctypes.data, cum.ctypes.data, len(first) - 1, costs.ctypes.data, keys.ctypes.data))
+        return costs, keys
+
+    def nth_element_logsoftmax(self, logits, prev_costs, dim_batch, beam, n, first=False, suppress_word=-1):
+        """(costs, keys) of the n best continuations per sentence from raw logits [beam, 1, batch, V]."""
+        prev = np.ascontiguousarray(prev_costs, dtype=np.float32)
+        costs = np.zeros(dim_batch * n, dtype=np.float32)
+        keys = np.zeros(dim_batch * n, dtype=np.uint32)
+        self._ck(self.c.mrn_nth_element_logsoftmax(logits, prev.ctypes.data, dim_batch, beam, n, int(first), suppress_word, costs.ctypes.data, keys.ctypes.data))
+        return costs, keys
+
     def trainer(self, options, device=0, rank=0, nranks=1):
         return Trainer(self, options, device, rank, nranks)
 
@@ -328,6 +349,28 @@ class Trainer:
         self.lib._ck(self.lib.c.mrn_trainer_validate(self.h, enc(src_path), enc(trg_path), enc(vocab_src), enc(vocab_trg), options.encode(), ctypes.byref(m), ctypes.byref(c),
                                                      ctypes.byref(n), ctypes.byref(w)))
         return {"metric": m.value, "cost_sum": c.value, "sentences": n.value, "target_words": w.value}
+
+    def translate(self, options="", n_best=1, max_len=None):
+        """Beam search over the source side of the current batch.  Returns, per sentence, a list of up to n_best
+        (words, score, raw_score) tuples, best first; words include the final 0 (</s>) of finished hypotheses."""
+        _, src_mask = self.get_batch(0)
+        B = src_mask.shape[1]
+        max_len = max_len or 3 * src_mask.shape[0] + 2
+        words = np.zeros((B, n_best, max_len), dtype=np.int64)
+        lengths = np.zeros((B, n_best), dtype=np.int32)
+        scores = np.zeros((B, n_best), dtype=np.float32)
+        raw = np.zeros((B, n_best), dtype=np.float32)
+        self.lib._ck(self.lib.c.mrn_trainer_translate(self.h, options.encode(), n_best, max_len, words.ctypes.data, lengths.ctypes.data, scores.ctypes.data, raw.ctypes.data))
+        out = []
+        for s in range(B):
+            out.append([(words[s, r, :lengths[s, r]].tolist(), float(scores[s, r]), float(raw[s, r])) for r in range(n_best) if lengths[s, r] >= 0])
+        return out
+
+    def translate_file(self, src_path, vocab_src, vocab_trg, out_path, options=""):
+        n = ctypes.c_size_t()
+        self.lib._ck(self.lib.c.mrn_trainer_translate_file(self.h, str(src_path).encode(), str(vocab_src).encode(), str(vocab_trg).encode(), options.encode(),
+                                                           str(out_path).encode(), ctypes.byref(n)))
+        return n.value
 
     def get_batch(self, side):
         """(indices [T, B] int64, mask [T, B] float32) of the current batch."""

@@ -14,6 +14,7 @@
 #include "training/checkpoint.h"
 #include "training/graph_group.h"
 #include "training/validator.h"
+#include "translator/translator.h"
 
 using namespace marian;
 
@@ -524,6 +525,67 @@ int mrn_trainer_validate(void* trainer, const char* srcPath, const char* trgPath
       *sentences = n;
     if(targetWords)
       *targetWords = w;
+  });
+}
+int mrn_nth_element_ranges(mrn_tensor scores, const int* rangeFirst, const int* cumN, int ranges, float* outCosts, unsigned* outKeys) {
+  return guarded([&] {
+    std::vector<int> first(rangeFirst, rangeFirst + ranges + 1), cum(cumN, cumN + ranges + 1);
+    std::vector<float> costs;
+    std::vector<unsigned> keys;
+    NthElementRanges(wrap(scores), first, cum, costs, keys);
+    std::copy(costs.begin(), costs.end(), outCosts);
+    std::copy(keys.begin(), keys.end(), outKeys);
+  });
+}
+int mrn_nth_element_logsoftmax(mrn_tensor logits, const float* prevCosts, int dimBatch, int beam, int n, int first, int suppressWord, float* outCosts, unsigned* outKeys) {
+  return guarded([&] {
+    std::vector<float> prev(prevCosts, prevCosts + (size_t)(first ? 1 : beam) * dimBatch);
+    std::vector<float> costs;
+    std::vector<unsigned> keys;
+    NthElementLogSoftmax(wrap(logits), prev, dimBatch, beam, n, first != 0, suppressWord, costs, keys);
+    std::copy(costs.begin(), costs.end(), outCosts);
+    std::copy(keys.begin(), keys.end(), outKeys);
+  });
+}
+// beam search over the source side of the current batch (translator/beam_search.h; reference translator/beam_search.h:91-225)
+int mrn_trainer_translate(void* trainer, const char* options, int nBest, int maxLen, int64_t* words, int* lengths, float* scores, float* rawScores) {
+  return guarded([&] {
+    auto t = (Trainer*)trainer;
+    auto graph = t->worker().graph();
+    ABORT_IF(!t->batch, "mrn_trainer_translate: no current batch");
+    ABORT_IF(graph->params()->size() == 0, "mrn_trainer_translate: the model has no parameters yet (run a step or load a checkpoint first)");
+    ABORT_IF(nBest < 1 || maxLen < 1, "mrn_trainer_translate: n_best and max_len must be positive");
+    Translator translator(t->options, New<Options>(options ? options : ""));
+    auto results = translator.translate(graph, t->batch, (size_t)nBest);
+    for(size_t s = 0; s < results.size(); ++s)
+      for(int r = 0; r < nBest; ++r) {
+        size_t slot = s * nBest + r;
+        bool have = r < (int)results[s].size();
+        int len = have ? (int)results[s][r].words.size() : -1;
+        lengths[slot] = len;
+        scores[slot] = have ? results[s][r].cost : 0.f;
+        if(rawScores)
+          rawScores[slot] = have ? results[s][r].rawCost : 0.f;
+        for(int k = 0; k < maxLen; ++k)
+          words[slot * maxLen + k] = (have && k < len) ? (int64_t)results[s][r].words[k] : -1;
+      }
+  });
+}
+// text file -> translations in corpus order (translator/translator.h; reference translator/translator.h:22-108)
+int mrn_trainer_translate_file(void* trainer, const char* srcPath, const char* vocabSrc, const char* vocabTrg, const char* options, const char* outPath, size_t* sentences) {
+  return guarded([&] {
+    auto t = (Trainer*)trainer;
+    auto graph = t->worker().graph();
+    ABORT_IF(graph->params()->size() == 0, "mrn_trainer_translate_file: the model has no parameters yet (run a step or load a checkpoint first)");
+    ABORT_IF(!vocabSrc || !vocabTrg, "mrn_trainer_translate_file: both vocabularies are required");
+    auto dims = t->options->get<std::vector<int>>("dim-vocabs");
+    auto vs = New<data::Vocab>(), vt = New<data::Vocab>();
+    vs->loadOrCreate(vocabSrc, srcPath, dims[0]);
+    vt->load(vocabTrg, dims[1]);
+    Translator translator(t->options, New<Options>(options ? options : ""));
+    size_t n = translator.translateFile(graph, srcPath, vs, vt, outPath);
+    if(sentences)
+      *sentences = n;
   });
 }
 // current batch as host arrays (time-major [T, B], the SubBatch layout); side 0 = source, 1 = target

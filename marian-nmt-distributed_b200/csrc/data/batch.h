@@ -87,6 +87,11 @@ public:
   }
   size_t sets() const { return batches_.size(); }
 
+  // line numbers of the sentences in their corpus (translations are written back in corpus order; reference
+  // src/data/batch.h getSentenceIds).  Empty for synthetic batches: sentence i is line i.
+  const std::vector<size_t>& getSentenceIds() const { return sentenceIds_; }
+  void setSentenceIds(const std::vector<size_t>& ids) { sentenceIds_ = ids; }
+
   std::vector<Ptr<CorpusBatch>> split(size_t n) {
     std::vector<std::vector<Ptr<SubBatch>>> subs(n);
     for(auto subBatch : batches_) {
@@ -123,6 +128,7 @@ public:
 
 private:
   std::vector<Ptr<SubBatch>> batches_;
+  std::vector<size_t> sentenceIds_;
 };
 
 // Synthetic bitext (SURVEY.md 8d / BASELINE.md section 3): a sentence is len-1

@@ -292,7 +292,12 @@ public:
         }
     for(size_t j = 0; j < maxDims.size(); ++j)
       subBatches[j]->setWords(words[j]);
-    return New<CorpusBatch>(subBatches);
+    auto batch = New<CorpusBatch>(subBatches);
+    std::vector<size_t> ids;
+    for(auto& ex : batchVector)
+      ids.push_back(ex.getId());
+    batch->setSentenceIds(ids);
+    return batch;
   }
 
 private:

@@ -178,6 +178,7 @@ public:
   }
 
   void setInference(bool inference) { inferenceOnly_ = inference; }
+  bool inference() const { return inferenceOnly_; }
 
   void setDevice(size_t device = 0) {
     device_ = (int)device;

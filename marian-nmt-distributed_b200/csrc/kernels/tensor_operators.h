@@ -232,6 +232,24 @@ void AdamUpdate(Tensor params, Tensor grads, Tensor mt, Tensor vt, const AdamArg
 void SgdUpdate(Tensor params, Tensor grads, float eta, float gradScale, float clipNorm, Tensor normSq = nullptr);
 void AdagradUpdate(Tensor params, Tensor grads, Tensor gt, float eta, float eps, float gradScale, float clipNorm, Tensor normSq = nullptr);
 
+// ---- beam search: n best continuations per sentence (kernels/nth_element.cu) ----------------------------------
+// Replaces NthElement::getNBestList (src/translator/nth_element.cu:270-402; gMaxElement + gMaxElementUpdate, one
+// iteration per returned element).  Both calls block until the result is on the host.
+//
+// NthElementRanges: scores is any tensor; range i covers the flat elements [rangeFirst[i], rangeFirst[i+1]) and
+// returns cumN[i+1]-cumN[i] (value, flat index) pairs, best first; ties go to the lower index.
+void NthElementRanges(Tensor scores, const std::vector<int>& rangeFirst, const std::vector<int>& cumN, std::vector<float>& outCosts,
+                      std::vector<unsigned>& outKeys);
+// NthElementLogSoftmax: the same result as
+//   totalCosts = transpose(prevCosts + logsoftmax(logits), {2, 1, 0, 3});  getNBestList(n per sentence, totalCosts)
+// read straight from the decoder's raw logits [beam, 1, batch, V]: row statistics and the row-local candidates come from
+// ONE pass over the logits (the n best of a row do not depend on the row's normaliser), the merge per sentence adds
+// prevCosts[row] + ((x - max) - log(sum)) in the LogSoftmax operator's order of operations.  Keys are those of the
+// transposed tensor: (sentence * beam + hypothesis) * V + word.  first: only hypothesis 0 of every sentence competes.
+// suppressWord >= 0: that word never wins (suppressUnk of src/translator/helpers.cu).
+void NthElementLogSoftmax(Tensor logits, const std::vector<float>& prevCosts, int dimBatch, int beam, int n, bool first, int suppressWord,
+                          std::vector<float>& outCosts, std::vector<unsigned>& outKeys);
+
 }  // namespace marian
 
 #include "kernels/element.h"

@@ -88,7 +88,9 @@ public:
     allocated_[gptr] = bytes;
     inUse_ += bytes;
     peak_ = std::max(peak_, inUse_);
-    return New<MemoryPiece>(gptr, bytes);
+    auto piece = New<MemoryPiece>(gptr, bytes);
+    piece->arenaEpoch = epoch_;
+    return piece;
   }
 
   // While side-stream work may still read freed tensors (see ExpressionGraph::backward) frees
@@ -107,6 +109,10 @@ public:
   bool free(Ptr<MemoryPiece> mp) {
     if(!mp || !mp->data())
       return false;
+    if(mp->arenaEpoch != epoch_) {  // allocated before the last clear(): its bytes already went back to the arena
+      mp->set(nullptr, 0);
+      return false;
+    }
     if(defer_) {
       deferred_.push_back(mp);
       return true;
@@ -123,6 +129,7 @@ public:
   }
 
   void clear() {
+    ++epoch_;
     deferred_.clear();
     bySize_.clear();
     byAddr_.clear();
@@ -218,6 +225,7 @@ private:
   std::map<uint8_t*, size_t> byAddr_;
   std::unordered_map<uint8_t*, size_t> allocated_;
   size_t inUse_{0};
+  uint32_t epoch_{0};
   size_t peak_{0};
   size_t generation_{0};
   bool defer_{false};

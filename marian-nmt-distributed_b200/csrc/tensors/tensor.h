@@ -44,6 +44,9 @@ public:
   // to fp32 tensors nobody reads).  fp32Skipped records that one did - fp32 readers must not appear after that.
   mutable bool shadowOnly{false};
   mutable bool fp32Skipped{false};
+  // arena generation this piece was cut from (Allocator::clear() starts a new one): a piece that outlives a clear() -
+  // an Expr kept across graph->clear() - must not free the new owner of its old address
+  uint32_t arenaEpoch{0};
 
 private:
   uint8_t* data_;

@@ -21,6 +21,8 @@
 // from these by ~1e-6 relative - inside every tolerance used.
 #include <immintrin.h>
 
+#include <algorithm>
+#include <limits>
 #include <cmath>
 #include <cstring>
 #include <random>
@@ -1218,6 +1220,73 @@ void AdagradUpdate(Tensor params, Tensor grads, Tensor gt, float eta, float eps,
     float gi = grads->data()[i] * scale;
     gt->data()[i] += gi * gi;
     params->data()[i] -= (eta / (sqrtf(gt->data()[i]) + eps)) * gi;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Beam search: n best per range      reference: src/translator/nth_element.cu:270-402 (getNBestList: range i of the
+// flat score tensor returns beamSizes[i] (value, flat index) pairs, found one maximum at a time -> best first).
+// Ties: the lower index wins (the reference leaves ties to its block schedule; real scores do not tie).
+// ---------------------------------------------------------------------------
+void NthElementRanges(Tensor scores, const std::vector<int>& rangeFirst, const std::vector<int>& cumN, std::vector<float>& outCosts,
+                      std::vector<unsigned>& outKeys) {
+  const float* x = scores->data();
+  for(size_t r = 0; r + 1 < rangeFirst.size(); ++r) {
+    int want = cumN[r + 1] - cumN[r];
+    std::vector<unsigned> idx;
+    for(int i = rangeFirst[r]; i < rangeFirst[r + 1]; ++i)
+      idx.push_back((unsigned)i);
+    auto cmp = [x](unsigned a, unsigned b) { return x[a] > x[b] || (x[a] == x[b] && a < b); };
+    size_t k = std::min((size_t)want, idx.size());
+    std::partial_sort(idx.begin(), idx.begin() + k, idx.end(), cmp);
+    for(int j = 0; j < want; ++j) {
+      if((size_t)j < k) {
+        outCosts.push_back(x[idx[j]]);
+        outKeys.push_back(idx[j]);
+      } else {
+        outCosts.push_back(-INFINITY);
+        outKeys.push_back(0xFFFFFFFFu);
+      }
+    }
+  }
+}
+
+// The node sequence of src/translator/beam_search.h:163-196 on plain arrays: logsoftmax per row (the LogSoftmax
+// restatement above), + previous cost of the row, rows regrouped per sentence, suppressed word set to lowest(), n best.
+void NthElementLogSoftmax(Tensor logits, const std::vector<float>& prevCosts, int dimBatch, int beam, int n, bool first, int suppressWord,
+                          std::vector<float>& outCosts, std::vector<unsigned>& outKeys) {
+  const int V = logits->shape().back();
+  const int rowsPerSentence = first ? 1 : beam;
+  std::vector<float> total((size_t)dimBatch * rowsPerSentence * V);
+  for(int b = 0; b < rowsPerSentence; ++b)
+    for(int s = 0; s < dimBatch; ++s) {
+      const float* sp = logits->data() + ((size_t)b * dimBatch + s) * V;
+      float* so = total.data() + ((size_t)s * rowsPerSentence + b) * V;
+      float max = sp[0];
+      for(int id = 1; id < V; ++id)
+        if(sp[id] > max)
+          max = sp[id];
+      double sum = 0;
+      for(int id = 0; id < V; ++id)
+        sum += expf(sp[id] - max);
+      float lsum = logf((float)sum);
+      float prev = prevCosts[(size_t)b * dimBatch + s];
+      for(int id = 0; id < V; ++id)
+        so[id] = prev + ((sp[id] - max) - lsum);
+      if(suppressWord >= 0 && suppressWord < V)
+        so[suppressWord] = std::numeric_limits<float>::lowest();
+    }
+  for(int s = 0; s < dimBatch; ++s) {
+    const float* x = total.data();
+    std::vector<unsigned> idx;
+    for(size_t i = (size_t)s * rowsPerSentence * V; i < (size_t)(s + 1) * rowsPerSentence * V; ++i)
+      idx.push_back((unsigned)i);
+    auto cmp = [x](unsigned a, unsigned b) { return x[a] > x[b] || (x[a] == x[b] && a < b); };
+    std::partial_sort(idx.begin(), idx.begin() + n, idx.end(), cmp);
+    for(int j = 0; j < n; ++j) {
+      outCosts.push_back(x[idx[j]]);
+      outKeys.push_back(idx[j]);
+    }
   }
 }
 

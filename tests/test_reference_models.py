@@ -63,3 +63,34 @@ def test_reference_model_code_matches_this_repos(oracle, refmodels, name):
     # +-lr per step (the two model codes order a few additions differently), all others agree
     diff = np.abs(ref["params"] - ours["params"])
     assert diff.max() <= 2 * 3 * 1e-3 + 1e-5 and np.mean(diff > 2e-5) < 0.01 and np.median(diff) < 1e-7, (diff.max(), np.mean(diff > 2e-5))
+
+
+@pytest.mark.parametrize("name", ["transformer", "transformer-tied", "s2s-gru", "s2s-deep"])
+def test_reference_model_code_decodes_like_this_repos(oracle, refmodels, name):
+    """Beam search (csrc/translator/beam_search.h) over the REFERENCE's decoder code - its TransformerState::select,
+    its single-step DecoderTransformer::step / DecoderS2S::step with cached states - against this repo's model classes:
+    same n-best lists.  Parameters are trained with this repo's model code and handed over through a checkpoint."""
+    import tempfile
+
+    opts = CONFIGS[name] + ";workspace=128;learn-rate=0.003;gemm-mode=0;graph-replay=false"
+    t = oracle.trainer(opts)
+    for _ in range(200):
+        t.next_synthetic_batch(6, 5, 6, padded=True)
+        t.compute_gradients()
+        t.update()
+    with tempfile.TemporaryDirectory() as d:
+        path = os.path.join(d, "model.npz")
+        t.save(path)
+        r = refmodels.trainer(opts)
+        r.load(path)
+    t.next_synthetic_batch(5, 6, 6, padded=True)
+    src, src_mask = t.get_batch(0)
+    trg, trg_mask = t.get_batch(1)
+    r.set_batch(src, src_mask, trg, trg_mask)
+    for o in ("beam-size=4;normalize=0.6", "beam-size=1;allow-unk=true", "beam-size=3;beam-fused-nth=false"):
+        ours, ref = t.translate(o, n_best=3), r.translate(o, n_best=3)
+        assert [[h[0] for h in s] for s in ours] == [[h[0] for h in s] for s in ref], o
+        assert np.allclose([h[1] for s in ours for h in s], [h[1] for s in ref for h in s], rtol=1e-5), o
+        assert o != "beam-size=4;normalize=0.6" or any(len(h[0]) > 1 for s in ours for h in s)  # more than one decoding step
+    t.close()
+    r.close()
