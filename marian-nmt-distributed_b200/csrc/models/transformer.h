@@ -169,8 +169,14 @@ struct TransformerSublayers {
   static Expr attend(const Env& env, Expr q, Expr k, Expr v, Expr mask, int heads) {
     const int beam = q->shape()[-4];
     const int width = q->shape()[-1];
-    const bool fusable = env.fuseAttention() && beam == 1 && k->shape()[-4] == 1 && mask && env.dropout("transformer-dropout-attention") == 0.f
-                         && AttentionFusable(q->shape()[-2], k->shape()[-2], width, heads);
+    bool fusable = env.fuseAttention() && beam == 1 && k->shape()[-4] == 1 && mask && env.dropout("transformer-dropout-attention") == 0.f
+                   && AttentionFusable(q->shape()[-2], k->shape()[-2], width, heads);
+    if(fusable) {  // the fused operator wants one mask row per key (B*Tk) or per query and key (B*Tq*Tk); decoding steps
+                   // carry a broadcast [1,1,1,1] causal mask and take the node sequence
+      const size_t sentences = q->shape().elements() / ((size_t)q->shape()[-2] * width);
+      const size_t keys = k->shape()[-2], queries = q->shape()[-2], have = mask->shape().elements();
+      fusable = have == sentences * keys || have == sentences * queries * keys;
+    }
     if(fusable)
       return multi_head_attention(q, k, v, mask, heads, 1.0f / std::sqrt((float)(width / heads)));
     return attendUnfused(env, q, k, v, mask, heads, beam);

@@ -142,6 +142,11 @@ public:
     const bool wasInference = graph->inference();
     graph->setInference(true);  // nodes of finished steps are released as soon as nothing refers to them
     graph->setBackwardSplit(nullptr, nullptr);
+    {
+      auto gemm = graph->getBackend()->getGemmHandle();
+      gemmAllowShadowOnly(gemm, false);  // every fp32 value stays readable (the selection reads the logits)
+      gemmPrepareStep(gemm);             // bf16 copy of the parameters up to date (e.g. right after a checkpoint load)
+    }
     for(auto& sc : scorers_)
       sc.model->clear(graph);
     std::vector<Ptr<DecoderState>> states;
@@ -257,11 +262,14 @@ public:
   }
 
 private:
+  // The reference runs forward() for the first step and forwardNext() afterwards; here every step is a full forward():
+  // it also rewinds the per-pass operand scratch of the products (bf16 shadows / packed operands), which a decoding run
+  // of a hundred steps would otherwise keep growing - nothing of an earlier step's scratch is read again, the decoder
+  // states are re-gathered per step.
   static void runForward(Ptr<ExpressionGraph> graph, bool first) {
-    if(first)
-      graph->forward();
-    else
-      graph->forwardNext();
+    graph->forward();
+    if(first)  // parameters loaded from a checkpoint and never stepped: the first forward() announced their range
+      gemmPrepareStep(graph->getBackend()->getGemmHandle());
   }
 
   Config config_;
