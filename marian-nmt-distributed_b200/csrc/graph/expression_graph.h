@@ -77,6 +77,7 @@ struct ParamNode : public Node {
     }
   }
   const std::string type() { return "param"; }
+  virtual bool paramOnly() { return true; }
   virtual size_t hash() {
     size_t seed = std::hash<std::string>()(name());
     hash_combine(seed, type());
@@ -236,11 +237,28 @@ public:
     hashMap_.clear();
     static const bool sideEnabled = std::getenv("MRN_NO_SIDE_STREAM") == nullptr;
     bool pending = false;  // side-stream results not yet joined into the main stream
+    // (an inference pass frees values as it goes - memory would be reused across lanes without any ordering)
+    const bool lanes = lanesInUse_ && !inferenceOnly_ && !nodeTiming();
+    if(lanes)
+      device::openLanes();
     while(!nodesForward_.empty()) {
       auto v = nodesForward_.front();
+      if(lanes) {
+        // this node's chain; values produced by other chains are waited for one by one
+        device::selectLane(v->lane());
+        for(auto& c : v->children())
+          if(c->lane() != v->lane()) {
+            if(!c->valMark()) {  // (no mark taken behind the producer: everything its lane has issued so far)
+              device::selectLane(c->lane());
+              c->setValMark(device::laneMark());
+              device::selectLane(v->lane());
+            }
+            device::laneWait(c->valMark());
+          }
+      }
       v->allocate();
       v->init();
-      if(sideEnabled && v->concurrent() && !v->children().empty()) {
+      if(sideEnabled && !lanes && v->concurrent() && !v->children().empty()) {
         // inputs were produced on the main stream before this point (or on the side stream
         // itself, which is in order): fork, run, hand back
         device::forkSide();
@@ -248,10 +266,6 @@ public:
         device::returnFromSide();
         v->setSideProduced(true);
         pending = true;
-      } else if(nodeTiming()) {
-        auto t0 = std::chrono::steady_clock::now();
-        v->forward();
-        timing_["fwd " + v->type()] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
       } else {
         if(pending) {
           bool fromSide = false;
@@ -264,24 +278,36 @@ public:
             } else {
               device::joinSide();  // joins ALL side work
               pending = false;
+              for(auto& c : v->children())
+                c->setSideProduced(false);
             }
           }
         }
-        if(!pending) {  // (a node computed together with its successors must not race with side-stream producers)
+        if(!pending && !lanes) {  // (a node computed together with its successors must not race with side-stream producers)
           std::vector<Expr> upcoming;
           auto it = nodesForward_.begin();
           for(++it; it != nodesForward_.end() && upcoming.size() < 2; ++it)
             upcoming.push_back(*it);
           v->fuseForward(upcoming);
         }
-        v->forward();
+        if(nodeTiming()) {
+          auto t0 = std::chrono::steady_clock::now();
+          v->forward();
+          timing_["fwd " + v->type()] += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        } else {
+          v->forward();
+        }
       }
+      if(lanes && v->crossLane())
+        v->setValMark(device::laneMark());
       if(inferenceOnly_)
         v->children().clear();
       nodesForward_.pop_front();
     }
     if(pending)
       device::joinSide();
+    if(lanes)
+      device::closeLanes();
   }
 
   void backward() {
@@ -307,13 +333,22 @@ public:
     if(backwardSplitChooser_)
       splitAfter = backwardSplitChooser_(nodesBackward_);
 
+    const bool lanes = lanesInUse_ && !nodeTiming();
+    if(lanes)
+      device::openLanes();
     while(!nodesBackward_.empty()) {
       if(swept++ == splitAfter && backwardSplitHook_) {
+        if(lanes)
+          device::closeLanes();
         device::joinSide();  // weight gradients issued so far are part of "before the split"
         backwardSplitHook_();
+        if(lanes)
+          device::openLanes();
       }
       auto v = nodesBackward_.back();
       nodesBackward_.pop_back();
+      if(lanes)
+        device::selectLane(v->lane());
 
       {
         auto tz = std::chrono::steady_clock::now();
@@ -325,7 +360,14 @@ public:
       }
 
       if(v->trainable()) {
-        {
+        if(lanes) {
+          // this node's chain waits for the other chains' writes to the adjoints it reads (its own) and updates
+          // (its children's: accumulation is read-modify-write)
+          v->waitAdjMarks();
+          for(auto&& child : v->children())
+            if(child->trainable())
+              child->waitAdjMarks();
+        } else {
           std::vector<Expr> upcoming;
           for(auto it = nodesBackward_.rbegin(); it != nodesBackward_.rend() && upcoming.size() < 2; ++it)
             upcoming.push_back(*it);
@@ -338,6 +380,15 @@ public:
         } else {
           v->backward();
         }
+        if(lanes) {
+          void* mark = nullptr;
+          for(auto&& child : v->children())
+            if(child->trainable() && child->adjSharedAcrossLanes(v->lane())) {
+              if(!mark)
+                mark = device::laneMark();
+              child->setAdjMark(v->lane(), mark);
+            }
+        }
       }
 
       {
@@ -347,6 +398,8 @@ public:
           timing_["(release children)"] += std::chrono::duration<double>(std::chrono::steady_clock::now() - tz).count();
       }
     }
+    if(lanes)
+      device::closeLanes();
     if(nodeTiming()) {
       // host wall time per node type: meaningful on the synchronous CPU oracle (MRN_NODE_TIMING=1)
       std::vector<std::pair<double, std::string>> rows;
@@ -414,6 +467,16 @@ public:
 
   Ptr<Parameters>& params() { return params_; }
 
+  // Lanes: nodes created while lane k is selected form a chain of their own; forward and backward run chain k > 0 on
+  // its own stream, ordered against the other chains only where values / adjoints actually cross (tensors/device.h).
+  // Model code brackets an independent sub-network: graph->setLane(1); ... ; graph->setLane(0);
+  void setLane(int lane) { currentLane_ = (lanesAllowed() && !inferenceOnly_ && lane > 0 && lane < device::kMaxLanes) ? lane : 0; }
+  int lane() const { return currentLane_; }
+  static bool lanesAllowed() {
+    static const bool on = std::getenv("MRN_NO_LANES") == nullptr;
+    return on;
+  }
+
   // Backward split: `chooser` sees the tape (forward order; the sweep runs it back to front) and returns after how
   // many swept nodes `hook` is to be called (or size_t(-1): never).  The side stream is joined before the hook.
   typedef std::function<size_t(const std::list<Expr>&)> SplitChooser;
@@ -439,6 +502,11 @@ public:
       for(auto& child : node->children())
         child->addConsumer(node->readsChildViaProduct(i++));
     }
+    node->setLane(currentLane_);
+    if(currentLane_ != 0)
+      lanesInUse_ = true;
+    for(auto& child : node->children())
+      child->noteConsumerLane(currentLane_);
 
     nodesForward_.push_back(node);
     if(!inferenceOnly_ && node->trainable()) {
@@ -459,6 +527,8 @@ public:
 
   void clear() {
     count_ = 0;
+    currentLane_ = 0;
+    lanesInUse_ = false;
     nodesForward_.clear();
     nodesBackward_.clear();
     topNodes_.clear();
@@ -497,6 +567,8 @@ private:
   }
   std::map<std::string, double> timing_;
   size_t count_{0};
+  int currentLane_{0};
+  bool lanesInUse_{false};  // some node of the current tape lives on a lane > 0
   std::list<Expr> nodesForward_;
   std::list<Expr> nodesBackward_;
   SplitChooser backwardSplitChooser_;

@@ -17,6 +17,7 @@
 #include "common/definitions.h"
 #include "common/keywords.h"
 #include "common/shape.h"
+#include "tensors/device.h"
 #include "tensors/tensor.h"
 
 namespace marian {
@@ -80,6 +81,18 @@ struct Chainable {
   virtual bool sideProduced() const { return false; }
   virtual void setSideProduced(bool) {}
 
+  // lanes (tensors/device.h, ExpressionGraph::setLane): which independent chain of the pass this node belongs to, and
+  // the bookkeeping that orders its value / adjoint against nodes of other lanes
+  virtual int lane() const { return 0; }
+  virtual void setLane(int) {}
+  virtual void noteConsumerLane(int) {}
+  virtual bool crossLane() const { return false; }
+  virtual bool adjSharedAcrossLanes(int /*writerLane*/) const { return false; }
+  virtual void* valMark() const { return nullptr; }
+  virtual void setValMark(void*) {}
+  virtual void setAdjMark(int /*lane*/, void*) {}
+  virtual void waitAdjMarks() {}
+
   // bf16 shadows of GEMM operands (kernels/shadow.h, GemmMode::BF16S).  A product node asks its
   // operand nodes for a bf16 copy of their VALUE and is itself marked as wanting one of its ADJOINT
   // (the A / B operand of its two backward products).  The graph counts the consumers of every node
@@ -89,6 +102,10 @@ struct Chainable {
   // `viaProduct`: the consumer reads this node's value only as a tensor-core product operand (through the bf16 copy)
   virtual void addConsumer(bool /*viaProduct*/ = false) {}
   virtual bool isView() const { return false; }
+  // true for parameters and for nodes built from parameters only (the [U | Ux] concatenations of the recurrent
+  // cells): nothing in the backward sweep reads their adjoints before the optimizer, so whatever writes them may
+  // leave the critical path (Node::offCriticalPath)
+  virtual bool paramOnly() { return false; }
   // child i of this node is read only as a product operand (Affine / Dot nodes: their two matrix arguments)
   virtual bool readsChildViaProduct(size_t /*i*/) const { return false; }
 };
@@ -112,6 +129,10 @@ protected:
   bool wantAdjShadow_{false};   // this node is a product: its adjoint is an operand of the backward products
   int consumers_{0};            // nodes on the tape that have this node as a child
   int productConsumers_{0};     // ... of which read the value only as a product operand
+  int lane_{0};                 // see Chainable::lane
+  unsigned consumerLanes_{0};   // bit k: a consumer lives on lane k
+  void* valMark_{nullptr};      // device::laneMark behind this node's forward (only taken for cross-lane consumers)
+  void* adjMarks_[device::kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};  // per lane: mark behind its latest write to adj_
 
 public:
   Node(Ptr<ExpressionGraph> graph, const Shape& shape) : graph_(graph), shape_(shape) {}
@@ -200,14 +221,33 @@ public:
       ++productConsumers_;
   }
 
+  virtual int lane() const { return lane_; }
+  virtual void setLane(int l) { lane_ = l; }
+  virtual void noteConsumerLane(int l) { consumerLanes_ |= 1u << l; }
+  // some consumer reads this node's value from another lane
+  virtual bool crossLane() const { return (consumerLanes_ & ~(1u << lane_)) != 0; }
+  // the adjoint is written by consumers (on their lanes) and read by this node's backward (on its own): does any of
+  // those parties live on a lane other than `writerLane`?
+  virtual bool adjSharedAcrossLanes(int writerLane) const { return ((consumerLanes_ | (1u << lane_)) & ~(1u << writerLane)) != 0; }
+  virtual void* valMark() const { return valMark_; }
+  virtual void setValMark(void* m) { valMark_ = m; }
+  virtual void setAdjMark(int l, void* m) { adjMarks_[l] = m; }
+  // the current lane waits for every other lane's latest write to this node's adjoint
+  virtual void waitAdjMarks() {
+    for(int l = 0; l < device::kMaxLanes; ++l)
+      if(adjMarks_[l])
+        device::laneWait(adjMarks_[l]);
+  }
+
   Ptr<Backend> getBackend();
 
-  // Runs f on the side stream when it only produces the gradient of PARAMETER `target`:
-  // nothing downstream in the backward sweep reads it (device.h: forkSide/joinSide).
+  // Runs f on the side stream when it only produces the gradient of PARAMETER `target` (or of a node made of
+  // parameters only, whose own backward then runs on the side stream as well): nothing downstream in the
+  // backward sweep reads it (device.h: forkSide/joinSide).
   template <class F>
   void offCriticalPath(Expr target, F f) {
     static const bool enabled = std::getenv("MRN_NO_SIDE_STREAM") == nullptr;
-    bool side = enabled && target->type() == "param";
+    bool side = enabled && target->paramOnly();
     if(side)
       device::forkSide();
     f();

@@ -398,14 +398,28 @@ struct ConcatenateNodeOp : public NaryNodeOp {
     Concatenate(val_, concatenees, ax_);
   }
   void backward() {
-    std::vector<Tensor> deconcatenees;
-    for(size_t i = 0; i < children_.size(); ++i) {
-      auto childPtr = child(i);
-      childPtr->set_zero_adjoint();
-      deconcatenees.push_back(childPtr->grad());
-    }
-    Deconcatenate(deconcatenees, adj_, ax_);
+    // [U | Ux]-style concatenations of parameters: the weight-gradient products that fill adj_ run on the side
+    // stream (Node::offCriticalPath), so this node's backward follows them there
+    offCriticalPath(shared_from_this(), [&] {
+      std::vector<Tensor> deconcatenees;
+      for(size_t i = 0; i < children_.size(); ++i) {
+        auto childPtr = child(i);
+        childPtr->set_zero_adjoint();
+        deconcatenees.push_back(childPtr->grad());
+      }
+      Deconcatenate(deconcatenees, adj_, ax_);
+    });
   }
+  virtual bool paramOnly() {
+    if(paramOnly_ < 0) {
+      paramOnly_ = 1;
+      for(auto& c : children_)
+        if(!c->paramOnly())
+          paramOnly_ = 0;
+    }
+    return paramOnly_ == 1;
+  }
+  int paramOnly_{-1};
 
   virtual size_t hash() {
     if(!hash_) {

@@ -368,20 +368,27 @@ struct RowsNodeOp : public UnaryNodeOp {
     return shape;
   }
 
+  // A lookup whose indices are refilled from the batch on every replay of a captured step (fill_) is its own node:
+  // two such lookups with equal capture-time indices (copy task, tied source / target embeddings) read DIFFERENT
+  // batch streams afterwards, merging them would feed one stream to both.
   virtual size_t hash() {
     if(!hash_) {
       size_t seed = NaryNodeOp::hash();
       for(auto i : indices_)
         hash_combine(seed, i);
+      if(fill_)
+        hash_combine(seed, (size_t)this);
       hash_ = seed;
     }
     return hash_;
   }
   virtual bool equal(Expr node) {
+    if(fill_)
+      return this == node.get();
     if(!NaryNodeOp::equal(node))
       return false;
     auto cnode = std::dynamic_pointer_cast<RowsNodeOp>(node);
-    return cnode && indices_ == cnode->indices_;
+    return cnode && !cnode->fill_ && indices_ == cnode->indices_;
   }
   const std::string type() { return "rows"; }
 
@@ -506,6 +513,19 @@ public:
   void requestValShadow() { reshapee_->requestValShadow(); }
   void addConsumer(bool viaProduct = false) { reshapee_->addConsumer(viaProduct); }
   bool isView() const { return true; }
+  // lanes: the adjoint IS the reshapee's - writers and waiters see through the view
+  void noteConsumerLane(int l) {
+    Node::noteConsumerLane(l);
+    reshapee_->noteConsumerLane(l);
+  }
+  void setAdjMark(int l, void* m) {
+    Node::setAdjMark(l, m);
+    reshapee_->setAdjMark(l, m);
+  }
+  void waitAdjMarks() {
+    Node::waitAdjMarks();
+    reshapee_->waitAdjMarks();
+  }
 
   Tensor& val() {
     auto childVal = reshapee_->val();
@@ -563,6 +583,19 @@ public:
   void backward() {}
   void init_dependent() { stepNode_->init_dependent(); }
   void set_zero_adjoint() { stepNode_->set_zero_adjoint(); }
+  // lanes: the adjoint is a slice of the stepped node's - writers and waiters see through the view
+  void noteConsumerLane(int l) {
+    Node::noteConsumerLane(l);
+    stepNode_->noteConsumerLane(l);
+  }
+  void setAdjMark(int l, void* m) {
+    Node::setAdjMark(l, m);
+    stepNode_->setAdjMark(l, m);
+  }
+  void waitAdjMarks() {
+    Node::waitAdjMarks();
+    stepNode_->waitAdjMarks();
+  }
 
   Tensor& val() {
     auto childVal = stepNode_->val();

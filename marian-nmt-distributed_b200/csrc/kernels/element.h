@@ -167,19 +167,28 @@ __global__ void __launch_bounds__(256) gAddReduceRows(Functor f, float* __restri
 // 128-bit loads, the 8 warps stride the rows of a slice, partial sums meet in shared memory
 // and leave through ONE atomicAdd per column and slice.
 template <int K, class Functor>
-__global__ void __launch_bounds__(256) gAddColumns(Functor f, float* __restrict__ out, Operands<K> ops, RowGeom g, float scale, int rowsPerSlice, int assign) {
+__global__ void __launch_bounds__(256) gAddColumns(Functor f, float* __restrict__ out, Operands<K> ops, RowGeom g, float scale, int rowsPerSlice, int assign, int keep2) {
   pdlEnter();
   __shared__ float red[8][32][5];
   const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
   const int r0 = blockIdx.y * rowsPerSlice;
   const int r1 = min(g.rows, r0 + rowsPerSlice);
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  if(keep2)  // out[.., o2, C]: the third axis is kept (blockIdx.z), rows run over the two leading axes only
+    out += (size_t)blockIdx.z * g.cols;
   if(c < g.cols) {
     for(int row = r0 + threadIdx.y; row < r1; row += 8) {
-      int o2 = row % g.d2;
-      int t = row / g.d2;
-      int o1 = t % g.d1;
-      int o0 = t / g.d1;
+      int o2, o1, o0;
+      if(keep2) {
+        o2 = blockIdx.z;
+        o1 = row % g.d1;
+        o0 = row / g.d1;
+      } else {
+        o2 = row % g.d2;
+        int t = row / g.d2;
+        o1 = t % g.d1;
+        o0 = t / g.d1;
+      }
       float v[K][4];
 #pragma unroll
       for(int k = 0; k < K; ++k) {
@@ -461,7 +470,31 @@ void Add(Functor functor, float scale, Tensor out, Tensors... tensors) {
     int rowsPerSlice = (g.rows + slices - 1) / slices;
     slices = (g.rows + rowsPerSlice - 1) / rowsPerSlice;
     int assign = (slices == 1 && out->takeLazyZero()) ? 1 : 0;
-    launchPdl(ew::gAddColumns<K, Functor>, dim3(strips, slices), dim3(32, 8), 0, stream, functor, out->data(), ops, g, scale, rowsPerSlice, assign);
+    launchPdl(ew::gAddColumns<K, Functor>, dim3(strips, slices), dim3(32, 8), 0, stream, functor, out->data(), ops, g, scale, rowsPerSlice, assign, 0);
+  } else if(outS.d[0] == 1 && outS.d[1] == 1 && outS.d[2] == full.d[2] && outS.d[3] == full.d[3] && full.d[2] <= 65535 && (full.d[3] & 3) == 0 && ew::aligned16(out->memory()->data())
+            && ew::aligned16(out->data()) && [&] {
+                 for(int k = 0; k < K; ++k) {
+                   Shape4 sk(ts[k]->shape());
+                   if(sk.bst[3] == 1 && (!ew::aligned16(ts[k]->data()) || (sk.d[3] & 3)))
+                     return false;
+                 }
+                 return true;
+               }()) {
+    // (3b) sums over the two leading axes, the third axis kept: out[1,1,B,C] += sum_t f(ins[t,b,c]) - the context
+    // vector of the recurrent decoder's attention (scalar_product over source positions), means over time.  The
+    // same strip kernel as (3a), one grid layer per kept index.
+    ew::Operands<K> ops;
+    ew::RowGeom g;
+    bool vec;
+    ew::setupOperands<K>(full, ts, ops, g, vec, false);
+    g.rows = full.d[0] * full.d[1];
+    int strips = (g.cols / 4 + 31) / 32;
+    long layers = (long)strips * full.d[2];
+    int slices = (int)std::max<long>(1, std::min<long>((kNumSMs * 4 + layers - 1) / layers, (g.rows + 15) / 16));
+    int rowsPerSlice = (g.rows + slices - 1) / slices;
+    slices = (g.rows + rowsPerSlice - 1) / rowsPerSlice;
+    int assign = (slices == 1 && out->takeLazyZero()) ? 1 : 0;
+    launchPdl(ew::gAddColumns<K, Functor>, dim3(strips, slices, full.d[2]), dim3(32, 8), 0, stream, functor, out->data(), ops, g, scale, rowsPerSlice, assign, 1);
   } else {
     // (3) generic reduction over the dims where out has extent 1
     ew::FullOperands<K> ops;
@@ -500,14 +533,14 @@ void Add(Functor functor, Tensor out, Tensors... tensors) {
 
 template <class Functor, class... Tensors>
 void Reduce(Functor functor, float scale, Tensor out, Tensors... tensors) {
-  out->set(0);
+  out->setLazyZero();  // the accumulating kernel assigns where it can (no fill pass); memset-then-add on the CPU oracle
   Add(functor, scale, out, tensors...);
+  out->data();         // (a path that left the mark untouched: materialise)
 }
 
 template <class Functor, class... Tensors>
 void Reduce(Functor functor, Tensor out, Tensors... tensors) {
-  out->set(0);
-  Add(functor, 1.f, out, tensors...);
+  Reduce(functor, 1.f, out, tensors...);
 }
 
 }  // namespace marian

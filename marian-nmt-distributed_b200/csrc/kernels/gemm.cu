@@ -90,7 +90,7 @@ struct GemmContext {
   __nv_bfloat16* paramShadow{nullptr};
   size_t paramShadowElems{0};
   bool paramFresh{false};                         // the whole copy matches the fp32 arena
-  std::unordered_set<const void*> paramConverted;  // tensors converted one by one since the last invalidate
+  std::unordered_map<const void*, void*> paramConverted;  // tensors converted one by one since the last invalidate (-> lane mark behind the conversion)
 
   typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
   EncodeTiledFn encodeTiled{nullptr};
@@ -237,6 +237,7 @@ __nv_bfloat16* produce(const Tensor& t) {
     m.shadowGen = g_shadows.generation;
   }
   m.shadowValid = true;
+  m.shadowMark = nullptr;
   return (__nv_bfloat16*)m.shadow;
 }
 namespace {
@@ -315,16 +316,23 @@ const __nv_bfloat16* ensureShadow(GemmHandle h, const Tensor& t) {
   const size_t n = t->size();
   if(h->paramShadow && p >= h->stableLo && p + n * sizeof(float) <= h->stableHi) {
     __nv_bfloat16* dst = h->paramShadow + (p - h->stableLo) / sizeof(float);
-    if(!h->paramFresh && !h->paramConverted.count(p)) {
-      convertToBf16(dst, src, n);
-      h->paramConverted.insert(p);
+    if(!h->paramFresh) {
+      auto it = h->paramConverted.find(p);
+      if(it == h->paramConverted.end()) {
+        convertToBf16(dst, src, n);
+        h->paramConverted[p] = device::laneMark();  // (the conversion runs on the lane's stream even when called from the side stream)
+      } else {
+        device::laneWait(it->second);  // converted by a consumer on another lane (tensors/device.h)
+      }
     }
     return dst;
   }
   MemoryPiece& m = *t->memory();
   const size_t off = (size_t)(p - m.data()) / sizeof(float);
-  if(m.shadowValid && m.shadow && m.shadowGen == g_shadows.generation)
+  if(m.shadowValid && m.shadow && m.shadowGen == g_shadows.generation) {
+    device::laneWait(m.shadowMark);
     return (const __nv_bfloat16*)m.shadow + off;
+  }
   const bool whole = off == 0 && n * sizeof(float) == m.size();
   __nv_bfloat16* dst = (__nv_bfloat16*)g_shadows.take(n * sizeof(__nv_bfloat16));
   convertToBf16(dst, src, n);
@@ -332,6 +340,7 @@ const __nv_bfloat16* ensureShadow(GemmHandle h, const Tensor& t) {
     m.shadow = dst;
     m.shadowGen = g_shadows.generation;
     m.shadowValid = true;
+    m.shadowMark = device::laneMark();
   }
   return dst;
 }

@@ -841,6 +841,31 @@ __global__ void gAtt(float* __restrict__ out, const float* __restrict__ va, cons
   }
 }
 
+// 16-byte aligned rows, k % 4 == 0: one warp per (source position, sentence) row, 128-bit loads, four
+// independent partial sums per lane (the block-per-row form above spends two block barriers per row
+// of 2048 elements: 22 us per decoder step at 50 x 64 rows).
+__global__ void __launch_bounds__(256) gAttVec(float* __restrict__ out, const float* __restrict__ va, const float* __restrict__ ctx, const float* __restrict__ state, int m, int k, int b, int t) {
+  const int lane = threadIdx.x & 31;
+  const int k4 = k >> 2;
+  const float4* va4 = reinterpret_cast<const float4*>(va);
+  for(int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); j < m; j += gridDim.x * (blockDim.x >> 5)) {
+    const float4* ctxRow = reinterpret_cast<const float4*>(ctx + (size_t)(j % (b * t)) * k);
+    const float4* stateRow = reinterpret_cast<const float4*>(state + (size_t)((j / (b * t)) * b + j % b) * k);
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll 4
+    for(int id = lane; id < k4; id += 32) {
+      const float4 c = ctxRow[id], st = stateRow[id], v = va4[id];
+      s0 += tanhf(c.x + st.x) * v.x;
+      s1 += tanhf(c.y + st.y) * v.y;
+      s2 += tanhf(c.z + st.z) * v.z;
+      s3 += tanhf(c.w + st.w) * v.w;
+    }
+    float s = warpSum((s0 + s1) + (s2 + s3));
+    if(lane == 0)
+      out[j] = s;
+  }
+}
+
 // grid = (batch n, column chunks); a thread owns ONE column c of ONE batch
 // element and walks the rows j = bIdx, bIdx+n, ... (time steps): state row and
 // va are loaded once, gState / gVa sums stay in registers.
@@ -882,6 +907,12 @@ void Att(Tensor out, Tensor va, Tensor context, Tensor state) {
   int k = context->shape()[-1];
   int b = context->shape()[-2];
   int t = context->shape()[-3];
+  if(k % 4 == 0 && k >= 128 && ((((uintptr_t)va->data()) | ((uintptr_t)context->data()) | ((uintptr_t)state->data())) & 15) == 0) {
+    int blocks = std::max(1, std::min((m + 7) / 8, kNumSMs * 8));
+    gAttVec<<<blocks, 256, 0, cudaStreamOfEngine()>>>(out->data(), va->data(), context->data(), state->data(), m, k, b, t);
+    CUDA_LAUNCH_CHECK();
+    return;
+  }
   auto l = rowLaunch(m, k);
   ROW_DISPATCH(gAtt, l, out->data(), va->data(), context->data(), state->data(), m, k, b, t);
 }
@@ -910,7 +941,8 @@ __global__ void __launch_bounds__(256) gGRUFastForward(float* __restrict__ out,
                                                        const float* __restrict__ mask,
                                                        int rows,
                                                        int cols,
-                                                       bool final) {
+                                                       bool final,
+                                                       __nv_bfloat16* __restrict__ outShadow) {
   long long n = (long long)rows * cols;
   for(long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (long long)gridDim.x * blockDim.x) {
     int j = (int)(idx / cols);
@@ -930,7 +962,9 @@ __global__ void __launch_bounds__(256) gGRUFastForward(float* __restrict__ out,
     else
       h = tanhf(xWrow[l] + sUrow[l] * r + b[l]);
     float o = (1.0f - z) * h + z * st;
-    out[idx] = m * o + (1 - m) * st;
+    float res = m * o + (1 - m) * st;
+    out[idx] = res;
+    shadow::store1(outShadow, (size_t)idx, res);  // the next step's state product reads the bf16 copy (BF16S mode)
   }
 }
 
@@ -1007,6 +1041,126 @@ __global__ void __launch_bounds__(128) gGRUFastBackward(float* __restrict__ outS
     atomicAdd(outB + i, accR);
     atomicAdd(outB + k, accZ);
     atomicAdd(outB + l, accX);
+  }
+}
+
+// Vectorised backward of the fused GRU gate (cols % 4 == 0, 16-byte aligned rows): a lane owns FOUR
+// adjacent columns, a warp one row at a time, the 8 warps of a block walk `rowsPerBlock` rows of the
+// same 128-column strip.  Every input is read once with 128-bit loads that are all issued before
+// the first use; outputs flagged in `assignMask` (lazily-zero adjoints, tensors/tensor.h) are
+// stored instead of read-modify-written; the three bias-gradient sums meet in shared memory and
+// leave the block as one atomic per column.  (The scalar kernel above walked the rows serially:
+// 22 us for a 64 x 1024 state, the longest kernel of the recurrent backward chain.)
+__global__ void __launch_bounds__(256) gGRUFastBackwardVec(float* __restrict__ outState,
+                                                           float* __restrict__ outXW,
+                                                           float* __restrict__ outSU,
+                                                           float* __restrict__ outB,
+                                                           const float* __restrict__ state,
+                                                           const float* __restrict__ xW,
+                                                           const float* __restrict__ sU,
+                                                           const float* __restrict__ b,
+                                                           const float* __restrict__ mask,
+                                                           const float* __restrict__ adj,
+                                                           int rows,
+                                                           int cols,
+                                                           int rowsPerBlock,
+                                                           int assignMask,
+                                                           bool final,
+                                                           __nv_bfloat16* __restrict__ shadowSU) {
+  __shared__ float4 red[3][8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int i = (blockIdx.x * 32 + lane) * 4;
+  const bool active = i < cols;
+  float accR[4] = {0.f, 0.f, 0.f, 0.f}, accZ[4] = {0.f, 0.f, 0.f, 0.f}, accX[4] = {0.f, 0.f, 0.f, 0.f};
+  if(active) {
+    const float4 b4r = *(const float4*)(b + i), b4z = *(const float4*)(b + cols + i), b4x = *(const float4*)(b + 2 * cols + i);
+    const float br[4] = {b4r.x, b4r.y, b4r.z, b4r.w}, bz[4] = {b4z.x, b4z.y, b4z.z, b4z.w}, bx[4] = {b4x.x, b4x.y, b4x.z, b4x.w};
+    const int j0 = blockIdx.y * rowsPerBlock;
+    const int j1 = min(rows, j0 + rowsPerBlock);
+    for(int j = j0 + warp; j < j1; j += 8) {
+      const size_t rs = (size_t)j * cols + i, rg = (size_t)j * cols * 3 + i;
+      const float4 st4 = *(const float4*)(state + rs), a4 = *(const float4*)(adj + rs);
+      const float4 xr4 = *(const float4*)(xW + rg), xz4 = *(const float4*)(xW + rg + cols), xx4 = *(const float4*)(xW + rg + 2 * cols);
+      const float4 sr4 = *(const float4*)(sU + rg), sz4 = *(const float4*)(sU + rg + cols), sx4 = *(const float4*)(sU + rg + 2 * cols);
+      float4 oS = make_float4(0.f, 0.f, 0.f, 0.f), oXr = oS, oXz = oS, oXx = oS, oUr = oS, oUz = oS, oUx = oS;
+      if(outState && !(assignMask & 1))
+        oS = *(const float4*)(outState + rs);
+      if(outXW && !(assignMask & 2)) {
+        oXr = *(const float4*)(outXW + rg);
+        oXz = *(const float4*)(outXW + rg + cols);
+        oXx = *(const float4*)(outXW + rg + 2 * cols);
+      }
+      if(outSU && !(assignMask & 4)) {
+        oUr = *(const float4*)(outSU + rg);
+        oUz = *(const float4*)(outSU + rg + cols);
+        oUx = *(const float4*)(outSU + rg + 2 * cols);
+      }
+      const float m = !mask || mask[j];
+      const float st[4] = {st4.x, st4.y, st4.z, st4.w}, a[4] = {a4.x, a4.y, a4.z, a4.w};
+      const float xr[4] = {xr4.x, xr4.y, xr4.z, xr4.w}, xz[4] = {xz4.x, xz4.y, xz4.z, xz4.w}, xx[4] = {xx4.x, xx4.y, xx4.z, xx4.w};
+      const float sr[4] = {sr4.x, sr4.y, sr4.z, sr4.w}, sz[4] = {sz4.x, sz4.y, sz4.z, sz4.w}, sx[4] = {sx4.x, sx4.y, sx4.z, sx4.w};
+      float dS[4], dR[4], dZ[4], dX[4], dXu[4];
+#pragma unroll
+      for(int e = 0; e < 4; ++e) {
+        float r = stableLogit(xr[e] + sr[e] + br[e]);
+        float z = stableLogit(xz[e] + sz[e] + bz[e]);
+        float h;
+        if(final)
+          h = tanhf(xx[e] + (sx[e] + bx[e]) * r);
+        else
+          h = tanhf(xx[e] + sx[e] * r + bx[e]);
+        float t = (1 - z) * (1 - h * h);
+        dS[e] = (m * z - m + 1) * a[e];
+        float dfdxW_r = m * r * (1 - r) * t * a[e];
+        if(final)
+          dfdxW_r *= sx[e] + bx[e];
+        else
+          dfdxW_r *= sx[e];
+        float dfdxW_z = m * (1 - z) * z * (st[e] - h) * a[e];
+        float dfdxW_x = m * t * a[e];
+        dR[e] = dfdxW_r;
+        dZ[e] = dfdxW_z;
+        dX[e] = dfdxW_x;
+        dXu[e] = dfdxW_x * r;
+        accR[e] += dfdxW_r;
+        accZ[e] += dfdxW_z;
+        accX[e] += final ? dfdxW_x * r : dfdxW_x;
+      }
+      if(outState)
+        *(float4*)(outState + rs) = make_float4(oS.x + dS[0], oS.y + dS[1], oS.z + dS[2], oS.w + dS[3]);
+      if(outXW) {
+        *(float4*)(outXW + rg) = make_float4(oXr.x + dR[0], oXr.y + dR[1], oXr.z + dR[2], oXr.w + dR[3]);
+        *(float4*)(outXW + rg + cols) = make_float4(oXz.x + dZ[0], oXz.y + dZ[1], oXz.z + dZ[2], oXz.w + dZ[3]);
+        *(float4*)(outXW + rg + 2 * cols) = make_float4(oXx.x + dX[0], oXx.y + dX[1], oXx.z + dX[2], oXx.w + dX[3]);
+      }
+      if(outSU) {
+        *(float4*)(outSU + rg) = make_float4(oUr.x + dR[0], oUr.y + dR[1], oUr.z + dR[2], oUr.w + dR[3]);
+        *(float4*)(outSU + rg + cols) = make_float4(oUz.x + dZ[0], oUz.y + dZ[1], oUz.z + dZ[2], oUz.w + dZ[3]);
+        *(float4*)(outSU + rg + 2 * cols) = make_float4(oUx.x + dXu[0], oUx.y + dXu[1], oUx.z + dXu[2], oUx.w + dXu[3]);
+        // assigned adjoint with one writer: its two backward products read this bf16 copy (BF16S mode)
+        shadow::store4(shadowSU, rg, make_float4(dR[0], dR[1], dR[2], dR[3]));
+        shadow::store4(shadowSU, rg + cols, make_float4(dZ[0], dZ[1], dZ[2], dZ[3]));
+        shadow::store4(shadowSU, rg + 2 * cols, make_float4(dXu[0], dXu[1], dXu[2], dXu[3]));
+      }
+    }
+  }
+  if(!outB)
+    return;
+  red[0][warp][lane] = make_float4(accR[0], accR[1], accR[2], accR[3]);
+  red[1][warp][lane] = make_float4(accZ[0], accZ[1], accZ[2], accZ[3]);
+  red[2][warp][lane] = make_float4(accX[0], accX[1], accX[2], accX[3]);
+  __syncthreads();
+  // 3 gates x 128 columns = 384 sums of 8 partials: thread t takes gate t / 128, column t % 128 (and 256.. a second one)
+  for(int t = threadIdx.x; t < 384; t += 256) {
+    const int g = t >> 7, c = t & 127;
+    const int col = blockIdx.x * 128 + c;
+    if(col >= cols)
+      continue;
+    float s = 0.f;
+#pragma unroll
+    for(int w = 0; w < 8; ++w)
+      s += ((const float*)&red[g][w][c >> 2])[c & 3];
+    atomicAdd(outB + g * cols + col, s);
   }
 }
 
@@ -1180,8 +1334,9 @@ void GRUFastForward(Tensor out, std::vector<Tensor> inputs, bool final) {
   device::setDevice(out->getDevice());
   int cols = out->shape().back();
   int rows = out->shape().elements() / cols;
+  out->takeLazyZero();
   gGRUFastForward<<<gridFor((size_t)rows * cols, 256), 256, 0, cudaStreamOfEngine()>>>(
-      out->data(), inputs[0]->data(), inputs[1]->data(), inputs[2]->data(), inputs[3]->data(), dataOrNull(inputs, 4), rows, cols, final);
+      out->data(), inputs[0]->data(), inputs[1]->data(), inputs[2]->data(), inputs[3]->data(), dataOrNull(inputs, 4), rows, cols, final, shadow::produce(out));
   CUDA_LAUNCH_CHECK();
 }
 
@@ -1189,6 +1344,35 @@ void GRUFastBackward(std::vector<Tensor> outputs, std::vector<Tensor> inputs, Te
   device::setDevice(adj->getDevice());
   int cols = adj->shape().back();
   int rows = adj->shape().elements() / cols;
+  static const bool scalarOnly = std::getenv("MRN_GRU_SCALAR_BACKWARD") != nullptr;
+  bool vec = !scalarOnly && cols % 4 == 0;
+  for(size_t k = 0; vec && k < 4; ++k)
+    vec = ((uintptr_t)inputs[k]->data() & 15) == 0;
+  vec = vec && ((uintptr_t)adj->data() & 15) == 0;
+  for(size_t k = 0; vec && k < 3 && k < outputs.size(); ++k)
+    if(outputs[k])
+      vec = ((uintptr_t)outputs[k]->rawData() & 15) == 0;
+  if(vec) {
+    // lazily-zero adjoints (the first writer assigns): no memset, no read of the old value
+    int assignMask = 0;
+    float* out[3] = {nullptr, nullptr, nullptr};
+    for(size_t k = 0; k < 3 && k < outputs.size(); ++k)
+      if(outputs[k]) {
+        if(outputs[k]->takeLazyZero())
+          assignMask |= 1 << k;
+        out[k] = outputs[k]->rawData();
+      }
+    __nv_bfloat16* shadowSU = (out[2] && (assignMask & 4)) ? shadow::produce(outputs[2]) : nullptr;
+    int strips = (cols / 4 + 31) / 32;
+    // rows of a strip are split over blocks until the grid has about two blocks per SM, 8 rows (one per warp) at least
+    int splits = std::max(1, std::min((kNumSMs * 2 + strips - 1) / strips, (rows + 7) / 8));
+    int rowsPerBlock = ((rows + splits - 1) / splits + 7) / 8 * 8;
+    splits = (rows + rowsPerBlock - 1) / rowsPerBlock;
+    gGRUFastBackwardVec<<<dim3(strips, splits), 256, 0, cudaStreamOfEngine()>>>(out[0], out[1], out[2], dataOrNull(outputs, 3), inputs[0]->data(), inputs[1]->data(), inputs[2]->data(),
+                                                                                 inputs[3]->data(), dataOrNull(inputs, 4), adj->data(), rows, cols, rowsPerBlock, assignMask, final, shadowSU);
+    CUDA_LAUNCH_CHECK();
+    return;
+  }
   auto l = cellBwdLaunch(rows, cols);
   gGRUFastBackward<<<l.grid, 128, 0, cudaStreamOfEngine()>>>(dataOrNull(outputs, 0),
                                                             dataOrNull(outputs, 1),
@@ -1517,20 +1701,91 @@ void TransposeND(Tensor out, Tensor in, const std::vector<int>& vAxis) {
   CUDA_LAUNCH_CHECK();
 }
 
+namespace {
+// All blocks of a concatenation in ONE launch: the pointer table travels in the kernel
+// parameters (the reference issues one cudaMemcpy / kernel per input plus a stream sync,
+// tensor_operators.cu:35-162; a recurrent layer concatenates one state per time step).
+constexpr int kConcatMax = 96;
+struct ConcatTable {
+  float* narrow[kConcatMax];
+  int width[kConcatMax];   // elements (or float4) per row of input i
+  int offset[kConcatMax];  // its first column inside the wide row
+};
+
+// grid = (chunks, inputs); wide viewed as [rows][outWidth]
+template <bool TO_WIDE, typename T>
+__global__ void __launch_bounds__(256) gCopyBlocks(T* __restrict__ wide, const __grid_constant__ ConcatTable tab, int rows, int outWidth) {
+  const int i = blockIdx.y;
+  T* __restrict__ narrow = (T*)tab.narrow[i];
+  const int width = tab.width[i], offset = tab.offset[i];
+  const long long items = (long long)rows * width;
+  for(long long w = (long long)blockIdx.x * blockDim.x + threadIdx.x; w < items; w += (long long)gridDim.x * blockDim.x) {
+    int r = (int)(w / width);
+    int c = (int)(w - (long long)r * width);
+    size_t wi = (size_t)r * outWidth + offset + c;
+    if(TO_WIDE)
+      wide[wi] = narrow[w];
+    else
+      narrow[w] = wide[wi];
+  }
+}
+
+template <bool TO_WIDE>
+void copyBlocks(float* wide, const std::vector<float*>& narrow, const std::vector<int>& widths, int rows, int outWidth) {
+  auto st = cudaStreamOfEngine();
+  size_t n = narrow.size();
+  int offset = 0;
+  for(size_t first = 0; first < n; first += kConcatMax) {
+    size_t count = std::min<size_t>(kConcatMax, n - first);
+    if(count == 1) {  // the two-operand cases keep the plain kernel
+      copyBlock<TO_WIDE>(wide, narrow[first], rows, widths[first], outWidth, offset);
+      offset += widths[first];
+      continue;
+    }
+    ConcatTable tab;
+    bool vec = outWidth % 4 == 0 && (((uintptr_t)wide) & 15) == 0;
+    int maxWidth = 0;
+    for(size_t k = 0; k < count; ++k) {
+      tab.narrow[k] = narrow[first + k];
+      tab.width[k] = widths[first + k];
+      tab.offset[k] = offset;
+      vec = vec && widths[first + k] % 4 == 0 && offset % 4 == 0 && (((uintptr_t)narrow[first + k]) & 15) == 0;
+      maxWidth = std::max(maxWidth, widths[first + k]);
+      offset += widths[first + k];
+    }
+    if(vec)
+      for(size_t k = 0; k < count; ++k) {
+        tab.width[k] /= 4;
+        tab.offset[k] /= 4;
+      }
+    size_t items = (size_t)rows * (vec ? maxWidth / 4 : maxWidth);
+    // enough blocks over all inputs together to fill the machine, at least one per input
+    int perInput = (int)std::max<size_t>(1, std::min<size_t>((items + 255) / 256, (size_t)(kNumSMs * 8 + count - 1) / count));
+    dim3 grid(perInput, (unsigned)count);
+    if(vec)
+      gCopyBlocks<TO_WIDE, float4><<<grid, 256, 0, st>>>((float4*)wide, tab, rows, outWidth / 4);
+    else
+      gCopyBlocks<TO_WIDE, float><<<grid, 256, 0, st>>>(wide, tab, rows, outWidth);
+    CUDA_LAUNCH_CHECK();
+  }
+}
+}  // namespace
+
 void Concatenate(Tensor out, const std::vector<Tensor>& inputs, int ax) {
   device::setDevice(out->getDevice());
   // rows = product of dims before `ax`; each input contributes a contiguous
-  // block of (elements / rows) per row.  One launch per input, no sync.
+  // block of (elements / rows) per row.  One launch for (up to 96) inputs, no sync.
   int rows = 1;
   for(int i = 0; i < ax; ++i)
     rows *= out->shape()[i];
   int outWidth = out->shape().elements() / rows;
-  int offset = 0;
+  std::vector<float*> ptrs;
+  std::vector<int> widths;
   for(auto in : inputs) {
-    int width = in->shape().elements() / rows;
-    copyBlock<true>(out->data(), in->data(), rows, width, outWidth, offset);
-    offset += width;
+    ptrs.push_back(in->data());
+    widths.push_back(in->shape().elements() / rows);
   }
+  copyBlocks<true>(out->data(), ptrs, widths, rows, outWidth);
 }
 
 void Deconcatenate(std::vector<Tensor>& outputs, const Tensor in, int ax) {
@@ -1539,13 +1794,14 @@ void Deconcatenate(std::vector<Tensor>& outputs, const Tensor in, int ax) {
   for(int i = 0; i < ax; ++i)
     rows *= in->shape()[i];
   int inWidth = in->shape().elements() / rows;
-  int offset = 0;
+  std::vector<float*> ptrs;
+  std::vector<int> widths;
   for(auto out : outputs) {
-    int width = out->shape().elements() / rows;
-    out->takeLazyZero();
-    copyBlock<false>(in->data(), out->data(), rows, width, inWidth, offset);  // ASSIGNS
-    offset += width;
+    out->takeLazyZero();  // ASSIGNS
+    ptrs.push_back(out->rawData());
+    widths.push_back(out->shape().elements() / rows);
   }
+  copyBlocks<false>(in->data(), ptrs, widths, rows, inWidth);
 }
 
 void CopyRows(Tensor out, const Tensor in, const int* deviceIndices, size_t n) {

@@ -81,7 +81,11 @@ public:
     auto right = directional(alternate ? rnn::dir::alternating_backward : rnn::dir::backward, prefix_ + "_bi_r");
     // forward stack first: its parameters are created (and seeded) before the backward stack's
     Expr fw = left->transduce(embeddings, mask);
+    // the two directions share nothing but their input: the backward-direction stack is a chain (lane) of its own,
+    // forward and backward passes run both stacks side by side (ExpressionGraph::setLane, tensors/device.h)
+    graph->setLane(options_->get<bool>("rnn-lanes", true) ? 1 : 0);
     Expr bw = right->transduce(embeddings, mask);
+    graph->setLane(0);
     Expr context = concatenate({fw, bw}, axis = -1);
 
     if(!twoStacks && depth > 1) {

@@ -88,6 +88,26 @@ void joinSide();
 // true between forkSide() and returnFromSide()/joinSide()
 bool onSide();
 
+// ---- lanes: independent chains of one pass -------------------------------------------------------
+// The two directional stacks of a bidirectional recurrent encoder are two long chains of small,
+// dependent kernels that share nothing but their input; on one stream they run back to back.  The
+// graph tags nodes with a lane (ExpressionGraph::setLane); while a lane region is open, work of lane
+// k > 0 goes to that lane's own stream.  openLanes() starts a region (an event on the main stream that
+// every lane waits for at its first use); closeLanes() makes the main stream wait for every lane used
+// since and ends the region.  laneMark() / laneWait() order individual results across lanes: a mark
+// stands for "everything issued so far on the current lane", laneWait makes the current lane wait for
+// it (marks of an earlier region are complete by construction and ignored; nullptr is ignored).  The
+// side stream forks from the CURRENT lane.  Under capture the lanes join the recording, so the
+// replayed CUDA graph has the same parallel branches.  All no-ops on the CPU oracle.
+constexpr int kMaxLanes = 4;
+void openLanes();
+void closeLanes();
+bool lanesOpen();
+void selectLane(int lane);  // 0 = main stream; ignored (main) outside a region
+int currentLane();
+void* laneMark();
+void laneWait(void* mark);
+
 // ---- inter-process device memory (peer-memory gradient exchange) -----------------------------
 size_t ipcHandleBytes();
 // handle of the allocation that STARTS at ptr (arenas and the signal pad are whole allocations)

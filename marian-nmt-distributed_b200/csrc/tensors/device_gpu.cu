@@ -33,15 +33,38 @@ struct ThreadCtx {
   bool sideDirty{false};
   std::vector<cudaEvent_t> events;  // fork/join markers, reused every step
   size_t nextEvent{0};
+  // lanes (see device.h)
+  struct LaneMark {
+    cudaEvent_t event{nullptr};
+    int lane{0};
+    uint64_t seq{0};
+    uint64_t region{0};
+  };
+  cudaStream_t lanes[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
+  bool laneUsed[kMaxLanes] = {false, false, false, false};
+  uint64_t laneSeq[kMaxLanes] = {0, 0, 0, 0};               // marks taken per lane in this region
+  uint64_t laneSeen[kMaxLanes][kMaxLanes] = {};             // [waiter][source]: highest mark already waited for
+  int lane{0};
+  bool lanesOpen{false};
+  uint64_t region{0};
+  cudaEvent_t laneOpenEvent{nullptr};
+  std::vector<LaneMark*> marks;  // pooled per region
+  size_t nextMark{0};
 };
 thread_local ThreadCtx tctx;
 
 cudaStream_t mainStream();
 
+cudaStream_t laneStream() {
+  if(tctx.lanesOpen && tctx.lane > 0)
+    return tctx.lanes[tctx.lane];
+  return mainStream();
+}
+
 cudaStream_t stream() {
   if(tctx.onSide)
     return tctx.side;
-  return mainStream();
+  return laneStream();
 }
 
 cudaEvent_t nextMarker() {
@@ -79,6 +102,8 @@ void setDevice(int deviceId) {
   tctx.device = deviceId;
   tctx.own = nullptr;  // streams are (re)created lazily for the new device
   tctx.side = nullptr;
+  for(auto& l : tctx.lanes)
+    l = nullptr;
 }
 int getDevice() {
   return tctx.device < 0 ? 0 : tctx.device;
@@ -241,8 +266,9 @@ void forkSide() {
   cudaStream_t main = mainStream();
   if(!tctx.side)
     CUDA_CHECK(cudaStreamCreateWithFlags(&tctx.side, cudaStreamNonBlocking));
+  (void)main;
   cudaEvent_t e = nextMarker();
-  CUDA_CHECK(cudaEventRecord(e, main));
+  CUDA_CHECK(cudaEventRecord(e, laneStream()));  // the side work follows what its lane has issued so far
   CUDA_CHECK(cudaStreamWaitEvent(tctx.side, e, 0));
   tctx.onSide = true;
   tctx.sideDirty = true;
@@ -262,6 +288,81 @@ void joinSide() {
     tctx.sideDirty = false;
   }
   tctx.nextEvent = 0;
+}
+
+void openLanes() {
+  if(tctx.lanesOpen)
+    return;
+  if(!tctx.laneOpenEvent)
+    CUDA_CHECK(cudaEventCreateWithFlags(&tctx.laneOpenEvent, cudaEventDisableTiming));
+  CUDA_CHECK(cudaEventRecord(tctx.laneOpenEvent, mainStream()));
+  tctx.lanesOpen = true;
+  tctx.lane = 0;
+  ++tctx.region;
+  tctx.nextMark = 0;
+  for(int i = 0; i < kMaxLanes; ++i) {
+    tctx.laneUsed[i] = false;
+    tctx.laneSeq[i] = 0;
+    for(int j = 0; j < kMaxLanes; ++j)
+      tctx.laneSeen[i][j] = 0;
+  }
+}
+void closeLanes() {
+  if(!tctx.lanesOpen)
+    return;
+  ABORT_IF(tctx.onSide, "closeLanes() while on the side stream");
+  for(int k = 1; k < kMaxLanes; ++k)
+    if(tctx.laneUsed[k]) {
+      cudaEvent_t e = nextMarker();
+      CUDA_CHECK(cudaEventRecord(e, tctx.lanes[k]));
+      CUDA_CHECK(cudaStreamWaitEvent(mainStream(), e, 0));
+      tctx.laneUsed[k] = false;
+    }
+  tctx.lane = 0;
+  tctx.lanesOpen = false;
+}
+bool lanesOpen() {
+  return tctx.lanesOpen;
+}
+void selectLane(int lane) {
+  if(!tctx.lanesOpen || lane <= 0 || lane >= kMaxLanes) {
+    tctx.lane = 0;
+    return;
+  }
+  if(!tctx.laneUsed[lane]) {
+    if(!tctx.lanes[lane])
+      CUDA_CHECK(cudaStreamCreateWithFlags(&tctx.lanes[lane], cudaStreamNonBlocking));
+    CUDA_CHECK(cudaStreamWaitEvent(tctx.lanes[lane], tctx.laneOpenEvent, 0));
+    tctx.laneUsed[lane] = true;
+  }
+  tctx.lane = lane;
+}
+int currentLane() {
+  return tctx.lanesOpen ? tctx.lane : 0;
+}
+void* laneMark() {
+  if(!tctx.lanesOpen)
+    return nullptr;
+  if(tctx.nextMark == tctx.marks.size()) {
+    auto* m = new ThreadCtx::LaneMark();
+    CUDA_CHECK(cudaEventCreateWithFlags(&m->event, cudaEventDisableTiming));
+    tctx.marks.push_back(m);
+  }
+  auto* m = tctx.marks[tctx.nextMark++];
+  m->lane = tctx.lane;
+  m->seq = ++tctx.laneSeq[tctx.lane];
+  m->region = tctx.region;
+  CUDA_CHECK(cudaEventRecord(m->event, laneStream()));
+  return m;
+}
+void laneWait(void* mark) {
+  auto* m = (ThreadCtx::LaneMark*)mark;
+  if(!m || !tctx.lanesOpen || m->region != tctx.region || m->lane == tctx.lane)
+    return;
+  if(tctx.laneSeen[tctx.lane][m->lane] >= m->seq)
+    return;  // a later mark of that lane was already waited for
+  CUDA_CHECK(cudaStreamWaitEvent(laneStream(), m->event, 0));
+  tctx.laneSeen[tctx.lane][m->lane] = m->seq;
 }
 
 size_t ipcHandleBytes() {

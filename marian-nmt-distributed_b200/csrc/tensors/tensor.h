@@ -39,6 +39,9 @@ public:
   mutable bool shadowWanted{false};
   mutable bool shadowValid{false};
   mutable uint32_t shadowGen{0};  // pool generation the buffer belongs to (stale buffers are ignored)
+  // lane mark behind a shadow that a CONSUMER converted (device::laneMark): a consumer on another lane waits for it
+  // (shadows written by the producing kernel need none: consumers wait for the producing node anyway)
+  mutable void* shadowMark{nullptr};
   // shadowOnly: every reader of this tensor is a tensor-core product (graph analysis, see Node): a producer that
   // writes the bf16 shadow may leave the fp32 bytes unwritten (half of the step's activation write traffic goes
   // to fp32 tensors nobody reads).  fp32Skipped records that one did - fp32 readers must not appear after that.

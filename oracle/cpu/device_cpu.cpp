@@ -52,6 +52,14 @@ void forkSide() {}
 void returnFromSide() {}
 void joinSide() {}
 bool onSide() { return false; }
+// lanes: one host thread runs everything in tape order
+void openLanes() {}
+void closeLanes() {}
+bool lanesOpen() { return false; }
+void selectLane(int) {}
+int currentLane() { return 0; }
+void* laneMark() { return nullptr; }
+void laneWait(void*) {}
 void* recordMarker(void*) { return nullptr; }
 void waitMarker(void*) {}
 void freeMarker(void*) {}

@@ -108,13 +108,31 @@ def test_transformer_base_padded_batch_matches_oracle(cuda, pkg, oracle_tb_padde
 # ---------------------------------------------------------------- deep GRU s2s 64 x 50
 @pytest.fixture(scope="module")
 def oracle_gru(oracle):
-    return run(oracle, GRU_OPTS, 0, (64, 50, 50), 2)
+    return run(oracle, GRU_OPTS, 0, (64, 50, 50), 3)
 
 
 @pytest.mark.parametrize("mode,tol", [(0, 1e-4), (2, 1e-4), (3, 3e-3), (4, 2e-2)], ids=["fp32", "bf16x3", "tf32", "bf16"])
 def test_deep_gru_full_size_matches_oracle(cuda, oracle_gru, mode, tol):
     got = run(cuda, GRU_OPTS, mode, (64, 50, 50), 2)
     check(got, oracle_gru, tol, "deep GRU s2s 64x50 mode %d" % mode)
+
+
+def test_deep_gru_full_size_replay_matches_oracle(cuda, oracle_gru):
+    """The same updates through CUDA-graph capture + replay (what bench.py --model s2s-deep-gru times): the captured
+    graph carries the two encoder lanes and the side stream as parallel branches.  Exact mode."""
+    o = dict(GRU_OPTS)
+    o.update({"gemm-mode": 2, "graph-replay": "true", "data-seed": 1111})
+    t = cuda.trainer(o)
+    costs = []
+    for s in range(3):
+        t.next_synthetic_batch(64, 50, 50)
+        t.compute_gradients()
+        t.update()
+        costs.append(t.cost())
+    st = t.stats()
+    t.close()
+    assert st["plans"] == 1 and st["replays"] >= 1, st
+    assert np.allclose(costs, oracle_gru["costs"], rtol=3e-4), (costs, oracle_gru["costs"])
 
 
 # ---------------------------------------------------------------- Transformer-big geometry, T = 80

@@ -79,6 +79,28 @@ def test_graph_replay_equals_eager(cuda, opts, mode):
     assert np.mean(diff > 2e-5) < 0.01 and np.median(diff) < 2e-6
 
 
+@pytest.mark.parametrize("enc_type", ["bidirectional", "alternating", "bi-unidirectional"])
+@pytest.mark.parametrize("mode", [2, 4], ids=["bf16x3", "bf16-shadows"])
+def test_encoder_lanes_equal_single_stream(cuda, enc_type, mode):
+    """The backward-direction stack of the s2s encoder runs as a lane of its own (own stream, ordered against the
+    rest of the tape only where values / adjoints cross: ExpressionGraph::setLane).  Same results as the one-stream
+    schedule (rnn-lanes=false), eagerly and through the captured graph, on padded batches (mask path)."""
+    opts = "type=s2s;dim-vocabs=200,220;dim-emb=32;dim-rnn=64;enc-depth=3;dec-depth=2;enc-cell-depth=2;workspace=256;enc-type=" + enc_type
+    for replay in (False, True):
+        one = run_steps(cuda, opts + ";rnn-lanes=false", mode, steps=6, replay=replay, keep=not replay)
+        two = run_steps(cuda, opts, mode, steps=6, replay=replay, keep=not replay)
+        assert np.allclose(two["costs"], one["costs"], rtol=2e-5), (replay, two["costs"], one["costs"])
+        if not replay:
+            close(two["logits"], one["logits"], 1e-6, "logits")
+            for name, g in one["grads"].items():  # bias gradients are sums of atomics: order noise only
+                scale = max(float(np.abs(g).max()), 1e-6)
+                assert float(np.abs(two["grads"][name] - g).max()) <= 2e-5 * scale, name
+        diff = np.abs(two["params"] - one["params"])
+        assert np.mean(diff > 2e-5) < 0.01 and np.median(diff) < 2e-6
+        if replay:
+            assert two["stats"]["plans"] == 1 and two["stats"]["replays"] >= 3, two["stats"]
+
+
 @pytest.mark.parametrize("opts", [TRANSFORMER, S2S_GRU, S2S_LSTM], ids=["transformer", "s2s-gru", "s2s-lstm"])
 @pytest.mark.parametrize("optimizer", ["adam", "sgd"])
 def test_bf16_shadow_mode_equals_packed_bf16_model(cuda, opts, optimizer):

@@ -92,6 +92,9 @@ def test_element_inplace(cuda, oracle):
     ((1, 50, 64, 1), (1, 50, 64, 37)),  # last-axis reduction                 (case 1)
     ((5, 1), (5, 1000)),
     ((50, 1, 16), (50, 64, 16)),      # reduce a middle axis
+    ((1, 64, 2048), (50, 64, 2048)),  # leading axis reduced, two trailing axes kept (case 3b)
+    ((1, 1, 5, 36), (3, 7, 5, 36)),
+    ((1, 5, 35), (7, 5, 35)),         # same shape class, unaligned rows: generic kernel
     ((3, 50, 16), (3, 50, 16)),       # plain accumulate                      (case 2)
     ((50, 64, 16), (50, 64, 1)),      # broadcast input accumulated into full (case 2 + bcast)
 ])
@@ -114,6 +117,17 @@ def test_add_two_inputs_broadcast_reduce(cuda, oracle):
         lib.call("mrn_add", b"mult", 1.0, o2.t(), lib.tensor_list([a.t(), b.t()]), 2, 0.0)   # reduces over axis 0
         lib.call("mrn_add", b"tanh_grad", 1.0, o1.t(), lib.tensor_list([a.t(), a.t()]), 2, 0.0)
         return {"o1": o1.numpy(), "o2": o2.numpy()}
+
+    compare(cuda, oracle, fn, rtol=5e-5)
+
+
+def test_reduce_scalar_product_pattern(cuda, oracle):
+    # scalar_product forward of the recurrent attention: out[1,B,C] = sum_t ctx[t,b,c] * e[t,b]   (case 3b, broadcast operand)
+    def fn(lib):
+        ctx, e = lib.array(rnd(5, 50, 64, 512)), lib.array(rnd(6, 50, 64, 1))
+        o1 = lib.array(rnd(7, 1, 64, 512))
+        lib.call("mrn_add", b"mult", 1.0, o1.t(), lib.tensor_list([ctx.t(), e.t()]), 2, 0.0)
+        return {"o1": o1.numpy()}
 
     compare(cuda, oracle, fn, rtol=5e-5)
 
@@ -355,7 +369,8 @@ def test_layer_norm_reference_golden_input(cuda, oracle, goldens):
 
 
 # ---------------------------------------------------------------- GRU / LSTM / highway
-@pytest.mark.parametrize("rows,cols,with_mask,final", [(64, 128, True, False), (5, 33, False, True), (8, 1024, True, True)])
+@pytest.mark.parametrize("rows,cols,with_mask,final", [(64, 128, True, False), (5, 33, False, True), (8, 1024, True, True), (64, 1024, False, False), (3, 132, True, False),
+                                                        (70, 1024, True, True), (3200, 256, True, False)])
 def test_gru(cuda, oracle, rows, cols, with_mask, final):
     def fn(lib):
         state, xW, sU = lib.array(rnd(1, rows, cols)), lib.array(rnd(2, rows, 3 * cols)), lib.array(rnd(3, rows, 3 * cols))
@@ -409,7 +424,7 @@ def test_highway(cuda, oracle):
 
 
 # ---------------------------------------------------------------- Bahdanau attention
-@pytest.mark.parametrize("T,B,K", [(50, 64, 256), (7, 3, 33)])
+@pytest.mark.parametrize("T,B,K", [(50, 64, 256), (7, 3, 33), (50, 64, 2048), (9, 5, 132)])
 def test_att(cuda, oracle, T, B, K):
     def fn(lib):
         va, ctx, state = lib.array(rnd(1, K, 1)), lib.array(rnd(2, T, B, K)), lib.array(rnd(3, 1, 1, B, K))
@@ -444,7 +459,8 @@ def test_transpose(cuda, oracle, shape, axes):
     assert np.array_equal(exp["out"], np.transpose(rnd(1, *shape), axes))
 
 
-@pytest.mark.parametrize("shape,axis,n", [((1, 2, 2, 3), 2, 4), ((1, 2, 2, 3), -1, 4), ((1, 2, 2, 3), -3, 4), ((1, 2, 2, 3), 0, 4), ((1, 64, 128), -3, 50), ((64, 100), -1, 3)])
+@pytest.mark.parametrize("shape,axis,n", [((1, 2, 2, 3), 2, 4), ((1, 2, 2, 3), -1, 4), ((1, 2, 2, 3), -3, 4), ((1, 2, 2, 3), 0, 4), ((1, 64, 128), -3, 50), ((64, 100), -1, 3),
+                                          ((1, 8, 64), -3, 100), ((1, 3, 5), -3, 7), ((6, 5), -1, 97), ((1, 64, 1024), -3, 50)])
 def test_concatenate_roundtrip(cuda, oracle, shape, axis, n):
     ax = axis if axis >= 0 else len(shape) + axis
     oshape = list(shape)
