@@ -88,6 +88,13 @@ int mrn_prod_grouped_nt(void* gemm, mrn_tensor C, const mrn_tensor* As, const mr
  * AffineNodeOp::backwardOps followed by SwishNodeOp::backwardOps (src/graph/node_operators_unary.h, the
  * "swish" functor of src/functional/predicates.h).  tf32 mode only; returns an error otherwise. */
 int mrn_prod_swish_grad_nt(void* gemm, mrn_tensor C, mrn_tensor A, mrn_tensor B, mrn_tensor H, float beta);
+/* The two products above with the bias gradients they deliver in the training step: col_sums[g] (+)= column sums of
+ * A_g (A = the adjoint of an affine node, so its column sums are the gradient of that node's bias: Add(_1, bias->grad(),
+ * adj) of AffineNodeOp::backwardOps, src/graph/node_operators_binary.h:208-212, reference kernel gAddGeneric), taken
+ * from the A tiles while they stream through the tensor-core kernel.  Tensor-core modes; elsewhere the sums are
+ * produced by the column-sum kernel. */
+int mrn_prod_grouped_nt_sums(void* gemm, mrn_tensor C, const mrn_tensor* As, const mrn_tensor* Bs, int n, float beta, const mrn_tensor* col_sums);
+int mrn_prod_swish_grad_nt_sums(void* gemm, mrn_tensor C, mrn_tensor A, mrn_tensor B, mrn_tensor H, float beta, mrn_tensor col_sum);
 /* C_i = beta C_i + op(A) B_i (+ bias_i), i < n <= 3: products that share their A operand - the query / key / value
  * projections of Transformer::MultiHead (src/models/transformer.h:194-261: three affine() calls on the same input) and
  * their weight gradients (AffineNodeOp::backwardOps, three Prod(.., true, false, 1.0) with the same x) - as ONE launch in

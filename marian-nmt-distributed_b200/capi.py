@@ -41,6 +41,8 @@ _SIGNATURES = {
     "mrn_prod_batched": [_V, _T, _T, _T, _I, _I, _F, _F],
     "mrn_prod_grouped_nt": [_V, _T, _TP, _TP, _I, _F],
     "mrn_prod_swish_grad_nt": [_V, _T, _T, _T, _T, _F],
+    "mrn_prod_grouped_nt_sums": [_V, _T, _TP, _TP, _I, _F, _TP],
+    "mrn_prod_swish_grad_nt_sums": [_V, _T, _T, _T, _T, _F, _T],
     "mrn_prod_shared_a": [_V, _TP, _T, _TP, _TP, _I, _I, _F, ctypes.POINTER(_I)],
     "mrn_prod_affine": [_V, _T, _T, _T, _T],
     "mrn_element": [ctypes.c_char_p, _T, _TP, _I, _F],

@@ -145,6 +145,19 @@ int mrn_prod_grouped_nt(void* g, mrn_tensor C, const mrn_tensor* As, const mrn_t
     ProdGroupedNT((GemmHandle)g, wrap(C), wrapAll(As, n), wrapAll(Bs, n), beta);
   });
 }
+int mrn_prod_grouped_nt_sums(void* g, mrn_tensor C, const mrn_tensor* As, const mrn_tensor* Bs, int n, float beta, const mrn_tensor* col_sums) {
+  return guarded([&] {
+    gemmInvalidateCache((GemmHandle)g);
+    ProdGroupedNT((GemmHandle)g, wrap(C), wrapAll(As, n), wrapAll(Bs, n), beta, wrapAll(col_sums, n));
+  });
+}
+int mrn_prod_swish_grad_nt_sums(void* g, mrn_tensor C, mrn_tensor A, mrn_tensor B, mrn_tensor H, float beta, mrn_tensor col_sum) {
+  return guarded([&] {
+    gemmInvalidateCache((GemmHandle)g);
+    ABORT_IF(!ProdSwishGradFusable((GemmHandle)g, wrap(C), wrap(A), wrap(B), wrap(H)), "mrn_prod_swish_grad_nt_sums: needs a tensor-core mode and 16-byte aligned operands");
+    ProdSwishGradNT((GemmHandle)g, wrap(C), wrap(A), wrap(B), wrap(H), beta, wrap(col_sum));
+  });
+}
 int mrn_prod_shared_a(void* g, const mrn_tensor* Cs, mrn_tensor A, const mrn_tensor* Bs, const mrn_tensor* biases, int n, int tA, float beta, int* fused) {
   return guarded([&] {
     gemmInvalidateCache((GemmHandle)g);

@@ -167,10 +167,13 @@ __global__ void __launch_bounds__(256) gAddReduceRows(Functor f, float* __restri
 // 128-bit loads, the 8 warps stride the rows of a slice, partial sums meet in shared memory
 // and leave through ONE atomicAdd per column and slice.
 template <int K, class Functor>
-__global__ void __launch_bounds__(256) gAddColumns(Functor f, float* __restrict__ out, Operands<K> ops, RowGeom g, float scale, int rowsPerSlice, int assign, int keep2) {
+__global__ void __launch_bounds__(256) gAddColumns(Functor f, float* __restrict__ out, Operands<K> ops, RowGeom g, float scale, int rowsPerSlice, int assign, int keep2,
+                                                   __nv_bfloat16* __restrict__ outShadow) {
   pdlEnter();
   __shared__ float red[8][32][5];
   const int c = (blockIdx.x * 32 + threadIdx.x) * 4;
+  if(keep2 && outShadow)
+    outShadow += (size_t)blockIdx.z * g.cols;
   const int r0 = blockIdx.y * rowsPerSlice;
   const int r1 = min(g.rows, r0 + rowsPerSlice);
   float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -229,10 +232,12 @@ __global__ void __launch_bounds__(256) gAddColumns(Functor f, float* __restrict_
       sum[e] *= scale;
     }
     float4 v = make_float4(sum[0], sum[1], sum[2], sum[3]);
-    if(assign)
+    if(assign) {
       *reinterpret_cast<float4*>(out + c) = v;
-    else
+      shadow::store4(outShadow, (size_t)c, v);  // complete values: the bf16 copy a consuming product reads (BF16S mode)
+    } else {
       redAdd4(out + c, v);  // out is 16-byte aligned (checked by the launcher)
+    }
   }
 }
 
@@ -470,7 +475,7 @@ void Add(Functor functor, float scale, Tensor out, Tensors... tensors) {
     int rowsPerSlice = (g.rows + slices - 1) / slices;
     slices = (g.rows + rowsPerSlice - 1) / rowsPerSlice;
     int assign = (slices == 1 && out->takeLazyZero()) ? 1 : 0;
-    launchPdl(ew::gAddColumns<K, Functor>, dim3(strips, slices), dim3(32, 8), 0, stream, functor, out->data(), ops, g, scale, rowsPerSlice, assign, 0);
+    launchPdl(ew::gAddColumns<K, Functor>, dim3(strips, slices), dim3(32, 8), 0, stream, functor, out->data(), ops, g, scale, rowsPerSlice, assign, 0, (__nv_bfloat16*)nullptr);
   } else if(outS.d[0] == 1 && outS.d[1] == 1 && outS.d[2] == full.d[2] && outS.d[3] == full.d[3] && full.d[2] <= 65535 && (full.d[3] & 3) == 0 && ew::aligned16(out->memory()->data())
             && ew::aligned16(out->data()) && [&] {
                  for(int k = 0; k < K; ++k) {
@@ -494,7 +499,9 @@ void Add(Functor functor, float scale, Tensor out, Tensors... tensors) {
     int rowsPerSlice = (g.rows + slices - 1) / slices;
     slices = (g.rows + rowsPerSlice - 1) / rowsPerSlice;
     int assign = (slices == 1 && out->takeLazyZero()) ? 1 : 0;
-    launchPdl(ew::gAddColumns<K, Functor>, dim3(strips, slices, full.d[2]), dim3(32, 8), 0, stream, functor, out->data(), ops, g, scale, rowsPerSlice, assign, 1);
+    // (the attention context of a recurrent decoder step is the input of the next cell's product)
+    __nv_bfloat16* osh = assign ? shadow::produce(out) : nullptr;
+    launchPdl(ew::gAddColumns<K, Functor>, dim3(strips, slices, full.d[2]), dim3(32, 8), 0, stream, functor, out->data(), ops, g, scale, rowsPerSlice, assign, 1, osh);
   } else {
     // (3) generic reduction over the dims where out has extent 1
     ew::FullOperands<K> ops;

@@ -187,8 +187,10 @@ __global__ void __launch_bounds__(256) gAdamRemote(float* p, float* m, float* v,
     if(norm >= a.clipNorm)
       scale *= a.clipNorm / norm;
   }
-  const float t = (float)*steps;
-  const float denom1 = 1.f - powf(a.beta1, t), denom2 = 1.f - powf(a.beta2, t);
+  // the step number is only known on the device (it is counted under the shard lock): bias correction in double, as
+  // Adam::updateImpl computes it on the host (a float powf drifts from the singleton's results at large t)
+  const double t = (double)*steps;
+  const float denom1 = (float)(1.0 - pow((double)a.beta1, t)), denom2 = (float)(1.0 - pow((double)a.beta2, t));
   size_t n4 = n >> 2;
   for(size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (size_t)gridDim.x * blockDim.x) {
     float4 pp = reinterpret_cast<float4*>(p)[i];

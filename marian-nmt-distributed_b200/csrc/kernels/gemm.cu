@@ -208,6 +208,18 @@ __global__ void __launch_bounds__(256) gToBf16(__nv_bfloat16* __restrict__ dst, 
 // later main-stream product without any ordering.  Called from the side stream it steps back, converts,
 // and forks again (the side stream then waits for the conversion).
 void convertToBf16(__nv_bfloat16* dst, const float* src, size_t n) {
+  static const bool trace = std::getenv("MRN_SHADOW_TRACE") != nullptr;  // which operands still arrive without a bf16 copy
+  if(trace) {
+    static std::unordered_map<size_t, size_t>* hist = nullptr;
+    if(!hist) {
+      hist = new std::unordered_map<size_t, size_t>();
+      atexit([] {
+        for(auto& kv : *hist)
+          fprintf(stderr, "[shadow-trace] converted by the consumer: %zu elements x %zu times\n", kv.first, kv.second);
+      });
+    }
+    (*hist)[n]++;
+  }
   const bool side = device::onSide();
   if(side)
     device::returnFromSide();
@@ -1877,7 +1889,10 @@ __global__ void __launch_bounds__(192, GATE ? 2 : 1) gGemmBf16(const __grid_cons
   const int split = blockIdx.z - batch * a.splits;
   const int kb0 = split * a.kBlocksPerSplit;
   const int nkb = min(a.kBlocksPerSplit, a.kBlocks - kb0);
-  const bool doSums = !A_MN && a.colSum[0] != nullptr && blockIdx.y == 0;
+  // column sums of the A operand (bias gradients): the A tiles of a tile row pass through every CTA of that row, so
+  // the k-blocks are dealt out over the tile columns (k-block kb belongs to column kb mod gridDim.y) instead of
+  // leaving all of them to column 0 - those CTAs were the slowest of the grid (0.65 instead of 0.28 us per k-block)
+  const bool doSums = !A_MN && a.colSum[0] != nullptr;
 
   if(warp == 0 && lane == 0) {
 #pragma unroll
@@ -1966,25 +1981,27 @@ __global__ void __launch_bounds__(192, GATE ? 2 : 1) gGemmBf16(const __grid_cons
       for(int i = 0; i < nkb; ++i) {
         const int s = i % STAGES;
         mbarWait(fullBar + s, (uint32_t)(i / STAGES) & 1u);
-        const uint32_t* sa = reinterpret_cast<const uint32_t*>(smem + s * L::STAGE_BYTES);
-        float acc0 = 0.f, acc1 = 0.f;
-#pragma unroll
-        for(int r = 0; r < 32; ++r) {
-          const int R = rw + r;
-          const uint32_t w = sa[(R >> 3) * 256 + (R & 7) * 32 + ((((lane >> 2) ^ (R & 7)) << 2) | (lane & 3))];
-          acc0 += __uint_as_float(w << 16);
-          acc1 += __uint_as_float(w & 0xffff0000u);
-        }
         const int kAbs = kb0 + i;
-        const int grp = G == 1 ? 0 : kAbs / a.kBlocksGroup;
-        const int col = (G == 1 ? kAbs : kAbs - grp * a.kBlocksGroup) * BF_BLOCK_K + 2 * lane;
-        if(col < a.colSumLen)
-          atomicAdd(a.colSum[grp] + col, acc0);
-        if(col + 1 < a.colSumLen)
-          atomicAdd(a.colSum[grp] + col + 1, acc1);
+        if(kAbs % (int)gridDim.y == (int)blockIdx.y) {
+          const uint32_t* sa = reinterpret_cast<const uint32_t*>(smem + s * L::STAGE_BYTES);
+          float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll
+          for(int r = 0; r < 32; ++r) {
+            const int R = rw + r;
+            const uint32_t w = sa[(R >> 3) * 256 + (R & 7) * 32 + ((((lane >> 2) ^ (R & 7)) << 2) | (lane & 3))];
+            acc0 += __uint_as_float(w << 16);
+            acc1 += __uint_as_float(w & 0xffff0000u);
+          }
+          const int grp = G == 1 ? 0 : kAbs / a.kBlocksGroup;
+          const int col = (G == 1 ? kAbs : kAbs - grp * a.kBlocksGroup) * BF_BLOCK_K + 2 * lane;
+          if(col < a.colSumLen)
+            atomicAdd(a.colSum[grp] + col, acc0);
+          if(col + 1 < a.colSumLen)
+            atomicAdd(a.colSum[grp] + col + 1, acc1);
+        }
         __syncwarp();
         if(lane == 0)
-          mbarArrive(emptyBar + s);
+          mbarArrive(emptyBar + s);  // (every epilogue warp acknowledges every stage: emptyBar counts 5)
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
@@ -2029,9 +2046,9 @@ struct BfPersistSmem {
   static constexpr int TOTAL = BAR_OFFSET + (2 * STAGES + 4) * 8 + 16 + 1024;
 };
 
-// SUMS: two more warps follow the ring and, on the tiles of the first tile column, add the column sums of the
-// (K-major) A tiles into a.colSum[0] - the bias gradient, as in the one-tile kernels (there the idle epilogue
-// warps do it; here they are busy with the previous tile).  They acknowledge every stage (emptyBar counts 3).
+// SUMS: two more warps follow the ring and add the column sums of the (K-major) A tiles into a.colSum[0] - the bias
+// gradient, as in the one-tile kernels (there the idle epilogue warps do it; here they are busy with the previous
+// tile); the k-blocks of a tile row are dealt out over its tile columns.  They acknowledge every stage (emptyBar counts 3).
 // EPI = 8: two epilogue warps per TMEM lane quarter, each takes half of the tile's columns (the gated epilogue
 // evaluates swish'(H) for every element: with four warps it is 4x the main loop).
 template <int BN, int STAGES, bool A_MN, bool B_MN, bool GATE = false, bool SUMS = false, int EPI = 4>
@@ -2167,11 +2184,13 @@ __global__ void __launch_bounds__(64 + 32 * EPI + (SUMS ? 64 : 0), 1) gGemmBf16P
     const int rw = (warp - (2 + EPI)) * 64;
     uint32_t it = 0;
     for(int tile = blockIdx.x; tile < numTiles; tile += gridDim.x) {
-      const bool sumTile = tile < mTiles && a.colSum[0] != nullptr;  // tile column 0
+      // k-block i of a tile row is summed by the tile of column i mod nTiles (all columns stream the same A tiles)
+      const int tileCol = tile / mTiles;
+      const bool sums = a.colSum[0] != nullptr;
       for(int i = 0; i < nkb; ++i, ++it) {
         const int s = it % STAGES;
         mbarWait(fullBar + s, (it / STAGES) & 1u);
-        if(sumTile) {
+        if(sums && i % nTiles == tileCol) {
           // K-major SWIZZLE_128B bf16 tile: row R at (R / 8) * 1024 + (R % 8) * 128 bytes, 16-byte chunk c at c ^ (R % 8)
           const uint32_t* sa = reinterpret_cast<const uint32_t*>(smem + s * L::STAGE_BYTES);
           float acc0 = 0.f, acc1 = 0.f;
@@ -2283,10 +2302,21 @@ void launchBf16Maps(const TfMaps<G>& tm, const TcArgs& a, int batches) {
 
 template <bool A_MN, bool B_MN, int G, bool GATE = false>
 void launchBf16Tile(int BN, const TfMaps<G>& tm, const TcArgs& a, int batches) {
-  if(BN == 128)
+  if(BN == 128) {
     launchBf16Maps<128, 3, A_MN, B_MN, G, GATE>(tm, a, batches);
-  else
-    launchBf16Maps<64, 4, A_MN, B_MN, G, GATE>(tm, a, batches);
+    return;
+  }
+  // One tile row and a long K (the state products of a recurrent cell: 64 x 3072 x 1024 per time step, a chain of
+  // them): a few dozen CTAs, each a serial walk over 8..16 k-blocks - the duration is (k-blocks / ring depth) L2
+  // round trips.  An eight-stage ring (192 KB) has every k-block of such a CTA in flight at once.
+  if constexpr(G == 1 && !GATE && !A_MN) {
+    static const bool deepRing = std::getenv("MRN_GEMM_NO_DEEP_RING") == nullptr;
+    if(deepRing && a.M <= BLOCK_M && a.kBlocksPerSplit >= 6 && a.colSum[0] == nullptr) {
+      launchBf16Maps<64, 8, A_MN, B_MN, G, GATE>(tm, a, batches);
+      return;
+    }
+  }
+  launchBf16Maps<64, 4, A_MN, B_MN, G, GATE>(tm, a, batches);
 }
 
 // fp32 output [batches, rows, cols] as 32 x 32 tiles, 128-byte swizzle (rows of a tile = 128 bytes)

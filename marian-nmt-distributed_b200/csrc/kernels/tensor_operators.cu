@@ -886,7 +886,29 @@ __global__ void __launch_bounds__(256) gAttBack(float* __restrict__ gVa,
   float s = state[(size_t)bIdx * k + c];
   float v = va[c];
   float accState = 0.f, accVa = 0.f;
-  for(int j = bIdx; j < m; j += n) {
+  // five time steps per round: all fifteen loads are issued before the first use (one memory round trip per
+  // round instead of one per step - the walk is a serial chain of 50 otherwise); same summation order as before
+  constexpr int U = 5;
+  int j = bIdx;
+  for(; j + (U - 1) * n < m; j += U * n) {
+    float cx[U], a[U], g[U];
+#pragma unroll
+    for(int u = 0; u < U; ++u) {
+      const size_t at = (size_t)(j + u * n) * k + c;
+      cx[u] = context[at];
+      g[u] = gContext[at];
+      a[u] = adj[j + u * n];
+    }
+#pragma unroll
+    for(int u = 0; u < U; ++u) {
+      float t = tanhf(cx[u] + s);
+      float r = v * (1.f - t * t);
+      gContext[(size_t)(j + u * n) * k + c] = g[u] + r * a[u];
+      accState += r * a[u];
+      accVa += t * a[u];
+    }
+  }
+  for(; j < m; j += n) {
     float z = context[(size_t)j * k + c] + s;
     float t = tanhf(z);
     float r = v * (1.f - t * t);
@@ -1713,8 +1735,11 @@ struct ConcatTable {
 };
 
 // grid = (chunks, inputs); wide viewed as [rows][outWidth]
+__device__ __forceinline__ void concatShadow(__nv_bfloat16* sh, size_t at, float4 v) { shadow::store4(sh, 4 * at, v); }
+__device__ __forceinline__ void concatShadow(__nv_bfloat16*, size_t, float) {}  // (scalar path: the consumer converts)
+
 template <bool TO_WIDE, typename T>
-__global__ void __launch_bounds__(256) gCopyBlocks(T* __restrict__ wide, const __grid_constant__ ConcatTable tab, int rows, int outWidth) {
+__global__ void __launch_bounds__(256) gCopyBlocks(T* __restrict__ wide, const __grid_constant__ ConcatTable tab, int rows, int outWidth, __nv_bfloat16* __restrict__ wideShadow) {
   const int i = blockIdx.y;
   T* __restrict__ narrow = (T*)tab.narrow[i];
   const int width = tab.width[i], offset = tab.offset[i];
@@ -1723,21 +1748,25 @@ __global__ void __launch_bounds__(256) gCopyBlocks(T* __restrict__ wide, const _
     int r = (int)(w / width);
     int c = (int)(w - (long long)r * width);
     size_t wi = (size_t)r * outWidth + offset + c;
-    if(TO_WIDE)
-      wide[wi] = narrow[w];
-    else
+    if(TO_WIDE) {
+      const T v = narrow[w];
+      wide[wi] = v;
+      if(wideShadow)  // the concatenation feeds a product ([U | Ux] of a recurrent cell, the states of a layer): leave its bf16 copy
+        concatShadow(wideShadow, wi, v);
+    } else {
       narrow[w] = wide[wi];
+    }
   }
 }
 
 template <bool TO_WIDE>
-void copyBlocks(float* wide, const std::vector<float*>& narrow, const std::vector<int>& widths, int rows, int outWidth) {
+void copyBlocks(float* wide, const std::vector<float*>& narrow, const std::vector<int>& widths, int rows, int outWidth, __nv_bfloat16* wideShadow = nullptr) {
   auto st = cudaStreamOfEngine();
   size_t n = narrow.size();
   int offset = 0;
   for(size_t first = 0; first < n; first += kConcatMax) {
     size_t count = std::min<size_t>(kConcatMax, n - first);
-    if(count == 1) {  // the two-operand cases keep the plain kernel
+    if(count == 1 && !wideShadow) {  // a lone block keeps the plain kernel
       copyBlock<TO_WIDE>(wide, narrow[first], rows, widths[first], outWidth, offset);
       offset += widths[first];
       continue;
@@ -1762,10 +1791,11 @@ void copyBlocks(float* wide, const std::vector<float*>& narrow, const std::vecto
     // enough blocks over all inputs together to fill the machine, at least one per input
     int perInput = (int)std::max<size_t>(1, std::min<size_t>((items + 255) / 256, (size_t)(kNumSMs * 8 + count - 1) / count));
     dim3 grid(perInput, (unsigned)count);
+    ABORT_IF(wideShadow && !vec, "concatenation: a bf16 copy was promised but the blocks are not 16-byte aligned");
     if(vec)
-      gCopyBlocks<TO_WIDE, float4><<<grid, 256, 0, st>>>((float4*)wide, tab, rows, outWidth / 4);
+      gCopyBlocks<TO_WIDE, float4><<<grid, 256, 0, st>>>((float4*)wide, tab, rows, outWidth / 4, wideShadow);
     else
-      gCopyBlocks<TO_WIDE, float><<<grid, 256, 0, st>>>(wide, tab, rows, outWidth);
+      gCopyBlocks<TO_WIDE, float><<<grid, 256, 0, st>>>(wide, tab, rows, outWidth, nullptr);
     CUDA_LAUNCH_CHECK();
   }
 }
@@ -1781,11 +1811,17 @@ void Concatenate(Tensor out, const std::vector<Tensor>& inputs, int ax) {
   int outWidth = out->shape().elements() / rows;
   std::vector<float*> ptrs;
   std::vector<int> widths;
+  // every block 16-byte aligned: the copy can leave the bf16 copy a consuming product wants (BF16S mode)
+  bool vec = outWidth % 4 == 0 && (((uintptr_t)out->data()) & 15) == 0;
+  int offset = 0;
   for(auto in : inputs) {
     ptrs.push_back(in->data());
     widths.push_back(in->shape().elements() / rows);
+    vec = vec && widths.back() % 4 == 0 && offset % 4 == 0 && (((uintptr_t)ptrs.back()) & 15) == 0;
+    offset += widths.back();
   }
-  copyBlocks<true>(out->data(), ptrs, widths, rows, outWidth);
+  out->takeLazyZero();  // every element is written
+  copyBlocks<true>(out->data(), ptrs, widths, rows, outWidth, vec ? shadow::produce(out) : nullptr);
 }
 
 void Deconcatenate(std::vector<Tensor>& outputs, const Tensor in, int ax) {

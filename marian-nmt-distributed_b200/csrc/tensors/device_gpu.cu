@@ -27,10 +27,12 @@ struct ThreadCtx {
   bool hasUser{false};
   bool capturing{false};
   size_t lastKernelCount{0};
-  // side stream (see device.h)
-  cudaStream_t side{nullptr};
+  // side streams (see device.h): one per lane, so that the off-critical-path work of one chain does not queue
+  // behind that of another chain
+  cudaStream_t sides[kMaxLanes] = {nullptr, nullptr, nullptr, nullptr};
+  bool sideDirty[kMaxLanes] = {false, false, false, false};
+  int sideOf{0};  // lane whose side stream is selected while onSide
   bool onSide{false};
-  bool sideDirty{false};
   std::vector<cudaEvent_t> events;  // fork/join markers, reused every step
   size_t nextEvent{0};
   // lanes (see device.h)
@@ -63,7 +65,7 @@ cudaStream_t laneStream() {
 
 cudaStream_t stream() {
   if(tctx.onSide)
-    return tctx.side;
+    return tctx.sides[tctx.sideOf];
   return laneStream();
 }
 
@@ -95,15 +97,35 @@ __global__ void gFill(float* d, float v, size_t n) {
 }
 }  // namespace
 
+// One process drives ONE GPU (the multi-GPU groups are one process per GPU); a host thread may still be pointed at
+// another device, e.g. by a test harness.  Streams and events belong to the device they were created on: a device
+// change drops them (they are re-created lazily), including a stream injected by the harness.  The CUDA runtime's
+// current device can also be changed behind our back (torch.cuda.set_device): it is re-asserted when it differs.
 void setDevice(int deviceId) {
-  if(tctx.device == deviceId)
+  if(tctx.device == deviceId) {
+    int current = -1;
+    if(cudaGetDevice(&current) == cudaSuccess && current != deviceId)
+      CUDA_CHECK(cudaSetDevice(deviceId));
     return;
+  }
   CUDA_CHECK(cudaSetDevice(deviceId));
   tctx.device = deviceId;
   tctx.own = nullptr;  // streams are (re)created lazily for the new device
-  tctx.side = nullptr;
-  for(auto& l : tctx.lanes)
-    l = nullptr;
+  tctx.user = nullptr;
+  tctx.hasUser = false;
+  tctx.onSide = false;
+  for(int k = 0; k < kMaxLanes; ++k) {
+    tctx.sides[k] = nullptr;
+    tctx.sideDirty[k] = false;
+    tctx.lanes[k] = nullptr;
+  }
+  tctx.lanesOpen = false;
+  tctx.lane = 0;
+  tctx.laneOpenEvent = nullptr;
+  tctx.events.clear();  // events of the previous device are abandoned with its streams
+  tctx.nextEvent = 0;
+  tctx.marks.clear();
+  tctx.nextMark = 0;
 }
 int getDevice() {
   return tctx.device < 0 ? 0 : tctx.device;
@@ -263,15 +285,15 @@ void freeMarker(void* marker) {
 void forkSide() {
   if(tctx.onSide)
     return;
-  cudaStream_t main = mainStream();
-  if(!tctx.side)
-    CUDA_CHECK(cudaStreamCreateWithFlags(&tctx.side, cudaStreamNonBlocking));
-  (void)main;
+  const int k = tctx.lanesOpen ? tctx.lane : 0;
+  if(!tctx.sides[k])
+    CUDA_CHECK(cudaStreamCreateWithFlags(&tctx.sides[k], cudaStreamNonBlocking));
   cudaEvent_t e = nextMarker();
   CUDA_CHECK(cudaEventRecord(e, laneStream()));  // the side work follows what its lane has issued so far
-  CUDA_CHECK(cudaStreamWaitEvent(tctx.side, e, 0));
+  CUDA_CHECK(cudaStreamWaitEvent(tctx.sides[k], e, 0));
+  tctx.sideOf = k;
   tctx.onSide = true;
-  tctx.sideDirty = true;
+  tctx.sideDirty[k] = true;
 }
 void returnFromSide() {
   tctx.onSide = false;
@@ -281,12 +303,13 @@ bool onSide() {
 }
 void joinSide() {
   tctx.onSide = false;
-  if(tctx.sideDirty) {
-    cudaEvent_t e = nextMarker();
-    CUDA_CHECK(cudaEventRecord(e, tctx.side));
-    CUDA_CHECK(cudaStreamWaitEvent(mainStream(), e, 0));
-    tctx.sideDirty = false;
-  }
+  for(int k = 0; k < kMaxLanes; ++k)
+    if(tctx.sideDirty[k]) {
+      cudaEvent_t e = nextMarker();
+      CUDA_CHECK(cudaEventRecord(e, tctx.sides[k]));
+      CUDA_CHECK(cudaStreamWaitEvent(mainStream(), e, 0));
+      tctx.sideDirty[k] = false;
+    }
   tctx.nextEvent = 0;
 }
 

@@ -516,9 +516,15 @@ public:
     adam_ = std::dynamic_pointer_cast<Adam>(opt_);
     ABORT_IF(!adam_, "AsyncGraphGroup: the remote shard update is implemented for adam");
   }
+  // Peers push into / fetch from this rank's master block through their IPC mappings without any host
+  // involvement of this process: the harness must stop all ranks (AsyncTrainer.close(): barrier) before one of them
+  // is destroyed.  This rank's own queued kernels are drained here.
   ~AsyncGraphGroup() {
-    if(master_)
+    if(master_) {
+      device::setDevice((int)worker_.graph()->getDevice());
+      device::synchronize();
       device::freeDevice(master_);
+    }
   }
 
   // Builds the tape once (parameters initialised from the shared seed, identical on all ranks),

@@ -209,3 +209,11 @@ class AsyncTrainer:
 
     def cost(self):
         return self.trainer.cost()
+
+    def close(self):
+        """Peers write into this rank's master shard with no host involvement of this process: every rank drains
+        its own queue and all ranks meet before any master block is freed."""
+        self.trainer.cost()  # blocks until this rank's queued pushes / fetches have run
+        if self.nranks > 1 and self._ready:
+            self.dist.barrier(group=self.group)
+        self.trainer.close()

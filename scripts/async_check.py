@@ -43,5 +43,6 @@ wps = torch.tensor([2.0 * B * Ts * steps / dt], device="cuda"); dist.all_reduce(
 if rank == 0:
     print(json.dumps({"world": world, "ok": bool(flag.item()), "replicas_identical_after_fetch": same, "costs_rank0": costs,
                       "ms_per_step_rank0": 1000 * dt / steps, "words_per_s_all_ranks": float(wps.item()), "full_size": full}))
+a.close()  # drains this rank, barrier, then frees its master shard
 dist.destroy_process_group()
 sys.exit(0 if flag.item() else 1)

@@ -121,6 +121,55 @@ def test_prod_grouped_nt(cuda, oracle, mode, M, N, K, G, beta):
         close(run(oracle), exp, 1e-5, "oracle vs float64")
 
 
+@pytest.mark.parametrize("mode", [3, 4])
+@pytest.mark.parametrize("M,N,K,G,beta", [
+    (3200, 512, 2048, 1, 1.0),   # feed-forward dX (config B): 32 k-blocks dealt out over 8 tile columns
+    (3200, 512, 512, 3, 1.0),    # q/k/v dX, K-grouped: three bias gradients from one launch
+    (3200, 512, 512, 1, 0.0),
+    (300, 136, 192, 2, 1.0),     # ragged M / N: more tile columns than k-blocks per group
+    (64, 64, 64, 1, 0.0),        # one tile column
+    (3200, 1024, 1024, 1, 1.0),  # Transformer-big projection
+])
+def test_prod_grouped_nt_with_bias_gradients(cuda, mode, M, N, K, G, beta):
+    """The input-gradient products of the training step also deliver the bias gradients: column sums of their A
+    operands (the adjoints), taken from the A tiles inside the tensor-core kernel - every tile column sums its share
+    of the k-blocks.  Sums ACCUMULATE into their targets (gradients)."""
+    As = [rnd(10 + g, M, K) for g in range(G)]
+    Bs = [rnd(20 + g, N, K) for g in range(G)]
+    C0, S0 = rnd(3, M, N), [rnd(30 + g, 1, K) for g in range(G)]
+    exp = beta * C0.astype(np.float64) + sum(a.astype(np.float64) @ b.astype(np.float64).T for a, b in zip(As, Bs))
+    g = cuda.gemm(mode)
+    c = cuda.array(C0)
+    a = [cuda.array(x) for x in As]
+    b = [cuda.array(x) for x in Bs]
+    sums = [cuda.array(x) for x in S0]
+    cuda.call("mrn_prod_grouped_nt_sums", g.h, c.t(), cuda.tensor_list([x.t() for x in a]), cuda.tensor_list([x.t() for x in b]), G, beta,
+              cuda.tensor_list([x.t() for x in sums]))
+    cuda.synchronize()
+    close(c.numpy(), exp, TOL[mode], "product vs float64")
+    for k in range(G):
+        ref = S0[k].astype(np.float64) + As[k].astype(np.float64).sum(axis=0, keepdims=True)
+        # the sums are taken from the operand as the tensor core sees it (bf16 in mode 4, fp32 tiles in mode 3)
+        close(sums[k].numpy(), ref, 2e-2 if mode == 4 else 1e-4, "bias gradient %d" % k)
+
+
+@pytest.mark.parametrize("mode", [3, 4])
+@pytest.mark.parametrize("M,N,K", [(3200, 2048, 512), (3200, 4096, 1024), (304, 200, 96)])
+def test_prod_swish_grad_nt_with_bias_gradient(cuda, mode, M, N, K):
+    """Gated product (persistent kernel at full size) + column sums of dY by the column-sum warps: the k-blocks of a
+    tile row are dealt out over its tile columns."""
+    A, B, H, C0, S0 = rnd(1, M, K), rnd(2, N, K), 2.5 * rnd(3, M, N), rnd(4, M, N), rnd(5, 1, K)
+    h = H.astype(np.float64)
+    sg = 1.0 / (1.0 + np.exp(-h))
+    exp = C0 + (A.astype(np.float64) @ B.astype(np.float64).T) * (sg * (1.0 + h * (1.0 - sg)))
+    g = cuda.gemm(mode)
+    c, s = cuda.array(C0), cuda.array(S0)
+    cuda.call("mrn_prod_swish_grad_nt_sums", g.h, c.t(), cuda.array(A).t(), cuda.array(B).t(), cuda.array(H).t(), 1.0, s.t())
+    cuda.synchronize()
+    close(c.numpy(), exp, TOL[mode], "gated product vs float64")
+    close(s.numpy(), S0.astype(np.float64) + A.astype(np.float64).sum(axis=0, keepdims=True), 2e-2 if mode == 4 else 1e-4, "bias gradient")
+
+
 @pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("sa,sb,tA,tB", [
     ((64, 8, 50, 64), (64, 8, 50, 64), False, True),    # Q K^T  (config B)

@@ -46,3 +46,21 @@ def test_sync_exchanges_match_oracle(world, mode):
     for name in ("peer", "nccl"):
         assert res["exchanges"][name]["replicas_identical"], name
     assert res["exchanges"]["peer"]["used_peer_exchange"]
+
+
+@pytest.mark.parametrize("world", [2])
+def test_async_group_on_two_gpus(world):
+    """AsyncGraphGroup with N > 1: every rank trains without synchronising with the others - parameter
+    fetches and gradient pushes go through per-shard device locks over peer memory (csrc/kernels/exchange.cu), one rank
+    is deliberately slow.  scripts/async_check.py checks finite, falling costs and that after a final barrier + fetch
+    every rank holds the same parameters (= the master shards)."""
+    if _gpus() < world:
+        pytest.skip("needs %d GPUs" % world)
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr", "127.0.0.1",
+           "--master-port", str(_free_port()), os.path.join(ROOT, "scripts", "async_check.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, OMP_NUM_THREADS="4"))
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert lines, (r.returncode, r.stdout[-2000:], r.stderr[-2000:])
+    res = json.loads(lines[-1])
+    print(json.dumps(res))
+    assert r.returncode == 0 and res["ok"] and res["replicas_identical_after_fetch"], res
