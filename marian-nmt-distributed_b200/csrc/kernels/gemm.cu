@@ -2307,10 +2307,11 @@ void launchBf16Tile(int BN, const TfMaps<G>& tm, const TcArgs& a, int batches) {
     return;
   }
   // One tile row and a long K (the state products of a recurrent cell: 64 x 3072 x 1024 per time step, a chain of
-  // them): a few dozen CTAs, each a serial walk over 8..16 k-blocks - the duration is (k-blocks / ring depth) L2
-  // round trips.  An eight-stage ring (192 KB) has every k-block of such a CTA in flight at once.
+  // them): a few dozen CTAs, each a serial walk over 8..16 k-blocks.  An eight-stage ring (192 KB) has every k-block
+  // of such a CTA in flight at once - measured on config C: 22.46 ms per step against 22.20 with four stages (the
+  // 5 us of such a launch are prologue / first round trip / epilogue, not the ring), so it stays opt-in.
   if constexpr(G == 1 && !GATE && !A_MN) {
-    static const bool deepRing = std::getenv("MRN_GEMM_NO_DEEP_RING") == nullptr;
+    static const bool deepRing = std::getenv("MRN_GEMM_DEEP_RING") != nullptr;
     if(deepRing && a.M <= BLOCK_M && a.kBlocksPerSplit >= 6 && a.colSum[0] == nullptr) {
       launchBf16Maps<64, 8, A_MN, B_MN, G, GATE>(tm, a, batches);
       return;
@@ -2478,6 +2479,71 @@ void launchBf16NGroup(const NGroupMaps<NG>& tm, const TcArgs& a, const NGroupArg
   launchPdl(gGemmBf16NGroup<BN, STAGES, A_MN, NG>, grid, dim3(192), (size_t)L::TOTAL, cudaStreamOfEngine(), tm, a, ga);
 }
 
+// Column sums of a bf16 operand [rows, cols] (row-major), added into fp32 sums[cols]: the bias gradient that belongs to
+// an input-gradient product dX = adj W^T (column sums of adj).  Taking these sums from the A tiles inside the product
+// (the epilogue warps acknowledge every ring stage) costs the non-persistent kernel ~0.3 us per k-block - 10 us of the
+// 24 us of the 3200 x 512 x 2048 product (profiles/gemm_colsums_r02.md) - so for those products the sums are a pass of
+// their own over the bf16 copy, on the side stream: 13 MB, off the critical path.  blockDim (32, 8): a lane owns 8
+// adjacent columns (one 16-byte load per row), the 8 warps stride the rows of a slice, one atomic per column and block.
+__global__ void __launch_bounds__(256) gColumnSumsBf16(float* __restrict__ sums, const __nv_bfloat16* __restrict__ in, int rows, int cols, int rowsPerSlice) {
+  __shared__ float red[8][32][9];
+  const int c = (blockIdx.x * 32 + threadIdx.x) * 8;
+  const int r0 = blockIdx.y * rowsPerSlice;
+  const int r1 = min(rows, r0 + rowsPerSlice);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  if(c < cols) {
+    int row = r0 + threadIdx.y;
+    for(; row + 8 < r1; row += 16) {  // two rows in flight
+      const uint4 q0 = *reinterpret_cast<const uint4*>(in + (size_t)row * cols + c);
+      const uint4 q1 = *reinterpret_cast<const uint4*>(in + (size_t)(row + 8) * cols + c);
+      const uint32_t w0[4] = {q0.x, q0.y, q0.z, q0.w}, w1[4] = {q1.x, q1.y, q1.z, q1.w};
+#pragma unroll
+      for(int e = 0; e < 4; ++e) {
+        acc[2 * e] += __uint_as_float(w0[e] << 16) + __uint_as_float(w1[e] << 16);
+        acc[2 * e + 1] += __uint_as_float(w0[e] & 0xffff0000u) + __uint_as_float(w1[e] & 0xffff0000u);
+      }
+    }
+    for(; row < r1; row += 8) {
+      const uint4 q0 = *reinterpret_cast<const uint4*>(in + (size_t)row * cols + c);
+      const uint32_t w0[4] = {q0.x, q0.y, q0.z, q0.w};
+#pragma unroll
+      for(int e = 0; e < 4; ++e) {
+        acc[2 * e] += __uint_as_float(w0[e] << 16);
+        acc[2 * e + 1] += __uint_as_float(w0[e] & 0xffff0000u);
+      }
+    }
+  }
+#pragma unroll
+  for(int e = 0; e < 8; ++e)
+    red[threadIdx.y][threadIdx.x][e] = acc[e];
+  __syncthreads();
+  // 256 columns of the strip, one per thread
+  const int t = threadIdx.y * 32 + threadIdx.x;
+  const int col = blockIdx.x * 256 + t;
+  if(col < cols) {
+    float sum = 0.f;
+#pragma unroll
+    for(int y = 0; y < 8; ++y)
+      sum += red[y][t >> 3][t & 7];
+    atomicAdd(sums + col, sum);
+  }
+}
+
+// on the side stream (a bias gradient: nothing reads it before the optimizer); joins are the caller's (graph) business
+void columnSumsBf16OnSide(float* sums, const __nv_bfloat16* in, int rows, int cols) {
+  const bool side = device::onSide();
+  if(!side)
+    device::forkSide();
+  int strips = (cols + 255) / 256;
+  int slices = std::max(1, std::min((kNumSMs * 2 + strips - 1) / strips, (rows + 31) / 32));
+  int rowsPerSlice = (rows + slices - 1) / slices;
+  slices = (rows + rowsPerSlice - 1) / rowsPerSlice;
+  gColumnSumsBf16<<<dim3(strips, slices), dim3(32, 8), 0, cudaStreamOfEngine()>>>(sums, in, rows, cols, rowsPerSlice);
+  CUDA_LAUNCH_CHECK();
+  if(!side)
+    device::returnFromSide();
+}
+
 // Returns false when an operand cannot be described by a tensor map; the caller then takes the packed path.
 bool runBf16(GemmHandle h, const GemmProblem& p) {
   if(!tmaUsableBf16(p.A->rawData(), p.colsA, p.strideA) || !tmaUsableBf16(p.B->rawData(), p.colsB, p.strideB))
@@ -2574,9 +2640,16 @@ bool runBf16(GemmHandle h, const GemmProblem& p) {
   a.colSumLen = K;
   if(!p.colSums.empty()) {
     ABORT_IF(aMN || batched || (int)p.colSums.size() != G, "column sums need a K-major, unbatched A operand per group");
+    // 0: always inside the product (the A tiles stream through anyway); 1 (default): inside the persistent kernel (its two
+    // column-sum warps), a pass of their own for the one-tile kernels (see gColumnSumsBf16); 2: always a pass of their own
+    static const int policy = std::getenv("MRN_COLSUM_POLICY") ? std::atoi(std::getenv("MRN_COLSUM_POLICY")) : 1;
+    const bool outside = policy == 2 || (policy == 1 && !persistent);
     for(int g = 0; g < G; ++g) {
       ABORT_IF((int)p.colSums[g]->size() != K, "column-sum target has the wrong length");
-      a.colSum[g] = p.colSums[g]->data();
+      if(outside)
+        columnSumsBf16OnSide(p.colSums[g]->data(), g == 0 ? a16 : ensureShadow(h, p.moreA[g - 1]), M, K);
+      else
+        a.colSum[g] = p.colSums[g]->data();
     }
   }
   a.rowsPerBatchA = (batched && p.strideA) ? 1 : 0;

@@ -878,7 +878,9 @@ __global__ void __launch_bounds__(256) gAttBack(float* __restrict__ gVa,
                                                 const float* __restrict__ adj,
                                                 int m,
                                                 int k,
-                                                int n) {
+                                                int n,
+                                                int assignState,
+                                                __nv_bfloat16* __restrict__ gStateShadow) {
   int c = blockIdx.y * blockDim.x + threadIdx.x;
   int bIdx = blockIdx.x;
   if(c >= k)
@@ -917,7 +919,11 @@ __global__ void __launch_bounds__(256) gAttBack(float* __restrict__ gVa,
     accState += r * a;
     accVa += t * a;
   }
-  gState[(size_t)bIdx * k + c] += accState;
+  // a lazily-zero state adjoint (one attention per decoder step writes it) is assigned, and leaves the bf16 copy its two
+  // backward products read
+  const float gs = assignState ? accState : gState[(size_t)bIdx * k + c] + accState;
+  gState[(size_t)bIdx * k + c] = gs;
+  shadow::store1(gStateShadow, (size_t)bIdx * k + c, gs);
   atomicAdd(gVa + c, accVa);
 }
 
@@ -945,8 +951,12 @@ void AttBack(Tensor gVa, Tensor gContext, Tensor gState, Tensor va, Tensor conte
   int k = context->shape()[-1];
   int n = context->shape()[-2];
   dim3 grid(n, (k + 255) / 256);
+  // (the kernel covers every element of gState exactly when the state has one row per sentence: no beam dimension)
+  const bool whole = (size_t)gState->size() == (size_t)n * k;
+  const int assignState = (whole && gState->takeLazyZero()) ? 1 : 0;
+  __nv_bfloat16* gss = assignState ? shadow::produce(gState) : nullptr;
   gAttBack<<<grid, 256, 0, cudaStreamOfEngine()>>>(
-      gVa->data(), gContext->data(), gState->data(), va->data(), context->data(), state->data(), adj->data(), m, k, n);
+      gVa->data(), gContext->data(), gState->data(), va->data(), context->data(), state->data(), adj->data(), m, k, n, assignState, gss);
   CUDA_LAUNCH_CHECK();
 }
 
@@ -1088,7 +1098,8 @@ __global__ void __launch_bounds__(256) gGRUFastBackwardVec(float* __restrict__ o
                                                            int rowsPerBlock,
                                                            int assignMask,
                                                            bool final,
-                                                           __nv_bfloat16* __restrict__ shadowSU) {
+                                                           __nv_bfloat16* __restrict__ shadowSU,
+                                                           __nv_bfloat16* __restrict__ shadowXW) {
   __shared__ float4 red[3][8][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int i = (blockIdx.x * 32 + lane) * 4;
@@ -1154,6 +1165,9 @@ __global__ void __launch_bounds__(256) gGRUFastBackwardVec(float* __restrict__ o
         *(float4*)(outXW + rg) = make_float4(oXr.x + dR[0], oXr.y + dR[1], oXr.z + dR[2], oXr.w + dR[3]);
         *(float4*)(outXW + rg + cols) = make_float4(oXz.x + dZ[0], oXz.y + dZ[1], oXz.z + dZ[2], oXz.w + dZ[3]);
         *(float4*)(outXW + rg + 2 * cols) = make_float4(oXx.x + dX[0], oXx.y + dX[1], oXx.z + dX[2], oXx.w + dX[3]);
+        shadow::store4(shadowXW, rg, make_float4(dR[0], dR[1], dR[2], dR[3]));  // (only handed in for an assigned adjoint)
+        shadow::store4(shadowXW, rg + cols, make_float4(dZ[0], dZ[1], dZ[2], dZ[3]));
+        shadow::store4(shadowXW, rg + 2 * cols, make_float4(dX[0], dX[1], dX[2], dX[3]));
       }
       if(outSU) {
         *(float4*)(outSU + rg) = make_float4(oUr.x + dR[0], oUr.y + dR[1], oUr.z + dR[2], oUr.w + dR[3]);
@@ -1385,13 +1399,14 @@ void GRUFastBackward(std::vector<Tensor> outputs, std::vector<Tensor> inputs, Te
         out[k] = outputs[k]->rawData();
       }
     __nv_bfloat16* shadowSU = (out[2] && (assignMask & 4)) ? shadow::produce(outputs[2]) : nullptr;
+    __nv_bfloat16* shadowXW = (out[1] && (assignMask & 2)) ? shadow::produce(outputs[1]) : nullptr;  // per-step input projections (conditional cell)
     int strips = (cols / 4 + 31) / 32;
     // rows of a strip are split over blocks until the grid has about two blocks per SM, 8 rows (one per warp) at least
     int splits = std::max(1, std::min((kNumSMs * 2 + strips - 1) / strips, (rows + 7) / 8));
     int rowsPerBlock = ((rows + splits - 1) / splits + 7) / 8 * 8;
     splits = (rows + rowsPerBlock - 1) / rowsPerBlock;
     gGRUFastBackwardVec<<<dim3(strips, splits), 256, 0, cudaStreamOfEngine()>>>(out[0], out[1], out[2], dataOrNull(outputs, 3), inputs[0]->data(), inputs[1]->data(), inputs[2]->data(),
-                                                                                 inputs[3]->data(), dataOrNull(inputs, 4), adj->data(), rows, cols, rowsPerBlock, assignMask, final, shadowSU);
+                                                                                 inputs[3]->data(), dataOrNull(inputs, 4), adj->data(), rows, cols, rowsPerBlock, assignMask, final, shadowSU, shadowXW);
     CUDA_LAUNCH_CHECK();
     return;
   }

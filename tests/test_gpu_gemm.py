@@ -121,7 +121,7 @@ def test_prod_grouped_nt(cuda, oracle, mode, M, N, K, G, beta):
         close(run(oracle), exp, 1e-5, "oracle vs float64")
 
 
-@pytest.mark.parametrize("mode", [3, 4])
+@pytest.mark.parametrize("mode", [4, 3])
 @pytest.mark.parametrize("M,N,K,G,beta", [
     (3200, 512, 2048, 1, 1.0),   # feed-forward dX (config B): 32 k-blocks dealt out over 8 tile columns
     (3200, 512, 512, 3, 1.0),    # q/k/v dX, K-grouped: three bias gradients from one launch
@@ -150,7 +150,8 @@ def test_prod_grouped_nt_with_bias_gradients(cuda, mode, M, N, K, G, beta):
     for k in range(G):
         ref = S0[k].astype(np.float64) + As[k].astype(np.float64).sum(axis=0, keepdims=True)
         # the sums are taken from the operand as the tensor core sees it (bf16 in mode 4, fp32 tiles in mode 3)
-        close(sums[k].numpy(), ref, 2e-2 if mode == 4 else 1e-4, "bias gradient %d" % k)
+        # (fp32 accumulation of M values through atomics: 5e-4 of the largest sum)
+        close(sums[k].numpy(), ref, 2e-2 if mode == 4 else 5e-4, "bias gradient %d" % k)
 
 
 @pytest.mark.parametrize("mode", [3, 4])
@@ -167,7 +168,7 @@ def test_prod_swish_grad_nt_with_bias_gradient(cuda, mode, M, N, K):
     cuda.call("mrn_prod_swish_grad_nt_sums", g.h, c.t(), cuda.array(A).t(), cuda.array(B).t(), cuda.array(H).t(), 1.0, s.t())
     cuda.synchronize()
     close(c.numpy(), exp, TOL[mode], "gated product vs float64")
-    close(s.numpy(), S0.astype(np.float64) + A.astype(np.float64).sum(axis=0, keepdims=True), 2e-2 if mode == 4 else 1e-4, "bias gradient")
+    close(s.numpy(), S0.astype(np.float64) + A.astype(np.float64).sum(axis=0, keepdims=True), 2e-2 if mode == 4 else 5e-4, "bias gradient")
 
 
 @pytest.mark.parametrize("mode", [0, 1, 2, 3, 4])
