@@ -149,7 +149,8 @@ int mrn_prod_grouped_nt_sums(void* g, mrn_tensor C, const mrn_tensor* As, const 
   return guarded([&] {
     gemmInvalidateCache((GemmHandle)g);
     ProdGroupedNT((GemmHandle)g, wrap(C), wrapAll(As, n), wrapAll(Bs, n), beta, wrapAll(col_sums, n));
-    device::joinSide();  // the sums may have been taken by a pass of their own on the side stream
+    ProdFlushColumnSums((GemmHandle)g);  // sums the product queued: a pass of their own on the side stream
+    device::joinSide();
   });
 }
 int mrn_prod_swish_grad_nt_sums(void* g, mrn_tensor C, mrn_tensor A, mrn_tensor B, mrn_tensor H, float beta, mrn_tensor col_sum) {
@@ -157,6 +158,7 @@ int mrn_prod_swish_grad_nt_sums(void* g, mrn_tensor C, mrn_tensor A, mrn_tensor 
     gemmInvalidateCache((GemmHandle)g);
     ABORT_IF(!ProdSwishGradFusable((GemmHandle)g, wrap(C), wrap(A), wrap(B), wrap(H)), "mrn_prod_swish_grad_nt_sums: needs a tensor-core mode and 16-byte aligned operands");
     ProdSwishGradNT((GemmHandle)g, wrap(C), wrap(A), wrap(B), wrap(H), beta, wrap(col_sum));
+    ProdFlushColumnSums((GemmHandle)g);
     device::joinSide();
   });
 }

@@ -30,6 +30,7 @@
 #include "common/keywords.h"
 #include "graph/backend.h"
 #include "graph/node.h"
+#include "kernels/tensor_operators.h"
 #include "layers/param_initializers.h"
 #include "tensors/allocator.h"
 #include "tensors/staging.h"
@@ -338,6 +339,7 @@ public:
       device::openLanes();
     while(!nodesBackward_.empty()) {
       if(swept++ == splitAfter && backwardSplitHook_) {
+        ProdFlushColumnSums(backend_->getGemmHandle());
         if(lanes)
           device::closeLanes();
         device::joinSide();  // weight gradients issued so far are part of "before the split"
@@ -398,6 +400,7 @@ public:
           timing_["(release children)"] += std::chrono::duration<double>(std::chrono::steady_clock::now() - tz).count();
       }
     }
+    ProdFlushColumnSums(backend_->getGemmHandle());  // (a bias without gradient closure: nothing may stay queued)
     if(lanes)
       device::closeLanes();
     if(nodeTiming()) {

@@ -260,6 +260,9 @@ struct AffineNodeOp : public NaryNodeOp {
                 ABORT_IF(adj_->memory()->fp32Skipped, "affine: bias gradient needs the fp32 adjoint, but only its bf16 copy was written");
                 Add(_1, child(2)->grad(), adj_);
               }
+              // column sums the input-gradient product queued instead of taking them from its own tiles: issued here,
+              // behind this node's weight-gradient product on the side stream
+              ProdFlushColumnSums(getBackend()->getGemmHandle());
             }))};
   }
   const std::string type() { return "affine"; }

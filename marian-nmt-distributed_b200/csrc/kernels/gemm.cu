@@ -90,6 +90,13 @@ struct GemmContext {
   __nv_bfloat16* paramShadow{nullptr};
   size_t paramShadowElems{0};
   bool paramFresh{false};                         // the whole copy matches the fp32 arena
+  // bias-gradient column sums queued by products (ProdFlushColumnSums)
+  struct PendingSums {
+    float* sums;
+    const __nv_bfloat16* in;
+    int rows, cols;
+  };
+  std::vector<PendingSums> pendingSums;
   std::unordered_map<const void*, void*> paramConverted;  // tensors converted one by one since the last invalidate (-> lane mark behind the conversion)
 
   typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -270,6 +277,7 @@ float* fp32Target(const Tensor& t, const __nv_bfloat16* producedShadow) {
 }  // namespace shadow
 
 void gemmInvalidateCache(GemmHandle h) {
+  ABORT_IF(!h->pendingSums.empty(), "bias-gradient sums still queued when the operand copies are dropped (ProdFlushColumnSums)");
   h->cache.clear();
   h->cur = 0;
   h->off = 0;
@@ -2544,6 +2552,16 @@ void columnSumsBf16OnSide(float* sums, const __nv_bfloat16* in, int rows, int co
     device::returnFromSide();
 }
 
+}  // namespace
+void ProdFlushColumnSums(GemmHandle h) {
+  if(!h || h->pendingSums.empty())
+    return;
+  device::setDevice(h->device);
+  for(auto& ps : h->pendingSums)
+    columnSumsBf16OnSide(ps.sums, ps.in, ps.rows, ps.cols);
+  h->pendingSums.clear();
+}
+namespace {
 // Returns false when an operand cannot be described by a tensor map; the caller then takes the packed path.
 bool runBf16(GemmHandle h, const GemmProblem& p) {
   if(!tmaUsableBf16(p.A->rawData(), p.colsA, p.strideA) || !tmaUsableBf16(p.B->rawData(), p.colsB, p.strideB))
@@ -2647,7 +2665,7 @@ bool runBf16(GemmHandle h, const GemmProblem& p) {
     for(int g = 0; g < G; ++g) {
       ABORT_IF((int)p.colSums[g]->size() != K, "column-sum target has the wrong length");
       if(outside)
-        columnSumsBf16OnSide(p.colSums[g]->data(), g == 0 ? a16 : ensureShadow(h, p.moreA[g - 1]), M, K);
+        h->pendingSums.push_back({p.colSums[g]->data(), g == 0 ? a16 : ensureShadow(h, p.moreA[g - 1]), M, K});
       else
         a.colSum[g] = p.colSums[g]->data();
     }

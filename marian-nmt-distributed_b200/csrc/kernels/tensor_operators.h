@@ -100,6 +100,11 @@ void ProdGroupedNT(GemmHandle handle, Tensor C, const std::vector<Tensor>& As, c
 // an attention block, their weight gradients).  false = not applicable here, nothing was done (issue them one by one).
 bool ProdSharedA(GemmHandle handle, const std::vector<Tensor>& Cs, const Tensor A, const std::vector<Tensor>& Bs, const std::vector<Tensor>& biases, bool transA, float beta);
 bool ProdColumnSumsFusable(GemmHandle handle, const Tensor A);
+// Column sums (bias gradients) that a product did not take from its own A tiles are queued by the product and issued
+// here, on the side stream, as passes over the bf16 copies of those operands (kernels/gemm.cu: gColumnSumsBf16).  The
+// graph calls this from the bias-gradient closure of the node - i.e. BEHIND the node's weight-gradient product on the
+// side stream - and once more at the end of the backward sweep.
+void ProdFlushColumnSums(GemmHandle handle);
 // C = beta C + (A B^T) o swish'(H): "affine after swish" backward in the product's epilogue (tf32 tensor-core path only)
 bool ProdSwishGradFusable(GemmHandle handle, const Tensor C, const Tensor A, const Tensor B, const Tensor H);
 void ProdSwishGradNT(GemmHandle handle, Tensor C, const Tensor A, const Tensor B, const Tensor H, float beta = 0, Tensor colSum = nullptr);

@@ -390,6 +390,7 @@ void Prod(GemmHandle, Tensor C, const Tensor A, const Tensor B, bool transA, boo
 bool ProdSwishGradFusable(GemmHandle, const Tensor, const Tensor, const Tensor, const Tensor) {
   return false;
 }
+void ProdFlushColumnSums(GemmHandle) {}
 bool ProdColumnSumsFusable(GemmHandle, const Tensor) {
   return false;
 }
