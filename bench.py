@@ -326,7 +326,7 @@ def main():
     lib.call("mrn_set_device", local_rank)
     # engine work, NCCL collectives and the timing events all live on ONE side stream
     # (the legacy default stream cannot be graph-captured)
-    side = torch.cuda.Stream()
+    side = torch.cuda.Stream(priority=-1)  # the engine's chain stream: above its side streams (tensors/device_gpu.cu)
     torch.cuda.set_stream(side)
     lib.set_stream(side.cuda_stream)
 

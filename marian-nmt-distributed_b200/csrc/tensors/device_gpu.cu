@@ -78,13 +78,38 @@ cudaEvent_t nextMarker() {
   return tctx.events[tctx.nextEvent++];
 }
 
+// Stream priorities: the main stream and the lanes carry the dependency chain of the step, the side streams carry
+// work nothing waits for before the optimizer (weight / bias gradients, the early exchange phase).  When CTAs of both
+// are pending the block scheduler takes the high-priority ones first, so a weight-gradient product that happens to
+// run next to an input-gradient product of the chain no longer takes half of the machine from it.  (Kernel nodes of
+// a captured graph keep the priority of the stream they were captured on.)  MRN_NO_STREAM_PRIORITY=1: all equal.
+bool usePriorities() {
+  static const bool on = std::getenv("MRN_NO_STREAM_PRIORITY") == nullptr;
+  return on;
+}
+cudaStream_t newStream(bool chain) {
+  cudaStream_t st = nullptr;
+  int least = 0, greatest = 0;
+  if(usePriorities() && cudaDeviceGetStreamPriorityRange(&least, &greatest) == cudaSuccess && least != greatest) {
+    int pr = greatest;
+    if(!chain)
+      pr = least;
+    else if(tctx.hasUser)  // lanes next to a stream injected by the harness: its priority
+      cudaStreamGetPriority(tctx.user, &pr);
+    CUDA_CHECK(cudaStreamCreateWithPriority(&st, cudaStreamNonBlocking, pr));
+  } else {
+    CUDA_CHECK(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  }
+  return st;
+}
+
 cudaStream_t mainStream() {
   if(tctx.hasUser)
     return tctx.user;
   if(!tctx.own) {
     if(tctx.device < 0)
       setDevice(0);
-    CUDA_CHECK(cudaStreamCreateWithFlags(&tctx.own, cudaStreamNonBlocking));
+    tctx.own = newStream(true);
   }
   return tctx.own;
 }
@@ -287,7 +312,7 @@ void forkSide() {
     return;
   const int k = tctx.lanesOpen ? tctx.lane : 0;
   if(!tctx.sides[k])
-    CUDA_CHECK(cudaStreamCreateWithFlags(&tctx.sides[k], cudaStreamNonBlocking));
+    tctx.sides[k] = newStream(false);
   cudaEvent_t e = nextMarker();
   CUDA_CHECK(cudaEventRecord(e, laneStream()));  // the side work follows what its lane has issued so far
   CUDA_CHECK(cudaStreamWaitEvent(tctx.sides[k], e, 0));
@@ -354,7 +379,7 @@ void selectLane(int lane) {
   }
   if(!tctx.laneUsed[lane]) {
     if(!tctx.lanes[lane])
-      CUDA_CHECK(cudaStreamCreateWithFlags(&tctx.lanes[lane], cudaStreamNonBlocking));
+      tctx.lanes[lane] = newStream(true);
     CUDA_CHECK(cudaStreamWaitEvent(tctx.lanes[lane], tctx.laneOpenEvent, 0));
     tctx.laneUsed[lane] = true;
   }

@@ -86,7 +86,7 @@ class SyncTrainer:
             # NCCL and CUDA-event timing are then ordered by the stream with no host
             # synchronisation.  (The legacy default stream cannot be graph-captured.)
             if torch.cuda.current_stream().cuda_stream == 0:
-                self.stream = torch.cuda.Stream(device)
+                self.stream = torch.cuda.Stream(device, priority=-1)  # chain stream above the engine's side streams
                 torch.cuda.set_stream(self.stream)
             lib.set_stream(torch.cuda.current_stream().cuda_stream)
         self.trainer = lib.trainer(options, device=device, rank=rank, nranks=nranks)

@@ -94,8 +94,9 @@ def test_encoder_lanes_equal_single_stream(cuda, enc_type, mode):
         assert np.allclose(two["costs"], one["costs"], rtol=2e-5), (replay, two["costs"], one["costs"])
         if not replay:
             close(two["logits"], one["logits"], 1e-6, "logits")
+            gscale = max(float(np.abs(g).max()) for g in one["grads"].values())
             for name, g in one["grads"].items():  # bias gradients are sums of atomics: order noise only
-                scale = max(float(np.abs(g).max()), 1e-6)
+                scale = max(float(np.abs(g).max()), 1e-2 * gscale)  # (analytically zero gradients, e.g. the attention bias, are rounding noise)
                 assert float(np.abs(two["grads"][name] - g).max()) <= 2e-5 * scale, name
         diff = np.abs(two["params"] - one["params"])
         assert np.mean(diff > 2e-5) < 0.01 and np.median(diff) < 2e-6
