@@ -259,7 +259,10 @@ public:
       }
       v->allocate();
       v->init();
-      if(sideEnabled && !lanes && v->concurrent() && !v->children().empty()) {
+      // (not in an inference pass: values are freed as soon as their last consumer has been ISSUED - a value read only
+      // by side-stream nodes, e.g. the per-beam view of the encoder context under the key / value projections of a
+      // decoding step, would be recycled by the main stream while the side stream still reads it)
+      if(sideEnabled && !lanes && !inferenceOnly_ && v->concurrent() && !v->children().empty()) {
         // inputs were produced on the main stream before this point (or on the side stream
         // itself, which is in order): fork, run, hand back
         device::forkSide();
