@@ -134,12 +134,15 @@ def test_copy_task_text_round_trip_on_gpu(cuda, tmp_path):
     from test_translator import write_copy_task
 
     lines = write_copy_task(tmp_path)
+    # learn-rate 0.002 x 200 epochs: the copy model converges (CPU oracle: 17 of 17 lines and a cost of 0.003 for seeds
+    # 3..6), so the count below does not move with the rounding-level differences between runs (atomics) and arithmetic
+    # modes.  (60 epochs at 0.01, the CPU test's setting, leave a half-trained model: 12 - 16 of 17 over those seeds.)
     opts = ("type=transformer;dim-vocabs=16,16;dim-emb=32;transformer-heads=4;transformer-dim-ffn=64;enc-depth=1;dec-depth=1;tied-embeddings-all=true;"
-            "workspace=128;graph-replay=true;gemm-mode=4;seed=3;learn-rate=0.01;clip-norm=1;label-smoothing=0")
+            "workspace=128;graph-replay=true;gemm-mode=4;seed=3;learn-rate=0.002;clip-norm=1;label-smoothing=0")
     t = cuda.trainer(opts)
     vs = str(tmp_path / "vocab.src.yml")
     t.open_corpus(str(tmp_path / "train.src"), str(tmp_path / "train.trg"), vs, vs, "mini-batch=32;maxi-batch=4;seed=1")
-    for _ in range(60):
+    for _ in range(200):
         while t.next_corpus_batch():
             t.compute_gradients()
             t.update()
@@ -147,10 +150,7 @@ def test_copy_task_text_round_trip_on_gpu(cuda, tmp_path):
     out = tmp_path / "test.out"
     assert t.translate_file(tmp_path / "test.src", vs, vs, out, "beam-size=3;normalize=0.6;mini-batch=5;maxi-batch=2") == 17
     got = out.read_text().splitlines()
-    # 60 epochs at learn-rate 0.01 leave a good but not converged copy model: the exact-arithmetic CPU oracle gets 12 - 16
-    # of these 17 lines right over seeds 3..6 (16 with this seed), i.e. the count moves with rounding-level changes of the
-    # training trajectory (bf16 products here).  Chance level is 0 of 17.
-    assert sum(g == e for g, e in zip(got, lines[:17])) >= 12, list(zip(got, lines[:17]))
+    assert sum(g == e for g, e in zip(got, lines[:17])) >= 15, list(zip(got, lines[:17]))
     # training continues after decoding (graph plans, inference flag and staging are restored)
     while t.next_corpus_batch():
         t.compute_gradients()
