@@ -335,23 +335,35 @@ def test_transformer_step_against_independent_torch_model(oracle):
 
 
 # ------------------------------------------------------------------ whole s2s (RNN + attention) step
-def marian_s2s_torch(params, src, smask, trg, tmask, enc_depth, dec_depth):
-    """Marian's deep GRU encoder-decoder with Bahdanau attention (src/models/s2s.h, src/rnn/{rnn,cells,attention}.h,
+def marian_s2s_torch(params, src, smask, trg, tmask, enc_depth, dec_depth, cell_type="gru"):
+    """Marian's deep RNN encoder-decoder with Bahdanau attention (src/models/s2s.h, src/rnn/{rnn,cells,attention}.h,
     enc-type bidirectional) re-stated in PyTorch from the parameter names and the papers' formulas alone:
       GRU:            r, z = sigmoid(x W_{r,z} + s U_{r,z} + b_{r,z});  h~ = tanh(x W_x + (s U_x) r + b_x)
                       ("final" cells of the conditional GRU: h~ = tanh(x W_x + (s U_x + b_x) r));  s' = (1 - z) h~ + z s
+      LSTM:           f, i, o = sigmoid(.), g = tanh(.) of x W + h U + b (column blocks f | i | g | o);  c' = f c + i g;
+                      h' = o tanh(c');  a padded step keeps c (h is recomputed from the kept c with this step's o)
       encoder:        two full-depth stacks, one reading left-to-right, one right-to-left (padded steps keep the state),
                       top outputs concatenated
-      decoder start:  tanh(W mean_t(context) + b), the same vector for every layer
-      cGRU:           s1 = GRU1(y_{t-1}, s);  c_t = sum_j softmax_j(v . tanh(W_c ctx_j + W_s s1 + b)) ctx_j;  s' = GRU2(c_t, s1)
+      decoder start:  tanh(W mean_t(context) + b), the same vector for every layer (output and cell state)
+      conditional:    s1 = CELL1(y_{t-1}, s);  c_t = sum_j softmax_j(v . tanh(W_c ctx_j + W_s s1 + b)) ctx_j;  s' = CELL2(c_t, s1)
       readout:        logits = W2 tanh(W0 y + b0 + W1 s_top + b1 + W2 c + b2) + b
-    """
+    A state is the pair (output, cell); GRUs carry no cell."""
     P = params
     Ts, B = src.shape
     Tt = trg.shape[0]
+    lstm = cell_type == "lstm"
 
-    def cell(name, x_proj, s, mask=None, final=False):
+    def cell(name, x_proj, state, mask=None, final=False):
+        s, c = state
         D = s.shape[-1]
+        if lstm:
+            g = s @ P[name + "_U"] + P[name + "_b"]
+            if x_proj is not None:
+                g = g + x_proj
+            c2 = torch.sigmoid(g[..., :D]) * c + torch.sigmoid(g[..., D:2 * D]) * torch.tanh(g[..., 2 * D:3 * D])
+            if mask is not None:
+                c2 = mask * c2 + (1 - mask) * c
+            return torch.sigmoid(g[..., 3 * D:]) * torch.tanh(c2), c2
         U = torch.cat([P[name + "_U"], P[name + "_Ux"]], -1)
         b = torch.cat([P[name + "_b"], P[name + "_bx"]], -1)
         su = s @ U
@@ -363,25 +375,25 @@ def marian_s2s_torch(params, src, smask, trg, tmask, enc_depth, dec_depth):
         else:
             h = torch.tanh(xp[..., 2 * D:] + su[..., 2 * D:] * r + b[..., 2 * D:])
         out = (1 - z) * h + z * s
-        return out if mask is None else mask * out + (1 - mask) * s
+        return (out if mask is None else mask * out + (1 - mask) * s), None
 
     def in_proj(name, x):
-        return x @ torch.cat([P[name + "_W"], P[name + "_Wx"]], -1)
+        return x @ (P[name + "_W"] if lstm else torch.cat([P[name + "_W"], P[name + "_Wx"]], -1))
 
     def layer(name, xs, start, mask, backward=False):
         xp = in_proj(name, xs)  # all time steps at once
         T = xs.shape[0]
-        s = start
+        state = start
         outs = [None] * T
         for t in (range(T - 1, -1, -1) if backward else range(T)):
-            s = cell(name, xp[t], s, None if mask is None else mask[t])
-            outs[t] = s
+            state = cell(name, xp[t], state, None if mask is None else mask[t])
+            outs[t] = state[0]
         return torch.stack(outs, 0)
 
-    D = P["encoder_bi_Ux"].shape[0]
+    D = P["encoder_bi_U"].shape[0]
     x = P["encoder_Wemb"][src]  # [Ts, B, E]
     m = smask.unsqueeze(-1)     # [Ts, B, 1]
-    zeros = torch.zeros(B, D)
+    zeros = (torch.zeros(B, D), torch.zeros(B, D))
 
     def stack(base, backward):
         h = x
@@ -400,19 +412,19 @@ def marian_s2s_torch(params, src, smask, trg, tmask, enc_depth, dec_depth):
 
     mapped_ctx = ctx @ P["decoder_Wc_att"] + P["decoder_b_att"]  # [Ts, B, 2D]
     xp1 = in_proj("decoder_cell1", y)
-    s = start
+    state = (start, start)
     tops, contexts = [], []
     for t in range(Tt):
-        s1 = cell("decoder_cell1", xp1[t], s)
-        score = (torch.tanh(mapped_ctx + (s1 @ P["decoder_W_comb_att"]).unsqueeze(0)) @ P["decoder_U_att"]).squeeze(-1)  # [Ts, B]
+        s1 = cell("decoder_cell1", xp1[t], state)
+        score = (torch.tanh(mapped_ctx + (s1[0] @ P["decoder_W_comb_att"]).unsqueeze(0)) @ P["decoder_U_att"]).squeeze(-1)  # [Ts, B]
         e = torch.softmax(score.masked_fill(smask == 0, -math.inf), 0)
         c = (e.unsqueeze(-1) * ctx).sum(0)  # [B, 2D]
-        s = cell("decoder_cell2", in_proj("decoder_cell2", c), s1, final=True)
-        tops.append(s)
+        state = cell("decoder_cell2", in_proj("decoder_cell2", c), s1, final=True)
+        tops.append(state[0])
         contexts.append(c)
     h = torch.stack(tops, 0)
     for l in range(2, dec_depth + 1):
-        h = layer("decoder_l%d_cell1" % l, h, start, None)
+        h = layer("decoder_l%d_cell1" % l, h, (start, start), None)
     c_all = torch.stack(contexts, 0)
     hid = torch.tanh(y @ P["decoder_ff_logit_l1_W0"] + P["decoder_ff_logit_l1_b0"] + h @ P["decoder_ff_logit_l1_W1"] + P["decoder_ff_logit_l1_b1"]
                      + c_all @ P["decoder_ff_logit_l1_W2"] + P["decoder_ff_logit_l1_b2"])
@@ -421,13 +433,14 @@ def marian_s2s_torch(params, src, smask, trg, tmask, enc_depth, dec_depth):
     return (ce * tmask).sum(0).mean(), logits
 
 
-@pytest.mark.parametrize("enc_depth,dec_depth", [(1, 1), (2, 3)])
-def test_s2s_step_against_independent_torch_model(oracle, enc_depth, dec_depth):
+@pytest.mark.parametrize("cell_type,enc_depth,dec_depth", [("gru", 1, 1), ("gru", 2, 3), ("lstm", 1, 1), ("lstm", 2, 2)])
+def test_s2s_step_against_independent_torch_model(oracle, cell_type, enc_depth, dec_depth):
     """The RNN + attention half of the hot path: loss, logits and ALL parameter gradients of one training step of the
     deep GRU s2s model (the architecture of BASELINE.json configs[0] / configs[2]) against float64 PyTorch autograd on
-    an implementation written from the formulas - pins the graph-level backward of GRU cells (incl. the "final" cell),
+    an implementation written from the formulas - pins the graph-level backward of GRU (incl. the "final" cell) and LSTM cells,
     masked bidirectional stacks, the attention cell input, the multi-input readout and the parameter naming."""
-    opts = ("type=s2s;dim-vocabs=60,70;dim-emb=16;dim-rnn=24;enc-depth=%d;dec-depth=%d;workspace=64;clip-norm=0" % (enc_depth, dec_depth))
+    opts = ("type=s2s;dim-vocabs=60,70;dim-emb=16;dim-rnn=24;enc-depth=%d;dec-depth=%d;enc-cell=%s;dec-cell=%s;workspace=64;clip-norm=0"
+            % (enc_depth, dec_depth, cell_type, cell_type))
     rs = np.random.RandomState(1)
     B, Ts, Tt = 4, 6, 5
     src, trg = rs.randint(2, 60, size=(Ts, B)), rs.randint(2, 70, size=(Tt, B))
@@ -444,7 +457,7 @@ def test_s2s_step_against_independent_torch_model(oracle, enc_depth, dec_depth):
     cost = t.cost()
     names = t.param_names()
     params = {n: torch.tensor(t.get_tensor(n).reshape(s).astype(np.float64), requires_grad=True) for n, s in names}
-    C, L = marian_s2s_torch(params, torch.tensor(src), torch.tensor(sm.astype(np.float64)), torch.tensor(trg), torch.tensor(tm.astype(np.float64)), enc_depth, dec_depth)
+    C, L = marian_s2s_torch(params, torch.tensor(src), torch.tensor(sm.astype(np.float64)), torch.tensor(trg), torch.tensor(tm.astype(np.float64)), enc_depth, dec_depth, cell_type)
     assert abs(cost - C.item()) <= 2e-6 * abs(C.item()), (cost, C.item())
     close(t.get_tensor("logits"), L.detach().numpy().reshape(-1), 5e-6, "logits")
     grads = torch.autograd.grad(C, [params[n] for n, _ in names], allow_unused=True)
