@@ -51,8 +51,16 @@ VOCAB = 32000
 MODE_NAMES = {0: "f32", 1: "bf16-packed", 2: "bf16x3", 3: "tf32", 4: "bf16"}
 
 
+_SHAPE_OVERRIDE = {"batch": None, "len": None}  # --batch / --len: another batch shape of the same model (e.g. one rank's share of config E)
+
+
 def model_config(name, pkg, gemm_mode):
     """BASELINE.json configs -> (trainer options, sentences, length, label)."""
+    o, b, l, label = _model_config(name, pkg, gemm_mode)
+    return o, _SHAPE_OVERRIDE["batch"] or b, _SHAPE_OVERRIDE["len"] or l, label
+
+
+def _model_config(name, pkg, gemm_mode):
     if name == "transformer-base":
         return pkg.transformer_base_options(gemm_mode=gemm_mode), 64, 50, "Transformer-base (6+6, d=512, 8 heads, ffn 2048, V=32000)"
     if name == "transformer-big":
@@ -287,6 +295,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="transformer-base", choices=["transformer-base", "transformer-big", "s2s-deep-gru"])
+    ap.add_argument("--batch", type=int, default=None, help="sentences per batch instead of the config's own (a rank's share of a global batch)")
+    ap.add_argument("--len", type=int, default=None, help="tokens per sentence instead of the config's own")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
     ap.add_argument("--padded", action="store_true", help="sentence lengths uniform in [T/2, T] (mask path) instead of dense batches")
     ap.add_argument("--gemm-mode", type=int, default=int(os.environ.get("MRN_BENCH_GEMM_MODE", "4")),
@@ -300,6 +310,7 @@ def main():
     ap.add_argument("--traffic-child", action="store_true", help=argparse.SUPPRESS)
     ap.add_argument("--no-traffic", action="store_true", help="skip the ncu pass that measures the GEMM family's DRAM traffic")
     args = ap.parse_args()
+    _SHAPE_OVERRIDE["batch"], _SHAPE_OVERRIDE["len"] = args.batch, args.len
 
     if args.oracle_child:
         oracle_child(args.oracle_child)
@@ -528,6 +539,10 @@ def measure_gemm_traffic(args, launches_per_step):
     log = os.path.join(tempfile.gettempdir(), "mrn_gemm_traffic_%d.csv" % os.getpid())
     cmd = [ncu, "--metrics", "dram__bytes_read.sum,dram__bytes_write.sum", "--clock-control", "none", "-k", "regex:gGemm", "--csv", "--log-file", log,
            sys.executable, os.path.abspath(__file__), "--traffic-child", "--model", args.model, "--gemm-mode", str(args.gemm_mode)]
+    if args.batch:
+        cmd += ["--batch", str(args.batch)]
+    if args.len:
+        cmd += ["--len", str(args.len)]
     try:
         r = subprocess.run(cmd, capture_output=True, text=True, timeout=float(os.environ.get("MRN_TRAFFIC_BUDGET_S", "150")))
     except subprocess.TimeoutExpired:
